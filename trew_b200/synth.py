@@ -1,0 +1,288 @@
+"""Synthetic read generators for parity tests and benchmarks (no real data is available offline).
+
+Two families:
+
+* ``adversarial_*``: small mixed sets built to hit every routing branch of the reference's
+  buffer_task / buffer_task_pair / buffer_task_long: perfect and noisy
+  repeats of every unit length, half-repeat reads, reverse complements, indels, N runs, lowercase,
+  and read lengths that flip each guard (n < 2*MIN, n < 4*MIN, n < 4*MAX).
+* ``config_*``: the BASELINE.json workload shapes (fixed-length 150 bp short reads with ~1 %
+  TTAGGG-repeat reads, paired fragments, HiFi-like long reads), vectorised with numpy so that tens
+  of millions of reads can be generated on the GPU box in seconds.
+"""
+from __future__ import annotations
+
+import random
+from typing import List, Tuple
+
+import numpy as np
+
+BASES = b"ACGT"
+COMP = bytes.maketrans(b"ACGTacgtN", b"TGCAtgcaN")
+KNOWN_UNITS = [b"TTAGGG", b"TTTAGGG", b"TTAGG", b"TG", b"A", b"TTGGGG", b"TTAGGC", b"CCCTAA", b"AATGG"]
+
+
+def revcomp(s: bytes) -> bytes:
+    return s.translate(COMP)[::-1]
+
+
+def _rand_seq(rng: random.Random, n: int) -> bytes:
+    return bytes(rng.choice(BASES) for _ in range(n))
+
+
+def _repeat(rng: random.Random, unit: bytes, n: int) -> bytes:
+    phase = rng.randrange(len(unit))
+    reps = (n + phase) // len(unit) + 2
+    return (unit * reps)[phase:phase + n]
+
+
+def _mutate(rng: random.Random, s: bytes, sub: float, indel: bool) -> bytes:
+    b = bytearray(s)
+    if sub > 0:
+        for i in range(len(b)):
+            if rng.random() < sub:
+                b[i] = rng.choice(BASES)
+    if indel and len(b) > 10:
+        p = rng.randrange(2, len(b) - 2)
+        if rng.random() < 0.5:
+            del b[p]
+            b.append(rng.choice(BASES))
+        else:
+            b.insert(p, rng.choice(BASES))
+            b.pop()
+    return bytes(b)
+
+
+def _decorate(rng: random.Random, s: bytes) -> bytes:
+    b = bytearray(s)
+    if rng.random() < 0.3:  # 2 % N in 30 % of reads
+        for i in range(len(b)):
+            if rng.random() < 0.02:
+                b[i] = ord("N")
+    if rng.random() < 0.1:
+        b = bytearray(bytes(b).lower())
+    return bytes(b)
+
+
+def _unit(rng: random.Random, max_unit: int) -> bytes:
+    if rng.random() < 0.4:
+        return rng.choice(KNOWN_UNITS)
+    return _rand_seq(rng, rng.randint(1, max_unit))
+
+
+def adversarial_read(rng: random.Random, n: int, max_unit: int = 32) -> bytes:
+    """One read of length n drawn from the Appendix-C mixture."""
+    sub = rng.choice([0, 0, 0.01, 0.03, 0.08, 0.15, 0.30])
+    kind = rng.random()
+    if kind < 0.15:
+        s = _rand_seq(rng, n)
+    elif kind < 0.50:
+        s = _mutate(rng, _repeat(rng, _unit(rng, max_unit), n), sub, rng.random() < 0.2)
+    elif kind < 0.62:  # repeat in the left half only
+        h = n // 2
+        s = _mutate(rng, _repeat(rng, _unit(rng, max_unit), h), sub, False) + _rand_seq(rng, n - h)
+    elif kind < 0.74:  # right half only
+        h = n // 2
+        s = _rand_seq(rng, h) + _mutate(rng, _repeat(rng, _unit(rng, max_unit), n - h), sub, False)
+    elif kind < 0.86:  # different units in the two halves
+        h = n // 2
+        s = _mutate(rng, _repeat(rng, _unit(rng, max_unit), h), sub, False) + \
+            _mutate(rng, _repeat(rng, _unit(rng, max_unit), n - h), sub, False)
+    else:  # repeat occupying a random stretch
+        a = rng.randrange(0, max(1, n // 2))
+        b = rng.randrange(a, n)
+        s = _rand_seq(rng, a) + _repeat(rng, _unit(rng, max_unit), b - a) + _rand_seq(rng, n - b)
+    if rng.random() < 0.5:
+        s = revcomp(s)
+    return _decorate(rng, s)
+
+
+SHORT_LENGTHS = [9, 12, 25, 40, 60, 75, 100, 150, 151, 246, 300]
+
+
+def adversarial_short(seed: int, count: int, max_unit: int = 32, lengths=None) -> List[bytes]:
+    rng = random.Random(seed)
+    lengths = lengths or SHORT_LENGTHS
+    return [adversarial_read(rng, rng.choice(lengths), max_unit) for _ in range(count)]
+
+
+def adversarial_pairs(seed: int, count: int, read_len: int = 150, max_unit: int = 32,
+                      truncate_mate2: float = 0.0) -> Tuple[List[bytes], List[bytes]]:
+    """Mates cut from one fragment of length L..3L whose repeat covers a random prefix / suffix /
+    middle / everything.  Mate 2 is the reverse complement of the fragment's tail."""
+    rng = random.Random(seed)
+    r1: List[bytes] = []
+    r2: List[bytes] = []
+    for _ in range(count):
+        flen = rng.randint(read_len, 3 * read_len)
+        kind = rng.random()
+        unit = _unit(rng, max_unit)
+        sub = rng.choice([0, 0, 0.01, 0.03, 0.08])
+        if kind < 0.2:
+            frag = _rand_seq(rng, flen)
+        elif kind < 0.5:
+            frag = _mutate(rng, _repeat(rng, unit, flen), sub, False)
+        else:
+            a = rng.randrange(0, flen)
+            b = rng.randrange(a, flen + 1)
+            if rng.random() < 0.5:
+                a = 0
+            if rng.random() < 0.5:
+                b = flen
+            frag = _rand_seq(rng, a) + _mutate(rng, _repeat(rng, unit, b - a), sub, False) + _rand_seq(rng, flen - b)
+        if rng.random() < 0.5:
+            frag = revcomp(frag)
+        m1 = frag[:read_len]
+        m2 = revcomp(frag[-read_len:])
+        if rng.random() < truncate_mate2:
+            m2 = m2[:rng.randint(max(1, read_len // 3), read_len)]
+        r1.append(_decorate(rng, m1))
+        r2.append(_decorate(rng, m2))
+    return r1, r2
+
+
+def adversarial_long(seed: int, count: int, min_len: int = 140, max_len: int = 2500,
+                     max_unit: int = 32) -> List[bytes]:
+    """Long reads with a repeat at the 5' end, 3' end, both ends, a unit switch or a strand switch."""
+    rng = random.Random(seed)
+    out: List[bytes] = []
+    for _ in range(count):
+        n = rng.randint(min_len, max_len)
+        unit = _unit(rng, max_unit)
+        sub = rng.choice([0, 0, 0.001, 0.01, 0.03])
+        kind = rng.random()
+        a = rng.randint(0, n)
+        if kind < 0.15:
+            s = _rand_seq(rng, n)
+        elif kind < 0.35:
+            s = _mutate(rng, _repeat(rng, unit, a), sub, False) + _rand_seq(rng, n - a)
+        elif kind < 0.55:
+            s = _rand_seq(rng, n - a) + _mutate(rng, _repeat(rng, unit, a), sub, False)
+        elif kind < 0.70:
+            a = rng.randint(0, n // 2)
+            b = rng.randint(0, n // 2)
+            s = _mutate(rng, _repeat(rng, unit, a), sub, False) + _rand_seq(rng, n - a - b) + \
+                _mutate(rng, _repeat(rng, unit, b), sub, False)
+        elif kind < 0.80:
+            s = _mutate(rng, _repeat(rng, unit, n), sub, False)
+        elif kind < 0.90:  # unit switch
+            s = _repeat(rng, unit, a) + _repeat(rng, _unit(rng, max_unit), n - a)
+        else:  # strand switch
+            s = _repeat(rng, unit, a) + revcomp(_repeat(rng, unit, n - a))
+        if rng.random() < 0.5:
+            s = revcomp(s)
+        out.append(_decorate(rng, s))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json workload shapes, vectorised.
+# ---------------------------------------------------------------------------------------------
+
+_ASCII = np.frombuffer(b"ACGT", dtype=np.uint8)
+_COMP_IDX = np.array([3, 2, 1, 0], dtype=np.uint8)  # A<->T, C<->G on indices into "ACGT"
+
+
+def _telomeric_rows(rng: np.random.Generator, n: int, length: int, sub: float) -> np.ndarray:
+    """n rows of (TTAGGG)^m at uniform random phase, 50 % reverse-complemented, per-base substitutions."""
+    unit = np.array([3, 3, 0, 2, 2, 2], dtype=np.uint8)  # TTAGGG as indices into "ACGT"
+    phase = rng.integers(0, 6, size=(n, 1))
+    idx = (np.arange(length)[None, :] + phase) % 6
+    rows = unit[idx]
+    rc = rng.random(n) < 0.5
+    rows[rc] = _COMP_IDX[rows[rc]][:, ::-1]
+    if sub > 0:
+        m = rng.random((n, length)) < sub
+        rows[m] = rng.integers(0, 4, size=int(m.sum()), dtype=np.uint8)
+    return rows
+
+
+def config_short(seed: int, n_reads: int, length: int = 150, telomeric: float = 0.01,
+                 half_telomeric: float = 0.002, n_rate: float = 0.001, sub: float = 0.01) -> np.ndarray:
+    """BASELINE.json configs[1] shape (SURVEY.md 8(d) cfg 2): n_reads x length ASCII matrix.
+    99 % i.i.d. uniform ACGT; ``telomeric`` (TTAGGG)^n reads; ``half_telomeric`` reads telomeric in one
+    half only; ``n_rate`` of all bases replaced by N."""
+    rng = np.random.default_rng(seed)
+    idx = rng.integers(0, 4, size=(n_reads, length), dtype=np.uint8)
+    kind = rng.random(n_reads)
+    tel = np.nonzero(kind < telomeric)[0]
+    if tel.size:
+        idx[tel] = _telomeric_rows(rng, tel.size, length, sub)
+    half = np.nonzero((kind >= telomeric) & (kind < telomeric + half_telomeric))[0]
+    if half.size:
+        rows = _telomeric_rows(rng, half.size, length, sub)
+        left = rng.random(half.size) < 0.5
+        h = length // 2
+        keep = idx[half]
+        keep[left, :h] = rows[left, :h]
+        keep[~left, h:] = rows[~left, h:]
+        idx[half] = keep
+    out = _ASCII[idx]
+    if n_rate > 0:
+        cnt = rng.binomial(n_reads * length, n_rate)
+        pos = rng.integers(0, n_reads * length, size=cnt)
+        out.reshape(-1)[pos] = ord("N")
+    return out
+
+
+def config_pairs(seed: int, n_pairs: int, length: int = 150, telomeric: float = 0.01,
+                 sub: float = 0.01) -> Tuple[np.ndarray, np.ndarray]:
+    """BASELINE.json configs[2] shape: mate 1 and mate 2 from one fragment; telomeric fragments give two
+    repeat mates (mate 2 reverse-complemented), the rest are independent random mates."""
+    rng = np.random.default_rng(seed)
+    i1 = rng.integers(0, 4, size=(n_pairs, length), dtype=np.uint8)
+    i2 = rng.integers(0, 4, size=(n_pairs, length), dtype=np.uint8)
+    tel = np.nonzero(rng.random(n_pairs) < telomeric)[0]
+    if tel.size:
+        frag = _telomeric_rows(rng, tel.size, 2 * length + 50, 0.0)
+        m1 = frag[:, :length].copy()
+        m2 = _COMP_IDX[frag[:, -length:]][:, ::-1].copy()
+        for m in (m1, m2):
+            s = rng.random(m.shape) < sub
+            m[s] = rng.integers(0, 4, size=int(s.sum()), dtype=np.uint8)
+        i1[tel] = m1
+        i2[tel] = m2
+    return _ASCII[i1], _ASCII[i2]
+
+
+def config_long(seed: int, n_reads: int, mean_len: int = 15000, sd_len: int = 2000, min_len: int = 1000,
+                telomeric: float = 0.02, err: float = 0.001) -> List[np.ndarray]:
+    """BASELINE.json configs[3] shape: HiFi-like reads, ``telomeric`` of them carry (TTAGGG)^n on the
+    first or last 0.5-5 kb."""
+    rng = np.random.default_rng(seed)
+    lens = np.maximum(min_len, rng.normal(mean_len, sd_len, size=n_reads).astype(np.int64))
+    out: List[np.ndarray] = []
+    for n in lens:
+        n = int(n)
+        idx = rng.integers(0, 4, size=n, dtype=np.uint8)
+        if rng.random() < telomeric:
+            tl = int(min(n, rng.integers(500, 5001)))
+            row = _telomeric_rows(rng, 1, tl, err)[0]
+            if rng.random() < 0.5:
+                idx[:tl] = row
+            else:
+                idx[n - tl:] = row
+        out.append(_ASCII[idx])
+    return out
+
+
+def fastq_bytes(reads, name_prefix: str = "r") -> bytes:
+    """Minimal 4-line FASTQ for a list of byte strings / uint8 rows."""
+    parts = []
+    for i, r in enumerate(reads):
+        s = bytes(r) if not isinstance(r, (bytes, bytearray)) else r
+        parts.append(b"@%s%d\n%s\n+\n%s\n" % (name_prefix.encode(), i, s, b"I" * len(s)))
+    return b"".join(parts)
+
+
+def fastq_matrix_bytes(mat: np.ndarray) -> bytes:
+    """Vectorised FASTQ for a fixed-length ASCII matrix (header '@r', quality 'I' * L)."""
+    n, L = mat.shape
+    rec = np.empty((n, 3 + L + 1 + 2 + L + 1), dtype=np.uint8)
+    rec[:, 0:3] = np.frombuffer(b"@r\n", dtype=np.uint8)
+    rec[:, 3:3 + L] = mat
+    rec[:, 3 + L] = 10
+    rec[:, 4 + L:6 + L] = np.frombuffer(b"+\n", dtype=np.uint8)
+    rec[:, 6 + L:6 + 2 * L] = ord("I")
+    rec[:, 6 + 2 * L] = 10
+    return rec.tobytes()
