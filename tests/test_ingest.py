@@ -1,0 +1,87 @@
+"""FASTQ / FASTQ.gz reader semantics (read_fastq_thread & co, src/kmer.cpp:987-1213).  CPU only."""
+import gzip
+import os
+
+import pytest
+
+from trew_b200 import api, synth
+
+REF_TEST = "/root/reference/test"
+
+
+def py_records(data: bytes):
+    """Every 4k+2-th '\\n'-terminated line; a last unterminated line is never seen."""
+    lines = data.split(b"\n")[:-1]
+    return lines[1::4]
+
+
+def write(tmp_path, name, data, gz=False):
+    p = os.path.join(tmp_path, name)
+    with (gzip.open(p, "wb") if gz else open(p, "wb")) as f:
+        f.write(data)
+    return p
+
+
+@pytest.mark.parametrize("gz", [False, True])
+@pytest.mark.parametrize("chunk", [64, 1000, 0])
+def test_short_records(tmp_path, gz, chunk):
+    reads = synth.adversarial_short(5, 300)
+    data = synth.fastq_bytes(reads) + b"@tail\nACGT"  # unterminated sequence line: ignored
+    p = write(tmp_path, "a.fastq" + (".gz" if gz else ""), data, gz)
+    rc, msg, r1, _ = api.ingest_records(api.MODE_SHORT, p, chunk_bytes=chunk)
+    assert rc == 0, msg
+    assert r1 == py_records(data) == reads
+
+
+def test_crlf_counts_toward_length(tmp_path):
+    data = b"@r\r\nACGTACGTAC\r\n+\r\nIIIIIIIIII\r\n"
+    p = write(tmp_path, "a.fastq", data)
+    rc, _, r1, _ = api.ingest_records(api.MODE_SHORT, p)
+    assert rc == 0 and r1 == [b"ACGTACGTAC\r"]
+
+
+def test_short_rejects_long_reads(tmp_path):
+    p = write(tmp_path, "a.fastq", synth.fastq_bytes([b"A" * 1000, b"C" * 1001]))
+    rc, msg, _, _ = api.ingest_records(api.MODE_SHORT, p)
+    assert rc == 4 and msg == "This mode is designed for short-read sequencing. Please use 'trew long'."
+    p = write(tmp_path, "b.fastq", synth.fastq_bytes([b"A" * 1000]))
+    assert api.ingest_records(api.MODE_SHORT, p)[0] == 0
+
+
+def test_long_drops_short_reads(tmp_path):
+    reads = [b"A" * 149, b"C" * 150, b"G" * 5000, b"T" * 10]
+    p = write(tmp_path, "a.fastq", synth.fastq_bytes(reads))
+    rc, _, r1, _ = api.ingest_records(api.MODE_LONG, p, slice_length=150, chunk_bytes=512)
+    assert rc == 0 and r1 == [reads[1], reads[2]]
+
+
+@pytest.mark.parametrize("chunk", [100, 777, 0])
+def test_pairs_index_wise(tmp_path, chunk):
+    r1, r2 = synth.adversarial_pairs(3, 200, read_len=100, truncate_mate2=0.3)
+    p1 = write(tmp_path, "a.fastq", synth.fastq_bytes(r1, "longer_header_name_"))
+    p2 = write(tmp_path, "b.fastq.gz", synth.fastq_bytes(r2), gz=True)
+    rc, msg, o1, o2 = api.ingest_records(api.MODE_PAIR, p1, p2, chunk_bytes=chunk)
+    assert rc == 0, msg
+    assert o1 == r1 and o2 == r2
+
+
+def test_pairs_mismatch_is_an_error(tmp_path):
+    r1, r2 = synth.adversarial_pairs(4, 20)
+    p1 = write(tmp_path, "a.fastq", synth.fastq_bytes(r1))
+    p2 = write(tmp_path, "b.fastq", synth.fastq_bytes(r2[:-1]))
+    rc, msg, _, _ = api.ingest_records(api.MODE_PAIR, p1, p2)
+    assert rc == 6 and msg == "Error: Mismatched record counts between files (num1: 80, num2: 76)."
+
+
+def test_missing_file():
+    rc, msg, _, _ = api.ingest_records(api.MODE_SHORT, "/nonexistent/x.fastq")
+    assert rc == 5 and msg == "File open failed"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_TEST), reason="reference fixtures only exist in the build container")
+@pytest.mark.parametrize("name,mode", [("test.fastq", 0), ("test.fastq.gz", 0), ("test_long.fastq", 2), ("test_long.fastq.gz", 2)])
+def test_bundled_fixtures(name, mode):
+    p = os.path.join(REF_TEST, name)
+    data = (gzip.open(p) if name.endswith(".gz") else open(p, "rb")).read()
+    rc, _, r1, _ = api.ingest_records(mode, p, chunk_bytes=4096)
+    assert rc == 0 and r1 == py_records(data)

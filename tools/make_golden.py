@@ -128,6 +128,17 @@ def cli_cases():
         m1, m2 = synth.config_pairs(25, 800, telomeric=0.05)
         run("pair_5_32", ["short", "5", "32", "--paired_end", "--fq1", "a.fastq", "--fq2", "b.fastq", "-t", "2"],
             {"a.fastq": synth.fastq_bytes(m1), "b.fastq": synth.fastq_bytes(m2)})
+        # few distinct units, well separated counts: no ties at any top-4 cut of get_score_map, so the
+        # reference's >Putative_TRM is a function of its input here
+        rng = random.Random(27)
+        tf = []
+        for unit, n_fwd, n_rev in [(b"TTAGGG", 90, 7), (b"TTTAGGG", 11, 40), (b"TTAGGC", 25, 3), (b"TGTGGG", 5, 14)]:
+            for i in range(n_fwd + n_rev):
+                s = synth._repeat(rng, unit, 150)
+                tf.append(s if i < n_fwd else synth.revcomp(s))
+        tf += [synth._rand_seq(rng, 150) for _ in range(200)]
+        rng.shuffle(tf)
+        run("short_tie_free", ["short", "5", "32", "a.fastq", "-t", "2"], {"a.fastq": synth.fastq_bytes(tf)})
         lr = synth.config_long(26, 40, mean_len=3000, sd_len=800, min_len=200, telomeric=0.4, err=0.002)
         run("long_5_32", ["long", "5", "32", "a.fastq", "-t", "2"], {"a.fastq": synth.fastq_bytes(lr)})
     dump(cases, "cli_cases.json.gz")

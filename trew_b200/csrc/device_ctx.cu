@@ -1,0 +1,559 @@
+// C ABI implementation: device context, pinned staging ring, asynchronous submit, table export.
+//
+// Stands in for the consumer side of the reference's queue (buffer_task* workers started by
+// process_kmer*, src/kmer.cpp:1278-1325) and for the per-worker result maps that process_output sums
+// (src/kmer.cpp:1486-1515).  One context = one GPU.  Per staging slot: pinned host buffer, device
+// buffer, stream and completion event, so packing of batch i+1 on the host overlaps the H2D copy and
+// the kernels of batch i (double/triple buffering with cudaMemcpyAsync).
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "host_internal.h"
+#include "scan_kernels.cuh"
+
+using namespace trew;
+
+namespace {
+
+struct SlotRes {
+    void* h_buf = nullptr;      // pinned
+    void* d_buf = nullptr;
+    unsigned int* d_survivors = nullptr;
+    unsigned int* d_counters = nullptr;  // [0] n_survivors [1] work counter
+    unsigned char* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    size_t survivors_cap = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_done = nullptr;
+    bool in_flight = false;
+};
+
+}  // namespace
+
+struct trew_resident {
+    void* d_buf = nullptr;
+    DevBatch batch{};
+    uint32_t n_reads = 0, n_units = 0, max_read_len = 0;
+    uint64_t bases = 0;
+    unsigned int* d_survivors = nullptr;
+    unsigned int* d_counters = nullptr;
+    unsigned char* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+
+struct trew_ctx {
+    trew_config cfg{};
+    int sm_count = 0;
+    DevCfg dcfg{};
+    size_t n_slots = 0;
+    unsigned int* d_error = nullptr;
+    unsigned short* d_thr = nullptr;
+    unsigned long long* d_total_surv = nullptr;
+    std::vector<SlotRes> slots;
+    size_t next_slot = 0;
+    size_t staging_bytes = 0;
+    cudaStream_t main_stream = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    // export buffers
+    unsigned int* d_meta = nullptr; unsigned long long* d_seq = nullptr; unsigned long long* d_count = nullptr;
+    unsigned int* d_n = nullptr;
+    uint64_t n_export = 0;
+    std::vector<trew_entry> entries;
+    trew_stats stats{};
+    Pool* pool = nullptr;
+    std::string err;
+    std::vector<ReadRef> reads_tmp;
+};
+
+namespace {
+
+int fail(trew_ctx* c, int status, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    if (c) c->err = buf;
+    return status;
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(ctx, TREW_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+// smallest M with (double)M / (double)T >= B, exactly as the reference forms the ratio (src/kmer.cpp:2223-2224)
+void build_thr(double B, std::vector<unsigned short>& thr) {
+    thr.assign(kThrTableSize, 0xFFFF);
+    for (int T = 1; T < kThrTableSize; T++) {
+        int lo = 0, hi = T;  // ratio is monotone in M; M = T gives 1.0 >= B
+        while (lo < hi) {
+            int mid = (lo + hi) / 2;
+            if ((double)mid / (double)T >= B) hi = mid; else lo = mid + 1;
+        }
+        thr[T] = (unsigned short)lo;
+    }
+}
+
+int run_cap_for(const trew_config& cfg, uint32_t max_read_len) {
+    uint32_t w = max_read_len;
+    if (cfg.mode == TREW_MODE_LONG) w = std::min<uint32_t>(max_read_len, 2u * (uint32_t)cfg.slice_length);
+    w = std::min<uint32_t>(w, (uint32_t)kMaxWindow);
+    return (int)((w + 2 + 7) & ~7u);
+}
+
+size_t scratch_need(const trew_ctx* ctx, uint32_t max_read_len, unsigned int* stride) {
+    unsigned int st = 16;
+    if (ctx->cfg.mode == TREW_MODE_LONG) st = 2u * (max_read_len / (uint32_t)ctx->cfg.slice_length + 2u);
+    st = (st + 15u) & ~15u;
+    *stride = st;
+    return (size_t)st * (size_t)exact_warps_total(ctx->sm_count);
+}
+
+int launch_scan(trew_ctx* ctx, const DevBatch& b, uint32_t n_units, uint32_t max_read_len, unsigned int* d_survivors,
+                unsigned int* d_counters, unsigned char** d_scratch, size_t* scratch_bytes, cudaStream_t st) {
+    unsigned int stride;
+    size_t need = scratch_need(ctx, max_read_len, &stride);
+    if (need > *scratch_bytes) {
+        if (*d_scratch) { CK(cudaStreamSynchronize(st)); CK(cudaFree(*d_scratch)); *d_scratch = nullptr; }
+        CK(cudaMalloc((void**)d_scratch, need));
+        *scratch_bytes = need;
+    }
+    CK(cudaMemsetAsync(d_counters, 0, 2 * sizeof(unsigned int), st));
+    launch_filter(ctx->dcfg, b, n_units, max_read_len, d_survivors, d_counters, ctx->sm_count, st);
+    ExactArgs a{};
+    a.survivors = d_survivors; a.n_survivors = d_counters; a.work_counter = d_counters + 1;
+    a.slice_scratch = *d_scratch; a.slice_scratch_stride = stride; a.run_cap = run_cap_for(ctx->cfg, max_read_len);
+    a.total_survivors = ctx->d_total_surv;
+    launch_exact(ctx->dcfg, b, a, ctx->sm_count, st);
+    CK(cudaGetLastError());
+    ctx->stats.kernel_launches += 2;
+    return TREW_OK;
+}
+
+int retire_slot(trew_ctx* ctx, SlotRes& s) {
+    if (!s.in_flight) return TREW_OK;
+    CK(cudaEventSynchronize(s.ev_done));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, s.ev_start, s.ev_done));
+    ctx->stats.device_ms += ms;
+    s.in_flight = false;
+    return TREW_OK;
+}
+
+// Pack reads (host threads) into the next free staging slot and launch copy + kernels on its stream.
+int submit_reads(trew_ctx* ctx, const ReadRef* reads, uint32_t n, uint64_t total_bases, uint32_t max_len) {
+    if (n == 0) return TREW_OK;
+    SlotRes& s = ctx->slots[ctx->next_slot];
+    ctx->next_slot = (ctx->next_slot + 1) % ctx->slots.size();
+    int rc = retire_slot(ctx, s);
+    if (rc) return rc;
+    BatchView v;
+    batch_layout(s.h_buf, n, total_bases, &v);
+    // split into ranges of roughly equal bases, one per pool thread
+    int P = std::max(1, std::min(ctx->pool->size(), (int)(total_bases / 65536) + 1));
+    std::vector<uint32_t> starts;
+    starts.push_back(0);
+    if (P > 1) {
+        uint64_t acc = 0, target = total_bases / P;
+        for (uint32_t r = 0; r < n && (int)starts.size() < P; r++) {
+            if (acc >= target * starts.size() && r != starts.back()) starts.push_back(r);
+            acc += reads[r].len;
+        }
+    }
+    pack_prepare(reads, n, starts.data(), (int)starts.size(), v);
+    int nr = (int)starts.size();
+    ctx->pool->run(nr, [&](int i) { pack_range(reads, starts[i], i + 1 < nr ? starts[i + 1] : n, v); });
+
+    CK(cudaEventRecord(s.ev_start, s.stream));
+    CK(cudaMemcpyAsync(s.d_buf, s.h_buf, v.bytes, cudaMemcpyHostToDevice, s.stream));
+    DevBatch b{};
+    b.n_reads = n;
+    b.bit_off = (const unsigned int*)s.d_buf;
+    b.hi = (const unsigned int*)((char*)s.d_buf + ((char*)v.hi - (char*)s.h_buf));
+    b.lo = b.hi + v.plane_words; b.val = b.lo + v.plane_words;
+    uint32_t n_units = ctx->cfg.mode == TREW_MODE_PAIR ? n / 2 : n;
+    rc = launch_scan(ctx, b, n_units, max_len, s.d_survivors, s.d_counters, &s.d_scratch, &s.scratch_bytes, s.stream);
+    if (rc) return rc;
+    CK(cudaEventRecord(s.ev_done, s.stream));
+    s.in_flight = true;
+    ctx->stats.reads += n; ctx->stats.bases += total_bases; ctx->stats.units += n_units; ctx->stats.h2d_bytes += v.bytes;
+    return TREW_OK;
+}
+
+// Greedy split of a read list into sub-batches that fit one staging slot.
+int submit_split(trew_ctx* ctx, const std::vector<ReadRef>& reads, uint32_t unit) {
+    size_t i = 0, n = reads.size();
+    while (i < n) {
+        size_t j = i; uint64_t bases = 0; uint32_t mx = 0;
+        while (j < n) {
+            uint64_t add = 0; uint32_t m2 = mx;
+            for (uint32_t t = 0; t < unit; t++) { add += reads[j + t].len; m2 = std::max(m2, reads[j + t].len); }
+            if (j > i && (batch_bytes((uint32_t)(j - i + unit), bases + add) > ctx->staging_bytes ||
+                          (j - i + unit) > ctx->slots[0].survivors_cap || bases + add >= 0xfffff000ULL)) break;
+            bases += add; mx = m2; j += unit;
+        }
+        if (batch_bytes((uint32_t)(j - i), bases) > ctx->staging_bytes)
+            return fail(ctx, TREW_ERR_ARG, "a single read/pair (%llu bases) does not fit a staging buffer of %zu bytes",
+                        (unsigned long long)bases, ctx->staging_bytes);
+        int rc = submit_reads(ctx, reads.data() + i, (uint32_t)(j - i), bases, mx);
+        if (rc) return rc;
+        i = j;
+    }
+    return TREW_OK;
+}
+
+int check_device_error(trew_ctx* ctx) {
+    unsigned int e = 0;
+    CK(cudaMemcpy(&e, ctx->d_error, sizeof(e), cudaMemcpyDeviceToHost));
+    if (e == 3u) return fail(ctx, TREW_ERR_TABLE_FULL, "device count table full (%zu slots): raise table_log2_slots", ctx->n_slots);
+    if (e) return fail(ctx, TREW_ERR_CUDA, "device error flag %u", e);
+    return TREW_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int trew_abi_version(void) { return TREW_ABI_VERSION; }
+
+const char* trew_status_string(int status) {
+    switch (status) {
+        case TREW_OK: return "ok";
+        case TREW_ERR_ARG: return "bad argument";
+        case TREW_ERR_CUDA: return "CUDA failure";
+        case TREW_ERR_TABLE_FULL: return "device count table full";
+        case TREW_ERR_TOO_LONG: return "This mode is designed for short-read sequencing. Please use 'trew long'.";
+        case TREW_ERR_IO: return "file I/O error";
+        case TREW_ERR_PAIRING: return "paired-end record mismatch";
+        case TREW_ERR_NOMEM: return "memory allocation failure";
+        default: return "unknown status";
+    }
+}
+
+const char* trew_dev_last_error(const trew_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int trew_dev_create(const trew_config* cfg, trew_ctx** out) {
+    if (!cfg || !out) return TREW_ERR_ARG;
+    *out = nullptr;
+    // same range checks as the reference CLI (src/trew.cpp:174-228, 255-304)
+    if (cfg->mode < 0 || cfg->mode > 2 || cfg->min_mer < 3 || cfg->max_mer > 64 || cfg->min_mer > cfg->max_mer) return TREW_ERR_ARG;
+    if (!(0 < cfg->low_baseline && cfg->low_baseline <= 1) || !(0 < cfg->high_baseline && cfg->high_baseline <= 1) ||
+        cfg->low_baseline > cfg->high_baseline) return TREW_ERR_ARG;
+    if (cfg->mode == TREW_MODE_LONG && (cfg->slice_length < 2 * cfg->max_mer || cfg->slice_length > 512)) return TREW_ERR_ARG;
+    trew_ctx* ctx = new trew_ctx();
+    ctx->cfg = *cfg;
+    if (ctx->cfg.slice_length <= 0) ctx->cfg.slice_length = 150;
+    auto bail = [&](int rc) { std::string e = ctx->err; trew_dev_destroy(ctx); fprintf(stderr, "trew_dev_create: %s\n", e.c_str()); return rc; };
+#define CKC(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) { fail(ctx, TREW_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); return bail(TREW_ERR_CUDA); } \
+    } while (0)
+    int ndev = 0;
+    CKC(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) { fail(ctx, TREW_ERR_CUDA, "no CUDA device %d (found %d)", cfg->device, ndev); return bail(TREW_ERR_CUDA); }
+    CKC(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CKC(cudaGetDeviceProperties(&prop, cfg->device));
+    ctx->sm_count = prop.multiProcessorCount;
+    int lg = cfg->table_log2_slots > 0 ? cfg->table_log2_slots : 20;
+    if (lg < 10 || lg > 28) { fail(ctx, TREW_ERR_ARG, "table_log2_slots out of range"); return bail(TREW_ERR_ARG); }
+    ctx->n_slots = (size_t)1 << lg;
+    Slot* d_slots = nullptr;
+    CKC(cudaMalloc((void**)&d_slots, ctx->n_slots * sizeof(Slot)));
+    CKC(cudaMemset(d_slots, 0, ctx->n_slots * sizeof(Slot)));
+    CKC(cudaMalloc((void**)&ctx->d_error, sizeof(unsigned int)));
+    CKC(cudaMemset(ctx->d_error, 0, sizeof(unsigned int)));
+    CKC(cudaMalloc((void**)&ctx->d_total_surv, sizeof(unsigned long long)));
+    CKC(cudaMemset(ctx->d_total_surv, 0, sizeof(unsigned long long)));
+    std::vector<unsigned short> thr;
+    build_thr(cfg->low_baseline, thr);
+    CKC(cudaMalloc((void**)&ctx->d_thr, thr.size() * sizeof(unsigned short)));
+    CKC(cudaMemcpy(ctx->d_thr, thr.data(), thr.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    ctx->dcfg.mode = cfg->mode; ctx->dcfg.min_mer = cfg->min_mer; ctx->dcfg.max_mer = cfg->max_mer;
+    ctx->dcfg.slice_len = ctx->cfg.slice_length; ctx->dcfg.low = cfg->low_baseline; ctx->dcfg.high = cfg->high_baseline;
+    ctx->dcfg.slots = d_slots; ctx->dcfg.slot_mask = (unsigned int)(ctx->n_slots - 1);
+    ctx->dcfg.error_flag = ctx->d_error; ctx->dcfg.thr_low = ctx->d_thr;
+    CKC(prepare_exact(kMaxWindow + 9));
+    CKC(cudaStreamCreateWithFlags(&ctx->main_stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreate(&ctx->ev_a));
+    CKC(cudaEventCreate(&ctx->ev_b));
+    ctx->staging_bytes = cfg->staging_bytes ? (size_t)cfg->staging_bytes : ((size_t)64 << 20);
+    int ns = cfg->n_staging > 0 ? cfg->n_staging : 3;
+    ctx->slots.resize((size_t)ns);
+    for (auto& s : ctx->slots) {
+        CKC(cudaHostAlloc(&s.h_buf, ctx->staging_bytes, cudaHostAllocDefault));
+        CKC(cudaMalloc(&s.d_buf, ctx->staging_bytes));
+        s.survivors_cap = ctx->staging_bytes / 8;  // >= reads of >= 11 bases; submit_split enforces it
+        CKC(cudaMalloc((void**)&s.d_survivors, s.survivors_cap * sizeof(unsigned int)));
+        CKC(cudaMalloc((void**)&s.d_counters, 2 * sizeof(unsigned int)));
+        CKC(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CKC(cudaEventCreate(&s.ev_start));
+        CKC(cudaEventCreate(&s.ev_done));
+    }
+    CKC(cudaMalloc((void**)&ctx->d_n, sizeof(unsigned int)));
+    int nt = cfg->host_threads > 0 ? cfg->host_threads : (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+    ctx->pool = new Pool(nt);
+#undef CKC
+    *out = ctx;
+    return TREW_OK;
+}
+
+void trew_dev_destroy(trew_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    cudaDeviceSynchronize();
+    for (auto& s : ctx->slots) {
+        if (s.h_buf) cudaFreeHost(s.h_buf);
+        if (s.d_buf) cudaFree(s.d_buf);
+        if (s.d_survivors) cudaFree(s.d_survivors);
+        if (s.d_counters) cudaFree(s.d_counters);
+        if (s.d_scratch) cudaFree(s.d_scratch);
+        if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.ev_start) cudaEventDestroy(s.ev_start);
+        if (s.ev_done) cudaEventDestroy(s.ev_done);
+    }
+    if (ctx->dcfg.slots) cudaFree(ctx->dcfg.slots);
+    if (ctx->d_error) cudaFree(ctx->d_error);
+    if (ctx->d_thr) cudaFree(ctx->d_thr);
+    if (ctx->d_total_surv) cudaFree(ctx->d_total_surv);
+    if (ctx->d_meta) cudaFree(ctx->d_meta);
+    if (ctx->d_seq) cudaFree(ctx->d_seq);
+    if (ctx->d_count) cudaFree(ctx->d_count);
+    if (ctx->d_n) cudaFree(ctx->d_n);
+    if (ctx->main_stream) cudaStreamDestroy(ctx->main_stream);
+    if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+    if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+    delete ctx->pool;
+    delete ctx;
+}
+
+int trew_dev_submit_chunk(trew_ctx* ctx, const char* buffer1, const int32_t* locs1, uint32_t n1,
+                          const char* buffer2, const int32_t* locs2, uint32_t n2) {
+    if (!ctx) return TREW_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    const bool pair = ctx->cfg.mode == TREW_MODE_PAIR;
+    if (pair ? (!buffer2 && n2) : (buffer2 != nullptr || n2 != 0)) return fail(ctx, TREW_ERR_ARG, "second chunk only in pair mode");
+    if ((n1 && (!buffer1 || !locs1)) || (n2 && !locs2)) return fail(ctx, TREW_ERR_ARG, "null chunk");
+    auto& reads = ctx->reads_tmp;
+    reads.clear();
+    auto ref = [](const char* buf, const int32_t* locs, uint32_t i) {
+        int32_t st = locs[2 * i], nd = locs[2 * i + 1];
+        return ReadRef{buf + st, nd >= st ? (uint32_t)(nd - st + 1) : 0u};
+    };
+    if (pair) {
+        uint32_t n = std::min(n1, n2);  // index-wise pairing, src/kmer.cpp:321-322
+        reads.reserve((size_t)2 * n);
+        for (uint32_t i = 0; i < n; i++) { reads.push_back(ref(buffer1, locs1, i)); reads.push_back(ref(buffer2, locs2, i)); }
+    } else {
+        reads.reserve(n1);
+        for (uint32_t i = 0; i < n1; i++) {
+            ReadRef r = ref(buffer1, locs1, i);
+            if (ctx->cfg.mode == TREW_MODE_SHORT && r.len > 1000)  // MAX_SEQ, src/kmer.cpp:1006-1008
+                return fail(ctx, TREW_ERR_TOO_LONG, "%s", trew_status_string(TREW_ERR_TOO_LONG));
+            reads.push_back(r);
+        }
+    }
+    if (pair) for (auto& r : reads) if (r.len > (uint32_t)kMaxWindow) return fail(ctx, TREW_ERR_TOO_LONG, "paired read longer than %d", kMaxWindow);
+    return submit_split(ctx, reads, pair ? 2u : 1u);
+}
+
+int trew_dev_submit_packed(trew_ctx* ctx, const trew_batch* batch) {
+    if (!ctx || !batch) return TREW_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    uint32_t n = batch->n_reads;
+    if (n == 0) return TREW_OK;
+    uint64_t bases = batch->bit_off[n];
+    size_t bytes = batch_bytes(n, bases);
+    if (bytes > ctx->staging_bytes || n > ctx->slots[0].survivors_cap)
+        return fail(ctx, TREW_ERR_ARG, "packed batch (%zu bytes) larger than a staging buffer (%zu)", bytes, ctx->staging_bytes);
+    if (batch->bit_off[0] != 0) return fail(ctx, TREW_ERR_ARG, "bit_off[0] must be 0");
+    SlotRes& s = ctx->slots[ctx->next_slot];
+    ctx->next_slot = (ctx->next_slot + 1) % ctx->slots.size();
+    int rc = retire_slot(ctx, s);
+    if (rc) return rc;
+    BatchView v;
+    batch_layout(s.h_buf, n, bases, &v);
+    size_t words = (size_t)((bases + 31) / 32);
+    memcpy(v.bit_off, batch->bit_off, (size_t)(n + 1) * 4);
+    const uint32_t* src[3] = {batch->hi, batch->lo, batch->val};
+    uint32_t* dst[3] = {v.hi, v.lo, v.val};
+    ctx->pool->run(3, [&](int i) {
+        memcpy(dst[i], src[i], words * 4);
+        memset(dst[i] + words, 0, (v.plane_words - words) * 4);
+    });
+    CK(cudaEventRecord(s.ev_start, s.stream));
+    CK(cudaMemcpyAsync(s.d_buf, s.h_buf, v.bytes, cudaMemcpyHostToDevice, s.stream));
+    DevBatch b{};
+    b.n_reads = n;
+    b.bit_off = (const unsigned int*)s.d_buf;
+    b.hi = (const unsigned int*)((char*)s.d_buf + ((char*)v.hi - (char*)s.h_buf));
+    b.lo = b.hi + v.plane_words; b.val = b.lo + v.plane_words;
+    uint32_t n_units = ctx->cfg.mode == TREW_MODE_PAIR ? n / 2 : n;
+    rc = launch_scan(ctx, b, n_units, batch->max_read_len, s.d_survivors, s.d_counters, &s.d_scratch, &s.scratch_bytes, s.stream);
+    if (rc) return rc;
+    CK(cudaEventRecord(s.ev_done, s.stream));
+    s.in_flight = true;
+    ctx->stats.reads += n; ctx->stats.bases += bases; ctx->stats.units += n_units; ctx->stats.h2d_bytes += v.bytes;
+    return TREW_OK;
+}
+
+int trew_dev_upload(trew_ctx* ctx, const trew_batch* batch, trew_resident** out) {
+    if (!ctx || !batch || !out) return TREW_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    uint32_t n = batch->n_reads;
+    uint64_t bases = n ? batch->bit_off[n] : 0;
+    trew_resident* r = new trew_resident();
+    size_t bytes = batch_bytes(n, bases);
+    std::vector<char> tmp(bytes, 0);
+    BatchView v;
+    batch_layout(tmp.data(), n, bases, &v);
+    size_t words = (size_t)((bases + 31) / 32);
+    if (n) {
+        memcpy(v.bit_off, batch->bit_off, (size_t)(n + 1) * 4);
+        memcpy(v.hi, batch->hi, words * 4); memcpy(v.lo, batch->lo, words * 4); memcpy(v.val, batch->val, words * 4);
+    }
+    CK(cudaMalloc(&r->d_buf, bytes));
+    CK(cudaMemcpy(r->d_buf, tmp.data(), bytes, cudaMemcpyHostToDevice));
+    r->batch.n_reads = n;
+    r->batch.bit_off = (const unsigned int*)r->d_buf;
+    r->batch.hi = (const unsigned int*)((char*)r->d_buf + ((char*)v.hi - tmp.data()));
+    r->batch.lo = r->batch.hi + v.plane_words; r->batch.val = r->batch.lo + v.plane_words;
+    r->n_reads = n; r->n_units = ctx->cfg.mode == TREW_MODE_PAIR ? n / 2 : n; r->max_read_len = batch->max_read_len; r->bases = bases;
+    CK(cudaMalloc((void**)&r->d_survivors, (size_t)std::max<uint32_t>(r->n_units, 1) * sizeof(unsigned int)));
+    CK(cudaMalloc((void**)&r->d_counters, 2 * sizeof(unsigned int)));
+    *out = r;
+    return TREW_OK;
+}
+
+int trew_dev_scan_resident(trew_ctx* ctx, const trew_resident* rb) {
+    if (!ctx || !rb) return TREW_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    trew_resident* r = const_cast<trew_resident*>(rb);
+    CK(cudaEventRecord(ctx->ev_a, ctx->main_stream));
+    int rc = launch_scan(ctx, r->batch, r->n_units, r->max_read_len, r->d_survivors, r->d_counters, &r->d_scratch,
+                         &r->scratch_bytes, ctx->main_stream);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev_b, ctx->main_stream));
+    ctx->stats.reads += r->n_reads; ctx->stats.bases += r->bases; ctx->stats.units += r->n_units;
+    return TREW_OK;
+}
+
+void trew_dev_free_resident(trew_ctx* ctx, trew_resident* r) {
+    if (!r) return;
+    if (ctx) { cudaSetDevice(ctx->cfg.device); cudaStreamSynchronize(ctx->main_stream); }
+    if (r->d_buf) cudaFree(r->d_buf);
+    if (r->d_survivors) cudaFree(r->d_survivors);
+    if (r->d_counters) cudaFree(r->d_counters);
+    if (r->d_scratch) cudaFree(r->d_scratch);
+    delete r;
+}
+
+int trew_dev_sync(trew_ctx* ctx) {
+    if (!ctx) return TREW_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    for (auto& s : ctx->slots) { int rc = retire_slot(ctx, s); if (rc) return rc; }
+    CK(cudaStreamSynchronize(ctx->main_stream));
+    return check_device_error(ctx);
+}
+
+int trew_dev_export_device(trew_ctx* ctx, const uint32_t** d_meta, const uint64_t** d_seq, const uint64_t** d_count,
+                           uint64_t* n_entries) {
+    if (!ctx) return TREW_ERR_ARG;
+    int rc = trew_dev_sync(ctx);
+    if (rc) return rc;
+    if (!ctx->d_meta) {
+        CK(cudaMalloc((void**)&ctx->d_meta, ctx->n_slots * sizeof(unsigned int)));
+        CK(cudaMalloc((void**)&ctx->d_seq, ctx->n_slots * 2 * sizeof(unsigned long long)));
+        CK(cudaMalloc((void**)&ctx->d_count, ctx->n_slots * sizeof(unsigned long long)));
+    }
+    CK(cudaMemsetAsync(ctx->d_n, 0, sizeof(unsigned int), ctx->main_stream));
+    launch_compact(ctx->dcfg.slots, (unsigned int)ctx->n_slots, ctx->d_meta, ctx->d_seq, ctx->d_count, ctx->d_n, ctx->main_stream);
+    CK(cudaGetLastError());
+    ctx->stats.kernel_launches += 1;
+    unsigned int n = 0;
+    CK(cudaMemcpyAsync(&n, ctx->d_n, sizeof(n), cudaMemcpyDeviceToHost, ctx->main_stream));
+    CK(cudaStreamSynchronize(ctx->main_stream));
+    ctx->n_export = n;
+    if (d_meta) *d_meta = ctx->d_meta;
+    if (d_seq) *d_seq = (const uint64_t*)ctx->d_seq;
+    if (d_count) *d_count = (const uint64_t*)ctx->d_count;
+    if (n_entries) *n_entries = n;
+    return TREW_OK;
+}
+
+int trew_dev_finish(trew_ctx* ctx, const trew_entry** entries, uint64_t* n_entries) {
+    if (!ctx) return TREW_ERR_ARG;
+    uint64_t n = 0;
+    int rc = trew_dev_export_device(ctx, nullptr, nullptr, nullptr, &n);
+    if (rc) return rc;
+    std::vector<unsigned int> meta(n);
+    std::vector<unsigned long long> seq(2 * n), cnt(n);
+    if (n) {
+        CK(cudaMemcpy(meta.data(), ctx->d_meta, n * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(seq.data(), ctx->d_seq, 2 * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(cnt.data(), ctx->d_count, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    }
+    ctx->stats.d2h_bytes += n * 28 + 4;
+    ctx->entries.resize(n);
+    for (uint64_t i = 0; i < n; i++) {
+        trew_entry& e = ctx->entries[i];
+        e.table = (int32_t)(meta[i] >> 8); e.k = (int32_t)(meta[i] & 0xff);
+        e.seq_lo = seq[2 * i]; e.seq_hi = seq[2 * i + 1]; e.count = cnt[i];
+    }
+    std::sort(ctx->entries.begin(), ctx->entries.end(), [](const trew_entry& a, const trew_entry& b) {
+        if (a.table != b.table) return a.table < b.table;
+        if (a.k != b.k) return a.k < b.k;
+        if (a.seq_hi != b.seq_hi) return a.seq_hi < b.seq_hi;
+        return a.seq_lo < b.seq_lo;
+    });
+    if (entries) *entries = ctx->entries.data();
+    if (n_entries) *n_entries = n;
+    return TREW_OK;
+}
+
+int trew_dev_reset(trew_ctx* ctx) {
+    if (!ctx) return TREW_ERR_ARG;
+    int rc = trew_dev_sync(ctx);
+    if (rc && rc != TREW_ERR_TABLE_FULL) return rc;
+    CK(cudaMemset(ctx->dcfg.slots, 0, ctx->n_slots * sizeof(Slot)));
+    CK(cudaMemset(ctx->d_error, 0, sizeof(unsigned int)));
+    return TREW_OK;
+}
+
+int trew_dev_get_stats(trew_ctx* ctx, trew_stats* out) {
+    if (!ctx || !out) return TREW_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    unsigned long long s = 0;
+    CK(cudaMemcpy(&s, ctx->d_total_surv, sizeof(s), cudaMemcpyDeviceToHost));
+    ctx->stats.survivors = s;
+    *out = ctx->stats;
+    return TREW_OK;
+}
+
+// elapsed device time of the last trew_dev_scan_resident (ms); the caller must have synchronised
+int trew_dev_last_resident_ms(trew_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return TREW_ERR_ARG;
+    CK(cudaEventSynchronize(ctx->ev_b));
+    CK(cudaEventElapsedTime(ms, ctx->ev_a, ctx->ev_b));
+    return TREW_OK;
+}
+
+int trew_dev_process_file(trew_ctx* ctx, const char* file1, int is_gz1, const char* file2, int is_gz2) {
+    if (!ctx || !file1) return TREW_ERR_ARG;
+    if ((ctx->cfg.mode == TREW_MODE_PAIR) != (file2 != nullptr)) return fail(ctx, TREW_ERR_ARG, "second file only in pair mode");
+    IngestResult r = ingest_file(ctx->cfg.mode, ctx->cfg.slice_length, file1, is_gz1 != 0, file2, is_gz2 != 0, (size_t)32 << 20,
+                                 [&](const char* b1, const std::vector<int32_t>& l1, const char* b2, const std::vector<int32_t>& l2) {
+                                     return trew_dev_submit_chunk(ctx, b1, l1.data(), (uint32_t)(l1.size() / 2), b2,
+                                                                  b2 ? l2.data() : nullptr, b2 ? (uint32_t)(l2.size() / 2) : 0u);
+                                 });
+    if (r.status != TREW_OK && r.status != TREW_ERR_CUDA && !r.message.empty()) ctx->err = r.message;
+    return r.status;
+}
+
+}  // extern "C"

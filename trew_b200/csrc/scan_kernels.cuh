@@ -1,0 +1,69 @@
+// Device-side declarations shared by scan_kernels.cu (kernels) and device_ctx.cu (host driver).
+//
+// Two kernels implement the reference's per-read scan-and-count (buffer_task*, src/kmer.cpp:80-985,
+// with k_mer_check/k_mer_target, src/kmer.cpp:1894-2547):
+//
+//   trew_filter_kernel  one THREAD per read/pair.  Bit-parallel, sound rejection test: for every probe
+//                       window the routing would scan first and every period k, an upper bound U_k on
+//                       the largest rotation-class count M_k is compared with the smallest count that
+//                       would pass LOW_BASELINE.  Units where no (window, k) can pass emit nothing in
+//                       the reference, so they are done; the rest go to a survivor list.
+//   trew_exact_kernel   one WARP per survivor.  Re-does the reference's routing exactly: per-period
+//                       class counts via match-bit runs + canonical rotations, the ascending-k
+//                       selection with IEEE double ratios, and emission into the device count table.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace trew {
+
+constexpr int kThrTableSize = 1025;  // thr[T] for T = 0..1024 valid windows
+constexpr int kMaxWindow = 1023;     // longest window the exact kernel handles (32 lanes x 32 bits)
+
+// 32-byte open-addressing slot of the device count table
+struct __align__(32) Slot {
+    unsigned long long seq_lo;
+    unsigned long long seq_hi;
+    unsigned long long count;
+    unsigned int meta;   // table << 8 | k
+    unsigned int state;  // 0 empty, 1 being written, 2 ready
+};
+
+struct DevCfg {
+    int mode, min_mer, max_mer, slice_len;
+    double low, high;
+    Slot* slots;
+    unsigned int slot_mask;
+    unsigned int* error_flag;        // set to TREW_ERR_TABLE_FULL on overflow
+    const unsigned short* thr_low;   // kThrTableSize entries: min M with (double)M/(double)T >= low; 0xFFFF for T = 0
+};
+
+struct DevBatch {
+    unsigned int n_reads;
+    const unsigned int* bit_off;
+    const unsigned int* hi;
+    const unsigned int* lo;
+    const unsigned int* val;
+};
+
+struct ExactArgs {
+    const unsigned int* survivors;
+    const unsigned int* n_survivors;
+    unsigned int* work_counter;      // zeroed before launch
+    unsigned char* slice_scratch;    // long mode: per-warp (th, tl) per slice
+    unsigned int slice_scratch_stride;  // bytes per warp
+    int run_cap;                     // run-list capacity per warp (>= longest window + 1)
+    unsigned long long* total_survivors;  // running total over all launches (statistics)
+};
+
+// host-side launchers (scan_kernels.cu)
+void launch_filter(const DevCfg& cfg, const DevBatch& b, unsigned int n_units, unsigned int max_read_len,
+                   unsigned int* survivors, unsigned int* n_survivors, int sm_count, cudaStream_t stream);
+size_t exact_smem_bytes(int run_cap, bool wide);
+cudaError_t prepare_exact(int run_cap_max);
+void launch_exact(const DevCfg& cfg, const DevBatch& b, const ExactArgs& a, int sm_count, cudaStream_t stream);
+int exact_warps_total(int sm_count);
+void launch_compact(const Slot* slots, unsigned int n_slots, unsigned int* d_meta, unsigned long long* d_seq,
+                    unsigned long long* d_count, unsigned int* d_n, cudaStream_t stream);
+
+}  // namespace trew
