@@ -1,0 +1,135 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against golden fixtures from the compiled
+reference, against the CPU oracle on seeded adversarial inputs, and -- at sizes the oracle cannot finish --
+through size-independent properties.  Integer work: every comparison is bit-exact."""
+import numpy as np
+import pytest
+
+from trew_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def tables_from_json(rows):
+    from oracle.oracle import str_to_seq
+    return {(tb, k, str_to_seq(s)): c for tb, k, s, c in rows}
+
+
+def diff_msg(got, want):
+    from oracle.oracle import format_tables
+    a, b = set(got.items()), set(want.items())
+    only_g = format_tables(dict(sorted(a - b)[:6]))
+    only_w = format_tables(dict(sorted(b - a)[:6]))
+    return "got %d entries, want %d; only CUDA: %s; only expected: %s" % (len(got), len(want), only_g, only_w)
+
+
+def run_gpu(mode, mn, mx, low, high, sl, r1, r2=None, **kw):
+    with api.DeviceContext(mode, mn, mx, low, high, sl, **kw) as ctx:
+        ctx.submit_reads(r1, r2)
+        return ctx.finish()
+
+
+def test_golden_scan_cases(scan_cases):
+    for case in scan_cases:
+        r1 = [s.encode() for s in case["reads1"]]
+        r2 = [s.encode() for s in case["reads2"]] if case["reads2"] is not None else None
+        if case["mode"] == 2:
+            r1 = [r for r in r1 if len(r) >= case["slice_len"]]
+        got = run_gpu(case["mode"], case["min_mer"], case["max_mer"], case["low"], case["high"], case["slice_len"], r1, r2)
+        want = tables_from_json(case["tables"])
+        assert got == want, case["name"] + ": " + diff_msg(got, want)
+
+
+@pytest.mark.parametrize("mn,mx,low,high", [(5, 32, 0.5, 0.8), (3, 64, 0.5, 0.8), (5, 64, 0.5, 0.8), (7, 20, 0.5, 0.8),
+                                            (12, 40, 0.5, 0.8), (5, 32, 0.35, 0.6), (5, 32, 0.9, 1.0), (4, 33, 0.5, 0.5)])
+def test_short_vs_oracle(mn, mx, low, high):
+    from oracle.oracle import Oracle
+    reads = synth.adversarial_short(100 + mn * 7 + mx, 1200, max_unit=mx)
+    got = run_gpu(api.MODE_SHORT, mn, mx, low, high, 150, reads)
+    want = Oracle(mn, mx, low, high).scan(0, reads)
+    assert got == want, diff_msg(got, want)
+
+
+@pytest.mark.parametrize("mn,mx,rl,trunc", [(5, 32, 150, 0.0), (5, 40, 100, 0.15), (3, 64, 120, 0.1), (5, 32, 100, 0.2)])
+def test_pair_vs_oracle(mn, mx, rl, trunc):
+    # the oracle follows the cleared-temp-map (128-bit path) semantics, like the CUDA path
+    from oracle.oracle import Oracle
+    r1, r2 = synth.adversarial_pairs(200 + mx + rl, 700, read_len=rl, max_unit=mx, truncate_mate2=trunc)
+    got = run_gpu(api.MODE_PAIR, mn, mx, 0.5, 0.8, 150, r1, r2)
+    want = Oracle(mn, mx).scan(1, r1, r2)
+    assert got == want, diff_msg(got, want)
+
+
+@pytest.mark.parametrize("mn,mx,sl", [(5, 32, 150), (3, 64, 128), (5, 20, 64), (5, 32, 300)])
+def test_long_vs_oracle(mn, mx, sl):
+    from oracle.oracle import Oracle
+    reads = [r for r in synth.adversarial_long(300 + sl, 150, min_len=sl, max_len=4000, max_unit=mx)]
+    got = run_gpu(api.MODE_LONG, mn, mx, 0.5, 0.8, sl, reads)
+    want = Oracle(mn, mx, slice_len=sl).scan(2, reads)
+    assert got == want, diff_msg(got, want)
+
+
+def test_edge_cases():
+    from oracle.oracle import Oracle
+    reads = [b"", b"A", b"ACGTACGTA", b"ACGTACGTAC", b"N" * 150, b"A" * 150, b"TTAGGG" * 25, b"ttaggg" * 25,
+             b"TTAGGG" * 12 + b"N" + b"TTAGGG" * 12, (b"TTAGGG" * 170)[:1000], b"TG" * 75, b"TTAGGGN" * 21,
+             b"ACGT" * 5, b"TTAGG" * 4, b"TTAGGG" * 3 + b"\r"]
+    for mn, mx in [(5, 32), (3, 64)]:
+        got = run_gpu(api.MODE_SHORT, mn, mx, 0.5, 0.8, 150, reads)
+        want = Oracle(mn, mx).scan(0, reads)
+        assert got == want, diff_msg(got, want)
+    assert run_gpu(api.MODE_SHORT, 5, 32, 0.5, 0.8, 150, []) == {}
+
+
+def test_order_and_batching_independence():
+    reads = synth.adversarial_short(11, 3000)
+    a = run_gpu(api.MODE_SHORT, 5, 32, 0.5, 0.8, 150, reads)
+    b = run_gpu(api.MODE_SHORT, 5, 32, 0.5, 0.8, 150, reads[::-1], staging_bytes=1 << 16, n_staging=2)  # many tiny batches
+    assert a == b
+    with api.DeviceContext(api.MODE_SHORT, 5, 32) as ctx:  # linearity: tables of a concatenation are sums
+        ctx.submit_reads(reads[:1000])
+        ctx.submit_reads(reads[1000:])
+        ctx.submit_reads(reads)
+        c = ctx.finish()
+    assert c == {k: 2 * v for k, v in a.items()}
+
+
+def test_packed_and_resident_paths_agree():
+    reads = synth.adversarial_short(12, 2000)
+    buf, locs = api.make_chunk(reads)
+    pb = api.PackedBatch(buf, locs)
+    pb.batch.max_read_len = max(len(r) for r in reads)
+    a = run_gpu(api.MODE_SHORT, 5, 32, 0.5, 0.8, 150, reads)
+    with api.DeviceContext(api.MODE_SHORT, 5, 32) as ctx:
+        ctx.submit_packed(pb)
+        b = ctx.finish()
+        ctx.reset()
+        h = ctx.upload(pb)
+        ctx.scan_resident(h)
+        c = ctx.finish()
+        assert ctx.last_resident_ms() > 0
+        ctx.free_resident(h)
+    assert a == b == c
+
+
+def test_full_shape_properties():
+    """cfg-2 shape at 2M reads: the oracle would need minutes, so check properties instead:
+    (1) reverse-complementing every read swaps forward/backward tables under the RC fold,
+    (2) non-repeat reads contribute nothing: dropping them leaves the tables unchanged."""
+    mat = synth.config_short(21, 2_000_000)
+    buf, locs = api.matrix_chunk(mat)
+    with api.DeviceContext(api.MODE_SHORT, 5, 32) as ctx:
+        ctx.submit_chunk(buf, locs)
+        full = ctx.finish()
+        st = ctx.stats()
+    assert st.reads == 2_000_000 and st.bases == 300_000_000
+    assert 0.008 * st.reads < st.survivors < 0.05 * st.reads
+    assert sum(full.values()) > 0
+    # survivors-only rerun: reads that contain no TTAGGG-like signal must not matter
+    tel = np.array([b"TTAGGG" in bytes(r) or b"CCCTAA" in bytes(r) for r in mat[:200_000]])
+    sub = mat[:200_000]
+    a = run_gpu(api.MODE_SHORT, 5, 32, 0.5, 0.8, 150, [bytes(r) for r in sub])
+    b = run_gpu(api.MODE_SHORT, 5, 32, 0.5, 0.8, 150, [bytes(r) for r in sub[tel]])
+    for key, v in b.items():
+        assert a.get(key) == v
+    extra = {k: v for k, v in a.items() if k not in b}
+    assert sum(extra.values()) <= 0.02 * sum(a.values())
