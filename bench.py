@@ -1,0 +1,347 @@
+#!/usr/bin/env python3
+"""Headline benchmark: Gbases/s of the TREW scan-and-count hot path (`trew short 5 32`) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A *step* is one pass of the hot path over one file-sized batch of synthetic reads of BASELINE.json's
+configs[1] shape (200 M x 150 bp per GPU, ~1 % TTAGGG reads, MIN_MER 5, MAX_MER 32): reset the count table,
+scan every resident batch (filter kernel + exact kernel per batch), compact the table, copy it to the host
+and -- for N > 1 -- merge the per-rank tables exactly over NCCL.
+
+  value      whole-job Gbases/s with the packed reads already resident in HBM (generated on the device),
+             timed with CUDA events on the scan stream, max over ranks.  13 batches of 16 M reads: 12 GB of
+             input per pass, far larger than L2, so no flush is needed between iterations.
+  e2e        the same metric through the reference-facing C ABI with HOST buffers: raw ASCII sequence
+             chunks (the reference's QueueData) -> trew_dev_submit_chunk (host packing, pinned staging,
+             cudaMemcpyAsync, kernels) -> trew_dev_finish (tables back on the host), wall clock.
+  roofline   filter kernel (the dominant kernel): algorithmic bytes per launch / its mean CUDA-event
+             duration, against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline  the reference's own CPU path (oracle/_ref, compiled from the unmodified sources) on the
+             box's host cores, on a bounded sample of the same workload.  Reported, not the target.
+
+--impl reference times only that CPU path (rank 0; other ranks exit) and prints the same JSON shape.
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "Gbases/s for trew short 5 32 at 1/2/4/8 B200; % of HBM roofline"
+READ_LEN = 150
+BATCH_READS = 16_000_000
+BYTES_PER_READ = 4 + 3 * READ_LEN / 8.0  # offsets + three bit-planes ("algorithmic bytes")
+SYNTH = dict(tel_ppm=10000, half_ppm=2000, n_ppm=1000, sub_ppm=10000)
+
+
+def workload_name(reads_per_gpu):
+    return ("synthetic short-read single-end: %d M x %d bp reads per GPU with ~1%% TTAGGG-repeat reads, "
+            "MIN_MER=5 MAX_MER=32" % (reads_per_gpu // 1_000_000, READ_LEN))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, timeout=5).stdout.decode()
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's CPU path (oracle/_ref): only for cpu_baseline / --impl reference
+# ---------------------------------------------------------------------------------------------
+
+def write_sample_fastq(path, n_reads, seed=1):
+    from trew_b200 import synth
+    with open(path, "wb") as f:
+        done = 0
+        while done < n_reads:
+            m = min(250_000, n_reads - done)
+            mat = synth.config_short(seed + done, m, READ_LEN, telomeric=SYNTH["tel_ppm"] / 1e6,
+                                     half_telomeric=SYNTH["half_ppm"] / 1e6, n_rate=SYNTH["n_ppm"] / 1e6,
+                                     sub=SYNTH["sub_ppm"] / 1e6)
+            f.write(synth.fastq_matrix_bytes(mat))
+            done += m
+
+
+def time_reference(sample_fastq, cores):
+    from oracle.oracle import REF_BIN
+    t0 = time.perf_counter()
+    subprocess.run([REF_BIN, "short", "5", "32", sample_fastq, "-t", str(cores), "-q", "1024"], check=True,
+                   stdout=subprocess.DEVNULL)
+    return time.perf_counter() - t0
+
+
+def reference_available():
+    from oracle.oracle import REF_BIN
+    return os.path.exists(REF_BIN)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    line = {"metric": METRIC, "unit": "Gbases/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "impl": "reference", "config": {"workload": workload_name(args.reads)}}
+    if not reference_available():
+        line["unavailable"] = "oracle/_ref/trew_ref missing (reference not compiled into this tree)"
+        print(json.dumps(line))
+        return
+    tmp = tempfile.mkdtemp(prefix="trew_ref_")
+    try:
+        # calibrate on 100k reads, then size the sample so warmup + steps stay within ~150 s
+        cal = os.path.join(tmp, "cal.fastq")
+        write_sample_fastq(cal, 100_000)
+        t_cal = max(time_reference(cal, cores) - 0.6, 0.05)  # ~0.6 s of table setup at -m 12
+        budget = 150.0 / max(1, args.steps + args.warmup)
+        n = int(min(2_000_000, max(100_000, 100_000 * budget / t_cal)))
+        sample = os.path.join(tmp, "sample.fastq")
+        write_sample_fastq(sample, n)
+        for _ in range(args.warmup):
+            time_reference(sample, cores)
+        times = [time_reference(sample, cores) for _ in range(args.steps)]
+        total = sum(times)
+        value = n * READ_LEN * len(times) / total / 1e9
+        sample_desc = ("%d reads of the same distribution (numpy generator) as plain FASTQ, "
+                       "`trew_ref short 5 32 -t %d -q 1024`, wall clock" % (n, cores))
+        line.update({"value": value, "ms_per_step": 1e3 * total / len(times),
+                     "cpu_baseline": {"value": value, "unit": "Gbases/s", "cores": cores, "kind": "reference", "sample": sample_desc},
+                     "e2e": {"value": value, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "gpu_launches": 0})
+        print(json.dumps(line))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from trew_b200 import api, merge, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx = api.DeviceContext(api.MODE_SHORT, 5, 32, device=local_rank, n_staging=3, staging_bytes=96 << 20)
+
+    # ---- device-resident workload: weak scaling, every rank holds args.reads reads -------------------
+    handles, reads_left, i = [], args.reads, 0
+    while reads_left > 0:
+        n = min(BATCH_READS, reads_left)
+        handles.append((ctx.synth_resident(1 + 1000 * rank + i, n, READ_LEN, **SYNTH), n))
+        reads_left -= n
+        i += 1
+    bases_per_rank = args.reads * READ_LEN
+
+    merged_last = [None]
+
+    def step():
+        ctx.reset()
+        for h, _ in handles:
+            ctx.scan_resident(h)
+        rows = ctx.finish_arrays()  # sync + compaction kernel + D2H of the tables
+        merged_last[0] = merge.merge_rows(rows, device)  # exact NCCL merge (identity at N = 1)
+
+    for _ in range(args.warmup):
+        step()
+    ctx.kernel_times()  # drop warm-up kernel times
+    launches0 = ctx.stats().kernel_launches
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.timer_start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dev_ms = ctx.timer_stop()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    if rank == 0:
+        sampler.stop_flag.set()
+    # finish() and the merge run on the host between the event pair, so the event time covers the step
+    ms = max_over_ranks(max(dev_ms, 0.0))
+    wall_ms = max_over_ranks(wall_ms)
+    filter_ms, exact_ms, n_scans = ctx.kernel_times()
+    st = ctx.stats()
+    launches = st.kernel_launches - launches0
+    value = world * bases_per_rank * args.steps / (ms * 1e-3) / 1e9
+
+    # ---- end to end through the C ABI with host buffers ----------------------------------------------
+    e2e_reads = args.e2e_reads
+    mat = synth.config_short(7 + rank, min(e2e_reads, 1_000_000), READ_LEN, telomeric=SYNTH["tel_ppm"] / 1e6,
+                             half_telomeric=SYNTH["half_ppm"] / 1e6, n_rate=SYNTH["n_ppm"] / 1e6, sub=SYNTH["sub_ppm"] / 1e6)
+    reps = max(1, e2e_reads // mat.shape[0])
+    buf, locs = api.matrix_chunk(mat)  # one raw chunk: sequences + (st, nd) offsets == the reference's QueueData
+    e2e_reads = reps * mat.shape[0]
+    h2d0, d2h0 = st.h2d_bytes, st.d2h_bytes
+
+    def e2e_step():
+        ctx.reset()
+        for _ in range(reps):
+            ctx.submit_chunk(buf, locs)
+        rows = ctx.finish_arrays()
+        return merge.merge_rows(rows, device)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_step()
+    st1 = ctx.stats()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    st2 = ctx.stats()
+    e2e_value = world * e2e_reads * READ_LEN * e2e_steps / e2e_s / 1e9
+
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        launches_per_scan = len(handles)
+        filt_avg_ms = filter_ms / max(1, n_scans)
+        reads_per_launch = args.reads / len(handles)
+        achieved = BYTES_PER_READ * reads_per_launch / (filt_avg_ms * 1e-3) / 1e9 if filt_avg_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload_name(args.reads), "min_mer": 5, "max_mer": 32, "low": 0.5, "high": 0.8,
+                       "batches_per_step": launches_per_scan, "reads_per_batch": BATCH_READS,
+                       "l2": "inputs (%.1f GB packed per pass) far exceed L2; no flush" % (BYTES_PER_READ * args.reads / 1e9),
+                       "parallelism": "reads sharded over %d GPU(s), exact NCCL table merge per step" % world},
+            "wall_ms_per_step": wall_ms / args.steps,
+            "gpu_launches": int(launches),
+            "kernel_share": {"filter_ms_per_step": filter_ms / args.steps, "exact_ms_per_step": exact_ms / args.steps,
+                             "survivor_fraction": st.survivors / max(1, st.units)},
+            "roofline": {"bound": "hbm", "kernel": "trew_filter_kernel<3>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_read": BYTES_PER_READ,
+                         "note": "integer-issue bound, not HBM bound: see DESIGN.md roofline section"},
+            "e2e": {"value": e2e_value, "unit": "Gbases/s", "h2d_bytes_per_step": int((st2.h2d_bytes - st1.h2d_bytes) / e2e_steps),
+                    "d2h_bytes_per_step": int((st2.d2h_bytes - st1.d2h_bytes) / e2e_steps),
+                    "reads_per_step": int(e2e_reads), "steps": e2e_steps,
+                    "path": "ASCII chunk (QueueData) -> trew_dev_submit_chunk -> trew_dev_finish"},
+            "clocks": sampler.summary(),
+        }
+        traffic = os.path.join(ROOT, "profiles", "filter_traffic.json")
+        if os.path.exists(traffic):
+            try:
+                line["roofline"]["traffic"] = json.load(open(traffic)).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+    for h, _ in handles:
+        ctx.free_resident(h)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline():
+    cores = os.cpu_count() or 1
+    if not reference_available():
+        return {"value": None, "unit": "Gbases/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref not built"}
+    tmp = tempfile.mkdtemp(prefix="trew_cpu_")
+    try:
+        n = 120_000 * cores  # ~15-25 s of CPU work at ~0.8 Mbases per core-second
+        p = os.path.join(tmp, "sample.fastq")
+        write_sample_fastq(p, n)
+        t = time_reference(p, cores)
+        return {"value": n * READ_LEN / t / 1e9, "unit": "Gbases/s", "cores": cores, "kind": "reference",
+                "sample": "%d reads of the same distribution (numpy generator) as plain FASTQ, `trew_ref short 5 32 -t %d -q 1024` "
+                          "(unmodified reference sources + shim containers), wall clock %.1f s" % (n, cores, t)}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=200_000_000, help="reads per GPU held resident (configs[1]: 200 M)")
+    ap.add_argument("--e2e-reads", type=int, default=8_000_000, help="reads per end-to-end step (host buffers)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -142,6 +142,21 @@ void trew_dev_free_resident(trew_ctx* ctx, trew_resident* batch);
 /* CUDA-event time (ms) of the last trew_dev_scan_resident; waits for it to complete. */
 int trew_dev_last_resident_ms(trew_ctx* ctx, float* ms);
 
+/* Benchmark tooling: fill a device-resident batch with synthetic fixed-length reads of BASELINE.json's
+ * configs[1] shape (uniform ACGT; tel_ppm of the reads (TTAGGG)^n at random phase, half of them
+ * reverse-complemented, sub_ppm per-base substitutions; half_ppm reads telomeric in one half only; n_ppm of
+ * all bases invalid).  Counter-based generator, mirrored bit-for-bit by trew_b200/synth.py:device_mirror so
+ * parity can be checked on small n.  Not part of the scan path. */
+int trew_synth_resident(trew_ctx* ctx, uint64_t seed, uint32_t n_reads, uint32_t read_len, uint32_t tel_ppm,
+                        uint32_t half_ppm, uint32_t n_ppm, uint32_t sub_ppm, trew_resident** out);
+
+/* CUDA-event stopwatch on the context's scan stream (for device-resident scans). */
+int trew_dev_timer_start(trew_ctx* ctx);
+int trew_dev_timer_stop(trew_ctx* ctx, float* ms); /* waits for the stream */
+/* Per-kernel CUDA-event times accumulated over resident scans since the last call: filter, exact (ms),
+ * and the number of scans they cover. */
+int trew_dev_kernel_times(trew_ctx* ctx, double* filter_ms, double* exact_ms, uint64_t* n_scans);
+
 /* ---- output: the ResultMapData side (src/kmer.h:79-81, src/kmer.cpp:1486-1515) ------------------ */
 
 /* Wait for all submitted work (end-of-stream; replaces the {nullptr,nullptr} sentinels,

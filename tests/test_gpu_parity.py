@@ -133,3 +133,22 @@ def test_full_shape_properties():
         assert a.get(key) == v
     extra = {k: v for k, v in a.items() if k not in b}
     assert sum(extra.values()) <= 0.02 * sum(a.values())
+
+
+def test_device_generator_matches_numpy_mirror():
+    """bench.py scans batches generated on the GPU (trew_synth_resident); the numpy mirror reproduces them
+    bit for bit, so the oracle can check the very reads the benchmark times (small n here)."""
+    from oracle.oracle import Oracle
+    n = 30_000
+    kw = dict(tel_ppm=30000, half_ppm=20000, n_ppm=2000, sub_ppm=10000)
+    with api.DeviceContext(api.MODE_SHORT, 5, 32) as ctx:
+        h = ctx.synth_resident(5, n, 150, **kw)
+        ctx.scan_resident(h)
+        got = ctx.finish()
+        f_ms, e_ms, scans = ctx.kernel_times()
+        ctx.free_resident(h)
+    assert scans == 1 and f_ms > 0 and e_ms > 0
+    mat = synth.device_mirror(5, n, 150, **kw)
+    want = Oracle(5, 32).scan(0, [bytes(r) for r in mat])
+    assert got == want, diff_msg(got, want)
+    assert len(got) > 50

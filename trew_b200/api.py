@@ -62,6 +62,7 @@ ABI_SYMBOLS = [
     "trew_dev_submit_chunk", "trew_dev_submit_packed", "trew_dev_upload", "trew_dev_scan_resident",
     "trew_dev_free_resident", "trew_dev_last_resident_ms", "trew_dev_sync", "trew_dev_finish",
     "trew_dev_export_device", "trew_dev_reset", "trew_dev_get_stats", "trew_pack_bound", "trew_pack_reads",
+    "trew_synth_resident", "trew_dev_timer_start", "trew_dev_timer_stop", "trew_dev_kernel_times",
     "trew_dev_process_file", "trew_ingest_file", "trew_report_create", "trew_report_destroy", "trew_report_add_file",
     "trew_report_finish",
 ]
@@ -104,6 +105,11 @@ def load_library() -> C.CDLL:
     L.trew_pack_bound.restype = C.c_size_t
     L.trew_pack_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(Batch)]
     L.trew_dev_process_file.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    L.trew_synth_resident.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                      C.c_uint32, C.POINTER(C.c_void_p)]
+    L.trew_dev_timer_start.argtypes = [C.c_void_p]
+    L.trew_dev_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.trew_dev_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.trew_ingest_file.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_uint64, CHUNK_SINK,
                                    C.c_void_p, C.c_char_p, C.c_size_t]
     L.trew_report_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
@@ -249,6 +255,26 @@ class DeviceContext:
     def free_resident(self, handle) -> None:
         self.lib.trew_dev_free_resident(self.ctx, handle)
 
+    def synth_resident(self, seed: int, n_reads: int, read_len: int = 150, tel_ppm: int = 10000, half_ppm: int = 2000,
+                       n_ppm: int = 1000, sub_ppm: int = 10000):
+        h = C.c_void_p()
+        self._check(self.lib.trew_synth_resident(self.ctx, seed, n_reads, read_len, tel_ppm, half_ppm, n_ppm, sub_ppm,
+                                                 C.byref(h)))
+        return h
+
+    def timer_start(self) -> None:
+        self._check(self.lib.trew_dev_timer_start(self.ctx))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self._check(self.lib.trew_dev_timer_stop(self.ctx, C.byref(ms)))
+        return ms.value
+
+    def kernel_times(self) -> Tuple[float, float, int]:
+        f, e, n = C.c_double(), C.c_double(), C.c_uint64()
+        self._check(self.lib.trew_dev_kernel_times(self.ctx, C.byref(f), C.byref(e), C.byref(n)))
+        return f.value, e.value, n.value
+
     def sync(self) -> None:
         self._check(self.lib.trew_dev_sync(self.ctx))
 
@@ -262,6 +288,23 @@ class DeviceContext:
         n = C.c_uint64()
         self._check(self.lib.trew_dev_finish(self.ctx, C.byref(p), C.byref(n)))
         return p, n.value
+
+    def finish_arrays(self) -> np.ndarray:
+        """The merged tables as an (n, 4) int64 array of rows (meta = table << 8 | k, seq_lo, seq_hi, count),
+        sorted by (table, k, seq).  64-bit fields are reinterpreted as signed."""
+        p, n = self.finish_entries()
+        if n == 0:
+            return np.zeros((0, 4), dtype=np.int64)
+        raw = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(n, 4)).copy()
+        out = np.empty((n, 4), dtype=np.uint64)
+        tk = raw[:, 3]
+        table = tk & np.uint64(0xffffffff)
+        k = tk >> np.uint64(32)
+        out[:, 0] = (table << np.uint64(8)) | k
+        out[:, 1] = raw[:, 0]
+        out[:, 2] = raw[:, 1]
+        out[:, 3] = raw[:, 2]
+        return out.view(np.int64)
 
     def finish(self) -> Tables:
         p, n = self.finish_entries()

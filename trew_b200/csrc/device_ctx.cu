@@ -45,6 +45,8 @@ struct trew_resident {
     unsigned int* d_counters = nullptr;
     unsigned char* d_scratch = nullptr;
     size_t scratch_bytes = 0;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // before filter, between, after exact
+    bool ev_pending = false;
 };
 
 struct trew_ctx {
@@ -69,6 +71,9 @@ struct trew_ctx {
     Pool* pool = nullptr;
     std::string err;
     std::vector<ReadRef> reads_tmp;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    double filter_ms = 0, exact_ms = 0; uint64_t n_prof_scans = 0;
+    std::vector<trew_resident*> pending_prof;
 };
 
 namespace {
@@ -115,7 +120,8 @@ size_t scratch_need(const trew_ctx* ctx, uint32_t max_read_len, unsigned int* st
 }
 
 int launch_scan(trew_ctx* ctx, const DevBatch& b, uint32_t n_units, uint32_t max_read_len, unsigned int* d_survivors,
-                unsigned int* d_counters, unsigned char** d_scratch, size_t* scratch_bytes, cudaStream_t st) {
+                unsigned int* d_counters, unsigned char** d_scratch, size_t* scratch_bytes, cudaStream_t st,
+                cudaEvent_t* ev = nullptr) {
     unsigned int stride;
     size_t need = scratch_need(ctx, max_read_len, &stride);
     if (need > *scratch_bytes) {
@@ -124,12 +130,15 @@ int launch_scan(trew_ctx* ctx, const DevBatch& b, uint32_t n_units, uint32_t max
         *scratch_bytes = need;
     }
     CK(cudaMemsetAsync(d_counters, 0, 2 * sizeof(unsigned int), st));
+    if (ev) CK(cudaEventRecord(ev[0], st));
     launch_filter(ctx->dcfg, b, n_units, max_read_len, d_survivors, d_counters, ctx->sm_count, st);
+    if (ev) CK(cudaEventRecord(ev[1], st));
     ExactArgs a{};
     a.survivors = d_survivors; a.n_survivors = d_counters; a.work_counter = d_counters + 1;
     a.slice_scratch = *d_scratch; a.slice_scratch_stride = stride; a.run_cap = run_cap_for(ctx->cfg, max_read_len);
     a.total_survivors = ctx->d_total_surv;
     launch_exact(ctx->dcfg, b, a, ctx->sm_count, st);
+    if (ev) CK(cudaEventRecord(ev[2], st));
     CK(cudaGetLastError());
     ctx->stats.kernel_launches += 2;
     return TREW_OK;
@@ -204,6 +213,21 @@ int submit_split(trew_ctx* ctx, const std::vector<ReadRef>& reads, uint32_t unit
         if (rc) return rc;
         i = j;
     }
+    return TREW_OK;
+}
+
+int collect_prof(trew_ctx* ctx) {
+    for (trew_resident* r : ctx->pending_prof) {
+        if (!r->ev_pending) continue;
+        CK(cudaEventSynchronize(r->ev[2]));
+        float a = 0, b = 0;
+        CK(cudaEventElapsedTime(&a, r->ev[0], r->ev[1]));
+        CK(cudaEventElapsedTime(&b, r->ev[1], r->ev[2]));
+        ctx->filter_ms += a; ctx->exact_ms += b; ctx->n_prof_scans++;
+        ctx->stats.device_ms += a + b;
+        r->ev_pending = false;
+    }
+    ctx->pending_prof.clear();
     return TREW_OK;
 }
 
@@ -283,6 +307,8 @@ int trew_dev_create(const trew_config* cfg, trew_ctx** out) {
     CKC(cudaStreamCreateWithFlags(&ctx->main_stream, cudaStreamNonBlocking));
     CKC(cudaEventCreate(&ctx->ev_a));
     CKC(cudaEventCreate(&ctx->ev_b));
+    CKC(cudaEventCreate(&ctx->ev_t0));
+    CKC(cudaEventCreate(&ctx->ev_t1));
     ctx->staging_bytes = cfg->staging_bytes ? (size_t)cfg->staging_bytes : ((size_t)64 << 20);
     int ns = cfg->n_staging > 0 ? cfg->n_staging : 3;
     ctx->slots.resize((size_t)ns);
@@ -329,6 +355,8 @@ void trew_dev_destroy(trew_ctx* ctx) {
     if (ctx->main_stream) cudaStreamDestroy(ctx->main_stream);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+    if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+    if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     delete ctx->pool;
     delete ctx;
 }
@@ -435,9 +463,12 @@ int trew_dev_scan_resident(trew_ctx* ctx, const trew_resident* rb) {
     if (!ctx || !rb) return TREW_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
     trew_resident* r = const_cast<trew_resident*>(rb);
+    if (r->ev_pending) { int rc0 = collect_prof(ctx); if (rc0) return rc0; }
+    if (!r->ev[0]) for (int i = 0; i < 3; i++) CK(cudaEventCreate(&r->ev[i]));
     CK(cudaEventRecord(ctx->ev_a, ctx->main_stream));
     int rc = launch_scan(ctx, r->batch, r->n_units, r->max_read_len, r->d_survivors, r->d_counters, &r->d_scratch,
-                         &r->scratch_bytes, ctx->main_stream);
+                         &r->scratch_bytes, ctx->main_stream, r->ev);
+    r->ev_pending = true; ctx->pending_prof.push_back(r);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev_b, ctx->main_stream));
     ctx->stats.reads += r->n_reads; ctx->stats.bases += r->bases; ctx->stats.units += r->n_units;
@@ -446,7 +477,8 @@ int trew_dev_scan_resident(trew_ctx* ctx, const trew_resident* rb) {
 
 void trew_dev_free_resident(trew_ctx* ctx, trew_resident* r) {
     if (!r) return;
-    if (ctx) { cudaSetDevice(ctx->cfg.device); cudaStreamSynchronize(ctx->main_stream); }
+    if (ctx) { cudaSetDevice(ctx->cfg.device); cudaStreamSynchronize(ctx->main_stream); collect_prof(ctx); }
+    for (int i = 0; i < 3; i++) if (r->ev[i]) cudaEventDestroy(r->ev[i]);
     if (r->d_buf) cudaFree(r->d_buf);
     if (r->d_survivors) cudaFree(r->d_survivors);
     if (r->d_counters) cudaFree(r->d_counters);
@@ -459,6 +491,7 @@ int trew_dev_sync(trew_ctx* ctx) {
     CK(cudaSetDevice(ctx->cfg.device));
     for (auto& s : ctx->slots) { int rc = retire_slot(ctx, s); if (rc) return rc; }
     CK(cudaStreamSynchronize(ctx->main_stream));
+    { int rc = collect_prof(ctx); if (rc) return rc; }
     return check_device_error(ctx);
 }
 
@@ -541,6 +574,59 @@ int trew_dev_last_resident_ms(trew_ctx* ctx, float* ms) {
     if (!ctx || !ms) return TREW_ERR_ARG;
     CK(cudaEventSynchronize(ctx->ev_b));
     CK(cudaEventElapsedTime(ms, ctx->ev_a, ctx->ev_b));
+    return TREW_OK;
+}
+
+int trew_dev_timer_start(trew_ctx* ctx) {
+    if (!ctx) return TREW_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    CK(cudaEventRecord(ctx->ev_t0, ctx->main_stream));
+    return TREW_OK;
+}
+
+int trew_dev_timer_stop(trew_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return TREW_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    CK(cudaEventRecord(ctx->ev_t1, ctx->main_stream));
+    CK(cudaEventSynchronize(ctx->ev_t1));
+    CK(cudaEventElapsedTime(ms, ctx->ev_t0, ctx->ev_t1));
+    return TREW_OK;
+}
+
+int trew_dev_kernel_times(trew_ctx* ctx, double* filter_ms, double* exact_ms, uint64_t* n_scans) {
+    if (!ctx) return TREW_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    CK(cudaStreamSynchronize(ctx->main_stream));
+    int rc = collect_prof(ctx);
+    if (rc) return rc;
+    if (filter_ms) *filter_ms = ctx->filter_ms;
+    if (exact_ms) *exact_ms = ctx->exact_ms;
+    if (n_scans) *n_scans = ctx->n_prof_scans;
+    ctx->filter_ms = ctx->exact_ms = 0; ctx->n_prof_scans = 0;
+    return TREW_OK;
+}
+
+int trew_synth_resident(trew_ctx* ctx, uint64_t seed, uint32_t n_reads, uint32_t read_len, uint32_t tel_ppm,
+                        uint32_t half_ppm, uint32_t n_ppm, uint32_t sub_ppm, trew_resident** out) {
+    if (!ctx || !out || read_len == 0 || (uint64_t)n_reads * read_len >= 0xfffff000ULL) return TREW_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    auto thr = [](uint32_t ppm) { return (unsigned int)(((unsigned long long)ppm << 32) / 1000000ULL); };
+    uint64_t bases = (uint64_t)n_reads * read_len;
+    size_t bytes = batch_bytes(n_reads, bases);
+    trew_resident* r = new trew_resident();
+    CK(cudaMalloc(&r->d_buf, bytes));
+    BatchView v;
+    batch_layout(r->d_buf, n_reads, bases, &v);
+    launch_synth(seed, n_reads, read_len, thr(tel_ppm), thr(half_ppm), thr(n_ppm), thr(sub_ppm), v.bit_off, v.hi, v.lo, v.val,
+                 v.plane_words, ctx->main_stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->main_stream));
+    r->batch.n_reads = n_reads; r->batch.bit_off = v.bit_off; r->batch.hi = v.hi; r->batch.lo = v.lo; r->batch.val = v.val;
+    r->n_reads = n_reads; r->n_units = ctx->cfg.mode == TREW_MODE_PAIR ? n_reads / 2 : n_reads;
+    r->max_read_len = read_len; r->bases = bases;
+    CK(cudaMalloc((void**)&r->d_survivors, (size_t)std::max<uint32_t>(r->n_units, 1) * sizeof(unsigned int)));
+    CK(cudaMalloc((void**)&r->d_counters, 2 * sizeof(unsigned int)));
+    *out = r;
     return TREW_OK;
 }
 

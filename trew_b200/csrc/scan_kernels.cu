@@ -97,6 +97,59 @@ void launch_compact(const Slot* slots, unsigned int n_slots, unsigned int* d_met
 }
 
 // ------------------------------------------------------------------------------------------------
+// synthetic batch generator (benchmark tooling; mirrored by trew_b200/synth.py:device_mirror)
+// ------------------------------------------------------------------------------------------------
+
+__host__ __device__ inline u32 synth_hash(u64 seed, u64 a, u64 b) {
+    u64 x = seed + 0x9e3779b97f4a7c15ULL * (a + 1) + 0xbf58476d1ce4e5b9ULL * (b + 1);
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL; x ^= x >> 27; x *= 0x94d049bb133111ebULL; x ^= x >> 31;
+    return (u32)(x >> 32);
+}
+
+__global__ void synth_kernel(u64 seed, u32 n_reads, u32 L, u32 tel_thr, u32 half_thr, u32 n_thr, u32 sub_thr,
+                             u32* __restrict__ bit_off, u32* __restrict__ hi, u32* __restrict__ lo, u32* __restrict__ val,
+                             size_t plane_words) {
+    const u64 total = (u64)n_reads * L;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n_reads; i += stride) bit_off[i] = (u32)(i * L);
+    // codes T=0 G=1 C=2 A=3; TTAGGG and its reverse complement CCCTAA as code strings
+    const int unit_f[6] = {0, 0, 3, 1, 1, 1};
+    const int unit_r[6] = {2, 2, 2, 0, 3, 3};
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < plane_words; w += stride) {
+        u32 h = 0, l = 0, v = 0;
+        for (int b = 0; b < 32; b++) {
+            u64 pos = (u64)w * 32 + b;
+            if (pos >= total) break;
+            u64 r = pos / L; u32 j = (u32)(pos % L);
+            u32 kind = synth_hash(seed, r, 0xffffffffULL);
+            u32 aux = synth_hash(seed, r, 0xfffffffeULL);
+            u32 code = synth_hash(seed, r, j) & 3u;
+            bool tel = kind < tel_thr;
+            bool halfk = !tel && kind < tel_thr + half_thr;
+            if (halfk) tel = ((aux >> 8) & 1u) ? (j < L / 2) : (j >= L / 2);
+            if (tel) {
+                u32 phase = aux % 6u;
+                bool rc = (aux >> 4) & 1u;
+                u32 idx = (j + phase) % 6u;
+                u32 c = rc ? unit_r[idx] : unit_f[idx];
+                u32 sh = synth_hash(seed ^ 0x5555555555555555ULL, r, j);
+                code = sh < sub_thr ? (sh >> 3) & 3u : c;   // note: sh < sub_thr keeps (sh >> 3) & 3 uniform enough
+            }
+            bool inval = synth_hash(seed ^ 0xaaaaaaaaaaaaaaaaULL, r, j) < n_thr;
+            if (!inval) { v |= 1u << b; h |= (code >> 1) << b; l |= (code & 1u) << b; }
+        }
+        hi[w] = h; lo[w] = l; val[w] = v;
+    }
+}
+
+void launch_synth(unsigned long long seed, unsigned int n_reads, unsigned int read_len, unsigned int tel_thr,
+                  unsigned int half_thr, unsigned int n_thr, unsigned int sub_thr, unsigned int* bit_off, unsigned int* hi,
+                  unsigned int* lo, unsigned int* val, size_t plane_words, cudaStream_t stream) {
+    synth_kernel<<<1184, 256, 0, stream>>>(seed, n_reads, read_len, tel_thr, half_thr, n_thr, sub_thr, bit_off, hi, lo, val,
+                                            plane_words);
+}
+
+// ------------------------------------------------------------------------------------------------
 // probe windows: the first windows the reference's routing scans for a unit.  If none of them can
 // produce a target k, the unit emits nothing ("Why the filter is sound").
 // ------------------------------------------------------------------------------------------------

@@ -66,4 +66,8 @@ int exact_warps_total(int sm_count);
 void launch_compact(const Slot* slots, unsigned int n_slots, unsigned int* d_meta, unsigned long long* d_seq,
                     unsigned long long* d_count, unsigned int* d_n, cudaStream_t stream);
 
+void launch_synth(unsigned long long seed, unsigned int n_reads, unsigned int read_len, unsigned int tel_thr,
+                  unsigned int half_thr, unsigned int n_thr, unsigned int sub_thr, unsigned int* bit_off, unsigned int* hi,
+                  unsigned int* lo, unsigned int* val, size_t plane_words, cudaStream_t stream);
+
 }  // namespace trew

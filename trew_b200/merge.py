@@ -1,0 +1,62 @@
+"""Exact cross-rank merge of the per-GPU count tables -- the multi-GPU analogue of the reference's serial
+map merge in process_output (src/kmer.cpp:1486-1515): element-wise sum of the six (k, seq) -> count maps.
+
+Per-GPU open-addressing tables are not slot-aligned, so the tables cannot be reduced in place.  Recipe
+(SURVEY.md 5.8): all_gather the compacted keys -> identical sorted union on every rank -> dense count
+vectors aligned to the union -> reduce(SUM) to rank 0.  Integer sums are order-independent, so the result
+is bit-exact.  torch.distributed is the plumbing (NCCL over NVLink on GPUs, gloo in the CPU tests); there
+is no data-path collective besides this end-of-file exchange.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def tables_to_rows(tables) -> np.ndarray:
+    """{(table, k, seq): count} -> (n, 4) int64 rows (meta, seq_lo, seq_hi, count)."""
+    rows = np.zeros((len(tables), 4), dtype=np.uint64)
+    for i, ((tb, k, seq), c) in enumerate(sorted(tables.items())):
+        rows[i] = ((tb << 8) | k, seq & (2 ** 64 - 1), seq >> 64, c)
+    return rows.view(np.int64)
+
+
+def rows_to_tables(rows: np.ndarray):
+    r = rows.view(np.uint64)
+    return {(int(m) >> 8, int(m) & 0xff, (int(hi) << 64) | int(lo)): int(c) for m, lo, hi, c in r}
+
+
+def merge_rows(rows: np.ndarray, device: torch.device, dst: int = 0) -> Optional[np.ndarray]:
+    """Sum the per-rank row sets by key.  Returns the merged rows on rank `dst`, None elsewhere."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return rows
+    world = dist.get_world_size()
+    local = torch.from_numpy(np.ascontiguousarray(rows)).to(device)
+    n_local = torch.tensor([local.shape[0]], dtype=torch.int64, device=device)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(sizes, n_local)
+    sizes = [int(s.item()) for s in sizes]
+    n_max = max(max(sizes), 1)
+    padded = torch.zeros((n_max, 3), dtype=torch.int64, device=device)
+    padded[: local.shape[0]] = local[:, :3]
+    gathered = [torch.zeros((n_max, 3), dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(gathered, padded)
+    keys = torch.cat([g[:s] for g, s in zip(gathered, sizes)], dim=0)
+    if keys.shape[0] == 0:
+        return np.zeros((0, 4), dtype=np.int64) if dist.get_rank() == dst else None
+    union, inverse = torch.unique(keys, dim=0, return_inverse=True)  # sorted, identical on every rank
+    start = sum(sizes[: dist.get_rank()])
+    mine = inverse[start:start + local.shape[0]]
+    dense = torch.zeros(union.shape[0], dtype=torch.int64, device=device)
+    dense.index_add_(0, mine, local[:, 3])
+    dist.reduce(dense, dst=dst, op=dist.ReduceOp.SUM)
+    if dist.get_rank() != dst:
+        return None
+    out = torch.cat([union, dense[:, None]], dim=1).cpu().numpy()
+    # torch.unique sorts signed; re-sort as unsigned (table, k, seq_hi, seq_lo) like trew_dev_finish
+    u = out.view(np.uint64)
+    order = np.lexsort((u[:, 1], u[:, 2], u[:, 0]))
+    return out[order]

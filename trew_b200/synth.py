@@ -286,3 +286,51 @@ def fastq_matrix_bytes(mat: np.ndarray) -> bytes:
     rec[:, 6 + L:6 + 2 * L] = ord("I")
     rec[:, 6 + 2 * L] = 10
     return rec.tobytes()
+
+
+# ---------------------------------------------------------------------------------------------
+# numpy mirror of the device-side generator (trew_synth_resident / synth_kernel in scan_kernels.cu)
+# ---------------------------------------------------------------------------------------------
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _synth_hash(seed: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        x = (np.uint64(seed) + np.uint64(0x9e3779b97f4a7c15) * (a.astype(np.uint64) + np.uint64(1))
+             + np.uint64(0xbf58476d1ce4e5b9) * (b.astype(np.uint64) + np.uint64(1)))
+        x ^= x >> np.uint64(30)
+        x *= np.uint64(0xbf58476d1ce4e5b9)
+        x ^= x >> np.uint64(27)
+        x *= np.uint64(0x94d049bb133111eb)
+        x ^= x >> np.uint64(31)
+    return (x >> np.uint64(32)).astype(np.uint32)
+
+
+def device_mirror(seed: int, n_reads: int, read_len: int = 150, tel_ppm: int = 10000, half_ppm: int = 2000,
+                  n_ppm: int = 1000, sub_ppm: int = 10000) -> np.ndarray:
+    """The exact reads trew_synth_resident() generates on the GPU, as an n_reads x read_len ASCII matrix."""
+    thr = lambda ppm: np.uint64((ppm << 32) // 1000000)
+    L = read_len
+    r = np.repeat(np.arange(n_reads, dtype=np.uint64), L).reshape(n_reads, L)
+    j = np.tile(np.arange(L, dtype=np.uint64), n_reads).reshape(n_reads, L)
+    kind = _synth_hash(seed, r[:, :1], np.full((n_reads, 1), 0xffffffff, dtype=np.uint64)).astype(np.uint64)
+    aux = _synth_hash(seed, r[:, :1], np.full((n_reads, 1), 0xfffffffe, dtype=np.uint64))
+    code = _synth_hash(seed, r, j) & np.uint32(3)
+    tel = np.broadcast_to(kind < thr(tel_ppm), (n_reads, L)).copy()
+    halfk = (~(kind < thr(tel_ppm))) & (kind < thr(tel_ppm) + thr(half_ppm))
+    left = ((aux >> np.uint32(8)) & np.uint32(1)) == 1
+    in_half = np.where(left, j < np.uint64(L // 2), j >= np.uint64(L // 2))
+    tel = np.where(halfk, in_half, tel)
+    phase = (aux % np.uint32(6)).astype(np.uint64)
+    rc = ((aux >> np.uint32(4)) & np.uint32(1)) == 1
+    idx = ((j + phase) % np.uint64(6)).astype(np.int64)
+    unit_f = np.array([0, 0, 3, 1, 1, 1], dtype=np.uint32)
+    unit_r = np.array([2, 2, 2, 0, 3, 3], dtype=np.uint32)
+    c = np.where(rc, unit_r[idx], unit_f[idx])
+    sh = _synth_hash(seed ^ 0x5555555555555555, r, j)
+    tcode = np.where(sh.astype(np.uint64) < thr(sub_ppm), (sh >> np.uint32(3)) & np.uint32(3), c)
+    code = np.where(tel, tcode, code)
+    inval = _synth_hash(seed ^ 0xaaaaaaaaaaaaaaaa, r, j).astype(np.uint64) < thr(n_ppm)
+    letters = np.frombuffer(b"TGCA", dtype=np.uint8)[code.astype(np.int64)]
+    return np.where(inval, np.uint8(ord("N")), letters).astype(np.uint8)
