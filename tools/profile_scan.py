@@ -1,0 +1,26 @@
+#!/usr/bin/env python3
+"""Small driver for ncu: one device-resident batch of the configs[1] shape, scanned a few times.
+
+    python tools/profile_scan.py [reads] [scans] [min_mer] [max_mer]
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from trew_b200 import api  # noqa: E402
+
+reads = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
+scans = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+mn = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+mx = int(sys.argv[4]) if len(sys.argv) > 4 else 32
+with api.DeviceContext(api.MODE_SHORT, mn, mx) as ctx:
+    h = ctx.synth_resident(1, reads, 150, tel_ppm=10000, half_ppm=2000, n_ppm=1000, sub_ppm=10000)
+    for _ in range(scans):
+        ctx.scan_resident(h)
+    ctx.sync()
+    f, e, n = ctx.kernel_times()
+    st = ctx.stats()
+    print("reads %d scans %d filter %.3f ms/scan exact %.3f ms/scan survivors %.4f" %
+          (reads, n, f / n, e / n, st.survivors / st.units))
+    ctx.free_resident(h)

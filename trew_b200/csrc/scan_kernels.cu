@@ -719,41 +719,51 @@ __device__ void emit_classes(const DevCfg& cfg, Warp& w, int k, int nruns, int t
     __syncwarp();
 }
 
-__device__ __forceinline__ bool divides_any(u64 acc, int k) {
-    while (acc) {
-        int t = __ffsll((long long)acc) - 1;
-        acc &= acc - 1;
-        if (k % t == 0) return true;
-    }
-    return false;
+// bit j set for every multiple j of k, j <= 64 (bit 64 does not exist: k = 64 is never a proper divisor target)
+__device__ __forceinline__ u64 multiples_mask(int k) {
+    u64 m = 0;
+    for (int j = k; j < 64; j += k) m |= 1ULL << j;
+    return m;
 }
 
 // k_mer_check / k_mer_check_128 (src/kmer.cpp:2144-2547) without emission: target_k_high / target_k_low and
 // the K_MER_DATA_MAX_SEQ of each.  Periods that cannot be accepted by either selection (divisor rule,
 // or the signature bound below the running threshold) are skipped without an exact count.
+//
+// Pre-test soundness: the reference accepts k iff fl(M/T) >= need.  fl(M/T) >= need implies
+// M >= need*T*(1 - 2^-53), and U >= M, so "U >= need*T*(1 - 1e-12)" (evaluated in double, relative error
+// ~2^-52) never rejects a period the reference would accept.  The exact test after eval_k uses the same
+// IEEE division as the reference.
 __device__ ScanRes scan_stats(const DevCfg& cfg, Warp& w, const DevBatch& b, u32 pos, int len, int kmin, int kmax) {
     ScanRes res; res.th = res.tl = 0; res.sh_lo = res.sh_hi = res.sl_lo = res.sl_hi = 0;
     if (kmax < kmin) return res;
     load_window(w, b, pos, len);
     u32 wv = wv_for_k(w, kmin);
-    u64 accL = 0, accH = 0;
-    double tfL = 0.0, tfH = 0.0;
+    u64 blockedL = 0, blockedH = 0;   // periods with an accepted divisor (k % tk == 0, src/kmer.cpp:2225-2230)
+    bool blk64L = false, blk64H = false;
+    double needL = cfg.low, needH = cfg.high;  // max(baseline, last accepted frequency)
+    const double slack = 1.0 - 1e-12;
     for (int k = kmin; k <= kmax; k++, wv = wv_step(wv, w.lane)) {
-        bool blkL = divides_any(accL, k), blkH = divides_any(accH, k);
+        bool blkL = k < 64 ? ((blockedL >> k) & 1ULL) != 0 : blk64L;
+        bool blkH = k < 64 ? ((blockedH >> k) & 1ULL) != 0 : blk64H;
         if (blkL && blkH) continue;
         int T = (int)__reduce_add_sync(0xffffffffu, (u32)__popc(wv));
         if (T == 0) continue;
-        double needL = fmax(cfg.low, tfL), needH = fmax(cfg.high, tfH);
         int U = bound_k(w, k, wv, T);
-        double fU = (double)U / (double)T;
-        bool candL = !blkL && fU >= needL, candH = !blkH && fU >= needH;
+        double dU = (double)U, dT = (double)T;
+        bool candL = !blkL && dU >= needL * dT * slack, candH = !blkH && dU >= needH * dT * slack;
         if (!candL && !candH) continue;
         KStat ks = eval_k(w, k, wv);
         w.ev = ks; w.ev_pos = pos; w.ev_len = len; w.ev_k = k;
         if (ks.homo) continue;
         double f = (double)ks.M / (double)ks.T;
-        if (!blkL && f >= needL) { res.tl = k; tfL = f; accL |= 1ULL << k; res.sl_lo = ks.s_lo; res.sl_hi = ks.s_hi; }
-        if (!blkH && f >= needH) { res.th = k; tfH = f; accH |= 1ULL << k; res.sh_lo = ks.s_lo; res.sh_hi = ks.s_hi; }
+        bool accL = !blkL && f >= needL, accH = !blkH && f >= needH;
+        if (accL || accH) {
+            u64 mm = multiples_mask(k);
+            bool m64 = (64 % k) == 0;
+            if (accL) { res.tl = k; needL = f; blockedL |= mm; blk64L |= m64; res.sl_lo = ks.s_lo; res.sl_hi = ks.s_hi; }
+            if (accH) { res.th = k; needH = f; blockedH |= mm; blk64H |= m64; res.sh_lo = ks.s_lo; res.sh_hi = ks.s_hi; }
+        }
     }
     return res;
 }
@@ -1004,7 +1014,8 @@ __global__ void __launch_bounds__(kExactWarps * 32) trew_exact_kernel(DevCfg cfg
     }
 }
 
-int exact_warps_total(int sm_count) { return sm_count * 4 * kExactWarps; }
+constexpr int kExactBlocksPerSM = 5;
+int exact_warps_total(int sm_count) { return sm_count * kExactBlocksPerSM * kExactWarps; }
 
 cudaError_t prepare_exact(int run_cap_max) {
     return cudaFuncSetAttribute(trew_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1013,7 +1024,7 @@ cudaError_t prepare_exact(int run_cap_max) {
 
 void launch_exact(const DevCfg& cfg, const DevBatch& b, const ExactArgs& a, int sm_count, cudaStream_t stream) {
     size_t smem = exact_smem_bytes(a.run_cap, true);
-    trew_exact_kernel<<<sm_count * 4, kExactWarps * 32, smem, stream>>>(cfg, b, a);
+    trew_exact_kernel<<<sm_count * kExactBlocksPerSM, kExactWarps * 32, smem, stream>>>(cfg, b, a);
 }
 
 }  // namespace trew
