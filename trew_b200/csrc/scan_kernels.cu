@@ -49,7 +49,7 @@ __device__ __forceinline__ u64 mix64(u64 x) {
 // (stands in for the per-worker ResultMap objects, src/kmer.h:79-81)
 // ------------------------------------------------------------------------------------------------
 
-__device__ void table_add(const DevCfg& cfg, u32 meta, u64 lo, u64 hi, u64 cnt) {
+__device__ __noinline__ void table_add(const DevCfg& cfg, u32 meta, u64 lo, u64 hi, u64 cnt) {
     u64 h = mix64(lo ^ mix64(hi + 0x9e3779b97f4a7c15ULL * (u64)(meta + 1)));
     u32 i = (u32)h & cfg.slot_mask;
     for (u32 probe = 0; probe <= cfg.slot_mask; probe++, i = (i + 1) & cfg.slot_mask) {
@@ -444,7 +444,7 @@ struct ScanRes { int th, tl; u64 sh_lo, sh_hi, sl_lo, sl_hi; };
 
 // ---- k-mer arithmetic (src/kmer.cpp:39-74, 1815-1867) ------------------------------------------
 
-__device__ __forceinline__ u64 canon64(u64 w, int k) {
+__device__ __noinline__ u64 canon64(u64 w, int k) {
     u64 best = w, cur = w;
     int sh = 2 * (k - 1);
     for (int r = 1; r < k; r++) {
@@ -454,7 +454,7 @@ __device__ __forceinline__ u64 canon64(u64 w, int k) {
     return best;
 }
 
-__device__ __forceinline__ u128 canon128(u128 w, int k) {
+__device__ __noinline__ u128 canon128(u128 w, int k) {
     u128 best = w, cur = w;
     int sh = 2 * (k - 1);
     for (int r = 1; r < k; r++) {
@@ -514,7 +514,7 @@ __device__ __forceinline__ u32 shfl_next_bit0(u32 x, u32 lane) {  // bit 0 of th
 }
 
 // load window [pos, pos+len) of the batch planes; builds prefix-XOR planes and the reversed 2-bit stream
-__device__ void load_window(Warp& w, const DevBatch& b, u32 pos, int len) {
+__device__ __noinline__ void load_window(Warp& w, const DevBatch& b, u32 pos, int len) {
     if (w.cur_len == len && w.cur_pos == pos) return;
     __syncwarp();
     const u32 lane = w.lane;
@@ -620,7 +620,7 @@ __device__ __forceinline__ int bound_k(const Warp& w, int k, u32 wv, int T) {
 // src/kmer.cpp:2183-2216, without the early break): T valid windows, M largest class, S the class that
 // first reaches M.  Leaves the run list in shared memory (run_lo/hi canonical class per run, run_total
 // class total on the first run of each class) for emit_classes().
-__device__ KStat eval_k(Warp& w, int k, u32 wv) {
+__device__ __noinline__ KStat eval_k(Warp& w, int k, u32 wv) {
     KStat ks; ks.T = 0; ks.M = 0; ks.s_lo = ks.s_hi = 0; ks.homo = false; ks.nruns = 0;
     const u32 lane = w.lane;
     int T = (int)__reduce_add_sync(0xffffffffu, (u32)__popc(wv));
@@ -703,7 +703,7 @@ __device__ KStat eval_k(Warp& w, int k, u32 wv) {
 }
 
 // add every distinct class of the last eval_k() to a result table (optionally RC-folded)
-__device__ void emit_classes(const DevCfg& cfg, Warp& w, int k, int nruns, int table, bool folded) {
+__device__ __noinline__ void emit_classes(const DevCfg& cfg, Warp& w, int k, int nruns, int table, bool folded) {
     u32 meta = ((u32)table << 8) | (u32)k;
     for (int q = w.lane; q < nruns; q += 32) {
         int total = w.m.run_total[q];
@@ -734,42 +734,101 @@ __device__ __forceinline__ u64 multiples_mask(int k) {
 // M >= need*T*(1 - 2^-53), and U >= M, so "U >= need*T*(1 - 1e-12)" (evaluated in double, relative error
 // ~2^-52) never rejects a period the reference would accept.  The exact test after eval_k uses the same
 // IEEE division as the reference.
-__device__ ScanRes scan_stats(const DevCfg& cfg, Warp& w, const DevBatch& b, u32 pos, int len, int kmin, int kmax) {
-    ScanRes res; res.th = res.tl = 0; res.sh_lo = res.sh_hi = res.sl_lo = res.sl_hi = 0;
-    if (kmax < kmin) return res;
+struct SelState {
+    ScanRes res;
+    u64 blockedL, blockedH;   // periods with an accepted divisor (k % tk == 0, src/kmer.cpp:2225-2230)
+    bool blk64L, blk64H;
+    double needL, needH;      // max(baseline, last accepted frequency)
+};
+
+// one exact evaluation + the two acceptance tests of src/kmer.cpp:2221-2258
+__device__ __noinline__ void consider(Warp& w, SelState& st, u32 pos, int len, int k, u32 wv) {
+    KStat ks = eval_k(w, k, wv);
+    w.ev = ks; w.ev_pos = pos; w.ev_len = len; w.ev_k = k;
+    if (ks.homo) return;
+    bool blkL = k < 64 ? ((st.blockedL >> k) & 1ULL) != 0 : st.blk64L;
+    bool blkH = k < 64 ? ((st.blockedH >> k) & 1ULL) != 0 : st.blk64H;
+    double f = (double)ks.M / (double)ks.T;
+    bool accL = !blkL && f >= st.needL, accH = !blkH && f >= st.needH;
+    if (accL || accH) {
+        u64 mm = multiples_mask(k);
+        bool m64 = (64 % k) == 0;
+        if (accL) { st.res.tl = k; st.needL = f; st.blockedL |= mm; st.blk64L |= m64; st.res.sl_lo = ks.s_lo; st.res.sl_hi = ks.s_hi; }
+        if (accH) { st.res.th = k; st.needH = f; st.blockedH |= mm; st.blk64H |= m64; st.res.sh_lo = ks.s_lo; st.res.sh_hi = ks.s_hi; }
+    }
+}
+
+__device__ __noinline__ ScanRes scan_stats(const DevCfg& cfg, Warp& w, const DevBatch& b, u32 pos, int len, int kmin, int kmax) {
+    SelState st;
+    st.res.th = st.res.tl = 0; st.res.sh_lo = st.res.sh_hi = st.res.sl_lo = st.res.sl_hi = 0;
+    if (kmax < kmin) return st.res;
     load_window(w, b, pos, len);
-    u32 wv = wv_for_k(w, kmin);
-    u64 blockedL = 0, blockedH = 0;   // periods with an accepted divisor (k % tk == 0, src/kmer.cpp:2225-2230)
-    bool blk64L = false, blk64H = false;
-    double needL = cfg.low, needH = cfg.high;  // max(baseline, last accepted frequency)
+    st.blockedL = st.blockedH = 0; st.blk64L = st.blk64H = false;
+    st.needL = cfg.low; st.needH = cfg.high;
     const double slack = 1.0 - 1e-12;
-    for (int k = kmin; k <= kmax; k++, wv = wv_step(wv, w.lane)) {
-        bool blkL = k < 64 ? ((blockedL >> k) & 1ULL) != 0 : blk64L;
-        bool blkH = k < 64 ? ((blockedH >> k) & 1ULL) != 0 : blk64H;
+    const u32 lane = w.lane;
+
+    const bool all_valid = (int)__reduce_add_sync(0xffffffffu, (u32)__popc(w.v)) == len;
+    if (all_valid) {
+        // No invalid base: the valid windows of period k are exactly positions [0, len - k], so every lane
+        // can bound its own period (lane <-> k) without any cross-lane traffic; only the few periods whose
+        // bound reaches the LOW threshold are then visited in ascending order.
+        for (int kb = kmin; kb <= kmax; kb += 32) {
+            const int k = kb + (int)lane;
+            const int T = len - k + 1;
+            int U = 0;
+            if (k <= kmax && T > 0) {
+                const int s = k >> 5, r = k & 31;
+                int cH = 0, cL = 0, c11 = 0;
+                for (int j = 0; j * 32 < T; j++) {
+                    u32 wvj = low_mask(min(32, T - 32 * j));
+                    u32 dh = (__funnelshift_r(w.m.PH[j + s], w.m.PH[j + s + 1], r) ^ w.m.PH[j]) & wvj;
+                    u32 dl = (__funnelshift_r(w.m.PL[j + s], w.m.PL[j + s + 1], r) ^ w.m.PL[j]) & wvj;
+                    cH += __popc(dh); cL += __popc(dl); c11 += __popc(dh & dl);
+                }
+                int c10 = cH - c11, c01 = cL - c11, c00 = T - cH - cL + c11;
+                U = max(max(c00, c01), max(c10, c11));
+            }
+            bool cand = k <= kmax && T > 0 && (double)U >= cfg.low * (double)T * slack;
+            u32 cm = __ballot_sync(0xffffffffu, cand);
+            while (cm) {
+                int bit = __ffs(cm) - 1;
+                cm &= cm - 1;
+                int kk = kb + bit;
+                bool blkL = kk < 64 ? ((st.blockedL >> kk) & 1ULL) != 0 : st.blk64L;
+                bool blkH = kk < 64 ? ((st.blockedH >> kk) & 1ULL) != 0 : st.blk64H;
+                if (blkL && blkH) continue;
+                int Uk = __shfl_sync(0xffffffffu, U, bit);
+                int Tk = len - kk + 1;
+                double dU = (double)Uk, dT = (double)Tk;
+                bool candL = !blkL && dU >= st.needL * dT * slack, candH = !blkH && dU >= st.needH * dT * slack;
+                if (!candL && !candH) continue;
+                int vb = Tk - 32 * (int)lane;
+                consider(w, st, pos, len, kk, vb <= 0 ? 0u : low_mask(min(32, vb)));
+            }
+        }
+        return st.res;
+    }
+
+    // windows with invalid bases: walk the periods in order, keeping the window-valid mask incrementally
+    u32 wv = wv_for_k(w, kmin);
+    for (int k = kmin; k <= kmax; k++, wv = wv_step(wv, lane)) {
+        bool blkL = k < 64 ? ((st.blockedL >> k) & 1ULL) != 0 : st.blk64L;
+        bool blkH = k < 64 ? ((st.blockedH >> k) & 1ULL) != 0 : st.blk64H;
         if (blkL && blkH) continue;
         int T = (int)__reduce_add_sync(0xffffffffu, (u32)__popc(wv));
         if (T == 0) continue;
         int U = bound_k(w, k, wv, T);
         double dU = (double)U, dT = (double)T;
-        bool candL = !blkL && dU >= needL * dT * slack, candH = !blkH && dU >= needH * dT * slack;
+        bool candL = !blkL && dU >= st.needL * dT * slack, candH = !blkH && dU >= st.needH * dT * slack;
         if (!candL && !candH) continue;
-        KStat ks = eval_k(w, k, wv);
-        w.ev = ks; w.ev_pos = pos; w.ev_len = len; w.ev_k = k;
-        if (ks.homo) continue;
-        double f = (double)ks.M / (double)ks.T;
-        bool accL = !blkL && f >= needL, accH = !blkH && f >= needH;
-        if (accL || accH) {
-            u64 mm = multiples_mask(k);
-            bool m64 = (64 % k) == 0;
-            if (accL) { res.tl = k; needL = f; blockedL |= mm; blk64L |= m64; res.sl_lo = ks.s_lo; res.sl_hi = ks.s_hi; }
-            if (accH) { res.th = k; needH = f; blockedH |= mm; blk64H |= m64; res.sh_lo = ks.s_lo; res.sh_hi = ks.s_hi; }
-        }
+        consider(w, st, pos, len, k, wv);
     }
-    return res;
+    return st.res;
 }
 
 // class statistics + run list of (window, k), re-using the last evaluation when it is the same one
-__device__ KStat eval_cached(Warp& w, const DevBatch& b, u32 pos, int len, int k) {
+__device__ __noinline__ KStat eval_cached(Warp& w, const DevBatch& b, u32 pos, int len, int k) {
     if (w.ev_k == k && w.ev_pos == pos && w.ev_len == len) return w.ev;
     load_window(w, b, pos, len);
     u32 wv = wv_for_k(w, k);
@@ -980,7 +1039,8 @@ __device__ void route_long(const DevCfg& cfg, Warp& w, const DevBatch& b, u32 u,
     }
 }
 
-__global__ void __launch_bounds__(kExactWarps * 32) trew_exact_kernel(DevCfg cfg, DevBatch b, ExactArgs a) {
+template <int MODE>
+__global__ void __launch_bounds__(kExactWarps * 32, 5) trew_exact_kernel(DevCfg cfg, DevBatch b, ExactArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int wid = threadIdx.x >> 5;
     unsigned char* base = smem + (size_t)wid * exact_warp_bytes(a.run_cap);
@@ -1008,8 +1068,8 @@ __global__ void __launch_bounds__(kExactWarps * 32) trew_exact_kernel(DevCfg cfg
         idx = __shfl_sync(0xffffffffu, idx, 0);
         if (idx >= n) break;
         u32 u = a.survivors[idx];
-        if (cfg.mode == 0) route_short(cfg, w, b, u);
-        else if (cfg.mode == 1) route_pair(cfg, w, b, u);
+        if constexpr (MODE == 0) route_short(cfg, w, b, u);
+        else if constexpr (MODE == 1) route_pair(cfg, w, b, u);
         else route_long(cfg, w, b, u, scratch);
     }
 }
@@ -1018,13 +1078,19 @@ constexpr int kExactBlocksPerSM = 5;
 int exact_warps_total(int sm_count) { return sm_count * kExactBlocksPerSM * kExactWarps; }
 
 cudaError_t prepare_exact(int run_cap_max) {
-    return cudaFuncSetAttribute(trew_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)exact_smem_bytes(run_cap_max, true));
+    int bytes = (int)exact_smem_bytes(run_cap_max, true);
+    cudaError_t e = cudaFuncSetAttribute(trew_exact_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(trew_exact_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(trew_exact_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    return e;
 }
 
 void launch_exact(const DevCfg& cfg, const DevBatch& b, const ExactArgs& a, int sm_count, cudaStream_t stream) {
     size_t smem = exact_smem_bytes(a.run_cap, true);
-    trew_exact_kernel<<<sm_count * kExactBlocksPerSM, kExactWarps * 32, smem, stream>>>(cfg, b, a);
+    dim3 grid(sm_count * kExactBlocksPerSM), block(kExactWarps * 32);
+    if (cfg.mode == 0) trew_exact_kernel<0><<<grid, block, smem, stream>>>(cfg, b, a);
+    else if (cfg.mode == 1) trew_exact_kernel<1><<<grid, block, smem, stream>>>(cfg, b, a);
+    else trew_exact_kernel<2><<<grid, block, smem, stream>>>(cfg, b, a);
 }
 
 }  // namespace trew
