@@ -425,6 +425,7 @@ struct WarpMem {
     unsigned short* run_cw;                      // [cap + 1] ordinal of the run's first window among valid windows
     unsigned short* run_total;                   // [cap] class total for leaders, 0 otherwise
     u64* run_lo; u64* run_hi;                    // [cap] canonical rotation of the run's class
+    u32* run_hash;                               // [cap + 4] 32-bit fold of the canonical rotation
     int cap;
 };
 
@@ -433,6 +434,7 @@ __host__ __device__ inline size_t exact_warp_bytes(int cap) {
     b += (size_t)(3 * cap + 4) * sizeof(unsigned short);
     b = (b + 15) & ~(size_t)15;
     b += (size_t)2 * cap * sizeof(u64);
+    b += (size_t)(cap + 4) * sizeof(u32);
     return (b + 15) & ~(size_t)15;
 }
 
@@ -665,21 +667,32 @@ __device__ __noinline__ KStat eval_k(Warp& w, int k, u32 wv) {
         kmer_at(w, w.m.run_start[q], k, lo, hi);
         canon_pair(lo, hi, k);
         w.m.run_lo[q] = lo; w.m.run_hi[q] = hi;
+        w.m.run_hash[q] = (u32)lo ^ (u32)(lo >> 32) ^ (u32)hi ^ (u32)(hi >> 32);
     }
     __syncwarp();
-    // merge runs of the same class: total windows, ordinal of the class's last window, leader = first run
+    // merge runs of the same class: total windows, ordinal of the class's last window, leader = first run.
+    // All pairs, but the inner loop only touches a 32-bit hash per run (4 per 128-bit load); the full key and
+    // the counts are read on a hash hit only.
     u32 best = 0; int best_q = -1;
     const bool wide = k > 32;
+    const int R4 = (R + 3) & ~3;
     for (int q0 = 0; q0 < R; q0 += 32) {
         int q = q0 + lane;
         if (q < R) {
             u64 mlo = w.m.run_lo[q], mhi = w.m.run_hi[q];
+            u32 mh = w.m.run_hash[q];
             int total = 0, last = 0; bool leader = true;
-            for (int p = 0; p < R; p++) {
-                if (w.m.run_lo[p] == mlo && (!wide || w.m.run_hi[p] == mhi)) {
-                    int c0 = w.m.run_cw[p], c1 = w.m.run_cw[p + 1];
-                    total += c1 - c0; last = max(last, c1 - 1);
-                    if (p < q) leader = false;
+            for (int p4 = 0; p4 < R4; p4 += 4) {
+                uint4 hv = *reinterpret_cast<const uint4*>(w.m.run_hash + p4);
+                u32 hh[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    int p = p4 + t;
+                    if (hh[t] == mh && p < R && w.m.run_lo[p] == mlo && (!wide || w.m.run_hi[p] == mhi)) {
+                        int c0 = w.m.run_cw[p], c1 = w.m.run_cw[p + 1];
+                        total += c1 - c0; last = max(last, c1 - 1);
+                        if (p < q) leader = false;
+                    }
                 }
             }
             w.m.run_total[q] = leader ? (unsigned short)total : (unsigned short)0;
@@ -768,16 +781,73 @@ __device__ __noinline__ ScanRes scan_stats(const DevCfg& cfg, Warp& w, const Dev
     const double slack = 1.0 - 1e-12;
     const u32 lane = w.lane;
 
-    const bool all_valid = (int)__reduce_add_sync(0xffffffffu, (u32)__popc(w.v)) == len;
-    if (all_valid) {
-        // No invalid base: the valid windows of period k are exactly positions [0, len - k], so every lane
-        // can bound its own period (lane <-> k) without any cross-lane traffic; only the few periods whose
-        // bound reaches the LOW threshold are then visited in ascending order.
+    // Visit, in ascending order, the periods of one 32-wide block whose bound reached the LOW threshold.
+    // U / T are per-lane (lane <-> period kb + lane); wv_of(bit) yields this lane's window-valid word.
+    auto visit = [&](int kb, u32 cm, int U, int T, auto wv_of) {
+        while (cm) {
+            int bit = __ffs(cm) - 1;
+            cm &= cm - 1;
+            int kk = kb + bit;
+            bool blkL = kk < 64 ? ((st.blockedL >> kk) & 1ULL) != 0 : st.blk64L;
+            bool blkH = kk < 64 ? ((st.blockedH >> kk) & 1ULL) != 0 : st.blk64H;
+            int Uk = __shfl_sync(0xffffffffu, U, bit), Tk = __shfl_sync(0xffffffffu, T, bit);
+            u32 wv = wv_of(bit, Tk);
+            if (blkL && blkH) continue;
+            double dU = (double)Uk, dT = (double)Tk;
+            bool candL = !blkL && dU >= st.needL * dT * slack, candH = !blkH && dU >= st.needH * dT * slack;
+            if (!candL && !candH) continue;
+            consider(w, st, pos, len, kk, wv);
+        }
+    };
+
+    if (len <= 127) {
+        // Short window (the 75 / 150-base case): every lane bounds its own period (lane <-> k) with the
+        // window's planes held in registers, invalid bases included; no cross-lane traffic until a
+        // period qualifies.
+        u32 ph[5], pl[5], vv[4];
+#pragma unroll
+        for (int j = 0; j < 5; j++) { ph[j] = w.m.PH[j]; pl[j] = w.m.PL[j]; }
+#pragma unroll
+        for (int j = 0; j < 4; j++) vv[j] = w.m.V[j];
         for (int kb = kmin; kb <= kmax; kb += 32) {
             const int k = kb + (int)lane;
-            const int T = len - k + 1;
+            u32 wvv[4] = {0, 0, 0, 0};
+            int U = 0, T = 0;
+            if (k <= kmax) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) wvv[j] = vv[j];
+                sliding_and<4>(wvv, k);
+                u32 qh[5], ql[5];
+                shr_var<5>(ph, k, qh);
+                shr_var<5>(pl, k, ql);
+                int cH = 0, cL = 0, c11 = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    u32 dh = (qh[j] ^ ph[j]) & wvv[j], dl = (ql[j] ^ pl[j]) & wvv[j];
+                    T += __popc(wvv[j]); cH += __popc(dh); cL += __popc(dl); c11 += __popc(dh & dl);
+                }
+                int c10 = cH - c11, c01 = cL - c11, c00 = T - cH - cL + c11;
+                U = max(max(c00, c01), max(c10, c11));
+            }
+            bool cand = T > 0 && (double)U >= cfg.low * (double)T * slack;
+            u32 cm = __ballot_sync(0xffffffffu, cand);
+            visit(kb, cm, U, T, [&](int bit, int) {
+                u32 a0 = __shfl_sync(0xffffffffu, wvv[0], bit), a1 = __shfl_sync(0xffffffffu, wvv[1], bit);
+                u32 a2 = __shfl_sync(0xffffffffu, wvv[2], bit), a3 = __shfl_sync(0xffffffffu, wvv[3], bit);
+                return lane == 0 ? a0 : lane == 1 ? a1 : lane == 2 ? a2 : lane == 3 ? a3 : 0u;
+            });
+        }
+        return st.res;
+    }
+
+    const bool all_valid = (int)__reduce_add_sync(0xffffffffu, (u32)__popc(w.v)) == len;
+    if (all_valid) {
+        // Long window without invalid bases: the valid windows of period k are positions [0, len - k].
+        for (int kb = kmin; kb <= kmax; kb += 32) {
+            const int k = kb + (int)lane;
+            const int T = (k <= kmax && len - k + 1 > 0) ? len - k + 1 : 0;
             int U = 0;
-            if (k <= kmax && T > 0) {
+            if (T > 0) {
                 const int s = k >> 5, r = k & 31;
                 int cH = 0, cL = 0, c11 = 0;
                 for (int j = 0; j * 32 < T; j++) {
@@ -789,23 +859,12 @@ __device__ __noinline__ ScanRes scan_stats(const DevCfg& cfg, Warp& w, const Dev
                 int c10 = cH - c11, c01 = cL - c11, c00 = T - cH - cL + c11;
                 U = max(max(c00, c01), max(c10, c11));
             }
-            bool cand = k <= kmax && T > 0 && (double)U >= cfg.low * (double)T * slack;
+            bool cand = T > 0 && (double)U >= cfg.low * (double)T * slack;
             u32 cm = __ballot_sync(0xffffffffu, cand);
-            while (cm) {
-                int bit = __ffs(cm) - 1;
-                cm &= cm - 1;
-                int kk = kb + bit;
-                bool blkL = kk < 64 ? ((st.blockedL >> kk) & 1ULL) != 0 : st.blk64L;
-                bool blkH = kk < 64 ? ((st.blockedH >> kk) & 1ULL) != 0 : st.blk64H;
-                if (blkL && blkH) continue;
-                int Uk = __shfl_sync(0xffffffffu, U, bit);
-                int Tk = len - kk + 1;
-                double dU = (double)Uk, dT = (double)Tk;
-                bool candL = !blkL && dU >= st.needL * dT * slack, candH = !blkH && dU >= st.needH * dT * slack;
-                if (!candL && !candH) continue;
+            visit(kb, cm, U, T, [&](int, int Tk) {
                 int vb = Tk - 32 * (int)lane;
-                consider(w, st, pos, len, kk, vb <= 0 ? 0u : low_mask(min(32, vb)));
-            }
+                return vb <= 0 ? 0u : low_mask(min(32, vb));
+            });
         }
         return st.res;
     }
@@ -1057,6 +1116,7 @@ __global__ void __launch_bounds__(kExactWarps * 32, 5) trew_exact_kernel(DevCfg 
     off = (off + 15) & ~(size_t)15;
     w.m.run_lo = (u64*)(base + off);
     w.m.run_hi = w.m.run_lo + a.run_cap;
+    w.m.run_hash = (u32*)(w.m.run_hi + a.run_cap);
     w.cur_len = -1; w.cur_pos = 0; w.ev_k = -1; w.ev_pos = 0; w.ev_len = -1;
     w.h = w.l = w.v = 0;
     const u32 n = *a.n_survivors;
