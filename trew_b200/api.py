@@ -18,7 +18,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtrew_b200.so")
+LIB_PATH = os.environ.get("TREW_B200_LIB", os.path.join(HERE, "libtrew_b200.so"))  # override: experiments only
 CLI_PATH = os.path.join(HERE, "trew")
 
 MODE_SHORT, MODE_PAIR, MODE_LONG = 0, 1, 2

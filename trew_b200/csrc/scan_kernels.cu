@@ -416,6 +416,9 @@ void launch_filter(const DevCfg& cfg, const DevBatch& b, unsigned int n_units, u
 // ------------------------------------------------------------------------------------------------
 
 constexpr int kPlaneWords = 36;  // 32 window words + zero padding for shifted reads
+#ifndef TREW_EXACT_BPS
+#define TREW_EXACT_BPS 8   // resident exact-kernel blocks per SM (latency-bound: occupancy beats registers)
+#endif
 constexpr int kExactWarps = 4;
 
 struct WarpMem {
@@ -1099,7 +1102,7 @@ __device__ void route_long(const DevCfg& cfg, Warp& w, const DevBatch& b, u32 u,
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kExactWarps * 32, 5) trew_exact_kernel(DevCfg cfg, DevBatch b, ExactArgs a) {
+__global__ void __launch_bounds__(kExactWarps * 32, TREW_EXACT_BPS) trew_exact_kernel(DevCfg cfg, DevBatch b, ExactArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int wid = threadIdx.x >> 5;
     unsigned char* base = smem + (size_t)wid * exact_warp_bytes(a.run_cap);
@@ -1134,7 +1137,7 @@ __global__ void __launch_bounds__(kExactWarps * 32, 5) trew_exact_kernel(DevCfg 
     }
 }
 
-constexpr int kExactBlocksPerSM = 5;
+constexpr int kExactBlocksPerSM = TREW_EXACT_BPS;
 int exact_warps_total(int sm_count) { return sm_count * kExactBlocksPerSM * kExactWarps; }
 
 cudaError_t prepare_exact(int run_cap_max) {
