@@ -59,7 +59,7 @@ typedef struct trew_config {
     double low_baseline;      /* LOW_BASELINE  (-L, default 0.5)                                   */
     double high_baseline;     /* HIGH_BASELINE (-H, default 0.8)                                   */
     int32_t device;           /* CUDA device ordinal                                               */
-    int32_t table_log2_slots; /* device count-table capacity, 0 = default (2^20 slots)             */
+    int32_t table_log2_slots; /* device count-table capacity, 0 = default (2^22 slots)             */
     int32_t n_staging;        /* pinned staging buffers (double buffering = 2), 0 = default (3)    */
     int32_t host_threads;     /* host packing threads, 0 = all cores (capped at 32)                 */
     uint64_t staging_bytes;   /* bytes per staging buffer, 0 = default (64 MiB)                    */

@@ -74,6 +74,7 @@ struct trew_ctx {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     double filter_ms = 0, exact_ms = 0; uint64_t n_prof_scans = 0;
     std::vector<trew_resident*> pending_prof;
+    void* h_export = nullptr; size_t h_export_bytes = 0;
 };
 
 namespace {
@@ -285,7 +286,7 @@ int trew_dev_create(const trew_config* cfg, trew_ctx** out) {
     cudaDeviceProp prop;
     CKC(cudaGetDeviceProperties(&prop, cfg->device));
     ctx->sm_count = prop.multiProcessorCount;
-    int lg = cfg->table_log2_slots > 0 ? cfg->table_log2_slots : 20;
+    int lg = cfg->table_log2_slots > 0 ? cfg->table_log2_slots : 22;
     if (lg < 10 || lg > 28) { fail(ctx, TREW_ERR_ARG, "table_log2_slots out of range"); return bail(TREW_ERR_ARG); }
     ctx->n_slots = (size_t)1 << lg;
     Slot* d_slots = nullptr;
@@ -352,6 +353,7 @@ void trew_dev_destroy(trew_ctx* ctx) {
     if (ctx->d_seq) cudaFree(ctx->d_seq);
     if (ctx->d_count) cudaFree(ctx->d_count);
     if (ctx->d_n) cudaFree(ctx->d_n);
+    if (ctx->h_export) cudaFreeHost(ctx->h_export);
     if (ctx->main_stream) cudaStreamDestroy(ctx->main_stream);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
@@ -525,26 +527,53 @@ int trew_dev_finish(trew_ctx* ctx, const trew_entry** entries, uint64_t* n_entri
     uint64_t n = 0;
     int rc = trew_dev_export_device(ctx, nullptr, nullptr, nullptr, &n);
     if (rc) return rc;
-    std::vector<unsigned int> meta(n);
-    std::vector<unsigned long long> seq(2 * n), cnt(n);
+    // D2H through a pinned bounce buffer (grown on demand)
+    size_t need = (size_t)n * 28 + 64;
+    if (need > ctx->h_export_bytes) {
+        if (ctx->h_export) CK(cudaFreeHost(ctx->h_export));
+        ctx->h_export = nullptr;
+        size_t cap = std::max(need * 2, (size_t)1 << 20);
+        CK(cudaHostAlloc(&ctx->h_export, cap, cudaHostAllocDefault));
+        ctx->h_export_bytes = cap;
+    }
+    unsigned long long* seq = (unsigned long long*)ctx->h_export;
+    unsigned long long* cnt = seq + 2 * n;
+    unsigned int* meta = (unsigned int*)(cnt + n);
     if (n) {
-        CK(cudaMemcpy(meta.data(), ctx->d_meta, n * sizeof(unsigned int), cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(seq.data(), ctx->d_seq, 2 * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(cnt.data(), ctx->d_count, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpyAsync(seq, ctx->d_seq, 2 * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->main_stream));
+        CK(cudaMemcpyAsync(cnt, ctx->d_count, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->main_stream));
+        CK(cudaMemcpyAsync(meta, ctx->d_meta, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->main_stream));
+        CK(cudaStreamSynchronize(ctx->main_stream));
     }
     ctx->stats.d2h_bytes += n * 28 + 4;
     ctx->entries.resize(n);
-    for (uint64_t i = 0; i < n; i++) {
-        trew_entry& e = ctx->entries[i];
-        e.table = (int32_t)(meta[i] >> 8); e.k = (int32_t)(meta[i] & 0xff);
-        e.seq_lo = seq[2 * i]; e.seq_hi = seq[2 * i + 1]; e.count = cnt[i];
-    }
-    std::sort(ctx->entries.begin(), ctx->entries.end(), [](const trew_entry& a, const trew_entry& b) {
+    auto less = [](const trew_entry& a, const trew_entry& b) {
         if (a.table != b.table) return a.table < b.table;
         if (a.k != b.k) return a.k < b.k;
         if (a.seq_hi != b.seq_hi) return a.seq_hi < b.seq_hi;
         return a.seq_lo < b.seq_lo;
+    };
+    // sort by (table, k, seq) so the output does not depend on insertion order: chunk sorts on the pool,
+    // then pairwise merges
+    int P = (int)std::min<uint64_t>((uint64_t)ctx->pool->size(), n / 4096 + 1);
+    std::vector<uint64_t> cut(P + 1);
+    for (int i = 0; i <= P; i++) cut[i] = n * (uint64_t)i / (uint64_t)P;
+    trew_entry* E = ctx->entries.data();
+    ctx->pool->run(P, [&](int i) {
+        for (uint64_t j = cut[i]; j < cut[i + 1]; j++) {
+            trew_entry& e = E[j];
+            e.table = (int32_t)(meta[j] >> 8); e.k = (int32_t)(meta[j] & 0xff);
+            e.seq_lo = seq[2 * j]; e.seq_hi = seq[2 * j + 1]; e.count = cnt[j];
+        }
+        std::sort(E + cut[i], E + cut[i + 1], less);
     });
+    for (int step = 1; step < P; step *= 2) {
+        int pairs = (P + 2 * step - 1) / (2 * step);
+        ctx->pool->run(pairs, [&](int i) {
+            int a = i * 2 * step, m = std::min(a + step, P), b = std::min(a + 2 * step, P);
+            if (m < b) std::inplace_merge(E + cut[a], E + cut[m], E + cut[b], less);
+        });
+    }
     if (entries) *entries = ctx->entries.data();
     if (n_entries) *n_entries = n;
     return TREW_OK;
