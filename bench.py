@@ -209,8 +209,8 @@ def run_ours(args):
         ctx.reset()
         for h, _ in handles:
             ctx.scan_resident(h)
-        rows = ctx.finish_arrays()  # sync + compaction kernel + D2H of the tables
-        merged_last[0] = merge.merge_rows(rows, device)  # exact NCCL merge (identity at N = 1)
+        # sync + compaction kernel + D2H of the tables (+ exact NCCL merge across ranks for N > 1)
+        merged_last[0] = ctx.finish_view() if world == 1 else merge.merge_rows(ctx.finish_arrays(), device)
 
     for _ in range(args.warmup):
         step()
@@ -250,8 +250,7 @@ def run_ours(args):
         ctx.reset()
         for _ in range(reps):
             ctx.submit_chunk(buf, locs)
-        rows = ctx.finish_arrays()
-        return merge.merge_rows(rows, device)
+        return ctx.finish_view() if world == 1 else merge.merge_rows(ctx.finish_arrays(), device)
 
     for _ in range(max(1, min(args.warmup, 2))):
         e2e_step()

@@ -289,21 +289,26 @@ class DeviceContext:
         self._check(self.lib.trew_dev_finish(self.ctx, C.byref(p), C.byref(n)))
         return p, n.value
 
+    ENTRY_DTYPE = np.dtype([("seq_lo", "<u8"), ("seq_hi", "<u8"), ("count", "<u8"), ("table", "<i4"), ("k", "<i4")])
+
+    def finish_view(self) -> np.ndarray:
+        """The merged tables as a zero-copy structured view of the library's entry array (sorted by
+        (table, k, seq)); valid until the next call that touches the tables."""
+        p, n = self.finish_entries()
+        if n == 0:
+            return np.zeros(0, dtype=self.ENTRY_DTYPE)
+        buf = (C.c_char * (n * 32)).from_address(C.addressof(p.contents))
+        return np.frombuffer(buf, dtype=self.ENTRY_DTYPE, count=n)
+
     def finish_arrays(self) -> np.ndarray:
         """The merged tables as an (n, 4) int64 array of rows (meta = table << 8 | k, seq_lo, seq_hi, count),
         sorted by (table, k, seq).  64-bit fields are reinterpreted as signed."""
-        p, n = self.finish_entries()
-        if n == 0:
-            return np.zeros((0, 4), dtype=np.int64)
-        raw = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(n, 4)).copy()
-        out = np.empty((n, 4), dtype=np.uint64)
-        tk = raw[:, 3]
-        table = tk & np.uint64(0xffffffff)
-        k = tk >> np.uint64(32)
-        out[:, 0] = (table << np.uint64(8)) | k
-        out[:, 1] = raw[:, 0]
-        out[:, 2] = raw[:, 1]
-        out[:, 3] = raw[:, 2]
+        v = self.finish_view()
+        out = np.empty((v.shape[0], 4), dtype=np.uint64)
+        out[:, 0] = (v["table"].astype(np.uint64) << np.uint64(8)) | v["k"].astype(np.uint64)
+        out[:, 1] = v["seq_lo"]
+        out[:, 2] = v["seq_hi"]
+        out[:, 3] = v["count"]
         return out.view(np.int64)
 
     def finish(self) -> Tables:

@@ -553,26 +553,50 @@ int trew_dev_finish(trew_ctx* ctx, const trew_entry** entries, uint64_t* n_entri
         if (a.seq_hi != b.seq_hi) return a.seq_hi < b.seq_hi;
         return a.seq_lo < b.seq_lo;
     };
-    // sort by (table, k, seq) so the output does not depend on insertion order: chunk sorts on the pool,
-    // then pairwise merges
-    int P = (int)std::min<uint64_t>((uint64_t)ctx->pool->size(), n / 4096 + 1);
-    std::vector<uint64_t> cut(P + 1);
-    for (int i = 0; i <= P; i++) cut[i] = n * (uint64_t)i / (uint64_t)P;
+    // Sort by (table, k, seq) so the output does not depend on insertion order.  Sample sort on the pool:
+    // splitters from a regular sample, scatter into key-range buckets, sort every bucket independently.
+    const int P = (int)std::min<uint64_t>((uint64_t)ctx->pool->size(), n / 8192 + 1);
+    auto unpack = [&](uint64_t j) {
+        trew_entry e;
+        e.table = (int32_t)(meta[j] >> 8); e.k = (int32_t)(meta[j] & 0xff);
+        e.seq_lo = seq[2 * j]; e.seq_hi = seq[2 * j + 1]; e.count = cnt[j];
+        return e;
+    };
     trew_entry* E = ctx->entries.data();
-    ctx->pool->run(P, [&](int i) {
-        for (uint64_t j = cut[i]; j < cut[i + 1]; j++) {
-            trew_entry& e = E[j];
-            e.table = (int32_t)(meta[j] >> 8); e.k = (int32_t)(meta[j] & 0xff);
-            e.seq_lo = seq[2 * j]; e.seq_hi = seq[2 * j + 1]; e.count = cnt[j];
-        }
-        std::sort(E + cut[i], E + cut[i + 1], less);
-    });
-    for (int step = 1; step < P; step *= 2) {
-        int pairs = (P + 2 * step - 1) / (2 * step);
-        ctx->pool->run(pairs, [&](int i) {
-            int a = i * 2 * step, m = std::min(a + step, P), b = std::min(a + 2 * step, P);
-            if (m < b) std::inplace_merge(E + cut[a], E + cut[m], E + cut[b], less);
+    if (P <= 1) {
+        for (uint64_t j = 0; j < n; j++) E[j] = unpack(j);
+        std::sort(E, E + n, less);
+    } else {
+        std::vector<trew_entry> sample;
+        const uint64_t ns = (uint64_t)P * 64;
+        for (uint64_t i = 0; i < ns; i++) sample.push_back(unpack(i * n / ns));
+        std::sort(sample.begin(), sample.end(), less);
+        std::vector<trew_entry> split;
+        for (int i = 1; i < P; i++) split.push_back(sample[(size_t)i * 64]);
+        std::vector<uint64_t> cut(P + 1);
+        for (int i = 0; i <= P; i++) cut[i] = n * (uint64_t)i / (uint64_t)P;
+        std::vector<uint64_t> counts((size_t)P * P, 0);
+        std::vector<unsigned char> bucket(n);
+        ctx->pool->run(P, [&](int t) {
+            for (uint64_t j = cut[t]; j < cut[t + 1]; j++) {
+                trew_entry e = unpack(j);
+                int bk = (int)(std::upper_bound(split.begin(), split.end(), e, less) - split.begin());
+                bucket[j] = (unsigned char)bk;
+                counts[(size_t)t * P + bk]++;
+            }
         });
+        std::vector<uint64_t> start((size_t)P * P), bstart(P + 1, 0);
+        uint64_t acc = 0;
+        for (int bk = 0; bk < P; bk++) {
+            bstart[bk] = acc;
+            for (int t = 0; t < P; t++) { start[(size_t)t * P + bk] = acc; acc += counts[(size_t)t * P + bk]; }
+        }
+        bstart[P] = acc;
+        ctx->pool->run(P, [&](int t) {
+            uint64_t* st = &start[(size_t)t * P];
+            for (uint64_t j = cut[t]; j < cut[t + 1]; j++) E[st[bucket[j]]++] = unpack(j);
+        });
+        ctx->pool->run(P, [&](int bk) { std::sort(E + bstart[bk], E + bstart[bk + 1], less); });
     }
     if (entries) *entries = ctx->entries.data();
     if (n_entries) *n_entries = n;
