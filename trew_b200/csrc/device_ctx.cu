@@ -156,7 +156,7 @@ int retire_slot(trew_ctx* ctx, SlotRes& s) {
 }
 
 // Pack reads (host threads) into the next free staging slot and launch copy + kernels on its stream.
-int submit_reads(trew_ctx* ctx, const ReadRef* reads, uint32_t n, uint64_t total_bases, uint32_t max_len) {
+int submit_reads(trew_ctx* ctx, const ReadRef* reads, uint32_t n, uint64_t total_bases, uint32_t max_len, const char* buf_end) {
     if (n == 0) return TREW_OK;
     SlotRes& s = ctx->slots[ctx->next_slot];
     ctx->next_slot = (ctx->next_slot + 1) % ctx->slots.size();
@@ -177,7 +177,7 @@ int submit_reads(trew_ctx* ctx, const ReadRef* reads, uint32_t n, uint64_t total
     }
     pack_prepare(reads, n, starts.data(), (int)starts.size(), v);
     int nr = (int)starts.size();
-    ctx->pool->run(nr, [&](int i) { pack_range(reads, starts[i], i + 1 < nr ? starts[i + 1] : n, v); });
+    ctx->pool->run(nr, [&](int i) { pack_range(reads, starts[i], i + 1 < nr ? starts[i + 1] : n, v, buf_end); });
 
     CK(cudaEventRecord(s.ev_start, s.stream));
     CK(cudaMemcpyAsync(s.d_buf, s.h_buf, v.bytes, cudaMemcpyHostToDevice, s.stream));
@@ -196,7 +196,7 @@ int submit_reads(trew_ctx* ctx, const ReadRef* reads, uint32_t n, uint64_t total
 }
 
 // Greedy split of a read list into sub-batches that fit one staging slot.
-int submit_split(trew_ctx* ctx, const std::vector<ReadRef>& reads, uint32_t unit) {
+int submit_split(trew_ctx* ctx, const std::vector<ReadRef>& reads, uint32_t unit, const char* buf_end) {
     size_t i = 0, n = reads.size();
     while (i < n) {
         size_t j = i; uint64_t bases = 0; uint32_t mx = 0;
@@ -210,7 +210,7 @@ int submit_split(trew_ctx* ctx, const std::vector<ReadRef>& reads, uint32_t unit
         if (batch_bytes((uint32_t)(j - i), bases) > ctx->staging_bytes)
             return fail(ctx, TREW_ERR_ARG, "a single read/pair (%llu bases) does not fit a staging buffer of %zu bytes",
                         (unsigned long long)bases, ctx->staging_bytes);
-        int rc = submit_reads(ctx, reads.data() + i, (uint32_t)(j - i), bases, mx);
+        int rc = submit_reads(ctx, reads.data() + i, (uint32_t)(j - i), bases, mx, buf_end);
         if (rc) return rc;
         i = j;
     }
@@ -390,7 +390,10 @@ int trew_dev_submit_chunk(trew_ctx* ctx, const char* buffer1, const int32_t* loc
         }
     }
     if (pair) for (auto& r : reads) if (r.len > (uint32_t)kMaxWindow) return fail(ctx, TREW_ERR_TOO_LONG, "paired read longer than %d", kMaxWindow);
-    return submit_split(ctx, reads, pair ? 2u : 1u);
+    // one past the last byte the caller vouches for: lets the packer load whole 32-byte blocks at read tails
+    const char* buf_end = nullptr;
+    if (!pair) for (const auto& r : reads) if (r.ptr + r.len > buf_end) buf_end = r.ptr + r.len;
+    return submit_split(ctx, reads, pair ? 2u : 1u, buf_end);
 }
 
 int trew_dev_submit_packed(trew_ctx* ctx, const trew_batch* batch) {

@@ -23,7 +23,8 @@ struct BatchView {
 size_t batch_bytes(uint32_t n_reads, uint64_t total_bases);
 void batch_layout(void* dst, uint32_t n_reads, uint64_t total_bases, BatchView* v);
 void pack_prepare(const ReadRef* reads, uint32_t n, const uint32_t* range_starts, int n_ranges, const BatchView& v);
-void pack_range(const ReadRef* reads, uint32_t r0, uint32_t r1, const BatchView& v);
+// buf_end: one past the last readable byte of the chunk the reads point into (nullptr: unknown)
+void pack_range(const ReadRef* reads, uint32_t r0, uint32_t r1, const BatchView& v, const char* buf_end);
 
 // Minimal fork-join pool: run(n, fn) calls fn(i) for i in [0, n) on the workers plus the caller.
 class Pool {

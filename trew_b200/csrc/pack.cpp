@@ -104,18 +104,26 @@ struct BitWriter {
     }
 };
 
-inline void pack_one(BitWriter& w, const unsigned char* s, int n, bool avx2) {
+// `slack` = readable bytes after the read's last byte (inside the caller's chunk): when at least 31 the tail
+// block is loaded straight from the chunk and the excess lanes are masked off.
+inline void pack_one(BitWriter& w, const unsigned char* s, int n, bool avx2, size_t slack) {
     int i = 0;
     uint32_t h, l, v;
 #if defined(__x86_64__)
     if (avx2) {
         for (; i + 32 <= n; i += 32) { masks_avx2(s + i, h, l, v); w.put(h, l, v, 32); }
         if (i < n) {
-            unsigned char tmp[32];
-            memset(tmp, 0, sizeof(tmp));
-            memcpy(tmp, s + i, (size_t)(n - i));
-            masks_avx2(tmp, h, l, v);
-            w.put(h, l, v, n - i);
+            int m = n - i;
+            uint32_t keep = (1u << m) - 1u;
+            if (slack >= 31) {
+                masks_avx2(s + i, h, l, v);
+            } else {
+                unsigned char tmp[32];
+                memset(tmp, 0, sizeof(tmp));
+                memcpy(tmp, s + i, (size_t)m);
+                masks_avx2(tmp, h, l, v);
+            }
+            w.put(h & keep, l & keep, v & keep, m);
         }
         return;
     }
@@ -149,11 +157,15 @@ void batch_layout(void* dst, uint32_t n_reads, uint64_t total_bases, BatchView* 
 }
 
 // Pack reads[r0, r1) whose first base sits at bit position v.bit_off[r0].
-void pack_range(const ReadRef* reads, uint32_t r0, uint32_t r1, const BatchView& v) {
+void pack_range(const ReadRef* reads, uint32_t r0, uint32_t r1, const BatchView& v, const char* buf_end) {
     if (r0 >= r1) return;
     const bool avx2 = have_avx2();
     BitWriter w(v.hi, v.lo, v.val, v.bit_off[r0]);
-    for (uint32_t r = r0; r < r1; r++) pack_one(w, (const unsigned char*)reads[r].ptr, (int)reads[r].len, avx2);
+    for (uint32_t r = r0; r < r1; r++) {
+        const char* e = reads[r].ptr + reads[r].len;
+        size_t slack = (buf_end && buf_end > e) ? (size_t)(buf_end - e) : 0;
+        pack_one(w, (const unsigned char*)reads[r].ptr, (int)reads[r].len, avx2, slack);
+    }
     w.finish();
 }
 
@@ -191,7 +203,7 @@ int trew_pack_reads(const char* buffer, const int32_t* locs, uint32_t n, void* d
     trew::batch_layout(dst, n, total, &v);
     uint32_t zero = 0;
     trew::pack_prepare(reads.data(), n, &zero, n ? 1 : 0, v);
-    trew::pack_range(reads.data(), 0, n, v);
+    trew::pack_range(reads.data(), 0, n, v, nullptr);
     out->n_reads = n; out->max_read_len = mx; out->bit_off = v.bit_off; out->hi = v.hi; out->lo = v.lo; out->val = v.val;
     return TREW_OK;
 }
