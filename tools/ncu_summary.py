@@ -1,0 +1,54 @@
+#!/usr/bin/env python3
+"""Text summary of an .ncu-rep (key raw metrics per profiled launch + per-function / per-line shares).
+    python tools/ncu_summary.py report.ncu-rep [source.cu] > profiles/<name>.txt"""
+import csv
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum", "sm__inst_issued.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+]
+
+rep = sys.argv[1]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True).stdout.decode()
+rows = list(csv.reader(raw.splitlines()))
+hdr, units = rows[0], rows[1]
+idx = {h: i for i, h in enumerate(hdr)}
+print("# ncu --set full summary of %s" % rep.split("/")[-1])
+kernels = []
+for r in rows[2:]:
+    name = r[idx["Kernel Name"]]
+    kernels.append(name)
+    print("\n== launch id %s: %s" % (r[idx["ID"]], name))
+    for k in KEYS:
+        if k in idx:
+            print("  %-82s %s %s" % (k, r[idx[k]], units[idx[k]]))
+if len(sys.argv) > 2:
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    seen = set()
+    for name in kernels:
+        short = name.split("(")[0].split("::")[-1].split("<")[0].replace("void ", "").strip()
+        if short in seen:
+            continue
+        seen.add(short)
+        print("\n== %s: share of warp instructions / stall samples per source function" % short)
+        print(subprocess.run([sys.executable, os.path.join(here, "ncu_by_function.py"), rep, short, sys.argv[2]],
+                             capture_output=True).stdout.decode().rstrip())
+        print("\n== %s: hottest source lines" % short)
+        print(subprocess.run([sys.executable, os.path.join(here, "ncu_hot_lines.py"), rep, short, "15"],
+                             capture_output=True).stdout.decode().rstrip())

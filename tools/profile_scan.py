@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Small driver for ncu: one device-resident batch of the configs[1] shape, scanned a few times.
 
-    python tools/profile_scan.py [reads] [scans] [min_mer] [max_mer]
+    python tools/profile_scan.py [reads] [scans] [min_mer] [max_mer] [tel_ppm] [half_ppm] [n_ppm]
 """
 import os
 import sys
@@ -14,8 +14,11 @@ reads = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
 scans = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 mn = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 mx = int(sys.argv[4]) if len(sys.argv) > 4 else 32
+tel = int(sys.argv[5]) if len(sys.argv) > 5 else 10000
+half = int(sys.argv[6]) if len(sys.argv) > 6 else 2000
+nppm = int(sys.argv[7]) if len(sys.argv) > 7 else 1000
 with api.DeviceContext(api.MODE_SHORT, mn, mx) as ctx:
-    h = ctx.synth_resident(1, reads, 150, tel_ppm=10000, half_ppm=2000, n_ppm=1000, sub_ppm=10000)
+    h = ctx.synth_resident(1, reads, 150, tel_ppm=tel, half_ppm=half, n_ppm=nppm, sub_ppm=10000)
     for _ in range(scans):
         ctx.scan_resident(h)
     ctx.sync()

@@ -25,7 +25,7 @@ struct SlotRes {
     void* h_buf = nullptr;      // pinned
     void* d_buf = nullptr;
     unsigned int* d_survivors = nullptr;
-    unsigned int* d_counters = nullptr;  // [0] n_survivors [1] work counter
+    unsigned int* d_counters = nullptr;  // [0] n_survivors [1] work counter [2] n_deferred
     unsigned char* d_scratch = nullptr;
     size_t scratch_bytes = 0;
     size_t survivors_cap = 0;
@@ -120,6 +120,7 @@ size_t scratch_need(const trew_ctx* ctx, uint32_t max_read_len, unsigned int* st
     return (size_t)st * (size_t)exact_warps_total(ctx->sm_count);
 }
 
+// d_survivors holds 2 * n_units entries: survivors in the first half, the screen kernel's deferred list in the second
 int launch_scan(trew_ctx* ctx, const DevBatch& b, uint32_t n_units, uint32_t max_read_len, unsigned int* d_survivors,
                 unsigned int* d_counters, unsigned char** d_scratch, size_t* scratch_bytes, cudaStream_t st,
                 cudaEvent_t* ev = nullptr) {
@@ -130,9 +131,9 @@ int launch_scan(trew_ctx* ctx, const DevBatch& b, uint32_t n_units, uint32_t max
         CK(cudaMalloc((void**)d_scratch, need));
         *scratch_bytes = need;
     }
-    CK(cudaMemsetAsync(d_counters, 0, 2 * sizeof(unsigned int), st));
+    CK(cudaMemsetAsync(d_counters, 0, 4 * sizeof(unsigned int), st));
     if (ev) CK(cudaEventRecord(ev[0], st));
-    launch_filter(ctx->dcfg, b, n_units, max_read_len, d_survivors, d_counters, ctx->sm_count, st);
+    launch_filter(ctx->dcfg, b, n_units, max_read_len, d_survivors + n_units, d_counters + 2, d_survivors, d_counters, ctx->sm_count, st);
     if (ev) CK(cudaEventRecord(ev[1], st));
     ExactArgs a{};
     a.survivors = d_survivors; a.n_survivors = d_counters; a.work_counter = d_counters + 1;
@@ -141,7 +142,7 @@ int launch_scan(trew_ctx* ctx, const DevBatch& b, uint32_t n_units, uint32_t max
     launch_exact(ctx->dcfg, b, a, ctx->sm_count, st);
     if (ev) CK(cudaEventRecord(ev[2], st));
     CK(cudaGetLastError());
-    ctx->stats.kernel_launches += 2;
+    ctx->stats.kernel_launches += 3;
     return TREW_OK;
 }
 
@@ -317,8 +318,8 @@ int trew_dev_create(const trew_config* cfg, trew_ctx** out) {
         CKC(cudaHostAlloc(&s.h_buf, ctx->staging_bytes, cudaHostAllocDefault));
         CKC(cudaMalloc(&s.d_buf, ctx->staging_bytes));
         s.survivors_cap = ctx->staging_bytes / 8;  // >= reads of >= 11 bases; submit_split enforces it
-        CKC(cudaMalloc((void**)&s.d_survivors, s.survivors_cap * sizeof(unsigned int)));
-        CKC(cudaMalloc((void**)&s.d_counters, 2 * sizeof(unsigned int)));
+        CKC(cudaMalloc((void**)&s.d_survivors, 2 * s.survivors_cap * sizeof(unsigned int)));
+        CKC(cudaMalloc((void**)&s.d_counters, 4 * sizeof(unsigned int)));
         CKC(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         CKC(cudaEventCreate(&s.ev_start));
         CKC(cudaEventCreate(&s.ev_done));
@@ -458,8 +459,8 @@ int trew_dev_upload(trew_ctx* ctx, const trew_batch* batch, trew_resident** out)
     r->batch.hi = (const unsigned int*)((char*)r->d_buf + ((char*)v.hi - tmp.data()));
     r->batch.lo = r->batch.hi + v.plane_words; r->batch.val = r->batch.lo + v.plane_words;
     r->n_reads = n; r->n_units = ctx->cfg.mode == TREW_MODE_PAIR ? n / 2 : n; r->max_read_len = batch->max_read_len; r->bases = bases;
-    CK(cudaMalloc((void**)&r->d_survivors, (size_t)std::max<uint32_t>(r->n_units, 1) * sizeof(unsigned int)));
-    CK(cudaMalloc((void**)&r->d_counters, 2 * sizeof(unsigned int)));
+    CK(cudaMalloc((void**)&r->d_survivors, 2 * (size_t)std::max<uint32_t>(r->n_units, 1) * sizeof(unsigned int)));
+    CK(cudaMalloc((void**)&r->d_counters, 4 * sizeof(unsigned int)));
     *out = r;
     return TREW_OK;
 }
@@ -680,8 +681,8 @@ int trew_synth_resident(trew_ctx* ctx, uint64_t seed, uint32_t n_reads, uint32_t
     r->batch.n_reads = n_reads; r->batch.bit_off = v.bit_off; r->batch.hi = v.hi; r->batch.lo = v.lo; r->batch.val = v.val;
     r->n_reads = n_reads; r->n_units = ctx->cfg.mode == TREW_MODE_PAIR ? n_reads / 2 : n_reads;
     r->max_read_len = read_len; r->bases = bases;
-    CK(cudaMalloc((void**)&r->d_survivors, (size_t)std::max<uint32_t>(r->n_units, 1) * sizeof(unsigned int)));
-    CK(cudaMalloc((void**)&r->d_counters, 2 * sizeof(unsigned int)));
+    CK(cudaMalloc((void**)&r->d_survivors, 2 * (size_t)std::max<uint32_t>(r->n_units, 1) * sizeof(unsigned int)));
+    CK(cudaMalloc((void**)&r->d_counters, 4 * sizeof(unsigned int)));
     *out = r;
     return TREW_OK;
 }

@@ -49,11 +49,11 @@ __device__ __forceinline__ u64 mix64(u64 x) {
 // (stands in for the per-worker ResultMap objects, src/kmer.h:79-81)
 // ------------------------------------------------------------------------------------------------
 
-__device__ __noinline__ void table_add(const DevCfg& cfg, u32 meta, u64 lo, u64 hi, u64 cnt) {
+__device__ __noinline__ void table_add_impl(Slot* slots, u32 slot_mask, u32* error_flag, u32 meta, u64 lo, u64 hi, u64 cnt) {
     u64 h = mix64(lo ^ mix64(hi + 0x9e3779b97f4a7c15ULL * (u64)(meta + 1)));
-    u32 i = (u32)h & cfg.slot_mask;
-    for (u32 probe = 0; probe <= cfg.slot_mask; probe++, i = (i + 1) & cfg.slot_mask) {
-        Slot* s = cfg.slots + i;
+    u32 i = (u32)h & slot_mask;
+    for (u32 probe = 0; probe <= slot_mask; probe++, i = (i + 1) & slot_mask) {
+        Slot* s = slots + i;
         u32 st = atomicCAS(&s->state, 0u, 1u);
         if (st == 0u) {
             s->seq_lo = lo; s->seq_hi = hi; s->meta = meta;
@@ -69,7 +69,7 @@ __device__ __noinline__ void table_add(const DevCfg& cfg, u32 meta, u64 lo, u64 
             return;
         }
     }
-    atomicExch(cfg.error_flag, 3u);  // TREW_ERR_TABLE_FULL
+    atomicExch(error_flag, 3u);  // TREW_ERR_TABLE_FULL
 }
 
 __global__ void compact_kernel(const Slot* __restrict__ slots, u32 n_slots, u32* __restrict__ d_meta,
@@ -319,6 +319,8 @@ __device__ __noinline__ bool probe_filter(const DevBatch& b, u32 pos, int wl, in
     shr_var<NW>(PH, k0, QH);
     shr_var<NW>(PL, k0, QL);
     sliding_and<NW>(WV, k0);
+    u32 PA[NW];
+    bool have_pa = false;
     for (int k = k0; k <= k1; k++) {
         u32 a[NW], bb[NW], c[NW];
 #pragma unroll
@@ -327,17 +329,22 @@ __device__ __noinline__ bool probe_filter(const DevBatch& b, u32 pos, int wl, in
             a[j] = dh & WV[j]; bb[j] = dl & WV[j]; c[j] = a[j] & dl;
         }
         int T = popc_multi<NW>(WV);
+        if (T == 0) break;  // the valid-window mask only shrinks with k
         int cH = popc_multi<NW>(a), cL = popc_multi<NW>(bb), c11 = popc_multi<NW>(c);
         int c10 = cH - c11, c01 = cL - c11, c00 = T - cH - cL + c11;
         int U = max(max(c00, c01), max(c10, c11));
         int need = thr[T];
         if (U >= need) {
             // second level: add the parity of the A count (rare: ~2.5e-4 per (window, k) on random reads)
-            u32 A[NW], PA[NW], QA[NW], t[NW];
-            load_bits<NW>(b.hi, pos, A); load_bits<NW>(b.lo, pos, t);
+            u32 QA[NW];
+            if (!have_pa) {
+                u32 A[NW], t[NW];
+                load_bits<NW>(b.hi, pos, A); load_bits<NW>(b.lo, pos, t);
 #pragma unroll
-            for (int j = 0; j < NW; j++) A[j] &= t[j];
-            prefix_xor_excl<NW>(A, PA);
+                for (int j = 0; j < NW; j++) A[j] &= t[j];
+                prefix_xor_excl<NW>(A, PA);
+                have_pa = true;
+            }
             shr_var<NW>(PA, k, QA);
             u32 x11[NW], x10[NW], x01[NW], x00[NW];
 #pragma unroll
@@ -371,81 +378,225 @@ __device__ __forceinline__ bool probe_dispatch(const DevBatch& b, const Probe& p
     return true;  // window too long for the bit-parallel filter: let the exact kernel decide
 }
 
-template <int MAXNW>
-__global__ void __launch_bounds__(256) trew_filter_kernel(DevCfg cfg, DevBatch b, u32 n_units,
-                                                          u32* __restrict__ survivors, u32* __restrict__ n_survivors) {
-    __shared__ unsigned short thr[kThrTableSize];
-    for (int i = threadIdx.x; i < kThrTableSize; i += blockDim.x) thr[i] = cfg.thr_low[i];
+// ---- screen kernel: fast first level ---------------------------------------------------------------
+//
+// For probe windows of at most 95 bases without invalid bases the first-level test runs on the first 64
+// window positions only (two words per plane): with T = wl - k + 1 windows, T01 = min(T, 64) of them start
+// in [0, 64) and E = T - T01 beyond, and
+//     M <= U01 + E,   U01 = largest of the four parity-signature buckets among the first 64 positions,
+// so "U01 >= need(T) - E" is necessary for period k to reach LOW.  The four bucket counts are formed as the
+// four bytes of one word on the FMA pipe (byte0 = c11, byte1 = cH - c11, byte2 = cL - c11,
+// byte3 = T01 - cH - cL + c11) on top of a per-T base that adds 128 - (need - E) to every byte: a bucket
+// reaches the threshold iff the top bit of its byte is set.  A unit whose probes all fail the test emits
+// nothing.  Everything else -- a first-level hit, an invalid base, a longer window -- is put on the
+// deferred list and decided by the exact-bound kernel below, so this level only has to be sound, not tight.
+
+constexpr u32 kPackC11 = 1u - (1u << 8) - (1u << 16) + (1u << 24);
+constexpr u32 kPackH = (1u << 8) - (1u << 24);
+constexpr u32 kPackL = (1u << 16) - (1u << 24);
+constexpr int kFastMaxWl = 95;
+constexpr int kFastTabSize = kFastMaxWl + 2;
+
+// per-T entry: x = packed base word, y / z = masks of the window positions in words 0 / 1
+__device__ __forceinline__ uint4 fast_entry(int T, int need) {
+    uint4 e = make_uint4(0u, 0u, 0u, 0u);
+    if (T <= 0) return e;                       // no window: every byte stays 0
+    int T01 = min(T, 64);
+    e.y = T >= 32 ? 0xffffffffu : ((1u << T) - 1u);
+    e.z = T <= 32 ? 0u : (T >= 64 ? 0xffffffffu : ((1u << (T - 32)) - 1u));
+    int np = need - (T - T01);
+    if (np <= 0) e.x = 0x80808080u;             // the bound cannot reject: always a hit
+    else if (np > 64) e.x = (u32)T01 << 24;     // no bucket of <= 64 positions can reach it
+    else e.x = ((u32)T01 << 24) + (u32)(128 - np) * 0x01010101u;
+    return e;
+}
+
+// periods ka..kb (all with k >> 5 == S) of one all-valid window; true iff some period passes the first level
+template <int S>
+__device__ __forceinline__ bool fast_span(const u32 (&ph)[5], const u32 (&pl)[5], int wl, int ka, int kb,
+                                          const uint4* __restrict__ tab) {
+    const uint4* tp = tab + (wl - ka + 1);
+#pragma unroll 2
+    for (int k = ka; k <= kb; k++, tp--) {
+        const uint4 e = *tp;
+        u32 qh0 = __funnelshift_r(ph[S], ph[S + 1], k), qh1 = __funnelshift_r(ph[S + 1], ph[S + 2], k);
+        u32 ql0 = __funnelshift_r(pl[S], pl[S + 1], k), ql1 = __funnelshift_r(pl[S + 1], pl[S + 2], k);
+        u32 a0 = (qh0 ^ ph[0]) & e.y, a1 = (qh1 ^ ph[1]) & e.z;
+        u32 b0 = (ql0 ^ pl[0]) & e.y, b1 = (ql1 ^ pl[1]) & e.z;
+        u32 x = e.x + (u32)(__popc(a0) + __popc(a1)) * kPackH + (u32)(__popc(b0) + __popc(b1)) * kPackL +
+                (u32)(__popc(a0 & b0) + __popc(a1 & b1)) * kPackC11;
+        if (x & 0x80808080u) return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ bool probe_is_fast(const Probe& p) { return p.wl <= kFastMaxWl && p.k1 <= 63 && p.k1 <= p.wl; }
+
+// true iff the probe must be decided by the exact-bound kernel
+__device__ __forceinline__ bool screen_probe(const DevBatch& b, const Probe& p, const uint4* __restrict__ tab) {
+    if (p.k1 < p.k0) return false;
+    if (!probe_is_fast(p)) return true;
+    u32 t[3], full[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
+    mask_bits<3>(full, p.wl);
+    load_bits<3>(b.val, p.pos, t);
+    if ((((t[0] & full[0]) ^ full[0]) | ((t[1] & full[1]) ^ full[1]) | ((t[2] & full[2]) ^ full[2])) != 0u) return true;
+    u32 ph[5], pl[5], q[3];
+    load_bits<3>(b.hi, p.pos, t); mask_bits<3>(t, p.wl); prefix_xor_excl<3>(t, q);
+    ph[0] = q[0]; ph[1] = q[1]; ph[2] = q[2]; ph[3] = 0u; ph[4] = 0u;
+    load_bits<3>(b.lo, p.pos, t); mask_bits<3>(t, p.wl); prefix_xor_excl<3>(t, q);
+    pl[0] = q[0]; pl[1] = q[1]; pl[2] = q[2]; pl[3] = 0u; pl[4] = 0u;
+    int k0 = p.k0;
+    if (k0 < 32) {
+        if (fast_span<0>(ph, pl, p.wl, k0, min(p.k1, 31), tab)) return true;
+        k0 = 32;
+    }
+    return p.k1 >= 32 && fast_span<1>(ph, pl, p.wl, k0, p.k1, tab);
+}
+
+// warp-aggregated append of the flagged lanes' values to a global list
+__device__ __forceinline__ void list_append(bool flag, u32 value, u32* __restrict__ list, u32* __restrict__ count) {
+    u32 m = __ballot_sync(0xffffffffu, flag);
+    if (m) {
+        u32 base = 0;
+        if (lane_id() == 0) base = atomicAdd(count, (u32)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (flag) list[base + __popc(m & ((1u << lane_id()) - 1u))] = value;
+    }
+}
+
+#ifndef TREW_SCREEN_BPS
+#define TREW_SCREEN_BPS 8
+#endif
+__global__ void __launch_bounds__(256, TREW_SCREEN_BPS) trew_screen_kernel(DevCfg cfg, DevBatch b, u32 n_units,
+                                                                          u32* __restrict__ deferred, u32* __restrict__ n_deferred) {
+    __shared__ uint4 tab[kFastTabSize];
+    for (int T = threadIdx.x; T < kFastTabSize; T += blockDim.x) tab[T] = fast_entry(T, (int)cfg.thr_low[T]);
     __syncthreads();
     u32 stride = gridDim.x * blockDim.x;
     u32 n_round = (n_units + 31u) & ~31u;
     for (u32 u = blockIdx.x * blockDim.x + threadIdx.x; u < n_round; u += stride) {
-        bool maybe = false;
+        bool defer = false;
         if (u < n_units) {
             Probe p[4];
             int np = unit_probes(cfg, b, u, p);
-            for (int i = 0; i < np && !maybe; i++) maybe = probe_dispatch<MAXNW>(b, p[i], thr);
+            for (int i = 0; i < np && !defer; i++) defer = screen_probe(b, p[i], tab);
         }
-        u32 m = __ballot_sync(0xffffffffu, maybe);
-        if (m) {
-            u32 base = 0;
-            if (lane_id() == 0) base = atomicAdd(n_survivors, (u32)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (maybe) survivors[base + __popc(m & ((1u << lane_id()) - 1u))] = u;
+        list_append(defer, u, deferred, n_deferred);
+    }
+}
+
+// ---- decide kernel: exact 4-bucket bound + A-parity second level for every (probe, k) of the deferred units ----
+template <int MAXNW>
+__global__ void __launch_bounds__(256) trew_filter_kernel(DevCfg cfg, DevBatch b, const u32* __restrict__ units,
+                                                          const u32* __restrict__ n_units_ptr, u32 n_units_all,
+                                                          u32* __restrict__ survivors, u32* __restrict__ n_survivors) {
+    __shared__ unsigned short thr[kThrTableSize];
+    for (int i = threadIdx.x; i < kThrTableSize; i += blockDim.x) thr[i] = cfg.thr_low[i];
+    __syncthreads();
+    const u32 n_units = units ? *n_units_ptr : n_units_all;   // no list: every unit of the batch
+    u32 stride = gridDim.x * blockDim.x;
+    u32 n_round = (n_units + 31u) & ~31u;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        bool maybe = false;
+        u32 u = 0;
+        if (i < n_units) {
+            u = units ? units[i] : i;
+            Probe p[4];
+            int np = unit_probes(cfg, b, u, p);
+            for (int j = 0; j < np && !maybe; j++) maybe = probe_dispatch<MAXNW>(b, p[j], thr);
         }
+        list_append(maybe, u, survivors, n_survivors);
     }
 }
 
 void launch_filter(const DevCfg& cfg, const DevBatch& b, unsigned int n_units, unsigned int max_read_len,
-                   unsigned int* survivors, unsigned int* n_survivors, int sm_count, cudaStream_t stream) {
+                   unsigned int* deferred, unsigned int* n_deferred, unsigned int* survivors, unsigned int* n_survivors,
+                   int sm_count, cudaStream_t stream) {
     if (n_units == 0) return;
     // longest probe window: a half read, a whole read (n < 4*MAX) or a slice (long mode)
     unsigned int longest;
     if (cfg.mode == 2) longest = 2u * (unsigned)cfg.slice_len;
     else longest = (max_read_len < 4u * (unsigned)cfg.max_mer) ? max_read_len : (max_read_len + 1) / 2;
-    int blocks = sm_count * 8;
     unsigned int need = (n_units + 255) / 256;
+    // the screen handles windows of at most 95 bases; long-mode slices longer than that all go to the decide kernel
+    const bool screen = deferred != nullptr && !(cfg.mode == 2 && cfg.slice_len > kFastMaxWl);
+    if (screen) {
+        int blocks = sm_count * TREW_SCREEN_BPS;
+        if ((unsigned)blocks > need) blocks = (int)need;
+        trew_screen_kernel<<<blocks, 256, 0, stream>>>(cfg, b, n_units, deferred, n_deferred);
+    }
+    const unsigned int* list = screen ? deferred : nullptr;
+    int blocks = sm_count * 8;
     if ((unsigned)blocks > need) blocks = (int)need;
-    if (longest + 1 <= 96) trew_filter_kernel<3><<<blocks, 256, 0, stream>>>(cfg, b, n_units, survivors, n_survivors);
-    else if (longest + 1 <= 160) trew_filter_kernel<5><<<blocks, 256, 0, stream>>>(cfg, b, n_units, survivors, n_survivors);
-    else trew_filter_kernel<8><<<blocks, 256, 0, stream>>>(cfg, b, n_units, survivors, n_survivors);
+    if (longest + 1 <= 96) trew_filter_kernel<3><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors);
+    else if (longest + 1 <= 160) trew_filter_kernel<5><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors);
+    else trew_filter_kernel<8><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors);
 }
 
 // ------------------------------------------------------------------------------------------------
 // exact kernel: warp per survivor unit
 // ------------------------------------------------------------------------------------------------
+//
+// Per-warp shared-memory region (all state a warp needs between its building blocks lives here, addressed from
+// the kernel's dynamic shared-memory base so every access is a shared-space LDS/STS):
+//   header (16 words)  | planes H L V PH PL (36 words each, word j owned by lane j) | rev2 (36 x u64)
+//   run_lo / run_hi (u64[cap])  | htab (u32[hs])  | grp_tot / grp_last (u32[cap])
+//   run_start (u16[cap]) | run_cw (u16[cap + 4]) | run_total (u16[cap])
+
+extern __shared__ __align__(16) unsigned char g_smem[];
 
 constexpr int kPlaneWords = 36;  // 32 window words + zero padding for shifted reads
 #ifndef TREW_EXACT_BPS
-#define TREW_EXACT_BPS 8   // resident exact-kernel blocks per SM (latency-bound: occupancy beats registers)
+#define TREW_EXACT_BPS 8   // resident exact-kernel blocks per SM the register budget allows
 #endif
 constexpr int kExactWarps = 4;
+constexpr u32 kEmptySlot = 0xffffffffu;
 
-struct WarpMem {
-    u32* H; u32* L; u32* V; u32* PH; u32* PL;  // kPlaneWords each; word j owned by lane j
-    u64* rev2;                                   // kPlaneWords words: reversed, interleaved 2-bit stream
-    unsigned short* run_start;                   // [cap]
-    unsigned short* run_cw;                      // [cap + 1] ordinal of the run's first window among valid windows
-    unsigned short* run_total;                   // [cap] class total for leaders, 0 otherwise
-    u64* run_lo; u64* run_hi;                    // [cap] canonical rotation of the run's class
-    u32* run_hash;                               // [cap + 4] 32-bit fold of the canonical rotation
-    int cap;
-};
+enum { HD_CUR_POS = 0, HD_CUR_LEN, HD_ALLVALID, HD_EV_POS, HD_EV_LEN, HD_EV_K, HD_EV_PACK, HD_S = 8 /* 4 words: s_lo, s_hi */ };
+
+__host__ __device__ inline int exact_hash_slots(int cap) {
+    int hs = 64;
+    while (hs < cap + cap / 4) hs <<= 1;
+    return hs;
+}
 
 __host__ __device__ inline size_t exact_warp_bytes(int cap) {
-    size_t b = 5 * kPlaneWords * sizeof(u32) + kPlaneWords * sizeof(u64);
+    size_t b = 64 + 5 * kPlaneWords * sizeof(u32) + kPlaneWords * sizeof(u64);
+    b += (size_t)2 * cap * sizeof(u64) + (size_t)exact_hash_slots(cap) * sizeof(u32) + (size_t)2 * cap * sizeof(u32);
     b += (size_t)(3 * cap + 4) * sizeof(unsigned short);
-    b = (b + 15) & ~(size_t)15;
-    b += (size_t)2 * cap * sizeof(u64);
-    b += (size_t)(cap + 4) * sizeof(u32);
     return (b + 15) & ~(size_t)15;
 }
 
 size_t exact_smem_bytes(int run_cap, bool) { return exact_warp_bytes(run_cap) * kExactWarps; }
 
-struct KStat { int T, M; u64 s_lo, s_hi; bool homo; int nruns; };
+struct WS {  // this warp's region
+    u32 off; int cap; int hs;
+    __device__ __forceinline__ u32* hdr() const { return (u32*)(g_smem + off); }
+    __device__ __forceinline__ u32* H() const { return (u32*)(g_smem + off + 64); }
+    __device__ __forceinline__ u32* L() const { return H() + kPlaneWords; }
+    __device__ __forceinline__ u32* V() const { return H() + 2 * kPlaneWords; }
+    __device__ __forceinline__ u32* PH() const { return H() + 3 * kPlaneWords; }
+    __device__ __forceinline__ u32* PL() const { return H() + 4 * kPlaneWords; }
+    __device__ __forceinline__ u64* rev2() const { return (u64*)(H() + 5 * kPlaneWords); }
+    __device__ __forceinline__ u64* run_lo() const { return rev2() + kPlaneWords; }
+    __device__ __forceinline__ u64* run_hi() const { return run_lo() + cap; }
+    __device__ __forceinline__ u32* htab() const { return (u32*)(run_hi() + cap); }
+    __device__ __forceinline__ u32* grp_tot() const { return htab() + hs; }
+    __device__ __forceinline__ u32* grp_last() const { return grp_tot() + cap; }
+    __device__ __forceinline__ unsigned short* run_start() const { return (unsigned short*)(grp_last() + cap); }
+    __device__ __forceinline__ unsigned short* run_cw() const { return run_start() + cap; }
+    __device__ __forceinline__ unsigned short* run_total() const { return run_cw() + cap + 4; }
+};
+
+struct TableRef { Slot* slots; u32 mask; u32* err; };
 
 struct ScanRes { int th, tl; u64 sh_lo, sh_hi, sl_lo, sl_hi; };
+
+// packed result of eval_k: T (bits 0-9), M (10-19), number of runs (20-29), homopolymer flag (30)
+__device__ __forceinline__ int pk_T(u32 p) { return (int)(p & 1023u); }
+__device__ __forceinline__ int pk_M(u32 p) { return (int)((p >> 10) & 1023u); }
+__device__ __forceinline__ int pk_runs(u32 p) { return (int)((p >> 20) & 1023u); }
+__device__ __forceinline__ bool pk_homo(u32 p) { return ((p >> 30) & 1u) != 0; }
 
 // ---- k-mer arithmetic (src/kmer.cpp:39-74, 1815-1867) ------------------------------------------
 
@@ -502,37 +653,30 @@ __device__ __forceinline__ bool less_pair(u64 alo, u64 ahi, u64 blo, u64 bhi) {
     return ahi < bhi || (ahi == bhi && alo < blo);
 }
 
-// ---- warp state ----------------------------------------------------------------------------------
-
-struct Warp {
-    WarpMem m;
-    u32 lane;
-    u32 cur_pos; int cur_len;  // window currently loaded (cur_len < 0: none)
-    u32 h, l, v;               // this lane's word of the window planes
-    u32 ev_pos; int ev_len, ev_k;  // (window, k) whose run list is in shared memory (ev_k < 0: none)
-    KStat ev;
-};
-
 __device__ __forceinline__ u32 shfl_next_bit0(u32 x, u32 lane) {  // bit 0 of the next lane's word (0 for lane 31)
     u32 nx = __shfl_down_sync(0xffffffffu, x, 1);
     return lane == 31 ? 0u : (nx & 1u);
 }
 
+// ---- window loading --------------------------------------------------------------------------------
+
 // load window [pos, pos+len) of the batch planes; builds prefix-XOR planes and the reversed 2-bit stream
-__device__ __noinline__ void load_window(Warp& w, const DevBatch& b, u32 pos, int len) {
-    if (w.cur_len == len && w.cur_pos == pos) return;
+__device__ __noinline__ void load_window(WS ws, const u32* __restrict__ bhi, const u32* __restrict__ blo,
+                                         const u32* __restrict__ bval, u32 pos, int len) {
+    u32* hd = ws.hdr();
+    if ((int)hd[HD_CUR_LEN] == len && hd[HD_CUR_POS] == pos) return;
     __syncwarp();
-    const u32 lane = w.lane;
+    const u32 lane = lane_id();
     int vbits = len - 32 * (int)lane;
     u32 msk = vbits <= 0 ? 0u : low_mask(vbits);
     u32 h = 0, l = 0, v = 0;
     if (vbits > 0) {
         u32 wi = (pos >> 5) + lane, sh = pos & 31;
-        h = __funnelshift_r(__ldg(b.hi + wi), __ldg(b.hi + wi + 1), sh) & msk;
-        l = __funnelshift_r(__ldg(b.lo + wi), __ldg(b.lo + wi + 1), sh) & msk;
-        v = __funnelshift_r(__ldg(b.val + wi), __ldg(b.val + wi + 1), sh) & msk;
+        h = __funnelshift_r(__ldg(bhi + wi), __ldg(bhi + wi + 1), sh) & msk;
+        l = __funnelshift_r(__ldg(blo + wi), __ldg(blo + wi + 1), sh) & msk;
+        v = __funnelshift_r(__ldg(bval + wi), __ldg(bval + wi + 1), sh) & msk;
     }
-    w.h = h; w.l = l; w.v = v;
+    const bool all_valid = __all_sync(0xffffffffu, v == msk);
     // exclusive prefix-XOR planes, word j in lane j (len + 1 <= 1024 entries)
     u32 ih = prefix_xor32(h), il = prefix_xor32(l);
     u32 bh = __ballot_sync(0xffffffffu, ih >> 31), bl = __ballot_sync(0xffffffffu, il >> 31);
@@ -542,10 +686,12 @@ __device__ __noinline__ void load_window(Warp& w, const DevBatch& b, u32 pos, in
     u32 ph_prev = __shfl_up_sync(0xffffffffu, ih, 1), pl_prev = __shfl_up_sync(0xffffffffu, il, 1);
     u32 ph = (ih << 1) | (lane ? ph_prev >> 31 : 0u);
     u32 pl = (il << 1) | (lane ? pl_prev >> 31 : 0u);
-    w.m.H[lane] = h; w.m.L[lane] = l; w.m.V[lane] = v; w.m.PH[lane] = ph; w.m.PL[lane] = pl;
+    u32 *H = ws.H(), *L = ws.L(), *V = ws.V(), *PH = ws.PH(), *PL = ws.PL();
+    u64* rev2 = ws.rev2();
+    H[lane] = h; L[lane] = l; V[lane] = v; PH[lane] = ph; PL[lane] = pl;
     if (lane < kPlaneWords - 32) {
-        w.m.H[32 + lane] = 0; w.m.L[32 + lane] = 0; w.m.V[32 + lane] = 0; w.m.PH[32 + lane] = 0; w.m.PL[32 + lane] = 0;
-        w.m.rev2[32 + lane] = 0;
+        H[32 + lane] = 0; L[32 + lane] = 0; V[32 + lane] = 0; PH[32 + lane] = 0; PL[32 + lane] = 0;
+        rev2[32 + lane] = 0;
     }
     __syncwarp();
     // reversed interleaved stream: 64-bit word j covers reversed positions [32j, 32j+32), i.e. original
@@ -557,11 +703,11 @@ __device__ __noinline__ void load_window(Warp& w, const DevBatch& b, u32 pos, in
         if (cs > -32) {
             if (cs >= 0) {
                 int wi = cs >> 5, sh = cs & 31;
-                hb = __funnelshift_r(w.m.H[wi], w.m.H[wi + 1], sh);
-                lb = __funnelshift_r(w.m.L[wi], w.m.L[wi + 1], sh);
+                hb = __funnelshift_r(H[wi], H[wi + 1], sh);
+                lb = __funnelshift_r(L[wi], L[wi + 1], sh);
             } else {
-                hb = w.m.H[0] << (-cs);
-                lb = w.m.L[0] << (-cs);
+                hb = H[0] << (-cs);
+                lb = L[0] << (-cs);
             }
         }
         hb = __brev(hb); lb = __brev(lb);
@@ -571,33 +717,38 @@ __device__ __noinline__ void load_window(Warp& w, const DevBatch& b, u32 pos, in
         x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0FULL;  y = (y | (y << 4)) & 0x0F0F0F0F0F0F0F0FULL;
         x = (x | (x << 2)) & 0x3333333333333333ULL;  y = (y | (y << 2)) & 0x3333333333333333ULL;
         x = (x | (x << 1)) & 0x5555555555555555ULL;  y = (y | (y << 1)) & 0x5555555555555555ULL;
-        w.m.rev2[lane] = (x << 1) | y;
+        rev2[lane] = (x << 1) | y;
     }
+    if (lane == 0) { hd[HD_CUR_POS] = pos; hd[HD_CUR_LEN] = (u32)len; hd[HD_ALLVALID] = all_valid ? 1u : 0u; }
     __syncwarp();
-    w.cur_pos = pos; w.cur_len = len;
 }
 
-// k-mer starting at base i (first base most significant)
-__device__ __forceinline__ void kmer_at(const Warp& w, int i, int k, u64& lo, u64& hi) {
-    int o = 2 * (w.cur_len - i - k);
+// k-mer starting at base i of the loaded window (first base most significant)
+__device__ __forceinline__ void kmer_at(const u64* __restrict__ rev2, int len, int i, int k, u64& lo, u64& hi) {
+    int o = 2 * (len - i - k);
     int wi = o >> 6, sh = o & 63;
-    u64 a = w.m.rev2[wi], b = w.m.rev2[wi + 1];
+    u64 a = rev2[wi], b = rev2[wi + 1];
     lo = sh ? (a >> sh) | (b << (64 - sh)) : a;
     if (k <= 32) {
         if (k < 32) lo &= (1ULL << (2 * k)) - 1ULL;
         hi = 0;
     } else {
-        u64 c = w.m.rev2[wi + 2];
+        u64 c = rev2[wi + 2];
         hi = sh ? (b >> sh) | (c << (64 - sh)) : b;
         if (k < 64) hi &= (1ULL << (2 * k - 64)) - 1ULL;
     }
 }
 
-// window-valid word for period k from scratch: WV_1 = V, WV_{t+1} = WV_t & (WV_t >> 1)
-__device__ __forceinline__ u32 wv_for_k(const Warp& w, int k) {
-    u32 wv = w.v;
+// this lane's window-valid word for period k: bit i of word j set iff bases 32j+i .. 32j+i+k-1 are all valid
+__device__ __forceinline__ u32 wv_for_k(WS ws, int len, int k) {
+    const u32 lane = lane_id();
+    if (ws.hdr()[HD_ALLVALID]) {
+        int vb = len - k + 1 - 32 * (int)lane;
+        return vb <= 0 ? 0u : low_mask(min(32, vb));
+    }
+    u32 wv = ws.V()[lane];
     for (int t = 1; t < k; t++) {
-        u32 nb = shfl_next_bit0(wv, w.lane);
+        u32 nb = shfl_next_bit0(wv, lane);
         wv &= (wv >> 1) | (nb << 31);
     }
     return wv;
@@ -608,12 +759,14 @@ __device__ __forceinline__ u32 wv_step(u32 wv, u32 lane) {
     return wv & ((wv >> 1) | (nb << 31));
 }
 
-// upper bound on the largest class count for period k from the 4-bucket parity signature
-__device__ __forceinline__ int bound_k(const Warp& w, int k, u32 wv, int T) {
+// upper bound on the largest class count for period k from the 4-bucket parity signature (warp-cooperative)
+__device__ __forceinline__ int bound_k(WS ws, int k, u32 wv, int T) {
+    const u32 lane = lane_id();
+    const u32 *PH = ws.PH(), *PL = ws.PL();
     int s = k >> 5, r = k & 31;
-    u32 qh = __funnelshift_r(w.m.PH[w.lane + s], w.m.PH[w.lane + s + 1], r);
-    u32 ql = __funnelshift_r(w.m.PL[w.lane + s], w.m.PL[w.lane + s + 1], r);
-    u32 dh = (qh ^ w.m.PH[w.lane]) & wv, dl = (ql ^ w.m.PL[w.lane]) & wv;
+    u32 qh = __funnelshift_r(PH[lane + s], PH[lane + s + 1], r);
+    u32 ql = __funnelshift_r(PL[lane + s], PL[lane + s + 1], r);
+    u32 dh = (qh ^ PH[lane]) & wv, dl = (ql ^ PL[lane]) & wv;
     u32 packed = (u32)__popc(dh) | ((u32)__popc(dl) << 10) | ((u32)__popc(dh & dl) << 20);
     packed = __reduce_add_sync(0xffffffffu, packed);
     int cH = packed & 1023, cL = (packed >> 10) & 1023, c11 = packed >> 20;
@@ -623,19 +776,19 @@ __device__ __forceinline__ int bound_k(const Warp& w, int k, u32 wv, int T) {
 
 // Exact class statistics of the loaded window for one period (the inner loops of k_mer_check,
 // src/kmer.cpp:2183-2216, without the early break): T valid windows, M largest class, S the class that
-// first reaches M.  Leaves the run list in shared memory (run_lo/hi canonical class per run, run_total
-// class total on the first run of each class) for emit_classes().
-__device__ __noinline__ KStat eval_k(Warp& w, int k, u32 wv) {
-    KStat ks; ks.T = 0; ks.M = 0; ks.s_lo = ks.s_hi = 0; ks.homo = false; ks.nruns = 0;
-    const u32 lane = w.lane;
+// first reaches M (stored in the header).  Leaves the run list in shared memory (run_lo/hi canonical class
+// per run, run_total = class total on one run of each class, 0 on the others) for emit_classes().
+__device__ __noinline__ u32 eval_k(WS ws, int len, int k, u32 wv) {
+    const u32 lane = lane_id();
+    u32* hd = ws.hdr();
     int T = (int)__reduce_add_sync(0xffffffffu, (u32)__popc(wv));
-    ks.T = T;
-    if (T == 0) return ks;
+    if (T == 0) return 0u;
+    const u32 *H = ws.H(), *L = ws.L();
     // link bits: windows i and i+1 are both valid and base[i] == base[i+k]   (Lemma L1)
     int s = k >> 5, r = k & 31;
-    u32 hs = __funnelshift_r(w.m.H[lane + s], w.m.H[lane + s + 1], r);
-    u32 ls = __funnelshift_r(w.m.L[lane + s], w.m.L[lane + s + 1], r);
-    u32 eq = ~((hs ^ w.h) | (ls ^ w.l));
+    u32 hs = __funnelshift_r(H[lane + s], H[lane + s + 1], r);
+    u32 ls = __funnelshift_r(L[lane + s], L[lane + s + 1], r);
+    u32 eq = ~((hs ^ H[lane]) | (ls ^ L[lane]));
     u32 nb = shfl_next_bit0(wv, lane);
     u32 link = eq & wv & ((wv >> 1) | (nb << 31));
     u32 link_prev = __shfl_up_sync(0xffffffffu, link, 1);
@@ -649,98 +802,118 @@ __device__ __noinline__ KStat eval_k(Warp& w, int k, u32 wv) {
         if ((int)lane >= d) inc += t;
     }
     u32 exc = inc - pk;
-    int R = (int)(__shfl_sync(0xffffffffu, inc, 31) >> 16);
-    ks.nruns = R;
+    const int R = (int)(__shfl_sync(0xffffffffu, inc, 31) >> 16);
+    unsigned short *run_start = ws.run_start(), *run_cw = ws.run_cw(), *run_total = ws.run_total();
+    u64 *run_lo = ws.run_lo(), *run_hi = ws.run_hi();
+    u32 *htab = ws.htab(), *grp_tot = ws.grp_tot(), *grp_last = ws.grp_last();
     {
         u32 cwb = exc & 0xffffu, rb = exc >> 16;
         u32 x = rs;
         while (x) {
             int bit = __ffs(x) - 1;
             x &= x - 1;
-            w.m.run_start[rb] = (unsigned short)(32 * lane + bit);
-            w.m.run_cw[rb] = (unsigned short)(cwb + __popc(wv & ((1u << bit) - 1u)));
+            run_start[rb] = (unsigned short)(32 * lane + bit);
+            run_cw[rb] = (unsigned short)(cwb + __popc(wv & ((1u << bit) - 1u)));
             rb++;
         }
-        if (lane == 0) w.m.run_cw[R] = (unsigned short)T;
+        if (lane == 0) run_cw[R] = (unsigned short)T;
     }
+    // hash table sized to the run count (power of two >= 2R, at most hs)
+    int hsz = 64;
+    while (hsz < 2 * R && hsz < ws.hs) hsz <<= 1;
+    const u32 hmask = (u32)hsz - 1u;
+    for (int i = lane; i < hsz; i += 32) htab[i] = kEmptySlot;
+    for (int q = lane; q < R; q += 32) { grp_tot[q] = 0u; grp_last[q] = 0u; }
     __syncwarp();
+    const u64* rev2 = ws.rev2();
+    const bool wide = k > 32;
     // one canonicalisation per run
     for (int q = lane; q < R; q += 32) {
         u64 lo, hi;
-        kmer_at(w, w.m.run_start[q], k, lo, hi);
+        kmer_at(rev2, len, run_start[q], k, lo, hi);
         canon_pair(lo, hi, k);
-        w.m.run_lo[q] = lo; w.m.run_hi[q] = hi;
-        w.m.run_hash[q] = (u32)lo ^ (u32)(lo >> 32) ^ (u32)hi ^ (u32)(hi >> 32);
+        run_lo[q] = lo; if (wide) run_hi[q] = hi;
     }
     __syncwarp();
-    // merge runs of the same class: total windows, ordinal of the class's last window, leader = first run.
-    // All pairs, but the inner loop only touches a 32-bit hash per run (4 per 128-bit load); the full key and
-    // the counts are read on a hash hit only.
+    // group runs of the same class through the hash table: the first run to claim a slot leads its class and
+    // collects the class's window total and the ordinal of its last window
+    for (int q = lane; q < R; q += 32) {
+        u64 lo = run_lo[q], hi = wide ? run_hi[q] : 0ULL;
+        u32 hsh = (u32)lo ^ (u32)(lo >> 32) ^ (u32)hi ^ (u32)(hi >> 32);
+        u32 slot = (hsh * 0x9e3779b1u) >> 7 & hmask;
+        int leader;
+        for (;;) {
+            u32 old = atomicCAS(&htab[slot], kEmptySlot, (u32)q);
+            if (old == kEmptySlot) { leader = q; break; }
+            if (run_lo[old] == lo && (!wide || run_hi[old] == hi)) { leader = (int)old; break; }
+            slot = (slot + 1) & hmask;
+        }
+        u32 c0 = run_cw[q], c1 = run_cw[q + 1];
+        atomicAdd(&grp_tot[leader], c1 - c0);
+        atomicMax(&grp_last[leader], c1 - 1u);
+    }
+    __syncwarp();
     u32 best = 0; int best_q = -1;
-    const bool wide = k > 32;
-    const int R4 = (R + 3) & ~3;
-    for (int q0 = 0; q0 < R; q0 += 32) {
-        int q = q0 + lane;
-        if (q < R) {
-            u64 mlo = w.m.run_lo[q], mhi = w.m.run_hi[q];
-            u32 mh = w.m.run_hash[q];
-            int total = 0, last = 0; bool leader = true;
-            for (int p4 = 0; p4 < R4; p4 += 4) {
-                uint4 hv = *reinterpret_cast<const uint4*>(w.m.run_hash + p4);
-                u32 hh[4] = {hv.x, hv.y, hv.z, hv.w};
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    int p = p4 + t;
-                    if (hh[t] == mh && p < R && w.m.run_lo[p] == mlo && (!wide || w.m.run_hi[p] == mhi)) {
-                        int c0 = w.m.run_cw[p], c1 = w.m.run_cw[p + 1];
-                        total += c1 - c0; last = max(last, c1 - 1);
-                        if (p < q) leader = false;
-                    }
-                }
-            }
-            w.m.run_total[q] = leader ? (unsigned short)total : (unsigned short)0;
-            if (leader) {
-                // K_MER_DATA_MAX_SEQ: the class whose running count first reaches the final maximum
-                // (strict '<' at src/kmer.cpp:2202) = max total, ties broken by the EARLIEST last window
-                u32 score = ((u32)total << 10) | (u32)(1023 - last);
-                if (score > best) { best = score; best_q = q; }
-            }
+    for (int q = lane; q < R; q += 32) {
+        u32 total = grp_tot[q];
+        run_total[q] = (unsigned short)total;
+        if (total) {
+            // K_MER_DATA_MAX_SEQ: the class whose running count first reaches the final maximum
+            // (strict '<' at src/kmer.cpp:2202) = max total, ties broken by the EARLIEST last window
+            u32 score = (total << 10) | (1023u - grp_last[q]);
+            if (score > best) { best = score; best_q = q; }
         }
     }
     u32 wbest = __reduce_max_sync(0xffffffffu, best);
     u32 who = __ballot_sync(0xffffffffu, best == wbest && best_q >= 0);
-    int src = __ffs(who) - 1;
-    int bq = __shfl_sync(0xffffffffu, best_q, src);
+    int bq = __shfl_sync(0xffffffffu, best_q, __ffs(who) - 1);
+    u64 s_lo = run_lo[bq], s_hi = wide ? run_hi[bq] : 0ULL;
+    bool homo = homo_pair(s_lo, s_hi, k);
+    u32 packed = (u32)T | ((wbest >> 10) << 10) | ((u32)R << 20) | (homo ? 1u << 30 : 0u);
+    if (lane == 0) {
+        hd[HD_S] = (u32)s_lo; hd[HD_S + 1] = (u32)(s_lo >> 32); hd[HD_S + 2] = (u32)s_hi; hd[HD_S + 3] = (u32)(s_hi >> 32);
+    }
     __syncwarp();
-    ks.M = (int)(wbest >> 10);
-    ks.s_lo = w.m.run_lo[bq]; ks.s_hi = w.m.run_hi[bq];
-    ks.homo = homo_pair(ks.s_lo, ks.s_hi, k);
-    return ks;
+    return packed;
+}
+
+__device__ __forceinline__ void eval_S(WS ws, u64& lo, u64& hi) {
+    const u32* hd = ws.hdr();
+    lo = (u64)hd[HD_S] | ((u64)hd[HD_S + 1] << 32);
+    hi = (u64)hd[HD_S + 2] | ((u64)hd[HD_S + 3] << 32);
 }
 
 // add every distinct class of the last eval_k() to a result table (optionally RC-folded)
-__device__ __noinline__ void emit_classes(const DevCfg& cfg, Warp& w, int k, int nruns, int table, bool folded) {
+__device__ __noinline__ void emit_classes(TableRef tr, WS ws, int k, int nruns, int table, bool folded) {
     u32 meta = ((u32)table << 8) | (u32)k;
-    for (int q = w.lane; q < nruns; q += 32) {
-        int total = w.m.run_total[q];
+    const unsigned short* run_total = ws.run_total();
+    const u64 *run_lo = ws.run_lo(), *run_hi = ws.run_hi();
+    for (int q = lane_id(); q < nruns; q += 32) {
+        int total = run_total[q];
         if (total == 0) continue;
-        u64 lo = w.m.run_lo[q], hi = w.m.run_hi[q];
+        u64 lo = run_lo[q], hi = k > 32 ? run_hi[q] : 0ULL;
         if (folded) {
             u64 rlo = lo, rhi = hi;
             crc_pair(rlo, rhi, k);
             if (less_pair(rlo, rhi, lo, hi)) { lo = rlo; hi = rhi; }
         }
-        table_add(cfg, meta, lo, hi, (u64)total);
+        table_add_impl(tr.slots, tr.mask, tr.err, meta, lo, hi, (u64)total);
     }
     __syncwarp();
 }
 
-// bit j set for every multiple j of k, j <= 64 (bit 64 does not exist: k = 64 is never a proper divisor target)
-__device__ __forceinline__ u64 multiples_mask(int k) {
-    u64 m = 0;
-    for (int j = k; j < 64; j += k) m |= 1ULL << j;
-    return m;
+// multiples of k below 64 as a bit mask (bit j set iff k | j, 0 < j < 64); k = 64 is tracked separately
+struct MultTab { u64 m[65]; };
+constexpr MultTab make_mult_tab() {
+    MultTab t{};
+    for (int k = 1; k <= 64; k++) {
+        u64 m = 0;
+        for (int j = k; j < 64; j += k) m |= 1ULL << j;
+        t.m[k] = m;
+    }
+    return t;
 }
+__constant__ MultTab c_mult = make_mult_tab();
 
 // k_mer_check / k_mer_check_128 (src/kmer.cpp:2144-2547) without emission: target_k_high / target_k_low and
 // the K_MER_DATA_MAX_SEQ of each.  Periods that cannot be accepted by either selection (divisor rule,
@@ -750,165 +923,132 @@ __device__ __forceinline__ u64 multiples_mask(int k) {
 // M >= need*T*(1 - 2^-53), and U >= M, so "U >= need*T*(1 - 1e-12)" (evaluated in double, relative error
 // ~2^-52) never rejects a period the reference would accept.  The exact test after eval_k uses the same
 // IEEE division as the reference.
-struct SelState {
+__device__ __noinline__ ScanRes scan_stats(WS ws, DevBatch b, u32 pos, int len, int kmin, int kmax, double low, double high) {
     ScanRes res;
-    u64 blockedL, blockedH;   // periods with an accepted divisor (k % tk == 0, src/kmer.cpp:2225-2230)
-    bool blk64L, blk64H;
-    double needL, needH;      // max(baseline, last accepted frequency)
-};
-
-// one exact evaluation + the two acceptance tests of src/kmer.cpp:2221-2258
-__device__ __noinline__ void consider(Warp& w, SelState& st, u32 pos, int len, int k, u32 wv) {
-    KStat ks = eval_k(w, k, wv);
-    w.ev = ks; w.ev_pos = pos; w.ev_len = len; w.ev_k = k;
-    if (ks.homo) return;
-    bool blkL = k < 64 ? ((st.blockedL >> k) & 1ULL) != 0 : st.blk64L;
-    bool blkH = k < 64 ? ((st.blockedH >> k) & 1ULL) != 0 : st.blk64H;
-    double f = (double)ks.M / (double)ks.T;
-    bool accL = !blkL && f >= st.needL, accH = !blkH && f >= st.needH;
-    if (accL || accH) {
-        u64 mm = multiples_mask(k);
-        bool m64 = (64 % k) == 0;
-        if (accL) { st.res.tl = k; st.needL = f; st.blockedL |= mm; st.blk64L |= m64; st.res.sl_lo = ks.s_lo; st.res.sl_hi = ks.s_hi; }
-        if (accH) { st.res.th = k; st.needH = f; st.blockedH |= mm; st.blk64H |= m64; st.res.sh_lo = ks.s_lo; st.res.sh_hi = ks.s_hi; }
-    }
-}
-
-__device__ __noinline__ ScanRes scan_stats(const DevCfg& cfg, Warp& w, const DevBatch& b, u32 pos, int len, int kmin, int kmax) {
-    SelState st;
-    st.res.th = st.res.tl = 0; st.res.sh_lo = st.res.sh_hi = st.res.sl_lo = st.res.sl_hi = 0;
-    if (kmax < kmin) return st.res;
-    load_window(w, b, pos, len);
-    st.blockedL = st.blockedH = 0; st.blk64L = st.blk64H = false;
-    st.needL = cfg.low; st.needH = cfg.high;
+    res.th = res.tl = 0; res.sh_lo = res.sh_hi = res.sl_lo = res.sl_hi = 0;
+    if (kmax < kmin) return res;
+    load_window(ws, b.hi, b.lo, b.val, pos, len);
+    u64 blockedL = 0, blockedH = 0;   // periods with an accepted divisor (k % tk == 0, src/kmer.cpp:2225-2230)
+    bool blk64L = false, blk64H = false;
+    double needL = low, needH = high; // max(baseline, last accepted frequency)
     const double slack = 1.0 - 1e-12;
-    const u32 lane = w.lane;
+    const u32 lane = lane_id();
+    u32* hd = ws.hdr();
+    const bool all_valid = hd[HD_ALLVALID] != 0;
 
-    // Visit, in ascending order, the periods of one 32-wide block whose bound reached the LOW threshold.
-    // U / T are per-lane (lane <-> period kb + lane); wv_of(bit) yields this lane's window-valid word.
-    auto visit = [&](int kb, u32 cm, int U, int T, auto wv_of) {
-        while (cm) {
-            int bit = __ffs(cm) - 1;
-            cm &= cm - 1;
-            int kk = kb + bit;
-            bool blkL = kk < 64 ? ((st.blockedL >> kk) & 1ULL) != 0 : st.blk64L;
-            bool blkH = kk < 64 ? ((st.blockedH >> kk) & 1ULL) != 0 : st.blk64H;
-            int Uk = __shfl_sync(0xffffffffu, U, bit), Tk = __shfl_sync(0xffffffffu, T, bit);
-            u32 wv = wv_of(bit, Tk);
-            if (blkL && blkH) continue;
-            double dU = (double)Uk, dT = (double)Tk;
-            bool candL = !blkL && dU >= st.needL * dT * slack, candH = !blkH && dU >= st.needH * dT * slack;
-            if (!candL && !candH) continue;
-            consider(w, st, pos, len, kk, wv);
+    // one exact evaluation + the two acceptance tests of src/kmer.cpp:2221-2258
+    auto try_k = [&](int kk, int Uk, int Tk, u32 wv) {
+        bool blkL = kk < 64 ? ((blockedL >> kk) & 1ULL) != 0 : blk64L;
+        bool blkH = kk < 64 ? ((blockedH >> kk) & 1ULL) != 0 : blk64H;
+        if (blkL && blkH) return;
+        double dU = (double)Uk, dT = (double)Tk;
+        bool candL = !blkL && dU >= needL * dT * slack, candH = !blkH && dU >= needH * dT * slack;
+        if (!candL && !candH) return;
+        u32 ev = eval_k(ws, len, kk, wv);
+        if (lane == 0) { hd[HD_EV_POS] = pos; hd[HD_EV_LEN] = (u32)len; hd[HD_EV_K] = (u32)kk; hd[HD_EV_PACK] = ev; }
+        __syncwarp();
+        if (pk_homo(ev) || pk_T(ev) == 0) return;
+        double f = (double)pk_M(ev) / (double)pk_T(ev);
+        bool accL = !blkL && f >= needL, accH = !blkH && f >= needH;
+        if (accL || accH) {
+            u64 mm = c_mult.m[kk];
+            bool m64 = (64 % kk) == 0;
+            u64 slo, shi;
+            eval_S(ws, slo, shi);
+            if (accL) { res.tl = kk; needL = f; blockedL |= mm; blk64L |= m64; res.sl_lo = slo; res.sl_hi = shi; }
+            if (accH) { res.th = kk; needH = f; blockedH |= mm; blk64H |= m64; res.sh_lo = slo; res.sh_hi = shi; }
         }
     };
 
-    if (len <= 127) {
-        // Short window (the 75 / 150-base case): every lane bounds its own period (lane <-> k) with the
-        // window's planes held in registers, invalid bases included; no cross-lane traffic until a
-        // period qualifies.
-        u32 ph[5], pl[5], vv[4];
-#pragma unroll
-        for (int j = 0; j < 5; j++) { ph[j] = w.m.PH[j]; pl[j] = w.m.PL[j]; }
-#pragma unroll
-        for (int j = 0; j < 4; j++) vv[j] = w.m.V[j];
+    if (len <= 127 || all_valid) {
+        // Every lane bounds its own period (lane <-> k); the qualifying periods are then visited in ascending order.
+        const u32 *PH = ws.PH(), *PL = ws.PL(), *V = ws.V();
+        const int nw = (len + 31) >> 5;
         for (int kb = kmin; kb <= kmax; kb += 32) {
             const int k = kb + (int)lane;
-            u32 wvv[4] = {0, 0, 0, 0};
             int U = 0, T = 0;
-            if (k <= kmax) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) wvv[j] = vv[j];
-                sliding_and<4>(wvv, k);
-                u32 qh[5], ql[5];
-                shr_var<5>(ph, k, qh);
-                shr_var<5>(pl, k, ql);
-                int cH = 0, cL = 0, c11 = 0;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    u32 dh = (qh[j] ^ ph[j]) & wvv[j], dl = (ql[j] ^ pl[j]) & wvv[j];
-                    T += __popc(wvv[j]); cH += __popc(dh); cL += __popc(dl); c11 += __popc(dh & dl);
-                }
-                int c10 = cH - c11, c01 = cL - c11, c00 = T - cH - cL + c11;
-                U = max(max(c00, c01), max(c10, c11));
-            }
-            bool cand = T > 0 && (double)U >= cfg.low * (double)T * slack;
-            u32 cm = __ballot_sync(0xffffffffu, cand);
-            visit(kb, cm, U, T, [&](int bit, int) {
-                u32 a0 = __shfl_sync(0xffffffffu, wvv[0], bit), a1 = __shfl_sync(0xffffffffu, wvv[1], bit);
-                u32 a2 = __shfl_sync(0xffffffffu, wvv[2], bit), a3 = __shfl_sync(0xffffffffu, wvv[3], bit);
-                return lane == 0 ? a0 : lane == 1 ? a1 : lane == 2 ? a2 : lane == 3 ? a3 : 0u;
-            });
-        }
-        return st.res;
-    }
-
-    const bool all_valid = (int)__reduce_add_sync(0xffffffffu, (u32)__popc(w.v)) == len;
-    if (all_valid) {
-        // Long window without invalid bases: the valid windows of period k are positions [0, len - k].
-        for (int kb = kmin; kb <= kmax; kb += 32) {
-            const int k = kb + (int)lane;
-            const int T = (k <= kmax && len - k + 1 > 0) ? len - k + 1 : 0;
-            int U = 0;
-            if (T > 0) {
+            u32 wvv[4] = {0u, 0u, 0u, 0u};   // this lane's window-valid words (short windows with invalid bases only)
+            if (k <= kmax && k <= len) {
                 const int s = k >> 5, r = k & 31;
                 int cH = 0, cL = 0, c11 = 0;
-                for (int j = 0; j * 32 < T; j++) {
-                    u32 wvj = low_mask(min(32, T - 32 * j));
-                    u32 dh = (__funnelshift_r(w.m.PH[j + s], w.m.PH[j + s + 1], r) ^ w.m.PH[j]) & wvj;
-                    u32 dl = (__funnelshift_r(w.m.PL[j + s], w.m.PL[j + s + 1], r) ^ w.m.PL[j]) & wvj;
-                    cH += __popc(dh); cL += __popc(dl); c11 += __popc(dh & dl);
+                if (all_valid) {
+                    T = len - k + 1;
+                    for (int j = 0; j * 32 < T; j++) {
+                        u32 wvj = low_mask(min(32, T - 32 * j));
+                        u32 dh = (__funnelshift_r(PH[j + s], PH[j + s + 1], r) ^ PH[j]) & wvj;
+                        u32 dl = (__funnelshift_r(PL[j + s], PL[j + s + 1], r) ^ PL[j]) & wvj;
+                        cH += __popc(dh); cL += __popc(dl); c11 += __popc(dh & dl);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) wvv[j] = V[j];
+                    sliding_and<4>(wvv, k);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (j < nw) {
+                            u32 dh = (__funnelshift_r(PH[j + s], PH[j + s + 1], r) ^ PH[j]) & wvv[j];
+                            u32 dl = (__funnelshift_r(PL[j + s], PL[j + s + 1], r) ^ PL[j]) & wvv[j];
+                            T += __popc(wvv[j]); cH += __popc(dh); cL += __popc(dl); c11 += __popc(dh & dl);
+                        }
+                    }
                 }
                 int c10 = cH - c11, c01 = cL - c11, c00 = T - cH - cL + c11;
                 U = max(max(c00, c01), max(c10, c11));
             }
-            bool cand = T > 0 && (double)U >= cfg.low * (double)T * slack;
+            bool cand = T > 0 && (double)U >= low * (double)T * slack;
             u32 cm = __ballot_sync(0xffffffffu, cand);
-            visit(kb, cm, U, T, [&](int, int Tk) {
-                int vb = Tk - 32 * (int)lane;
-                return vb <= 0 ? 0u : low_mask(min(32, vb));
-            });
+            while (cm) {
+                int bit = __ffs(cm) - 1;
+                cm &= cm - 1;
+                int Uk = __shfl_sync(0xffffffffu, U, bit), Tk = __shfl_sync(0xffffffffu, T, bit);
+                u32 wv;
+                if (all_valid) {
+                    int vb = Tk - 32 * (int)lane;
+                    wv = vb <= 0 ? 0u : low_mask(min(32, vb));
+                } else {
+                    u32 a0 = __shfl_sync(0xffffffffu, wvv[0], bit), a1 = __shfl_sync(0xffffffffu, wvv[1], bit);
+                    u32 a2 = __shfl_sync(0xffffffffu, wvv[2], bit), a3 = __shfl_sync(0xffffffffu, wvv[3], bit);
+                    wv = lane == 0 ? a0 : lane == 1 ? a1 : lane == 2 ? a2 : lane == 3 ? a3 : 0u;
+                }
+                try_k(kb + bit, Uk, Tk, wv);
+            }
         }
-        return st.res;
+        return res;
     }
 
-    // windows with invalid bases: walk the periods in order, keeping the window-valid mask incrementally
-    u32 wv = wv_for_k(w, kmin);
+    // long windows with invalid bases: walk the periods in order, keeping the window-valid mask incrementally
+    u32 wv = wv_for_k(ws, len, kmin);
     for (int k = kmin; k <= kmax; k++, wv = wv_step(wv, lane)) {
-        bool blkL = k < 64 ? ((st.blockedL >> k) & 1ULL) != 0 : st.blk64L;
-        bool blkH = k < 64 ? ((st.blockedH >> k) & 1ULL) != 0 : st.blk64H;
-        if (blkL && blkH) continue;
         int T = (int)__reduce_add_sync(0xffffffffu, (u32)__popc(wv));
-        if (T == 0) continue;
-        int U = bound_k(w, k, wv, T);
-        double dU = (double)U, dT = (double)T;
-        bool candL = !blkL && dU >= st.needL * dT * slack, candH = !blkH && dU >= st.needH * dT * slack;
-        if (!candL && !candH) continue;
-        consider(w, st, pos, len, k, wv);
+        if (T == 0) break;
+        int U = bound_k(ws, k, wv, T);
+        try_k(k, U, T, wv);
     }
-    return st.res;
+    return res;
 }
 
 // class statistics + run list of (window, k), re-using the last evaluation when it is the same one
-__device__ __noinline__ KStat eval_cached(Warp& w, const DevBatch& b, u32 pos, int len, int k) {
-    if (w.ev_k == k && w.ev_pos == pos && w.ev_len == len) return w.ev;
-    load_window(w, b, pos, len);
-    u32 wv = wv_for_k(w, k);
-    w.ev = eval_k(w, k, wv);
-    w.ev_pos = pos; w.ev_len = len; w.ev_k = k;
-    return w.ev;
+__device__ __noinline__ u32 eval_cached(WS ws, DevBatch b, u32 pos, int len, int k) {
+    u32* hd = ws.hdr();
+    if ((int)hd[HD_EV_K] == k && hd[HD_EV_POS] == pos && (int)hd[HD_EV_LEN] == len) return hd[HD_EV_PACK];
+    load_window(ws, b.hi, b.lo, b.val, pos, len);
+    u32 wv = wv_for_k(ws, len, k);
+    u32 ev = eval_k(ws, len, k, wv);
+    if (lane_id() == 0) { hd[HD_EV_POS] = pos; hd[HD_EV_LEN] = (u32)len; hd[HD_EV_K] = (u32)k; hd[HD_EV_PACK] = ev; }
+    __syncwarp();
+    return ev;
 }
 
 // the emission half of k_mer_check for one target k (src/kmer.cpp:2264-2328): every class, un-folded unless asked
-__device__ void emit_window(const DevCfg& cfg, Warp& w, const DevBatch& b, u32 pos, int len, int k, int table, bool folded) {
-    KStat ks = eval_cached(w, b, pos, len, k);
-    emit_classes(cfg, w, k, ks.nruns, table, folded);
+__device__ void emit_window(TableRef tr, WS ws, const DevBatch& b, u32 pos, int len, int k, int table, bool folded) {
+    u32 ev = eval_cached(ws, b, pos, len, k);
+    emit_classes(tr, ws, k, pk_runs(ev), table, folded);
 }
 
 // k_mer_target / k_mer_target_128 (src/kmer.cpp:1894-2142)
-__device__ void target_window(const DevCfg& cfg, Warp& w, const DevBatch& b, u32 pos, int len, int k, double B, int table) {
-    KStat ks = eval_cached(w, b, pos, len, k);
-    if (ks.T > 0 && !ks.homo && (double)ks.M / (double)ks.T >= B) emit_classes(cfg, w, k, ks.nruns, table, true);
+__device__ void target_window(TableRef tr, WS ws, const DevBatch& b, u32 pos, int len, int k, double B, int table) {
+    u32 ev = eval_cached(ws, b, pos, len, k);
+    if (pk_T(ev) > 0 && !pk_homo(ev) && (double)pk_M(ev) / (double)pk_T(ev) >= B) emit_classes(tr, ws, k, pk_runs(ev), table, true);
 }
 
 // ---- routing -----------------------------------------------------------------------------------
@@ -916,7 +1056,7 @@ __device__ void target_window(const DevCfg& cfg, Warp& w, const DevBatch& b, u32
 enum { T_F = 0, T_B = 2, T_O = 4 };
 
 // buffer_task (src/kmer.cpp:80-266)
-__device__ void route_short(const DevCfg& cfg, Warp& w, const DevBatch& b, u32 u) {
+__device__ void route_short(const DevCfg& cfg, TableRef tr, WS ws, const DevBatch& b, u32 u) {
     const int MINM = cfg.min_mer, MAXM = cfg.max_mer;
     u32 b0 = __ldg(b.bit_off + u);
     int n = (int)(__ldg(b.bit_off + u + 1) - b0);
@@ -926,29 +1066,29 @@ __device__ void route_short(const DevCfg& cfg, Warp& w, const DevBatch& b, u32 u
         int kmax = min(n / 4, MAXM);
         u32 lpos = b0, rpos = b0 + (u32)(n - (n + 1) / 2);
         int llen = n / 2, rlen = (n + 1) / 2;
-        ScanRes l = scan_stats(cfg, w, b, lpos, llen, MINM, kmax);
-        ScanRes r = scan_stats(cfg, w, b, rpos, rlen, MINM, kmax);  // always evaluated
+        ScanRes l = scan_stats(ws, b, lpos, llen, MINM, kmax, cfg.low, cfg.high);
+        ScanRes r = scan_stats(ws, b, rpos, rlen, MINM, kmax, cfg.low, cfg.high);  // always evaluated
         L[0] = l.th; L[1] = l.tl; R[0] = r.th; R[1] = r.tl;
         // right-half emissions survive only for classes where the left half found nothing
         // (nullptr maps at src/kmer.cpp:125, result.backward at :158)
 #pragma unroll
         for (int c = 0; c < 2; c++) {
-            if (L[c] > 0 && L[c] == R[c]) target_window(cfg, w, b, b0, n, L[c], c == 0 ? cfg.high : cfg.low, T_O + c);
-            else if (L[c] > 0) emit_window(cfg, w, b, lpos, llen, L[c], T_F + c, false);
-            else if (R[c] > 0) emit_window(cfg, w, b, rpos, rlen, R[c], T_B + c, false);
+            if (L[c] > 0 && L[c] == R[c]) target_window(tr, ws, b, b0, n, L[c], c == 0 ? cfg.high : cfg.low, T_O + c);
+            else if (L[c] > 0) emit_window(tr, ws, b, lpos, llen, L[c], T_F + c, false);
+            else if (R[c] > 0) emit_window(tr, ws, b, rpos, rlen, R[c], T_B + c, false);
         }
     }
     bool hc[2] = {L[0] == 0 && R[0] == 0, L[1] == 0 && R[1] == 0};
     if (4 * MAXM > n && (hc[0] || hc[1])) {
-        ScanRes s = scan_stats(cfg, w, b, b0, n, max(n / 4 + 1, MINM), min(n / 2, MAXM));
-        if (hc[0] && s.th) emit_window(cfg, w, b, b0, n, s.th, T_O + 0, false);  // un-folded into 'both'
-        if (hc[1] && s.tl) emit_window(cfg, w, b, b0, n, s.tl, T_O + 1, false);
+        ScanRes s = scan_stats(ws, b, b0, n, max(n / 4 + 1, MINM), min(n / 2, MAXM), cfg.low, cfg.high);
+        if (hc[0] && s.th) emit_window(tr, ws, b, b0, n, s.th, T_O + 0, false);  // un-folded into 'both'
+        if (hc[1] && s.tl) emit_window(tr, ws, b, b0, n, s.tl, T_O + 1, false);
     }
 }
 
 // buffer_task_pair (src/kmer.cpp:268-745); follows the 128-bit path where the two differ (temp map cleared
 // after the large-k block, src/kmer.cpp:722-723)
-__device__ void route_pair(const DevCfg& cfg, Warp& w, const DevBatch& b, u32 u) {
+__device__ void route_pair(const DevCfg& cfg, TableRef tr, WS ws, const DevBatch& b, u32 u) {
     const int MINM = cfg.min_mer, MAXM = cfg.max_mer;
     u32 a0 = __ldg(b.bit_off + 2 * u), a1 = __ldg(b.bit_off + 2 * u + 1), a2 = __ldg(b.bit_off + 2 * u + 2);
     int n1 = (int)(a1 - a0), n2 = (int)(a2 - a1);
@@ -965,7 +1105,7 @@ __device__ void route_pair(const DevCfg& cfg, Warp& w, const DevBatch& b, u32 u)
         int si[2] = {1, 1}; bool ended[2] = {false, false};
         u64 ks_lo[2] = {0, 0}, ks_hi[2] = {0, 0};
         for (int ti = 1; ti <= 4 && !(ended[0] && ended[1]); ti++) {
-            if (!have[ti]) { sr[ti] = scan_stats(cfg, w, b, spos[ti], slen[ti], MINM, kmax); have[ti] = true; }
+            if (!have[ti]) { sr[ti] = scan_stats(ws, b, spos[ti], slen[ti], MINM, kmax, cfg.low, cfg.high); have[ti] = true; }
             int k[2] = {sr[ti].th, sr[ti].tl};
             u64 slo[2] = {sr[ti].sh_lo, sr[ti].sl_lo}, shi[2] = {sr[ti].sh_hi, sr[ti].sl_hi};
 #pragma unroll
@@ -987,14 +1127,14 @@ __device__ void route_pair(const DevCfg& cfg, Warp& w, const DevBatch& b, u32 u)
             if (si[c] == 5) {
                 for (int e = 0; e < np[c]; e++) {
                     int sg = pseg[c][e];
-                    emit_window(cfg, w, b, spos[sg], slen[sg], c == 0 ? sr[sg].th : sr[sg].tl, T_O + c, true);
+                    emit_window(tr, ws, b, spos[sg], slen[sg], c == 0 ? sr[sg].th : sr[sg].tl, T_O + c, true);
                 }
             }
         }
         if (si[0] <= 4 || si[1] <= 4) {
             int sj[2] = {4, 4}; km[0] = km[1] = 0; ended[0] = ended[1] = false;
             for (int tj = 4; tj >= 1 && !(ended[0] && ended[1]); tj--) {
-                if (!have[tj]) { sr[tj] = scan_stats(cfg, w, b, spos[tj], slen[tj], MINM, kmax); have[tj] = true; }
+                if (!have[tj]) { sr[tj] = scan_stats(ws, b, spos[tj], slen[tj], MINM, kmax, cfg.low, cfg.high); have[tj] = true; }
                 int k[2] = {sr[tj].th, sr[tj].tl};
                 u64 slo[2] = {sr[tj].sh_lo, sr[tj].sl_lo}, shi[2] = {sr[tj].sh_hi, sr[tj].sl_hi};
 #pragma unroll
@@ -1016,7 +1156,7 @@ __device__ void route_pair(const DevCfg& cfg, Warp& w, const DevBatch& b, u32 u)
             if (si[c] <= 4) {
                 for (int e = 0; e < np[c]; e++) {
                     int sg = pseg[c][e];
-                    emit_window(cfg, w, b, spos[sg], slen[sg], c == 0 ? sr[sg].th : sr[sg].tl,
+                    emit_window(tr, ws, b, spos[sg], slen[sg], c == 0 ? sr[sg].th : sr[sg].tl,
                                 (ptmp[c][e] == 0 ? T_F : T_B) + c, false);
                 }
             }
@@ -1025,8 +1165,8 @@ __device__ void route_pair(const DevCfg& cfg, Warp& w, const DevBatch& b, u32 u)
     if (4 * MAXM > n && (lef[0] == 0 || lef[1] == 0 || km[0] == 0 || km[1] == 0)) {
         int lo = max(n / 4 + 1, MINM), hi = min(n / 2, MAXM);
         ScanRes l, r; l.th = l.tl = r.th = r.tl = 0; l.sh_lo = l.sh_hi = l.sl_lo = l.sl_hi = 0; r = l;
-        if (lef[0] == 0 || lef[1] == 0) l = scan_stats(cfg, w, b, a0, n1, lo, hi);
-        if (km[0] == 0 || km[1] == 0) r = scan_stats(cfg, w, b, a1, n2, lo, hi);
+        if (lef[0] == 0 || lef[1] == 0) l = scan_stats(ws, b, a0, n1, lo, hi, cfg.low, cfg.high);
+        if (km[0] == 0 || km[1] == 0) r = scan_stats(ws, b, a1, n2, lo, hi, cfg.low, cfg.high);
         int ltk[2] = {l.th, l.tl}, rtk[2] = {r.th, r.tl};
         u64 llo[2] = {l.sh_lo, l.sl_lo}, lhi[2] = {l.sh_hi, l.sl_hi}, rlo[2] = {r.sh_lo, r.sl_lo}, rhi[2] = {r.sh_hi, r.sl_hi};
 #pragma unroll
@@ -1039,17 +1179,17 @@ __device__ void route_pair(const DevCfg& cfg, Warp& w, const DevBatch& b, u32 u)
                 both = llo[c] == dlo && lhi[c] == dhi;
             }
             if (both) {
-                if (el) emit_window(cfg, w, b, a0, n1, ltk[c], T_O + c, true);
-                if (er) emit_window(cfg, w, b, a1, n2, rtk[c], T_O + c, true);
+                if (el) emit_window(tr, ws, b, a0, n1, ltk[c], T_O + c, true);
+                if (er) emit_window(tr, ws, b, a1, n2, rtk[c], T_O + c, true);
             }
-            if (el) emit_window(cfg, w, b, a0, n1, ltk[c], T_F + c, false);
-            if (er) emit_window(cfg, w, b, a1, n2, rtk[c], T_F + c, false);
+            if (el) emit_window(tr, ws, b, a0, n1, ltk[c], T_F + c, false);
+            if (er) emit_window(tr, ws, b, a1, n2, rtk[c], T_F + c, false);
         }
     }
 }
 
 // buffer_task_long (src/kmer.cpp:747-985)
-__device__ void route_long(const DevCfg& cfg, Warp& w, const DevBatch& b, u32 u, unsigned char* scratch) {
+__device__ void route_long(const DevCfg& cfg, TableRef tr, WS ws, const DevBatch& b, u32 u, unsigned char* scratch) {
     const int MINM = cfg.min_mer, MAXM = cfg.max_mer, SL = cfg.slice_len;
     u32 b0 = __ldg(b.bit_off + u);
     int n = (int)(__ldg(b.bit_off + u + 1) - b0);
@@ -1061,8 +1201,8 @@ __device__ void route_long(const DevCfg& cfg, Warp& w, const DevBatch& b, u32 u,
     int si[2] = {1, 1}, km[2] = {0, 0}; bool ended[2] = {false, false};
     int nf = 0;
     for (int ti = 1; ti <= snum && !(ended[0] && ended[1]); ti++) {
-        ScanRes sr = scan_stats(cfg, w, b, b0 + s_start(ti), s_len(ti), MINM, MAXM);
-        if (w.lane == 0) { scratch[2 * (ti - 1)] = (unsigned char)sr.th; scratch[2 * (ti - 1) + 1] = (unsigned char)sr.tl; }
+        ScanRes sr = scan_stats(ws, b, b0 + s_start(ti), s_len(ti), MINM, MAXM, cfg.low, cfg.high);
+        if (lane_id() == 0) { scratch[2 * (ti - 1)] = (unsigned char)sr.th; scratch[2 * (ti - 1) + 1] = (unsigned char)sr.tl; }
         int k[2] = {sr.th, sr.tl};
 #pragma unroll
         for (int c = 0; c < 2; c++) {
@@ -1080,7 +1220,7 @@ __device__ void route_long(const DevCfg& cfg, Warp& w, const DevBatch& b, u32 u,
             int k[2] = {scratch[2 * (ti - 1)], scratch[2 * (ti - 1) + 1]};
 #pragma unroll
             for (int c = 0; c < 2; c++) {
-                if (!en[c] && k[c]) emit_window(cfg, w, b, b0 + s_start(ti), s_len(ti), k[c], (full[c] ? T_O : T_F) + c, full[c]);
+                if (!en[c] && k[c]) emit_window(tr, ws, b, b0 + s_start(ti), s_len(ti), k[c], (full[c] ? T_O : T_F) + c, full[c]);
                 if (!en[c] && k[c] > 0 && (ti == 1 || kk[c] == k[c])) kk[c] = k[c];
                 else en[c] = true;
             }
@@ -1089,11 +1229,11 @@ __device__ void route_long(const DevCfg& cfg, Warp& w, const DevBatch& b, u32 u,
     if (si[0] <= snum || si[1] <= snum) {
         int sj[2] = {snum, snum}; km[0] = km[1] = 0; ended[0] = ended[1] = false;
         for (int tj = snum; tj >= 1 && !(ended[0] && ended[1]); tj--) {
-            ScanRes sr = scan_stats(cfg, w, b, b0 + s_start(tj), s_len(tj), MINM, MAXM);
+            ScanRes sr = scan_stats(ws, b, b0 + s_start(tj), s_len(tj), MINM, MAXM, cfg.low, cfg.high);
             int k[2] = {sr.th, sr.tl};
 #pragma unroll
             for (int c = 0; c < 2; c++) {
-                if (!ended[c] && k[c]) emit_window(cfg, w, b, b0 + s_start(tj), s_len(tj), k[c], T_B + c, false);  // straight into 'backward'
+                if (!ended[c] && k[c]) emit_window(tr, ws, b, b0 + s_start(tj), s_len(tj), k[c], T_B + c, false);  // straight into 'backward'
                 if (sj[c] >= si[c] && !ended[c] && k[c] > 0 && (tj == snum || km[c] == k[c])) { sj[c]--; km[c] = k[c]; }
                 else ended[c] = true;
             }
@@ -1103,37 +1243,26 @@ __device__ void route_long(const DevCfg& cfg, Warp& w, const DevBatch& b, u32 u,
 
 template <int MODE>
 __global__ void __launch_bounds__(kExactWarps * 32, TREW_EXACT_BPS) trew_exact_kernel(DevCfg cfg, DevBatch b, ExactArgs a) {
-    extern __shared__ __align__(16) unsigned char smem[];
     const int wid = threadIdx.x >> 5;
-    unsigned char* base = smem + (size_t)wid * exact_warp_bytes(a.run_cap);
-    Warp w;
-    w.lane = lane_id();
-    w.m.cap = a.run_cap;
-    w.m.H = (u32*)base; w.m.L = w.m.H + kPlaneWords; w.m.V = w.m.L + kPlaneWords;
-    w.m.PH = w.m.V + kPlaneWords; w.m.PL = w.m.PH + kPlaneWords;
-    w.m.rev2 = (u64*)(w.m.PL + kPlaneWords);
-    w.m.run_start = (unsigned short*)(w.m.rev2 + kPlaneWords);
-    w.m.run_cw = w.m.run_start + a.run_cap;
-    w.m.run_total = w.m.run_cw + a.run_cap + 1;
-    size_t off = 5 * kPlaneWords * sizeof(u32) + kPlaneWords * sizeof(u64) + (size_t)(3 * a.run_cap + 4) * sizeof(unsigned short);
-    off = (off + 15) & ~(size_t)15;
-    w.m.run_lo = (u64*)(base + off);
-    w.m.run_hi = w.m.run_lo + a.run_cap;
-    w.m.run_hash = (u32*)(w.m.run_hi + a.run_cap);
-    w.cur_len = -1; w.cur_pos = 0; w.ev_k = -1; w.ev_pos = 0; w.ev_len = -1;
-    w.h = w.l = w.v = 0;
+    const u32 lane = lane_id();
+    WS ws;
+    ws.cap = a.run_cap; ws.hs = exact_hash_slots(a.run_cap);
+    ws.off = (u32)((size_t)wid * exact_warp_bytes(a.run_cap));
+    TableRef tr{cfg.slots, cfg.slot_mask, cfg.error_flag};
+    if (lane < 16) ws.hdr()[lane] = lane == HD_CUR_LEN || lane == HD_EV_LEN || lane == HD_EV_K ? 0xffffffffu : 0u;
+    __syncwarp();
     const u32 n = *a.n_survivors;
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.total_survivors) atomicAdd(a.total_survivors, (u64)n);
     unsigned char* scratch = a.slice_scratch + (size_t)(blockIdx.x * kExactWarps + wid) * a.slice_scratch_stride;
     for (;;) {
         u32 idx = 0;
-        if (w.lane == 0) idx = atomicAdd(a.work_counter, 1u);
+        if (lane == 0) idx = atomicAdd(a.work_counter, 1u);
         idx = __shfl_sync(0xffffffffu, idx, 0);
         if (idx >= n) break;
         u32 u = a.survivors[idx];
-        if constexpr (MODE == 0) route_short(cfg, w, b, u);
-        else if constexpr (MODE == 1) route_pair(cfg, w, b, u);
-        else route_long(cfg, w, b, u, scratch);
+        if constexpr (MODE == 0) route_short(cfg, tr, ws, b, u);
+        else if constexpr (MODE == 1) route_pair(cfg, tr, ws, b, u);
+        else route_long(cfg, tr, ws, b, u, scratch);
     }
 }
 
