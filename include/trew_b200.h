@@ -182,8 +182,8 @@ int trew_dev_get_stats(trew_ctx* ctx, trew_stats* out);
 /* Bytes a packed batch of n_reads reads with total_bases bases needs (offsets + three planes + pad). */
 size_t trew_pack_bound(uint32_t n_reads, uint64_t total_bases);
 
-/* Pack n reads given as (st, nd) inclusive offsets into `buffer` into caller memory `dst` of at least
- * trew_pack_bound bytes; fills *out with pointers into dst.  Single-threaded building block. */
+/* Pack n reads given as (st, nd) inclusive offsets into `buffer` into caller memory `dst` (8-byte aligned) of at
+ * least trew_pack_bound bytes; fills *out with pointers into dst.  Single-threaded building block. */
 int trew_pack_reads(const char* buffer, const int32_t* locs, uint32_t n, void* dst, size_t dst_bytes,
                     trew_batch* out);
 

@@ -34,6 +34,9 @@ struct SlotRes {
     bool in_flight = false;
 };
 
+// reads [r0, r1) of a chunk with their base total and longest read
+struct RangeInfo { uint32_t r0, r1; uint64_t bases; uint32_t max_len; };
+
 }  // namespace
 
 struct trew_resident {
@@ -70,7 +73,7 @@ struct trew_ctx {
     trew_stats stats{};
     Pool* pool = nullptr;
     std::string err;
-    std::vector<ReadRef> reads_tmp;
+    std::vector<RangeInfo> ranges_tmp;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     double filter_ms = 0, exact_ms = 0; uint64_t n_prof_scans = 0;
     std::vector<trew_resident*> pending_prof;
@@ -156,8 +159,11 @@ int retire_slot(trew_ctx* ctx, SlotRes& s) {
     return TREW_OK;
 }
 
-// Pack reads (host threads) into the next free staging slot and launch copy + kernels on its stream.
-int submit_reads(trew_ctx* ctx, const ReadRef* reads, uint32_t n, uint64_t total_bases, uint32_t max_len, const char* buf_end) {
+// Pack ranges [g0, g1) of a chunk (host threads) into the next free staging slot and launch copy + kernels on its stream.
+int submit_ranges(trew_ctx* ctx, const ChunkView& cv, const RangeInfo* rg, int n_ranges) {
+    uint64_t total_bases = 0; uint32_t max_len = 0;
+    for (int i = 0; i < n_ranges; i++) { total_bases += rg[i].bases; max_len = std::max(max_len, rg[i].max_len); }
+    const uint32_t n = n_ranges ? rg[n_ranges - 1].r1 - rg[0].r0 : 0u;
     if (n == 0) return TREW_OK;
     SlotRes& s = ctx->slots[ctx->next_slot];
     ctx->next_slot = (ctx->next_slot + 1) % ctx->slots.size();
@@ -165,20 +171,16 @@ int submit_reads(trew_ctx* ctx, const ReadRef* reads, uint32_t n, uint64_t total
     if (rc) return rc;
     BatchView v;
     batch_layout(s.h_buf, n, total_bases, &v);
-    // split into ranges of roughly equal bases, one per pool thread
-    int P = std::max(1, std::min(ctx->pool->size(), (int)(total_bases / 65536) + 1));
-    std::vector<uint32_t> starts;
-    starts.push_back(0);
-    if (P > 1) {
-        uint64_t acc = 0, target = total_bases / P;
-        for (uint32_t r = 0; r < n && (int)starts.size() < P; r++) {
-            if (acc >= target * starts.size() && r != starts.back()) starts.push_back(r);
-            acc += reads[r].len;
-        }
-    }
-    pack_prepare(reads, n, starts.data(), (int)starts.size(), v);
-    int nr = (int)starts.size();
-    ctx->pool->run(nr, [&](int i) { pack_range(reads, starts[i], i + 1 < nr ? starts[i + 1] : n, v, buf_end); });
+    std::vector<uint64_t> bit0((size_t)n_ranges);
+    uint64_t acc = 0;
+    for (int i = 0; i < n_ranges; i++) { bit0[i] = acc; acc += rg[i].bases; }
+    pack_prepare(bit0.data(), n_ranges, total_bases, v);
+    v.bit_off[n] = (uint32_t)total_bases;
+    const uint32_t first = rg[0].r0;
+    std::vector<uint64_t> side_flat((size_t)3 * n_ranges);
+    uint64_t (*side)[3] = (uint64_t (*)[3])side_flat.data();
+    ctx->pool->run(n_ranges, [&](int i) { pack_chunk_range(cv, rg[i].r0, rg[i].r1, rg[i].r0 - first, bit0[i], v, side[i]); });
+    pack_fixup(bit0.data(), side, n_ranges, v);
 
     CK(cudaEventRecord(s.ev_start, s.stream));
     CK(cudaMemcpyAsync(s.d_buf, s.h_buf, v.bytes, cudaMemcpyHostToDevice, s.stream));
@@ -196,24 +198,81 @@ int submit_reads(trew_ctx* ctx, const ReadRef* reads, uint32_t n, uint64_t total
     return TREW_OK;
 }
 
-// Greedy split of a read list into sub-batches that fit one staging slot.
-int submit_split(trew_ctx* ctx, const std::vector<ReadRef>& reads, uint32_t unit, const char* buf_end) {
-    size_t i = 0, n = reads.size();
-    while (i < n) {
-        size_t j = i; uint64_t bases = 0; uint32_t mx = 0;
-        while (j < n) {
-            uint64_t add = 0; uint32_t m2 = mx;
-            for (uint32_t t = 0; t < unit; t++) { add += reads[j + t].len; m2 = std::max(m2, reads[j + t].len); }
-            if (j > i && (batch_bytes((uint32_t)(j - i + unit), bases + add) > ctx->staging_bytes ||
-                          (j - i + unit) > ctx->slots[0].survivors_cap || bases + add >= 0xfffff000ULL)) break;
-            bases += add; mx = m2; j += unit;
+// Split a chunk of n reads into ranges (statistics gathered on the pool), group consecutive ranges into batches
+// that fit one staging slot and submit them.
+int submit_chunk_view(trew_ctx* ctx, const ChunkView& cv, uint32_t n) {
+    if (n == 0) return TREW_OK;
+    const uint32_t unit = cv.unit;
+    const uint32_t n_units = n / unit;
+    // ranges small enough that any single one is far below a staging slot, and enough of them to feed the pool
+    uint64_t span = 0;
+    for (int sd = 0; sd < (int)unit; sd++) {
+        const int32_t* l = cv.locs[sd];
+        span += (uint64_t)std::max<int64_t>(0, (int64_t)l[2 * (size_t)(n_units - 1) + 1] - l[0] + 1);
+    }
+    uint64_t by_size = span / std::max<uint64_t>(1, ctx->staging_bytes / 16) + 1;
+    uint32_t n_ranges = (uint32_t)std::min<uint64_t>(n_units, std::max<uint64_t>(by_size, (uint64_t)ctx->pool->size() * 4));
+    auto& rg = ctx->ranges_tmp;
+    rg.resize(n_ranges);
+    for (uint32_t i = 0; i < n_ranges; i++) {
+        rg[i].r0 = (uint32_t)((uint64_t)n_units * i / n_ranges) * unit;
+        rg[i].r1 = (uint32_t)((uint64_t)n_units * (i + 1) / n_ranges) * unit;
+    }
+    ctx->pool->run((int)n_ranges, [&](int i) { chunk_stats(cv, rg[i].r0, rg[i].r1, &rg[i].bases, &rg[i].max_len); });
+    uint32_t mx = 0;
+    for (auto& r : rg) mx = std::max(mx, r.max_len);
+    if (ctx->cfg.mode == TREW_MODE_SHORT && mx > 1000)  // MAX_SEQ, src/kmer.cpp:1006-1008
+        return fail(ctx, TREW_ERR_TOO_LONG, "%s", trew_status_string(TREW_ERR_TOO_LONG));
+    if (ctx->cfg.mode == TREW_MODE_PAIR && mx > (uint32_t)kMaxWindow) return fail(ctx, TREW_ERR_TOO_LONG, "paired read longer than %d", kMaxWindow);
+    const size_t cap = ctx->slots[0].survivors_cap;
+    uint32_t g = 0;
+    while (g < n_ranges) {
+        uint32_t h = g; uint64_t bases = 0; uint64_t reads = 0;
+        while (h < n_ranges) {
+            uint64_t nb = bases + rg[h].bases, nr = reads + (rg[h].r1 - rg[h].r0);
+            if (batch_bytes((uint32_t)nr, nb) > ctx->staging_bytes || nr > cap || nb >= 0xfffff000ULL) break;
+            bases = nb; reads = nr; h++;
         }
-        if (batch_bytes((uint32_t)(j - i), bases) > ctx->staging_bytes)
-            return fail(ctx, TREW_ERR_ARG, "a single read/pair (%llu bases) does not fit a staging buffer of %zu bytes",
-                        (unsigned long long)bases, ctx->staging_bytes);
-        int rc = submit_reads(ctx, reads.data() + i, (uint32_t)(j - i), bases, mx, buf_end);
+        if (h == g) {
+            // a single range does not fit: fall back to unit-sized ranges for it
+            if (rg[g].r1 - rg[g].r0 <= unit)
+                return fail(ctx, TREW_ERR_ARG, "a single read/pair (%llu bases) does not fit a staging buffer of %zu bytes",
+                            (unsigned long long)rg[g].bases, ctx->staging_bytes);
+            std::vector<RangeInfo> fine;
+            for (uint32_t r = rg[g].r0; r < rg[g].r1; r += unit) {
+                RangeInfo f{r, r + unit, 0, 0};
+                chunk_stats(cv, f.r0, f.r1, &f.bases, &f.max_len);
+                fine.push_back(f);
+            }
+            size_t a = 0;
+            while (a < fine.size()) {
+                size_t e = a; uint64_t fb = 0, fr = 0;
+                while (e < fine.size()) {
+                    uint64_t nb = fb + fine[e].bases, nr = fr + unit;
+                    if (batch_bytes((uint32_t)nr, nb) > ctx->staging_bytes || nr > cap || nb >= 0xfffff000ULL) break;
+                    fb = nb; fr = nr; e++;
+                }
+                if (e == a)
+                    return fail(ctx, TREW_ERR_ARG, "a single read/pair (%llu bases) does not fit a staging buffer of %zu bytes",
+                                (unsigned long long)fine[a].bases, ctx->staging_bytes);
+                // merge the unit ranges of this batch into at most pool-size ranges
+                std::vector<RangeInfo> merged;
+                size_t per = std::max<size_t>(1, (e - a) / (size_t)ctx->pool->size());
+                for (size_t i = a; i < e; i += per) {
+                    RangeInfo m{fine[i].r0, 0, 0, 0};
+                    for (size_t j = i; j < std::min(e, i + per); j++) { m.r1 = fine[j].r1; m.bases += fine[j].bases; m.max_len = std::max(m.max_len, fine[j].max_len); }
+                    merged.push_back(m);
+                }
+                int rc = submit_ranges(ctx, cv, merged.data(), (int)merged.size());
+                if (rc) return rc;
+                a = e;
+            }
+            g++;
+            continue;
+        }
+        int rc = submit_ranges(ctx, cv, rg.data() + g, (int)(h - g));
         if (rc) return rc;
-        i = j;
+        g = h;
     }
     return TREW_OK;
 }
@@ -371,30 +430,18 @@ int trew_dev_submit_chunk(trew_ctx* ctx, const char* buffer1, const int32_t* loc
     const bool pair = ctx->cfg.mode == TREW_MODE_PAIR;
     if (pair ? (!buffer2 && n2) : (buffer2 != nullptr || n2 != 0)) return fail(ctx, TREW_ERR_ARG, "second chunk only in pair mode");
     if ((n1 && (!buffer1 || !locs1)) || (n2 && !locs2)) return fail(ctx, TREW_ERR_ARG, "null chunk");
-    auto& reads = ctx->reads_tmp;
-    reads.clear();
-    auto ref = [](const char* buf, const int32_t* locs, uint32_t i) {
-        int32_t st = locs[2 * i], nd = locs[2 * i + 1];
-        return ReadRef{buf + st, nd >= st ? (uint32_t)(nd - st + 1) : 0u};
-    };
-    if (pair) {
-        uint32_t n = std::min(n1, n2);  // index-wise pairing, src/kmer.cpp:321-322
-        reads.reserve((size_t)2 * n);
-        for (uint32_t i = 0; i < n; i++) { reads.push_back(ref(buffer1, locs1, i)); reads.push_back(ref(buffer2, locs2, i)); }
-    } else {
-        reads.reserve(n1);
-        for (uint32_t i = 0; i < n1; i++) {
-            ReadRef r = ref(buffer1, locs1, i);
-            if (ctx->cfg.mode == TREW_MODE_SHORT && r.len > 1000)  // MAX_SEQ, src/kmer.cpp:1006-1008
-                return fail(ctx, TREW_ERR_TOO_LONG, "%s", trew_status_string(TREW_ERR_TOO_LONG));
-            reads.push_back(r);
-        }
-    }
-    if (pair) for (auto& r : reads) if (r.len > (uint32_t)kMaxWindow) return fail(ctx, TREW_ERR_TOO_LONG, "paired read longer than %d", kMaxWindow);
+    ChunkView cv{{buffer1, buffer2}, {locs1, locs2}, {nullptr, nullptr}, pair ? 2u : 1u};
+    const uint32_t n = pair ? 2u * std::min(n1, n2) : n1;  // index-wise pairing, src/kmer.cpp:321-322
+    if (n == 0) return TREW_OK;
     // one past the last byte the caller vouches for: lets the packer load whole 32-byte blocks at read tails
-    const char* buf_end = nullptr;
-    if (!pair) for (const auto& r : reads) if (r.ptr + r.len > buf_end) buf_end = r.ptr + r.len;
-    return submit_split(ctx, reads, pair ? 2u : 1u, buf_end);
+    // (sequence lines are produced in ascending order, so the last one bounds the buffer from below)
+    for (int sd = 0; sd < (pair ? 2 : 1); sd++) {
+        const int32_t* l = cv.locs[sd];
+        uint32_t cnt = pair ? n / 2 : n;
+        int32_t last = l[2 * (size_t)(cnt - 1) + 1];
+        if (last >= l[2 * (size_t)(cnt - 1)]) cv.end[sd] = cv.buf[sd] + last + 1;
+    }
+    return submit_chunk_view(ctx, cv, n);
 }
 
 int trew_dev_submit_packed(trew_ctx* ctx, const trew_batch* batch) {

@@ -13,7 +13,22 @@
 
 namespace trew {
 
-struct ReadRef { const char* ptr; uint32_t len; };
+// A raw chunk as the reference's reader threads produce it (QueueData / PairQueueData, src/kmer.h:93-103): text
+// buffer(s) plus inclusive (st, nd) offsets.  unit == 2: read r is mate (r & 1) of pair (r >> 1).
+struct ChunkView {
+    const char* buf[2];
+    const int32_t* locs[2];
+    const char* end[2];   // one past the last byte the caller vouches for per buffer (nullptr: unknown)
+    uint32_t unit;        // 1 single / long, 2 paired
+    inline void get(uint32_t r, const char*& p, uint32_t& len, size_t& slack) const {
+        const int sd = unit == 2 ? (int)(r & 1u) : 0;
+        const uint32_t i = unit == 2 ? r >> 1 : r;
+        const int32_t st = locs[sd][2 * (size_t)i], nd = locs[sd][2 * (size_t)i + 1];
+        len = nd >= st ? (uint32_t)(nd - st + 1) : 0u;
+        p = buf[sd] + st;
+        slack = end[sd] && end[sd] > p + len ? (size_t)(end[sd] - (p + len)) : 0;
+    }
+};
 
 struct BatchView {
     uint32_t* bit_off; uint32_t* hi; uint32_t* lo; uint32_t* val;
@@ -22,9 +37,17 @@ struct BatchView {
 
 size_t batch_bytes(uint32_t n_reads, uint64_t total_bases);
 void batch_layout(void* dst, uint32_t n_reads, uint64_t total_bases, BatchView* v);
-void pack_prepare(const ReadRef* reads, uint32_t n, const uint32_t* range_starts, int n_ranges, const BatchView& v);
-// buf_end: one past the last readable byte of the chunk the reads point into (nullptr: unknown)
-void pack_range(const ReadRef* reads, uint32_t r0, uint32_t r1, const BatchView& v, const char* buf_end);
+// total bases and longest read of reads [r0, r1)
+void chunk_stats(const ChunkView& cv, uint32_t r0, uint32_t r1, uint64_t* bases, uint32_t* max_len);
+// Zero the 64-bit plane units nobody may store to (the unit holding each range's first bit) and the tail pad.
+void pack_prepare(const uint64_t* range_bit0, int n_ranges, uint64_t total_bases, const BatchView& v);
+// Pack reads [r0, r1) of the chunk as reads out0 .. of the batch, the first base at bit position bit0: writes
+// bit_off[out0 ..] and the three planes.  Ranges may be packed concurrently: the bits that fall into the range's
+// first 64-bit unit (possibly shared with the previous range) are returned in side[] instead of being stored.
+void pack_chunk_range(const ChunkView& cv, uint32_t r0, uint32_t r1, uint32_t out0, uint64_t bit0, const BatchView& v,
+                      uint64_t side[3]);
+// After all ranges are packed: OR every range's side bits into its first unit (single-threaded, n_ranges items).
+void pack_fixup(const uint64_t* range_bit0, const uint64_t (*side)[3], int n_ranges, const BatchView& v);
 
 // Minimal fork-join pool: run(n, fn) calls fn(i) for i in [0, n) on the workers plus the caller.
 class Pool {

@@ -2,12 +2,14 @@
 //
 // Restates codes[] (src/kmer.cpp:14-31): T=0 G=1 C=2 A=3 for either case, every other byte invalid.
 // The two code bits and the validity bit are written as three bit-planes (see include/trew_b200.h,
-// trew_batch).  With AVX2 a 32-byte block becomes three 32-bit masks via movemask:
+// trew_batch).  A 32-byte (AVX2) or 64-byte (AVX-512BW) block becomes three bit masks:
 //     x1 = bit 2 of the byte, x0 = bit 1:   A -> 00, C -> 01, T -> 10, G -> 11
 //     hi = ~x1, lo = ~(x1 ^ x0)             A -> 11, C -> 10, G -> 01, T -> 00   (the reference's codes)
+// The instruction set is picked at run time (scalar fallback for other CPUs; the DEVICE path has no fallback).
 #include "host_internal.h"
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 #if defined(__x86_64__)
@@ -31,108 +33,205 @@ struct Lut {
 };
 const Lut g_lut;
 
-inline void masks_scalar(const unsigned char* p, int n, uint32_t& hi, uint32_t& lo, uint32_t& val) {
-    uint32_t h = 0, l = 0, v = 0;
+inline void masks_scalar(const unsigned char* p, int n, uint64_t& hi, uint64_t& lo, uint64_t& val) {
+    uint64_t h = 0, l = 0, v = 0;
     for (int i = 0; i < n; i++) {
-        unsigned c = g_lut.v[p[i]];
-        l |= (uint32_t)(c & 1) << i;
-        h |= (uint32_t)((c >> 1) & 1) << i;
-        v |= (uint32_t)((c >> 2) & 1) << i;
+        uint64_t c = g_lut.v[p[i]];
+        l |= (c & 1) << i;
+        h |= ((c >> 1) & 1) << i;
+        v |= ((c >> 2) & 1) << i;
     }
     hi = h; lo = l; val = v;
 }
 
-#if defined(__x86_64__)
-__attribute__((target("avx2"))) inline void masks_avx2(const unsigned char* p, uint32_t& hi, uint32_t& lo, uint32_t& val) {
-    __m256i x = _mm256_loadu_si256((const __m256i*)p);
-    uint32_t x1 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(x, 5));
-    uint32_t x0 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(x, 6));
-    __m256i lc = _mm256_or_si256(x, _mm256_set1_epi8(0x20));
-    __m256i ok = _mm256_or_si256(
-        _mm256_or_si256(_mm256_cmpeq_epi8(lc, _mm256_set1_epi8('a')), _mm256_cmpeq_epi8(lc, _mm256_set1_epi8('c'))),
-        _mm256_or_si256(_mm256_cmpeq_epi8(lc, _mm256_set1_epi8('g')), _mm256_cmpeq_epi8(lc, _mm256_set1_epi8('t'))));
-    uint32_t v = (uint32_t)_mm256_movemask_epi8(ok);
-    hi = ~x1 & v; lo = ~(x1 ^ x0) & v; val = v;
-}
-#endif
-
-bool have_avx2() {
-#if defined(__x86_64__)
-    static const bool v = __builtin_cpu_supports("avx2");
-    return v;
-#else
-    return false;
-#endif
-}
-
-// Appends bits to the three planes starting at an arbitrary bit position.  The first and the last
-// word it touches may be shared with a neighbouring range packed by another thread: those two are
-// OR-ed atomically into pre-zeroed memory, interior words are plain stores.
+// Appends bits to the three planes starting at an arbitrary bit position, 64 bits at a time (the planes are
+// 8-byte aligned; a little-endian u64 store is two consecutive u32 plane words).  Branch-free in the steady
+// state: every put stores the current (possibly still partial) unit and a later put overwrites it with the
+// complete value.  Ranges are packed concurrently by different threads, and a range's FIRST unit may also hold
+// the last bits of the previous range: those bits are never stored here but kept in `side` and OR-ed in by
+// the caller once all ranges are done (pack_fixup); every other unit has exactly one writer.
 struct BitWriter {
-    uint32_t* hi; uint32_t* lo; uint32_t* val;
-    uint64_t word;       // index of the next word to flush
-    uint64_t ah, al, av; // accumulators
-    int fill;            // valid bits in the accumulators
-    bool first;
+    uint64_t* hi; uint64_t* lo; uint64_t* val;
+    uint64_t unit;        // index of the 64-bit unit being filled
+    uint64_t first_unit;
+    uint64_t ah, al, av;  // accumulators
+    int fill;             // valid bits in the accumulators
+    uint64_t side[3];     // hi / lo / val bits of the first unit
 
     BitWriter(uint32_t* h, uint32_t* l, uint32_t* v, uint64_t bitpos)
-        : hi(h), lo(l), val(v), word(bitpos >> 5), ah(0), al(0), av(0), fill((int)(bitpos & 31)), first(true) {}
+        : hi((uint64_t*)h), lo((uint64_t*)l), val((uint64_t*)v), unit(bitpos >> 6), first_unit(bitpos >> 6), ah(0), al(0),
+          av(0), fill((int)(bitpos & 63)) { side[0] = side[1] = side[2] = 0; }
 
-    inline void flush_word() {
-        uint32_t h = (uint32_t)ah, l = (uint32_t)al, v = (uint32_t)av;
-        if (first) {
-            __atomic_fetch_or(&hi[word], h, __ATOMIC_RELAXED);
-            __atomic_fetch_or(&lo[word], l, __ATOMIC_RELAXED);
-            __atomic_fetch_or(&val[word], v, __ATOMIC_RELAXED);
-            first = false;
+    // FULL: nbits == 64.  PEEL: the first unit may still be the current one.  Bits above nbits must be zero.
+    template <bool FULL, bool PEEL>
+    __attribute__((always_inline)) inline void put(uint64_t h, uint64_t l, uint64_t v, int nbits) {
+        const uint64_t th = ah | (h << fill), tl = al | (l << fill), tv = av | (v << fill);
+        if (PEEL && unit == first_unit) { side[0] = th; side[1] = tl; side[2] = tv; }
+        else { hi[unit] = th; lo[unit] = tl; val[unit] = tv; }
+        const int back = 63 - fill;  // x >> (64 - fill) without the undefined shift by 64
+        const uint64_t ch = (h >> 1) >> back, cl = (l >> 1) >> back, cvv = (v >> 1) >> back;
+        if (FULL) {
+            ah = ch; al = cl; av = cvv; unit++;
         } else {
-            hi[word] = h; lo[word] = l; val[word] = v;
+            const int nf = fill + nbits;
+            const bool adv = nf >= 64;
+            ah = adv ? ch : th; al = adv ? cl : tl; av = adv ? cvv : tv;
+            unit += adv ? 1 : 0;
+            fill = nf & 63;
         }
-        word++; ah >>= 32; al >>= 32; av >>= 32; fill -= 32;
     }
-    inline void put(uint32_t h, uint32_t l, uint32_t v, int nbits) {
-        ah |= (uint64_t)h << fill; al |= (uint64_t)l << fill; av |= (uint64_t)v << fill;
-        fill += nbits;
-        if (fill >= 32) flush_word();
-    }
-    inline void finish() {
-        if (fill > 0) {
-            __atomic_fetch_or(&hi[word], (uint32_t)ah, __ATOMIC_RELAXED);
-            __atomic_fetch_or(&lo[word], (uint32_t)al, __ATOMIC_RELAXED);
-            __atomic_fetch_or(&val[word], (uint32_t)av, __ATOMIC_RELAXED);
-        }
+    bool peeling() const { return unit == first_unit; }
+    // the bits carried past the last completed unit
+    void finish() {
+        if (fill == 0) return;
+        if (unit == first_unit) { side[0] = ah; side[1] = al; side[2] = av; }
+        else { hi[unit] = ah; lo[unit] = al; val[unit] = av; }
     }
 };
 
-// `slack` = readable bytes after the read's last byte (inside the caller's chunk): when at least 31 the tail
-// block is loaded straight from the chunk and the excess lanes are masked off.
-inline void pack_one(BitWriter& w, const unsigned char* s, int n, bool avx2, size_t slack) {
-    int i = 0;
-    uint32_t h, l, v;
+template <bool PEEL>
+inline void pack_read_scalar(BitWriter& w, const unsigned char* s, uint32_t len) {
+    uint64_t h, l, v;
+    uint32_t i = 0;
+    for (; i + 64 <= len; i += 64) { masks_scalar(s + i, 64, h, l, v); w.put<true, PEEL>(h, l, v, 64); }
+    if (i < len) { masks_scalar(s + i, (int)(len - i), h, l, v); w.put<false, PEEL>(h, l, v, (int)(len - i)); }
+}
+
+void pack_reads_scalar(const ChunkView& cv, uint32_t r0, uint32_t r1, uint32_t* off, uint64_t pos, BitWriter& w_out) {
+    BitWriter w = w_out;  // local copy: its address never escapes, so the state stays in registers across the plane stores
+    const char* p; uint32_t len; size_t slack;
+    uint32_t r = r0;
+    for (; r < r1 && w.peeling(); r++) {
+        cv.get(r, p, len, slack);
+        *off++ = (uint32_t)pos; pos += len;
+        pack_read_scalar<true>(w, (const unsigned char*)p, len);
+    }
+    for (; r < r1; r++) {
+        cv.get(r, p, len, slack);
+        *off++ = (uint32_t)pos; pos += len;
+        pack_read_scalar<false>(w, (const unsigned char*)p, len);
+    }
+    w_out = w;
+}
+
 #if defined(__x86_64__)
-    if (avx2) {
-        for (; i + 32 <= n; i += 32) { masks_avx2(s + i, h, l, v); w.put(h, l, v, 32); }
-        if (i < n) {
-            int m = n - i;
-            uint32_t keep = (1u << m) - 1u;
-            if (slack >= 31) {
-                masks_avx2(s + i, h, l, v);
-            } else {
-                unsigned char tmp[32];
-                memset(tmp, 0, sizeof(tmp));
-                memcpy(tmp, s + i, (size_t)m);
-                masks_avx2(tmp, h, l, v);
-            }
-            w.put(h & keep, l & keep, v & keep, m);
+#define TREW_AVX2 __attribute__((target("avx2")))
+#define TREW_AVX512 __attribute__((target("avx512f,avx512bw")))
+
+// AVX2: a 32-byte block becomes three 32-bit masks.  x1 = bit 2 of the byte, x0 = bit 1: A -> 00, C -> 01,
+// T -> 10, G -> 11; hi = ~x1, lo = ~(x1 ^ x0) give the reference's codes.  Validity: a 16-entry shuffle table
+// keyed by the low nibble returns the one lower-case base letter with that nibble (or 0); the byte is a base
+// iff it equals that letter once its case bit is set.
+TREW_AVX2 __attribute__((always_inline)) inline void masks_avx2(const unsigned char* q, uint64_t keep, __m256i lut, __m256i case_bit,
+                                                                uint64_t& h, uint64_t& l, uint64_t& v) {
+    __m256i x = _mm256_loadu_si256((const __m256i*)q);
+    uint32_t x1 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(x, 5));
+    uint32_t x0 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(x, 6));
+    uint32_t vv = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_shuffle_epi8(lut, x), _mm256_or_si256(x, case_bit))) & (uint32_t)keep;
+    h = ~x1 & vv; l = ~(x1 ^ x0) & vv; v = vv;
+}
+
+template <bool PEEL>
+TREW_AVX2 __attribute__((always_inline)) inline void pack_read_avx2(BitWriter& w, const unsigned char* s, uint32_t len, size_t slack,
+                                                                    __m256i lut, __m256i case_bit) {
+    uint64_t h, l, v, h2, l2, v2;
+    uint32_t i = 0;
+    for (; i + 64 <= len; i += 64) {
+        masks_avx2(s + i, 0xffffffffu, lut, case_bit, h, l, v);
+        masks_avx2(s + i + 32, 0xffffffffu, lut, case_bit, h2, l2, v2);
+        w.put<true, PEEL>(h | (h2 << 32), l | (l2 << 32), v | (v2 << 32), 64);
+    }
+    if (i < len) {
+        const int m = (int)(len - i);
+        const uint64_t keep = m >= 64 ? ~0ULL : ((1ULL << m) - 1ULL);
+        unsigned char tmp[64];
+        const unsigned char* q = s + i;
+        if (slack + (size_t)m < 64) {  // the 64-byte window would leave the caller's chunk: copy the tail
+            memset(tmp, 0, sizeof(tmp));
+            memcpy(tmp, q, (size_t)m);
+            q = tmp;
         }
-        return;
+        masks_avx2(q, keep, lut, case_bit, h, l, v);
+        h2 = l2 = v2 = 0;
+        if (m > 32) masks_avx2(q + 32, keep >> 32, lut, case_bit, h2, l2, v2);
+        w.put<false, PEEL>(h | (h2 << 32), l | (l2 << 32), v | (v2 << 32), m);
     }
+}
+
+TREW_AVX2 void pack_reads_avx2(const ChunkView& cv, uint32_t r0, uint32_t r1, uint32_t* off, uint64_t pos, BitWriter& w_out) {
+    BitWriter w = w_out;  // local copy: its address never escapes, so the state stays in registers across the plane stores
+    const __m256i lut = _mm256_setr_epi8(0, 'a', 0, 'c', 't', 0, 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0,
+                                         0, 'a', 0, 'c', 't', 0, 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0);
+    const __m256i case_bit = _mm256_set1_epi8(0x20);
+    const char* p; uint32_t len; size_t slack;
+    uint32_t r = r0;
+    for (; r < r1 && w.peeling(); r++) {
+        cv.get(r, p, len, slack);
+        *off++ = (uint32_t)pos; pos += len;
+        pack_read_avx2<true>(w, (const unsigned char*)p, len, slack, lut, case_bit);
+    }
+    for (; r < r1; r++) {
+        cv.get(r, p, len, slack);
+        *off++ = (uint32_t)pos; pos += len;
+        pack_read_avx2<false>(w, (const unsigned char*)p, len, slack, lut, case_bit);
+    }
+    w_out = w;
+}
+
+// AVX-512BW: 64-byte blocks, mask registers instead of movemask, masked loads for read tails.
+template <bool PEEL>
+TREW_AVX512 __attribute__((always_inline)) inline void pack_read_avx512(BitWriter& w, const unsigned char* s, uint32_t len, __m512i lut,
+                                                                        __m512i case_bit, __m512i b2, __m512i b1) {
+    uint32_t i = 0;
+    for (; i + 64 <= len; i += 64) {
+        __m512i x = _mm512_loadu_si512((const void*)(s + i));
+        uint64_t x1 = _mm512_test_epi8_mask(x, b2), x0 = _mm512_test_epi8_mask(x, b1);
+        uint64_t v = _mm512_cmpeq_epi8_mask(_mm512_shuffle_epi8(lut, x), _mm512_or_si512(x, case_bit));
+        w.put<true, PEEL>(~x1 & v, ~(x1 ^ x0) & v, v, 64);
+    }
+    if (i < len) {
+        const int m = (int)(len - i);
+        const uint64_t keep = (1ULL << m) - 1ULL;
+        __m512i x = _mm512_maskz_loadu_epi8((__mmask64)keep, (const void*)(s + i));
+        uint64_t x1 = _mm512_test_epi8_mask(x, b2), x0 = _mm512_test_epi8_mask(x, b1);
+        uint64_t v = _mm512_cmpeq_epi8_mask(_mm512_shuffle_epi8(lut, x), _mm512_or_si512(x, case_bit)) & keep;
+        w.put<false, PEEL>(~x1 & v, ~(x1 ^ x0) & v, v, m);
+    }
+}
+
+TREW_AVX512 void pack_reads_avx512(const ChunkView& cv, uint32_t r0, uint32_t r1, uint32_t* off, uint64_t pos, BitWriter& w_out) {
+    BitWriter w = w_out;  // local copy: its address never escapes, so the state stays in registers across the plane stores
+    const __m512i lut = _mm512_broadcast_i32x4(_mm_setr_epi8(0, 'a', 0, 'c', 't', 0, 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0));
+    const __m512i case_bit = _mm512_set1_epi8(0x20), b2 = _mm512_set1_epi8(4), b1 = _mm512_set1_epi8(2);
+    const char* p; uint32_t len; size_t slack;
+    uint32_t r = r0;
+    for (; r < r1 && w.peeling(); r++) {
+        cv.get(r, p, len, slack);
+        *off++ = (uint32_t)pos; pos += len;
+        pack_read_avx512<true>(w, (const unsigned char*)p, len, lut, case_bit, b2, b1);
+    }
+    for (; r < r1; r++) {
+        cv.get(r, p, len, slack);
+        *off++ = (uint32_t)pos; pos += len;
+        pack_read_avx512<false>(w, (const unsigned char*)p, len, lut, case_bit, b2, b1);
+    }
+    w_out = w;
+}
 #endif
-    for (; i < n; i += 32) {
-        int m = n - i < 32 ? n - i : 32;
-        masks_scalar(s + i, m, h, l, v);
-        w.put(h, l, v, m);
-    }
+
+int simd_level() {  // 0 scalar, 1 AVX2, 2 AVX-512BW; TREW_PACK_SIMD=0/1/2 caps it (tests)
+#if defined(__x86_64__)
+    static const int v = [] {
+        int lvl = 0;
+        if (__builtin_cpu_supports("avx2")) lvl = 1;
+        if (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw")) lvl = 2;
+        if (const char* e = getenv("TREW_PACK_SIMD")) { int cap = atoi(e); if (cap < lvl) lvl = cap < 0 ? 0 : cap; }
+        return lvl;
+    }();
+    return v;
+#else
+    return 0;
+#endif
 }
 
 }  // namespace
@@ -156,29 +255,45 @@ void batch_layout(void* dst, uint32_t n_reads, uint64_t total_bases, BatchView* 
     v->bytes = off + 3 * words * 4;
 }
 
-// Pack reads[r0, r1) whose first base sits at bit position v.bit_off[r0].
-void pack_range(const ReadRef* reads, uint32_t r0, uint32_t r1, const BatchView& v, const char* buf_end) {
-    if (r0 >= r1) return;
-    const bool avx2 = have_avx2();
-    BitWriter w(v.hi, v.lo, v.val, v.bit_off[r0]);
-    for (uint32_t r = r0; r < r1; r++) {
-        const char* e = reads[r].ptr + reads[r].len;
-        size_t slack = (buf_end && buf_end > e) ? (size_t)(buf_end - e) : 0;
-        pack_one(w, (const unsigned char*)reads[r].ptr, (int)reads[r].len, avx2, slack);
-    }
-    w.finish();
+void chunk_stats(const ChunkView& cv, uint32_t r0, uint32_t r1, uint64_t* bases, uint32_t* max_len) {
+    uint64_t t = 0; uint32_t mx = 0;
+    const char* p; uint32_t len; size_t slack;
+    for (uint32_t r = r0; r < r1; r++) { cv.get(r, p, len, slack); t += len; if (len > mx) mx = len; }
+    *bases = t; *max_len = mx;
 }
 
-// Fills bit_off and zeroes the words that pack_range() will OR into (range boundaries + tail pad).
-void pack_prepare(const ReadRef* reads, uint32_t n, const uint32_t* range_starts, int n_ranges, const BatchView& v) {
-    uint64_t pos = 0;
-    for (uint32_t r = 0; r < n; r++) { v.bit_off[r] = (uint32_t)pos; pos += reads[r].len; }
-    v.bit_off[n] = (uint32_t)pos;
+void pack_chunk_range(const ChunkView& cv, uint32_t r0, uint32_t r1, uint32_t out0, uint64_t bit0, const BatchView& v,
+                      uint64_t side[3]) {
+    side[0] = side[1] = side[2] = 0;
+    if (r0 >= r1) return;
+    BitWriter w(v.hi, v.lo, v.val, bit0);
+    const int lvl = simd_level();
+#if defined(__x86_64__)
+    if (lvl == 2) pack_reads_avx512(cv, r0, r1, v.bit_off + out0, bit0, w);
+    else if (lvl == 1) pack_reads_avx2(cv, r0, r1, v.bit_off + out0, bit0, w);
+    else
+#endif
+        pack_reads_scalar(cv, r0, r1, v.bit_off + out0, bit0, w);
+    (void)lvl;
+    w.finish();
+    side[0] = w.side[0]; side[1] = w.side[1]; side[2] = w.side[2];
+}
+
+void pack_fixup(const uint64_t* range_bit0, const uint64_t (*side)[3], int n_ranges, const BatchView& v) {
+    uint64_t *hi = (uint64_t*)v.hi, *lo = (uint64_t*)v.lo, *val = (uint64_t*)v.val;
     for (int i = 0; i < n_ranges; i++) {
-        uint64_t wi = (uint64_t)v.bit_off[range_starts[i]] >> 5;
-        v.hi[wi] = 0; v.lo[wi] = 0; v.val[wi] = 0;
+        uint64_t u = range_bit0[i] >> 6;
+        hi[u] |= side[i][0]; lo[u] |= side[i][1]; val[u] |= side[i][2];
     }
-    for (size_t wi = (size_t)(pos >> 5); wi < v.plane_words; wi++) { v.hi[wi] = 0; v.lo[wi] = 0; v.val[wi] = 0; }
+}
+
+void pack_prepare(const uint64_t* range_bit0, int n_ranges, uint64_t total_bases, const BatchView& v) {
+    // 64-bit units: the one holding each range's first bit, and everything from the unit of the last bit on
+    for (int i = 0; i < n_ranges; i++) {
+        uint64_t wi = (range_bit0[i] >> 6) * 2;
+        v.hi[wi] = 0; v.lo[wi] = 0; v.val[wi] = 0; v.hi[wi + 1] = 0; v.lo[wi + 1] = 0; v.val[wi + 1] = 0;
+    }
+    for (size_t wi = (size_t)(total_bases >> 6) * 2; wi < v.plane_words; wi++) { v.hi[wi] = 0; v.lo[wi] = 0; v.val[wi] = 0; }
 }
 
 }  // namespace trew
@@ -188,22 +303,20 @@ extern "C" {
 size_t trew_pack_bound(uint32_t n_reads, uint64_t total_bases) { return trew::batch_bytes(n_reads, total_bases); }
 
 int trew_pack_reads(const char* buffer, const int32_t* locs, uint32_t n, void* dst, size_t dst_bytes, trew_batch* out) {
-    if ((n && (!buffer || !locs)) || !dst || !out) return TREW_ERR_ARG;
-    std::vector<trew::ReadRef> reads(n);
+    if ((n && (!buffer || !locs)) || !dst || !out || ((uintptr_t)dst & 7) != 0) return TREW_ERR_ARG;
+    trew::ChunkView cv{{buffer, nullptr}, {locs, nullptr}, {nullptr, nullptr}, 1u};
     uint64_t total = 0; uint32_t mx = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        int32_t st = locs[2 * i], nd = locs[2 * i + 1];
-        uint32_t len = nd >= st ? (uint32_t)(nd - st + 1) : 0u;
-        reads[i] = trew::ReadRef{buffer + st, len};
-        total += len; if (len > mx) mx = len;
-    }
+    trew::chunk_stats(cv, 0, n, &total, &mx);
     if (total >= 0xffffffffULL) return TREW_ERR_ARG;
     if (trew::batch_bytes(n, total) > dst_bytes) return TREW_ERR_ARG;
     trew::BatchView v;
     trew::batch_layout(dst, n, total, &v);
-    uint32_t zero = 0;
-    trew::pack_prepare(reads.data(), n, &zero, n ? 1 : 0, v);
-    trew::pack_range(reads.data(), 0, n, v, nullptr);
+    uint64_t zero = 0;
+    trew::pack_prepare(&zero, 1, total, v);
+    uint64_t side[1][3];
+    trew::pack_chunk_range(cv, 0, n, 0, 0, v, side[0]);
+    trew::pack_fixup(&zero, side, 1, v);
+    v.bit_off[n] = (uint32_t)total;
     out->n_reads = n; out->max_read_len = mx; out->bit_off = v.bit_off; out->hi = v.hi; out->lo = v.lo; out->val = v.val;
     return TREW_OK;
 }
