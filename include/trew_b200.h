@@ -153,9 +153,9 @@ int trew_synth_resident(trew_ctx* ctx, uint64_t seed, uint32_t n_reads, uint32_t
 /* CUDA-event stopwatch on the context's scan stream (for device-resident scans). */
 int trew_dev_timer_start(trew_ctx* ctx);
 int trew_dev_timer_stop(trew_ctx* ctx, float* ms); /* waits for the stream */
-/* Per-kernel CUDA-event times accumulated over resident scans since the last call: filter, exact (ms),
- * and the number of scans they cover. */
-int trew_dev_kernel_times(trew_ctx* ctx, double* filter_ms, double* exact_ms, uint64_t* n_scans);
+/* Per-kernel CUDA-event times (ms) accumulated over resident scans since the last call -- screen kernel, decide
+ * kernel, exact kernel -- and the number of scans they cover. */
+int trew_dev_kernel_times(trew_ctx* ctx, double* screen_ms, double* decide_ms, double* exact_ms, uint64_t* n_scans);
 
 /* ---- output: the ResultMapData side (src/kmer.h:79-81, src/kmer.cpp:1486-1515) ------------------ */
 

@@ -22,8 +22,8 @@ with api.DeviceContext(api.MODE_SHORT, mn, mx) as ctx:
     for _ in range(scans):
         ctx.scan_resident(h)
     ctx.sync()
-    f, e, n = ctx.kernel_times()
+    s, d, e, n = ctx.kernel_times()
     st = ctx.stats()
-    print("reads %d scans %d filter %.3f ms/scan exact %.3f ms/scan survivors %.4f" %
-          (reads, n, f / n, e / n, st.survivors / st.units))
+    print("reads %d scans %d screen %.3f decide %.3f exact %.3f ms/scan survivors %.4f" %
+          (reads, n, s / n, d / n, e / n, st.survivors / st.units))
     ctx.free_resident(h)

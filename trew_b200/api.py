@@ -109,7 +109,8 @@ def load_library() -> C.CDLL:
                                       C.c_uint32, C.POINTER(C.c_void_p)]
     L.trew_dev_timer_start.argtypes = [C.c_void_p]
     L.trew_dev_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
-    L.trew_dev_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    L.trew_dev_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                        C.POINTER(C.c_uint64)]
     L.trew_ingest_file.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_uint64, CHUNK_SINK,
                                    C.c_void_p, C.c_char_p, C.c_size_t]
     L.trew_report_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
@@ -270,10 +271,11 @@ class DeviceContext:
         self._check(self.lib.trew_dev_timer_stop(self.ctx, C.byref(ms)))
         return ms.value
 
-    def kernel_times(self) -> Tuple[float, float, int]:
-        f, e, n = C.c_double(), C.c_double(), C.c_uint64()
-        self._check(self.lib.trew_dev_kernel_times(self.ctx, C.byref(f), C.byref(e), C.byref(n)))
-        return f.value, e.value, n.value
+    def kernel_times(self) -> Tuple[float, float, float, int]:
+        """(screen_ms, decide_ms, exact_ms, n_scans) accumulated over resident scans since the last call."""
+        s, d, e, n = C.c_double(), C.c_double(), C.c_double(), C.c_uint64()
+        self._check(self.lib.trew_dev_kernel_times(self.ctx, C.byref(s), C.byref(d), C.byref(e), C.byref(n)))
+        return s.value, d.value, e.value, n.value
 
     def sync(self) -> None:
         self._check(self.lib.trew_dev_sync(self.ctx))

@@ -48,7 +48,7 @@ struct trew_resident {
     unsigned int* d_counters = nullptr;
     unsigned char* d_scratch = nullptr;
     size_t scratch_bytes = 0;
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // before filter, between, after exact
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // before screen, after screen, after decide, after exact
     bool ev_pending = false;
 };
 
@@ -75,7 +75,7 @@ struct trew_ctx {
     std::string err;
     std::vector<RangeInfo> ranges_tmp;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
-    double filter_ms = 0, exact_ms = 0; uint64_t n_prof_scans = 0;
+    double screen_ms = 0, decide_ms = 0, exact_ms = 0; uint64_t n_prof_scans = 0;
     std::vector<trew_resident*> pending_prof;
     void* h_export = nullptr; size_t h_export_bytes = 0;
 };
@@ -136,14 +136,15 @@ int launch_scan(trew_ctx* ctx, const DevBatch& b, uint32_t n_units, uint32_t max
     }
     CK(cudaMemsetAsync(d_counters, 0, 4 * sizeof(unsigned int), st));
     if (ev) CK(cudaEventRecord(ev[0], st));
-    launch_filter(ctx->dcfg, b, n_units, max_read_len, d_survivors + n_units, d_counters + 2, d_survivors, d_counters, ctx->sm_count, st);
-    if (ev) CK(cudaEventRecord(ev[1], st));
+    launch_filter(ctx->dcfg, b, n_units, max_read_len, d_survivors + n_units, d_counters + 2, d_survivors, d_counters, ctx->sm_count, st,
+                  ev ? ev[1] : nullptr);
+    if (ev) CK(cudaEventRecord(ev[2], st));
     ExactArgs a{};
     a.survivors = d_survivors; a.n_survivors = d_counters; a.work_counter = d_counters + 1;
     a.slice_scratch = *d_scratch; a.slice_scratch_stride = stride; a.run_cap = run_cap_for(ctx->cfg, max_read_len);
     a.total_survivors = ctx->d_total_surv;
     launch_exact(ctx->dcfg, b, a, ctx->sm_count, st);
-    if (ev) CK(cudaEventRecord(ev[2], st));
+    if (ev) CK(cudaEventRecord(ev[3], st));
     CK(cudaGetLastError());
     ctx->stats.kernel_launches += 3;
     return TREW_OK;
@@ -280,12 +281,13 @@ int submit_chunk_view(trew_ctx* ctx, const ChunkView& cv, uint32_t n) {
 int collect_prof(trew_ctx* ctx) {
     for (trew_resident* r : ctx->pending_prof) {
         if (!r->ev_pending) continue;
-        CK(cudaEventSynchronize(r->ev[2]));
-        float a = 0, b = 0;
+        CK(cudaEventSynchronize(r->ev[3]));
+        float a = 0, b = 0, c = 0;
         CK(cudaEventElapsedTime(&a, r->ev[0], r->ev[1]));
         CK(cudaEventElapsedTime(&b, r->ev[1], r->ev[2]));
-        ctx->filter_ms += a; ctx->exact_ms += b; ctx->n_prof_scans++;
-        ctx->stats.device_ms += a + b;
+        CK(cudaEventElapsedTime(&c, r->ev[2], r->ev[3]));
+        ctx->screen_ms += a; ctx->decide_ms += b; ctx->exact_ms += c; ctx->n_prof_scans++;
+        ctx->stats.device_ms += a + b + c;
         r->ev_pending = false;
     }
     ctx->pending_prof.clear();
@@ -517,7 +519,7 @@ int trew_dev_scan_resident(trew_ctx* ctx, const trew_resident* rb) {
     CK(cudaSetDevice(ctx->cfg.device));
     trew_resident* r = const_cast<trew_resident*>(rb);
     if (r->ev_pending) { int rc0 = collect_prof(ctx); if (rc0) return rc0; }
-    if (!r->ev[0]) for (int i = 0; i < 3; i++) CK(cudaEventCreate(&r->ev[i]));
+    if (!r->ev[0]) for (int i = 0; i < 4; i++) CK(cudaEventCreate(&r->ev[i]));
     CK(cudaEventRecord(ctx->ev_a, ctx->main_stream));
     int rc = launch_scan(ctx, r->batch, r->n_units, r->max_read_len, r->d_survivors, r->d_counters, &r->d_scratch,
                          &r->scratch_bytes, ctx->main_stream, r->ev);
@@ -531,7 +533,7 @@ int trew_dev_scan_resident(trew_ctx* ctx, const trew_resident* rb) {
 void trew_dev_free_resident(trew_ctx* ctx, trew_resident* r) {
     if (!r) return;
     if (ctx) { cudaSetDevice(ctx->cfg.device); cudaStreamSynchronize(ctx->main_stream); collect_prof(ctx); }
-    for (int i = 0; i < 3; i++) if (r->ev[i]) cudaEventDestroy(r->ev[i]);
+    for (int i = 0; i < 4; i++) if (r->ev[i]) cudaEventDestroy(r->ev[i]);
     if (r->d_buf) cudaFree(r->d_buf);
     if (r->d_survivors) cudaFree(r->d_survivors);
     if (r->d_counters) cudaFree(r->d_counters);
@@ -697,16 +699,17 @@ int trew_dev_timer_stop(trew_ctx* ctx, float* ms) {
     return TREW_OK;
 }
 
-int trew_dev_kernel_times(trew_ctx* ctx, double* filter_ms, double* exact_ms, uint64_t* n_scans) {
+int trew_dev_kernel_times(trew_ctx* ctx, double* screen_ms, double* decide_ms, double* exact_ms, uint64_t* n_scans) {
     if (!ctx) return TREW_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
     CK(cudaStreamSynchronize(ctx->main_stream));
     int rc = collect_prof(ctx);
     if (rc) return rc;
-    if (filter_ms) *filter_ms = ctx->filter_ms;
+    if (screen_ms) *screen_ms = ctx->screen_ms;
+    if (decide_ms) *decide_ms = ctx->decide_ms;
     if (exact_ms) *exact_ms = ctx->exact_ms;
     if (n_scans) *n_scans = ctx->n_prof_scans;
-    ctx->filter_ms = ctx->exact_ms = 0; ctx->n_prof_scans = 0;
+    ctx->screen_ms = ctx->decide_ms = ctx->exact_ms = 0; ctx->n_prof_scans = 0;
     return TREW_OK;
 }
 

@@ -50,11 +50,31 @@ __device__ __forceinline__ u64 mix64(u64 x) {
 // ------------------------------------------------------------------------------------------------
 
 __device__ __noinline__ void table_add_impl(Slot* slots, u32 slot_mask, u32* error_flag, u32 meta, u64 lo, u64 hi, u64 cnt) {
+#ifdef TREW_EXP_NOADD
+    return;
+#endif
     u64 h = mix64(lo ^ mix64(hi + 0x9e3779b97f4a7c15ULL * (u64)(meta + 1)));
     u32 i = (u32)h & slot_mask;
     for (u32 probe = 0; probe <= slot_mask; probe++, i = (i + 1) & slot_mask) {
         Slot* s = slots + i;
-        u32 st = atomicCAS(&s->state, 0u, 1u);
+        // fast path (almost every add hits an existing key): one 32-byte read of the slot, then a fire-and-forget add
+        const uint4 a = __ldcg(reinterpret_cast<const uint4*>(s)), c = __ldcg(reinterpret_cast<const uint4*>(s) + 1);
+        u32 st = c.w;
+        if (st == 2u) {
+            if (c.z == meta && a.x == (u32)lo && a.y == (u32)(lo >> 32) && a.z == (u32)hi && a.w == (u32)(hi >> 32)) {
+                atomicAdd(&s->count, cnt);  // keys never change once written, so a match cannot be a torn read
+                return;
+            }
+            // mismatch: the two 16-byte reads are not ordered against a concurrent writer, so look again now that the
+            // slot is known to be ready before concluding that another key lives here
+            __threadfence();
+            if (__ldcg(&s->meta) == meta && __ldcg(&s->seq_lo) == lo && __ldcg(&s->seq_hi) == hi) {
+                atomicAdd(&s->count, cnt);
+                return;
+            }
+            continue;
+        }
+        st = atomicCAS(&s->state, 0u, 1u);
         if (st == 0u) {
             s->seq_lo = lo; s->seq_hi = hi; s->meta = meta;
             __threadfence();
@@ -396,6 +416,7 @@ constexpr u32 kPackH = (1u << 8) - (1u << 24);
 constexpr u32 kPackL = (1u << 16) - (1u << 24);
 constexpr int kFastMaxWl = 95;
 constexpr int kFastTabSize = kFastMaxWl + 2;
+constexpr int kProbeShift = 28;  // deferred-list entry: unit index | probe mask << 28
 
 // per-T entry: x = packed base word, y / z = masks of the window positions in words 0 / 1
 __device__ __forceinline__ uint4 fast_entry(int T, int need) {
@@ -475,14 +496,74 @@ __global__ void __launch_bounds__(256, TREW_SCREEN_BPS) trew_screen_kernel(DevCf
     u32 stride = gridDim.x * blockDim.x;
     u32 n_round = (n_units + 31u) & ~31u;
     for (u32 u = blockIdx.x * blockDim.x + threadIdx.x; u < n_round; u += stride) {
-        bool defer = false;
+        u32 pm = 0;  // probes the decide kernel has to look at
         if (u < n_units) {
             Probe p[4];
             int np = unit_probes(cfg, b, u, p);
-            for (int i = 0; i < np && !defer; i++) defer = screen_probe(b, p[i], tab);
+            for (int i = 0; i < np; i++) pm |= screen_probe(b, p[i], tab) ? 1u << i : 0u;
         }
-        list_append(defer, u, deferred, n_deferred);
+        list_append(pm != 0, u | (pm << kProbeShift), deferred, n_deferred);
     }
+}
+
+// Deciding test for one probe window of at most 95 bases, invalid bases allowed: per period, the 4-bucket bound on the
+// first 64 window positions plus the E windows beyond them (necessary condition, as in the screen), then the exact
+// 3-word bound, then the #A-parity second level.  Same decisions as probe_filter<3>, fewer instructions.
+__device__ __forceinline__ int max4(int a, int b, int c, int d) { return max(max(a, b), max(c, d)); }
+
+template <int S>
+__device__ __forceinline__ bool decide_span(const u32 (&ph)[5], const u32 (&pl)[5], const u32 (&pa)[5], u32 (&wv)[3], int ka, int kb,
+                                            const unsigned short* __restrict__ thr, bool& done) {
+    for (int k = ka; k <= kb; k++) {
+        const int T01 = __popc(wv[0]) + __popc(wv[1]), E = __popc(wv[2]), T = T01 + E;
+        if (T == 0) { done = true; return false; }  // the valid-window mask only shrinks with k
+        const int need = thr[T];
+        u32 a0 = (__funnelshift_r(ph[S], ph[S + 1], k) ^ ph[0]) & wv[0], a1 = (__funnelshift_r(ph[S + 1], ph[S + 2], k) ^ ph[1]) & wv[1];
+        u32 b0 = (__funnelshift_r(pl[S], pl[S + 1], k) ^ pl[0]) & wv[0], b1 = (__funnelshift_r(pl[S + 1], pl[S + 2], k) ^ pl[1]) & wv[1];
+        int cH = __popc(a0) + __popc(a1), cL = __popc(b0) + __popc(b1), c11 = __popc(a0 & b0) + __popc(a1 & b1);
+        if (max4(c11, cH - c11, cL - c11, T01 - cH - cL + c11) + E >= need) {
+            u32 a2 = (__funnelshift_r(ph[S + 2], ph[S + 3], k) ^ ph[2]) & wv[2], b2 = (__funnelshift_r(pl[S + 2], pl[S + 3], k) ^ pl[2]) & wv[2];
+            cH += __popc(a2); cL += __popc(b2); c11 += __popc(a2 & b2);
+            const int c10 = cH - c11, c01 = cL - c11, c00 = T - cH - cL + c11;
+            if (max4(c11, c10, c01, c00) >= need) {
+                u32 x0 = __funnelshift_r(pa[S], pa[S + 1], k) ^ pa[0], x1 = __funnelshift_r(pa[S + 1], pa[S + 2], k) ^ pa[1];
+                u32 x2 = __funnelshift_r(pa[S + 2], pa[S + 3], k) ^ pa[2];
+                int n11 = __popc(a0 & b0 & x0) + __popc(a1 & b1 & x1) + __popc(a2 & b2 & x2);
+                int n10 = __popc(a0 & ~b0 & x0) + __popc(a1 & ~b1 & x1) + __popc(a2 & ~b2 & x2);
+                int n01 = __popc(b0 & ~a0 & x0) + __popc(b1 & ~a1 & x1) + __popc(b2 & ~a2 & x2);
+                int n00 = __popc(wv[0] & ~a0 & ~b0 & x0) + __popc(wv[1] & ~a1 & ~b1 & x1) + __popc(wv[2] & ~a2 & ~b2 & x2);
+                int U2 = max(max4(n11, c11 - n11, n10, c10 - n10), max4(n01, c01 - n01, n00, c00 - n00));
+                if (U2 >= need) return true;
+            }
+        }
+        u32 t0 = __funnelshift_r(wv[0], wv[1], 1), t1 = __funnelshift_r(wv[1], wv[2], 1), t2 = wv[2] >> 1;
+        wv[0] &= t0; wv[1] &= t1; wv[2] &= t2;
+    }
+    return false;
+}
+
+__device__ __noinline__ bool decide_short(const DevBatch& b, u32 pos, int wl, int k0, int k1, const unsigned short* __restrict__ thr) {
+    u32 wv[3], ph[5], pl[5], pa[5];
+    load_bits<3>(b.val, pos, wv); mask_bits<3>(wv, wl);
+    {
+        u32 h[3], l[3], q[3];
+        load_bits<3>(b.hi, pos, h); mask_bits<3>(h, wl); prefix_xor_excl<3>(h, q);
+        ph[0] = q[0]; ph[1] = q[1]; ph[2] = q[2]; ph[3] = 0u; ph[4] = 0u;
+        load_bits<3>(b.lo, pos, l); mask_bits<3>(l, wl); prefix_xor_excl<3>(l, q);
+        pl[0] = q[0]; pl[1] = q[1]; pl[2] = q[2]; pl[3] = 0u; pl[4] = 0u;
+#pragma unroll
+        for (int j = 0; j < 3; j++) h[j] &= l[j];
+        prefix_xor_excl<3>(h, q);
+        pa[0] = q[0]; pa[1] = q[1]; pa[2] = q[2]; pa[3] = 0u; pa[4] = 0u;
+    }
+    sliding_and<3>(wv, k0);
+    bool done = false;
+    if (k0 < 32) {
+        if (decide_span<0>(ph, pl, pa, wv, k0, min(k1, 31), thr, done)) return true;
+        if (done) return false;
+        k0 = 32;
+    }
+    return k1 >= 32 && decide_span<1>(ph, pl, pa, wv, k0, k1, thr, done);
 }
 
 // ---- decide kernel: exact 4-bucket bound + A-parity second level for every (probe, k) of the deferred units ----
@@ -500,10 +581,15 @@ __global__ void __launch_bounds__(256) trew_filter_kernel(DevCfg cfg, DevBatch b
         bool maybe = false;
         u32 u = 0;
         if (i < n_units) {
-            u = units ? units[i] : i;
+            u32 pm = 0xfu;
+            u = i;
+            if (units) { u32 e = units[i]; u = e & ((1u << kProbeShift) - 1u); pm = e >> kProbeShift; }
             Probe p[4];
             int np = unit_probes(cfg, b, u, p);
-            for (int j = 0; j < np && !maybe; j++) maybe = probe_dispatch<MAXNW>(b, p[j], thr);
+            for (int j = 0; j < np && !maybe; j++) {
+                if (!((pm >> j) & 1u) || p[j].k1 < p[j].k0) continue;
+                maybe = probe_is_fast(p[j]) ? decide_short(b, p[j].pos, p[j].wl, p[j].k0, p[j].k1, thr) : probe_dispatch<MAXNW>(b, p[j], thr);
+            }
         }
         list_append(maybe, u, survivors, n_survivors);
     }
@@ -511,7 +597,7 @@ __global__ void __launch_bounds__(256) trew_filter_kernel(DevCfg cfg, DevBatch b
 
 void launch_filter(const DevCfg& cfg, const DevBatch& b, unsigned int n_units, unsigned int max_read_len,
                    unsigned int* deferred, unsigned int* n_deferred, unsigned int* survivors, unsigned int* n_survivors,
-                   int sm_count, cudaStream_t stream) {
+                   int sm_count, cudaStream_t stream, cudaEvent_t after_screen) {
     if (n_units == 0) return;
     // longest probe window: a half read, a whole read (n < 4*MAX) or a slice (long mode)
     unsigned int longest;
@@ -519,12 +605,13 @@ void launch_filter(const DevCfg& cfg, const DevBatch& b, unsigned int n_units, u
     else longest = (max_read_len < 4u * (unsigned)cfg.max_mer) ? max_read_len : (max_read_len + 1) / 2;
     unsigned int need = (n_units + 255) / 256;
     // the screen handles windows of at most 95 bases; long-mode slices longer than that all go to the decide kernel
-    const bool screen = deferred != nullptr && !(cfg.mode == 2 && cfg.slice_len > kFastMaxWl);
+    const bool screen = deferred != nullptr && !(cfg.mode == 2 && cfg.slice_len > kFastMaxWl) && n_units < (1u << kProbeShift);
     if (screen) {
         int blocks = sm_count * TREW_SCREEN_BPS;
         if ((unsigned)blocks > need) blocks = (int)need;
         trew_screen_kernel<<<blocks, 256, 0, stream>>>(cfg, b, n_units, deferred, n_deferred);
     }
+    if (after_screen) cudaEventRecord(after_screen, stream);
     const unsigned int* list = screen ? deferred : nullptr;
     int blocks = sm_count * 8;
     if ((unsigned)blocks > need) blocks = (int)need;
@@ -549,7 +636,10 @@ constexpr int kPlaneWords = 36;  // 32 window words + zero padding for shifted r
 #ifndef TREW_EXACT_BPS
 #define TREW_EXACT_BPS 8   // resident exact-kernel blocks per SM the register budget allows
 #endif
-constexpr int kExactWarps = 4;
+#ifndef TREW_EXACT_WARPS
+#define TREW_EXACT_WARPS 4
+#endif
+constexpr int kExactWarps = TREW_EXACT_WARPS;
 constexpr u32 kEmptySlot = 0xffffffffu;
 
 enum { HD_CUR_POS = 0, HD_CUR_LEN, HD_ALLVALID, HD_EV_POS, HD_EV_LEN, HD_EV_K, HD_EV_PACK, HD_S = 8 /* 4 words: s_lo, s_hi */ };
@@ -570,7 +660,7 @@ __host__ __device__ inline size_t exact_warp_bytes(int cap) {
 size_t exact_smem_bytes(int run_cap, bool) { return exact_warp_bytes(run_cap) * kExactWarps; }
 
 struct WS {  // this warp's region
-    u32 off; int cap; int hs;
+    u32 off; int cap; int hs; u32 lane;
     __device__ __forceinline__ u32* hdr() const { return (u32*)(g_smem + off); }
     __device__ __forceinline__ u32* H() const { return (u32*)(g_smem + off + 64); }
     __device__ __forceinline__ u32* L() const { return H() + kPlaneWords; }
@@ -666,7 +756,7 @@ __device__ __noinline__ void load_window(WS ws, const u32* __restrict__ bhi, con
     u32* hd = ws.hdr();
     if ((int)hd[HD_CUR_LEN] == len && hd[HD_CUR_POS] == pos) return;
     __syncwarp();
-    const u32 lane = lane_id();
+    const u32 lane = ws.lane;
     int vbits = len - 32 * (int)lane;
     u32 msk = vbits <= 0 ? 0u : low_mask(vbits);
     u32 h = 0, l = 0, v = 0;
@@ -741,7 +831,7 @@ __device__ __forceinline__ void kmer_at(const u64* __restrict__ rev2, int len, i
 
 // this lane's window-valid word for period k: bit i of word j set iff bases 32j+i .. 32j+i+k-1 are all valid
 __device__ __forceinline__ u32 wv_for_k(WS ws, int len, int k) {
-    const u32 lane = lane_id();
+    const u32 lane = ws.lane;
     if (ws.hdr()[HD_ALLVALID]) {
         int vb = len - k + 1 - 32 * (int)lane;
         return vb <= 0 ? 0u : low_mask(min(32, vb));
@@ -761,7 +851,7 @@ __device__ __forceinline__ u32 wv_step(u32 wv, u32 lane) {
 
 // upper bound on the largest class count for period k from the 4-bucket parity signature (warp-cooperative)
 __device__ __forceinline__ int bound_k(WS ws, int k, u32 wv, int T) {
-    const u32 lane = lane_id();
+    const u32 lane = ws.lane;
     const u32 *PH = ws.PH(), *PL = ws.PL();
     int s = k >> 5, r = k & 31;
     u32 qh = __funnelshift_r(PH[lane + s], PH[lane + s + 1], r);
@@ -779,7 +869,7 @@ __device__ __forceinline__ int bound_k(WS ws, int k, u32 wv, int T) {
 // first reaches M (stored in the header).  Leaves the run list in shared memory (run_lo/hi canonical class
 // per run, run_total = class total on one run of each class, 0 on the others) for emit_classes().
 __device__ __noinline__ u32 eval_k(WS ws, int len, int k, u32 wv) {
-    const u32 lane = lane_id();
+    const u32 lane = ws.lane;
     u32* hd = ws.hdr();
     int T = (int)__reduce_add_sync(0xffffffffu, (u32)__popc(wv));
     if (T == 0) return 0u;
@@ -888,8 +978,8 @@ __device__ __noinline__ void emit_classes(TableRef tr, WS ws, int k, int nruns, 
     u32 meta = ((u32)table << 8) | (u32)k;
     const unsigned short* run_total = ws.run_total();
     const u64 *run_lo = ws.run_lo(), *run_hi = ws.run_hi();
-    for (int q = lane_id(); q < nruns; q += 32) {
-        int total = run_total[q];
+    for (int q = ws.lane; q < nruns; q += 32) {
+        u32 total = run_total[q];
         if (total == 0) continue;
         u64 lo = run_lo[q], hi = k > 32 ? run_hi[q] : 0ULL;
         if (folded) {
@@ -932,22 +1022,23 @@ __device__ __noinline__ ScanRes scan_stats(WS ws, DevBatch b, u32 pos, int len, 
     bool blk64L = false, blk64H = false;
     double needL = low, needH = high; // max(baseline, last accepted frequency)
     const double slack = 1.0 - 1e-12;
-    const u32 lane = lane_id();
+    const u32 lane = ws.lane;
     u32* hd = ws.hdr();
     const bool all_valid = hd[HD_ALLVALID] != 0;
 
     // one exact evaluation + the two acceptance tests of src/kmer.cpp:2221-2258
-    auto try_k = [&](int kk, int Uk, int Tk, u32 wv) {
+    // returns true when a period was accepted (the thresholds / divisor masks changed)
+    auto try_k = [&](int kk, int Uk, int Tk, u32 wv) -> bool {
         bool blkL = kk < 64 ? ((blockedL >> kk) & 1ULL) != 0 : blk64L;
         bool blkH = kk < 64 ? ((blockedH >> kk) & 1ULL) != 0 : blk64H;
-        if (blkL && blkH) return;
+        if (blkL && blkH) return false;
         double dU = (double)Uk, dT = (double)Tk;
         bool candL = !blkL && dU >= needL * dT * slack, candH = !blkH && dU >= needH * dT * slack;
-        if (!candL && !candH) return;
+        if (!candL && !candH) return false;
         u32 ev = eval_k(ws, len, kk, wv);
         if (lane == 0) { hd[HD_EV_POS] = pos; hd[HD_EV_LEN] = (u32)len; hd[HD_EV_K] = (u32)kk; hd[HD_EV_PACK] = ev; }
         __syncwarp();
-        if (pk_homo(ev) || pk_T(ev) == 0) return;
+        if (pk_homo(ev) || pk_T(ev) == 0) return false;
         double f = (double)pk_M(ev) / (double)pk_T(ev);
         bool accL = !blkL && f >= needL, accH = !blkH && f >= needH;
         if (accL || accH) {
@@ -957,7 +1048,9 @@ __device__ __noinline__ ScanRes scan_stats(WS ws, DevBatch b, u32 pos, int len, 
             eval_S(ws, slo, shi);
             if (accL) { res.tl = kk; needL = f; blockedL |= mm; blk64L |= m64; res.sl_lo = slo; res.sl_hi = shi; }
             if (accH) { res.th = kk; needH = f; blockedH |= mm; blk64H |= m64; res.sh_lo = slo; res.sh_hi = shi; }
+            return true;
         }
+        return false;
     };
 
     if (len <= 127 || all_valid) {
@@ -1010,7 +1103,14 @@ __device__ __noinline__ ScanRes scan_stats(WS ws, DevBatch b, u32 pos, int len, 
                     u32 a2 = __shfl_sync(0xffffffffu, wvv[2], bit), a3 = __shfl_sync(0xffffffffu, wvv[3], bit);
                     wv = lane == 0 ? a0 : lane == 1 ? a1 : lane == 2 ? a2 : lane == 3 ? a3 : 0u;
                 }
-                try_k(kb + bit, Uk, Tk, wv);
+                if (try_k(kb + bit, Uk, Tk, wv) && cm) {
+                    // an acceptance raised the thresholds / blocked multiples: drop the remaining periods of
+                    // this block that can no longer be accepted by either selection (lane <-> period again)
+                    bool bl = k < 64 ? ((blockedL >> k) & 1ULL) != 0 : blk64L, bh = k < 64 ? ((blockedH >> k) & 1ULL) != 0 : blk64H;
+                    double dU = (double)U, dT = (double)T;
+                    bool still = (!bl && dU >= needL * dT * slack) || (!bh && dU >= needH * dT * slack);
+                    cm &= __ballot_sync(0xffffffffu, still);
+                }
             }
         }
         return res;
@@ -1034,7 +1134,7 @@ __device__ __noinline__ u32 eval_cached(WS ws, DevBatch b, u32 pos, int len, int
     load_window(ws, b.hi, b.lo, b.val, pos, len);
     u32 wv = wv_for_k(ws, len, k);
     u32 ev = eval_k(ws, len, k, wv);
-    if (lane_id() == 0) { hd[HD_EV_POS] = pos; hd[HD_EV_LEN] = (u32)len; hd[HD_EV_K] = (u32)k; hd[HD_EV_PACK] = ev; }
+    if (ws.lane == 0) { hd[HD_EV_POS] = pos; hd[HD_EV_LEN] = (u32)len; hd[HD_EV_K] = (u32)k; hd[HD_EV_PACK] = ev; }
     __syncwarp();
     return ev;
 }
@@ -1202,7 +1302,7 @@ __device__ void route_long(const DevCfg& cfg, TableRef tr, WS ws, const DevBatch
     int nf = 0;
     for (int ti = 1; ti <= snum && !(ended[0] && ended[1]); ti++) {
         ScanRes sr = scan_stats(ws, b, b0 + s_start(ti), s_len(ti), MINM, MAXM, cfg.low, cfg.high);
-        if (lane_id() == 0) { scratch[2 * (ti - 1)] = (unsigned char)sr.th; scratch[2 * (ti - 1) + 1] = (unsigned char)sr.tl; }
+        if (ws.lane == 0) { scratch[2 * (ti - 1)] = (unsigned char)sr.th; scratch[2 * (ti - 1) + 1] = (unsigned char)sr.tl; }
         int k[2] = {sr.th, sr.tl};
 #pragma unroll
         for (int c = 0; c < 2; c++) {
@@ -1247,7 +1347,7 @@ __global__ void __launch_bounds__(kExactWarps * 32, TREW_EXACT_BPS) trew_exact_k
     const u32 lane = lane_id();
     WS ws;
     ws.cap = a.run_cap; ws.hs = exact_hash_slots(a.run_cap);
-    ws.off = (u32)((size_t)wid * exact_warp_bytes(a.run_cap));
+    ws.off = (u32)((size_t)wid * exact_warp_bytes(a.run_cap)); ws.lane = lane;
     TableRef tr{cfg.slots, cfg.slot_mask, cfg.error_flag};
     if (lane < 16) ws.hdr()[lane] = lane == HD_CUR_LEN || lane == HD_EV_LEN || lane == HD_EV_K ? 0xffffffffu : 0u;
     __syncwarp();

@@ -60,7 +60,7 @@ struct ExactArgs {
 // deferred / n_deferred: scratch list of n_units entries + its counter (zeroed) for the screen kernel
 void launch_filter(const DevCfg& cfg, const DevBatch& b, unsigned int n_units, unsigned int max_read_len,
                    unsigned int* deferred, unsigned int* n_deferred, unsigned int* survivors, unsigned int* n_survivors,
-                   int sm_count, cudaStream_t stream);
+                   int sm_count, cudaStream_t stream, cudaEvent_t after_screen = nullptr);
 size_t exact_smem_bytes(int run_cap, bool wide);
 cudaError_t prepare_exact(int run_cap_max);
 void launch_exact(const DevCfg& cfg, const DevBatch& b, const ExactArgs& a, int sm_count, cudaStream_t stream);
