@@ -126,15 +126,14 @@ def reference_available():
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     cores = os.cpu_count() or 1
     line = {"metric": METRIC, "unit": "Gbases/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "impl": "reference", "config": {"workload": workload_name(args.reads)}}
     if not reference_available():
         line["unavailable"] = "oracle/_ref/trew_ref missing (reference not compiled into this tree)"
-        print(json.dumps(line))
-        return
+        return line
     tmp = tempfile.mkdtemp(prefix="trew_ref_")
     try:
         # calibrate on 100k reads, then size the sample so warmup + steps stay within ~150 s
@@ -156,7 +155,7 @@ def run_reference_arm(args):
                      "cpu_baseline": {"value": value, "unit": "Gbases/s", "cores": cores, "kind": "reference", "sample": sample_desc},
                      "e2e": {"value": value, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                      "gpu_launches": 0})
-        print(json.dumps(line))
+        return line
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 
@@ -175,6 +174,8 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints one JSON line
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     device = torch.device("cuda", local_rank)
@@ -192,7 +193,10 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    ctx = api.DeviceContext(api.MODE_SHORT, 5, 32, device=local_rank, n_staging=3, staging_bytes=96 << 20)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    host_threads = max(2, (os.cpu_count() or 2) // max(1, local_world))  # the ranks of one box share its cores
+    ctx = api.DeviceContext(api.MODE_SHORT, 5, 32, device=local_rank, n_staging=3, staging_bytes=96 << 20,
+                            host_threads=min(32, host_threads))
 
     # ---- device-resident workload: weak scaling, every rank holds args.reads reads -------------------
     handles, reads_left, i = [], args.reads, 0
@@ -210,7 +214,9 @@ def run_ours(args):
         for h, _ in handles:
             ctx.scan_resident(h)
         # sync + compaction kernel + D2H of the tables (+ exact NCCL merge across ranks for N > 1)
-        merged_last[0] = ctx.finish_view() if world == 1 else merge.merge_rows(ctx.finish_arrays(), device)
+        if world > 1:
+            merge.merge_device(ctx, device)
+        merged_last[0] = ctx.finish_view() if rank == 0 else None
 
     for _ in range(args.warmup):
         step()
@@ -250,7 +256,9 @@ def run_ours(args):
         ctx.reset()
         for _ in range(reps):
             ctx.submit_chunk(buf, locs)
-        return ctx.finish_view() if world == 1 else merge.merge_rows(ctx.finish_arrays(), device)
+        if world > 1:
+            merge.merge_device(ctx, device)
+        return ctx.finish_view() if rank == 0 else None
 
     for _ in range(max(1, min(args.warmup, 2))):
         e2e_step()
@@ -307,12 +315,12 @@ def run_ours(args):
                 pass
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line))
     for h, _ in handles:
         ctx.free_resident(h)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+    return line if rank == 0 else None
 
 
 def cpu_baseline():
@@ -342,10 +350,19 @@ def main():
     ap.add_argument("--e2e-reads", type=int, default=8_000_000, help="reads per end-to-end step (host buffers)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference_arm(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly one JSON line (rank 0): native libraries that print there (NCCL's version banner)
+    # are diverted to stderr for the duration of the run
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = run_reference_arm(args) if args.impl == "reference" else run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

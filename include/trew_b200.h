@@ -164,13 +164,19 @@ int trew_dev_kernel_times(trew_ctx* ctx, double* screen_ms, double* decide_ms, d
 int trew_dev_sync(trew_ctx* ctx);
 
 /* Drain, compact the device table and return the six maps as one array sorted by (table, k, seq).
- * The array is owned by the context and valid until the next call that touches the tables. */
+ * The array (pinned host memory) is owned by the context and valid until the next call that touches the tables. */
 int trew_dev_finish(trew_ctx* ctx, const trew_entry** entries, uint64_t* n_entries);
 
-/* Device-side view of the same compacted entries (for NCCL merges across ranks): three parallel
- * device arrays of n entries: meta = table << 8 | k, seq (lo, hi interleaved), count. */
-int trew_dev_export_device(trew_ctx* ctx, const uint32_t** d_meta, const uint64_t** d_seq,
-                           const uint64_t** d_count, uint64_t* n_entries);
+/* Device-side view of the same entries (compacted and sorted on the device): n entries in device memory, owned by
+ * the context and valid until the next call that touches the tables. */
+int trew_dev_export_device(trew_ctx* ctx, const trew_entry** d_entries, uint64_t* n_entries);
+
+/* Cross-rank merge (one process per GPU): copy the compacted table (trew_entry rows, 32 bytes each) into
+ * caller-owned DEVICE memory -- e.g. the buffer of an NCCL gather -- and add rows received from another rank to this
+ * context's table.  Integer sums, hence exact; this is the multi-GPU form of the per-worker map sum in
+ * process_output (src/kmer.cpp:1486-1515).  trew_dev_export_rows with d_rows == NULL only reports the row count. */
+int trew_dev_export_rows(trew_ctx* ctx, trew_entry* d_rows, uint64_t capacity_rows, uint64_t* n_rows);
+int trew_dev_merge_rows(trew_ctx* ctx, const trew_entry* d_rows, uint64_t n_rows);
 
 /* Zero the count table (start of a new file; the reference allocates fresh maps per file,
  * src/kmer.cpp:89). */

@@ -152,3 +152,22 @@ def test_device_generator_matches_numpy_mirror():
     want = Oracle(5, 32).scan(0, [bytes(r) for r in mat])
     assert got == want, diff_msg(got, want)
     assert len(got) > 50
+
+
+def test_device_row_merge():
+    """The multi-GPU merge path on one GPU: two contexts scan disjoint shards, the second one's table is exported as
+    device rows and added to the first (trew_dev_export_rows / trew_dev_merge_rows); the result equals one context
+    scanning everything."""
+    import torch
+    reads = synth.adversarial_short(13, 2400)
+    whole = run_gpu(api.MODE_SHORT, 5, 32, 0.5, 0.8, 150, reads)
+    with api.DeviceContext(api.MODE_SHORT, 5, 32) as c1, api.DeviceContext(api.MODE_SHORT, 5, 32) as c2:
+        c1.submit_reads(reads[:1000])
+        c2.submit_reads(reads[1000:])
+        n = c2.export_rows()
+        assert n > 0
+        rows = torch.zeros((n, 4), dtype=torch.int64, device="cuda:0")
+        assert c2.export_rows(rows.data_ptr(), n) == n
+        c1.merge_rows(rows.data_ptr(), n)
+        merged = c1.finish()
+    assert merged == whole, diff_msg(merged, whole)

@@ -64,7 +64,7 @@ ABI_SYMBOLS = [
     "trew_dev_export_device", "trew_dev_reset", "trew_dev_get_stats", "trew_pack_bound", "trew_pack_reads",
     "trew_synth_resident", "trew_dev_timer_start", "trew_dev_timer_stop", "trew_dev_kernel_times",
     "trew_dev_process_file", "trew_ingest_file", "trew_report_create", "trew_report_destroy", "trew_report_add_file",
-    "trew_report_finish",
+    "trew_report_finish", "trew_dev_export_rows", "trew_dev_merge_rows",
 ]
 
 CHUNK_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_uint32, C.c_void_p,
@@ -97,8 +97,9 @@ def load_library() -> C.CDLL:
     L.trew_dev_last_resident_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.trew_dev_sync.argtypes = [C.c_void_p]
     L.trew_dev_finish.argtypes = [C.c_void_p, C.POINTER(C.POINTER(Entry)), C.POINTER(C.c_uint64)]
-    L.trew_dev_export_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
-                                         C.POINTER(C.c_uint64)]
+    L.trew_dev_export_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.trew_dev_export_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.trew_dev_merge_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     L.trew_dev_reset.argtypes = [C.c_void_p]
     L.trew_dev_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     L.trew_pack_bound.argtypes = [C.c_uint32, C.c_uint64]
@@ -318,10 +319,21 @@ class DeviceContext:
         return {(p[i].table, p[i].k, (p[i].seq_hi << 64) | p[i].seq_lo): p[i].count for i in range(n)}
 
     def export_device(self):
-        """(meta_ptr, seq_ptr, count_ptr, n): device pointers to the compacted table (for NCCL merges)."""
-        m, s, c, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint64()
-        self._check(self.lib.trew_dev_export_device(self.ctx, C.byref(m), C.byref(s), C.byref(c), C.byref(n)))
-        return m.value, s.value, c.value, n.value
+        """(entries_ptr, n): device pointer to the compacted, sorted table (trew_entry rows)."""
+        e, n = C.c_void_p(), C.c_uint64()
+        self._check(self.lib.trew_dev_export_device(self.ctx, C.byref(e), C.byref(n)))
+        return e.value, n.value
+
+    def export_rows(self, d_rows: Optional[int] = None, capacity_rows: int = 0) -> int:
+        """Compact the table; with a device pointer, also copy it there as trew_entry rows (32 bytes each).
+        Returns the row count."""
+        n = C.c_uint64()
+        self._check(self.lib.trew_dev_export_rows(self.ctx, d_rows, capacity_rows, C.byref(n)))
+        return n.value
+
+    def merge_rows(self, d_rows: int, n_rows: int) -> None:
+        """Add rows (device pointer, the format of export_rows) to this context's table."""
+        self._check(self.lib.trew_dev_merge_rows(self.ctx, d_rows, n_rows))
 
     def reset(self) -> None:
         self._check(self.lib.trew_dev_reset(self.ctx))

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -55,6 +56,11 @@ struct trew_resident {
 struct trew_ctx {
     trew_config cfg{};
     int sm_count = 0;
+    LaunchPlan plan{};
+    cudaStream_t aux_stream = nullptr;   // second stream for device-resident scans (consecutive batches overlap)
+    cudaEvent_t ev_join = nullptr;
+    int resident_streams = 1;
+    uint64_t resident_seq = 0;
     DevCfg dcfg{};
     size_t n_slots = 0;
     unsigned int* d_error = nullptr;
@@ -66,10 +72,10 @@ struct trew_ctx {
     cudaStream_t main_stream = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     // export buffers
-    unsigned int* d_meta = nullptr; unsigned long long* d_seq = nullptr; unsigned long long* d_count = nullptr;
+    trew_entry* d_entries = nullptr; size_t d_entries_cap = 0;   // compacted, sorted table (device)
+    void* d_sort_tmp = nullptr; size_t sort_tmp_bytes = 0;
     unsigned int* d_n = nullptr;
     uint64_t n_export = 0;
-    std::vector<trew_entry> entries;
     trew_stats stats{};
     Pool* pool = nullptr;
     std::string err;
@@ -136,14 +142,14 @@ int launch_scan(trew_ctx* ctx, const DevBatch& b, uint32_t n_units, uint32_t max
     }
     CK(cudaMemsetAsync(d_counters, 0, 4 * sizeof(unsigned int), st));
     if (ev) CK(cudaEventRecord(ev[0], st));
-    launch_filter(ctx->dcfg, b, n_units, max_read_len, d_survivors + n_units, d_counters + 2, d_survivors, d_counters, ctx->sm_count, st,
+    launch_filter(ctx->dcfg, b, n_units, max_read_len, d_survivors + n_units, d_counters + 2, d_survivors, d_counters, ctx->plan, st,
                   ev ? ev[1] : nullptr);
     if (ev) CK(cudaEventRecord(ev[2], st));
     ExactArgs a{};
     a.survivors = d_survivors; a.n_survivors = d_counters; a.work_counter = d_counters + 1;
     a.slice_scratch = *d_scratch; a.slice_scratch_stride = stride; a.run_cap = run_cap_for(ctx->cfg, max_read_len);
     a.total_survivors = ctx->d_total_surv;
-    launch_exact(ctx->dcfg, b, a, ctx->sm_count, st);
+    launch_exact(ctx->dcfg, b, a, ctx->plan, st);
     if (ev) CK(cudaEventRecord(ev[3], st));
     CK(cudaGetLastError());
     ctx->stats.kernel_launches += 3;
@@ -294,6 +300,22 @@ int collect_prof(trew_ctx* ctx) {
     return TREW_OK;
 }
 
+// main_stream waits for everything queued on aux_stream so far
+int join_aux(trew_ctx* ctx) {
+    if (ctx->resident_streams != 2) return TREW_OK;
+    CK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+    CK(cudaStreamWaitEvent(ctx->main_stream, ctx->ev_join, 0));
+    return TREW_OK;
+}
+
+// aux_stream waits for everything queued on main_stream so far
+int fork_aux(trew_ctx* ctx) {
+    if (ctx->resident_streams != 2) return TREW_OK;
+    CK(cudaEventRecord(ctx->ev_join, ctx->main_stream));
+    CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_join, 0));
+    return TREW_OK;
+}
+
 int check_device_error(trew_ctx* ctx) {
     unsigned int e = 0;
     CK(cudaMemcpy(&e, ctx->d_error, sizeof(e), cudaMemcpyDeviceToHost));
@@ -348,6 +370,16 @@ int trew_dev_create(const trew_config* cfg, trew_ctx** out) {
     cudaDeviceProp prop;
     CKC(cudaGetDeviceProperties(&prop, cfg->device));
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->plan = default_launch_plan(ctx->sm_count);
+    {
+        // tuning knobs (experiments): blocks per SM of each scan kernel, and 2 streams for resident scans
+        auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e && *e ? atoi(e) : dflt; };
+        int v;
+        if ((v = env_int("TREW_GRID_SCREEN", 0)) > 0) ctx->plan.screen_blocks = std::min(ctx->plan.screen_blocks, ctx->sm_count * v);
+        if ((v = env_int("TREW_GRID_DECIDE", 0)) > 0) ctx->plan.decide_blocks = std::min(ctx->plan.decide_blocks, ctx->sm_count * v);
+        if ((v = env_int("TREW_GRID_EXACT", 0)) > 0) ctx->plan.exact_blocks = std::min(ctx->plan.exact_blocks, ctx->sm_count * v);
+        ctx->resident_streams = env_int("TREW_RESIDENT_STREAMS", 1) >= 2 ? 2 : 1;
+    }
     int lg = cfg->table_log2_slots > 0 ? cfg->table_log2_slots : 22;
     if (lg < 10 || lg > 28) { fail(ctx, TREW_ERR_ARG, "table_log2_slots out of range"); return bail(TREW_ERR_ARG); }
     ctx->n_slots = (size_t)1 << lg;
@@ -368,6 +400,8 @@ int trew_dev_create(const trew_config* cfg, trew_ctx** out) {
     ctx->dcfg.error_flag = ctx->d_error; ctx->dcfg.thr_low = ctx->d_thr;
     CKC(prepare_exact(kMaxWindow + 9));
     CKC(cudaStreamCreateWithFlags(&ctx->main_stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     CKC(cudaEventCreate(&ctx->ev_a));
     CKC(cudaEventCreate(&ctx->ev_b));
     CKC(cudaEventCreate(&ctx->ev_t0));
@@ -411,12 +445,13 @@ void trew_dev_destroy(trew_ctx* ctx) {
     if (ctx->d_error) cudaFree(ctx->d_error);
     if (ctx->d_thr) cudaFree(ctx->d_thr);
     if (ctx->d_total_surv) cudaFree(ctx->d_total_surv);
-    if (ctx->d_meta) cudaFree(ctx->d_meta);
-    if (ctx->d_seq) cudaFree(ctx->d_seq);
-    if (ctx->d_count) cudaFree(ctx->d_count);
+    if (ctx->d_entries) cudaFree(ctx->d_entries);
+    if (ctx->d_sort_tmp) cudaFree(ctx->d_sort_tmp);
     if (ctx->d_n) cudaFree(ctx->d_n);
     if (ctx->h_export) cudaFreeHost(ctx->h_export);
     if (ctx->main_stream) cudaStreamDestroy(ctx->main_stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
@@ -520,19 +555,20 @@ int trew_dev_scan_resident(trew_ctx* ctx, const trew_resident* rb) {
     trew_resident* r = const_cast<trew_resident*>(rb);
     if (r->ev_pending) { int rc0 = collect_prof(ctx); if (rc0) return rc0; }
     if (!r->ev[0]) for (int i = 0; i < 4; i++) CK(cudaEventCreate(&r->ev[i]));
-    CK(cudaEventRecord(ctx->ev_a, ctx->main_stream));
+    cudaStream_t st = (ctx->resident_streams == 2 && (ctx->resident_seq++ & 1)) ? ctx->aux_stream : ctx->main_stream;
+    CK(cudaEventRecord(ctx->ev_a, st));
     int rc = launch_scan(ctx, r->batch, r->n_units, r->max_read_len, r->d_survivors, r->d_counters, &r->d_scratch,
-                         &r->scratch_bytes, ctx->main_stream, r->ev);
+                         &r->scratch_bytes, st, r->ev);
     r->ev_pending = true; ctx->pending_prof.push_back(r);
     if (rc) return rc;
-    CK(cudaEventRecord(ctx->ev_b, ctx->main_stream));
+    CK(cudaEventRecord(ctx->ev_b, st));
     ctx->stats.reads += r->n_reads; ctx->stats.bases += r->bases; ctx->stats.units += r->n_units;
     return TREW_OK;
 }
 
 void trew_dev_free_resident(trew_ctx* ctx, trew_resident* r) {
     if (!r) return;
-    if (ctx) { cudaSetDevice(ctx->cfg.device); cudaStreamSynchronize(ctx->main_stream); collect_prof(ctx); }
+    if (ctx) { cudaSetDevice(ctx->cfg.device); cudaStreamSynchronize(ctx->main_stream); cudaStreamSynchronize(ctx->aux_stream); collect_prof(ctx); }
     for (int i = 0; i < 4; i++) if (r->ev[i]) cudaEventDestroy(r->ev[i]);
     if (r->d_buf) cudaFree(r->d_buf);
     if (r->d_survivors) cudaFree(r->d_survivors);
@@ -545,32 +581,52 @@ int trew_dev_sync(trew_ctx* ctx) {
     if (!ctx) return TREW_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
     for (auto& s : ctx->slots) { int rc = retire_slot(ctx, s); if (rc) return rc; }
+    { int rc = join_aux(ctx); if (rc) return rc; }
     CK(cudaStreamSynchronize(ctx->main_stream));
     { int rc = collect_prof(ctx); if (rc) return rc; }
     return check_device_error(ctx);
 }
 
-int trew_dev_export_device(trew_ctx* ctx, const uint32_t** d_meta, const uint64_t** d_seq, const uint64_t** d_count,
-                           uint64_t* n_entries) {
+int trew_dev_export_device(trew_ctx* ctx, const trew_entry** d_entries, uint64_t* n_entries) {
     if (!ctx) return TREW_ERR_ARG;
     int rc = trew_dev_sync(ctx);
     if (rc) return rc;
-    if (!ctx->d_meta) {
-        CK(cudaMalloc((void**)&ctx->d_meta, ctx->n_slots * sizeof(unsigned int)));
-        CK(cudaMalloc((void**)&ctx->d_seq, ctx->n_slots * 2 * sizeof(unsigned long long)));
-        CK(cudaMalloc((void**)&ctx->d_count, ctx->n_slots * sizeof(unsigned long long)));
-    }
-    CK(cudaMemsetAsync(ctx->d_n, 0, sizeof(unsigned int), ctx->main_stream));
-    launch_compact(ctx->dcfg.slots, (unsigned int)ctx->n_slots, ctx->d_meta, ctx->d_seq, ctx->d_count, ctx->d_n, ctx->main_stream);
-    CK(cudaGetLastError());
-    ctx->stats.kernel_launches += 1;
+    // count first (the table is sparse: sizing the entry array by the slot count would waste 128 MB)
     unsigned int n = 0;
-    CK(cudaMemcpyAsync(&n, ctx->d_n, sizeof(n), cudaMemcpyDeviceToHost, ctx->main_stream));
-    CK(cudaStreamSynchronize(ctx->main_stream));
+    for (int pass = 0; pass < 2; pass++) {
+        CK(cudaMemsetAsync(ctx->d_n, 0, sizeof(unsigned int), ctx->main_stream));
+        if (pass == 0 && ctx->d_entries_cap == 0) {
+            ctx->d_entries_cap = (size_t)1 << 20;
+            CK(cudaMalloc((void**)&ctx->d_entries, ctx->d_entries_cap * sizeof(trew_entry)));
+        }
+        launch_compact(ctx->dcfg.slots, (unsigned int)ctx->n_slots, ctx->d_entries, ctx->d_n, ctx->main_stream, (unsigned int)ctx->d_entries_cap);
+        CK(cudaGetLastError());
+        ctx->stats.kernel_launches += 1;
+        CK(cudaMemcpyAsync(&n, ctx->d_n, sizeof(n), cudaMemcpyDeviceToHost, ctx->main_stream));
+        CK(cudaStreamSynchronize(ctx->main_stream));
+        if (n <= ctx->d_entries_cap) break;
+        // the array was too small (the kernel only counted past its end): grow and compact again
+        CK(cudaFree(ctx->d_entries));
+        ctx->d_entries = nullptr;
+        ctx->d_entries_cap = (size_t)n + n / 4 + 1024;
+        CK(cudaMalloc((void**)&ctx->d_entries, ctx->d_entries_cap * sizeof(trew_entry)));
+    }
+    if (n > 1) {
+        size_t need = 0;
+        CK(sort_entries(ctx->d_entries, n, nullptr, &need, ctx->main_stream));
+        if (need > ctx->sort_tmp_bytes) {
+            if (ctx->d_sort_tmp) CK(cudaFree(ctx->d_sort_tmp));
+            ctx->d_sort_tmp = nullptr;
+            ctx->sort_tmp_bytes = need + need / 4;
+            CK(cudaMalloc(&ctx->d_sort_tmp, ctx->sort_tmp_bytes));
+        }
+        size_t bytes = ctx->sort_tmp_bytes;
+        CK(sort_entries(ctx->d_entries, n, ctx->d_sort_tmp, &bytes, ctx->main_stream));
+        CK(cudaStreamSynchronize(ctx->main_stream));
+        ctx->stats.kernel_launches += 2;
+    }
     ctx->n_export = n;
-    if (d_meta) *d_meta = ctx->d_meta;
-    if (d_seq) *d_seq = (const uint64_t*)ctx->d_seq;
-    if (d_count) *d_count = (const uint64_t*)ctx->d_count;
+    if (d_entries) *d_entries = ctx->d_entries;
     if (n_entries) *n_entries = n;
     return TREW_OK;
 }
@@ -578,10 +634,10 @@ int trew_dev_export_device(trew_ctx* ctx, const uint32_t** d_meta, const uint64_
 int trew_dev_finish(trew_ctx* ctx, const trew_entry** entries, uint64_t* n_entries) {
     if (!ctx) return TREW_ERR_ARG;
     uint64_t n = 0;
-    int rc = trew_dev_export_device(ctx, nullptr, nullptr, nullptr, &n);
+    int rc = trew_dev_export_device(ctx, nullptr, &n);
     if (rc) return rc;
-    // D2H through a pinned bounce buffer (grown on demand)
-    size_t need = (size_t)n * 28 + 64;
+    // one D2H of the sorted entries into a pinned array (grown on demand) that is handed to the caller as is
+    size_t need = (size_t)n * sizeof(trew_entry) + 64;
     if (need > ctx->h_export_bytes) {
         if (ctx->h_export) CK(cudaFreeHost(ctx->h_export));
         ctx->h_export = nullptr;
@@ -589,79 +645,48 @@ int trew_dev_finish(trew_ctx* ctx, const trew_entry** entries, uint64_t* n_entri
         CK(cudaHostAlloc(&ctx->h_export, cap, cudaHostAllocDefault));
         ctx->h_export_bytes = cap;
     }
-    unsigned long long* seq = (unsigned long long*)ctx->h_export;
-    unsigned long long* cnt = seq + 2 * n;
-    unsigned int* meta = (unsigned int*)(cnt + n);
     if (n) {
-        CK(cudaMemcpyAsync(seq, ctx->d_seq, 2 * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->main_stream));
-        CK(cudaMemcpyAsync(cnt, ctx->d_count, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->main_stream));
-        CK(cudaMemcpyAsync(meta, ctx->d_meta, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->main_stream));
+        CK(cudaMemcpyAsync(ctx->h_export, ctx->d_entries, n * sizeof(trew_entry), cudaMemcpyDeviceToHost, ctx->main_stream));
         CK(cudaStreamSynchronize(ctx->main_stream));
     }
-    ctx->stats.d2h_bytes += n * 28 + 4;
-    ctx->entries.resize(n);
-    auto less = [](const trew_entry& a, const trew_entry& b) {
-        if (a.table != b.table) return a.table < b.table;
-        if (a.k != b.k) return a.k < b.k;
-        if (a.seq_hi != b.seq_hi) return a.seq_hi < b.seq_hi;
-        return a.seq_lo < b.seq_lo;
-    };
-    // Sort by (table, k, seq) so the output does not depend on insertion order.  Sample sort on the pool:
-    // splitters from a regular sample, scatter into key-range buckets, sort every bucket independently.
-    const int P = (int)std::min<uint64_t>((uint64_t)ctx->pool->size(), n / 8192 + 1);
-    auto unpack = [&](uint64_t j) {
-        trew_entry e;
-        e.table = (int32_t)(meta[j] >> 8); e.k = (int32_t)(meta[j] & 0xff);
-        e.seq_lo = seq[2 * j]; e.seq_hi = seq[2 * j + 1]; e.count = cnt[j];
-        return e;
-    };
-    trew_entry* E = ctx->entries.data();
-    if (P <= 1) {
-        for (uint64_t j = 0; j < n; j++) E[j] = unpack(j);
-        std::sort(E, E + n, less);
-    } else {
-        std::vector<trew_entry> sample;
-        const uint64_t ns = (uint64_t)P * 64;
-        for (uint64_t i = 0; i < ns; i++) sample.push_back(unpack(i * n / ns));
-        std::sort(sample.begin(), sample.end(), less);
-        std::vector<trew_entry> split;
-        for (int i = 1; i < P; i++) split.push_back(sample[(size_t)i * 64]);
-        std::vector<uint64_t> cut(P + 1);
-        for (int i = 0; i <= P; i++) cut[i] = n * (uint64_t)i / (uint64_t)P;
-        std::vector<uint64_t> counts((size_t)P * P, 0);
-        std::vector<unsigned char> bucket(n);
-        ctx->pool->run(P, [&](int t) {
-            for (uint64_t j = cut[t]; j < cut[t + 1]; j++) {
-                trew_entry e = unpack(j);
-                int bk = (int)(std::upper_bound(split.begin(), split.end(), e, less) - split.begin());
-                bucket[j] = (unsigned char)bk;
-                counts[(size_t)t * P + bk]++;
-            }
-        });
-        std::vector<uint64_t> start((size_t)P * P), bstart(P + 1, 0);
-        uint64_t acc = 0;
-        for (int bk = 0; bk < P; bk++) {
-            bstart[bk] = acc;
-            for (int t = 0; t < P; t++) { start[(size_t)t * P + bk] = acc; acc += counts[(size_t)t * P + bk]; }
-        }
-        bstart[P] = acc;
-        ctx->pool->run(P, [&](int t) {
-            uint64_t* st = &start[(size_t)t * P];
-            for (uint64_t j = cut[t]; j < cut[t + 1]; j++) E[st[bucket[j]]++] = unpack(j);
-        });
-        ctx->pool->run(P, [&](int bk) { std::sort(E + bstart[bk], E + bstart[bk + 1], less); });
-    }
-    if (entries) *entries = ctx->entries.data();
+    ctx->stats.d2h_bytes += n * sizeof(trew_entry) + 4;
+    if (entries) *entries = (const trew_entry*)ctx->h_export;
     if (n_entries) *n_entries = n;
     return TREW_OK;
+}
+
+int trew_dev_export_rows(trew_ctx* ctx, trew_entry* d_rows, uint64_t capacity_rows, uint64_t* n_rows) {
+    if (!ctx || !n_rows) return TREW_ERR_ARG;
+    uint64_t n = 0;
+    int rc = trew_dev_export_device(ctx, nullptr, &n);
+    if (rc) return rc;
+    *n_rows = n;
+    if (!d_rows) return TREW_OK;  // size query
+    if (n > capacity_rows) return fail(ctx, TREW_ERR_ARG, "row buffer too small: %llu rows, capacity %llu", (unsigned long long)n,
+                                       (unsigned long long)capacity_rows);
+    if (n) CK(cudaMemcpyAsync(d_rows, ctx->d_entries, n * sizeof(trew_entry), cudaMemcpyDeviceToDevice, ctx->main_stream));
+    CK(cudaStreamSynchronize(ctx->main_stream));
+    return TREW_OK;
+}
+
+int trew_dev_merge_rows(trew_ctx* ctx, const trew_entry* d_rows, uint64_t n_rows) {
+    if (!ctx || (n_rows && !d_rows) || n_rows > 0xffffffffULL) return TREW_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    launch_merge_entries(ctx->dcfg, d_rows, (unsigned int)n_rows, ctx->main_stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->main_stream));
+    ctx->stats.kernel_launches += n_rows ? 1 : 0;
+    return check_device_error(ctx);
 }
 
 int trew_dev_reset(trew_ctx* ctx) {
     if (!ctx) return TREW_ERR_ARG;
     int rc = trew_dev_sync(ctx);
     if (rc && rc != TREW_ERR_TABLE_FULL) return rc;
-    CK(cudaMemset(ctx->dcfg.slots, 0, ctx->n_slots * sizeof(Slot)));
-    CK(cudaMemset(ctx->d_error, 0, sizeof(unsigned int)));
+    // on the scan stream (the context's streams do not synchronise with the legacy default stream)
+    CK(cudaMemsetAsync(ctx->dcfg.slots, 0, ctx->n_slots * sizeof(Slot), ctx->main_stream));
+    CK(cudaMemsetAsync(ctx->d_error, 0, sizeof(unsigned int), ctx->main_stream));
+    CK(cudaStreamSynchronize(ctx->main_stream));
     return TREW_OK;
 }
 
@@ -687,12 +712,13 @@ int trew_dev_timer_start(trew_ctx* ctx) {
     if (!ctx) return TREW_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
     CK(cudaEventRecord(ctx->ev_t0, ctx->main_stream));
-    return TREW_OK;
+    return fork_aux(ctx);
 }
 
 int trew_dev_timer_stop(trew_ctx* ctx, float* ms) {
     if (!ctx || !ms) return TREW_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
+    { int rc = join_aux(ctx); if (rc) return rc; }
     CK(cudaEventRecord(ctx->ev_t1, ctx->main_stream));
     CK(cudaEventSynchronize(ctx->ev_t1));
     CK(cudaEventElapsedTime(ms, ctx->ev_t0, ctx->ev_t1));
@@ -702,6 +728,7 @@ int trew_dev_timer_stop(trew_ctx* ctx, float* ms) {
 int trew_dev_kernel_times(trew_ctx* ctx, double* screen_ms, double* decide_ms, double* exact_ms, uint64_t* n_scans) {
     if (!ctx) return TREW_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
+    { int rc0 = join_aux(ctx); if (rc0) return rc0; }
     CK(cudaStreamSynchronize(ctx->main_stream));
     int rc = collect_prof(ctx);
     if (rc) return rc;

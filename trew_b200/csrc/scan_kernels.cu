@@ -92,28 +92,14 @@ __device__ __noinline__ void table_add_impl(Slot* slots, u32 slot_mask, u32* err
     atomicExch(error_flag, 3u);  // TREW_ERR_TABLE_FULL
 }
 
-__global__ void compact_kernel(const Slot* __restrict__ slots, u32 n_slots, u32* __restrict__ d_meta,
-                               u64* __restrict__ d_seq, u64* __restrict__ d_count, u32* __restrict__ d_n) {
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += gridDim.x * blockDim.x) {
-        Slot s = slots[i];
-        bool used = s.state == 2u && s.count != 0;
-        u32 m = __ballot_sync(0xffffffffu, used);
-        if (m) {
-            u32 base = 0;
-            if (lane_id() == (u32)(__ffs(m) - 1)) base = atomicAdd(d_n, (u32)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-            if (used) {
-                u32 o = base + __popc(m & ((1u << lane_id()) - 1u));
-                d_meta[o] = s.meta; d_seq[2 * (size_t)o] = s.seq_lo; d_seq[2 * (size_t)o + 1] = s.seq_hi; d_count[o] = s.count;
-            }
-        }
-    }
+// adds another table's entries to this one: the device-side analogue of the per-thread map sum, src/kmer.cpp:1486-1515
+__global__ void merge_entries_kernel(Slot* slots, u32 slot_mask, u32* error_flag, const trew_entry* __restrict__ e, u32 n) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        table_add_impl(slots, slot_mask, error_flag, ((u32)e[i].table << 8) | (u32)e[i].k, e[i].seq_lo, e[i].seq_hi, e[i].count);
 }
 
-void launch_compact(const Slot* slots, unsigned int n_slots, unsigned int* d_meta, unsigned long long* d_seq,
-                    unsigned long long* d_count, unsigned int* d_n, cudaStream_t stream) {
-    // n_slots is a power of two >= 1024, so every warp iterates the same number of times
-    compact_kernel<<<592, 256, 0, stream>>>(slots, n_slots, d_meta, d_seq, d_count, d_n);
+void launch_merge_entries(const DevCfg& cfg, const trew_entry* entries, unsigned int n, cudaStream_t stream) {
+    if (n) merge_entries_kernel<<<(n + 255) / 256, 256, 0, stream>>>(cfg.slots, cfg.slot_mask, cfg.error_flag, entries, n);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -597,7 +583,7 @@ __global__ void __launch_bounds__(256) trew_filter_kernel(DevCfg cfg, DevBatch b
 
 void launch_filter(const DevCfg& cfg, const DevBatch& b, unsigned int n_units, unsigned int max_read_len,
                    unsigned int* deferred, unsigned int* n_deferred, unsigned int* survivors, unsigned int* n_survivors,
-                   int sm_count, cudaStream_t stream, cudaEvent_t after_screen) {
+                   const LaunchPlan& plan, cudaStream_t stream, cudaEvent_t after_screen) {
     if (n_units == 0) return;
     // longest probe window: a half read, a whole read (n < 4*MAX) or a slice (long mode)
     unsigned int longest;
@@ -607,13 +593,13 @@ void launch_filter(const DevCfg& cfg, const DevBatch& b, unsigned int n_units, u
     // the screen handles windows of at most 95 bases; long-mode slices longer than that all go to the decide kernel
     const bool screen = deferred != nullptr && !(cfg.mode == 2 && cfg.slice_len > kFastMaxWl) && n_units < (1u << kProbeShift);
     if (screen) {
-        int blocks = sm_count * TREW_SCREEN_BPS;
+        int blocks = plan.screen_blocks;
         if ((unsigned)blocks > need) blocks = (int)need;
         trew_screen_kernel<<<blocks, 256, 0, stream>>>(cfg, b, n_units, deferred, n_deferred);
     }
     if (after_screen) cudaEventRecord(after_screen, stream);
     const unsigned int* list = screen ? deferred : nullptr;
-    int blocks = sm_count * 8;
+    int blocks = plan.decide_blocks;
     if ((unsigned)blocks > need) blocks = (int)need;
     if (longest + 1 <= 96) trew_filter_kernel<3><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors);
     else if (longest + 1 <= 160) trew_filter_kernel<5><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors);
@@ -1377,9 +1363,11 @@ cudaError_t prepare_exact(int run_cap_max) {
     return e;
 }
 
-void launch_exact(const DevCfg& cfg, const DevBatch& b, const ExactArgs& a, int sm_count, cudaStream_t stream) {
+LaunchPlan default_launch_plan(int sm_count) { return LaunchPlan{sm_count * TREW_SCREEN_BPS, sm_count * 8, sm_count * kExactBlocksPerSM}; }
+
+void launch_exact(const DevCfg& cfg, const DevBatch& b, const ExactArgs& a, const LaunchPlan& plan, cudaStream_t stream) {
     size_t smem = exact_smem_bytes(a.run_cap, true);
-    dim3 grid(sm_count * kExactBlocksPerSM), block(kExactWarps * 32);
+    dim3 grid(plan.exact_blocks), block(kExactWarps * 32);
     if (cfg.mode == 0) trew_exact_kernel<0><<<grid, block, smem, stream>>>(cfg, b, a);
     else if (cfg.mode == 1) trew_exact_kernel<1><<<grid, block, smem, stream>>>(cfg, b, a);
     else trew_exact_kernel<2><<<grid, block, smem, stream>>>(cfg, b, a);

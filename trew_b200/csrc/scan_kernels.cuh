@@ -15,6 +15,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "../../include/trew_b200.h"
+
 namespace trew {
 
 constexpr int kThrTableSize = 1025;  // thr[T] for T = 0..1024 valid windows
@@ -56,17 +58,24 @@ struct ExactArgs {
     unsigned long long* total_survivors;  // running total over all launches (statistics)
 };
 
+// grid sizes (total blocks) of the three scan kernels; all three are grid-stride / work-counter kernels
+struct LaunchPlan { int screen_blocks, decide_blocks, exact_blocks; };
+LaunchPlan default_launch_plan(int sm_count);
+
 // host-side launchers (scan_kernels.cu)
 // deferred / n_deferred: scratch list of n_units entries + its counter (zeroed) for the screen kernel
 void launch_filter(const DevCfg& cfg, const DevBatch& b, unsigned int n_units, unsigned int max_read_len,
                    unsigned int* deferred, unsigned int* n_deferred, unsigned int* survivors, unsigned int* n_survivors,
-                   int sm_count, cudaStream_t stream, cudaEvent_t after_screen = nullptr);
+                   const LaunchPlan& plan, cudaStream_t stream, cudaEvent_t after_screen = nullptr);
 size_t exact_smem_bytes(int run_cap, bool wide);
 cudaError_t prepare_exact(int run_cap_max);
-void launch_exact(const DevCfg& cfg, const DevBatch& b, const ExactArgs& a, int sm_count, cudaStream_t stream);
+void launch_exact(const DevCfg& cfg, const DevBatch& b, const ExactArgs& a, const LaunchPlan& plan, cudaStream_t stream);
 int exact_warps_total(int sm_count);
-void launch_compact(const Slot* slots, unsigned int n_slots, unsigned int* d_meta, unsigned long long* d_seq,
-                    unsigned long long* d_count, unsigned int* d_n, cudaStream_t stream);
+// table_kernels.cu
+void launch_compact(const Slot* slots, unsigned int n_slots, trew_entry* out, unsigned int* d_n, cudaStream_t stream, unsigned int cap);
+// in-place sort by (table, k, seq); call with d_temp == nullptr to query *temp_bytes
+cudaError_t sort_entries(trew_entry* d_entries, unsigned int n, void* d_temp, size_t* temp_bytes, cudaStream_t stream);
+void launch_merge_entries(const DevCfg& cfg, const trew_entry* entries, unsigned int n, cudaStream_t stream);
 
 void launch_synth(unsigned long long seed, unsigned int n_reads, unsigned int read_len, unsigned int tel_thr,
                   unsigned int half_thr, unsigned int n_thr, unsigned int sub_thr, unsigned int* bit_off, unsigned int* hi,

@@ -60,3 +60,27 @@ def merge_rows(rows: np.ndarray, device: torch.device, dst: int = 0) -> Optional
     u = out.view(np.uint64)
     order = np.lexsort((u[:, 1], u[:, 2], u[:, 0]))
     return out[order]
+
+
+def merge_device(ctx, device: torch.device, dst: int = 0) -> None:
+    """Device-side exact merge for one process per GPU: every rank copies its compacted table (32-byte trew_entry rows) into a
+    padded buffer, the buffers are gathered to rank `dst` over NCCL, and `dst` adds the other ranks' rows to its own
+    count table with trew_dev_merge_rows (integer atomics).  Afterwards `ctx.finish*()` on rank `dst` returns the
+    merged tables.  Two small collectives per file; nothing but the rows crosses NVLink."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n = ctx.export_rows()
+    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([n], dtype=torch.int64, device=device))
+    sizes = [int(s.item()) for s in sizes]
+    n_max = max(max(sizes), 1)
+    rows = torch.zeros((n_max, 4), dtype=torch.int64, device=device)
+    ctx.export_rows(rows.data_ptr(), n_max)
+    gathered = [torch.empty_like(rows) for _ in range(world)] if rank == dst else None
+    dist.gather(rows, gathered, dst=dst)
+    if rank == dst:
+        torch.cuda.synchronize(device)
+        for r in range(world):
+            if r != dst and sizes[r]:
+                ctx.merge_rows(gathered[r].data_ptr(), sizes[r])
