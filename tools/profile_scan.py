@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Small driver for ncu: one device-resident batch of the configs[1] shape, scanned a few times.
 
-    python tools/profile_scan.py [reads] [scans] [min_mer] [max_mer] [tel_ppm] [half_ppm] [n_ppm]
+    python tools/profile_scan.py [reads] [scans] [min_mer] [max_mer] [tel_ppm] [half_ppm] [n_ppm] [mode 0 short / 1 pair / 2 long] [read_len]
 """
 import os
 import sys
@@ -17,8 +17,10 @@ mx = int(sys.argv[4]) if len(sys.argv) > 4 else 32
 tel = int(sys.argv[5]) if len(sys.argv) > 5 else 10000
 half = int(sys.argv[6]) if len(sys.argv) > 6 else 2000
 nppm = int(sys.argv[7]) if len(sys.argv) > 7 else 1000
-with api.DeviceContext(api.MODE_SHORT, mn, mx) as ctx:
-    h = ctx.synth_resident(1, reads, 150, tel_ppm=tel, half_ppm=half, n_ppm=nppm, sub_ppm=10000)
+mode = int(sys.argv[8]) if len(sys.argv) > 8 else api.MODE_SHORT
+read_len = int(sys.argv[9]) if len(sys.argv) > 9 else 150
+with api.DeviceContext(mode, mn, mx) as ctx:
+    h = ctx.synth_resident(1, reads, read_len, tel_ppm=tel, half_ppm=half, n_ppm=nppm, sub_ppm=10000)
     for _ in range(scans):
         ctx.scan_resident(h)
     ctx.sync()

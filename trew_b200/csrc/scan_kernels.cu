@@ -464,6 +464,79 @@ __device__ __forceinline__ bool screen_probe(const DevBatch& b, const Probe& p, 
     return p.k1 >= 32 && fast_span<1>(ph, pl, p.wl, k0, p.k1, tab);
 }
 
+// ---- the same first level for windows of 96..159 bases (long-read slices, 300-base short reads, the whole-read probe
+// of 150-base reads when MAX_MER > 37): four words per plane, i.e. the first 128 window positions, E = T - 128 beyond.
+constexpr int kFastMaxWlLong = 159;
+constexpr int kFastTabSizeLong = kFastMaxWlLong + 2;
+struct __align__(16) FastEntryLong { u32 base, m0, m1, m2, m3, pad0, pad1, pad2; };
+
+__device__ __forceinline__ FastEntryLong fast_entry_long(int T, int need) {
+    FastEntryLong e = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    if (T <= 0) return e;
+    const int T01 = min(T, 128);
+    u32 m[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { int vb = T - 32 * j; m[j] = vb <= 0 ? 0u : low_mask(min(32, vb)); }
+    e.m0 = m[0]; e.m1 = m[1]; e.m2 = m[2]; e.m3 = m[3];
+    const int np = need - (T - T01);
+    if (np <= 0) e.base = 0x80808080u;
+    else if (np > 128) e.base = 0u;   // no bucket of <= 128 positions can reach it: never a hit (T01 dropped on purpose:
+                                      // without the offset the byte arithmetic is not needed at all)
+    else e.base = ((u32)T01 << 24) + (u32)(128 - np) * 0x01010101u;
+    return e;
+}
+
+template <int S>
+__device__ __forceinline__ bool fast_span_long(const u32 (&ph)[8], const u32 (&pl)[8], int wl, int ka, int kb,
+                                               const FastEntryLong* __restrict__ tab) {
+    const FastEntryLong* tp = tab + (wl - ka + 1);
+    for (int k = ka; k <= kb; k++, tp--) {
+        const uint4 e0 = *reinterpret_cast<const uint4*>(tp);       // base, m0, m1, m2
+        const u32 m3 = tp->m3;
+        if (e0.x == 0u) continue;                                    // unreachable threshold (or no window)
+        const u32 mk[4] = {e0.y, e0.z, e0.w, m3};
+        int cH = 0, cL = 0, c11 = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            u32 a = (__funnelshift_r(ph[S + j], ph[S + j + 1], k) ^ ph[j]) & mk[j];
+            u32 bb = (__funnelshift_r(pl[S + j], pl[S + j + 1], k) ^ pl[j]) & mk[j];
+            cH += __popc(a); cL += __popc(bb); c11 += __popc(a & bb);
+        }
+        u32 x = e0.x + (u32)cH * kPackH + (u32)cL * kPackL + (u32)c11 * kPackC11;
+        if (x & 0x80808080u) return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ bool probe_is_fast_long(const Probe& p) { return p.wl <= kFastMaxWlLong && p.k1 <= 64 && p.k1 <= p.wl; }
+
+__device__ __noinline__ bool screen_probe_long(const DevBatch& b, const Probe& p, const FastEntryLong* __restrict__ tab) {
+    u32 t[5], full[5] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    mask_bits<5>(full, p.wl);
+    load_bits<5>(b.val, p.pos, t);
+    u32 bad = 0;
+#pragma unroll
+    for (int j = 0; j < 5; j++) bad |= (t[j] & full[j]) ^ full[j];
+    if (bad) return true;
+    u32 ph[8], pl[8], q[5];
+    load_bits<5>(b.hi, p.pos, t); mask_bits<5>(t, p.wl); prefix_xor_excl<5>(t, q);
+#pragma unroll
+    for (int j = 0; j < 8; j++) ph[j] = j < 5 ? q[j] : 0u;
+    load_bits<5>(b.lo, p.pos, t); mask_bits<5>(t, p.wl); prefix_xor_excl<5>(t, q);
+#pragma unroll
+    for (int j = 0; j < 8; j++) pl[j] = j < 5 ? q[j] : 0u;
+    int k0 = p.k0;
+    if (k0 < 32) {
+        if (fast_span_long<0>(ph, pl, p.wl, k0, min(p.k1, 31), tab)) return true;
+        k0 = 32;
+    }
+    if (k0 < 64 && p.k1 >= 32) {
+        if (fast_span_long<1>(ph, pl, p.wl, k0, min(p.k1, 63), tab)) return true;
+        k0 = 64;
+    }
+    return p.k1 >= 64 && fast_span_long<2>(ph, pl, p.wl, k0, p.k1, tab);
+}
+
 // warp-aggregated append of the flagged lanes' values to a global list
 __device__ __forceinline__ void list_append(bool flag, u32 value, u32* __restrict__ list, u32* __restrict__ count) {
     u32 m = __ballot_sync(0xffffffffu, flag);
@@ -478,10 +551,13 @@ __device__ __forceinline__ void list_append(bool flag, u32 value, u32* __restric
 #ifndef TREW_SCREEN_BPS
 #define TREW_SCREEN_BPS 8
 #endif
-__global__ void __launch_bounds__(256, TREW_SCREEN_BPS) trew_screen_kernel(DevCfg cfg, DevBatch b, u32 n_units,
-                                                                          u32* __restrict__ deferred, u32* __restrict__ n_deferred) {
+template <bool LONG>
+__global__ void __launch_bounds__(256, LONG ? 4 : TREW_SCREEN_BPS) trew_screen_kernel(DevCfg cfg, DevBatch b, u32 n_units,
+                                                                                     u32* __restrict__ deferred, u32* __restrict__ n_deferred) {
     __shared__ uint4 tab[kFastTabSize];
+    __shared__ FastEntryLong tab_long[LONG ? kFastTabSizeLong : 1];
     for (int T = threadIdx.x; T < kFastTabSize; T += blockDim.x) tab[T] = fast_entry(T, (int)cfg.thr_low[T]);
+    if (LONG) for (int T = threadIdx.x; T < kFastTabSizeLong; T += blockDim.x) tab_long[T] = fast_entry_long(T, (int)cfg.thr_low[T]);
     __syncthreads();
     u32 stride = gridDim.x * blockDim.x;
     u32 n_round = (n_units + 31u) & ~31u;
@@ -490,7 +566,12 @@ __global__ void __launch_bounds__(256, TREW_SCREEN_BPS) trew_screen_kernel(DevCf
         if (u < n_units) {
             Probe p[4];
             int np = unit_probes(cfg, b, u, p);
-            for (int i = 0; i < np; i++) pm |= screen_probe(b, p[i], tab) ? 1u << i : 0u;
+            for (int i = 0; i < np; i++) {
+                bool d;
+                if (LONG && p[i].k1 >= p[i].k0 && !probe_is_fast(p[i]) && probe_is_fast_long(p[i])) d = screen_probe_long(b, p[i], tab_long);
+                else d = screen_probe(b, p[i], tab);
+                pm |= d ? 1u << i : 0u;
+            }
         }
         list_append(pm != 0, u | (pm << kProbeShift), deferred, n_deferred);
     }
@@ -594,12 +675,13 @@ void launch_filter(const DevCfg& cfg, const DevBatch& b, unsigned int n_units, u
     if (cfg.mode == 2) longest = 2u * (unsigned)cfg.slice_len;
     else longest = (max_read_len < 4u * (unsigned)cfg.max_mer) ? max_read_len : (max_read_len + 1) / 2;
     unsigned int need = (n_units + 255) / 256;
-    // the screen handles windows of at most 95 bases; long-mode slices longer than that all go to the decide kernel
-    const bool screen = deferred != nullptr && !(cfg.mode == 2 && cfg.slice_len > kFastMaxWl) && n_units < (1u << kProbeShift);
+    // the screen handles windows of at most 159 bases; long-mode slices longer than that all go to the decide kernel
+    const bool screen = deferred != nullptr && !(cfg.mode == 2 && cfg.slice_len > kFastMaxWlLong) && n_units < (1u << kProbeShift);
     if (screen) {
         int blocks = plan.screen_blocks;
         if ((unsigned)blocks > need) blocks = (int)need;
-        trew_screen_kernel<<<blocks, 256, 0, stream>>>(cfg, b, n_units, deferred, n_deferred);
+        if (longest <= (unsigned)kFastMaxWl) trew_screen_kernel<false><<<blocks, 256, 0, stream>>>(cfg, b, n_units, deferred, n_deferred);
+        else trew_screen_kernel<true><<<blocks, 256, 0, stream>>>(cfg, b, n_units, deferred, n_deferred);
     }
     if (after_screen) cudaEventRecord(after_screen, stream);
     const unsigned int* list = screen ? deferred : nullptr;
