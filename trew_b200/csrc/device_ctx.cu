@@ -60,7 +60,6 @@ struct trew_ctx {
     cudaStream_t aux_stream = nullptr;   // second stream for device-resident scans (consecutive batches overlap)
     cudaEvent_t ev_join = nullptr;
     int resident_streams = 1;
-    bool thread_exact = false;   // experimental thread-per-survivor exact kernel (TREW_THREAD_EXACT=1)
     uint64_t resident_seq = 0;
     DevCfg dcfg{};
     size_t n_slots = 0;
@@ -150,15 +149,6 @@ int launch_scan(trew_ctx* ctx, const DevBatch& b, uint32_t n_units, uint32_t max
     a.survivors = d_survivors; a.n_survivors = d_counters; a.work_counter = d_counters + 1;
     a.slice_scratch = *d_scratch; a.slice_scratch_stride = stride; a.run_cap = run_cap_for(ctx->cfg, max_read_len);
     a.total_survivors = ctx->d_total_surv;
-    if (ctx->cfg.mode == TREW_MODE_SHORT && ctx->cfg.max_mer <= 32 && ctx->thread_exact) {
-        // short reads: one thread per survivor; what it cannot finish lands on the overflow list (the deferred list's
-        // storage, dead by now) and is done by the warp kernel
-        unsigned int* d_overflow = d_survivors + n_units;
-        launch_exact_thread(ctx->dcfg, b, d_survivors, d_counters, d_overflow, d_counters + 3, ctx->d_total_surv,
-                            ctx->plan.exact_thread_blocks, st);
-        a.survivors = d_overflow; a.n_survivors = d_counters + 3; a.total_survivors = nullptr;
-        ctx->stats.kernel_launches += 1;
-    }
     launch_exact(ctx->dcfg, b, a, ctx->plan, st);
     if (ev) CK(cudaEventRecord(ev[3], st));
     CK(cudaGetLastError());
@@ -389,8 +379,6 @@ int trew_dev_create(const trew_config* cfg, trew_ctx** out) {
         if ((v = env_int("TREW_GRID_DECIDE", 0)) > 0) ctx->plan.decide_blocks = std::min(ctx->plan.decide_blocks, ctx->sm_count * v);
         if ((v = env_int("TREW_GRID_EXACT", 0)) > 0) ctx->plan.exact_blocks = std::min(ctx->plan.exact_blocks, ctx->sm_count * v);
         ctx->resident_streams = env_int("TREW_RESIDENT_STREAMS", 1) >= 2 ? 2 : 1;
-        ctx->thread_exact = env_int("TREW_THREAD_EXACT", 0) != 0;
-        if ((v = env_int("TREW_GRID_EXACT_THREAD", 0)) > 0) ctx->plan.exact_thread_blocks = ctx->sm_count * v;
     }
     int lg = cfg->table_log2_slots > 0 ? cfg->table_log2_slots : 22;
     if (lg < 10 || lg > 28) { fail(ctx, TREW_ERR_ARG, "table_log2_slots out of range"); return bail(TREW_ERR_ARG); }

@@ -763,8 +763,16 @@ __device__ __forceinline__ bool pk_homo(u32 p) { return ((p >> 30) & 1u) != 0; }
 // ---- k-mer arithmetic (src/kmer.cpp:39-74, 1815-1867) ------------------------------------------
 
 __device__ __noinline__ u64 canon64(u64 w, int k) {
-    u64 best = w, cur = w;
     int sh = 2 * (k - 1);
+    if (k <= 16) {  // the k-mer fits 32 bits: a third of the instructions per rotation step
+        u32 b32 = (u32)w, c32 = (u32)w;
+        for (int r = 1; r < k; r++) {
+            c32 = ((c32 & 3u) << sh) | (c32 >> 2);
+            b32 = min(b32, c32);
+        }
+        return b32;
+    }
+    u64 best = w, cur = w;
     for (int r = 1; r < k; r++) {
         cur = ((cur & 3ULL) << sh) | (cur >> 2);
         best = cur < best ? cur : best;
@@ -1413,465 +1421,6 @@ __device__ void route_long(const DevCfg& cfg, TableRef tr, WS ws, const DevBatch
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// exact kernel, THREAD per survivor: short single-end reads (n <= 159 bases, MAX_MER <= 32)
-// ------------------------------------------------------------------------------------------------
-//
-// The warp-per-survivor kernel above keeps 32 lanes busy only on long windows; on a 75-base half read three lanes
-// hold data and the rest idle.  For short reads one thread does the whole of buffer_task for its survivor
-// (src/kmer.cpp:80-179) with the window's planes in registers: the same bounds, the same ascending-k selection,
-// the same run / canonical-rotation / first-to-reach-max rules as scan_stats / eval_k, restated serially.
-// Differences that keep a warp of 32 unrelated survivors convergent:
-//   * candidates are collected for all periods first, then visited by index, so the lanes' expensive evaluations
-//     line up even when their periods differ;
-//   * before an evaluation a 64-bucket bound (composition counts mod 4: rotation invariant) removes the chance
-//     candidates of windows with few valid k-windows;
-//   * an evaluation stops as soon as no class can reach the count the current thresholds require.
-// A survivor the thread path cannot finish (read longer than 159 bases, more than kThreadClassCap distinct classes
-// in one evaluation) is appended to an overflow list for the warp kernel; nothing is emitted for it here.
-
-constexpr int kThreadMaxRead = 159;
-constexpr int kThreadClassCap = 48;
-
-template <int NW>
-struct TWin {
-    u32 h[NW + 1], l[NW + 1];    // code planes of the window (bit 0 = first base), one zero word of padding
-    u32 v[NW];                   // validity plane
-    u32 ph[NW + 1], pl[NW + 1];  // exclusive prefix-XOR planes of h and l
-    u64 rev[NW + 2];             // reversed, interleaved 2-bit stream as in load_window(); indexed dynamically
-    int len;
-    bool all_valid;
-};
-
-struct TClassTab {
-    u64 key[kThreadClassCap];    // canonical rotation of the class
-    u32 agg[kThreadClassCap];    // windows in the class << 16 | ordinal of its last window
-    int n;
-};
-
-__device__ __forceinline__ u64 spread32(u32 x) {  // bit i -> bit 2i
-    u64 y = x;
-    y = (y | (y << 16)) & 0x0000FFFF0000FFFFULL;
-    y = (y | (y << 8)) & 0x00FF00FF00FF00FFULL;
-    y = (y | (y << 4)) & 0x0F0F0F0F0F0F0F0FULL;
-    y = (y | (y << 2)) & 0x3333333333333333ULL;
-    y = (y | (y << 1)) & 0x5555555555555555ULL;
-    return y;
-}
-
-template <int NW>
-__device__ __forceinline__ void shl_var(const u32 (&in)[NW], int s, u32 (&out)[NW]) {  // multiword left shift, 0 <= s < 32 * NW
-#pragma unroll
-    for (int j = 0; j < NW; j++) out[j] = in[j];
-    for (int t = s >> 5; t > 0; t--) {
-#pragma unroll
-        for (int j = NW - 1; j >= 0; j--) out[j] = j > 0 ? out[j - 1] : 0u;
-    }
-    const u32 r = (u32)s & 31u;
-#pragma unroll
-    for (int j = NW - 1; j >= 0; j--) out[j] = __funnelshift_l(j > 0 ? out[j - 1] : 0u, out[j], r);
-}
-
-template <int NW>
-__device__ __forceinline__ void tw_load(TWin<NW>& w, const DevBatch& b, u32 pos, int len) {
-    u32 t[NW], full[NW];
-    w.len = len;
-    load_bits<NW>(b.val, pos, t); mask_bits<NW>(t, len);
-    u32 diff = 0;
-#pragma unroll
-    for (int j = 0; j < NW; j++) { full[j] = 0xffffffffu; }
-    mask_bits<NW>(full, len);
-#pragma unroll
-    for (int j = 0; j < NW; j++) { w.v[j] = t[j]; diff |= t[j] ^ full[j]; }
-    w.all_valid = diff == 0u;
-    u32 hh[NW], ll[NW], q[NW];
-    load_bits<NW>(b.hi, pos, hh); mask_bits<NW>(hh, len);
-    load_bits<NW>(b.lo, pos, ll); mask_bits<NW>(ll, len);
-    prefix_xor_excl<NW>(hh, q);
-#pragma unroll
-    for (int j = 0; j < NW; j++) { w.h[j] = hh[j]; w.ph[j] = q[j]; }
-    prefix_xor_excl<NW>(ll, q);
-#pragma unroll
-    for (int j = 0; j < NW; j++) { w.l[j] = ll[j]; w.pl[j] = q[j]; }
-    w.h[NW] = 0u; w.l[NW] = 0u; w.ph[NW] = 0u; w.pl[NW] = 0u;
-    // reversed stream: left-align the window in NW words, then word j of the stream is the bit reversal of word NW-1-j
-    u32 yh[NW], yl[NW];
-    shl_var<NW>(hh, 32 * NW - len, yh);
-    shl_var<NW>(ll, 32 * NW - len, yl);
-#pragma unroll
-    for (int j = 0; j < NW; j++) w.rev[j] = (spread32(__brev(yh[NW - 1 - j])) << 1) | spread32(__brev(yl[NW - 1 - j]));
-    w.rev[NW] = 0ULL; w.rev[NW + 1] = 0ULL;
-}
-
-// window-valid words for period k, from scratch
-template <int NW>
-__device__ __forceinline__ int tw_wv(const TWin<NW>& w, int k, u32 (&wv)[NW]) {
-    if (w.all_valid) {
-        const int T = w.len - k + 1;
-#pragma unroll
-        for (int j = 0; j < NW; j++) { int vb = T - 32 * j; wv[j] = vb <= 0 ? 0u : low_mask(min(32, vb)); }
-        return T > 0 ? T : 0;
-    }
-#pragma unroll
-    for (int j = 0; j < NW; j++) wv[j] = w.v[j];
-    sliding_and<NW>(wv, k);
-    int T = 0;
-#pragma unroll
-    for (int j = 0; j < NW; j++) T += __popc(wv[j]);
-    return T;
-}
-
-// 4-bucket parity bound on the largest class (k <= 32)
-template <int NW>
-__device__ __forceinline__ int tw_bound(const TWin<NW>& w, int k, const u32 (&wv)[NW], int T) {
-    int cH = 0, cL = 0, c11 = 0;
-#pragma unroll
-    for (int j = 0; j < NW; j++) {
-        u32 dh = (__funnelshift_rc(w.ph[j], w.ph[j + 1], k) ^ w.ph[j]) & wv[j];
-        u32 dl = (__funnelshift_rc(w.pl[j], w.pl[j + 1], k) ^ w.pl[j]) & wv[j];
-        cH += __popc(dh); cL += __popc(dl); c11 += __popc(dh & dl);
-    }
-    return max4(c11, cH - c11, cL - c11, T - cH - cL + c11);
-}
-
-// 64-bucket bound: composition counts of {C,A}, {G,A}, {A} modulo 4 (see decide kernel for the mod-2 levels).  Bit 1 of
-// an exclusive prefix count is P1 = prefix-XOR of (X & P0); bit 1 of the window's count is Q1 ^ P1 ^ (~Q0 & P0).
-// Returns false iff no bucket holds `nc` windows, i.e. the largest class is smaller than nc.
-template <int NW>
-__device__ __noinline__ bool tw_strong(const TWin<NW>& w, int k, const u32 (&wv)[NW], int nc) {
-    if (nc <= 1) return true;
-    u32 d0[3][NW], d1[3][NW];
-    {
-        u32 x[NW], p0[NW + 1], p1[NW + 1], t[NW], q[NW];
-#pragma unroll
-        for (int pn = 0; pn < 3; pn++) {
-#pragma unroll
-            for (int j = 0; j < NW; j++) x[j] = pn == 0 ? w.h[j] : pn == 1 ? w.l[j] : (w.h[j] & w.l[j]);
-            if (pn == 2) { prefix_xor_excl<NW>(x, q); }
-#pragma unroll
-            for (int j = 0; j < NW; j++) p0[j] = pn == 0 ? w.ph[j] : pn == 1 ? w.pl[j] : q[j];
-            p0[NW] = 0u;
-#pragma unroll
-            for (int j = 0; j < NW; j++) t[j] = x[j] & p0[j];
-            prefix_xor_excl<NW>(t, q);
-#pragma unroll
-            for (int j = 0; j < NW; j++) p1[j] = q[j];
-            p1[NW] = 0u;
-#pragma unroll
-            for (int j = 0; j < NW; j++) {
-                u32 q0 = __funnelshift_rc(p0[j], p0[j + 1], k), q1 = __funnelshift_rc(p1[j], p1[j + 1], k);
-                d0[pn][j] = q0 ^ p0[j];
-                d1[pn][j] = q1 ^ p1[j] ^ (~q0 & p0[j]);
-            }
-        }
-    }
-    for (int v = 0; v < 8; v++) {
-        u32 m[NW];
-        int cnt = 0;
-#pragma unroll
-        for (int j = 0; j < NW; j++) {
-            m[j] = wv[j] & ((v & 1) ? d0[0][j] : ~d0[0][j]) & ((v & 2) ? d0[1][j] : ~d0[1][j]) & ((v & 4) ? d0[2][j] : ~d0[2][j]);
-            cnt += __popc(m[j]);
-        }
-        if (cnt < nc) continue;
-        for (int x = 0; x < 8; x++) {
-            int c2 = 0;
-#pragma unroll
-            for (int j = 0; j < NW; j++)
-                c2 += __popc(m[j] & ((x & 1) ? d1[0][j] : ~d1[0][j]) & ((x & 2) ? d1[1][j] : ~d1[1][j]) & ((x & 4) ? d1[2][j] : ~d1[2][j]));
-            if (c2 >= nc) return true;
-        }
-    }
-    return false;
-}
-
-// result of tw_eval: T | M << 10 | best class index << 20 | homopolymer << 28 | stopped early << 29 | overflow << 30
-__device__ __forceinline__ int te_T(u32 p) { return (int)(p & 1023u); }
-__device__ __forceinline__ int te_M(u32 p) { return (int)((p >> 10) & 1023u); }
-__device__ __forceinline__ int te_best(u32 p) { return (int)((p >> 20) & 255u); }
-__device__ __forceinline__ bool te_homo(u32 p) { return ((p >> 28) & 1u) != 0; }
-__device__ __forceinline__ bool te_stopped(u32 p) { return ((p >> 29) & 1u) != 0; }
-__device__ __forceinline__ bool te_overflow(u32 p) { return ((p >> 30) & 1u) != 0; }
-
-// Class statistics of one (window, k): the serial form of eval_k().  stop_below > 0: give up (stopped flag) as soon as
-// no class can reach stop_below windows.  Leaves every distinct class with its window total in `ct`.
-template <int NW>
-__device__ __noinline__ u32 tw_eval(const TWin<NW>& w, int k, const u32 (&wv)[NW], int T, TClassTab& ct, int stop_below) {
-    ct.n = 0;
-    if (T <= 0) return 0u;
-    u32 rs[NW];
-    {
-        u32 link[NW];
-#pragma unroll
-        for (int j = 0; j < NW; j++) {
-            u32 hs = __funnelshift_rc(w.h[j], w.h[j + 1], k), ls = __funnelshift_rc(w.l[j], w.l[j + 1], k);
-            u32 eq = ~((hs ^ w.h[j]) | (ls ^ w.l[j]));
-            u32 nxt = (wv[j] >> 1) | (j + 1 < NW ? wv[j + 1] << 31 : 0u);
-            link[j] = eq & wv[j] & nxt;   // windows i and i+1 both valid and base[i] == base[i+k]   (Lemma L1)
-        }
-#pragma unroll
-        for (int j = 0; j < NW; j++) rs[j] = wv[j] & ~((link[j] << 1) | (j > 0 ? link[j - 1] >> 31 : 0u));
-    }
-    const u64 kmask = k < 32 ? (1ULL << (2 * k)) - 1ULL : ~0ULL;
-    const int rot_sh = 2 * (k - 1);
-    int best_tot = 0, prev_cls = -1, prev_c0 = 0, ord_base = 0;
-    bool stopped = false, overflow = false;
-    u64 memo_raw[8];
-    int memo_cls[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) memo_cls[i] = -1;
-#pragma unroll
-    for (int j = 0; j < NW; j++) {
-        u32 x = stopped ? 0u : rs[j];
-        while (x) {
-            const int bit = __ffs(x) - 1;
-            x &= x - 1;
-            const int c0 = ord_base + __popc(wv[j] & ((1u << bit) - 1u));
-            if (prev_cls >= 0) {  // close the previous run: it covered ordinals [prev_c0, c0)
-                u32 a = ct.agg[prev_cls];
-                int tot = (int)(a >> 16) + (c0 - prev_c0);
-                ct.agg[prev_cls] = ((u32)tot << 16) | (u32)(c0 - 1);
-                best_tot = max(best_tot, tot);
-            }
-            if (stop_below > 0 && best_tot + (T - c0) < stop_below) { stopped = true; break; }
-            // the run's first window as a k-mer (first base most significant)
-            const int o = 2 * (w.len - (32 * j + bit) - k), wi = o >> 6, sh = o & 63;
-            const u64 ra = w.rev[wi], rb = w.rev[wi + 1];
-            const u64 raw = (sh ? (ra >> sh) | (rb << (64 - sh)) : ra) & kmask;
-            // periodic reads repeat the same few raw k-mers run after run: a tiny memo (raw -> class) skips the rotation
-            const u32 mh = (u32)((raw * 0x9e3779b97f4a7c15ULL) >> 61);
-            int c;
-            if (memo_cls[mh] >= 0 && memo_raw[mh] == raw) {
-                c = memo_cls[mh];
-            } else {
-                u64 bestv;
-                if (k <= 16) {   // canonical rotation in 32-bit arithmetic
-                    u32 cur = (u32)raw, b32 = cur;
-                    for (int r = 1; r < k; r++) {
-                        cur = ((cur & 3u) << rot_sh) | (cur >> 2);
-                        b32 = min(b32, cur);
-                    }
-                    bestv = b32;
-                } else {
-                    u64 cur = raw;
-                    bestv = raw;
-                    for (int r = 1; r < k; r++) {
-                        cur = ((cur & 3ULL) << rot_sh) | (cur >> 2);
-                        bestv = cur < bestv ? cur : bestv;
-                    }
-                }
-                c = 0;
-                const int n = ct.n;
-                while (c < n && ct.key[c] != bestv) c++;
-                if (c == n) {
-                    if (n == kThreadClassCap) { overflow = true; stopped = true; break; }
-                    ct.key[n] = bestv; ct.agg[n] = 0u; ct.n = n + 1;
-                }
-                memo_raw[mh] = raw; memo_cls[mh] = c;
-            }
-            prev_cls = c; prev_c0 = c0;
-        }
-        ord_base += __popc(wv[j]);
-    }
-    if (overflow) return 1u << 30;
-    if (stopped) return (u32)T | (1u << 29);
-    if (prev_cls >= 0) {
-        u32 a = ct.agg[prev_cls];
-        ct.agg[prev_cls] = (((a >> 16) + (u32)(T - prev_c0)) << 16) | (u32)(T - 1);
-    }
-    // K_MER_DATA_MAX_SEQ: max total, ties broken by the EARLIEST last window (strict '<' at src/kmer.cpp:2202)
-    u32 best = 0; int bi = 0;
-    for (int c = 0; c < ct.n; c++) {
-        u32 a = ct.agg[c];
-        u32 score = ((a >> 16) << 10) | (1023u - (a & 0xffffu));
-        if (score > best) { best = score; bi = c; }
-    }
-    const bool homo = homo_pair(ct.key[bi], 0ULL, k);
-    return (u32)T | ((best >> 10) << 10) | ((u32)bi << 20) | (homo ? 1u << 28 : 0u);
-}
-
-struct TScan { int th, tl; u64 sh, sl; bool overflow; };
-
-// k_mer_check without emission for one window, periods kmin..kmax (<= 32): the thread form of scan_stats()
-template <int NW>
-__device__ __noinline__ TScan tw_scan(const TWin<NW>& w, int kmin, int kmax, double low, double high, TClassTab& ct) {
-    TScan res; res.th = res.tl = 0; res.sh = res.sl = 0; res.overflow = false;
-    kmax = min(kmax, w.len);
-    if (kmax < kmin) return res;
-    const double slack = 1.0 - 1e-12;
-    u64 cand = 0;
-    {   // all periods first: which ones can reach LOW at all
-        u32 wv[NW];
-        int T = tw_wv<NW>(w, kmin, wv);
-        for (int k = kmin; k <= kmax && T > 0; k++) {
-            int U = tw_bound<NW>(w, k, wv, T);
-            if ((double)U >= low * (double)T * slack) cand |= 1ULL << k;
-            if (w.all_valid) {
-                T--;
-#pragma unroll
-                for (int j = 0; j < NW; j++) { int vb = T - 32 * j; wv[j] = vb <= 0 ? 0u : low_mask(min(32, vb)); }
-            } else {
-                T = 0;
-#pragma unroll
-                for (int j = 0; j < NW; j++) {
-                    wv[j] &= (wv[j] >> 1) | (j + 1 < NW ? wv[j + 1] << 31 : 0u);
-                    T += __popc(wv[j]);
-                }
-            }
-        }
-    }
-    u64 blockedL = 0, blockedH = 0;   // periods with an accepted divisor (src/kmer.cpp:2225-2230)
-    double needL = low, needH = high; // max(baseline, last accepted frequency)
-    while (cand) {
-        const int k = __ffsll((long long)cand) - 1;
-        cand &= cand - 1;
-        const bool blkL = ((blockedL >> k) & 1ULL) != 0, blkH = ((blockedH >> k) & 1ULL) != 0;
-        if (blkL && blkH) continue;
-        u32 wv[NW];
-        const int T = tw_wv<NW>(w, k, wv);
-        if (T <= 0) continue;
-        const int U = tw_bound<NW>(w, k, wv, T);
-        const double dU = (double)U, dT = (double)T;
-        const bool candL = !blkL && dU >= needL * dT * slack, candH = !blkH && dU >= needH * dT * slack;
-        if (!candL && !candH) continue;
-        // smallest class size either selection could still accept (fl(M/T) >= need implies M >= need * T * slack)
-        const double need_min = candL ? (candH ? fmin(needL, needH) : needL) : needH;
-        const int nc = (int)floor(need_min * dT * slack);
-        if (!tw_strong<NW>(w, k, wv, nc)) continue;
-        const u32 ev = tw_eval<NW>(w, k, wv, T, ct, nc);
-        if (te_overflow(ev)) { res.overflow = true; return res; }
-        if (te_stopped(ev) || te_homo(ev)) continue;
-        const double f = (double)te_M(ev) / (double)te_T(ev);
-        const bool accL = !blkL && f >= needL, accH = !blkH && f >= needH;
-        if (accL || accH) {
-            const u64 mm = c_mult.m[k], S = ct.key[te_best(ev)];
-            if (accL) { res.tl = k; needL = f; blockedL |= mm; res.sl = S; }
-            if (accH) { res.th = k; needH = f; blockedH |= mm; res.sh = S; }
-        }
-    }
-    return res;
-}
-
-// every class of (window, k) into a result table: the emission half of k_mer_check / k_mer_target
-template <int NW>
-__device__ __noinline__ bool tw_emit(TableRef tr, const TWin<NW>& w, int k, int table, bool folded, TClassTab& ct) {
-    u32 wv[NW];
-    const int T = tw_wv<NW>(w, k, wv);
-    const u32 ev = tw_eval<NW>(w, k, wv, T, ct, 0);
-    if (te_overflow(ev)) return false;
-    const u32 meta = ((u32)table << 8) | (u32)k;
-    for (int c = 0; c < ct.n; c++) {
-        u64 lo = ct.key[c], hi = 0;
-        if (folded) {
-            u64 rlo = lo, rhi = 0;
-            crc_pair(rlo, rhi, k);
-            if (rlo < lo) lo = rlo;
-        }
-        table_add_impl(tr.slots, tr.mask, tr.err, meta, lo, hi, (u64)(ct.agg[c] >> 16));
-    }
-    return true;
-}
-
-// buffer_task for one read (src/kmer.cpp:111-171).  Returns false when the read must go to the warp kernel instead
-// (nothing has been emitted in that case): decisions first, emissions after all of them are known.
-__device__ bool route_short_thread(const DevCfg& cfg, TableRef tr, const DevBatch& b, u32 u, TClassTab& ct) {
-    const int MINM = cfg.min_mer, MAXM = cfg.max_mer;
-    const u32 b0 = __ldg(b.bit_off + u);
-    const int n = (int)(__ldg(b.bit_off + u + 1) - b0);
-    if (n < 2 * MINM) return true;
-    if (n > kThreadMaxRead) return false;
-    const u32 rpos = b0 + (u32)(n - (n + 1) / 2);
-    const int llen = n / 2, rlen = (n + 1) / 2;
-    int act_win[4], act_k[4], act_table[4], na = 0;   // win: 0 left half, 1 right half, 2 whole read (un-folded), 3 whole (folded)
-    int L[2] = {0, 0}, R[2] = {0, 0};
-    if (n >= 4 * MINM) {
-        const int kmax = min(n / 4, MAXM);
-        {
-            TWin<3> w;
-            tw_load<3>(w, b, b0, llen);
-            TScan l = tw_scan<3>(w, MINM, kmax, cfg.low, cfg.high, ct);
-            if (l.overflow) return false;
-            L[0] = l.th; L[1] = l.tl;
-        }
-        {
-            TWin<3> w;
-            tw_load<3>(w, b, rpos, rlen);
-            TScan r = tw_scan<3>(w, MINM, kmax, cfg.low, cfg.high, ct);  // always evaluated
-            if (r.overflow) return false;
-            R[0] = r.th; R[1] = r.tl;
-        }
-        bool need_whole = (L[0] > 0 && L[0] == R[0]) || (L[1] > 0 && L[1] == R[1]);
-        TWin<5> ww;
-        if (need_whole) tw_load<5>(ww, b, b0, n);
-#pragma unroll
-        for (int c = 0; c < 2; c++) {
-            if (L[c] > 0 && L[c] == R[c]) {   // k_mer_target on the whole read (src/kmer.cpp:129, 142)
-                u32 wv[5];
-                const int T = tw_wv<5>(ww, L[c], wv);
-                const u32 ev = tw_eval<5>(ww, L[c], wv, T, ct, 0);
-                if (te_overflow(ev)) return false;
-                if (te_T(ev) > 0 && !te_homo(ev) && (double)te_M(ev) / (double)te_T(ev) >= (c == 0 ? cfg.high : cfg.low)) {
-                    act_win[na] = 3; act_k[na] = L[c]; act_table[na] = T_O + c; na++;
-                }
-            } else if (L[c] > 0) { act_win[na] = 0; act_k[na] = L[c]; act_table[na] = T_F + c; na++; }
-            else if (R[c] > 0) { act_win[na] = 1; act_k[na] = R[c]; act_table[na] = T_B + c; na++; }
-        }
-    }
-    const bool hc0 = L[0] == 0 && R[0] == 0, hc1 = L[1] == 0 && R[1] == 0;
-    if (4 * MAXM > n && (hc0 || hc1)) {
-        TWin<5> ww;
-        tw_load<5>(ww, b, b0, n);
-        TScan s = tw_scan<5>(ww, max(n / 4 + 1, MINM), min(n / 2, MAXM), cfg.low, cfg.high, ct);
-        if (s.overflow) return false;
-        if (hc0 && s.th) { act_win[na] = 2; act_k[na] = s.th; act_table[na] = T_O + 0; na++; }  // un-folded into 'both'
-        if (hc1 && s.tl) { act_win[na] = 2; act_k[na] = s.tl; act_table[na] = T_O + 1; na++; }
-    }
-    // emissions (every (window, k) below was evaluated completely above, so the class table cannot overflow now)
-    for (int i = 0; i < na; i++) {
-        bool ok;
-        if (act_win[i] >= 2) {
-            TWin<5> ww;
-            tw_load<5>(ww, b, b0, n);
-            ok = tw_emit<5>(tr, ww, act_k[i], act_table[i], act_win[i] == 3, ct);
-        } else {
-            TWin<3> w;
-            tw_load<3>(w, b, act_win[i] == 0 ? b0 : rpos, act_win[i] == 0 ? llen : rlen);
-            ok = tw_emit<3>(tr, w, act_k[i], act_table[i], false, ct);
-        }
-        if (!ok) atomicExch(tr.err, 4u);
-    }
-    return true;
-}
-
-#ifndef TREW_THREAD_BPS
-#define TREW_THREAD_BPS 8
-#endif
-__global__ void __launch_bounds__(128, TREW_THREAD_BPS) trew_exact_thread_kernel(DevCfg cfg, DevBatch b, const u32* __restrict__ survivors,
-                                                                const u32* __restrict__ n_survivors, u32* __restrict__ overflow,
-                                                                u32* __restrict__ n_overflow, u64* total_survivors) {
-    const u32 n = *n_survivors;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && total_survivors) atomicAdd(total_survivors, (u64)n);
-    TableRef tr{cfg.slots, cfg.slot_mask, cfg.error_flag};
-    TClassTab ct;
-    const u32 stride = gridDim.x * blockDim.x;
-    const u32 n_round = (n + 31u) & ~31u;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        bool to_warp = false;
-        u32 u = 0;
-        if (i < n) {
-            u = survivors[i];
-            to_warp = !route_short_thread(cfg, tr, b, u, ct);
-        }
-        list_append(to_warp, u, overflow, n_overflow);
-    }
-}
-
-void launch_exact_thread(const DevCfg& cfg, const DevBatch& b, const unsigned int* survivors, const unsigned int* n_survivors,
-                         unsigned int* overflow, unsigned int* n_overflow, unsigned long long* total_survivors, int blocks,
-                         cudaStream_t stream) {
-    trew_exact_thread_kernel<<<blocks, 128, 0, stream>>>(cfg, b, survivors, n_survivors, overflow, n_overflow, total_survivors);
-}
-
 template <int MODE>
 __global__ void __launch_bounds__(kExactWarps * 32, TREW_EXACT_BPS) trew_exact_kernel(DevCfg cfg, DevBatch b, ExactArgs a) {
     const int wid = threadIdx.x >> 5;
@@ -1908,7 +1457,7 @@ cudaError_t prepare_exact(int run_cap_max) {
     return e;
 }
 
-LaunchPlan default_launch_plan(int sm_count) { return LaunchPlan{sm_count * TREW_SCREEN_BPS, sm_count * 8, sm_count * kExactBlocksPerSM, sm_count * TREW_THREAD_BPS}; }
+LaunchPlan default_launch_plan(int sm_count) { return LaunchPlan{sm_count * TREW_SCREEN_BPS, sm_count * 8, sm_count * kExactBlocksPerSM}; }
 
 void launch_exact(const DevCfg& cfg, const DevBatch& b, const ExactArgs& a, const LaunchPlan& plan, cudaStream_t stream) {
     size_t smem = exact_smem_bytes(a.run_cap, true);

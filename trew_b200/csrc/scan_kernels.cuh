@@ -59,7 +59,7 @@ struct ExactArgs {
 };
 
 // grid sizes (total blocks) of the three scan kernels; all three are grid-stride / work-counter kernels
-struct LaunchPlan { int screen_blocks, decide_blocks, exact_blocks, exact_thread_blocks; };
+struct LaunchPlan { int screen_blocks, decide_blocks, exact_blocks; };
 LaunchPlan default_launch_plan(int sm_count);
 
 // host-side launchers (scan_kernels.cu)
@@ -71,10 +71,6 @@ size_t exact_smem_bytes(int run_cap, bool wide);
 cudaError_t prepare_exact(int run_cap_max);
 void launch_exact(const DevCfg& cfg, const DevBatch& b, const ExactArgs& a, const LaunchPlan& plan, cudaStream_t stream);
 int exact_warps_total(int sm_count);
-// thread-per-survivor exact kernel (short single-end reads, MAX_MER <= 32); survivors it cannot finish go to `overflow`
-void launch_exact_thread(const DevCfg& cfg, const DevBatch& b, const unsigned int* survivors, const unsigned int* n_survivors,
-                         unsigned int* overflow, unsigned int* n_overflow, unsigned long long* total_survivors, int blocks,
-                         cudaStream_t stream);
 // table_kernels.cu
 void launch_compact(const Slot* slots, unsigned int n_slots, trew_entry* out, unsigned int* d_n, cudaStream_t stream, unsigned int cap);
 // in-place sort by (table, k, seq); call with d_temp == nullptr to query *temp_bytes
