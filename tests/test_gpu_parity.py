@@ -171,3 +171,36 @@ def test_device_row_merge():
         c1.merge_rows(rows.data_ptr(), n)
         merged = c1.finish()
     assert merged == whole, diff_msg(merged, whole)
+
+
+def test_pair_and_long_batching_independence():
+    """Order / batch-split independence and linearity for the paired and the long-read routing (size-independent
+    properties; the oracle comparison of the same generators is in test_pair_vs_oracle / test_long_vs_oracle)."""
+    r1, r2 = synth.adversarial_pairs(77, 1500, read_len=150, max_unit=32, truncate_mate2=0.0)
+    a = run_gpu(api.MODE_PAIR, 5, 32, 0.5, 0.8, 150, r1, r2)
+    b = run_gpu(api.MODE_PAIR, 5, 32, 0.5, 0.8, 150, r1[::-1], r2[::-1], staging_bytes=1 << 16, n_staging=2)
+    assert a == b and len(a) > 20
+    with api.DeviceContext(api.MODE_PAIR, 5, 32) as ctx:
+        ctx.submit_reads(r1[:400], r2[:400])
+        ctx.submit_reads(r1[400:], r2[400:])
+        ctx.submit_reads(r1, r2)
+        c = ctx.finish()
+    assert c == {k: 2 * v for k, v in a.items()}
+    reads = synth.adversarial_long(78, 160, min_len=150, max_len=3000, max_unit=32)
+    d = run_gpu(api.MODE_LONG, 5, 32, 0.5, 0.8, 150, reads)
+    e = run_gpu(api.MODE_LONG, 5, 32, 0.5, 0.8, 150, reads[::-1], staging_bytes=1 << 16, n_staging=2)
+    assert d == e and len(d) > 20
+
+
+def test_long_windows_through_the_screen():
+    """300-base reads (half windows of 150 bases) and MAX_MER 64 on 150-base reads (whole-read probe of 150 bases)
+    take the 4-word first level of the screen kernel; results still equal the oracle's."""
+    from oracle.oracle import Oracle
+    reads = synth.adversarial_short(91, 900, max_unit=32, lengths=[246, 260, 300, 300, 318, 150])
+    got = run_gpu(api.MODE_SHORT, 5, 32, 0.5, 0.8, 150, reads)
+    want = Oracle(5, 32).scan(0, reads)
+    assert got == want, diff_msg(got, want)
+    reads = synth.adversarial_short(92, 900, max_unit=64, lengths=[150, 150, 140, 159, 128])
+    got = run_gpu(api.MODE_SHORT, 5, 64, 0.5, 0.8, 150, reads)
+    want = Oracle(5, 64).scan(0, reads)
+    assert got == want, diff_msg(got, want)

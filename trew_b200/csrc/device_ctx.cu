@@ -80,6 +80,7 @@ struct trew_ctx {
     Pool* pool = nullptr;
     std::string err;
     std::vector<RangeInfo> ranges_tmp;
+    IngestScratch ingest;   // file block buffers, kept across files
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     double screen_ms = 0, decide_ms = 0, exact_ms = 0; uint64_t n_prof_scans = 0;
     std::vector<trew_resident*> pending_prof;
@@ -767,11 +768,14 @@ int trew_synth_resident(trew_ctx* ctx, uint64_t seed, uint32_t n_reads, uint32_t
 int trew_dev_process_file(trew_ctx* ctx, const char* file1, int is_gz1, const char* file2, int is_gz2) {
     if (!ctx || !file1) return TREW_ERR_ARG;
     if ((ctx->cfg.mode == TREW_MODE_PAIR) != (file2 != nullptr)) return fail(ctx, TREW_ERR_ARG, "second file only in pair mode");
-    IngestResult r = ingest_file(ctx->cfg.mode, ctx->cfg.slice_length, file1, is_gz1 != 0, file2, is_gz2 != 0, (size_t)32 << 20,
+    // plain files: large blocks read and indexed by the pool; .gz: the inflate stream is sequential, keep blocks small
+    const size_t chunk = (is_gz1 || is_gz2) ? ((size_t)32 << 20) : ((size_t)256 << 20);
+    IngestResult r = ingest_file(ctx->cfg.mode, ctx->cfg.slice_length, file1, is_gz1 != 0, file2, is_gz2 != 0, chunk,
                                  [&](const char* b1, const std::vector<int32_t>& l1, const char* b2, const std::vector<int32_t>& l2) {
                                      return trew_dev_submit_chunk(ctx, b1, l1.data(), (uint32_t)(l1.size() / 2), b2,
                                                                   b2 ? l2.data() : nullptr, b2 ? (uint32_t)(l2.size() / 2) : 0u);
-                                 });
+                                 },
+                                 ctx->pool, &ctx->ingest);
     if (r.status != TREW_OK && r.status != TREW_ERR_CUDA && !r.message.empty()) ctx->err = r.message;
     return r.status;
 }

@@ -113,11 +113,24 @@ private:
     int next_, n_tasks_, pending_;
 };
 
+// Growable byte buffer for file blocks: 2 MiB aligned and advised to use huge pages, never zero-filled, and kept
+// across files by the owner (first-touch page faults on a fresh 256 MiB block cost more than reading it).
+struct GrowBuf {
+    char* data = nullptr;
+    size_t cap = 0;
+    void reserve(size_t n, size_t keep);   // at least n bytes; the first `keep` bytes survive a reallocation
+    ~GrowBuf();
+    GrowBuf() = default;
+    GrowBuf(const GrowBuf&) = delete;
+    GrowBuf& operator=(const GrowBuf&) = delete;
+};
+struct IngestScratch { GrowBuf a, b; };
+
 // ingest.cpp: FASTQ / FASTQ.gz record reader with the reference's record semantics
 struct IngestResult { int status; std::string message; };
 typedef std::function<int(const char* buf1, const std::vector<int32_t>& locs1, const char* buf2,
                           const std::vector<int32_t>& locs2)> ChunkSink;
 IngestResult ingest_file(int mode, int slice_length, const char* file1, bool gz1, const char* file2, bool gz2,
-                         size_t chunk_bytes, const ChunkSink& sink);
+                         size_t chunk_bytes, const ChunkSink& sink, Pool* pool = nullptr, IngestScratch* scratch = nullptr);
 
 }  // namespace trew

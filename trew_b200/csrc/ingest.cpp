@@ -11,47 +11,97 @@
 #include "host_internal.h"
 
 #include <cerrno>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 namespace trew {
+
+void GrowBuf::reserve(size_t n, size_t keep) {
+    if (n <= cap) return;
+    size_t want = (n + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+    char* p = (char*)aligned_alloc((size_t)2 << 20, want);
+    if (!p) throw std::bad_alloc();
+#ifdef MADV_HUGEPAGE
+    madvise(p, want, MADV_HUGEPAGE);
+#endif
+    if (data && keep) memcpy(p, data, keep);
+    free(data);
+    data = p; cap = want;
+}
+
+GrowBuf::~GrowBuf() { free(data); }
 
 namespace {
 
 struct Reader {
     bool gz = false;
-    FILE* fp = nullptr;
+    int fd = -1;
     gzFile gfp = nullptr;
+    uint64_t offset = 0;    // plain files: next byte to read
+    int64_t size = -1;      // plain regular files: total size, else -1
     bool open(const char* name, bool is_gz) {
         gz = is_gz;
         if (gz) { gfp = gzopen(name, "r"); if (gfp) gzbuffer(gfp, 1 << 20); return gfp != nullptr; }
-        fp = fopen(name, "r");
-        return fp != nullptr;
+        fd = ::open(name, O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) size = (int64_t)st.st_size;
+        return true;
     }
-    // returns bytes read (0 at EOF), -1 on error
-    long read(char* buf, size_t n) {
+    // returns bytes read (0 at EOF), -1 on error.  Plain regular files are read with pread in parallel slices when a
+    // pool is given and the request is large (the copy out of the page cache is the cost, and it scales with cores).
+    long read(char* buf, size_t n, Pool* pool, size_t par_min) {
         if (gz) {
             int r = gzread(gfp, buf, (unsigned)std::min<size_t>(n, 1u << 30));
             return r < 0 ? -1 : r;
         }
-        size_t r = fread(buf, 1, n, fp);
-        if (r == 0 && ferror(fp)) return -1;
-        return (long)r;
+        if (size >= 0) {
+            size_t want = (size_t)std::min<uint64_t>(n, (uint64_t)size > offset ? (uint64_t)size - offset : 0);
+            if (want == 0) return 0;
+            const int P = pool && want >= par_min ? std::min(pool->size(), (int)(want / (par_min / 4 + 1)) + 1) : 1;
+            std::vector<long> got((size_t)P, 0);
+            auto slice = [&](int i) {
+                size_t a = want * (size_t)i / (size_t)P, b = want * (size_t)(i + 1) / (size_t)P;
+                while (a < b) {
+                    ssize_t r = pread(fd, buf + a, b - a, (off_t)(offset + a));
+                    if (r < 0) { if (errno == EINTR) continue; got[(size_t)i] = -1; return; }
+                    if (r == 0) break;
+                    a += (size_t)r; got[(size_t)i] += (long)r;
+                }
+            };
+            if (P > 1) pool->run(P, slice); else slice(0);
+            long total = 0;
+            for (long g : got) { if (g < 0) return -1; total += g; }
+            offset += (uint64_t)total;
+            return total;
+        }
+        for (;;) {
+            ssize_t r = ::read(fd, buf, n);
+            if (r < 0 && errno == EINTR) continue;
+            return r < 0 ? -1 : (long)r;
+        }
     }
     std::string error() {
         if (gz) { int e; return gzerror(gfp, &e); }
         return strerror(errno);
     }
-    void close() { if (gz) { if (gfp) gzclose(gfp); gfp = nullptr; } else { if (fp) fclose(fp); fp = nullptr; } }
+    void close() { if (gz) { if (gfp) gzclose(gfp); gfp = nullptr; } else { if (fd >= 0) ::close(fd); fd = -1; } }
     ~Reader() { close(); }
 };
 
 // One side of the ingest: a buffer holding [carried bytes | fresh bytes] and the line phase.
 struct Side {
     Reader rd;
-    std::vector<char> buf;
+    GrowBuf own;
+    GrowBuf* buf = &own;   // the caller's scratch buffer when it provides one
     size_t have = 0;        // bytes in buf
     size_t scanned = 0;     // bytes already examined for newlines
     size_t line_start = 0;  // start of the line being assembled
@@ -61,37 +111,92 @@ struct Side {
     std::vector<int32_t> locs;  // sequence lines found in buf, inclusive (st, nd)
 
     // read more bytes; returns false on I/O error
-    bool fill(size_t chunk) {
-        if (buf.size() < have + chunk) buf.resize(have + chunk);
-        long r = rd.read(buf.data() + have, chunk);
+    bool fill(size_t chunk, Pool* pool, size_t par_min) {
+        buf->reserve(have + chunk, have);
+        long r = rd.read(buf->data + have, chunk, pool, par_min);
         if (r < 0) return false;
         if (r == 0) eof = true;
         have += (size_t)r;
         return true;
     }
-    // examine fresh bytes; mode 0: too_long set when a short read exceeds 1000; mode 2: drop < slice
-    void scan(int mode, int slice, bool* too_long) {
-        const char* p = buf.data();
+    inline void line_done(size_t st, size_t nl, int mode, int slice, bool* too_long, std::vector<int32_t>& out) {
+        size_t len = nl - st;
+        if (mode == TREW_MODE_SHORT && len > 1000) *too_long = true;
+        if (!(mode == TREW_MODE_LONG && len < (size_t)slice)) {
+            out.push_back((int32_t)st);
+            out.push_back((int32_t)nl - 1);
+        }
+    }
+    // examine fresh bytes; mode 0: too_long set when a short read exceeds 1000; mode 2: drop < slice.
+    // With a pool and enough fresh bytes the newline search runs in parallel slices: a line's role depends only on the
+    // ordinal of the newline that ends it, so the slices need nothing from each other but their newline counts.
+    void scan(int mode, int slice, bool* too_long, Pool* pool, size_t par_min) {
+        const char* p = buf->data;
+        if (pool && pool->size() > 1 && have - scanned >= par_min) {
+            const size_t begin = scanned, end = have;
+            const int P = std::min(pool->size() * 2, (int)((end - begin) / (par_min / 8 + 1)) + 1);
+            std::vector<std::vector<uint32_t>> nl((size_t)P);
+            pool->run(P, [&](int i) {
+                size_t a = begin + (end - begin) * (size_t)i / (size_t)P, b = begin + (end - begin) * (size_t)(i + 1) / (size_t)P;
+                auto& v = nl[(size_t)i];
+                v.reserve((b - a) / 64 + 16);
+                while (a < b) {
+                    const char* q = (const char*)memchr(p + a, '\n', b - a);
+                    if (!q) break;
+                    v.push_back((uint32_t)(q - p));
+                    a = (size_t)(q - p) + 1;
+                }
+            });
+            std::vector<uint64_t> base((size_t)P + 1);
+            std::vector<int64_t> prev((size_t)P);
+            base[0] = num;
+            int64_t last = (int64_t)line_start - 1;
+            for (int i = 0; i < P; i++) {
+                base[(size_t)i + 1] = base[(size_t)i] + nl[(size_t)i].size();
+                prev[(size_t)i] = last;
+                if (!nl[(size_t)i].empty()) last = (int64_t)nl[(size_t)i].back();
+            }
+            std::vector<std::vector<int32_t>> out((size_t)P);
+            std::vector<char> tl((size_t)P, 0);
+            pool->run(P, [&](int i) {
+                int64_t pv = prev[(size_t)i];
+                uint64_t g = base[(size_t)i];
+                bool t = false;
+                auto& o = out[(size_t)i];
+                o.reserve(nl[(size_t)i].size() / 2 + 8);
+                for (uint32_t pos : nl[(size_t)i]) {
+                    g++;
+                    if ((g & 3) == 2) line_done((size_t)(pv + 1), pos, mode, slice, &t, o);
+                    pv = (int64_t)pos;
+                }
+                tl[(size_t)i] = t ? 1 : 0;
+            });
+            size_t add = 0;
+            for (auto& o : out) add += o.size();
+            locs.reserve(locs.size() + add);
+            for (int i = 0; i < P; i++) {
+                locs.insert(locs.end(), out[(size_t)i].begin(), out[(size_t)i].end());
+                if (tl[(size_t)i]) *too_long = true;
+            }
+            total_lines += base[(size_t)P] - num;
+            num = base[(size_t)P];
+            line_start = (size_t)(last + 1);
+            scanned = have;
+            return;
+        }
         while (scanned < have) {
             const char* nl = (const char*)memchr(p + scanned, '\n', have - scanned);
             if (!nl) { scanned = have; break; }
             size_t i = (size_t)(nl - p);
             num++; total_lines++;
-            if ((num & 3) == 2) {
-                size_t len = i - line_start;
-                if (mode == TREW_MODE_SHORT && len > 1000) *too_long = true;
-                if (!(mode == TREW_MODE_LONG && len < (size_t)slice)) {
-                    locs.push_back((int32_t)line_start);
-                    locs.push_back((int32_t)i - 1);
-                }
-            }
+            if ((num & 3) == 2) line_done(line_start, i, mode, slice, too_long, locs);
             line_start = i + 1;
             scanned = i + 1;
         }
     }
     // drop everything before `from` (a line start); the line phase is kept
     void compact(size_t from) {
-        memmove(buf.data(), buf.data() + from, have - from);
+        memmove(buf->data, buf->data + from, have - from);
         have -= from; scanned -= from; line_start -= from;
         locs.clear();
     }
@@ -100,34 +205,45 @@ struct Side {
 }  // namespace
 
 IngestResult ingest_file(int mode, int slice_length, const char* file1, bool gz1, const char* file2, bool gz2,
-                         size_t chunk_bytes, const ChunkSink& sink) {
+                         size_t chunk_bytes, const ChunkSink& sink, Pool* pool, IngestScratch* scratch) {
     IngestResult res{TREW_OK, ""};
     static const std::vector<int32_t> kEmpty;
     if (chunk_bytes > ((size_t)1 << 30)) chunk_bytes = (size_t)1 << 30;  // offsets are int32 like the reference's
+    // fresh bytes from which reading / newline indexing go parallel (TREW_INGEST_PAR_MIN: tests force the path)
+    size_t par_min = (size_t)4 << 20;
+    if (const char* e = getenv("TREW_INGEST_PAR_MIN")) par_min = (size_t)std::max(1L, atol(e));
     Side a, b;
+    if (scratch) { a.buf = &scratch->a; b.buf = &scratch->b; }
     if (!a.rd.open(file1, gz1)) return IngestResult{TREW_ERR_IO, "File open failed"};
     const bool pair = mode == TREW_MODE_PAIR;
     if (pair && !b.rd.open(file2, gz2)) return IngestResult{TREW_ERR_IO, "File open failed"};
     bool too_long = false;
+    const bool trace = getenv("TREW_INGEST_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     if (!pair) {
         for (;;) {
-            if (!a.fill(chunk_bytes)) return IngestResult{TREW_ERR_IO, "File-IO Error: " + a.rd.error() + "."};
-            a.scan(mode, slice_length, &too_long);
+            double t0 = trace ? now() : 0;
+            if (!a.fill(chunk_bytes, pool, par_min)) return IngestResult{TREW_ERR_IO, "File-IO Error: " + a.rd.error() + "."};
+            double t1 = trace ? now() : 0;
+            a.scan(mode, slice_length, &too_long, pool, par_min);
+            double t2 = trace ? now() : 0;
             if (too_long) return IngestResult{TREW_ERR_TOO_LONG, trew_status_string(TREW_ERR_TOO_LONG)};
             if (!a.locs.empty()) {
-                int rc = sink(a.buf.data(), a.locs, nullptr, kEmpty);
+                int rc = sink(a.buf->data, a.locs, nullptr, kEmpty);
                 if (rc) return IngestResult{rc, ""};
             }
+            if (trace) fprintf(stderr, "[ingest] block %zu bytes: read %.1f ms, index %.1f ms, sink %.1f ms (%zu reads)\n", a.have, t1 - t0,
+                               t2 - t1, now() - t2, a.locs.size() / 2);
             if (a.eof) break;
             a.compact(a.line_start);
         }
         return res;
     }
     for (;;) {
-        if (!a.eof && !a.fill(chunk_bytes)) return IngestResult{TREW_ERR_IO, "File 1 IO Error: " + a.rd.error() + "."};
-        if (!b.eof && !b.fill(chunk_bytes)) return IngestResult{TREW_ERR_IO, "File 2 IO Error: " + b.rd.error() + "."};
-        a.scan(mode, slice_length, &too_long);
-        b.scan(mode, slice_length, &too_long);
+        if (!a.eof && !a.fill(chunk_bytes, pool, par_min)) return IngestResult{TREW_ERR_IO, "File 1 IO Error: " + a.rd.error() + "."};
+        if (!b.eof && !b.fill(chunk_bytes, pool, par_min)) return IngestResult{TREW_ERR_IO, "File 2 IO Error: " + b.rd.error() + "."};
+        a.scan(mode, slice_length, &too_long, pool, par_min);
+        b.scan(mode, slice_length, &too_long, pool, par_min);
         const bool done = a.eof && b.eof;
         if (done && a.total_lines != b.total_lines) {
             char msg[160];
@@ -138,7 +254,7 @@ IngestResult ingest_file(int mode, int slice_length, const char* file1, bool gz1
         size_t n = std::min(a.locs.size(), b.locs.size()) / 2;
         if (n) {
             std::vector<int32_t> la(a.locs.begin(), a.locs.begin() + 2 * n), lb(b.locs.begin(), b.locs.begin() + 2 * n);
-            int rc = sink(a.buf.data(), la, b.buf.data(), lb);
+            int rc = sink(a.buf->data, la, b.buf->data, lb);
             if (rc) return IngestResult{rc, ""};
         }
         if (done) break;
@@ -147,7 +263,7 @@ IngestResult ingest_file(int mode, int slice_length, const char* file1, bool gz1
             if (s->locs.size() / 2 > n) {
                 size_t from = (size_t)s->locs[2 * n];
                 uint64_t dropped = 0;  // newlines between `from` and the scan position are re-counted
-                for (size_t i = from; i < s->scanned; i++) dropped += s->buf[i] == '\n';
+                for (size_t i = from; i < s->scanned; i++) dropped += s->buf->data[i] == '\n';
                 s->num -= dropped; s->total_lines -= dropped;
                 s->scanned = from; s->line_start = from;
                 s->compact(from);
@@ -164,11 +280,13 @@ IngestResult ingest_file(int mode, int slice_length, const char* file1, bool gz1
 extern "C" int trew_ingest_file(int mode, int slice_length, const char* file1, int is_gz1, const char* file2, int is_gz2,
                                 uint64_t chunk_bytes, trew_chunk_sink sink, void* user, char* message, size_t message_cap) {
     if (!file1 || !sink || mode < 0 || mode > 2 || (mode == TREW_MODE_PAIR) != (file2 != nullptr)) return TREW_ERR_ARG;
+    trew::Pool pool(4);
     trew::IngestResult r = trew::ingest_file(
         mode, slice_length, file1, is_gz1 != 0, file2, is_gz2 != 0, chunk_bytes ? (size_t)chunk_bytes : ((size_t)32 << 20),
         [&](const char* b1, const std::vector<int32_t>& l1, const char* b2, const std::vector<int32_t>& l2) {
             return sink(user, b1, l1.data(), (uint32_t)(l1.size() / 2), b2, b2 ? l2.data() : nullptr, b2 ? (uint32_t)(l2.size() / 2) : 0u);
-        });
+        },
+        &pool);
     if (message && message_cap) { snprintf(message, message_cap, "%s", r.message.c_str()); }
     return r.status;
 }
