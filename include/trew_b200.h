@@ -31,7 +31,7 @@ extern "C" {
 #define TREW_OK 0
 #define TREW_ERR_ARG 1        /* bad argument / configuration                                   */
 #define TREW_ERR_CUDA 2       /* CUDA runtime failure or no usable device                        */
-#define TREW_ERR_TABLE_FULL 3 /* device count table overflowed (raise table_log2_slots)          */
+#define TREW_ERR_TABLE_FULL 3 /* device count table overflowed within one batch (raise table_log2_slots) */
 #define TREW_ERR_TOO_LONG 4   /* short mode: read longer than MAX_SEQ=1000 (src/kmer.cpp:1006)   */
 #define TREW_ERR_IO 5         /* file open / read failure (src/kmer.cpp:1021, 1288)              */
 #define TREW_ERR_PAIRING 6    /* paired files disagree (src/kmer.cpp:1111-1123)                  */
@@ -59,7 +59,8 @@ typedef struct trew_config {
     double low_baseline;      /* LOW_BASELINE  (-L, default 0.5)                                   */
     double high_baseline;     /* HIGH_BASELINE (-H, default 0.8)                                   */
     int32_t device;           /* CUDA device ordinal                                               */
-    int32_t table_log2_slots; /* device count-table capacity, 0 = default (2^22 slots)             */
+    int32_t table_log2_slots; /* initial device count-table capacity, 0 = default (2^22 slots); the
+                                 streaming path grows it when it passes a quarter full          */
     int32_t n_staging;        /* pinned staging buffers (double buffering = 2), 0 = default (3)    */
     int32_t host_threads;     /* host packing threads, 0 = all cores (capped at 32)                 */
     uint64_t staging_bytes;   /* bytes per staging buffer, 0 = default (64 MiB)                    */

@@ -204,3 +204,14 @@ def test_long_windows_through_the_screen():
     got = run_gpu(api.MODE_SHORT, 5, 64, 0.5, 0.8, 150, reads)
     want = Oracle(5, 64).scan(0, reads)
     assert got == want, diff_msg(got, want)
+
+
+def test_count_table_grows_while_streaming():
+    """A deliberately small count table (2^12 slots) must grow transparently in the streaming path."""
+    reads = synth.adversarial_short(14, 6000)
+    want = run_gpu(api.MODE_SHORT, 5, 32, 0.5, 0.8, 150, reads)
+    assert len(want) > 4096
+    with api.DeviceContext(api.MODE_SHORT, 5, 32, table_log2_slots=12, staging_bytes=1 << 14, n_staging=2) as ctx:
+        ctx.submit_reads(reads)
+        got = ctx.finish()
+    assert got == want, diff_msg(got, want)

@@ -168,6 +168,37 @@ int retire_slot(trew_ctx* ctx, SlotRes& s) {
 }
 
 // Pack ranges [g0, g1) of a chunk (host threads) into the next free staging slot and launch copy + kernels on its stream.
+int export_sorted(trew_ctx* ctx, uint64_t* n_out);
+int check_device_error(trew_ctx* ctx);
+
+// The streaming path keeps the count table at most a quarter full between batches: when the number of distinct keys
+// passes that, all in-flight batches are drained and the entries are re-inserted into a larger table (load <= 1/8).
+// The check runs once per batch, so a single batch that inserts more new keys than three quarters of the table can
+// still overflow it (TREW_ERR_TABLE_FULL: start with a larger table_log2_slots).
+int maybe_grow_table(trew_ctx* ctx) {
+    unsigned int keys = 0;
+    CK(cudaMemcpy(&keys, ctx->d_error + 1, sizeof(keys), cudaMemcpyDeviceToHost));
+    if ((size_t)keys * 4 <= ctx->n_slots || ctx->n_slots >= ((size_t)1 << 28)) return TREW_OK;
+    uint64_t n = 0;
+    int rc = export_sorted(ctx, &n);   // drains every stream, compacts into ctx->d_entries
+    if (rc) return rc;
+    size_t new_slots = ctx->n_slots;
+    while (new_slots < ((size_t)1 << 28) && (size_t)n * 8 > new_slots) new_slots <<= 1;
+    if (new_slots == ctx->n_slots) return TREW_OK;
+    Slot* d_new = nullptr;
+    CK(cudaMalloc((void**)&d_new, new_slots * sizeof(Slot)));
+    CK(cudaMemsetAsync(d_new, 0, new_slots * sizeof(Slot), ctx->main_stream));
+    CK(cudaMemsetAsync(ctx->d_error + 1, 0, sizeof(unsigned int), ctx->main_stream));
+    Slot* d_old = ctx->dcfg.slots;
+    ctx->dcfg.slots = d_new; ctx->dcfg.slot_mask = (unsigned int)(new_slots - 1); ctx->n_slots = new_slots;
+    launch_merge_entries(ctx->dcfg, ctx->d_entries, (unsigned int)n, ctx->main_stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->main_stream));
+    CK(cudaFree(d_old));
+    ctx->stats.kernel_launches += 1;
+    return check_device_error(ctx);
+}
+
 int submit_ranges(trew_ctx* ctx, const ChunkView& cv, const RangeInfo* rg, int n_ranges) {
     uint64_t total_bases = 0; uint32_t max_len = 0;
     for (int i = 0; i < n_ranges; i++) { total_bases += rg[i].bases; max_len = std::max(max_len, rg[i].max_len); }
@@ -177,6 +208,7 @@ int submit_ranges(trew_ctx* ctx, const ChunkView& cv, const RangeInfo* rg, int n
     ctx->next_slot = (ctx->next_slot + 1) % ctx->slots.size();
     int rc = retire_slot(ctx, s);
     if (rc) return rc;
+    if ((rc = maybe_grow_table(ctx)) != TREW_OK) return rc;
     BatchView v;
     batch_layout(s.h_buf, n, total_bases, &v);
     std::vector<uint64_t> bit0((size_t)n_ranges);
@@ -387,8 +419,8 @@ int trew_dev_create(const trew_config* cfg, trew_ctx** out) {
     Slot* d_slots = nullptr;
     CKC(cudaMalloc((void**)&d_slots, ctx->n_slots * sizeof(Slot)));
     CKC(cudaMemset(d_slots, 0, ctx->n_slots * sizeof(Slot)));
-    CKC(cudaMalloc((void**)&ctx->d_error, sizeof(unsigned int)));
-    CKC(cudaMemset(ctx->d_error, 0, sizeof(unsigned int)));
+    CKC(cudaMalloc((void**)&ctx->d_error, 2 * sizeof(unsigned int)));
+    CKC(cudaMemset(ctx->d_error, 0, 2 * sizeof(unsigned int)));
     CKC(cudaMalloc((void**)&ctx->d_total_surv, sizeof(unsigned long long)));
     CKC(cudaMemset(ctx->d_total_surv, 0, sizeof(unsigned long long)));
     std::vector<unsigned short> thr;
@@ -632,6 +664,14 @@ int trew_dev_export_device(trew_ctx* ctx, const trew_entry** d_entries, uint64_t
     return TREW_OK;
 }
 
+}  // extern "C"
+
+namespace {
+int export_sorted(trew_ctx* ctx, uint64_t* n_out) { return trew_dev_export_device(ctx, nullptr, n_out); }
+}  // namespace
+
+extern "C" {
+
 int trew_dev_finish(trew_ctx* ctx, const trew_entry** entries, uint64_t* n_entries) {
     if (!ctx) return TREW_ERR_ARG;
     uint64_t n = 0;
@@ -686,7 +726,7 @@ int trew_dev_reset(trew_ctx* ctx) {
     if (rc && rc != TREW_ERR_TABLE_FULL) return rc;
     // on the scan stream (the context's streams do not synchronise with the legacy default stream)
     CK(cudaMemsetAsync(ctx->dcfg.slots, 0, ctx->n_slots * sizeof(Slot), ctx->main_stream));
-    CK(cudaMemsetAsync(ctx->d_error, 0, sizeof(unsigned int), ctx->main_stream));
+    CK(cudaMemsetAsync(ctx->d_error, 0, 2 * sizeof(unsigned int), ctx->main_stream));
     CK(cudaStreamSynchronize(ctx->main_stream));
     return TREW_OK;
 }

@@ -80,6 +80,7 @@ __device__ __noinline__ void table_add_impl(Slot* slots, u32 slot_mask, u32* err
             __threadfence();
             atomicExch(&s->state, 2u);
             atomicAdd(&s->count, cnt);
+            atomicAdd(error_flag + 1, 1u);  // distinct keys so far: the host grows the table before it fills up
             return;
         }
         while (st == 1u) st = *(volatile u32*)&s->state;

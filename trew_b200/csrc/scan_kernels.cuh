@@ -36,7 +36,7 @@ struct DevCfg {
     double low, high;
     Slot* slots;
     unsigned int slot_mask;
-    unsigned int* error_flag;        // set to TREW_ERR_TABLE_FULL on overflow
+    unsigned int* error_flag;        // [0] set to TREW_ERR_TABLE_FULL on overflow, [1] number of distinct keys inserted
     const unsigned short* thr_low;   // kThrTableSize entries: min M with (double)M/(double)T >= low; 0xFFFF for T = 0
 };
 
