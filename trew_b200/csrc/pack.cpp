@@ -83,9 +83,10 @@ struct BitWriter {
     bool peeling() const { return unit == first_unit; }
     // the bits carried past the last completed unit
     void finish() {
-        if (fill == 0) return;
-        if (unit == first_unit) { side[0] = ah; side[1] = al; side[2] = av; }
-        else { hi[unit] = ah; lo[unit] = al; val[unit] = av; }
+        if (fill != 0) {
+            if (unit == first_unit) { side[0] = ah; side[1] = al; side[2] = av; }
+            else { hi[unit] = ah; lo[unit] = al; val[unit] = av; }
+        }
     }
 };
 
@@ -199,6 +200,58 @@ TREW_AVX512 __attribute__((always_inline)) inline void pack_read_avx512(BitWrite
     }
 }
 
+// Steady state of the AVX-512 packer for single-buffer chunks, written against register pressure (x86-64 has 16
+// general registers and the generic writer keeps a dozen values alive): one plane pointer that advances plus two
+// constant strides, no first-unit test.  Precondition: the writer has left its first unit.
+TREW_AVX512 void pack_lean_avx512(const char* buf, const int32_t* locs, uint32_t r0, uint32_t r1, uint32_t* off, BitWriter& w_out) {
+    const __m512i lut = _mm512_broadcast_i32x4(_mm_setr_epi8(0, 'a', 0, 'c', 't', 0, 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0));
+    const __m512i case_bit = _mm512_set1_epi8(0x20), b2 = _mm512_set1_epi8(4), b1 = _mm512_set1_epi8(2);
+    long long* ph = (long long*)(w_out.hi + w_out.unit);
+    const ptrdiff_t s1 = w_out.lo - w_out.hi, s2 = w_out.val - w_out.hi;
+    uint64_t ah = w_out.ah, al = w_out.al, av = w_out.av;
+    unsigned fill = (unsigned)w_out.fill;
+    uint32_t pos = (uint32_t)(w_out.unit * 64 + fill);
+    for (uint32_t r = r0; r < r1; r++) {
+        const int32_t st = locs[2 * (size_t)r], nd = locs[2 * (size_t)r + 1];
+        const uint32_t len = nd >= st ? (uint32_t)(nd - st + 1) : 0u;
+        const unsigned char* s = (const unsigned char*)buf + st;
+        *off++ = pos;
+        pos += len;
+        uint32_t i = 0;
+        for (; i + 64 <= len; i += 64) {
+            const __m512i x = _mm512_loadu_si512((const void*)(s + i));
+            const uint64_t x1 = _mm512_test_epi8_mask(x, b2), x0 = _mm512_test_epi8_mask(x, b1);
+            const uint64_t v = _mm512_cmpeq_epi8_mask(_mm512_shuffle_epi8(lut, x), _mm512_or_si512(x, case_bit));
+            const uint64_t h = ~x1 & v, l = ~(x1 ^ x0) & v;
+            ph[0] = (long long)(ah | (h << fill));
+            ph[s1] = (long long)(al | (l << fill));
+            ph[s2] = (long long)(av | (v << fill));
+            const unsigned back = 63u - fill;
+            ah = (h >> 1) >> back; al = (l >> 1) >> back; av = (v >> 1) >> back;
+            ph++;
+        }
+        if (i < len) {
+            const unsigned m = len - i;
+            const uint64_t keep = (1ULL << m) - 1ULL;
+            const __m512i x = _mm512_maskz_loadu_epi8((__mmask64)keep, (const void*)(s + i));
+            const uint64_t x1 = _mm512_test_epi8_mask(x, b2), x0 = _mm512_test_epi8_mask(x, b1);
+            const uint64_t v = _mm512_cmpeq_epi8_mask(_mm512_shuffle_epi8(lut, x), _mm512_or_si512(x, case_bit)) & keep;
+            const uint64_t h = ~x1 & v, l = ~(x1 ^ x0) & v;
+            const uint64_t th = ah | (h << fill), tl = al | (l << fill), tv = av | (v << fill);
+            ph[0] = (long long)th;
+            ph[s1] = (long long)tl;
+            ph[s2] = (long long)tv;
+            const unsigned back = 63u - fill, nf = fill + m;
+            const bool adv = nf >= 64;
+            ah = adv ? (h >> 1) >> back : th; al = adv ? (l >> 1) >> back : tl; av = adv ? (v >> 1) >> back : tv;
+            ph += adv ? 1 : 0;
+            fill = nf & 63u;
+        }
+    }
+    w_out.unit = (uint64_t)((uint64_t*)ph - w_out.hi);
+    w_out.ah = ah; w_out.al = al; w_out.av = av; w_out.fill = (int)fill;
+}
+
 TREW_AVX512 void pack_reads_avx512(const ChunkView& cv, uint32_t r0, uint32_t r1, uint32_t* off, uint64_t pos, BitWriter& w_out) {
     BitWriter w = w_out;  // local copy: its address never escapes, so the state stays in registers across the plane stores
     const __m512i lut = _mm512_broadcast_i32x4(_mm_setr_epi8(0, 'a', 0, 'c', 't', 0, 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0));
@@ -209,6 +262,11 @@ TREW_AVX512 void pack_reads_avx512(const ChunkView& cv, uint32_t r0, uint32_t r1
         cv.get(r, p, len, slack);
         *off++ = (uint32_t)pos; pos += len;
         pack_read_avx512<true>(w, (const unsigned char*)p, len, lut, case_bit, b2, b1);
+    }
+    if (cv.unit == 1 && r < r1) {   // single buffer: the lean steady-state loop
+        pack_lean_avx512(cv.buf[0], cv.locs[0], r, r1, off, w);
+        w_out = w;
+        return;
     }
     for (; r < r1; r++) {
         cv.get(r, p, len, slack);
