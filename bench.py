@@ -29,7 +29,6 @@ import shutil
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -49,29 +48,47 @@ def workload_name(reads_per_gpu):
             "MIN_MER=5 MAX_MER=32" % (reads_per_gpu // 1_000_000, READ_LEN))
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe): one nvidia-smi
+    process streaming a sample every 50 ms between start() and stop()."""
 
-    def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index = index
-        self.samples = []
-        self.stop_flag = threading.Event()
-
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag.is_set():
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.samples = []
+        self.window = (0.0, float("inf"))   # wall-clock bounds of the timed region
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return
+        try:
+            self.proc.terminate()
+            out = self.proc.communicate(timeout=5)[0].decode()
+        except Exception:
+            out = ""
+        import datetime
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, timeout=5).stdout.decode()
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 7:
-                    self.samples.append(f)
-            except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                ts = None
+            if ts is None or self.window[0] - 0.05 <= ts <= self.window[1] + 0.05:
+                self.samples.append(f[1:])
 
     def summary(self):
         if not self.samples:
@@ -79,8 +96,9 @@ class ClockSampler(threading.Thread):
         sm = sorted(float(s[0]) for s in self.samples)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        power = sorted(float(s[2]) for s in self.samples if s[2].replace(".", "", 1).isdigit())
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": power[-1] if power else None}
 
 
 def measured_hbm_peak():
@@ -218,23 +236,25 @@ def run_ours(args):
             merge.merge_device(ctx, device)
         merged_last[0] = ctx.finish_view() if rank == 0 else None
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()   # nvidia-smi needs a moment to come up: started before the warm-up, filtered to the timed region
     for _ in range(args.warmup):
         step()
     ctx.kernel_times()  # drop warm-up kernel times
     launches0 = ctx.stats().kernel_launches
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ctx.timer_start()
     t0 = time.perf_counter()
+    wall0 = time.time()
     for _ in range(args.steps):
         step()
     dev_ms = ctx.timer_stop()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     if rank == 0:
-        sampler.stop_flag.set()
+        sampler.window = (wall0, time.time())
+        sampler.stop()
     # finish() and the merge run on the host between the event pair, so the event time covers the step
     ms = max_over_ranks(max(dev_ms, 0.0))
     wall_ms = max_over_ranks(wall_ms)

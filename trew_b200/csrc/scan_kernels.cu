@@ -989,12 +989,14 @@ __device__ __noinline__ u32 eval_k(WS ws, int len, int k, u32 wv) {
         }
         if (lane == 0) run_cw[R] = (unsigned short)T;
     }
-    // hash table sized to the run count (power of two >= 2R, at most hs)
-    int hsz = 64;
-    while (hsz < 2 * R && hsz < ws.hs) hsz <<= 1;
+    // hash table sized to the run count (power of two >= 1.5 R, so hsz > R; at most hs >= 1.25 cap)
+    int hsz = 32;
+    while (hsz < R + (R >> 1) && hsz < ws.hs) hsz <<= 1;
     const u32 hmask = (u32)hsz - 1u;
-    for (int i = lane; i < hsz; i += 32) htab[i] = kEmptySlot;
-    for (int q = lane; q < R; q += 32) { grp_tot[q] = 0u; grp_last[q] = 0u; }
+    for (int i = lane; i < hsz; i += 32) {
+        htab[i] = kEmptySlot;
+        if (i < R) { grp_tot[i] = 0u; grp_last[i] = 0u; }
+    }
     __syncwarp();
     const u64* rev2 = ws.rev2();
     const bool wide = k > 32;
