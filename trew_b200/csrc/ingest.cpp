@@ -240,8 +240,17 @@ IngestResult ingest_file(int mode, int slice_length, const char* file1, bool gz1
         return res;
     }
     for (;;) {
-        if (!a.eof && !a.fill(chunk_bytes, pool, par_min)) return IngestResult{TREW_ERR_IO, "File 1 IO Error: " + a.rd.error() + "."};
-        if (!b.eof && !b.fill(chunk_bytes, pool, par_min)) return IngestResult{TREW_ERR_IO, "File 2 IO Error: " + b.rd.error() + "."};
+        if (pool && pool->size() > 1 && (gz1 || gz2)) {
+            // two inflate streams are independent: read both mates' blocks at the same time
+            bool ok[2] = {true, true};
+            Side* sides[2] = {&a, &b};
+            pool->run(2, [&](int i) { if (!sides[i]->eof) ok[i] = sides[i]->fill(chunk_bytes, nullptr, par_min); });
+            if (!ok[0]) return IngestResult{TREW_ERR_IO, "File 1 IO Error: " + a.rd.error() + "."};
+            if (!ok[1]) return IngestResult{TREW_ERR_IO, "File 2 IO Error: " + b.rd.error() + "."};
+        } else {
+            if (!a.eof && !a.fill(chunk_bytes, pool, par_min)) return IngestResult{TREW_ERR_IO, "File 1 IO Error: " + a.rd.error() + "."};
+            if (!b.eof && !b.fill(chunk_bytes, pool, par_min)) return IngestResult{TREW_ERR_IO, "File 2 IO Error: " + b.rd.error() + "."};
+        }
         a.scan(mode, slice_length, &too_long, pool, par_min);
         b.scan(mode, slice_length, &too_long, pool, par_min);
         const bool done = a.eof && b.eof;
