@@ -150,6 +150,7 @@ int launch_scan(trew_ctx* ctx, const DevBatch& b, uint32_t n_units, uint32_t max
     a.survivors = d_survivors; a.n_survivors = d_counters; a.work_counter = d_counters + 1;
     a.slice_scratch = *d_scratch; a.slice_scratch_stride = stride; a.run_cap = run_cap_for(ctx->cfg, max_read_len);
     a.total_survivors = ctx->d_total_surv;
+    a.packed_probes = n_units < (1u << 28) ? 1 : 0;
     launch_exact(ctx->dcfg, b, a, ctx->plan, st);
     if (ev) CK(cudaEventRecord(ev[3], st));
     CK(cudaGetLastError());

@@ -647,23 +647,27 @@ __global__ void __launch_bounds__(256) trew_filter_kernel(DevCfg cfg, DevBatch b
     for (int i = threadIdx.x; i < kThrTableSize; i += blockDim.x) thr[i] = cfg.thr_low[i];
     __syncthreads();
     const u32 n_units = units ? *n_units_ptr : n_units_all;   // no list: every unit of the batch
+    const bool pack_probes = n_units_all < (1u << kProbeShift);
     u32 stride = gridDim.x * blockDim.x;
     u32 n_round = (n_units + 31u) & ~31u;
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
         bool maybe = false;
-        u32 u = 0;
+        u32 u = 0, live = 0;
         if (i < n_units) {
             u32 pm = 0xfu;
             u = i;
             if (units) { u32 e = units[i]; u = e & ((1u << kProbeShift) - 1u); pm = e >> kProbeShift; }
             Probe p[4];
             int np = unit_probes(cfg, b, u, p);
+            live = pm & ((1u << np) - 1u);   // probes that may still find a target period
             for (int j = 0; j < np && !maybe; j++) {
-                if (!((pm >> j) & 1u) || p[j].k1 < p[j].k0) continue;
-                maybe = probe_is_fast(p[j]) ? decide_short(b, p[j].pos, p[j].wl, p[j].k0, p[j].k1, thr) : probe_dispatch<MAXNW>(b, p[j], thr);
+                if (((pm >> j) & 1u) && p[j].k1 >= p[j].k0)
+                    maybe = probe_is_fast(p[j]) ? decide_short(b, p[j].pos, p[j].wl, p[j].k0, p[j].k1, thr) : probe_dispatch<MAXNW>(b, p[j], thr);
+                if (!maybe) live &= ~(1u << j);
             }
         }
-        list_append(maybe, u, survivors, n_survivors);
+        // the exact kernel skips the scan of a window no probe vouches for (its result is "no target period")
+        list_append(maybe, pack_probes ? u | (live << kProbeShift) : u, survivors, n_survivors);
     }
 }
 
@@ -1239,7 +1243,8 @@ __device__ void target_window(TableRef tr, WS ws, const DevBatch& b, u32 pos, in
 enum { T_F = 0, T_B = 2, T_O = 4 };
 
 // buffer_task (src/kmer.cpp:80-266)
-__device__ void route_short(const DevCfg& cfg, TableRef tr, WS ws, const DevBatch& b, u32 u) {
+// pm: probes (unit_probes order) the filter kernels could not rule out; the scan of any other window finds nothing
+__device__ void route_short(const DevCfg& cfg, TableRef tr, WS ws, const DevBatch& b, u32 u, u32 pm) {
     const int MINM = cfg.min_mer, MAXM = cfg.max_mer;
     u32 b0 = __ldg(b.bit_off + u);
     int n = (int)(__ldg(b.bit_off + u + 1) - b0);
@@ -1249,9 +1254,9 @@ __device__ void route_short(const DevCfg& cfg, TableRef tr, WS ws, const DevBatc
         int kmax = min(n / 4, MAXM);
         u32 lpos = b0, rpos = b0 + (u32)(n - (n + 1) / 2);
         int llen = n / 2, rlen = (n + 1) / 2;
-        ScanRes l = scan_stats(ws, b, lpos, llen, MINM, kmax, cfg.low, cfg.high);
-        ScanRes r = scan_stats(ws, b, rpos, rlen, MINM, kmax, cfg.low, cfg.high);  // always evaluated
-        L[0] = l.th; L[1] = l.tl; R[0] = r.th; R[1] = r.tl;
+        if (pm & 1u) { ScanRes l = scan_stats(ws, b, lpos, llen, MINM, kmax, cfg.low, cfg.high); L[0] = l.th; L[1] = l.tl; }
+        if (pm & 2u) { ScanRes r = scan_stats(ws, b, rpos, rlen, MINM, kmax, cfg.low, cfg.high); R[0] = r.th; R[1] = r.tl; }  // "always evaluated"
+        pm >>= 2;
         // right-half emissions survive only for classes where the left half found nothing
         // (nullptr maps at src/kmer.cpp:125, result.backward at :158)
 #pragma unroll
@@ -1262,7 +1267,7 @@ __device__ void route_short(const DevCfg& cfg, TableRef tr, WS ws, const DevBatc
         }
     }
     bool hc[2] = {L[0] == 0 && R[0] == 0, L[1] == 0 && R[1] == 0};
-    if (4 * MAXM > n && (hc[0] || hc[1])) {
+    if (4 * MAXM > n && (hc[0] || hc[1]) && (pm & 1u)) {
         ScanRes s = scan_stats(ws, b, b0, n, max(n / 4 + 1, MINM), min(n / 2, MAXM), cfg.low, cfg.high);
         if (hc[0] && s.th) emit_window(tr, ws, b, b0, n, s.th, T_O + 0, false);  // un-folded into 'both'
         if (hc[1] && s.tl) emit_window(tr, ws, b, b0, n, s.tl, T_O + 1, false);
@@ -1442,8 +1447,9 @@ __global__ void __launch_bounds__(kExactWarps * 32, TREW_EXACT_BPS) trew_exact_k
         if (lane == 0) idx = atomicAdd(a.work_counter, 1u);
         idx = __shfl_sync(0xffffffffu, idx, 0);
         if (idx >= n) break;
-        u32 u = a.survivors[idx];
-        if constexpr (MODE == 0) route_short(cfg, tr, ws, b, u);
+        u32 u = a.survivors[idx], pm = 0xfu;
+        if (a.packed_probes) { pm = u >> kProbeShift; u &= (1u << kProbeShift) - 1u; }
+        if constexpr (MODE == 0) route_short(cfg, tr, ws, b, u, pm);
         else if constexpr (MODE == 1) route_pair(cfg, tr, ws, b, u);
         else route_long(cfg, tr, ws, b, u, scratch);
     }

@@ -56,6 +56,7 @@ struct ExactArgs {
     unsigned int slice_scratch_stride;  // bytes per warp
     int run_cap;                     // run-list capacity per warp (>= longest window + 1)
     unsigned long long* total_survivors;  // running total over all launches (statistics)
+    int packed_probes;               // survivor entries carry the undecided-probe mask in bits 28..31
 };
 
 // grid sizes (total blocks) of the three scan kernels; all three are grid-stride / work-counter kernels
