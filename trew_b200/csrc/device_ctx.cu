@@ -76,6 +76,7 @@ struct trew_ctx {
     void* d_sort_tmp = nullptr; size_t sort_tmp_bytes = 0;
     unsigned int* d_n = nullptr;
     uint64_t n_export = 0;
+    bool export_valid = false;   // d_entries reflects the current table (no scan / merge / reset since the last export)
     trew_stats stats{};
     Pool* pool = nullptr;
     std::string err;
@@ -141,6 +142,7 @@ int launch_scan(trew_ctx* ctx, const DevBatch& b, uint32_t n_units, uint32_t max
         CK(cudaMalloc((void**)d_scratch, need));
         *scratch_bytes = need;
     }
+    ctx->export_valid = false;
     CK(cudaMemsetAsync(d_counters, 0, 4 * sizeof(unsigned int), st));
     if (ev) CK(cudaEventRecord(ev[0], st));
     launch_filter(ctx->dcfg, b, n_units, max_read_len, d_survivors + n_units, d_counters + 2, d_survivors, d_counters, ctx->plan, st,
@@ -625,6 +627,11 @@ int trew_dev_export_device(trew_ctx* ctx, const trew_entry** d_entries, uint64_t
     if (!ctx) return TREW_ERR_ARG;
     int rc = trew_dev_sync(ctx);
     if (rc) return rc;
+    if (ctx->export_valid) {
+        if (d_entries) *d_entries = ctx->d_entries;
+        if (n_entries) *n_entries = ctx->n_export;
+        return TREW_OK;
+    }
     // count first (the table is sparse: sizing the entry array by the slot count would waste 128 MB)
     unsigned int n = 0;
     for (int pass = 0; pass < 2; pass++) {
@@ -660,6 +667,7 @@ int trew_dev_export_device(trew_ctx* ctx, const trew_entry** d_entries, uint64_t
         ctx->stats.kernel_launches += 2;
     }
     ctx->n_export = n;
+    ctx->export_valid = true;
     if (d_entries) *d_entries = ctx->d_entries;
     if (n_entries) *n_entries = n;
     return TREW_OK;
@@ -714,6 +722,7 @@ int trew_dev_export_rows(trew_ctx* ctx, trew_entry* d_rows, uint64_t capacity_ro
 int trew_dev_merge_rows(trew_ctx* ctx, const trew_entry* d_rows, uint64_t n_rows) {
     if (!ctx || (n_rows && !d_rows) || n_rows > 0xffffffffULL) return TREW_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
+    ctx->export_valid = false;
     launch_merge_entries(ctx->dcfg, d_rows, (unsigned int)n_rows, ctx->main_stream);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->main_stream));
@@ -725,6 +734,7 @@ int trew_dev_reset(trew_ctx* ctx) {
     if (!ctx) return TREW_ERR_ARG;
     int rc = trew_dev_sync(ctx);
     if (rc && rc != TREW_ERR_TABLE_FULL) return rc;
+    ctx->export_valid = false;
     // on the scan stream (the context's streams do not synchronise with the legacy default stream)
     CK(cudaMemsetAsync(ctx->dcfg.slots, 0, ctx->n_slots * sizeof(Slot), ctx->main_stream));
     CK(cudaMemsetAsync(ctx->d_error, 0, 2 * sizeof(unsigned int), ctx->main_stream));
