@@ -175,7 +175,9 @@ int trew_dev_export_device(trew_ctx* ctx, const trew_entry** d_entries, uint64_t
 /* Cross-rank merge (one process per GPU): copy the compacted table (trew_entry rows, 32 bytes each) into
  * caller-owned DEVICE memory -- e.g. the buffer of an NCCL gather -- and add rows received from another rank to this
  * context's table.  Integer sums, hence exact; this is the multi-GPU form of the per-worker map sum in
- * process_output (src/kmer.cpp:1486-1515).  trew_dev_export_rows with d_rows == NULL only reports the row count. */
+ * process_output (src/kmer.cpp:1486-1515).  trew_dev_export_rows with d_rows == NULL only reports the row count; its
+ * rows are in no particular order.  trew_dev_merge_rows is asynchronous: the rows must stay valid until the next
+ * trew_dev_sync / trew_dev_finish / export on this context, which also reports a table overflow. */
 int trew_dev_export_rows(trew_ctx* ctx, trew_entry* d_rows, uint64_t capacity_rows, uint64_t* n_rows);
 int trew_dev_merge_rows(trew_ctx* ctx, const trew_entry* d_rows, uint64_t n_rows);
 

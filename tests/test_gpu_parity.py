@@ -169,7 +169,7 @@ def test_device_row_merge():
         rows = torch.zeros((n, 4), dtype=torch.int64, device="cuda:0")
         assert c2.export_rows(rows.data_ptr(), n) == n
         c1.merge_rows(rows.data_ptr(), n)
-        merged = c1.finish()
+        merged = c1.finish()   # finish() waits for the asynchronous merge before `rows` goes away
     assert merged == whole, diff_msg(merged, whole)
 
 

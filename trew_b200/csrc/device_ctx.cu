@@ -72,7 +72,9 @@ struct trew_ctx {
     cudaStream_t main_stream = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     // export buffers
-    trew_entry* d_entries = nullptr; size_t d_entries_cap = 0;   // compacted, sorted table (device)
+    trew_entry* d_entries = nullptr; size_t d_entries_cap = 0;   // compacted table (device, unsorted)
+    trew_entry* d_sorted = nullptr; size_t d_sorted_cap = 0;     // the same rows sorted by (table, k, seq)
+    bool sorted_valid = false;
     void* d_sort_tmp = nullptr; size_t sort_tmp_bytes = 0;
     unsigned int* d_n = nullptr;
     uint64_t n_export = 0;
@@ -482,6 +484,7 @@ void trew_dev_destroy(trew_ctx* ctx) {
     if (ctx->d_thr) cudaFree(ctx->d_thr);
     if (ctx->d_total_surv) cudaFree(ctx->d_total_surv);
     if (ctx->d_entries) cudaFree(ctx->d_entries);
+    if (ctx->d_sorted) cudaFree(ctx->d_sorted);
     if (ctx->d_sort_tmp) cudaFree(ctx->d_sort_tmp);
     if (ctx->d_n) cudaFree(ctx->d_n);
     if (ctx->h_export) cudaFreeHost(ctx->h_export);
@@ -623,68 +626,88 @@ int trew_dev_sync(trew_ctx* ctx) {
     return check_device_error(ctx);
 }
 
-int trew_dev_export_device(trew_ctx* ctx, const trew_entry** d_entries, uint64_t* n_entries) {
-    if (!ctx) return TREW_ERR_ARG;
-    int rc = trew_dev_sync(ctx);
-    if (rc) return rc;
-    if (ctx->export_valid) {
-        if (d_entries) *d_entries = ctx->d_entries;
-        if (n_entries) *n_entries = ctx->n_export;
-        return TREW_OK;
-    }
-    // count first (the table is sparse: sizing the entry array by the slot count would waste 128 MB)
-    unsigned int n = 0;
-    for (int pass = 0; pass < 2; pass++) {
-        CK(cudaMemsetAsync(ctx->d_n, 0, sizeof(unsigned int), ctx->main_stream));
-        if (pass == 0 && ctx->d_entries_cap == 0) {
-            ctx->d_entries_cap = (size_t)1 << 20;
-            CK(cudaMalloc((void**)&ctx->d_entries, ctx->d_entries_cap * sizeof(trew_entry)));
-        }
-        launch_compact(ctx->dcfg.slots, (unsigned int)ctx->n_slots, ctx->d_entries, ctx->d_n, ctx->main_stream, (unsigned int)ctx->d_entries_cap);
-        CK(cudaGetLastError());
-        ctx->stats.kernel_launches += 1;
-        CK(cudaMemcpyAsync(&n, ctx->d_n, sizeof(n), cudaMemcpyDeviceToHost, ctx->main_stream));
-        CK(cudaStreamSynchronize(ctx->main_stream));
-        if (n <= ctx->d_entries_cap) break;
-        // the array was too small (the kernel only counted past its end): grow and compact again
-        CK(cudaFree(ctx->d_entries));
-        ctx->d_entries = nullptr;
-        ctx->d_entries_cap = (size_t)n + n / 4 + 1024;
-        CK(cudaMalloc((void**)&ctx->d_entries, ctx->d_entries_cap * sizeof(trew_entry)));
-    }
-    if (n > 1) {
-        size_t need = 0;
-        CK(sort_entries(ctx->d_entries, n, nullptr, &need, ctx->main_stream));
-        if (need > ctx->sort_tmp_bytes) {
-            if (ctx->d_sort_tmp) CK(cudaFree(ctx->d_sort_tmp));
-            ctx->d_sort_tmp = nullptr;
-            ctx->sort_tmp_bytes = need + need / 4;
-            CK(cudaMalloc(&ctx->d_sort_tmp, ctx->sort_tmp_bytes));
-        }
-        size_t bytes = ctx->sort_tmp_bytes;
-        CK(sort_entries(ctx->d_entries, n, ctx->d_sort_tmp, &bytes, ctx->main_stream));
-        CK(cudaStreamSynchronize(ctx->main_stream));
-        ctx->stats.kernel_launches += 2;
-    }
-    ctx->n_export = n;
-    ctx->export_valid = true;
-    if (d_entries) *d_entries = ctx->d_entries;
-    if (n_entries) *n_entries = n;
-    return TREW_OK;
-}
-
 }  // extern "C"
 
 namespace {
-int export_sorted(trew_ctx* ctx, uint64_t* n_out) { return trew_dev_export_device(ctx, nullptr, n_out); }
+
+// Compact the table into ctx->d_entries (cached until the table changes) and, on request, sort the rows by
+// (table, k, seq) into ctx->d_sorted with three radix passes.
+int export_entries(trew_ctx* ctx, bool need_sorted, const trew_entry** out, uint64_t* n_out) {
+    int rc = trew_dev_sync(ctx);
+    if (rc) return rc;
+    if (!ctx->export_valid) {
+        // count first (the table is sparse: sizing the entry array by the slot count would waste 128 MB)
+        unsigned int n = 0;
+        for (int pass = 0; pass < 2; pass++) {
+            CK(cudaMemsetAsync(ctx->d_n, 0, sizeof(unsigned int), ctx->main_stream));
+            if (pass == 0 && ctx->d_entries_cap == 0) {
+                ctx->d_entries_cap = (size_t)1 << 20;
+                CK(cudaMalloc((void**)&ctx->d_entries, ctx->d_entries_cap * sizeof(trew_entry)));
+            }
+            launch_compact(ctx->dcfg.slots, (unsigned int)ctx->n_slots, ctx->d_entries, ctx->d_n, ctx->main_stream,
+                           (unsigned int)ctx->d_entries_cap);
+            CK(cudaGetLastError());
+            ctx->stats.kernel_launches += 1;
+            CK(cudaMemcpyAsync(&n, ctx->d_n, sizeof(n), cudaMemcpyDeviceToHost, ctx->main_stream));
+            CK(cudaStreamSynchronize(ctx->main_stream));
+            if (n <= ctx->d_entries_cap) break;
+            // the array was too small (the kernel only counted past its end): grow and compact again
+            CK(cudaFree(ctx->d_entries));
+            ctx->d_entries = nullptr;
+            ctx->d_entries_cap = (size_t)n + n / 4 + 1024;
+            CK(cudaMalloc((void**)&ctx->d_entries, ctx->d_entries_cap * sizeof(trew_entry)));
+        }
+        ctx->n_export = n;
+        ctx->export_valid = true;
+        ctx->sorted_valid = false;
+    }
+    const unsigned int n = (unsigned int)ctx->n_export;
+    if (need_sorted && !ctx->sorted_valid) {
+        if (n > ctx->d_sorted_cap) {
+            if (ctx->d_sorted) CK(cudaFree(ctx->d_sorted));
+            ctx->d_sorted = nullptr;
+            ctx->d_sorted_cap = std::max<size_t>((size_t)n + n / 4 + 1024, (size_t)1 << 20);
+            CK(cudaMalloc((void**)&ctx->d_sorted, ctx->d_sorted_cap * sizeof(trew_entry)));
+        }
+        if (n == 1) CK(cudaMemcpyAsync(ctx->d_sorted, ctx->d_entries, sizeof(trew_entry), cudaMemcpyDeviceToDevice, ctx->main_stream));
+        if (n > 1) {
+            const bool wide = ctx->cfg.max_mer > 32;
+            size_t need = 0;
+            CK(sort_entries_radix(ctx->d_entries, ctx->d_sorted, n, wide, nullptr, &need, ctx->main_stream));
+            if (need > ctx->sort_tmp_bytes) {
+                if (ctx->d_sort_tmp) CK(cudaFree(ctx->d_sort_tmp));
+                ctx->d_sort_tmp = nullptr;
+                ctx->sort_tmp_bytes = need + need / 4;
+                CK(cudaMalloc(&ctx->d_sort_tmp, ctx->sort_tmp_bytes));
+            }
+            size_t bytes = ctx->sort_tmp_bytes;
+            CK(sort_entries_radix(ctx->d_entries, ctx->d_sorted, n, wide, ctx->d_sort_tmp, &bytes, ctx->main_stream));
+            ctx->stats.kernel_launches += wide ? 11 : 8;
+        }
+        CK(cudaStreamSynchronize(ctx->main_stream));
+        ctx->sorted_valid = true;
+    }
+    if (out) *out = need_sorted ? ctx->d_sorted : ctx->d_entries;
+    if (n_out) *n_out = n;
+    return TREW_OK;
+}
+
+int export_sorted(trew_ctx* ctx, uint64_t* n_out) { return export_entries(ctx, false, nullptr, n_out); }
+
 }  // namespace
 
 extern "C" {
 
+int trew_dev_export_device(trew_ctx* ctx, const trew_entry** d_entries, uint64_t* n_entries) {
+    if (!ctx) return TREW_ERR_ARG;
+    return export_entries(ctx, true, d_entries, n_entries);
+}
+
 int trew_dev_finish(trew_ctx* ctx, const trew_entry** entries, uint64_t* n_entries) {
     if (!ctx) return TREW_ERR_ARG;
     uint64_t n = 0;
-    int rc = trew_dev_export_device(ctx, nullptr, &n);
+    const trew_entry* d_rows = nullptr;
+    int rc = export_entries(ctx, true, &d_rows, &n);
     if (rc) return rc;
     // one D2H of the sorted entries into a pinned array (grown on demand) that is handed to the caller as is
     size_t need = (size_t)n * sizeof(trew_entry) + 64;
@@ -696,7 +719,7 @@ int trew_dev_finish(trew_ctx* ctx, const trew_entry** entries, uint64_t* n_entri
         ctx->h_export_bytes = cap;
     }
     if (n) {
-        CK(cudaMemcpyAsync(ctx->h_export, ctx->d_entries, n * sizeof(trew_entry), cudaMemcpyDeviceToHost, ctx->main_stream));
+        CK(cudaMemcpyAsync(ctx->h_export, d_rows, n * sizeof(trew_entry), cudaMemcpyDeviceToHost, ctx->main_stream));
         CK(cudaStreamSynchronize(ctx->main_stream));
     }
     ctx->stats.d2h_bytes += n * sizeof(trew_entry) + 4;
@@ -708,13 +731,14 @@ int trew_dev_finish(trew_ctx* ctx, const trew_entry** entries, uint64_t* n_entri
 int trew_dev_export_rows(trew_ctx* ctx, trew_entry* d_rows, uint64_t capacity_rows, uint64_t* n_rows) {
     if (!ctx || !n_rows) return TREW_ERR_ARG;
     uint64_t n = 0;
-    int rc = trew_dev_export_device(ctx, nullptr, &n);
+    const trew_entry* d_src = nullptr;
+    int rc = export_entries(ctx, false, &d_src, &n);   // the merge does not care about row order
     if (rc) return rc;
     *n_rows = n;
     if (!d_rows) return TREW_OK;  // size query
     if (n > capacity_rows) return fail(ctx, TREW_ERR_ARG, "row buffer too small: %llu rows, capacity %llu", (unsigned long long)n,
                                        (unsigned long long)capacity_rows);
-    if (n) CK(cudaMemcpyAsync(d_rows, ctx->d_entries, n * sizeof(trew_entry), cudaMemcpyDeviceToDevice, ctx->main_stream));
+    if (n) CK(cudaMemcpyAsync(d_rows, d_src, n * sizeof(trew_entry), cudaMemcpyDeviceToDevice, ctx->main_stream));
     CK(cudaStreamSynchronize(ctx->main_stream));
     return TREW_OK;
 }
@@ -723,11 +747,10 @@ int trew_dev_merge_rows(trew_ctx* ctx, const trew_entry* d_rows, uint64_t n_rows
     if (!ctx || (n_rows && !d_rows) || n_rows > 0xffffffffULL) return TREW_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
     ctx->export_valid = false;
-    launch_merge_entries(ctx->dcfg, d_rows, (unsigned int)n_rows, ctx->main_stream);
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(ctx->main_stream));
+    launch_merge_entries(ctx->dcfg, d_rows, (unsigned int)n_rows, ctx->main_stream);   // asynchronous: the next sync / export
+    CK(cudaGetLastError());                                                             // waits and checks the error flag
     ctx->stats.kernel_launches += n_rows ? 1 : 0;
-    return check_device_error(ctx);
+    return TREW_OK;
 }
 
 int trew_dev_reset(trew_ctx* ctx) {

@@ -76,6 +76,9 @@ int exact_warps_total(int sm_count);
 void launch_compact(const Slot* slots, unsigned int n_slots, trew_entry* out, unsigned int* d_n, cudaStream_t stream, unsigned int cap);
 // in-place sort by (table, k, seq); call with d_temp == nullptr to query *temp_bytes
 cudaError_t sort_entries(trew_entry* d_entries, unsigned int n, void* d_temp, size_t* temp_bytes, cudaStream_t stream);
+// radix variant: sorted rows into d_out (d_entries untouched); wide = some key uses seq_hi (MAX_MER > 32)
+cudaError_t sort_entries_radix(const trew_entry* d_entries, trew_entry* d_out, unsigned int n, bool wide, void* d_temp,
+                               size_t* temp_bytes, cudaStream_t stream);
 void launch_merge_entries(const DevCfg& cfg, const trew_entry* entries, unsigned int n, cudaStream_t stream);
 
 void launch_synth(unsigned long long seed, unsigned int n_reads, unsigned int read_len, unsigned int tel_thr,

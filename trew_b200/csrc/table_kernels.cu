@@ -3,7 +3,10 @@
 // handed to process_output, src/kmer.cpp:1486-1515).
 #include "scan_kernels.cuh"
 
+#include <algorithm>
+
 #include <cub/device/device_merge_sort.cuh>
+#include <cub/device/device_radix_sort.cuh>
 
 namespace trew {
 
@@ -48,6 +51,70 @@ void launch_compact(const Slot* slots, unsigned int n_slots, trew_entry* out, un
 
 cudaError_t sort_entries(trew_entry* d_entries, unsigned int n, void* d_temp, size_t* temp_bytes, cudaStream_t stream) {
     return cub::DeviceMergeSort::SortKeys(d_temp, *temp_bytes, d_entries, (int)n, EntryLess(), stream);
+}
+
+// ---- radix path: three stable LSD passes over (seq_lo, seq_hi, table << 8 | k) with a row index as payload, then one
+// gather of the 32-byte rows.  Moves 12 bytes per row and pass instead of merge-sorting 32-byte rows by a comparator.
+
+__global__ void key_from_entries_kernel(const trew_entry* __restrict__ e, const u32* __restrict__ idx, u32 n, int which,
+                                        u64* __restrict__ key64, unsigned short* __restrict__ key16, u32* __restrict__ idx_out) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u32 j = idx ? idx[i] : i;
+        if (which == 0) { key64[i] = e[j].seq_lo; idx_out[i] = i; }
+        else if (which == 1) key64[i] = e[j].seq_hi;
+        else key16[i] = (unsigned short)(((u32)e[j].table << 8) | (u32)e[j].k);
+    }
+}
+
+__global__ void gather_entries_kernel(const trew_entry* __restrict__ e, const u32* __restrict__ idx, u32 n, trew_entry* __restrict__ out) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = e[idx[i]];
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// d_out receives the sorted rows (d_entries is left untouched).  Call with d_temp == nullptr to query *temp_bytes.
+cudaError_t sort_entries_radix(const trew_entry* d_entries, trew_entry* d_out, unsigned int n, bool wide, void* d_temp,
+                               size_t* temp_bytes, cudaStream_t stream) {
+    size_t cub64 = 0, cub16 = 0;
+    cub::DoubleBuffer<u64> k64(nullptr, nullptr);
+    cub::DoubleBuffer<unsigned short> k16(nullptr, nullptr);
+    cub::DoubleBuffer<u32> ix(nullptr, nullptr);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, cub64, k64, ix, (int)n, 0, 64, stream);
+    if (e != cudaSuccess) return e;
+    e = cub::DeviceRadixSort::SortPairs(nullptr, cub16, k16, ix, (int)n, 0, 11, stream);
+    if (e != cudaSuccess) return e;
+    const size_t cub_bytes = align256(std::max(cub64, cub16));
+    const size_t need = 2 * align256((size_t)n * 8) + 2 * align256((size_t)n * 4) + 2 * align256((size_t)n * 2) + cub_bytes;
+    if (!d_temp) { *temp_bytes = need; return cudaSuccess; }
+    if (*temp_bytes < need) return cudaErrorInvalidValue;
+    char* p = (char*)d_temp;
+    u64* ka = (u64*)p; p += align256((size_t)n * 8);
+    u64* kb = (u64*)p; p += align256((size_t)n * 8);
+    u32* ia = (u32*)p; p += align256((size_t)n * 4);
+    u32* ib = (u32*)p; p += align256((size_t)n * 4);
+    unsigned short* sa = (unsigned short*)p; p += align256((size_t)n * 2);
+    unsigned short* sb = (unsigned short*)p; p += align256((size_t)n * 2);
+    void* cub_tmp = p;
+    const int blocks = (int)std::min<unsigned int>((n + 255) / 256, 4736u);
+    k64 = cub::DoubleBuffer<u64>(ka, kb);
+    ix = cub::DoubleBuffer<u32>(ia, ib);
+    key_from_entries_kernel<<<blocks, 256, 0, stream>>>(d_entries, nullptr, n, 0, k64.Current(), nullptr, ix.Current());
+    size_t tb = cub_bytes;
+    e = cub::DeviceRadixSort::SortPairs(cub_tmp, tb, k64, ix, (int)n, 0, 64, stream);
+    if (e != cudaSuccess) return e;
+    if (wide) {
+        key_from_entries_kernel<<<blocks, 256, 0, stream>>>(d_entries, ix.Current(), n, 1, k64.Current(), nullptr, nullptr);
+        tb = cub_bytes;
+        e = cub::DeviceRadixSort::SortPairs(cub_tmp, tb, k64, ix, (int)n, 0, 64, stream);
+        if (e != cudaSuccess) return e;
+    }
+    k16 = cub::DoubleBuffer<unsigned short>(sa, sb);
+    key_from_entries_kernel<<<blocks, 256, 0, stream>>>(d_entries, ix.Current(), n, 2, nullptr, k16.Current(), nullptr);
+    tb = cub_bytes;
+    e = cub::DeviceRadixSort::SortPairs(cub_tmp, tb, k16, ix, (int)n, 0, 11, stream);
+    if (e != cudaSuccess) return e;
+    gather_entries_kernel<<<blocks, 256, 0, stream>>>(d_entries, ix.Current(), n, d_out);
+    return cudaGetLastError();
 }
 
 }  // namespace trew

@@ -83,4 +83,5 @@ def merge_device(ctx, device: torch.device, dst: int = 0) -> None:
         torch.cuda.synchronize(device)
         for r in range(world):
             if r != dst and sizes[r]:
-                ctx.merge_rows(gathered[r].data_ptr(), sizes[r])
+                ctx.merge_rows(gathered[r].data_ptr(), sizes[r])   # asynchronous on the context's stream
+        ctx.sync()   # the gathered buffers must outlive the merge kernels
