@@ -232,9 +232,7 @@ def run_ours(args):
         for h, _ in handles:
             ctx.scan_resident(h)
         # sync + compaction kernel + D2H of the tables (+ exact NCCL merge across ranks for N > 1)
-        if world > 1:
-            merge.merge_device(ctx, device)
-        merged_last[0] = ctx.finish_view() if rank == 0 else None
+        merged_last[0] = merge.finish_merged(ctx, device) if world > 1 else ctx.finish_view()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -276,9 +274,7 @@ def run_ours(args):
         ctx.reset()
         for _ in range(reps):
             ctx.submit_chunk(buf, locs)
-        if world > 1:
-            merge.merge_device(ctx, device)
-        return ctx.finish_view() if rank == 0 else None
+        return merge.finish_merged(ctx, device) if world > 1 else ctx.finish_view()
 
     for _ in range(max(1, min(args.warmup, 2))):
         e2e_step()

@@ -180,6 +180,15 @@ int trew_dev_export_device(trew_ctx* ctx, const trew_entry** d_entries, uint64_t
  * trew_dev_sync / trew_dev_finish / export on this context, which also reports a table overflow. */
 int trew_dev_export_rows(trew_ctx* ctx, trew_entry* d_rows, uint64_t capacity_rows, uint64_t* n_rows);
 int trew_dev_merge_rows(trew_ctx* ctx, const trew_entry* d_rows, uint64_t n_rows);
+/* End of file on the merging rank: the union of this context's table and the other ranks' rows (device pointers, as
+ * written by trew_dev_export_rows on those ranks and moved here by an NCCL gather) -- concatenated, sorted by
+ * (table, k, seq) and equal keys summed on the device, then copied to the host like trew_dev_finish.  The context's own
+ * table is left as it is. */
+int trew_dev_finish_merged(trew_ctx* ctx, const trew_entry* const* d_lists, const uint64_t* n_rows, uint32_t n_lists,
+                           const trew_entry** entries, uint64_t* n_entries);
+/* Make room for about expected_new_keys more distinct keys (grows and re-hashes the table when it would pass a
+ * quarter full).  Call before merging other ranks' rows. */
+int trew_dev_reserve(trew_ctx* ctx, uint64_t expected_new_keys);
 
 /* Zero the count table (start of a new file; the reference allocates fresh maps per file,
  * src/kmer.cpp:89). */

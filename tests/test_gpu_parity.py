@@ -168,6 +168,10 @@ def test_device_row_merge():
         assert n > 0
         rows = torch.zeros((n, 4), dtype=torch.int64, device="cuda:0")
         assert c2.export_rows(rows.data_ptr(), n) == n
+        union = c1.finish_merged_view([(rows.data_ptr(), n)])   # sort-based union, c1's table untouched
+        union = {(int(r["table"]), int(r["k"]), (int(r["seq_hi"]) << 64) | int(r["seq_lo"])): int(r["count"]) for r in union}
+        assert union == whole, diff_msg(union, whole)
+        c1.reserve(n)
         c1.merge_rows(rows.data_ptr(), n)
         merged = c1.finish()   # finish() waits for the asynchronous merge before `rows` goes away
     assert merged == whole, diff_msg(merged, whole)

@@ -64,7 +64,7 @@ ABI_SYMBOLS = [
     "trew_dev_export_device", "trew_dev_reset", "trew_dev_get_stats", "trew_pack_bound", "trew_pack_reads",
     "trew_synth_resident", "trew_dev_timer_start", "trew_dev_timer_stop", "trew_dev_kernel_times",
     "trew_dev_process_file", "trew_ingest_file", "trew_report_create", "trew_report_destroy", "trew_report_add_file",
-    "trew_report_finish", "trew_dev_export_rows", "trew_dev_merge_rows",
+    "trew_report_finish", "trew_dev_export_rows", "trew_dev_merge_rows", "trew_dev_reserve", "trew_dev_finish_merged",
 ]
 
 CHUNK_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_uint32, C.c_void_p,
@@ -100,6 +100,9 @@ def load_library() -> C.CDLL:
     L.trew_dev_export_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     L.trew_dev_export_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.trew_dev_merge_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    L.trew_dev_reserve.argtypes = [C.c_void_p, C.c_uint64]
+    L.trew_dev_finish_merged.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_uint32,
+                                         C.POINTER(C.POINTER(Entry)), C.POINTER(C.c_uint64)]
     L.trew_dev_reset.argtypes = [C.c_void_p]
     L.trew_dev_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     L.trew_pack_bound.argtypes = [C.c_uint32, C.c_uint64]
@@ -334,6 +337,24 @@ class DeviceContext:
     def merge_rows(self, d_rows: int, n_rows: int) -> None:
         """Add rows (device pointer, the format of export_rows) to this context's table."""
         self._check(self.lib.trew_dev_merge_rows(self.ctx, d_rows, n_rows))
+
+    def finish_merged_view(self, lists) -> np.ndarray:
+        """Union of this context's table and other ranks' rows (`lists` = [(device pointer, n_rows), ...]) as a
+        zero-copy structured view sorted by (table, k, seq); this context's table is not modified."""
+        k = len(lists)
+        ptrs = (C.c_void_p * max(k, 1))(*[p for p, _ in lists])
+        sizes = (C.c_uint64 * max(k, 1))(*[n for _, n in lists])
+        p = C.POINTER(Entry)()
+        n = C.c_uint64()
+        self._check(self.lib.trew_dev_finish_merged(self.ctx, ptrs, sizes, k, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, dtype=self.ENTRY_DTYPE)
+        buf = (C.c_char * (n.value * 32)).from_address(C.addressof(p.contents))
+        return np.frombuffer(buf, dtype=self.ENTRY_DTYPE, count=n.value)
+
+    def reserve(self, expected_new_keys: int) -> None:
+        """Grow the count table so that about this many more distinct keys fit at a load factor <= 1/4."""
+        self._check(self.lib.trew_dev_reserve(self.ctx, expected_new_keys))
 
     def reset(self) -> None:
         self._check(self.lib.trew_dev_reset(self.ctx))

@@ -74,6 +74,7 @@ struct trew_ctx {
     // export buffers
     trew_entry* d_entries = nullptr; size_t d_entries_cap = 0;   // compacted table (device, unsorted)
     trew_entry* d_sorted = nullptr; size_t d_sorted_cap = 0;     // the same rows sorted by (table, k, seq)
+    trew_entry* d_concat = nullptr; size_t d_concat_cap = 0;     // finish_merged: this table's rows + the other ranks'
     bool sorted_valid = false;
     void* d_sort_tmp = nullptr; size_t sort_tmp_bytes = 0;
     unsigned int* d_n = nullptr;
@@ -180,16 +181,14 @@ int check_device_error(trew_ctx* ctx);
 // passes that, all in-flight batches are drained and the entries are re-inserted into a larger table (load <= 1/8).
 // The check runs once per batch, so a single batch that inserts more new keys than three quarters of the table can
 // still overflow it (TREW_ERR_TABLE_FULL: start with a larger table_log2_slots).
-int maybe_grow_table(trew_ctx* ctx) {
-    unsigned int keys = 0;
-    CK(cudaMemcpy(&keys, ctx->d_error + 1, sizeof(keys), cudaMemcpyDeviceToHost));
-    if ((size_t)keys * 4 <= ctx->n_slots || ctx->n_slots >= ((size_t)1 << 28)) return TREW_OK;
+// re-insert the table's entries into a table of at least min_slots slots (rounded up to a power of two, at most 2^28)
+int grow_table_to(trew_ctx* ctx, size_t min_slots) {
+    size_t new_slots = ctx->n_slots;
+    while (new_slots < ((size_t)1 << 28) && new_slots < min_slots) new_slots <<= 1;
+    if (new_slots == ctx->n_slots) return TREW_OK;
     uint64_t n = 0;
     int rc = export_sorted(ctx, &n);   // drains every stream, compacts into ctx->d_entries
     if (rc) return rc;
-    size_t new_slots = ctx->n_slots;
-    while (new_slots < ((size_t)1 << 28) && (size_t)n * 8 > new_slots) new_slots <<= 1;
-    if (new_slots == ctx->n_slots) return TREW_OK;
     Slot* d_new = nullptr;
     CK(cudaMalloc((void**)&d_new, new_slots * sizeof(Slot)));
     CK(cudaMemsetAsync(d_new, 0, new_slots * sizeof(Slot), ctx->main_stream));
@@ -202,6 +201,13 @@ int maybe_grow_table(trew_ctx* ctx) {
     CK(cudaFree(d_old));
     ctx->stats.kernel_launches += 1;
     return check_device_error(ctx);
+}
+
+int maybe_grow_table(trew_ctx* ctx) {
+    unsigned int keys = 0;
+    CK(cudaMemcpy(&keys, ctx->d_error + 1, sizeof(keys), cudaMemcpyDeviceToHost));
+    if ((size_t)keys * 4 <= ctx->n_slots) return TREW_OK;
+    return grow_table_to(ctx, (size_t)keys * 8);
 }
 
 int submit_ranges(trew_ctx* ctx, const ChunkView& cv, const RangeInfo* rg, int n_ranges) {
@@ -485,6 +491,7 @@ void trew_dev_destroy(trew_ctx* ctx) {
     if (ctx->d_total_surv) cudaFree(ctx->d_total_surv);
     if (ctx->d_entries) cudaFree(ctx->d_entries);
     if (ctx->d_sorted) cudaFree(ctx->d_sorted);
+    if (ctx->d_concat) cudaFree(ctx->d_concat);
     if (ctx->d_sort_tmp) cudaFree(ctx->d_sort_tmp);
     if (ctx->d_n) cudaFree(ctx->d_n);
     if (ctx->h_export) cudaFreeHost(ctx->h_export);
@@ -728,6 +735,75 @@ int trew_dev_finish(trew_ctx* ctx, const trew_entry** entries, uint64_t* n_entri
     return TREW_OK;
 }
 
+int trew_dev_finish_merged(trew_ctx* ctx, const trew_entry* const* d_lists, const uint64_t* n_rows, uint32_t n_lists,
+                           const trew_entry** entries, uint64_t* n_entries) {
+    if (!ctx || (n_lists && (!d_lists || !n_rows))) return TREW_ERR_ARG;
+    uint64_t n0 = 0;
+    const trew_entry* d_own = nullptr;
+    int rc = export_entries(ctx, false, &d_own, &n0);
+    if (rc) return rc;
+    uint64_t total = n0;
+    for (uint32_t i = 0; i < n_lists; i++) total += n_rows[i];
+    if (total > 0xfffffff0ULL) return fail(ctx, TREW_ERR_ARG, "too many rows to merge (%llu)", (unsigned long long)total);
+    // concatenate, sort, sum the counts of equal keys: the union of the tables without touching this context's table
+    auto ensure = [&](trew_entry** buf, size_t* cap) -> int {
+        if (total <= *cap) return TREW_OK;
+        if (*buf) CK(cudaFree(*buf));
+        *buf = nullptr;
+        *cap = std::max<size_t>((size_t)total + total / 4 + 1024, (size_t)1 << 20);
+        CK(cudaMalloc((void**)buf, *cap * sizeof(trew_entry)));
+        return TREW_OK;
+    };
+    if ((rc = ensure(&ctx->d_concat, &ctx->d_concat_cap)) != TREW_OK) return rc;
+    if ((rc = ensure(&ctx->d_sorted, &ctx->d_sorted_cap)) != TREW_OK) return rc;
+    ctx->sorted_valid = false;   // d_sorted is reused below
+    uint64_t at = 0;
+    if (n0) CK(cudaMemcpyAsync(ctx->d_concat, d_own, n0 * sizeof(trew_entry), cudaMemcpyDeviceToDevice, ctx->main_stream));
+    at += n0;
+    for (uint32_t i = 0; i < n_lists; i++) {
+        if (n_rows[i]) CK(cudaMemcpyAsync(ctx->d_concat + at, d_lists[i], n_rows[i] * sizeof(trew_entry), cudaMemcpyDeviceToDevice, ctx->main_stream));
+        at += n_rows[i];
+    }
+    const unsigned int n = (unsigned int)total;
+    unsigned int n_out = 0;
+    if (n) {
+        const bool wide = ctx->cfg.max_mer > 32;
+        size_t need_sort = 0, need_comb = 0;
+        CK(sort_entries_radix(ctx->d_concat, ctx->d_sorted, n, wide, nullptr, &need_sort, ctx->main_stream));
+        CK(combine_sorted_rows(ctx->d_sorted, n, ctx->d_concat, ctx->d_n, nullptr, &need_comb, ctx->main_stream));
+        const size_t need = std::max(need_sort, need_comb);
+        if (need > ctx->sort_tmp_bytes) {
+            if (ctx->d_sort_tmp) CK(cudaFree(ctx->d_sort_tmp));
+            ctx->d_sort_tmp = nullptr;
+            ctx->sort_tmp_bytes = need + need / 4;
+            CK(cudaMalloc(&ctx->d_sort_tmp, ctx->sort_tmp_bytes));
+        }
+        size_t bytes = ctx->sort_tmp_bytes;
+        CK(sort_entries_radix(ctx->d_concat, ctx->d_sorted, n, wide, ctx->d_sort_tmp, &bytes, ctx->main_stream));
+        bytes = ctx->sort_tmp_bytes;
+        CK(combine_sorted_rows(ctx->d_sorted, n, ctx->d_concat, ctx->d_n, ctx->d_sort_tmp, &bytes, ctx->main_stream));
+        CK(cudaMemcpyAsync(&n_out, ctx->d_n, sizeof(n_out), cudaMemcpyDeviceToHost, ctx->main_stream));
+        CK(cudaStreamSynchronize(ctx->main_stream));
+        ctx->stats.kernel_launches += (wide ? 11 : 8) + 3;
+    }
+    size_t need_host = (size_t)n_out * sizeof(trew_entry) + 64;
+    if (need_host > ctx->h_export_bytes) {
+        if (ctx->h_export) CK(cudaFreeHost(ctx->h_export));
+        ctx->h_export = nullptr;
+        size_t cap = std::max(need_host * 2, (size_t)1 << 20);
+        CK(cudaHostAlloc(&ctx->h_export, cap, cudaHostAllocDefault));
+        ctx->h_export_bytes = cap;
+    }
+    if (n_out) {
+        CK(cudaMemcpyAsync(ctx->h_export, ctx->d_concat, (size_t)n_out * sizeof(trew_entry), cudaMemcpyDeviceToHost, ctx->main_stream));
+        CK(cudaStreamSynchronize(ctx->main_stream));
+    }
+    ctx->stats.d2h_bytes += (uint64_t)n_out * sizeof(trew_entry) + 4;
+    if (entries) *entries = (const trew_entry*)ctx->h_export;
+    if (n_entries) *n_entries = n_out;
+    return TREW_OK;
+}
+
 int trew_dev_export_rows(trew_ctx* ctx, trew_entry* d_rows, uint64_t capacity_rows, uint64_t* n_rows) {
     if (!ctx || !n_rows) return TREW_ERR_ARG;
     uint64_t n = 0;
@@ -751,6 +827,17 @@ int trew_dev_merge_rows(trew_ctx* ctx, const trew_entry* d_rows, uint64_t n_rows
     CK(cudaGetLastError());                                                             // waits and checks the error flag
     ctx->stats.kernel_launches += n_rows ? 1 : 0;
     return TREW_OK;
+}
+
+int trew_dev_reserve(trew_ctx* ctx, uint64_t expected_new_keys) {
+    if (!ctx) return TREW_ERR_ARG;
+    int rc = trew_dev_sync(ctx);
+    if (rc) return rc;
+    unsigned int keys = 0;
+    CK(cudaMemcpy(&keys, ctx->d_error + 1, sizeof(keys), cudaMemcpyDeviceToHost));
+    const uint64_t want = ((uint64_t)keys + expected_new_keys) * 4;   // load factor <= 1/4 once they are all in
+    if (want <= ctx->n_slots) return TREW_OK;
+    return grow_table_to(ctx, (size_t)std::min<uint64_t>(want, (uint64_t)1 << 28));
 }
 
 int trew_dev_reset(trew_ctx* ctx) {

@@ -74,11 +74,13 @@ void launch_exact(const DevCfg& cfg, const DevBatch& b, const ExactArgs& a, cons
 int exact_warps_total(int sm_count);
 // table_kernels.cu
 void launch_compact(const Slot* slots, unsigned int n_slots, trew_entry* out, unsigned int* d_n, cudaStream_t stream, unsigned int cap);
-// in-place sort by (table, k, seq); call with d_temp == nullptr to query *temp_bytes
-cudaError_t sort_entries(trew_entry* d_entries, unsigned int n, void* d_temp, size_t* temp_bytes, cudaStream_t stream);
-// radix variant: sorted rows into d_out (d_entries untouched); wide = some key uses seq_hi (MAX_MER > 32)
+// sort by (table, k, seq): sorted rows into d_out (d_entries untouched); wide = some key uses seq_hi (MAX_MER > 32);
+// call with d_temp == nullptr to query *temp_bytes
 cudaError_t sort_entries_radix(const trew_entry* d_entries, trew_entry* d_out, unsigned int n, bool wide, void* d_temp,
                                size_t* temp_bytes, cudaStream_t stream);
+// sorted rows with repeated keys -> one row per key, counts summed (the union of several tables' rows)
+cudaError_t combine_sorted_rows(const trew_entry* d_sorted, unsigned int n, trew_entry* d_out, unsigned int* d_n_out, void* d_temp,
+                                size_t* temp_bytes, cudaStream_t stream);
 void launch_merge_entries(const DevCfg& cfg, const trew_entry* entries, unsigned int n, cudaStream_t stream);
 
 void launch_synth(unsigned long long seed, unsigned int n_reads, unsigned int read_len, unsigned int tel_thr,

@@ -1,12 +1,12 @@
-// Count-table export: compaction of the open-addressing table into an array of trew_entry, device-side sort by
+// Count-table export: compaction of the open-addressing table into an array of trew_entry, device-side radix sort by
 // (table, k, seq) and the cross-rank merge kernel.  Stands in for the end of buffer_task* (the six ResultMaps
 // handed to process_output, src/kmer.cpp:1486-1515).
 #include "scan_kernels.cuh"
 
 #include <algorithm>
 
-#include <cub/device/device_merge_sort.cuh>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 namespace trew {
 
@@ -35,25 +35,12 @@ __global__ void compact_kernel(const Slot* __restrict__ slots, u32 n_slots, trew
     }
 }
 
-struct EntryLess {
-    __host__ __device__ bool operator()(const trew_entry& a, const trew_entry& b) const {
-        if (a.table != b.table) return a.table < b.table;
-        if (a.k != b.k) return a.k < b.k;
-        if (a.seq_hi != b.seq_hi) return a.seq_hi < b.seq_hi;
-        return a.seq_lo < b.seq_lo;
-    }
-};
-
 void launch_compact(const Slot* slots, unsigned int n_slots, trew_entry* out, unsigned int* d_n, cudaStream_t stream, unsigned int cap) {
     // n_slots is a power of two >= 1024, so every warp iterates the same number of times
     compact_kernel<<<592, 256, 0, stream>>>(slots, n_slots, out, d_n, cap);
 }
 
-cudaError_t sort_entries(trew_entry* d_entries, unsigned int n, void* d_temp, size_t* temp_bytes, cudaStream_t stream) {
-    return cub::DeviceMergeSort::SortKeys(d_temp, *temp_bytes, d_entries, (int)n, EntryLess(), stream);
-}
-
-// ---- radix path: three stable LSD passes over (seq_lo, seq_hi, table << 8 | k) with a row index as payload, then one
+// ---- sort by (table, k, seq): three stable LSD passes over (seq_lo, seq_hi, table << 8 | k) with a row index as payload, then one
 // gather of the 32-byte rows.  Moves 12 bytes per row and pass instead of merge-sorting 32-byte rows by a comparator.
 
 __global__ void key_from_entries_kernel(const trew_entry* __restrict__ e, const u32* __restrict__ idx, u32 n, int which,
@@ -114,6 +101,49 @@ cudaError_t sort_entries_radix(const trew_entry* d_entries, trew_entry* d_out, u
     e = cub::DeviceRadixSort::SortPairs(cub_tmp, tb, k16, ix, (int)n, 0, 11, stream);
     if (e != cudaSuccess) return e;
     gather_entries_kernel<<<blocks, 256, 0, stream>>>(d_entries, ix.Current(), n, d_out);
+    return cudaGetLastError();
+}
+
+// ---- union of several tables' rows: after the sort equal keys are adjacent; the first row of every key sums its run ----
+
+__device__ __forceinline__ bool same_key(const trew_entry& a, const trew_entry& b) {
+    return a.seq_lo == b.seq_lo && a.seq_hi == b.seq_hi && a.table == b.table && a.k == b.k;
+}
+
+__global__ void head_flags_kernel(const trew_entry* __restrict__ e, u32 n, u32* __restrict__ flags) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        flags[i] = (i == 0 || !same_key(e[i], e[i - 1])) ? 1u : 0u;
+}
+
+__global__ void combine_runs_kernel(const trew_entry* __restrict__ e, u32 n, const u32* __restrict__ flags, const u32* __restrict__ pos,
+                                    trew_entry* __restrict__ out, u32* __restrict__ n_out) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (!flags[i]) continue;
+        trew_entry r = e[i];
+        for (u32 j = i + 1; j < n && !flags[j]; j++) r.count += e[j].count;
+        out[pos[i]] = r;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_out = n ? pos[n - 1] + flags[n - 1] : 0u;
+}
+
+// sorted rows with repeated keys -> one row per key with the counts summed.  d_temp == nullptr queries *temp_bytes.
+cudaError_t combine_sorted_rows(const trew_entry* d_sorted, unsigned int n, trew_entry* d_out, unsigned int* d_n_out, void* d_temp,
+                                size_t* temp_bytes, cudaStream_t stream) {
+    size_t scan_bytes = 0;
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (u32*)nullptr, (u32*)nullptr, (int)n, stream);
+    if (e != cudaSuccess) return e;
+    const size_t need = 2 * align256((size_t)n * 4) + align256(scan_bytes);
+    if (!d_temp) { *temp_bytes = need; return cudaSuccess; }
+    if (*temp_bytes < need) return cudaErrorInvalidValue;
+    char* p = (char*)d_temp;
+    u32* flags = (u32*)p; p += align256((size_t)n * 4);
+    u32* pos = (u32*)p; p += align256((size_t)n * 4);
+    const int blocks = (int)std::min<unsigned int>((n + 255) / 256, 4736u);
+    if (n) head_flags_kernel<<<blocks, 256, 0, stream>>>(d_sorted, n, flags);
+    size_t sb = align256(scan_bytes);
+    e = cub::DeviceScan::ExclusiveSum(p, sb, flags, pos, (int)n, stream);
+    if (e != cudaSuccess) return e;
+    combine_runs_kernel<<<n ? blocks : 1, 256, 0, stream>>>(d_sorted, n, flags, pos, d_out, d_n_out);
     return cudaGetLastError();
 }
 

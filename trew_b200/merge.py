@@ -81,7 +81,31 @@ def merge_device(ctx, device: torch.device, dst: int = 0) -> None:
     dist.gather(rows, gathered, dst=dst)
     if rank == dst:
         torch.cuda.synchronize(device)
+        ctx.reserve(sum(sizes[r] for r in range(world) if r != dst))   # the union can be world x the local table
         for r in range(world):
             if r != dst and sizes[r]:
                 ctx.merge_rows(gathered[r].data_ptr(), sizes[r])   # asynchronous on the context's stream
         ctx.sync()   # the gathered buffers must outlive the merge kernels
+
+
+def finish_merged(ctx, device: torch.device, dst: int = 0):
+    """End-of-file merge without touching the count tables: every rank copies its compacted rows into a padded
+    device buffer, the buffers are gathered to rank `dst` over NCCL, and `dst` forms the union on the device
+    (concatenate, radix sort, sum equal keys: trew_dev_finish_merged) and copies it to the host.  Returns the merged
+    entries (structured numpy view, sorted by (table, k, seq)) on `dst`, None elsewhere."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return ctx.finish_view()
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n = ctx.export_rows()
+    all_n = torch.zeros(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(all_n, torch.tensor([n], dtype=torch.int64, device=device))
+    sizes = all_n.tolist()
+    n_max = max(max(sizes), 1)
+    rows = torch.empty((n_max, 4), dtype=torch.int64, device=device)
+    ctx.export_rows(rows.data_ptr(), n_max)
+    gathered = [torch.empty_like(rows) for _ in range(world)] if rank == dst else None
+    dist.gather(rows, gathered, dst=dst)
+    if rank != dst:
+        return None
+    torch.cuda.synchronize(device)
+    return ctx.finish_merged_view([(gathered[r].data_ptr(), sizes[r]) for r in range(world) if r != dst])
