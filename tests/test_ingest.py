@@ -85,3 +85,41 @@ def test_bundled_fixtures(name, mode):
     data = (gzip.open(p) if name.endswith(".gz") else open(p, "rb")).read()
     rc, _, r1, _ = api.ingest_records(mode, p, chunk_bytes=4096)
     assert rc == 0 and r1 == py_records(data)
+
+
+def bgzf_bytes(data: bytes, block: int = 65280) -> bytes:
+    """BGZF (bgzip) container: independent gzip members of at most 64 KiB with a 'BC' extra field + the EOF member."""
+    import struct
+    import zlib
+    out = bytearray()
+    for i in list(range(0, len(data), block)) + [None]:
+        chunk = b"" if i is None else data[i:i + block]
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = c.compress(chunk) + c.flush()
+        bsize = 12 + 6 + len(body) + 8
+        out += b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", bsize - 1)
+        out += body + struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk))
+    return bytes(out)
+
+
+@pytest.mark.parametrize("chunk", [64, 5000, 70000, 0])
+@pytest.mark.parametrize("block", [700, 65280])
+def test_bgzf_blocks_inflate_in_parallel(tmp_path, chunk, block):
+    reads = synth.adversarial_short(6, 1500)
+    data = synth.fastq_bytes(reads)
+    raw = bgzf_bytes(data, block)
+    assert gzip.decompress(raw) == data            # a valid multi-member gzip file as far as zlib is concerned
+    p = os.path.join(tmp_path, "a.fastq.bgz")
+    open(p, "wb").write(raw)
+    rc, msg, r1, _ = api.ingest_records(api.MODE_SHORT, p, chunk_bytes=chunk)
+    assert rc == 0, msg
+    assert r1 == reads
+
+
+def test_truncated_bgzf_is_an_io_error(tmp_path):
+    data = synth.fastq_bytes(synth.adversarial_short(7, 400))
+    raw = bgzf_bytes(data, 3000)
+    p = os.path.join(tmp_path, "a.fastq.gz")
+    open(p, "wb").write(raw[:len(raw) // 2 + 7])
+    rc, msg, _, _ = api.ingest_records(api.MODE_SHORT, p)
+    assert rc == 5 and "IO Error" in msg

@@ -47,18 +47,157 @@ struct Reader {
     gzFile gfp = nullptr;
     uint64_t offset = 0;    // plain files: next byte to read
     int64_t size = -1;      // plain regular files: total size, else -1
+    // BGZF (bgzip) files are a series of independent gzip members of at most 64 KiB, each announcing its compressed
+    // size in a 'BC' extra field: the members of a batch are inflated in parallel.  Plain gzip stays on zlib's gzread.
+    bool bgzf = false;
+    std::vector<unsigned char> cbuf;   // window of the compressed file
+    uint64_t cbuf_off = 0;             // file offset of cbuf[0]
+    std::vector<char> pending;         // inflated bytes not yet handed out (a block that did not fit the caller's buffer)
+    size_t pending_pos = 0;
+
+    static bool bgzf_header(const unsigned char* p, size_t avail, uint32_t* bsize, uint32_t* hdr_len) {
+        if (avail < 18 || p[0] != 31 || p[1] != 139 || p[2] != 8 || !(p[3] & 4)) return false;
+        const uint32_t xlen = p[10] | ((uint32_t)p[11] << 8);
+        if (avail < 12 + xlen) return false;
+        for (uint32_t q = 12; q + 4 <= 12 + xlen;) {
+            const uint32_t slen = p[q + 2] | ((uint32_t)p[q + 3] << 8);
+            if (p[q] == 'B' && p[q + 1] == 'C' && slen == 2 && q + 6 <= 12 + xlen) {
+                *bsize = (p[q + 4] | ((uint32_t)p[q + 5] << 8)) + 1u;
+                *hdr_len = 12 + xlen;
+                return *bsize >= *hdr_len + 8;
+            }
+            q += 4 + slen;
+        }
+        return false;
+    }
+
     bool open(const char* name, bool is_gz) {
         gz = is_gz;
-        if (gz) { gfp = gzopen(name, "r"); if (gfp) gzbuffer(gfp, 1 << 20); return gfp != nullptr; }
+        if (gz) {
+            int probe = ::open(name, O_RDONLY);
+            if (probe >= 0) {
+                unsigned char h[64];
+                ssize_t got = pread(probe, h, sizeof(h), 0);
+                struct stat st;
+                uint32_t bs, hl;
+                if (got >= 18 && bgzf_header(h, (size_t)got, &bs, &hl) && fstat(probe, &st) == 0 && S_ISREG(st.st_mode) &&
+                    !getenv("TREW_NO_BGZF")) {
+                    bgzf = true; fd = probe; size = (int64_t)st.st_size;
+                    return true;
+                }
+                ::close(probe);
+            }
+            gfp = gzopen(name, "r");
+            if (gfp) gzbuffer(gfp, 1 << 20);
+            return gfp != nullptr;
+        }
         fd = ::open(name, O_RDONLY);
         if (fd < 0) return false;
         struct stat st;
         if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) size = (int64_t)st.st_size;
         return true;
     }
+
+    struct BgzfBlock { const unsigned char* cdata; uint32_t clen, isize; size_t out_off; };
+
+    static bool inflate_blocks(const BgzfBlock* blk, size_t n, char* out) {
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) return false;
+        bool ok = true;
+        for (size_t i = 0; i < n && ok; i++) {
+            if (blk[i].isize == 0) continue;
+            inflateReset(&zs);
+            zs.next_in = const_cast<unsigned char*>(blk[i].cdata); zs.avail_in = blk[i].clen;
+            zs.next_out = (unsigned char*)out + blk[i].out_off; zs.avail_out = blk[i].isize;
+            int rc = inflate(&zs, Z_FINISH);
+            ok = rc == Z_STREAM_END && zs.avail_out == 0;
+        }
+        inflateEnd(&zs);
+        return ok;
+    }
+
+    // make sure cbuf holds the whole block that starts at file offset `offset` (or as much as the file has)
+    bool bgzf_window(size_t want_bytes) {
+        if (offset >= cbuf_off && offset + 65536 + 64 <= cbuf_off + cbuf.size()) return true;
+        size_t len = (size_t)std::min<uint64_t>(std::max<size_t>(want_bytes, (size_t)1 << 20), (uint64_t)size - offset);
+        cbuf.resize(len);
+        cbuf_off = offset;
+        size_t a = 0;
+        while (a < len) {
+            ssize_t r = pread(fd, cbuf.data() + a, len - a, (off_t)(cbuf_off + a));
+            if (r < 0) { if (errno == EINTR) continue; return false; }
+            if (r == 0) { cbuf.resize(a); break; }
+            a += (size_t)r;
+        }
+        return true;
+    }
+
+    long read_bgzf(char* buf, size_t n, Pool* pool) {
+        size_t done = 0;
+        if (pending_pos < pending.size()) {
+            size_t m = std::min(n, pending.size() - pending_pos);
+            memcpy(buf, pending.data() + pending_pos, m);
+            pending_pos += m; done = m;
+            if (pending_pos == pending.size()) { pending.clear(); pending_pos = 0; }
+        }
+        while (done < n && offset < (uint64_t)size) {
+            if (!bgzf_window(n / 2 + ((size_t)4 << 20))) return -1;
+            // plan the blocks of this window that fit the caller's buffer
+            std::vector<BgzfBlock> plan;
+            uint64_t off = offset;
+            size_t out = done;
+            bool spill = false;
+            while (off < cbuf_off + cbuf.size()) {
+                const unsigned char* p = cbuf.data() + (off - cbuf_off);
+                const size_t avail = (size_t)(cbuf_off + cbuf.size() - off);
+                uint32_t bs = 0, hl = 0;
+                if (!bgzf_header(p, avail, &bs, &hl)) { if (avail < 18 + 65536 && off + avail < (uint64_t)size) break; return -1; }
+                if (bs > avail) { if (off + avail >= (uint64_t)size) return -1; break; }   // the block continues beyond the window
+                const uint32_t isize = p[bs - 4] | ((uint32_t)p[bs - 3] << 8) | ((uint32_t)p[bs - 2] << 16) | ((uint32_t)p[bs - 1] << 24);
+                if (isize > 65536) return -1;
+                if (out + isize > n) { spill = plan.empty(); break; }
+                plan.push_back(BgzfBlock{p + hl, bs - hl - 8, isize, out});
+                out += isize; off += bs;
+            }
+            if (!plan.empty()) {
+                const int P = pool ? std::min<int>(pool->size(), (int)(plan.size() / 8) + 1) : 1;
+                std::vector<char> okv((size_t)P, 1);
+                auto work = [&](int i) {
+                    size_t a = plan.size() * (size_t)i / (size_t)P, b = plan.size() * (size_t)(i + 1) / (size_t)P;
+                    okv[(size_t)i] = inflate_blocks(plan.data() + a, b - a, buf) ? 1 : 0;
+                };
+                if (P > 1) pool->run(P, work); else work(0);
+                for (char o : okv) if (!o) return -1;
+                done = out; offset = off;
+            } else if (spill) {
+                // the next block alone is larger than what is left of the caller's buffer: inflate it aside
+                const unsigned char* p = cbuf.data() + (offset - cbuf_off);
+                uint32_t bs = 0, hl = 0;
+                if (!bgzf_header(p, (size_t)(cbuf_off + cbuf.size() - offset), &bs, &hl)) return -1;
+                const uint32_t isize = p[bs - 4] | ((uint32_t)p[bs - 3] << 8) | ((uint32_t)p[bs - 2] << 16) | ((uint32_t)p[bs - 1] << 24);
+                pending.resize(isize); pending_pos = 0;
+                BgzfBlock one{p + hl, bs - hl - 8, isize, 0};
+                if (!inflate_blocks(&one, 1, pending.data())) return -1;
+                offset += bs;
+                size_t m = std::min(n - done, pending.size());
+                memcpy(buf + done, pending.data(), m);
+                pending_pos = m; done += m;
+                if (pending_pos == pending.size()) { pending.clear(); pending_pos = 0; }
+                break;
+            } else {
+                if (done > 0) break;       // nothing more fits: hand out what we have
+                if (cbuf_off + cbuf.size() >= (uint64_t)size) return -1;   // truncated file
+                cbuf.clear(); cbuf_off = 0;   // force a larger window from `offset`
+            }
+        }
+        return (long)done;
+    }
+
     // returns bytes read (0 at EOF), -1 on error.  Plain regular files are read with pread in parallel slices when a
     // pool is given and the request is large (the copy out of the page cache is the cost, and it scales with cores).
     long read(char* buf, size_t n, Pool* pool, size_t par_min) {
+        if (bgzf) return read_bgzf(buf, std::min<size_t>(n, (size_t)1 << 30), pool);
         if (gz) {
             int r = gzread(gfp, buf, (unsigned)std::min<size_t>(n, 1u << 30));
             return r < 0 ? -1 : r;
@@ -90,10 +229,16 @@ struct Reader {
         }
     }
     std::string error() {
+        if (bgzf) return "malformed BGZF block";
         if (gz) { int e; return gzerror(gfp, &e); }
         return strerror(errno);
     }
-    void close() { if (gz) { if (gfp) gzclose(gfp); gfp = nullptr; } else { if (fd >= 0) ::close(fd); fd = -1; } }
+    void close() {
+        if (gfp) gzclose(gfp);
+        gfp = nullptr;
+        if (fd >= 0) ::close(fd);
+        fd = -1;
+    }
     ~Reader() { close(); }
 };
 

@@ -334,3 +334,19 @@ def device_mirror(seed: int, n_reads: int, read_len: int = 150, tel_ppm: int = 1
     inval = _synth_hash(seed ^ 0xaaaaaaaaaaaaaaaa, r, j).astype(np.uint64) < thr(n_ppm)
     letters = np.frombuffer(b"TGCA", dtype=np.uint8)[code.astype(np.int64)]
     return np.where(inval, np.uint8(ord("N")), letters).astype(np.uint8)
+
+
+def bgzf_write(src_path: str, dst_path: str, level: int = 1, block: int = 65280) -> None:
+    """Re-write a file as BGZF (bgzip): independent gzip members of at most 64 KiB with the 'BC' extra field,
+    terminated by the empty EOF member.  Benchmark / test tooling."""
+    import struct
+    import zlib
+    with open(src_path, "rb") as src, open(dst_path, "wb") as dst:
+        while True:
+            chunk = src.read(block)
+            c = zlib.compressobj(level, zlib.DEFLATED, -15)
+            body = c.compress(chunk) + c.flush()
+            dst.write(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", 12 + 6 + len(body) + 8 - 1))
+            dst.write(body + struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk)))
+            if not chunk:
+                break
