@@ -205,6 +205,18 @@ size_t trew_pack_bound(uint32_t n_reads, uint64_t total_bases);
 int trew_pack_reads(const char* buffer, const int32_t* locs, uint32_t n, void* dst, size_t dst_bytes,
                     trew_batch* out);
 
+/* The same batch, packed the way trew_dev_submit_chunk fills a staging slot: the reads are cut into n_ranges
+ * consecutive ranges that n_threads host threads pack concurrently (a range may start in the middle of a plane
+ * word; the shared words are stitched afterwards).  With inv != NULL the bit positions of the bases that are not
+ * A/C/G/T (the zero bits of the val plane below bit_off[n]) are also listed, in no particular order: *n_inv is
+ * their number, and at most inv_cap of them are stored.  The streaming path sends this list instead of the val
+ * plane when it is short, and then does not write the plane either: TREW_PACK_NO_VAL in `flags` (needs inv) asks
+ * for the same -- the contents of out->val are then unspecified. */
+#define TREW_PACK_NO_VAL 1u
+int trew_pack_reads_ranges(const char* buffer, const int32_t* locs, uint32_t n, uint32_t n_ranges, uint32_t n_threads,
+                           uint32_t flags, void* dst, size_t dst_bytes, trew_batch* out, uint32_t* inv, size_t inv_cap,
+                           size_t* n_inv);
+
 /* ---- whole-file convenience: process_kmer / _pair / _long (src/kmer.cpp:1266-1476) -------------- */
 
 /* Reads FASTQ / FASTQ.gz with the reference's record semantics (every 4k+2-th line is a sequence,

@@ -47,3 +47,42 @@ def test_pack_matrix_chunk_equals_list_chunk():
     b1, l1 = api.matrix_chunk(mat)
     b2, l2 = api.make_chunk([bytes(r) for r in mat])
     assert bytes(b1) == bytes(b2) and (l1 == l2).all()
+
+
+@pytest.mark.parametrize("simd", ["0", "1", "2"])
+@pytest.mark.parametrize("n_ranges,n_threads", [(1, 1), (7, 1), (64, 4), (5000, 3)])
+def test_pack_ranges_equal_single_pass_and_list_the_invalid_bases(simd, n_ranges, n_threads):
+    """The concurrent range packer (what a staging slot is filled with) produces the same planes as the
+    single-threaded one for every cut of the reads, and its list is exactly the zero bits of the val plane."""
+    import subprocess, sys, textwrap
+    # simd_level() is latched on first use, so each instruction set runs in its own interpreter
+    code = textwrap.dedent("""
+        import numpy as np
+        from trew_b200 import api, synth
+        rng = np.random.default_rng(5)
+        reads = synth.adversarial_short(3, 400)
+        reads += [b"", b"N", b"", b"acgtnN\\r", b"A" * 31, b"N" * 64, b"C" * 65, b"T" * 128, b"TTAGGN" * 170, b""]
+        for _ in range(300):
+            L = int(rng.integers(0, 400))
+            r = rng.choice(np.frombuffer(b"ACGTNacgtn.", dtype=np.uint8), size=L, p=[.22, .22, .22, .22, .04, .02, .02, .01, .01, .01, .01])
+            reads.append(bytes(r))
+        buf, locs = api.make_chunk(reads)
+        ref = api.PackedBatch(buf, locs)
+        got = api.PackedBatch(buf, locs, n_ranges=%d, n_threads=%d, want_invalid=True)
+        for a, b in zip(ref.planes(), got.planes()):
+            assert (a == b).all()
+        val = ref.planes()[3]
+        bits = np.unpackbits(val.view(np.uint8), bitorder="little")[:ref.bases]
+        want = np.flatnonzero(bits == 0)
+        assert sorted(got.invalid.tolist()) == want.tolist(), (len(got.invalid), len(want))
+        # TREW_PACK_NO_VAL (what the streaming path asks for): same offsets, code planes and list; val unspecified
+        lean = api.PackedBatch(buf, locs, n_ranges=%d, n_threads=%d, want_invalid=True, no_val=True)
+        for a, b in zip(ref.planes()[:3], lean.planes()[:3]):
+            assert (a == b).all()
+        assert sorted(lean.invalid.tolist()) == want.tolist()
+        print("ok")
+    """ % (n_ranges, n_threads, n_ranges, n_threads))
+    import os
+    env = dict(os.environ, TREW_PACK_SIMD=simd)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(__file__)))
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]

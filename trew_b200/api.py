@@ -65,6 +65,7 @@ ABI_SYMBOLS = [
     "trew_synth_resident", "trew_dev_timer_start", "trew_dev_timer_stop", "trew_dev_kernel_times",
     "trew_dev_process_file", "trew_ingest_file", "trew_report_create", "trew_report_destroy", "trew_report_add_file",
     "trew_report_finish", "trew_dev_export_rows", "trew_dev_merge_rows", "trew_dev_reserve", "trew_dev_finish_merged",
+    "trew_pack_reads_ranges",
 ]
 
 CHUNK_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_uint32, C.c_void_p,
@@ -108,6 +109,8 @@ def load_library() -> C.CDLL:
     L.trew_pack_bound.argtypes = [C.c_uint32, C.c_uint64]
     L.trew_pack_bound.restype = C.c_size_t
     L.trew_pack_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(Batch)]
+    L.trew_pack_reads_ranges.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t,
+                                         C.POINTER(Batch), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.trew_dev_process_file.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
     L.trew_synth_resident.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                       C.c_uint32, C.POINTER(C.c_void_p)]
@@ -155,7 +158,10 @@ def matrix_chunk(mat: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
 class PackedBatch:
     """A packed batch in host memory (owner of the buffer the trew_batch pointers point into)."""
 
-    def __init__(self, buf: np.ndarray, locs: np.ndarray):
+    def __init__(self, buf: np.ndarray, locs: np.ndarray, n_ranges: int = 0, n_threads: int = 1, want_invalid: bool = False,
+                 no_val: bool = False):
+        """n_ranges > 0 packs through trew_pack_reads_ranges (concurrent ranges, optional invalid-base list in
+        self.invalid, no_val = TREW_PACK_NO_VAL); otherwise through the single-threaded trew_pack_reads."""
         L = load_library()
         buf = np.ascontiguousarray(buf, dtype=np.uint8)
         locs = np.ascontiguousarray(locs, dtype=np.int32).reshape(-1, 2)
@@ -166,7 +172,18 @@ class PackedBatch:
         self.nbytes = L.trew_pack_bound(n, self.bases)
         self.mem = np.zeros(self.nbytes, dtype=np.uint8)
         self.batch = Batch()
-        rc = L.trew_pack_reads(buf.ctypes.data, locs.ctypes.data, n, self.mem.ctypes.data, self.nbytes, C.byref(self.batch))
+        self.invalid = None
+        if n_ranges > 0:
+            cap = self.bases + 64 if want_invalid else 0
+            inv = np.zeros(max(cap, 1), dtype=np.uint32)
+            n_inv = C.c_size_t(0)
+            rc = L.trew_pack_reads_ranges(buf.ctypes.data, locs.ctypes.data, n, n_ranges, n_threads, 1 if no_val else 0, self.mem.ctypes.data,
+                                          self.nbytes, C.byref(self.batch), inv.ctypes.data if want_invalid else None, cap,
+                                          C.byref(n_inv))
+            if want_invalid and not rc:
+                self.invalid = inv[:n_inv.value].copy()
+        else:
+            rc = L.trew_pack_reads(buf.ctypes.data, locs.ctypes.data, n, self.mem.ctypes.data, self.nbytes, C.byref(self.batch))
         if rc:
             raise TrewError(rc, L.trew_status_string(rc).decode())
 

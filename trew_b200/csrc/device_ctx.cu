@@ -25,6 +25,9 @@ namespace {
 struct SlotRes {
     void* h_buf = nullptr;      // pinned
     void* d_buf = nullptr;
+    unsigned char* h_inv = nullptr;  // pinned: the batch's invalid-base records (sparse validity, see submit_ranges)
+    unsigned char* d_inv = nullptr;
+    size_t inv_cap = 0;              // records
     unsigned int* d_survivors = nullptr;
     unsigned int* d_counters = nullptr;  // [0] n_survivors [1] work counter [2] n_deferred
     unsigned char* d_scratch = nullptr;
@@ -84,6 +87,8 @@ struct trew_ctx {
     Pool* pool = nullptr;
     std::string err;
     std::vector<RangeInfo> ranges_tmp;
+    bool sparse_val = true;                      // TREW_DENSE_VAL=1: always copy the validity plane
+    std::vector<InvList> inv_tmp;                // per packing range: records of its blocks with invalid bases
     IngestScratch ingest;   // file block buffers, kept across files
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     double screen_ms = 0, decide_ms = 0, exact_ms = 0; uint64_t n_prof_scans = 0;
@@ -225,27 +230,69 @@ int submit_ranges(trew_ctx* ctx, const ChunkView& cv, const RangeInfo* rg, int n
     std::vector<uint64_t> bit0((size_t)n_ranges);
     uint64_t acc = 0;
     for (int i = 0; i < n_ranges; i++) { bit0[i] = acc; acc += rg[i].bases; }
-    pack_prepare(bit0.data(), n_ranges, total_bases, v);
     v.bit_off[n] = (uint32_t)total_bases;
     const uint32_t first = rg[0].r0;
     std::vector<uint64_t> side_flat((size_t)3 * n_ranges);
     uint64_t (*side)[3] = (uint64_t (*)[3])side_flat.data();
-    ctx->pool->run(n_ranges, [&](int i) { pack_chunk_range(cv, rg[i].r0, rg[i].r1, rg[i].r0 - first, bit0[i], v, side[i]); });
-    pack_fixup(bit0.data(), side, n_ranges, v);
+    // Validity travels as a list when it is sparse (it nearly always is: a few N per thousand bases at most): the
+    // packers record the 64-base blocks whose validity mask is not all ones (position + mask, 12 bytes) instead of
+    // writing the val plane, only [bit_off | hi | lo] and the records cross PCIe, and the device plane is a memset
+    // plus a scatter.  A batch with more such blocks than the record buffer holds is packed again with its val
+    // plane and copied whole.
+    if (ctx->inv_tmp.size() < (size_t)n_ranges) ctx->inv_tmp.resize((size_t)n_ranges);
+    auto pack = [&](bool list) {
+        pack_prepare(bit0.data(), n_ranges, total_bases, v);
+        ctx->pool->run(n_ranges, [&](int i) {
+            pack_chunk_range(cv, rg[i].r0, rg[i].r1, rg[i].r0 - first, bit0[i], v, side[i], list ? &ctx->inv_tmp[(size_t)i] : nullptr, list,
+                             rg[i].bases);
+        });
+        pack_fixup(bit0.data(), side, n_ranges, v);
+    };
+    size_t n_inv = 0;
+    bool sparse = ctx->sparse_val;
+    pack(sparse);
+    const bool tail_pad = (total_bases & 31) != 0;   // the padding bits of the last plane word are "invalid" too
+    if (sparse) {
+        n_inv = tail_pad ? 1 : 0;
+        for (int i = 0; i < n_ranges; i++) n_inv += ctx->inv_tmp[(size_t)i].size();
+        if (n_inv > s.inv_cap) { sparse = false; pack(false); }
+    }
 
     CK(cudaEventRecord(s.ev_start, s.stream));
-    CK(cudaMemcpyAsync(s.d_buf, s.h_buf, v.bytes, cudaMemcpyHostToDevice, s.stream));
+    const size_t head_bytes = (size_t)((char*)v.val - (char*)s.h_buf);
+    unsigned int* d_val = (unsigned int*)((char*)s.d_buf + head_bytes);
+    size_t sent = v.bytes;
+    if (sparse) {
+        unsigned char* dst = s.h_inv;
+        for (int i = 0; i < n_ranges; i++) {
+            const InvList& l = ctx->inv_tmp[(size_t)i];
+            if (l.bytes()) { memcpy(dst, l.buf.get(), l.bytes()); dst += l.bytes(); }
+        }
+        if (tail_pad) inv_record(dst, (uint32_t)total_bases, (1ULL << (32 - (total_bases & 31))) - 1ULL);
+        const size_t ones_words = (size_t)((total_bases + 31) / 32);
+        CK(cudaMemsetAsync(d_val, 0xFF, ones_words * 4, s.stream));
+        CK(cudaMemsetAsync(d_val + ones_words, 0, (v.plane_words - ones_words) * 4, s.stream));
+        CK(cudaMemcpyAsync(s.d_buf, s.h_buf, head_bytes, cudaMemcpyHostToDevice, s.stream));
+        if (n_inv) {
+            CK(cudaMemcpyAsync(s.d_inv, s.h_inv, n_inv * kInvRecBytes, cudaMemcpyHostToDevice, s.stream));
+            launch_clear_invalid(d_val, (const unsigned int*)s.d_inv, (unsigned int)n_inv, s.stream);
+            ctx->stats.kernel_launches += 1;
+        }
+        sent = head_bytes + n_inv * kInvRecBytes;
+    } else {
+        CK(cudaMemcpyAsync(s.d_buf, s.h_buf, v.bytes, cudaMemcpyHostToDevice, s.stream));
+    }
     DevBatch b{};
     b.n_reads = n;
     b.bit_off = (const unsigned int*)s.d_buf;
     b.hi = (const unsigned int*)((char*)s.d_buf + ((char*)v.hi - (char*)s.h_buf));
-    b.lo = b.hi + v.plane_words; b.val = b.lo + v.plane_words;
+    b.lo = b.hi + v.plane_words; b.val = d_val;
     uint32_t n_units = ctx->cfg.mode == TREW_MODE_PAIR ? n / 2 : n;
     rc = launch_scan(ctx, b, n_units, max_len, s.d_survivors, s.d_counters, &s.d_scratch, &s.scratch_bytes, s.stream);
     if (rc) return rc;
     CK(cudaEventRecord(s.ev_done, s.stream));
     s.in_flight = true;
-    ctx->stats.reads += n; ctx->stats.bases += total_bases; ctx->stats.units += n_units; ctx->stats.h2d_bytes += v.bytes;
+    ctx->stats.reads += n; ctx->stats.bases += total_bases; ctx->stats.units += n_units; ctx->stats.h2d_bytes += sent;
     return TREW_OK;
 }
 
@@ -423,6 +470,7 @@ int trew_dev_create(const trew_config* cfg, trew_ctx** out) {
         if ((v = env_int("TREW_GRID_DECIDE", 0)) > 0) ctx->plan.decide_blocks = std::min(ctx->plan.decide_blocks, ctx->sm_count * v);
         if ((v = env_int("TREW_GRID_EXACT", 0)) > 0) ctx->plan.exact_blocks = std::min(ctx->plan.exact_blocks, ctx->sm_count * v);
         ctx->resident_streams = env_int("TREW_RESIDENT_STREAMS", 1) >= 2 ? 2 : 1;
+        ctx->sparse_val = env_int("TREW_DENSE_VAL", 0) == 0;
     }
     int lg = cfg->table_log2_slots > 0 ? cfg->table_log2_slots : 22;
     if (lg < 10 || lg > 28) { fail(ctx, TREW_ERR_ARG, "table_log2_slots out of range"); return bail(TREW_ERR_ARG); }
@@ -456,6 +504,9 @@ int trew_dev_create(const trew_config* cfg, trew_ctx** out) {
     for (auto& s : ctx->slots) {
         CKC(cudaHostAlloc(&s.h_buf, ctx->staging_bytes, cudaHostAllocDefault));
         CKC(cudaMalloc(&s.d_buf, ctx->staging_bytes));
+        s.inv_cap = ctx->staging_bytes / 8 / kInvRecBytes;   // 1/8 of the slot: past that the dense plane is no larger
+        CKC(cudaHostAlloc((void**)&s.h_inv, (s.inv_cap + 1) * kInvRecBytes, cudaHostAllocDefault));
+        CKC(cudaMalloc((void**)&s.d_inv, (s.inv_cap + 1) * kInvRecBytes));
         s.survivors_cap = ctx->staging_bytes / 8;  // >= reads of >= 11 bases; submit_split enforces it
         CKC(cudaMalloc((void**)&s.d_survivors, 2 * s.survivors_cap * sizeof(unsigned int)));
         CKC(cudaMalloc((void**)&s.d_counters, 4 * sizeof(unsigned int)));
@@ -478,6 +529,8 @@ void trew_dev_destroy(trew_ctx* ctx) {
     for (auto& s : ctx->slots) {
         if (s.h_buf) cudaFreeHost(s.h_buf);
         if (s.d_buf) cudaFree(s.d_buf);
+        if (s.h_inv) cudaFreeHost(s.h_inv);
+        if (s.d_inv) cudaFree(s.d_inv);
         if (s.d_survivors) cudaFree(s.d_survivors);
         if (s.d_counters) cudaFree(s.d_counters);
         if (s.d_scratch) cudaFree(s.d_scratch);

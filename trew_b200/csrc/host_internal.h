@@ -3,7 +3,9 @@
 #include <condition_variable>
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -44,8 +46,34 @@ void pack_prepare(const uint64_t* range_bit0, int n_ranges, uint64_t total_bases
 // Pack reads [r0, r1) of the chunk as reads out0 .. of the batch, the first base at bit position bit0: writes
 // bit_off[out0 ..] and the three planes.  Ranges may be packed concurrently: the bits that fall into the range's
 // first 64-bit unit (possibly shared with the previous range) are returned in side[] instead of being stored.
+// Sparse validity: instead of the val plane a packer can emit one 12-byte record (u32 bit position of a 64-base
+// block, u64 mask of its invalid bases) per block that holds any base other than A/C/G/T.  Appending is branch-free
+// -- the record is always written and the cursor advances only when the mask is non-zero -- so the cost does not
+// depend on how the N's are spread; the buffer is sized for the worst case (every block) up front.
+constexpr size_t kInvRecBytes = 12;
+inline unsigned char* inv_record(unsigned char* p, uint32_t pos, uint64_t z) {
+    memcpy(p, &pos, 4);
+    memcpy(p + 4, &z, 8);
+    return p + kInvRecBytes * (size_t)(z != 0);
+}
+struct InvList {
+    std::unique_ptr<unsigned char[]> buf;
+    size_t cap = 0;              // records
+    unsigned char* p = nullptr;  // write cursor
+    void start(size_t max_records) {
+        if (max_records + 1 > cap) { cap = max_records + 1; buf.reset(new unsigned char[cap * kInvRecBytes]); }
+        p = buf.get();
+    }
+    void put(uint32_t pos, uint64_t z) { p = inv_record(p, pos, z); }
+    size_t size() const { return p ? (size_t)(p - buf.get()) / kInvRecBytes : 0; }
+    size_t bytes() const { return size() * kInvRecBytes; }
+    void get(size_t i, uint32_t* pos, uint64_t* z) const { memcpy(pos, buf.get() + i * kInvRecBytes, 4); memcpy(z, buf.get() + i * kInvRecBytes + 4, 8); }
+};
+// With inv != nullptr the range's blocks with invalid bases are recorded there (positions are plane bit
+// coordinates); skip_val (needs inv) additionally allows the packer to leave the val plane unwritten where that
+// saves work.  range_bases = the bases of reads [r0, r1) (sizes the record buffer).
 void pack_chunk_range(const ChunkView& cv, uint32_t r0, uint32_t r1, uint32_t out0, uint64_t bit0, const BatchView& v,
-                      uint64_t side[3]);
+                      uint64_t side[3], InvList* inv, bool skip_val, uint64_t range_bases);
 // After all ranges are packed: OR every range's side bits into its first unit (single-threaded, n_ranges items).
 void pack_fixup(const uint64_t* range_bit0, const uint64_t (*side)[3], int n_ranges, const BatchView& v);
 

@@ -11,6 +11,18 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
+
+#ifndef TREW_PACK_PREFETCH
+// Bytes ahead of the current read that the SIMD packers prefetch into L1 (0 = off).  The packers stream ~150 B per
+// read in and 56 B out on every core; alone, the hardware prefetchers keep a core at ~5 GB/s of input on the
+// B200 hosts measured, and an explicit prefetch 2-8 KB ahead shortens a 1 M-read batch from 1.9 to 1.3 ms on 16
+// cores (host packer).
+#define TREW_PACK_PREFETCH 3072
+#endif
+#ifndef TREW_PACK_PREFETCH_HINT
+#define TREW_PACK_PREFETCH_HINT _MM_HINT_T0
+#endif
 
 #if defined(__x86_64__)
 #include <immintrin.h>
@@ -91,26 +103,36 @@ struct BitWriter {
 };
 
 template <bool PEEL>
-inline void pack_read_scalar(BitWriter& w, const unsigned char* s, uint32_t len) {
+inline void pack_read_scalar(BitWriter& w, const unsigned char* s, uint32_t len, uint32_t rpos, InvList* inv) {
     uint64_t h, l, v;
     uint32_t i = 0;
-    for (; i + 64 <= len; i += 64) { masks_scalar(s + i, 64, h, l, v); w.put<true, PEEL>(h, l, v, 64); }
-    if (i < len) { masks_scalar(s + i, (int)(len - i), h, l, v); w.put<false, PEEL>(h, l, v, (int)(len - i)); }
+    for (; i + 64 <= len; i += 64) {
+        masks_scalar(s + i, 64, h, l, v);
+        if (inv) inv->put(rpos + i, ~v);
+        w.put<true, PEEL>(h, l, v, 64);
+    }
+    if (i < len) {
+        masks_scalar(s + i, (int)(len - i), h, l, v);
+        const uint64_t keep = (1ULL << (len - i)) - 1ULL;
+        if (inv) inv->put(rpos + i, ~v & keep);
+        w.put<false, PEEL>(h, l, v, (int)(len - i));
+    }
 }
 
-void pack_reads_scalar(const ChunkView& cv, uint32_t r0, uint32_t r1, uint32_t* off, uint64_t pos, BitWriter& w_out) {
+void pack_reads_scalar(const ChunkView& cv, uint32_t r0, uint32_t r1, uint32_t* off, uint64_t pos, BitWriter& w_out,
+                       InvList* inv) {
     BitWriter w = w_out;  // local copy: its address never escapes, so the state stays in registers across the plane stores
     const char* p; uint32_t len; size_t slack;
     uint32_t r = r0;
     for (; r < r1 && w.peeling(); r++) {
         cv.get(r, p, len, slack);
         *off++ = (uint32_t)pos; pos += len;
-        pack_read_scalar<true>(w, (const unsigned char*)p, len);
+        pack_read_scalar<true>(w, (const unsigned char*)p, len, (uint32_t)pos - len, inv);
     }
     for (; r < r1; r++) {
         cv.get(r, p, len, slack);
         *off++ = (uint32_t)pos; pos += len;
-        pack_read_scalar<false>(w, (const unsigned char*)p, len);
+        pack_read_scalar<false>(w, (const unsigned char*)p, len, (uint32_t)pos - len, inv);
     }
     w_out = w;
 }
@@ -134,13 +156,16 @@ TREW_AVX2 __attribute__((always_inline)) inline void masks_avx2(const unsigned c
 
 template <bool PEEL>
 TREW_AVX2 __attribute__((always_inline)) inline void pack_read_avx2(BitWriter& w, const unsigned char* s, uint32_t len, size_t slack,
-                                                                    __m256i lut, __m256i case_bit) {
+                                                                    __m256i lut, __m256i case_bit, uint32_t rpos,
+                                                                    InvList* inv) {
     uint64_t h, l, v, h2, l2, v2;
     uint32_t i = 0;
     for (; i + 64 <= len; i += 64) {
         masks_avx2(s + i, 0xffffffffu, lut, case_bit, h, l, v);
         masks_avx2(s + i + 32, 0xffffffffu, lut, case_bit, h2, l2, v2);
-        w.put<true, PEEL>(h | (h2 << 32), l | (l2 << 32), v | (v2 << 32), 64);
+        v |= v2 << 32;
+        if (inv) inv->put(rpos + i, ~v);
+        w.put<true, PEEL>(h | (h2 << 32), l | (l2 << 32), v, 64);
     }
     if (i < len) {
         const int m = (int)(len - i);
@@ -155,11 +180,14 @@ TREW_AVX2 __attribute__((always_inline)) inline void pack_read_avx2(BitWriter& w
         masks_avx2(q, keep, lut, case_bit, h, l, v);
         h2 = l2 = v2 = 0;
         if (m > 32) masks_avx2(q + 32, keep >> 32, lut, case_bit, h2, l2, v2);
-        w.put<false, PEEL>(h | (h2 << 32), l | (l2 << 32), v | (v2 << 32), m);
+        v |= v2 << 32;
+        if (inv) inv->put(rpos + i, ~v & keep);
+        w.put<false, PEEL>(h | (h2 << 32), l | (l2 << 32), v, m);
     }
 }
 
-TREW_AVX2 void pack_reads_avx2(const ChunkView& cv, uint32_t r0, uint32_t r1, uint32_t* off, uint64_t pos, BitWriter& w_out) {
+TREW_AVX2 void pack_reads_avx2(const ChunkView& cv, uint32_t r0, uint32_t r1, uint32_t* off, uint64_t pos, BitWriter& w_out,
+                               InvList* inv) {
     BitWriter w = w_out;  // local copy: its address never escapes, so the state stays in registers across the plane stores
     const __m256i lut = _mm256_setr_epi8(0, 'a', 0, 'c', 't', 0, 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0,
                                          0, 'a', 0, 'c', 't', 0, 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0);
@@ -169,12 +197,15 @@ TREW_AVX2 void pack_reads_avx2(const ChunkView& cv, uint32_t r0, uint32_t r1, ui
     for (; r < r1 && w.peeling(); r++) {
         cv.get(r, p, len, slack);
         *off++ = (uint32_t)pos; pos += len;
-        pack_read_avx2<true>(w, (const unsigned char*)p, len, slack, lut, case_bit);
+        pack_read_avx2<true>(w, (const unsigned char*)p, len, slack, lut, case_bit, (uint32_t)pos - len, inv);
     }
     for (; r < r1; r++) {
         cv.get(r, p, len, slack);
         *off++ = (uint32_t)pos; pos += len;
-        pack_read_avx2<false>(w, (const unsigned char*)p, len, slack, lut, case_bit);
+#if TREW_PACK_PREFETCH
+        for (uint32_t q = 0; q < len; q += 64) _mm_prefetch(p + TREW_PACK_PREFETCH + q, TREW_PACK_PREFETCH_HINT);
+#endif
+        pack_read_avx2<false>(w, (const unsigned char*)p, len, slack, lut, case_bit, (uint32_t)pos - len, inv);
     }
     w_out = w;
 }
@@ -182,12 +213,14 @@ TREW_AVX2 void pack_reads_avx2(const ChunkView& cv, uint32_t r0, uint32_t r1, ui
 // AVX-512BW: 64-byte blocks, mask registers instead of movemask, masked loads for read tails.
 template <bool PEEL>
 TREW_AVX512 __attribute__((always_inline)) inline void pack_read_avx512(BitWriter& w, const unsigned char* s, uint32_t len, __m512i lut,
-                                                                        __m512i case_bit, __m512i b2, __m512i b1) {
+                                                                        __m512i case_bit, __m512i b2, __m512i b1, uint32_t rpos,
+                                                                        InvList* inv) {
     uint32_t i = 0;
     for (; i + 64 <= len; i += 64) {
         __m512i x = _mm512_loadu_si512((const void*)(s + i));
         uint64_t x1 = _mm512_test_epi8_mask(x, b2), x0 = _mm512_test_epi8_mask(x, b1);
         uint64_t v = _mm512_cmpeq_epi8_mask(_mm512_shuffle_epi8(lut, x), _mm512_or_si512(x, case_bit));
+        if (inv) inv->put(rpos + i, ~v);
         w.put<true, PEEL>(~x1 & v, ~(x1 ^ x0) & v, v, 64);
     }
     if (i < len) {
@@ -196,6 +229,7 @@ TREW_AVX512 __attribute__((always_inline)) inline void pack_read_avx512(BitWrite
         __m512i x = _mm512_maskz_loadu_epi8((__mmask64)keep, (const void*)(s + i));
         uint64_t x1 = _mm512_test_epi8_mask(x, b2), x0 = _mm512_test_epi8_mask(x, b1);
         uint64_t v = _mm512_cmpeq_epi8_mask(_mm512_shuffle_epi8(lut, x), _mm512_or_si512(x, case_bit)) & keep;
+        if (inv) inv->put(rpos + i, ~v & keep);
         w.put<false, PEEL>(~x1 & v, ~(x1 ^ x0) & v, v, m);
     }
 }
@@ -203,7 +237,11 @@ TREW_AVX512 __attribute__((always_inline)) inline void pack_read_avx512(BitWrite
 // Steady state of the AVX-512 packer for single-buffer chunks, written against register pressure (x86-64 has 16
 // general registers and the generic writer keeps a dozen values alive): one plane pointer that advances plus two
 // constant strides, no first-unit test.  Precondition: the writer has left its first unit.
-TREW_AVX512 void pack_lean_avx512(const char* buf, const int32_t* locs, uint32_t r0, uint32_t r1, uint32_t* off, BitWriter& w_out) {
+// LIST: record the blocks with invalid bases in *inv (branch-free: see inv_record).  VAL == false (needs LIST): the val plane is not written at all -- a third
+// less store traffic; the list is then the only record of validity.
+template <bool LIST, bool VAL>
+TREW_AVX512 void pack_lean_avx512(const char* buf, const int32_t* locs, uint32_t r0, uint32_t r1, uint32_t* off, BitWriter& w_out,
+                                  InvList* inv) {
     const __m512i lut = _mm512_broadcast_i32x4(_mm_setr_epi8(0, 'a', 0, 'c', 't', 0, 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0));
     const __m512i case_bit = _mm512_set1_epi8(0x20), b2 = _mm512_set1_epi8(4), b1 = _mm512_set1_epi8(2);
     long long* ph = (long long*)(w_out.hi + w_out.unit);
@@ -211,23 +249,28 @@ TREW_AVX512 void pack_lean_avx512(const char* buf, const int32_t* locs, uint32_t
     uint64_t ah = w_out.ah, al = w_out.al, av = w_out.av;
     unsigned fill = (unsigned)w_out.fill;
     uint32_t pos = (uint32_t)(w_out.unit * 64 + fill);
+    unsigned char* ip = LIST ? inv->p : nullptr;
     for (uint32_t r = r0; r < r1; r++) {
         const int32_t st = locs[2 * (size_t)r], nd = locs[2 * (size_t)r + 1];
         const uint32_t len = nd >= st ? (uint32_t)(nd - st + 1) : 0u;
         const unsigned char* s = (const unsigned char*)buf + st;
         *off++ = pos;
-        pos += len;
+#if TREW_PACK_PREFETCH
+        for (uint32_t q = 0; q < len; q += 64) _mm_prefetch((const char*)s + TREW_PACK_PREFETCH + q, TREW_PACK_PREFETCH_HINT);
+#endif
         uint32_t i = 0;
         for (; i + 64 <= len; i += 64) {
             const __m512i x = _mm512_loadu_si512((const void*)(s + i));
             const uint64_t x1 = _mm512_test_epi8_mask(x, b2), x0 = _mm512_test_epi8_mask(x, b1);
             const uint64_t v = _mm512_cmpeq_epi8_mask(_mm512_shuffle_epi8(lut, x), _mm512_or_si512(x, case_bit));
             const uint64_t h = ~x1 & v, l = ~(x1 ^ x0) & v;
+            if (LIST) ip = inv_record(ip, pos + i, ~v);
             ph[0] = (long long)(ah | (h << fill));
             ph[s1] = (long long)(al | (l << fill));
-            ph[s2] = (long long)(av | (v << fill));
+            if (VAL) ph[s2] = (long long)(av | (v << fill));
             const unsigned back = 63u - fill;
-            ah = (h >> 1) >> back; al = (l >> 1) >> back; av = (v >> 1) >> back;
+            ah = (h >> 1) >> back; al = (l >> 1) >> back;
+            if (VAL) av = (v >> 1) >> back;
             ph++;
         }
         if (i < len) {
@@ -237,22 +280,27 @@ TREW_AVX512 void pack_lean_avx512(const char* buf, const int32_t* locs, uint32_t
             const uint64_t x1 = _mm512_test_epi8_mask(x, b2), x0 = _mm512_test_epi8_mask(x, b1);
             const uint64_t v = _mm512_cmpeq_epi8_mask(_mm512_shuffle_epi8(lut, x), _mm512_or_si512(x, case_bit)) & keep;
             const uint64_t h = ~x1 & v, l = ~(x1 ^ x0) & v;
-            const uint64_t th = ah | (h << fill), tl = al | (l << fill), tv = av | (v << fill);
+            if (LIST) ip = inv_record(ip, pos + i, ~v & keep);
+            const uint64_t th = ah | (h << fill), tl = al | (l << fill), tv = VAL ? av | (v << fill) : 0;
             ph[0] = (long long)th;
             ph[s1] = (long long)tl;
-            ph[s2] = (long long)tv;
+            if (VAL) ph[s2] = (long long)tv;
             const unsigned back = 63u - fill, nf = fill + m;
             const bool adv = nf >= 64;
-            ah = adv ? (h >> 1) >> back : th; al = adv ? (l >> 1) >> back : tl; av = adv ? (v >> 1) >> back : tv;
+            ah = adv ? (h >> 1) >> back : th; al = adv ? (l >> 1) >> back : tl;
+            if (VAL) av = adv ? (v >> 1) >> back : tv;
             ph += adv ? 1 : 0;
             fill = nf & 63u;
         }
+        pos += len;
     }
     w_out.unit = (uint64_t)((uint64_t*)ph - w_out.hi);
-    w_out.ah = ah; w_out.al = al; w_out.av = av; w_out.fill = (int)fill;
+    w_out.ah = ah; w_out.al = al; w_out.av = VAL ? av : 0; w_out.fill = (int)fill;
+    if (LIST) inv->p = ip;
 }
 
-TREW_AVX512 void pack_reads_avx512(const ChunkView& cv, uint32_t r0, uint32_t r1, uint32_t* off, uint64_t pos, BitWriter& w_out) {
+TREW_AVX512 void pack_reads_avx512(const ChunkView& cv, uint32_t r0, uint32_t r1, uint32_t* off, uint64_t pos, BitWriter& w_out,
+                                   InvList* inv, bool skip_val) {
     BitWriter w = w_out;  // local copy: its address never escapes, so the state stays in registers across the plane stores
     const __m512i lut = _mm512_broadcast_i32x4(_mm_setr_epi8(0, 'a', 0, 'c', 't', 0, 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0));
     const __m512i case_bit = _mm512_set1_epi8(0x20), b2 = _mm512_set1_epi8(4), b1 = _mm512_set1_epi8(2);
@@ -261,17 +309,22 @@ TREW_AVX512 void pack_reads_avx512(const ChunkView& cv, uint32_t r0, uint32_t r1
     for (; r < r1 && w.peeling(); r++) {
         cv.get(r, p, len, slack);
         *off++ = (uint32_t)pos; pos += len;
-        pack_read_avx512<true>(w, (const unsigned char*)p, len, lut, case_bit, b2, b1);
+        pack_read_avx512<true>(w, (const unsigned char*)p, len, lut, case_bit, b2, b1, (uint32_t)pos - len, inv);
     }
     if (cv.unit == 1 && r < r1) {   // single buffer: the lean steady-state loop
-        pack_lean_avx512(cv.buf[0], cv.locs[0], r, r1, off, w);
+        if (!inv) pack_lean_avx512<false, true>(cv.buf[0], cv.locs[0], r, r1, off, w, nullptr);
+        else if (skip_val) pack_lean_avx512<true, false>(cv.buf[0], cv.locs[0], r, r1, off, w, inv);
+        else pack_lean_avx512<true, true>(cv.buf[0], cv.locs[0], r, r1, off, w, inv);
         w_out = w;
         return;
     }
     for (; r < r1; r++) {
         cv.get(r, p, len, slack);
         *off++ = (uint32_t)pos; pos += len;
-        pack_read_avx512<false>(w, (const unsigned char*)p, len, lut, case_bit, b2, b1);
+#if TREW_PACK_PREFETCH
+        for (uint32_t q = 0; q < len; q += 64) _mm_prefetch(p + TREW_PACK_PREFETCH + q, TREW_PACK_PREFETCH_HINT);
+#endif
+        pack_read_avx512<false>(w, (const unsigned char*)p, len, lut, case_bit, b2, b1, (uint32_t)pos - len, inv);
     }
     w_out = w;
 }
@@ -321,18 +374,19 @@ void chunk_stats(const ChunkView& cv, uint32_t r0, uint32_t r1, uint64_t* bases,
 }
 
 void pack_chunk_range(const ChunkView& cv, uint32_t r0, uint32_t r1, uint32_t out0, uint64_t bit0, const BatchView& v,
-                      uint64_t side[3]) {
+                      uint64_t side[3], InvList* inv, bool skip_val, uint64_t range_bases) {
     side[0] = side[1] = side[2] = 0;
+    if (inv) inv->start((size_t)(range_bases >> 6) + (size_t)(r1 > r0 ? r1 - r0 : 0u) + 2);   // >= the range's 64-base blocks
     if (r0 >= r1) return;
     BitWriter w(v.hi, v.lo, v.val, bit0);
     const int lvl = simd_level();
 #if defined(__x86_64__)
-    if (lvl == 2) pack_reads_avx512(cv, r0, r1, v.bit_off + out0, bit0, w);
-    else if (lvl == 1) pack_reads_avx2(cv, r0, r1, v.bit_off + out0, bit0, w);
+    if (lvl == 2) pack_reads_avx512(cv, r0, r1, v.bit_off + out0, bit0, w, inv, inv && skip_val);
+    else if (lvl == 1) pack_reads_avx2(cv, r0, r1, v.bit_off + out0, bit0, w, inv);
     else
 #endif
-        pack_reads_scalar(cv, r0, r1, v.bit_off + out0, bit0, w);
-    (void)lvl;
+        pack_reads_scalar(cv, r0, r1, v.bit_off + out0, bit0, w, inv);
+    (void)lvl; (void)skip_val;
     w.finish();
     side[0] = w.side[0]; side[1] = w.side[1]; side[2] = w.side[2];
 }
@@ -372,9 +426,52 @@ int trew_pack_reads(const char* buffer, const int32_t* locs, uint32_t n, void* d
     uint64_t zero = 0;
     trew::pack_prepare(&zero, 1, total, v);
     uint64_t side[1][3];
-    trew::pack_chunk_range(cv, 0, n, 0, 0, v, side[0]);
+    trew::pack_chunk_range(cv, 0, n, 0, 0, v, side[0], nullptr, false, total);
     trew::pack_fixup(&zero, side, 1, v);
     v.bit_off[n] = (uint32_t)total;
+    out->n_reads = n; out->max_read_len = mx; out->bit_off = v.bit_off; out->hi = v.hi; out->lo = v.lo; out->val = v.val;
+    return TREW_OK;
+}
+
+int trew_pack_reads_ranges(const char* buffer, const int32_t* locs, uint32_t n, uint32_t n_ranges, uint32_t n_threads,
+                           uint32_t flags, void* dst, size_t dst_bytes, trew_batch* out, uint32_t* inv, size_t inv_cap,
+                           size_t* n_inv) {
+    if ((n && (!buffer || !locs)) || !dst || !out || ((uintptr_t)dst & 7) != 0 || (inv && !n_inv)) return TREW_ERR_ARG;
+    if ((flags & TREW_PACK_NO_VAL) && !inv) return TREW_ERR_ARG;
+    if (n_ranges == 0) n_ranges = 1;
+    trew::ChunkView cv{{buffer, nullptr}, {locs, nullptr}, {nullptr, nullptr}, 1u};
+    std::vector<uint32_t> r0((size_t)n_ranges + 1);
+    std::vector<uint64_t> bases(n_ranges), bit0(n_ranges);
+    for (uint32_t i = 0; i <= n_ranges; i++) r0[i] = (uint32_t)((uint64_t)n * i / n_ranges);
+    trew::Pool pool((int)(n_threads ? n_threads : 1u));
+    std::vector<uint32_t> mxs(n_ranges);
+    pool.run((int)n_ranges, [&](int i) { trew::chunk_stats(cv, r0[(size_t)i], r0[(size_t)i + 1], &bases[(size_t)i], &mxs[(size_t)i]); });
+    uint64_t total = 0; uint32_t mx = 0;
+    for (uint32_t i = 0; i < n_ranges; i++) { bit0[i] = total; total += bases[i]; if (mxs[i] > mx) mx = mxs[i]; }
+    if (total >= 0xffffffffULL) return TREW_ERR_ARG;
+    if (trew::batch_bytes(n, total) > dst_bytes) return TREW_ERR_ARG;
+    trew::BatchView v;
+    trew::batch_layout(dst, n, total, &v);
+    trew::pack_prepare(bit0.data(), (int)n_ranges, total, v);
+    v.bit_off[n] = (uint32_t)total;
+    std::vector<uint64_t> side_flat((size_t)3 * n_ranges);
+    uint64_t (*side)[3] = (uint64_t (*)[3])side_flat.data();
+    std::vector<trew::InvList> lists(inv ? n_ranges : 0u);
+    pool.run((int)n_ranges, [&](int i) {
+        trew::pack_chunk_range(cv, r0[(size_t)i], r0[(size_t)i + 1], r0[(size_t)i], bit0[(size_t)i], v, side[i],
+                               inv ? &lists[(size_t)i] : nullptr, (flags & TREW_PACK_NO_VAL) != 0, bases[(size_t)i]);
+    });
+    trew::pack_fixup(bit0.data(), side, (int)n_ranges, v);
+    if (inv) {
+        size_t k = 0;
+        for (const auto& l : lists)
+            for (size_t j = 0; j < l.size(); j++) {
+                uint32_t base; uint64_t z;
+                l.get(j, &base, &z);
+                for (; z; z &= z - 1) { if (k < inv_cap) inv[k] = base + (uint32_t)__builtin_ctzll(z); k++; }
+            }
+        *n_inv = k;
+    }
     out->n_reads = n; out->max_read_len = mx; out->bit_off = v.bit_off; out->hi = v.hi; out->lo = v.lo; out->val = v.val;
     return TREW_OK;
 }

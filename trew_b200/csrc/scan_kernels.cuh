@@ -81,6 +81,8 @@ cudaError_t sort_entries_radix(const trew_entry* d_entries, trew_entry* d_out, u
 // sorted rows with repeated keys -> one row per key, counts summed (the union of several tables' rows)
 cudaError_t combine_sorted_rows(const trew_entry* d_sorted, unsigned int n, trew_entry* d_out, unsigned int* d_n_out, void* d_temp,
                                 size_t* temp_bytes, cudaStream_t stream);
+// validity plane from n 12-byte records (u32 block position, u64 mask of invalid bases): clears those bits of val
+void launch_clear_invalid(unsigned int* val, const unsigned int* rec, unsigned int n, cudaStream_t stream);
 void launch_merge_entries(const DevCfg& cfg, const trew_entry* entries, unsigned int n, cudaStream_t stream);
 
 void launch_synth(unsigned long long seed, unsigned int n_reads, unsigned int read_len, unsigned int tel_thr,

@@ -40,6 +40,29 @@ void launch_compact(const Slot* slots, unsigned int n_slots, trew_entry* out, un
     compact_kernel<<<592, 256, 0, stream>>>(slots, n_slots, out, d_n, cap);
 }
 
+// ---- validity plane from a list: the streaming path sends one record per 64-base block that holds a base other than
+// A/C/G/T (u32 bit position of the block, u64 mask of its invalid bases; 12 bytes) instead of the whole plane; the
+// plane is set to ones by a memset and the recorded bits are cleared here.
+__global__ void clear_invalid_kernel(u32* __restrict__ val, const u32* __restrict__ rec, u32 n) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u32 pos = rec[3 * (size_t)i];
+        const u64 z = (u64)rec[3 * (size_t)i + 1] | ((u64)rec[3 * (size_t)i + 2] << 32);
+        const u32 sh = pos & 31u;
+        const u64 lo = z << sh;
+        const u32 m0 = (u32)lo, m1 = (u32)(lo >> 32), m2 = sh ? (u32)(z >> (64u - sh)) : 0u;
+        u32* w = val + (pos >> 5);
+        if (m0) atomicAnd(w, ~m0);
+        if (m1) atomicAnd(w + 1, ~m1);
+        if (m2) atomicAnd(w + 2, ~m2);
+    }
+}
+
+void launch_clear_invalid(unsigned int* val, const unsigned int* rec, unsigned int n, cudaStream_t stream) {
+    if (n == 0) return;
+    const unsigned int blocks = (n + 255u) / 256u;
+    clear_invalid_kernel<<<blocks < 592u ? blocks : 592u, 256, 0, stream>>>(val, rec, n);
+}
+
 // ---- sort by (table, k, seq): three stable LSD passes over (seq_lo, seq_hi, table << 8 | k) with a row index as payload, then one
 // gather of the 32-byte rows.  Moves 12 bytes per row and pass instead of merge-sorting 32-byte rows by a comparator.
 
