@@ -123,3 +123,39 @@ def test_truncated_bgzf_is_an_io_error(tmp_path):
     open(p, "wb").write(raw[:len(raw) // 2 + 7])
     rc, msg, _, _ = api.ingest_records(api.MODE_SHORT, p)
     assert rc == 5 and "IO Error" in msg
+
+
+@pytest.mark.parametrize("simd", ["0", "1", "2"])
+def test_parallel_newline_index_equals_serial(tmp_path, simd):
+    """The sliced SIMD newline search + per-slice role assignment (forced by a tiny TREW_INGEST_PAR_MIN) returns the
+    same records as the serial path in all three modes, for every instruction set, at awkward chunk sizes."""
+    import subprocess, sys, textwrap
+    reads = synth.adversarial_short(11, 400) + [b"", b"A", b"", b"ACGT" * 60, b"N" * 64, b"T" * 63, b"G" * 65]
+    data = synth.fastq_bytes(reads) + b"@tail\nACGT"
+    # blank-ish headers put several newlines into one 64-byte block
+    data2 = b"".join(b"@\n" + r + b"\n+\n" + b"I" * len(r) + b"\n" for r in reads)
+    p1 = write(tmp_path, "a.fastq", data)
+    p2 = write(tmp_path, "b.fastq", data2)
+    p3 = write(tmp_path, "c.fastq", synth.fastq_bytes(reads))
+    code = textwrap.dedent("""
+        import os, sys
+        from trew_b200 import api
+        p1, p2, p3 = sys.argv[1:4]
+        def run(par, mode, f1, f2, chunk):
+            if par: os.environ["TREW_INGEST_PAR_MIN"] = par
+            else: os.environ.pop("TREW_INGEST_PAR_MIN", None)
+            return api.ingest_records(mode, f1, f2, slice_length=100, chunk_bytes=chunk)
+        for chunk in (0, 777, 4096):
+            for mode, f1, f2 in ((api.MODE_SHORT, p1, None), (api.MODE_SHORT, p2, None), (api.MODE_LONG, p1, None),
+                                 (api.MODE_PAIR, p3, p2)):
+                want = run(None, mode, f1, f2, chunk)
+                for par in ("1", "50", "300"):
+                    got = run(par, mode, f1, f2, chunk)
+                    assert got == want, (chunk, mode, par)
+                assert want[0] == 0 and len(want[2]) > 0
+        print("ok")
+    """)
+    env = dict(os.environ, TREW_PACK_SIMD=simd)
+    out = subprocess.run([sys.executable, "-c", code, p1, p2, p3], env=env, capture_output=True, text=True,
+                         cwd=os.path.dirname(os.path.dirname(__file__)))
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]

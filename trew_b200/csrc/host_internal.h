@@ -22,6 +22,10 @@ struct ChunkView {
     const int32_t* locs[2];
     const char* end[2];   // one past the last byte the caller vouches for per buffer (nullptr: unknown)
     uint32_t unit;        // 1 single / long, 2 paired
+    inline const char* start(uint32_t r) const {
+        const int sd = unit == 2 ? (int)(r & 1u) : 0;
+        return buf[sd] + locs[sd][2 * (size_t)(unit == 2 ? r >> 1 : r)];
+    }
     inline void get(uint32_t r, const char*& p, uint32_t& len, size_t& slack) const {
         const int sd = unit == 2 ? (int)(r & 1u) : 0;
         const uint32_t i = unit == 2 ? r >> 1 : r;

@@ -21,6 +21,9 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 namespace trew {
 
@@ -40,6 +43,88 @@ void GrowBuf::reserve(size_t n, size_t keep) {
 GrowBuf::~GrowBuf() { free(data); }
 
 namespace {
+
+// uninitialised, grow-only array of uint32 (newline positions); untouched pages of a generous capacity cost nothing
+struct RawU32 {
+    uint32_t* d = nullptr;
+    size_t cap = 0, n = 0;
+    void ensure(size_t want) {
+        if (want <= cap) return;
+        uint32_t* q = (uint32_t*)malloc(want * sizeof(uint32_t));
+        if (!q) throw std::bad_alloc();
+        if (n) memcpy(q, d, n * sizeof(uint32_t));
+        free(d);
+        d = q; cap = want;
+    }
+    RawU32() = default;
+    RawU32(const RawU32&) = delete;
+    RawU32& operator=(const RawU32&) = delete;
+    RawU32(RawU32&& o) noexcept : d(o.d), cap(o.cap), n(o.n) { o.d = nullptr; o.cap = o.n = 0; }
+    ~RawU32() { free(d); }
+};
+
+// Offsets (relative to p) of the '\n' bytes in p[a, b), appended at o; returns the new end.  o must have room for
+// b - a + 3 entries.  FASTQ has a newline every ~80 bytes, so a memchr call per line is mostly call overhead; here a
+// 64-byte block becomes a bit mask and its first three set bits are stored without a branch (the cursor advances
+// only past real ones).
+inline uint32_t* nl_from_mask(uint32_t* o, uint32_t base, uint64_t m) {
+    const uint64_t top = 1ULL << 63;
+    *o = base + (uint32_t)__builtin_ctzll(m | top); o += (m != 0); m &= m - 1;
+    *o = base + (uint32_t)__builtin_ctzll(m | top); o += (m != 0); m &= m - 1;
+    *o = base + (uint32_t)__builtin_ctzll(m | top); o += (m != 0); m &= m - 1;
+    while (__builtin_expect(m != 0, 0)) { *o++ = base + (uint32_t)__builtin_ctzll(m); m &= m - 1; }
+    return o;
+}
+
+uint32_t* find_newlines_scalar(const char* p, size_t a, size_t b, uint32_t* o) {
+    while (a < b) {
+        const char* q = (const char*)memchr(p + a, '\n', b - a);
+        if (!q) break;
+        *o++ = (uint32_t)(q - p);
+        a = (size_t)(q - p) + 1;
+    }
+    return o;
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx512f,avx512bw"))) uint32_t* find_newlines_avx512(const char* p, size_t a, size_t b, uint32_t* o) {
+    const __m512i nl = _mm512_set1_epi8('\n');
+    size_t i = a;
+    for (; i + 64 <= b; i += 64)
+        o = nl_from_mask(o, (uint32_t)i, _mm512_cmpeq_epi8_mask(_mm512_loadu_si512((const void*)(p + i)), nl));
+    if (i < b) {
+        const __mmask64 keep = (__mmask64)((1ULL << (b - i)) - 1ULL);
+        o = nl_from_mask(o, (uint32_t)i, _mm512_mask_cmpeq_epi8_mask(keep, _mm512_maskz_loadu_epi8(keep, (const void*)(p + i)), nl));
+    }
+    return o;
+}
+
+__attribute__((target("avx2"))) uint32_t* find_newlines_avx2(const char* p, size_t a, size_t b, uint32_t* o) {
+    const __m256i nl = _mm256_set1_epi8('\n');
+    size_t i = a;
+    for (; i + 64 <= b; i += 64) {
+        const uint32_t m0 = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_loadu_si256((const __m256i*)(p + i)), nl));
+        const uint32_t m1 = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_loadu_si256((const __m256i*)(p + i + 32)), nl));
+        o = nl_from_mask(o, (uint32_t)i, (uint64_t)m0 | ((uint64_t)m1 << 32));
+    }
+    return find_newlines_scalar(p, i, b, o);
+}
+#endif
+
+uint32_t* find_newlines(const char* p, size_t a, size_t b, uint32_t* o) {
+#if defined(__x86_64__)
+    static const int lvl = [] {
+        int l = 0;
+        if (__builtin_cpu_supports("avx2")) l = 1;
+        if (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw")) l = 2;
+        if (const char* e = getenv("TREW_PACK_SIMD")) { int cap = atoi(e); if (cap < l) l = cap < 0 ? 0 : cap; }
+        return l;
+    }();
+    if (lvl == 2) return find_newlines_avx512(p, a, b, o);
+    if (lvl == 1) return find_newlines_avx2(p, a, b, o);
+#endif
+    return find_newlines_scalar(p, a, b, o);
+}
 
 struct Reader {
     bool gz = false;
@@ -196,7 +281,15 @@ struct Reader {
 
     // returns bytes read (0 at EOF), -1 on error.  Plain regular files are read with pread in parallel slices when a
     // pool is given and the request is large (the copy out of the page cache is the cost, and it scales with cores).
-    long read(char* buf, size_t n, Pool* pool, size_t par_min) {
+    // `hook` (parallel plain-file reads only): begin(slice, bytes) once per slice, then data(slice, a, b) after every
+    // ~1 MiB that landed in buf[a, b) -- the caller can look at the bytes while they are still in that core's cache;
+    // *hook_slices = the number of slices (0: the hook was not used).
+    struct Hook {
+        std::function<void(int, size_t)> begin;
+        std::function<void(int, size_t, size_t)> data;
+    };
+    long read(char* buf, size_t n, Pool* pool, size_t par_min, const Hook* hook = nullptr, int* hook_slices = nullptr) {
+        if (hook_slices) *hook_slices = 0;
         if (bgzf) return read_bgzf(buf, std::min<size_t>(n, (size_t)1 << 30), pool);
         if (gz) {
             int r = gzread(gfp, buf, (unsigned)std::min<size_t>(n, 1u << 30));
@@ -207,16 +300,21 @@ struct Reader {
             if (want == 0) return 0;
             const int P = pool && want >= par_min ? std::min(pool->size(), (int)(want / (par_min / 4 + 1)) + 1) : 1;
             std::vector<long> got((size_t)P, 0);
+            const bool hooked = hook && P > 1;
             auto slice = [&](int i) {
                 size_t a = want * (size_t)i / (size_t)P, b = want * (size_t)(i + 1) / (size_t)P;
+                if (hooked) hook->begin(i, b - a);
                 while (a < b) {
-                    ssize_t r = pread(fd, buf + a, b - a, (off_t)(offset + a));
+                    const size_t step = hooked ? std::min(b - a, (size_t)1 << 20) : b - a;
+                    ssize_t r = pread(fd, buf + a, step, (off_t)(offset + a));
                     if (r < 0) { if (errno == EINTR) continue; got[(size_t)i] = -1; return; }
                     if (r == 0) break;
+                    if (hooked) hook->data(i, a, a + (size_t)r);
                     a += (size_t)r; got[(size_t)i] += (long)r;
                 }
             };
             if (P > 1) pool->run(P, slice); else slice(0);
+            if (hooked && hook_slices) *hook_slices = P;
             long total = 0;
             for (long g : got) { if (g < 0) return -1; total += g; }
             offset += (uint64_t)total;
@@ -256,9 +354,24 @@ struct Side {
     std::vector<int32_t> locs;  // sequence lines found in buf, inclusive (st, nd)
 
     // read more bytes; returns false on I/O error
+    // With a pool, plain files are read in parallel slices and each slice's newlines are indexed right behind the
+    // read, 1 MiB at a time, instead of in a second pass over memory (scan() then only assigns the line roles).
     bool fill(size_t chunk, Pool* pool, size_t par_min) {
         buf->reserve(have + chunk, have);
-        long r = rd.read(buf->data + have, chunk, pool, par_min);
+        nl_slices = 0;
+        Reader::Hook hook;
+        const bool fuse = pool && pool->size() > 1 && scanned == have;
+        if (fuse) {
+            if (nl.size() < (size_t)pool->size()) nl.resize((size_t)pool->size());
+            const char* base = buf->data;
+            const size_t have0 = have;
+            hook.begin = [this](int i, size_t bytes) { nl[(size_t)i].n = 0; nl[(size_t)i].ensure(bytes + 3); };
+            hook.data = [this, base, have0](int i, size_t a, size_t b) {
+                RawU32& v = nl[(size_t)i];
+                v.n = (size_t)(find_newlines(base, have0 + a, have0 + b, v.d + v.n) - v.d);
+            };
+        }
+        long r = rd.read(buf->data + have, chunk, pool, par_min, fuse ? &hook : nullptr, &nl_slices);
         if (r < 0) return false;
         if (r == 0) eof = true;
         have += (size_t)r;
@@ -272,60 +385,95 @@ struct Side {
             out.push_back((int32_t)nl - 1);
         }
     }
+    std::vector<RawU32> nl;   // per slice: newline offsets found by the parallel search
+    int nl_slices = 0;        // > 0: fill() already indexed the fresh bytes into nl[0 .. nl_slices)
+    // Turn the newline offsets of slices [0, P) into sequence-line locations.  A line's role depends only on the
+    // ordinal of the newline that ends it, so a slice needs nothing from the others but their newline counts; except
+    // in long mode (which drops short lines) the number of sequence lines per slice follows from those counts too and
+    // every slice writes straight into its place in `locs`.
+    void finish_scan(int P, int mode, int slice, bool* too_long, Pool* pool) {
+        std::vector<uint64_t> base((size_t)P + 1), first((size_t)P + 1);
+        std::vector<int64_t> prev((size_t)P);
+        base[0] = num;
+        int64_t last = (int64_t)line_start - 1;
+        const size_t locs0 = locs.size();
+        first[0] = locs0;
+        for (int i = 0; i < P; i++) {
+            const uint64_t g0 = base[(size_t)i], g1 = g0 + nl[(size_t)i].n;
+            base[(size_t)i + 1] = g1;
+            first[(size_t)i + 1] = first[(size_t)i] + 2 * (((g1 + 2) >> 2) - ((g0 + 2) >> 2));   // ordinals g in (g0, g1] with g % 4 == 2
+            prev[(size_t)i] = last;
+            if (nl[(size_t)i].n) last = (int64_t)nl[(size_t)i].d[nl[(size_t)i].n - 1];
+        }
+        std::vector<char> tl((size_t)P, 0);
+        if (mode != TREW_MODE_LONG) {
+            locs.resize((size_t)first[(size_t)P]);
+            int32_t* out = locs.data();
+            auto work = [&](int i) {
+                const RawU32& v = nl[(size_t)i];
+                int32_t* o = out + first[(size_t)i];
+                const uint64_t g0 = base[(size_t)i];
+                bool t = false;
+                // the first newline of the slice with ordinal % 4 == 2, then every fourth
+                for (size_t j = (size_t)((2 - (g0 + 1)) & 3); j < v.n; j += 4) {
+                    const int64_t st = (j ? (int64_t)v.d[j - 1] : prev[(size_t)i]) + 1;
+                    const int64_t e = (int64_t)v.d[j];
+                    t |= mode == TREW_MODE_SHORT && e - st > 1000;
+                    *o++ = (int32_t)st; *o++ = (int32_t)e - 1;
+                }
+                tl[(size_t)i] = t ? 1 : 0;
+            };
+            if (pool && P > 1) pool->run(P, work); else for (int i = 0; i < P; i++) work(i);
+        } else {
+            std::vector<std::vector<int32_t>> out((size_t)P);
+            auto work = [&](int i) {
+                const RawU32& v = nl[(size_t)i];
+                int64_t pv = prev[(size_t)i];
+                uint64_t g = base[(size_t)i];
+                bool t = false;
+                auto& o = out[(size_t)i];
+                o.reserve(v.n / 2 + 8);
+                for (size_t j = 0; j < v.n; j++) {
+                    g++;
+                    if ((g & 3) == 2) line_done((size_t)(pv + 1), v.d[j], mode, slice, &t, o);
+                    pv = (int64_t)v.d[j];
+                }
+                tl[(size_t)i] = t ? 1 : 0;
+            };
+            if (pool && P > 1) pool->run(P, work); else for (int i = 0; i < P; i++) work(i);
+            size_t add = 0;
+            for (auto& o : out) add += o.size();
+            locs.reserve(locs.size() + add);
+            for (int i = 0; i < P; i++) locs.insert(locs.end(), out[(size_t)i].begin(), out[(size_t)i].end());
+        }
+        for (int i = 0; i < P; i++) if (tl[(size_t)i]) *too_long = true;
+        total_lines += base[(size_t)P] - num;
+        num = base[(size_t)P];
+        line_start = (size_t)(last + 1);
+    }
     // examine fresh bytes; mode 0: too_long set when a short read exceeds 1000; mode 2: drop < slice.
     // With a pool and enough fresh bytes the newline search runs in parallel slices: a line's role depends only on the
     // ordinal of the newline that ends it, so the slices need nothing from each other but their newline counts.
     void scan(int mode, int slice, bool* too_long, Pool* pool, size_t par_min) {
         const char* p = buf->data;
+        if (nl_slices > 0) {
+            finish_scan(nl_slices, mode, slice, too_long, pool);
+            nl_slices = 0;
+            scanned = have;
+            return;
+        }
         if (pool && pool->size() > 1 && have - scanned >= par_min) {
             const size_t begin = scanned, end = have;
             const int P = std::min(pool->size() * 2, (int)((end - begin) / (par_min / 8 + 1)) + 1);
-            std::vector<std::vector<uint32_t>> nl((size_t)P);
+            if (nl.size() < (size_t)P) nl.resize((size_t)P);
             pool->run(P, [&](int i) {
-                size_t a = begin + (end - begin) * (size_t)i / (size_t)P, b = begin + (end - begin) * (size_t)(i + 1) / (size_t)P;
-                auto& v = nl[(size_t)i];
-                v.reserve((b - a) / 64 + 16);
-                while (a < b) {
-                    const char* q = (const char*)memchr(p + a, '\n', b - a);
-                    if (!q) break;
-                    v.push_back((uint32_t)(q - p));
-                    a = (size_t)(q - p) + 1;
-                }
+                const size_t a = begin + (end - begin) * (size_t)i / (size_t)P, b = begin + (end - begin) * (size_t)(i + 1) / (size_t)P;
+                RawU32& v = nl[(size_t)i];
+                v.n = 0;
+                v.ensure(b - a + 3);
+                v.n = (size_t)(find_newlines(p, a, b, v.d) - v.d);
             });
-            std::vector<uint64_t> base((size_t)P + 1);
-            std::vector<int64_t> prev((size_t)P);
-            base[0] = num;
-            int64_t last = (int64_t)line_start - 1;
-            for (int i = 0; i < P; i++) {
-                base[(size_t)i + 1] = base[(size_t)i] + nl[(size_t)i].size();
-                prev[(size_t)i] = last;
-                if (!nl[(size_t)i].empty()) last = (int64_t)nl[(size_t)i].back();
-            }
-            std::vector<std::vector<int32_t>> out((size_t)P);
-            std::vector<char> tl((size_t)P, 0);
-            pool->run(P, [&](int i) {
-                int64_t pv = prev[(size_t)i];
-                uint64_t g = base[(size_t)i];
-                bool t = false;
-                auto& o = out[(size_t)i];
-                o.reserve(nl[(size_t)i].size() / 2 + 8);
-                for (uint32_t pos : nl[(size_t)i]) {
-                    g++;
-                    if ((g & 3) == 2) line_done((size_t)(pv + 1), pos, mode, slice, &t, o);
-                    pv = (int64_t)pos;
-                }
-                tl[(size_t)i] = t ? 1 : 0;
-            });
-            size_t add = 0;
-            for (auto& o : out) add += o.size();
-            locs.reserve(locs.size() + add);
-            for (int i = 0; i < P; i++) {
-                locs.insert(locs.end(), out[(size_t)i].begin(), out[(size_t)i].end());
-                if (tl[(size_t)i]) *too_long = true;
-            }
-            total_lines += base[(size_t)P] - num;
-            num = base[(size_t)P];
-            line_start = (size_t)(last + 1);
+            finish_scan(P, mode, slice, too_long, pool);
             scanned = have;
             return;
         }

@@ -14,11 +14,15 @@
 #include <vector>
 
 #ifndef TREW_PACK_PREFETCH
-// Bytes ahead of the current read that the SIMD packers prefetch into L1 (0 = off).  The packers stream ~150 B per
+// How far ahead the SIMD packers prefetch into L1 (0 = off): TREW_PACK_PREFETCH_READS reads ahead for reads of up to
+// 512 bases, TREW_PACK_PREFETCH bytes ahead within a longer read.  The packers stream ~150 B per
 // read in and 56 B out on every core; alone, the hardware prefetchers keep a core at ~5 GB/s of input on the
 // B200 hosts measured, and an explicit prefetch 2-8 KB ahead shortens a 1 M-read batch from 1.9 to 1.3 ms on 16
 // cores (host packer).
 #define TREW_PACK_PREFETCH 3072
+#endif
+#ifndef TREW_PACK_PREFETCH_READS
+#define TREW_PACK_PREFETCH_READS 16
 #endif
 #ifndef TREW_PACK_PREFETCH_HINT
 #define TREW_PACK_PREFETCH_HINT _MM_HINT_T0
@@ -31,6 +35,8 @@
 namespace trew {
 
 namespace {
+
+constexpr uint32_t kPrefetchReads = TREW_PACK_PREFETCH_READS;
 
 struct Lut {
     unsigned char v[256];  // bit0 = lo, bit1 = hi, bit2 = valid
@@ -203,7 +209,11 @@ TREW_AVX2 void pack_reads_avx2(const ChunkView& cv, uint32_t r0, uint32_t r1, ui
         cv.get(r, p, len, slack);
         *off++ = (uint32_t)pos; pos += len;
 #if TREW_PACK_PREFETCH
-        for (uint32_t q = 0; q < len; q += 64) _mm_prefetch(p + TREW_PACK_PREFETCH + q, TREW_PACK_PREFETCH_HINT);
+        {
+            const uint32_t ra = r + kPrefetchReads * cv.unit;
+            const char* pf = len <= 512u ? cv.start(ra < r1 ? ra : r) : p + TREW_PACK_PREFETCH;
+            for (uint32_t q = 0; q < len; q += 64) _mm_prefetch(pf + q, TREW_PACK_PREFETCH_HINT);
+        }
 #endif
         pack_read_avx2<false>(w, (const unsigned char*)p, len, slack, lut, case_bit, (uint32_t)pos - len, inv);
     }
@@ -256,7 +266,12 @@ TREW_AVX512 void pack_lean_avx512(const char* buf, const int32_t* locs, uint32_t
         const unsigned char* s = (const unsigned char*)buf + st;
         *off++ = pos;
 #if TREW_PACK_PREFETCH
-        for (uint32_t q = 0; q < len; q += 64) _mm_prefetch((const char*)s + TREW_PACK_PREFETCH + q, TREW_PACK_PREFETCH_HINT);
+        {   // short reads: the read kPrefetchReads ahead (the bytes between reads -- FASTQ headers, qualities -- are
+            // not wanted); long reads: further along the same read
+            const unsigned char* pf = len <= 512u ? (const unsigned char*)buf + locs[2 * (size_t)(r + kPrefetchReads < r1 ? r + kPrefetchReads : r)]
+                                                  : s + TREW_PACK_PREFETCH;
+            for (uint32_t q = 0; q < len; q += 64) _mm_prefetch((const char*)pf + q, TREW_PACK_PREFETCH_HINT);
+        }
 #endif
         uint32_t i = 0;
         for (; i + 64 <= len; i += 64) {
@@ -322,7 +337,11 @@ TREW_AVX512 void pack_reads_avx512(const ChunkView& cv, uint32_t r0, uint32_t r1
         cv.get(r, p, len, slack);
         *off++ = (uint32_t)pos; pos += len;
 #if TREW_PACK_PREFETCH
-        for (uint32_t q = 0; q < len; q += 64) _mm_prefetch(p + TREW_PACK_PREFETCH + q, TREW_PACK_PREFETCH_HINT);
+        {
+            const uint32_t ra = r + kPrefetchReads * cv.unit;
+            const char* pf = len <= 512u ? cv.start(ra < r1 ? ra : r) : p + TREW_PACK_PREFETCH;
+            for (uint32_t q = 0; q < len; q += 64) _mm_prefetch(pf + q, TREW_PACK_PREFETCH_HINT);
+        }
 #endif
         pack_read_avx512<false>(w, (const unsigned char*)p, len, lut, case_bit, b2, b1, (uint32_t)pos - len, inv);
     }
