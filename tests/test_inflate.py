@@ -1,0 +1,29 @@
+"""The DEFLATE decoder behind the .gz ingest path (trew_b200/csrc/inflate.cpp) against zlib.  CPU only.
+
+tests/native/inflate_check.cpp compresses varied data with zlib's deflate (all block types, levels, strategies, flush
+points), decodes it with the library's decoder whole and in arbitrary input / output chunks, and feeds it corrupted
+streams; it is built with AddressSanitizer + UBSan when the toolchain has them."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def checker(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("inflate") / "inflate_check")
+    src = [os.path.join(ROOT, "tests", "native", "inflate_check.cpp"), os.path.join(ROOT, "trew_b200", "csrc", "inflate.cpp")]
+    base = ["g++", "-O1", "-g", "-std=c++17", "-o", out] + src + ["-lz", "-lpthread"]
+    san = base[:4] + ["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"] + base[4:]
+    if subprocess.run(san, capture_output=True).returncode != 0:
+        r = subprocess.run(base, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+    return out
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_decoder_matches_zlib_and_survives_corruption(checker, seed):
+    r = subprocess.run([checker, str(seed), "14"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), (r.stdout[-500:], r.stderr[-2000:])

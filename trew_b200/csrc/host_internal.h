@@ -158,6 +158,34 @@ struct GrowBuf {
 };
 struct IngestScratch { GrowBuf a, b; };
 
+// inflate.cpp: raw DEFLATE decoder, resumable between symbols.  run() consumes input and produces output until one
+// of them runs out or the stream ends; unless in_final is set it wants at least 1 KiB of input in hand whenever a
+// block header is due (it returns kNeedInput otherwise), so callers feed it from a buffer they top up.
+class Inflater {
+public:
+    enum Status { kNeedInput, kOutputFull, kStreamEnd, kError };
+    Inflater() { reset(); }
+    void reset();   // start of a new DEFLATE stream
+    Status run(const uint8_t* in, size_t in_len, bool in_final, size_t* in_used, uint8_t* out, size_t out_cap, size_t* out_used);
+    // after kStreamEnd: the whole bytes that were pulled into the bit buffer but belong to whatever follows the stream
+    size_t leftover(uint8_t out[8]);
+
+private:
+    enum State { kHeader, kStored, kHuffman, kDone };
+    static constexpr size_t kWindow = 32768, kLitCap = 4096, kDistCap = 1024;   // tables: worst cases are 2342 / 402 entries
+    bool read_header(const uint8_t*& ip, const uint8_t* in_end);
+    void save_history(const uint8_t* out, size_t produced);
+    uint64_t bitbuf_;
+    int bitcnt_;
+    State state_;
+    bool final_;
+    uint32_t stored_left_;
+    size_t hist_len_;
+    uint64_t lit_[kLitCap];
+    uint32_t dist_[kDistCap];
+    uint8_t hist_[kWindow];
+};
+
 // ingest.cpp: FASTQ / FASTQ.gz record reader with the reference's record semantics
 struct IngestResult { int status; std::string message; };
 typedef std::function<int(const char* buf1, const std::vector<int32_t>& locs1, const char* buf2,

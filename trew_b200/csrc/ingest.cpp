@@ -139,6 +139,23 @@ struct Reader {
     uint64_t cbuf_off = 0;             // file offset of cbuf[0]
     std::vector<char> pending;         // inflated bytes not yet handed out (a block that did not fit the caller's buffer)
     size_t pending_pos = 0;
+    // Ordinary gzip files (regular file, gzip magic) go through the decoder in inflate.cpp instead of zlib's gzread:
+    // same stream semantics -- concatenated members, trailing garbage after a member ignored -- checked against
+    // each member's CRC-32 and ISIZE.  (Stricter than gzread in one point: a file that ends inside a member is an
+    // I/O error here; gzread hands out what it could decode and then reports end of file.)
+    bool ownz = false;
+    std::vector<unsigned char> zbuf;   // window of the compressed file
+    size_t z_pos = 0, z_have = 0;
+    bool z_eof = false, z_any_member = false;
+    enum ZPhase { kGzHeader, kGzBody, kGzTrailer, kGzEnd } zphase = kGzHeader;
+    std::unique_ptr<Inflater> inf;
+    uint64_t z_len = 0;                // bytes of the current member so far
+    const char* zerr = nullptr;
+    // CRC-32 work is deferred to finish_crc (it runs on the pool): output pieces in order, a member's last piece
+    // carrying the CRC its trailer announced
+    struct CrcPiece { const char* p; size_t len; bool member_end; uint32_t want; };
+    std::vector<CrcPiece> crc_todo;
+    uint32_t z_crc = 0;
 
     static bool bgzf_header(const unsigned char* p, size_t avail, uint32_t* bsize, uint32_t* hdr_len) {
         if (avail < 18 || p[0] != 31 || p[1] != 139 || p[2] != 8 || !(p[3] & 4)) return false;
@@ -170,6 +187,12 @@ struct Reader {
                     bgzf = true; fd = probe; size = (int64_t)st.st_size;
                     return true;
                 }
+                if (got >= 2 && h[0] == 31 && h[1] == 139 && fstat(probe, &st) == 0 && S_ISREG(st.st_mode) && !getenv("TREW_ZLIB_GZ")) {
+                    ownz = true; fd = probe; size = (int64_t)st.st_size;
+                    zbuf.resize(((size_t)8 << 20) + 64);
+                    inf.reset(new Inflater());
+                    return true;
+                }
                 ::close(probe);
             }
             gfp = gzopen(name, "r");
@@ -186,20 +209,15 @@ struct Reader {
     struct BgzfBlock { const unsigned char* cdata; uint32_t clen, isize; size_t out_off; };
 
     static bool inflate_blocks(const BgzfBlock* blk, size_t n, char* out) {
-        z_stream zs;
-        memset(&zs, 0, sizeof(zs));
-        if (inflateInit2(&zs, -15) != Z_OK) return false;
-        bool ok = true;
-        for (size_t i = 0; i < n && ok; i++) {
+        std::unique_ptr<Inflater> inf(new Inflater());
+        for (size_t i = 0; i < n; i++) {
             if (blk[i].isize == 0) continue;
-            inflateReset(&zs);
-            zs.next_in = const_cast<unsigned char*>(blk[i].cdata); zs.avail_in = blk[i].clen;
-            zs.next_out = (unsigned char*)out + blk[i].out_off; zs.avail_out = blk[i].isize;
-            int rc = inflate(&zs, Z_FINISH);
-            ok = rc == Z_STREAM_END && zs.avail_out == 0;
+            inf->reset();
+            size_t iu = 0, ou = 0;
+            const Inflater::Status st = inf->run(blk[i].cdata, blk[i].clen, true, &iu, (uint8_t*)out + blk[i].out_off, blk[i].isize, &ou);
+            if (st != Inflater::kStreamEnd || ou != blk[i].isize) return false;
         }
-        inflateEnd(&zs);
-        return ok;
+        return true;
     }
 
     // make sure cbuf holds the whole block that starts at file offset `offset` (or as much as the file has)
@@ -279,6 +297,129 @@ struct Reader {
         return (long)done;
     }
 
+    // refill the compressed window; keeps the 8 bytes before z_pos (the decoder may hand bytes back at a member's end)
+    bool z_topup() {
+        if (z_eof) return true;
+        const size_t keep_from = z_pos >= 8 ? z_pos - 8 : 0;
+        if (keep_from) { memmove(zbuf.data(), zbuf.data() + keep_from, z_have - keep_from); z_have -= keep_from; z_pos -= keep_from; }
+        while (z_have < zbuf.size()) {
+            ssize_t r = pread(fd, zbuf.data() + z_have, zbuf.size() - z_have, (off_t)offset);
+            if (r < 0) { if (errno == EINTR) continue; zerr = strerror(errno); return false; }
+            if (r == 0) { z_eof = true; break; }
+            z_have += (size_t)r; offset += (uint64_t)r;
+        }
+        return true;
+    }
+
+    // gzip member header (RFC 1952) at p: its length, 0 if incomplete within avail, -1 if malformed
+    static long gz_header_len(const unsigned char* p, size_t avail) {
+        if (avail < 10) return 0;
+        if (p[0] != 31 || p[1] != 139 || p[2] != 8 || (p[3] & 0xE0)) return -1;
+        const int flg = p[3];
+        size_t q = 10;
+        if (flg & 4) { if (avail < q + 2) return 0; q += 2 + (size_t)(p[q] | (p[q + 1] << 8)); if (avail < q) return 0; }
+        for (int bit : {8, 16})
+            if (flg & bit) { while (q < avail && p[q]) q++; if (q >= avail) return 0; q++; }
+        if (flg & 2) q += 2;
+        return avail < q ? 0 : (long)q;
+    }
+
+    long read_gz(char* buf, size_t n) {
+        size_t done = 0;
+        while (done < n) {
+            if (pending_pos < pending.size()) {   // bytes decoded aside (below) go out first, in order
+                const size_t m = std::min(n - done, pending.size() - pending_pos);
+                memcpy(buf + done, pending.data() + pending_pos, m);
+                crc_todo.push_back(CrcPiece{buf + done, m, false, 0});
+                pending_pos += m; done += m;
+                if (pending_pos == pending.size()) { pending.clear(); pending_pos = 0; }
+                continue;
+            }
+            if (zphase == kGzEnd) break;
+            if (!z_eof && z_have - z_pos < ((size_t)64 << 10) && !z_topup()) return -1;
+            const unsigned char* p = zbuf.data() + z_pos;
+            const size_t avail = z_have - z_pos;
+            if (zphase == kGzHeader) {
+                if (avail < 2 || p[0] != 31 || p[1] != 139) {
+                    // end of file, or bytes that are not another member: ignored once a member was read (as gzread does)
+                    if (avail == 0 || z_any_member) { zphase = kGzEnd; break; }
+                    zerr = "not in gzip format"; return -1;
+                }
+                const long hl = gz_header_len(p, avail);
+                if (hl < 0) { zerr = "unknown compression method or header flags"; return -1; }
+                if (hl == 0) { zerr = z_eof ? "unexpected end of file" : "gzip header too large"; return -1; }
+                z_pos += (size_t)hl;
+                inf->reset();
+                z_len = 0; z_any_member = true;
+                zphase = kGzBody;
+            } else if (zphase == kGzBody) {
+                size_t iu = 0, ou = 0;
+                Inflater::Status st;
+                if (n - done < 1024) {
+                    // too little room left for the decoder to be sure of progress (a match is up to 258 bytes): decode aside
+                    pending.resize((size_t)64 << 10); pending_pos = 0;
+                    st = inf->run(p, avail, z_eof, &iu, (uint8_t*)pending.data(), pending.size(), &ou);
+                    pending.resize(ou);
+                    z_len += ou;
+                } else {
+                    st = inf->run(p, avail, z_eof, &iu, (uint8_t*)buf + done, n - done, &ou);
+                    if (ou) crc_todo.push_back(CrcPiece{buf + done, ou, false, 0});
+                    done += ou; z_len += ou;
+                }
+                z_pos += iu;
+                if (st == Inflater::kError) { zerr = z_eof && z_pos >= z_have ? "unexpected end of file" : "invalid compressed data"; return -1; }
+                if (st == Inflater::kStreamEnd) {
+                    uint8_t back[8];
+                    z_pos -= inf->leftover(back);
+                    zphase = kGzTrailer;
+                } else if (st == Inflater::kOutputFull) {
+                    if (pending.empty()) break;   // the caller's buffer is as full as it gets
+                } else if (z_eof) {   // kNeedInput although the decoder was told the input is complete
+                    zerr = "unexpected end of file"; return -1;
+                }
+            } else {   // kGzTrailer: CRC-32 and ISIZE, little endian
+                if (avail < 8) {
+                    if (z_eof) { zerr = "unexpected end of file"; return -1; }
+                    if (!z_topup()) return -1;
+                    continue;
+                }
+                const uint32_t crc = p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+                const uint32_t isize = p[4] | ((uint32_t)p[5] << 8) | ((uint32_t)p[6] << 16) | ((uint32_t)p[7] << 24);
+                if (isize != (uint32_t)z_len) { zerr = "incorrect length check"; return -1; }
+                crc_todo.push_back(CrcPiece{buf + done, 0, true, crc});
+                z_pos += 8;
+                zphase = kGzHeader;
+            }
+        }
+        return (long)done;
+    }
+
+    // CRC-32 of what read_gz handed out since the last call (parallel slices combined with crc32_combine)
+    bool finish_crc(Pool* pool) {
+        bool ok = true;
+        for (const CrcPiece& c : crc_todo) {
+            if (c.len) {
+                const int P = pool && c.len >= ((size_t)1 << 20) ? pool->size() : 1;
+                std::vector<uint32_t> part((size_t)P);
+                auto work = [&](int i) {
+                    const size_t a = c.len * (size_t)i / (size_t)P, b = c.len * (size_t)(i + 1) / (size_t)P;
+                    part[(size_t)i] = (uint32_t)crc32_z(0L, (const Bytef*)c.p + a, b - a);
+                };
+                if (P > 1) pool->run(P, work); else work(0);
+                for (int i = 0; i < P; i++) {
+                    const size_t a = c.len * (size_t)i / (size_t)P, b = c.len * (size_t)(i + 1) / (size_t)P;
+                    z_crc = (uint32_t)crc32_combine(z_crc, part[(size_t)i], (z_off_t)(b - a));
+                }
+            }
+            if (c.member_end) {
+                if (z_crc != c.want) { zerr = "incorrect data check"; ok = false; }
+                z_crc = 0;
+            }
+        }
+        crc_todo.clear();
+        return ok;
+    }
+
     // returns bytes read (0 at EOF), -1 on error.  Plain regular files are read with pread in parallel slices when a
     // pool is given and the request is large (the copy out of the page cache is the cost, and it scales with cores).
     // `hook` (parallel plain-file reads only): begin(slice, bytes) once per slice, then data(slice, a, b) after every
@@ -291,6 +432,7 @@ struct Reader {
     long read(char* buf, size_t n, Pool* pool, size_t par_min, const Hook* hook = nullptr, int* hook_slices = nullptr) {
         if (hook_slices) *hook_slices = 0;
         if (bgzf) return read_bgzf(buf, std::min<size_t>(n, (size_t)1 << 30), pool);
+        if (ownz) return read_gz(buf, std::min<size_t>(n, (size_t)1 << 30));
         if (gz) {
             int r = gzread(gfp, buf, (unsigned)std::min<size_t>(n, 1u << 30));
             return r < 0 ? -1 : r;
@@ -328,6 +470,7 @@ struct Reader {
     }
     std::string error() {
         if (bgzf) return "malformed BGZF block";
+        if (ownz) return zerr ? zerr : "gzip stream error";
         if (gz) { int e; return gzerror(gfp, &e); }
         return strerror(errno);
     }
@@ -356,7 +499,7 @@ struct Side {
     // read more bytes; returns false on I/O error
     // With a pool, plain files are read in parallel slices and each slice's newlines are indexed right behind the
     // read, 1 MiB at a time, instead of in a second pass over memory (scan() then only assigns the line roles).
-    bool fill(size_t chunk, Pool* pool, size_t par_min) {
+    bool fill(size_t chunk, Pool* pool, size_t par_min, bool defer_crc = false) {
         buf->reserve(have + chunk, have);
         nl_slices = 0;
         Reader::Hook hook;
@@ -373,6 +516,7 @@ struct Side {
         }
         long r = rd.read(buf->data + have, chunk, pool, par_min, fuse ? &hook : nullptr, &nl_slices);
         if (r < 0) return false;
+        if (!defer_crc && !rd.finish_crc(pool)) return false;
         if (r == 0) eof = true;
         have += (size_t)r;
         return true;
@@ -537,7 +681,8 @@ IngestResult ingest_file(int mode, int slice_length, const char* file1, bool gz1
             // two inflate streams are independent: read both mates' blocks at the same time
             bool ok[2] = {true, true};
             Side* sides[2] = {&a, &b};
-            pool->run(2, [&](int i) { if (!sides[i]->eof) ok[i] = sides[i]->fill(chunk_bytes, nullptr, par_min); });
+            pool->run(2, [&](int i) { if (!sides[i]->eof) ok[i] = sides[i]->fill(chunk_bytes, nullptr, par_min, true); });
+            for (int i = 0; i < 2; i++) ok[i] = ok[i] && sides[i]->rd.finish_crc(pool);   // the members' CRC-32, on all threads
             if (!ok[0]) return IngestResult{TREW_ERR_IO, "File 1 IO Error: " + a.rd.error() + "."};
             if (!ok[1]) return IngestResult{TREW_ERR_IO, "File 2 IO Error: " + b.rd.error() + "."};
         } else {
