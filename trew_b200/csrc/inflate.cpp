@@ -282,33 +282,45 @@ Inflater::Status Inflater::run(const uint8_t* in, size_t in_len, bool in_final, 
         int bc = bitcnt_;
         bool block_done = false, bad = false;
         const uint32_t lit_mask = (1u << kLitBits) - 1, dist_mask = (1u << kDistBits) - 1;
-        if (in_end - ip >= 32 && out_end - op >= 320) {
-            const uint8_t* const in_fast = in_end - 24;
-            uint8_t* const out_fast = out_end - 300;
-            while (ip <= in_fast && op <= out_fast) {
-                bb |= load_u64(ip) << bc; ip += (63 - bc) >> 3; bc |= 56;
-                uint64_t e = lit_[bb & lit_mask];
+        if (in_end - ip >= 48 && out_end - op >= 400) {
+            // Per turn: up to three literal entries, or up to two and one match.  At most three refills (each loads 8
+            // bytes and advances < 8) and 12 + 258 + 15 output bytes, hence the margins.  The entry for the next turn
+            // is looked up before the match bytes are copied, so the copy overlaps the next decode.
+            const uint8_t* const in_fast = in_end - 40;
+            uint8_t* const out_fast = out_end - 340;
+#define TREW_REFILL() do { bb |= load_u64(ip) << bc; ip += (63 - bc) >> 3; bc |= 56; } while (0)
+#define TREW_LITS(e) do { const uint32_t lits_ = (uint32_t)((e) >> 16); memcpy(op, &lits_, 4); op += (e) >> 56; \
+                          bb >>= ((e) & 0xFFu); bc -= (int)((e) & 0xFFu); } while (0)
+            TREW_REFILL();
+            uint64_t e = lit_[bb & lit_mask];
+            for (;;) {
                 if (e & kLiteral) {
-                    uint32_t lits = (uint32_t)(e >> 16);
-                    memcpy(op, &lits, 4); op += e >> 56; bb >>= (e & 0xFFu); bc -= (int)(e & 0xFFu);
+                    TREW_LITS(e);
                     e = lit_[bb & lit_mask];
                     if (e & kLiteral) {
-                        lits = (uint32_t)(e >> 16);
-                        memcpy(op, &lits, 4); op += e >> 56; bb >>= (e & 0xFFu); bc -= (int)(e & 0xFFu);
+                        TREW_LITS(e);
                         e = lit_[bb & lit_mask];
                         if (e & kLiteral) {
-                            lits = (uint32_t)(e >> 16);
-                            memcpy(op, &lits, 4); op += e >> 56; bb >>= (e & 0xFFu); bc -= (int)(e & 0xFFu);
+                            TREW_LITS(e);
+                            TREW_REFILL();
+                            e = lit_[bb & lit_mask];
+                            if (ip > in_fast || op > out_fast) break;
                             continue;
                         }
                     }
-                    bb |= load_u64(ip) << bc; ip += (63 - bc) >> 3; bc |= 56;
+                    TREW_REFILL();
                 }
                 if (e & kExceptional) {
                     if (e & kSubtable) {
                         bb >>= kLitBits; bc -= kLitBits;
                         e = lit_[(uint32_t)(e >> 16) + (bb & ((1u << ((e >> 8) & 0x1Fu)) - 1))];
-                        if (e & kLiteral) { bb >>= (e & 0xFFu); bc -= (int)(e & 0xFFu); *op++ = (uint8_t)(e >> 16); continue; }
+                        if (e & kLiteral) {
+                            bb >>= (e & 0xFFu); bc -= (int)(e & 0xFFu); *op++ = (uint8_t)(e >> 16);
+                            TREW_REFILL();
+                            e = lit_[bb & lit_mask];
+                            if (ip > in_fast || op > out_fast) break;
+                            continue;
+                        }
                     }
                     if (e & kExceptional) {
                         if (e & kEndOfBlock) { bb >>= (e & 0xFFu); bc -= (int)(e & 0xFFu); block_done = true; break; }
@@ -330,6 +342,8 @@ Inflater::Status Inflater::run(const uint8_t* in, size_t in_len, bool in_final, 
                 const int dx = (int)((d >> 8) & 0x1Fu);
                 const size_t dist = (d >> 16) + (size_t)(bb & (((uint64_t)1 << dx) - 1));
                 bb >>= dx; bc -= dx;
+                TREW_REFILL();
+                e = lit_[bb & lit_mask];
                 const size_t produced = (size_t)(op - out);
                 if (__builtin_expect(dist > produced, 0)) {
                     if (dist - produced > hist_len_) { bad = true; break; }
@@ -338,27 +352,40 @@ Inflater::Status Inflater::run(const uint8_t* in, size_t in_len, bool in_final, 
                         op[i] = pos < 0 ? hist_[(ptrdiff_t)hist_len_ + pos] : out[pos];
                     }
                     op += len;
-                    continue;
-                }
-                const uint8_t* src = op - dist;
-                uint8_t* const stop = op + len;
-                if (dist >= 8) {
-                    do { memcpy(op, src, 8); op += 8; src += 8; } while (op < stop);
-                } else if (dist == 1) {
-                    const uint64_t v = 0x0101010101010101ULL * (uint64_t)*src;
-                    do { memcpy(op, &v, 8); op += 8; } while (op < stop);
                 } else {
-                    do { *op++ = *src++; } while (op < stop);
+                    const uint8_t* src = op - dist;
+                    uint8_t* const stop = op + len;
+                    if (dist >= 8) {
+                        memcpy(op, src, 8);
+                        memcpy(op + 8, src + 8, 8);
+                        if (len > 16) {
+                            op += 16; src += 16;
+                            do { memcpy(op, src, 8); op += 8; src += 8; } while (op < stop);
+                        }
+                    } else if (dist == 1) {
+                        const uint64_t v = 0x0101010101010101ULL * (uint64_t)*src;
+                        memcpy(op, &v, 8);
+                        memcpy(op + 8, &v, 8);
+                        if (len > 16) {
+                            op += 16;
+                            do { memcpy(op, &v, 8); op += 8; } while (op < stop);
+                        }
+                    } else {
+                        do { *op++ = *src++; } while (op < stop);
+                    }
+                    op = stop;
                 }
-                op = stop;
+                if (ip > in_fast || op > out_fast) break;
             }
+#undef TREW_REFILL
+#undef TREW_LITS
             bb &= bc >= 64 ? ~(uint64_t)0 : (((uint64_t)1 << bc) - 1);   // drop the look-ahead bits above bitcnt
         }
         // ---- careful loop near the end of either buffer: one symbol at a time, committed only if it fits
         while (!block_done && !bad) {
             while (bc < 56 && ip < in_end) { bb |= (uint64_t)*ip++ << bc; bc += 8; }
             if (bc < 48 && !in_final) { st = kNeedInput; goto suspend; }
-            if (ip + 32 <= in_end && op + 320 <= out_end) break;   // (after a refill by the caller) back to the fast loop
+            if (ip + 48 <= in_end && op + 400 <= out_end) break;   // (after a refill by the caller) back to the fast loop
             uint64_t b2 = bb;
             int c2 = bc;
             uint64_t e = lit_[b2 & lit_mask];
