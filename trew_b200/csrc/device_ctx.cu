@@ -6,6 +6,7 @@
 // buffer, stream and completion event, so packing of batch i+1 on the host overlaps the H2D copy and
 // the kernels of batch i (double/triple buffering with cudaMemcpyAsync).
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -28,6 +29,7 @@ struct SlotRes {
     unsigned char* h_inv = nullptr;  // pinned: the batch's invalid-base records (sparse validity, see submit_ranges)
     unsigned char* d_inv = nullptr;
     size_t inv_cap = 0;              // records
+    unsigned int* h_keys = nullptr;  // pinned: the table's distinct-key count as of this slot's last batch
     unsigned int* d_survivors = nullptr;
     unsigned int* d_counters = nullptr;  // [0] n_survivors [1] work counter [2] n_deferred
     unsigned char* d_scratch = nullptr;
@@ -87,6 +89,7 @@ struct trew_ctx {
     Pool* pool = nullptr;
     std::string err;
     std::vector<RangeInfo> ranges_tmp;
+    unsigned int keys_seen = 0;                  // distinct keys reported by the batches retired so far (lags the device)
     bool sparse_val = true;                      // TREW_DENSE_VAL=1: always copy the validity plane
     std::vector<InvList> inv_tmp;                // per packing range: records of its blocks with invalid bases
     IngestScratch ingest;   // file block buffers, kept across files
@@ -175,6 +178,7 @@ int retire_slot(trew_ctx* ctx, SlotRes& s) {
     CK(cudaEventElapsedTime(&ms, s.ev_start, s.ev_done));
     ctx->stats.device_ms += ms;
     s.in_flight = false;
+    ctx->keys_seen = std::max(ctx->keys_seen, *s.h_keys);
     return TREW_OK;
 }
 
@@ -205,12 +209,18 @@ int grow_table_to(trew_ctx* ctx, size_t min_slots) {
     CK(cudaStreamSynchronize(ctx->main_stream));
     CK(cudaFree(d_old));
     ctx->stats.kernel_launches += 1;
+    ctx->keys_seen = (unsigned int)n;
+    for (auto& sl : ctx->slots) *sl.h_keys = (unsigned int)n;
     return check_device_error(ctx);
 }
 
 int maybe_grow_table(trew_ctx* ctx) {
+    // Every batch copies the key counter back behind its kernels (no host wait); that value lags by the batches in
+    // flight, so it only serves to skip the exact, blocking read while the table is far (4x) from the threshold.
+    if ((size_t)ctx->keys_seen * 16 <= ctx->n_slots) return TREW_OK;
     unsigned int keys = 0;
     CK(cudaMemcpy(&keys, ctx->d_error + 1, sizeof(keys), cudaMemcpyDeviceToHost));
+    ctx->keys_seen = std::max(ctx->keys_seen, keys);
     if ((size_t)keys * 4 <= ctx->n_slots) return TREW_OK;
     return grow_table_to(ctx, (size_t)keys * 8);
 }
@@ -222,9 +232,14 @@ int submit_ranges(trew_ctx* ctx, const ChunkView& cv, const RangeInfo* rg, int n
     if (n == 0) return TREW_OK;
     SlotRes& s = ctx->slots[ctx->next_slot];
     ctx->next_slot = (ctx->next_slot + 1) % ctx->slots.size();
+    static const bool trace = getenv("TREW_SUBMIT_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = trace ? now() : 0;
     int rc = retire_slot(ctx, s);
     if (rc) return rc;
+    const double t1 = trace ? now() : 0;
     if ((rc = maybe_grow_table(ctx)) != TREW_OK) return rc;
+    const double t2 = trace ? now() : 0;
     BatchView v;
     batch_layout(s.h_buf, n, total_bases, &v);
     std::vector<uint64_t> bit0((size_t)n_ranges);
@@ -258,17 +273,20 @@ int submit_ranges(trew_ctx* ctx, const ChunkView& cv, const RangeInfo* rg, int n
         if (n_inv > s.inv_cap) { sparse = false; pack(false); }
     }
 
+    const double t3 = trace ? now() : 0;
     CK(cudaEventRecord(s.ev_start, s.stream));
     const size_t head_bytes = (size_t)((char*)v.val - (char*)s.h_buf);
     unsigned int* d_val = (unsigned int*)((char*)s.d_buf + head_bytes);
     size_t sent = v.bytes;
     if (sparse) {
-        unsigned char* dst = s.h_inv;
-        for (int i = 0; i < n_ranges; i++) {
+        // the ranges' record lists, back to back in the pinned buffer (on the pool: ~2 MB per batch at 0.1 % N)
+        std::vector<size_t> at((size_t)n_ranges + 1, 0);
+        for (int i = 0; i < n_ranges; i++) at[(size_t)i + 1] = at[(size_t)i] + ctx->inv_tmp[(size_t)i].bytes();
+        ctx->pool->run(n_ranges, [&](int i) {
             const InvList& l = ctx->inv_tmp[(size_t)i];
-            if (l.bytes()) { memcpy(dst, l.buf.get(), l.bytes()); dst += l.bytes(); }
-        }
-        if (tail_pad) inv_record(dst, (uint32_t)total_bases, (1ULL << (32 - (total_bases & 31))) - 1ULL);
+            if (l.bytes()) memcpy(s.h_inv + at[(size_t)i], l.buf.get(), l.bytes());
+        });
+        if (tail_pad) inv_record(s.h_inv + at[(size_t)n_ranges], (uint32_t)total_bases, (1ULL << (32 - (total_bases & 31))) - 1ULL);
         const size_t ones_words = (size_t)((total_bases + 31) / 32);
         CK(cudaMemsetAsync(d_val, 0xFF, ones_words * 4, s.stream));
         CK(cudaMemsetAsync(d_val + ones_words, 0, (v.plane_words - ones_words) * 4, s.stream));
@@ -290,9 +308,13 @@ int submit_ranges(trew_ctx* ctx, const ChunkView& cv, const RangeInfo* rg, int n
     uint32_t n_units = ctx->cfg.mode == TREW_MODE_PAIR ? n / 2 : n;
     rc = launch_scan(ctx, b, n_units, max_len, s.d_survivors, s.d_counters, &s.d_scratch, &s.scratch_bytes, s.stream);
     if (rc) return rc;
+    CK(cudaMemcpyAsync(s.h_keys, ctx->d_error + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, s.stream));
     CK(cudaEventRecord(s.ev_done, s.stream));
     s.in_flight = true;
     ctx->stats.reads += n; ctx->stats.bases += total_bases; ctx->stats.units += n_units; ctx->stats.h2d_bytes += sent;
+    if (trace)
+        fprintf(stderr, "[submit] %u reads: wait slot %.3f ms, table check %.3f ms, pack %.3f ms, enqueue %.3f ms\n", n, t1 - t0, t2 - t1,
+                t3 - t2, now() - t3);
     return TREW_OK;
 }
 
@@ -507,6 +529,8 @@ int trew_dev_create(const trew_config* cfg, trew_ctx** out) {
         s.inv_cap = ctx->staging_bytes / 8 / kInvRecBytes;   // 1/8 of the slot: past that the dense plane is no larger
         CKC(cudaHostAlloc((void**)&s.h_inv, (s.inv_cap + 1) * kInvRecBytes, cudaHostAllocDefault));
         CKC(cudaMalloc((void**)&s.d_inv, (s.inv_cap + 1) * kInvRecBytes));
+        CKC(cudaHostAlloc((void**)&s.h_keys, sizeof(unsigned int), cudaHostAllocDefault));
+        *s.h_keys = 0;
         s.survivors_cap = ctx->staging_bytes / 8;  // >= reads of >= 11 bases; submit_split enforces it
         CKC(cudaMalloc((void**)&s.d_survivors, 2 * s.survivors_cap * sizeof(unsigned int)));
         CKC(cudaMalloc((void**)&s.d_counters, 4 * sizeof(unsigned int)));
@@ -531,6 +555,7 @@ void trew_dev_destroy(trew_ctx* ctx) {
         if (s.d_buf) cudaFree(s.d_buf);
         if (s.h_inv) cudaFreeHost(s.h_inv);
         if (s.d_inv) cudaFree(s.d_inv);
+        if (s.h_keys) cudaFreeHost(s.h_keys);
         if (s.d_survivors) cudaFree(s.d_survivors);
         if (s.d_counters) cudaFree(s.d_counters);
         if (s.d_scratch) cudaFree(s.d_scratch);
@@ -614,6 +639,7 @@ int trew_dev_submit_packed(trew_ctx* ctx, const trew_batch* batch) {
     uint32_t n_units = ctx->cfg.mode == TREW_MODE_PAIR ? n / 2 : n;
     rc = launch_scan(ctx, b, n_units, batch->max_read_len, s.d_survivors, s.d_counters, &s.d_scratch, &s.scratch_bytes, s.stream);
     if (rc) return rc;
+    CK(cudaMemcpyAsync(s.h_keys, ctx->d_error + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, s.stream));
     CK(cudaEventRecord(s.ev_done, s.stream));
     s.in_flight = true;
     ctx->stats.reads += n; ctx->stats.bases += bases; ctx->stats.units += n_units; ctx->stats.h2d_bytes += v.bytes;
@@ -652,6 +678,7 @@ int trew_dev_scan_resident(trew_ctx* ctx, const trew_resident* rb) {
     if (!ctx || !rb) return TREW_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
     trew_resident* r = const_cast<trew_resident*>(rb);
+    ctx->keys_seen = std::max<unsigned int>(ctx->keys_seen, (unsigned int)(ctx->n_slots / 16 + 1));   // keys arrive outside the staging ring: streaming batches ask the device again
     if (r->ev_pending) { int rc0 = collect_prof(ctx); if (rc0) return rc0; }
     if (!r->ev[0]) for (int i = 0; i < 4; i++) CK(cudaEventCreate(&r->ev[i]));
     cudaStream_t st = (ctx->resident_streams == 2 && (ctx->resident_seq++ & 1)) ? ctx->aux_stream : ctx->main_stream;
@@ -876,6 +903,7 @@ int trew_dev_merge_rows(trew_ctx* ctx, const trew_entry* d_rows, uint64_t n_rows
     if (!ctx || (n_rows && !d_rows) || n_rows > 0xffffffffULL) return TREW_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
     ctx->export_valid = false;
+    ctx->keys_seen = std::max<unsigned int>(ctx->keys_seen, (unsigned int)(ctx->n_slots / 16 + 1));
     launch_merge_entries(ctx->dcfg, d_rows, (unsigned int)n_rows, ctx->main_stream);   // asynchronous: the next sync / export
     CK(cudaGetLastError());                                                             // waits and checks the error flag
     ctx->stats.kernel_launches += n_rows ? 1 : 0;
@@ -902,6 +930,8 @@ int trew_dev_reset(trew_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->dcfg.slots, 0, ctx->n_slots * sizeof(Slot), ctx->main_stream));
     CK(cudaMemsetAsync(ctx->d_error, 0, 2 * sizeof(unsigned int), ctx->main_stream));
     CK(cudaStreamSynchronize(ctx->main_stream));
+    ctx->keys_seen = 0;
+    for (auto& sl : ctx->slots) *sl.h_keys = 0;
     return TREW_OK;
 }
 

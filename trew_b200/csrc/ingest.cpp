@@ -221,18 +221,33 @@ struct Reader {
     }
 
     // make sure cbuf holds the whole block that starts at file offset `offset` (or as much as the file has)
-    bool bgzf_window(size_t want_bytes) {
+    bool bgzf_window(size_t want_bytes, Pool* pool) {
         if (offset >= cbuf_off && offset + 65536 + 64 <= cbuf_off + cbuf.size()) return true;
         size_t len = (size_t)std::min<uint64_t>(std::max<size_t>(want_bytes, (size_t)1 << 20), (uint64_t)size - offset);
         cbuf.resize(len);
         cbuf_off = offset;
-        size_t a = 0;
-        while (a < len) {
-            ssize_t r = pread(fd, cbuf.data() + a, len - a, (off_t)(cbuf_off + a));
-            if (r < 0) { if (errno == EINTR) continue; return false; }
-            if (r == 0) { cbuf.resize(a); break; }
-            a += (size_t)r;
+        // the copy out of the page cache scales with cores like the plain-file read does
+        const int P = pool && len >= ((size_t)4 << 20) ? pool->size() : 1;
+        std::vector<size_t> got((size_t)P, 0);
+        std::vector<char> okv((size_t)P, 1);
+        auto slice = [&](int i) {
+            size_t a = len * (size_t)i / (size_t)P;
+            const size_t b = len * (size_t)(i + 1) / (size_t)P;
+            while (a < b) {
+                ssize_t r = pread(fd, cbuf.data() + a, b - a, (off_t)(cbuf_off + a));
+                if (r < 0) { if (errno == EINTR) continue; okv[(size_t)i] = 0; return; }
+                if (r == 0) break;
+                a += (size_t)r; got[(size_t)i] += (size_t)r;
+            }
+        };
+        if (P > 1) pool->run(P, slice); else slice(0);
+        size_t total = 0;
+        for (int i = 0; i < P; i++) {
+            if (!okv[(size_t)i]) return false;
+            total += got[(size_t)i];
+            if (got[(size_t)i] < len * (size_t)(i + 1) / (size_t)P - len * (size_t)i / (size_t)P) break;   // the file ended here
         }
+        cbuf.resize(total);
         return true;
     }
 
@@ -245,7 +260,7 @@ struct Reader {
             if (pending_pos == pending.size()) { pending.clear(); pending_pos = 0; }
         }
         while (done < n && offset < (uint64_t)size) {
-            if (!bgzf_window(n / 2 + ((size_t)4 << 20))) return -1;
+            if (!bgzf_window(n / 2 + ((size_t)4 << 20), pool)) return -1;
             // plan the blocks of this window that fit the caller's buffer
             std::vector<BgzfBlock> plan;
             uint64_t off = offset;
