@@ -219,3 +219,37 @@ def test_count_table_grows_while_streaming():
         ctx.submit_reads(reads)
         got = ctx.finish()
     assert got == want, diff_msg(got, want)
+
+
+def test_sparse_and_dense_validity_paths(monkeypatch):
+    """The streaming path sends the invalid bases as records (block position + mask) and rebuilds the validity plane
+    on the device; a batch with more N-bearing blocks than the record buffer holds is packed again densely.  Both
+    routes, and TREW_DENSE_VAL=1, must give the oracle's tables."""
+    from oracle.oracle import Oracle
+    rng = np.random.default_rng(77)
+    base = synth.adversarial_short(15, 1500)
+    noisy = []
+    for r in base:   # N in almost every 64-base block, repeats still visible in places
+        a = np.frombuffer(r, dtype=np.uint8).copy()
+        if a.size:
+            a[rng.random(a.size) < 0.03] = ord("N")
+        noisy.append(a.tobytes())
+    clustered = [b"N" * 150, b"TTAGGG" * 10 + b"N" * 30 + b"TTAGGG" * 10, b"n" * 64 + b"CCCTAA" * 15, b"ACGT" * 16 + b"." + b"ACGT" * 16]
+    reads = noisy + clustered * 50 + base
+    want = Oracle(5, 32).scan(0, reads)
+
+    def run(**kw):
+        with api.DeviceContext(api.MODE_SHORT, 5, 32, **kw) as ctx:
+            ctx.submit_reads(reads)
+            got = ctx.finish()
+            return got, ctx.stats().h2d_bytes
+
+    sparse, b_sparse = run()                                         # default 64 MiB slots: everything fits the record buffer
+    overflow, b_over = run(staging_bytes=1 << 18, n_staging=2)       # 256 KiB slots hold 2730 records: most batches fall back
+    monkeypatch.setenv("TREW_DENSE_VAL", "1")
+    dense, b_dense = run(staging_bytes=1 << 18, n_staging=2)
+    assert sparse == want, diff_msg(sparse, want)
+    assert overflow == want, diff_msg(overflow, want)
+    assert dense == want, diff_msg(dense, want)
+    assert b_sparse < b_dense                                        # the records are smaller than the plane they replace
+    assert b_over <= b_dense and b_over > 0.9 * b_dense              # the fallback copied (nearly) everything densely

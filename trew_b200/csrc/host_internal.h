@@ -173,6 +173,9 @@ public:
 private:
     enum State { kHeader, kStored, kHuffman, kDone };
     static constexpr size_t kWindow = 32768, kLitCap = 4096, kDistCap = 1024;   // tables: worst cases are 2342 / 402 entries
+    Status run_impl(const uint8_t* in, size_t in_len, bool in_final, size_t* in_used, uint8_t* out, size_t out_cap, size_t* out_used);
+    Status run_generic(const uint8_t* in, size_t in_len, bool in_final, size_t* in_used, uint8_t* out, size_t out_cap, size_t* out_used);
+    Status run_bmi2(const uint8_t* in, size_t in_len, bool in_final, size_t* in_used, uint8_t* out, size_t out_cap, size_t* out_used);
     bool read_header(const uint8_t*& ip, const uint8_t* in_end);
     void save_history(const uint8_t* out, size_t produced);
     uint64_t bitbuf_;

@@ -250,8 +250,31 @@ bool Inflater::read_header(const uint8_t*& ip, const uint8_t* in_end) {
     return ok;
 }
 
+// One body, compiled twice: with BMI2 the variable shifts of the bit buffer are single three-operand instructions
+// (about 10 % on the whole decode); run() picks at run time.
 Inflater::Status Inflater::run(const uint8_t* in, size_t in_len, bool in_final, size_t* in_used, uint8_t* out, size_t out_cap,
                                size_t* out_used) {
+#if defined(__x86_64__)
+    static const bool bmi2 = __builtin_cpu_supports("bmi2") && __builtin_cpu_supports("bmi");
+    if (bmi2) return run_bmi2(in, in_len, in_final, in_used, out, out_cap, out_used);
+#endif
+    return run_generic(in, in_len, in_final, in_used, out, out_cap, out_used);
+}
+
+#if defined(__x86_64__)
+__attribute__((target("bmi,bmi2"))) Inflater::Status Inflater::run_bmi2(const uint8_t* in, size_t in_len, bool in_final, size_t* in_used,
+                                                                        uint8_t* out, size_t out_cap, size_t* out_used) {
+    return run_impl(in, in_len, in_final, in_used, out, out_cap, out_used);
+}
+#endif
+
+Inflater::Status Inflater::run_generic(const uint8_t* in, size_t in_len, bool in_final, size_t* in_used, uint8_t* out, size_t out_cap,
+                                       size_t* out_used) {
+    return run_impl(in, in_len, in_final, in_used, out, out_cap, out_used);
+}
+
+__attribute__((always_inline)) inline Inflater::Status Inflater::run_impl(const uint8_t* in, size_t in_len, bool in_final, size_t* in_used,
+                                                                          uint8_t* out, size_t out_cap, size_t* out_used) {
     const uint8_t* ip = in;
     const uint8_t* const in_end = in + in_len;
     uint8_t* op = out;
