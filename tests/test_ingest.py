@@ -141,17 +141,21 @@ def test_parallel_newline_index_equals_serial(tmp_path, simd):
         import os, sys
         from trew_b200 import api
         p1, p2, p3 = sys.argv[1:4]
-        def run(par, mode, f1, f2, chunk):
+        def run(par, mode, f1, f2, chunk, nommap=False):
             if par: os.environ["TREW_INGEST_PAR_MIN"] = par
             else: os.environ.pop("TREW_INGEST_PAR_MIN", None)
+            if nommap: os.environ["TREW_NO_MMAP"] = "1"     # read() into a buffer instead of mapping the file
+            else: os.environ.pop("TREW_NO_MMAP", None)
             return api.ingest_records(mode, f1, f2, slice_length=100, chunk_bytes=chunk)
         for chunk in (0, 777, 4096):
             for mode, f1, f2 in ((api.MODE_SHORT, p1, None), (api.MODE_SHORT, p2, None), (api.MODE_LONG, p1, None),
                                  (api.MODE_PAIR, p3, p2)):
                 want = run(None, mode, f1, f2, chunk)
                 for par in ("1", "50", "300"):
-                    got = run(par, mode, f1, f2, chunk)
-                    assert got == want, (chunk, mode, par)
+                    for nommap in (False, True):
+                        got = run(par, mode, f1, f2, chunk, nommap)
+                        assert got == want, (chunk, mode, par, nommap)
+                assert run(None, mode, f1, f2, chunk, True) == want
                 assert want[0] == 0 and len(want[2]) > 0
         print("ok")
     """)

