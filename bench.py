@@ -371,8 +371,8 @@ def file_e2e(ctx, api, synth, rank):
                 best = dt if best is None else min(best, dt)
             out[name] = {"value": n * READ_LEN / best / 1e9, "unit": "Gbases/s", "reads": n, "file_bytes": os.path.getsize(path)}
         out["note"] = ("one file: plain gzip is bound by single-stream inflate as in the reference (the library's own DEFLATE decoder, "
-                       "about 2x zlib); BGZF (bgzip) members are inflated in parallel; plain FASTQ by reading, newline indexing "
-                       "and packing")
+                       "about 2x zlib); BGZF (bgzip) members are inflated in parallel; plain FASTQ by the newline index and the packer, both working "
+                       "on the mapped file")
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     return out
