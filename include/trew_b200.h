@@ -219,14 +219,16 @@ int trew_pack_reads_ranges(const char* buffer, const int32_t* locs, uint32_t n, 
 
 /* ---- whole-file convenience: process_kmer / _pair / _long (src/kmer.cpp:1266-1476) -------------- */
 
-/* Reads FASTQ / FASTQ.gz with the reference's record semantics (every 4k+2-th line is a sequence,
- * 4 MiB - 1 chunks, short mode rejects reads > 1000, long mode drops reads < SLICE_LENGTH) and feeds
- * the context.  file2 must be NULL unless mode is TREW_MODE_PAIR.  is_gz*: 1 = zlib, 0 = plain. */
+/* Reads FASTQ / FASTQ.gz with the reference's record semantics (every 4k+2-th line is a sequence, short mode
+ * rejects reads > 1000, long mode drops reads < SLICE_LENGTH; the reference's 4 MiB - 1 chunking has no observable
+ * effect and is not reproduced) and feeds the context.  file2 must be NULL unless mode is TREW_MODE_PAIR.
+ * is_gz*: 1 = gzip (BGZF members are inflated in parallel), 0 = plain (regular files are mapped). */
 int trew_dev_process_file(trew_ctx* ctx, const char* file1, int is_gz1, const char* file2, int is_gz2);
 
 /* The reader alone (no device): calls `sink` once per chunk with the text buffer(s) and the inclusive
  * (st, nd) offsets of the sequence lines it found -- what the reference's reader threads push as
- * QueueData / PairQueueData.  A non-zero return from sink aborts.  message (may be NULL) receives the
+ * QueueData / PairQueueData.  The buffers are read-only and valid only during the call.  chunk_bytes: bytes per
+ * block, 0 = chosen by input kind.  A non-zero return from sink aborts.  message (may be NULL) receives the
  * reference's error text on failure. */
 typedef int (*trew_chunk_sink)(void* user, const char* buffer1, const int32_t* locs1, uint32_t n1,
                                const char* buffer2, const int32_t* locs2, uint32_t n2);

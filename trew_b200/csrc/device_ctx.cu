@@ -1013,7 +1013,7 @@ int trew_dev_process_file(trew_ctx* ctx, const char* file1, int is_gz1, const ch
     if (!ctx || !file1) return TREW_ERR_ARG;
     if ((ctx->cfg.mode == TREW_MODE_PAIR) != (file2 != nullptr)) return fail(ctx, TREW_ERR_ARG, "second file only in pair mode");
     // plain files: large blocks read and indexed by the pool; .gz: the inflate stream is sequential, keep blocks small
-    const size_t chunk = (is_gz1 || is_gz2) ? ((size_t)32 << 20) : ((size_t)256 << 20);
+    const size_t chunk = 0;   // the reader picks the block size by input kind
     IngestResult r = ingest_file(ctx->cfg.mode, ctx->cfg.slice_length, file1, is_gz1 != 0, file2, is_gz2 != 0, chunk,
                                  [&](const char* b1, const std::vector<int32_t>& l1, const char* b2, const std::vector<int32_t>& l2) {
                                      return trew_dev_submit_chunk(ctx, b1, l1.data(), (uint32_t)(l1.size() / 2), b2,

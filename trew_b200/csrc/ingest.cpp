@@ -682,6 +682,7 @@ IngestResult ingest_file(int mode, int slice_length, const char* file1, bool gz1
                          size_t chunk_bytes, const ChunkSink& sink, Pool* pool, IngestScratch* scratch) {
     IngestResult res{TREW_OK, ""};
     static const std::vector<int32_t> kEmpty;
+    const bool auto_chunk = chunk_bytes == 0;
     if (chunk_bytes > ((size_t)1 << 30)) chunk_bytes = (size_t)1 << 30;  // offsets are int32 like the reference's
     // fresh bytes from which reading / newline indexing go parallel (TREW_INGEST_PAR_MIN: tests force the path)
     size_t par_min = (size_t)4 << 20;
@@ -691,6 +692,13 @@ IngestResult ingest_file(int mode, int slice_length, const char* file1, bool gz1
     if (!a.rd.open(file1, gz1)) return IngestResult{TREW_ERR_IO, "File open failed"};
     const bool pair = mode == TREW_MODE_PAIR;
     if (pair && !b.rd.open(file2, gz2)) return IngestResult{TREW_ERR_IO, "File open failed"};
+    if (auto_chunk) {
+        // block size by what bounds the block: a sequential inflate stream wants short blocks (nothing overlaps it),
+        // parallel inflate and mapped plain files want few hand-offs between the phases
+        const bool stream = (a.rd.gz && !a.rd.bgzf) || (pair && b.rd.gz && !b.rd.bgzf);
+        const bool bgzf = a.rd.bgzf || (pair && b.rd.bgzf);
+        chunk_bytes = stream ? ((size_t)32 << 20) : bgzf ? ((size_t)128 << 20) : ((size_t)256 << 20);
+    }
     bool too_long = false;
     const bool trace = getenv("TREW_INGEST_TRACE") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -766,7 +774,7 @@ extern "C" int trew_ingest_file(int mode, int slice_length, const char* file1, i
     if (!file1 || !sink || mode < 0 || mode > 2 || (mode == TREW_MODE_PAIR) != (file2 != nullptr)) return TREW_ERR_ARG;
     trew::Pool pool(4);
     trew::IngestResult r = trew::ingest_file(
-        mode, slice_length, file1, is_gz1 != 0, file2, is_gz2 != 0, chunk_bytes ? (size_t)chunk_bytes : ((size_t)32 << 20),
+        mode, slice_length, file1, is_gz1 != 0, file2, is_gz2 != 0, (size_t)chunk_bytes,
         [&](const char* b1, const std::vector<int32_t>& l1, const char* b2, const std::vector<int32_t>& l2) {
             return sink(user, b1, l1.data(), (uint32_t)(l1.size() / 2), b2, b2 ? l2.data() : nullptr, b2 ? (uint32_t)(l2.size() / 2) : 0u);
         },
