@@ -83,3 +83,46 @@ def test_process_file_equals_submit(tmp_path):
         ctx.submit_reads(reads)
         b = ctx.finish()
     assert a == b and len(a) > 0
+
+
+def test_process_file_every_input_kind(tmp_path, monkeypatch):
+    """Plain (mapped and read), gzip (own decoder and zlib), multi-member gzip and BGZF inputs of the same records give
+    the same tables as submitting the reads directly, single and paired."""
+    r1 = synth.adversarial_short(32, 4000, lengths=[100, 150, 151])
+    r2 = synth.adversarial_short(33, 4000, lengths=[100, 150, 151])
+    d = str(tmp_path)
+    paths = {}
+    for tag, reads in (("1", r1), ("2", r2)):
+        data = synth.fastq_bytes(reads)
+        plain = os.path.join(d, "r%s.fastq" % tag)
+        open(plain, "wb").write(data)
+        gz = plain + ".gz"
+        with gzip.open(gz, "wb") as f:
+            f.write(data)
+        multi = os.path.join(d, "m%s.fastq.gz" % tag)
+        cut = len(data) // 3
+        cut = data.index(b"\n", cut) + 1
+        open(multi, "wb").write(gzip.compress(data[:cut]) + gzip.compress(data[cut:], 1))
+        bgz = os.path.join(d, "b%s.fastq.bgz" % tag)
+        synth.bgzf_write(plain, bgz)
+        paths[tag] = {"plain": plain, "gz": gz, "multi": multi, "bgzf": bgz}
+    with api.DeviceContext(api.MODE_SHORT, 5, 32) as ctx:
+        ctx.submit_reads(r1)
+        want = ctx.finish()
+        assert len(want) > 0
+        for env in ({}, {"TREW_NO_MMAP": "1", "TREW_ZLIB_GZ": "1"}):
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            for kind, p in paths["1"].items():
+                ctx.reset()
+                ctx.process_file(p)
+                assert ctx.finish() == want, (kind, env)
+    with api.DeviceContext(api.MODE_PAIR, 5, 32) as ctx:
+        for k in ("TREW_NO_MMAP", "TREW_ZLIB_GZ"):
+            monkeypatch.delenv(k, raising=False)
+        ctx.submit_reads(r1, r2)
+        want = ctx.finish()
+        for kind in ("plain", "gz", "bgzf"):
+            ctx.reset()
+            ctx.process_file(paths["1"][kind], paths["2"][kind])
+            assert ctx.finish() == want, kind
