@@ -213,9 +213,9 @@ int trew_pack_reads(const char* buffer, const int32_t* locs, uint32_t n, void* d
  * plane when it is short, and then does not write the plane either: TREW_PACK_NO_VAL in `flags` (needs inv) asks
  * for the same -- the contents of out->val are then unspecified. */
 #define TREW_PACK_NO_VAL 1u
-int trew_pack_reads_ranges(const char* buffer, const int32_t* locs, uint32_t n, uint32_t n_ranges, uint32_t n_threads,
-                           uint32_t flags, void* dst, size_t dst_bytes, trew_batch* out, uint32_t* inv, size_t inv_cap,
-                           size_t* n_inv);
+int trew_pack_reads_ranges(const char* buffer, const int32_t* locs, const char* buffer2, const int32_t* locs2, uint32_t n,
+                           uint32_t n_ranges, uint32_t n_threads, uint32_t flags, void* dst, size_t dst_bytes, trew_batch* out,
+                           uint32_t* inv, size_t inv_cap, size_t* n_inv);
 
 /* ---- whole-file convenience: process_kmer / _pair / _long (src/kmer.cpp:1266-1476) -------------- */
 

@@ -86,3 +86,33 @@ def test_pack_ranges_equal_single_pass_and_list_the_invalid_bases(simd, n_ranges
     env = dict(os.environ, TREW_PACK_SIMD=simd)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(__file__)))
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("simd", ["0", "1", "2"])
+def test_pack_paired_chunk_equals_interleaved_reads(simd):
+    """A paired chunk (two buffers, mates alternating in the batch) packs to exactly what the interleaved read list
+    packs to -- planes, offsets and invalid-base list -- for every instruction set and cut into ranges."""
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import numpy as np
+        from trew_b200 import api, synth
+        a = synth.adversarial_short(8, 700) + [b"", b"N" * 70, b"ACGT" * 40, b"T"]
+        b = synth.adversarial_short(9, 700) + [b"ACGTN", b"", b"n" * 129, b"G" * 64]
+        inter = [r for pair in zip(a, b) for r in pair]
+        ref = api.PackedBatch(*api.make_chunk(inter))
+        b1, l1 = api.make_chunk(a)
+        b2, l2 = api.make_chunk(b)
+        val = ref.planes()[3]
+        want = np.flatnonzero(np.unpackbits(val.view(np.uint8), bitorder="little")[:ref.bases] == 0).tolist()
+        for n_ranges, n_threads in ((1, 1), (5, 2), (64, 4), (2000, 3)):
+            for no_val in (False, True):
+                got = api.PackedBatch(b1, l1, n_ranges=n_ranges, n_threads=n_threads, want_invalid=True, no_val=no_val, buf2=b2, locs2=l2)
+                assert got.n_reads == ref.n_reads and got.bases == ref.bases
+                for x, y in list(zip(ref.planes(), got.planes()))[:3 if no_val else 4]:
+                    assert (x == y).all(), (n_ranges, no_val)
+                assert sorted(got.invalid.tolist()) == want
+        print("ok")
+    """)
+    env = dict(os.environ, TREW_PACK_SIMD=simd)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(__file__)))
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]

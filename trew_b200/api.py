@@ -109,7 +109,7 @@ def load_library() -> C.CDLL:
     L.trew_pack_bound.argtypes = [C.c_uint32, C.c_uint64]
     L.trew_pack_bound.restype = C.c_size_t
     L.trew_pack_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(Batch)]
-    L.trew_pack_reads_ranges.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t,
+    L.trew_pack_reads_ranges.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t,
                                          C.POINTER(Batch), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.trew_dev_process_file.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
     L.trew_synth_resident.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
@@ -159,7 +159,7 @@ class PackedBatch:
     """A packed batch in host memory (owner of the buffer the trew_batch pointers point into)."""
 
     def __init__(self, buf: np.ndarray, locs: np.ndarray, n_ranges: int = 0, n_threads: int = 1, want_invalid: bool = False,
-                 no_val: bool = False):
+                 no_val: bool = False, buf2: Optional[np.ndarray] = None, locs2: Optional[np.ndarray] = None):
         """n_ranges > 0 packs through trew_pack_reads_ranges (concurrent ranges, optional invalid-base list in
         self.invalid, no_val = TREW_PACK_NO_VAL); otherwise through the single-threaded trew_pack_reads."""
         L = load_library()
@@ -169,7 +169,13 @@ class PackedBatch:
         lens = (locs[:, 1].astype(np.int64) - locs[:, 0].astype(np.int64) + 1).clip(min=0)
         self.n_reads = n
         self.bases = int(lens.sum())
-        self.nbytes = L.trew_pack_bound(n, self.bases)
+        if buf2 is not None:   # a paired chunk (needs n_ranges > 0): 2 n reads, mates alternating
+            buf2 = np.ascontiguousarray(buf2, dtype=np.uint8)
+            locs2 = np.ascontiguousarray(locs2, dtype=np.int32).reshape(-1, 2)
+            assert locs2.shape[0] == n and n_ranges > 0
+            self.n_reads = 2 * n
+            self.bases += int((locs2[:, 1].astype(np.int64) - locs2[:, 0].astype(np.int64) + 1).clip(min=0).sum())
+        self.nbytes = L.trew_pack_bound(self.n_reads, self.bases)
         self.mem = np.zeros(self.nbytes, dtype=np.uint8)
         self.batch = Batch()
         self.invalid = None
@@ -177,7 +183,9 @@ class PackedBatch:
             cap = self.bases + 64 if want_invalid else 0
             inv = np.zeros(max(cap, 1), dtype=np.uint32)
             n_inv = C.c_size_t(0)
-            rc = L.trew_pack_reads_ranges(buf.ctypes.data, locs.ctypes.data, n, n_ranges, n_threads, 1 if no_val else 0, self.mem.ctypes.data,
+            rc = L.trew_pack_reads_ranges(buf.ctypes.data, locs.ctypes.data, buf2.ctypes.data if buf2 is not None else None,
+                                          locs2.ctypes.data if buf2 is not None else None, n, n_ranges, n_threads,
+                                          1 if no_val else 0, self.mem.ctypes.data,
                                           self.nbytes, C.byref(self.batch), inv.ctypes.data if want_invalid else None, cap,
                                           C.byref(n_inv))
             if want_invalid and not rc:

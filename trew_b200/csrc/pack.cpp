@@ -249,9 +249,14 @@ TREW_AVX512 __attribute__((always_inline)) inline void pack_read_avx512(BitWrite
 // constant strides, no first-unit test.  Precondition: the writer has left its first unit.
 // LIST: record the blocks with invalid bases in *inv (branch-free: see inv_record).  VAL == false (needs LIST): the val plane is not written at all -- a third
 // less store traffic; the list is then the only record of validity.
-template <bool LIST, bool VAL>
-TREW_AVX512 void pack_lean_avx512(const char* buf, const int32_t* locs, uint32_t r0, uint32_t r1, uint32_t* off, BitWriter& w_out,
-                                  InvList* inv) {
+// PAIR: read r is mate (r & 1) of pair (r >> 1), the mates coming from the chunk's two buffers.
+template <bool LIST, bool VAL, bool PAIR>
+TREW_AVX512 void pack_lean_avx512(const ChunkView& cv, uint32_t r0, uint32_t r1, uint32_t* off, BitWriter& w_out, InvList* inv) {
+    const char* const buf0 = cv.buf[0];
+    const char* const buf1 = PAIR ? cv.buf[1] : buf0;
+    const int32_t* const locs0 = cv.locs[0];
+    const int32_t* const locs1 = PAIR ? cv.locs[1] : locs0;
+    constexpr uint32_t kAhead = PAIR ? 2u * kPrefetchReads : kPrefetchReads;   // the same mate, kPrefetchReads pairs on
     const __m512i lut = _mm512_broadcast_i32x4(_mm_setr_epi8(0, 'a', 0, 'c', 't', 0, 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0));
     const __m512i case_bit = _mm512_set1_epi8(0x20), b2 = _mm512_set1_epi8(4), b1 = _mm512_set1_epi8(2);
     long long* ph = (long long*)(w_out.hi + w_out.unit);
@@ -261,14 +266,16 @@ TREW_AVX512 void pack_lean_avx512(const char* buf, const int32_t* locs, uint32_t
     uint32_t pos = (uint32_t)(w_out.unit * 64 + fill);
     unsigned char* ip = LIST ? inv->p : nullptr;
     for (uint32_t r = r0; r < r1; r++) {
-        const int32_t st = locs[2 * (size_t)r], nd = locs[2 * (size_t)r + 1];
+        const char* const buf = PAIR && (r & 1u) ? buf1 : buf0;
+        const int32_t* const locs = (PAIR && (r & 1u) ? locs1 : locs0) + 2 * (size_t)(PAIR ? r >> 1 : r);
+        const int32_t st = locs[0], nd = locs[1];
         const uint32_t len = nd >= st ? (uint32_t)(nd - st + 1) : 0u;
         const unsigned char* s = (const unsigned char*)buf + st;
         *off++ = pos;
 #if TREW_PACK_PREFETCH
         {   // short reads: the read kPrefetchReads ahead (the bytes between reads -- FASTQ headers, qualities -- are
             // not wanted); long reads: further along the same read
-            const unsigned char* pf = len <= 512u ? (const unsigned char*)buf + locs[2 * (size_t)(r + kPrefetchReads < r1 ? r + kPrefetchReads : r)]
+            const unsigned char* pf = len <= 512u ? (const unsigned char*)buf + locs[r + kAhead < r1 ? 2 * (size_t)kPrefetchReads : 0]
                                                   : s + TREW_PACK_PREFETCH;
             for (uint32_t q = 0; q < len; q += 64) _mm_prefetch((const char*)pf + q, TREW_PACK_PREFETCH_HINT);
         }
@@ -326,24 +333,16 @@ TREW_AVX512 void pack_reads_avx512(const ChunkView& cv, uint32_t r0, uint32_t r1
         *off++ = (uint32_t)pos; pos += len;
         pack_read_avx512<true>(w, (const unsigned char*)p, len, lut, case_bit, b2, b1, (uint32_t)pos - len, inv);
     }
-    if (cv.unit == 1 && r < r1) {   // single buffer: the lean steady-state loop
-        if (!inv) pack_lean_avx512<false, true>(cv.buf[0], cv.locs[0], r, r1, off, w, nullptr);
-        else if (skip_val) pack_lean_avx512<true, false>(cv.buf[0], cv.locs[0], r, r1, off, w, inv);
-        else pack_lean_avx512<true, true>(cv.buf[0], cv.locs[0], r, r1, off, w, inv);
-        w_out = w;
-        return;
-    }
-    for (; r < r1; r++) {
-        cv.get(r, p, len, slack);
-        *off++ = (uint32_t)pos; pos += len;
-#if TREW_PACK_PREFETCH
-        {
-            const uint32_t ra = r + kPrefetchReads * cv.unit;
-            const char* pf = len <= 512u ? cv.start(ra < r1 ? ra : r) : p + TREW_PACK_PREFETCH;
-            for (uint32_t q = 0; q < len; q += 64) _mm_prefetch(pf + q, TREW_PACK_PREFETCH_HINT);
+    if (r < r1) {   // the lean steady-state loop
+        if (cv.unit == 1) {
+            if (!inv) pack_lean_avx512<false, true, false>(cv, r, r1, off, w, nullptr);
+            else if (skip_val) pack_lean_avx512<true, false, false>(cv, r, r1, off, w, inv);
+            else pack_lean_avx512<true, true, false>(cv, r, r1, off, w, inv);
+        } else {
+            if (!inv) pack_lean_avx512<false, true, true>(cv, r, r1, off, w, nullptr);
+            else if (skip_val) pack_lean_avx512<true, false, true>(cv, r, r1, off, w, inv);
+            else pack_lean_avx512<true, true, true>(cv, r, r1, off, w, inv);
         }
-#endif
-        pack_read_avx512<false>(w, (const unsigned char*)p, len, lut, case_bit, b2, b1, (uint32_t)pos - len, inv);
     }
     w_out = w;
 }
@@ -452,16 +451,21 @@ int trew_pack_reads(const char* buffer, const int32_t* locs, uint32_t n, void* d
     return TREW_OK;
 }
 
-int trew_pack_reads_ranges(const char* buffer, const int32_t* locs, uint32_t n, uint32_t n_ranges, uint32_t n_threads,
-                           uint32_t flags, void* dst, size_t dst_bytes, trew_batch* out, uint32_t* inv, size_t inv_cap,
-                           size_t* n_inv) {
+int trew_pack_reads_ranges(const char* buffer, const int32_t* locs, const char* buffer2, const int32_t* locs2, uint32_t n,
+                           uint32_t n_ranges, uint32_t n_threads, uint32_t flags, void* dst, size_t dst_bytes, trew_batch* out,
+                           uint32_t* inv, size_t inv_cap, size_t* n_inv) {
     if ((n && (!buffer || !locs)) || !dst || !out || ((uintptr_t)dst & 7) != 0 || (inv && !n_inv)) return TREW_ERR_ARG;
     if ((flags & TREW_PACK_NO_VAL) && !inv) return TREW_ERR_ARG;
+    if ((buffer2 != nullptr) != (locs2 != nullptr)) return TREW_ERR_ARG;
     if (n_ranges == 0) n_ranges = 1;
-    trew::ChunkView cv{{buffer, nullptr}, {locs, nullptr}, {nullptr, nullptr}, 1u};
+    const uint32_t unit = buffer2 ? 2u : 1u;   // pairs: the batch holds 2 n reads, mate 1 and mate 2 alternating
+    if (unit == 2 && n > 0x7fffffffu) return TREW_ERR_ARG;
+    trew::ChunkView cv{{buffer, buffer2}, {locs, locs2}, {nullptr, nullptr}, unit};
+    const uint32_t n_units = n;
+    n *= unit;
     std::vector<uint32_t> r0((size_t)n_ranges + 1);
     std::vector<uint64_t> bases(n_ranges), bit0(n_ranges);
-    for (uint32_t i = 0; i <= n_ranges; i++) r0[i] = (uint32_t)((uint64_t)n * i / n_ranges);
+    for (uint32_t i = 0; i <= n_ranges; i++) r0[i] = (uint32_t)((uint64_t)n_units * i / n_ranges) * unit;
     trew::Pool pool((int)(n_threads ? n_threads : 1u));
     std::vector<uint32_t> mxs(n_ranges);
     pool.run((int)n_ranges, [&](int i) { trew::chunk_stats(cv, r0[(size_t)i], r0[(size_t)i + 1], &bases[(size_t)i], &mxs[(size_t)i]); });
