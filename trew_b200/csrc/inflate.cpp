@@ -37,15 +37,19 @@ inline uint32_t reverse_bits(uint32_t code, int len) {
 
 enum Kind { kLitLen, kDist, kPre };
 
+// Table entry (32 bits): bits 0-7 the input bits the symbol uses in this table -- code bits plus, for lengths and
+// distances, the extra bits, so that one shift consumes the symbol --, 8-12 the number of extra bits (or the index
+// width of a second-level table), 12-15 flags, 16-31 literal / base value / second-level table start.
+
 inline uint32_t leaf(Kind kind, int sym, int bits) {
     if (kind == kLitLen) {
         if (sym < 256) return kLiteral | ((uint32_t)sym << 16) | (uint32_t)bits;
         if (sym == 256) return kExceptional | kEndOfBlock | (uint32_t)bits;
-        if (sym < 286) return ((uint32_t)kLenBase[sym - 257] << 16) | ((uint32_t)kLenExtra[sym - 257] << 8) | (uint32_t)bits;
+        if (sym < 286) return ((uint32_t)kLenBase[sym - 257] << 16) | ((uint32_t)kLenExtra[sym - 257] << 8) | (uint32_t)(bits + kLenExtra[sym - 257]);
         return kInvalid;
     }
     if (kind == kDist) {
-        if (sym < 30) return ((uint32_t)kDistBase[sym] << 16) | ((uint32_t)kDistExtra[sym] << 8) | (uint32_t)bits;
+        if (sym < 30) return ((uint32_t)kDistBase[sym] << 16) | ((uint32_t)kDistExtra[sym] << 8) | (uint32_t)(bits + kDistExtra[sym]);
         return kInvalid;
     }
     return ((uint32_t)sym << 16) | (uint32_t)bits;
@@ -307,7 +311,7 @@ __attribute__((always_inline)) inline Inflater::Status Inflater::run_impl(const 
         const uint32_t lit_mask = (1u << kLitBits) - 1, dist_mask = (1u << kDistBits) - 1;
         if (in_end - ip >= 48 && out_end - op >= 400) {
             // Per turn: up to three literal entries, or up to two and one match.  At most three refills (each loads 8
-            // bytes and advances < 8) and 12 + 258 + 15 output bytes, hence the margins.  The entry for the next turn
+            // bytes and advances < 8) and 12 + 258 + 31 output bytes, hence the margins.  The entry for the next turn
             // is looked up before the match bytes are copied, so the copy overlaps the next decode.
             const uint8_t* const in_fast = in_end - 40;
             uint8_t* const out_fast = out_end - 340;
@@ -350,10 +354,10 @@ __attribute__((always_inline)) inline Inflater::Status Inflater::run_impl(const 
                         bad = true; break;
                     }
                 }
+                uint64_t sv = bb;   // the extra bits are cut out of the saved buffer, off the critical path
                 bb >>= (e & 0xFFu); bc -= (int)(e & 0xFFu);
-                const int lx = (int)((e >> 8) & 0x1Fu);
-                const uint32_t len = (uint32_t)(e >> 16) + (uint32_t)(bb & (((uint64_t)1 << lx) - 1));
-                bb >>= lx; bc -= lx;
+                const uint32_t lx = (uint32_t)((e >> 8) & 0x1Fu);
+                const uint32_t len = (uint32_t)(e >> 16) + (uint32_t)((sv >> ((uint32_t)(e & 0xFFu) - lx)) & (((uint64_t)1 << lx) - 1));
                 uint32_t d = dist_[bb & dist_mask];
                 if (d & kExceptional) {
                     if (!(d & kSubtable)) { bad = true; break; }
@@ -361,10 +365,10 @@ __attribute__((always_inline)) inline Inflater::Status Inflater::run_impl(const 
                     d = dist_[(d >> 16) + (bb & ((1u << ((d >> 8) & 0x1Fu)) - 1))];
                     if (d & kExceptional) { bad = true; break; }
                 }
+                sv = bb;
                 bb >>= (d & 0xFFu); bc -= (int)(d & 0xFFu);
-                const int dx = (int)((d >> 8) & 0x1Fu);
-                const size_t dist = (d >> 16) + (size_t)(bb & (((uint64_t)1 << dx) - 1));
-                bb >>= dx; bc -= dx;
+                const uint32_t dx = (d >> 8) & 0x1Fu;
+                const size_t dist = (d >> 16) + (size_t)((sv >> ((d & 0xFFu) - dx)) & (((uint64_t)1 << dx) - 1));
                 TREW_REFILL();
                 e = lit_[bb & lit_mask];
                 const size_t produced = (size_t)(op - out);
@@ -378,19 +382,23 @@ __attribute__((always_inline)) inline Inflater::Status Inflater::run_impl(const 
                 } else {
                     const uint8_t* src = op - dist;
                     uint8_t* const stop = op + len;
-                    if (dist >= 8) {
+                    if (dist >= 8) {   // word copies in order: a word may read what the previous one wrote
                         memcpy(op, src, 8);
                         memcpy(op + 8, src + 8, 8);
-                        if (len > 16) {
-                            op += 16; src += 16;
+                        memcpy(op + 16, src + 16, 8);
+                        memcpy(op + 24, src + 24, 8);
+                        if (len > 32) {
+                            op += 32; src += 32;
                             do { memcpy(op, src, 8); op += 8; src += 8; } while (op < stop);
                         }
                     } else if (dist == 1) {
                         const uint64_t v = 0x0101010101010101ULL * (uint64_t)*src;
                         memcpy(op, &v, 8);
                         memcpy(op + 8, &v, 8);
-                        if (len > 16) {
-                            op += 16;
+                        memcpy(op + 16, &v, 8);
+                        memcpy(op + 24, &v, 8);
+                        if (len > 32) {
+                            op += 32;
                             do { memcpy(op, &v, 8); op += 8; } while (op < stop);
                         }
                     } else {
@@ -426,13 +434,12 @@ __attribute__((always_inline)) inline Inflater::Status Inflater::run_impl(const 
                 bb = b2 >> l1; bc = c2 - l1;
                 continue;
             }
-            if ((int)(e & 0xFFu) > c2) { bad = true; break; }   // input ends inside a code
+            if ((int)(e & 0xFFu) > c2) { bad = true; break; }   // input ends inside a symbol
+            uint64_t sv2 = b2;
             b2 >>= (e & 0xFFu); c2 -= (int)(e & 0xFFu);
             if (e & kEndOfBlock) { bb = b2; bc = c2; block_done = true; break; }
-            const int lx = (int)((e >> 8) & 0x1Fu);
-            if (lx > c2) { bad = true; break; }
-            const uint32_t len = (uint32_t)(e >> 16) + (uint32_t)(b2 & (((uint64_t)1 << lx) - 1));
-            b2 >>= lx; c2 -= lx;
+            const uint32_t lx = (uint32_t)((e >> 8) & 0x1Fu);   // (the entry's bit count, consumed above, includes them)
+            const uint32_t len = (uint32_t)(e >> 16) + (uint32_t)((sv2 >> ((uint32_t)(e & 0xFFu) - lx)) & (((uint64_t)1 << lx) - 1));
             uint32_t d = dist_[b2 & dist_mask];
             if ((d & kExceptional) && (d & kSubtable)) {
                 if (c2 < kDistBits) { bad = true; break; }
@@ -441,11 +448,10 @@ __attribute__((always_inline)) inline Inflater::Status Inflater::run_impl(const 
             }
             if (d & kExceptional) { bad = true; break; }
             if ((int)(d & 0xFFu) > c2) { bad = true; break; }
+            sv2 = b2;
             b2 >>= (d & 0xFFu); c2 -= (int)(d & 0xFFu);
-            const int dx = (int)((d >> 8) & 0x1Fu);
-            if (dx > c2) { bad = true; break; }
-            const size_t dist = (d >> 16) + (size_t)(b2 & (((uint64_t)1 << dx) - 1));
-            b2 >>= dx; c2 -= dx;
+            const uint32_t dx = (d >> 8) & 0x1Fu;
+            const size_t dist = (d >> 16) + (size_t)((sv2 >> ((d & 0xFFu) - dx)) & (((uint64_t)1 << dx) - 1));
             if ((size_t)(out_end - op) < len) { st = kOutputFull; goto suspend; }
             const size_t produced = (size_t)(op - out);
             if (dist > produced && dist - produced > hist_len_) { bad = true; break; }

@@ -708,8 +708,13 @@ IngestResult ingest_file(int mode, int slice_length, const char* file1, bool gz1
         }
         size_t n = std::min(a.locs.size(), b.locs.size()) / 2;
         if (n) {
-            std::vector<int32_t> la(a.locs.begin(), a.locs.begin() + 2 * n), lb(b.locs.begin(), b.locs.begin() + 2 * n);
-            int rc = sink(a.data(), la, b.data(), lb);
+            int rc;
+            if (a.locs.size() == 2 * n && b.locs.size() == 2 * n) {   // the usual case: the blocks hold the same records
+                rc = sink(a.data(), a.locs, b.data(), b.locs);
+            } else {
+                std::vector<int32_t> la(a.locs.begin(), a.locs.begin() + 2 * n), lb(b.locs.begin(), b.locs.begin() + 2 * n);
+                rc = sink(a.data(), la, b.data(), lb);
+            }
             if (rc) return IngestResult{rc, ""};
         }
         if (done) break;
