@@ -23,7 +23,8 @@ def checker(tmp_path_factory):
     return out
 
 
-@pytest.mark.parametrize("seed", [1, 2, 3])
-def test_decoder_matches_zlib_and_survives_corruption(checker, seed):
-    r = subprocess.run([checker, str(seed), "14"], capture_output=True, text=True, timeout=600)
+@pytest.mark.parametrize("seed,no_bmi2", [(1, False), (2, False), (3, True)])
+def test_decoder_matches_zlib_and_survives_corruption(checker, seed, no_bmi2):
+    env = dict(os.environ, TREW_NO_BMI2="1") if no_bmi2 else dict(os.environ)   # the portable build of the decode loop
+    r = subprocess.run([checker, str(seed), "14"], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and r.stdout.startswith("ok"), (r.stdout[-500:], r.stderr[-2000:])

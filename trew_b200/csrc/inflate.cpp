@@ -13,6 +13,7 @@
 #include "host_internal.h"
 
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 
 namespace trew {
@@ -259,7 +260,7 @@ bool Inflater::read_header(const uint8_t*& ip, const uint8_t* in_end) {
 Inflater::Status Inflater::run(const uint8_t* in, size_t in_len, bool in_final, size_t* in_used, uint8_t* out, size_t out_cap,
                                size_t* out_used) {
 #if defined(__x86_64__)
-    static const bool bmi2 = __builtin_cpu_supports("bmi2") && __builtin_cpu_supports("bmi");
+    static const bool bmi2 = __builtin_cpu_supports("bmi2") && __builtin_cpu_supports("bmi") && !getenv("TREW_NO_BMI2");   // (tests run both builds)
     if (bmi2) return run_bmi2(in, in_len, in_final, in_used, out, out_cap, out_used);
 #endif
     return run_generic(in, in_len, in_final, in_used, out, out_cap, out_used);
