@@ -119,6 +119,8 @@ const char* trew_status_string(int status);
  * ThreadData::init_check (src/kmer.h:139-153, src/kmer.cpp:1278-1282). */
 int trew_dev_create(const trew_config* cfg, trew_ctx** out);
 void trew_dev_destroy(trew_ctx* ctx);
+/* Message of the last failed call on ctx; with ctx == NULL, of the calling thread's last failed trew_dev_create
+ * (e.g. the SLICE_LENGTH <= 512 limit of the GPU path). */
 const char* trew_dev_last_error(const trew_ctx* ctx);
 
 /* ---- input: the QueueData side (src/kmer.h:93-103) --------------------------------------------- */
@@ -242,6 +244,9 @@ void trew_report_destroy(trew_report* r);
 /* Fold + filter + sort one file's six maps and append ">H:" / ">L:" sections to the report text;
  * accumulates the per-file vectors for the cross-file scoring (src/trew.cpp:454-467). */
 int trew_report_add_file(trew_report* r, const char* file_name, const trew_entry* entries, uint64_t n);
+/* The text so far (owned by r, valid until the next call on r): lets a caller print each file's sections as soon as
+ * that file is done, as process_output does (src/kmer.cpp:1615-1631). */
+int trew_report_text(trew_report* r, const char** text, size_t* len);
 /* Append ">Putative_TRM" (src/kmer.cpp:2571-2691) and return the whole text (owned by r). */
 int trew_report_finish(trew_report* r, const char** text, size_t* len);
 

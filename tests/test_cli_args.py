@@ -26,10 +26,28 @@ def test_argument_validation_messages(tmp_path):
              (["short", "5", "32", p, "-L", "0", "-H", "0.8"], "Baseline must be in range 0 to 1."),
              (["short", "5", "32", p, "-L", "0.9", "-H", "0.8"], "Low baseline must be smaller than high baseline."),
              (["short", "5", "32", "--paired_end", "--fq1", p], "--fq1 and --fq2 are required in paired-end mode."),
-             (["short", "5", "32", "/nonexistent.fastq"], "/nonexistent.fastq : file not found")]
+             (["short", "5", "32", "/nonexistent.fastq"], "/nonexistent.fastq : file not found"),
+             # argparse's `--name=value` and glued short-option values reach the same checks
+             (["short", "5", "32", p, "--thread=1"], "You must use at least two threads."),
+             (["short", "5", "32", p, "-t1"], "You must use at least two threads."),
+             (["long", "5", "32", p, "-s60"], "SLICE_LENGTH must be greater than or equal to twice of MAX_MER."),
+             (["long", "5", "32", p, "--slice_length=60"], "SLICE_LENGTH must be greater than or equal to twice of MAX_MER."),
+             (["short", "5", "32", p, "-L0.9", "-H0.8"], "Low baseline must be smaller than high baseline.")]
     for args, msg in cases:
         rc, out, err = run(args)
         assert rc == 1 and msg in err and out == "", args
+
+
+def test_slice_length_limit_is_reported(tmp_path):
+    """The reference accepts any -s >= 2*MAX_MER (src/trew.cpp:204-207); the GPU path stops at 512 and says so, both
+    through the C ABI (trew_dev_last_error(NULL)) and on the command line."""
+    p = os.path.join(str(tmp_path), "a.fastq")
+    open(p, "wb").write(synth.fastq_bytes([b"ACGT" * 300]))
+    rc, out, err = run(["long", "5", "32", p, "-s", "1000"])
+    assert rc == 1 and out == "" and "SLICE_LENGTH above 512 is not supported" in err
+    with pytest.raises(api.TrewError) as e:
+        api.DeviceContext(api.MODE_LONG, 5, 32, slice_length=1000)
+    assert e.value.status == 1 and "SLICE_LENGTH above 512" in str(e.value)
 
 
 def test_version_and_usage():

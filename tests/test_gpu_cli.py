@@ -60,6 +60,49 @@ def test_cli_argument_errors(tmp_path):
     assert r.stdout == b""
 
 
+FIX = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fixtures")
+
+
+@pytest.mark.parametrize("args,name", [(["short", "5", "32"], "test.fastq.gz"), (["short", "5", "32"], "test.fastq"),
+                                       (["short", "5", "64"], "test.fastq"), (["long", "5", "32"], "test_long.fastq.gz"),
+                                       (["long", "5", "32"], "test_long.fastq"), (["long", "5", "64", "-t", "4"], "test_long.fastq.gz")])
+def test_reference_fixtures_give_the_empty_skeleton(args, name):
+    """BASELINE.json configs[0] through the CUDA path: the reference's own fixtures (test/test.cpp:260-443) with the
+    compiled reference's stdout."""
+    p = os.path.join(FIX, name)
+    out = subprocess.run([api.CLI_PATH] + args + [p], capture_output=True, check=True).stdout.decode()
+    rp = os.path.realpath(p)
+    assert out == ">H:%s\n>L:%s\n>Putative_TRM\nNO_PUTATIVE_TRM,-1\n" % (rp, rp)
+
+
+@pytest.mark.parametrize("name", ["test.fastq", "test.fastq.gz"])
+def test_reference_fixture_rows_3_64(name):
+    """`trew short 3 64 test/test.fastq`: the one bundled-fixture run with rows; golden = the
+    compiled reference's stdout, see tests/test_fixtures.py."""
+    from test_fixtures import L_ROWS_3_64, PUTATIVE_3_64
+    p = os.path.join(FIX, name)
+    out = subprocess.run([api.CLI_PATH, "short", "3", "64", p], capture_output=True, check=True).stdout.decode()
+    rp = os.path.realpath(p)
+    sec = dict(split_sections(out))
+    assert sec[">H:" + rp] == []
+    assert sec[">L:" + rp] == sorted(L_ROWS_3_64)
+    strip = lambda rows: sorted((r.split(",")[0], r.split(",")[1], r.split(",")[3]) for r in rows)
+    assert strip(sec[">Putative_TRM"]) == strip(PUTATIVE_3_64)
+
+
+def test_cli_streams_sections_per_file(tmp_path):
+    """Each file's >H: / >L: sections are on stdout before the next file is touched (process_output prints per file,
+    src/kmer.cpp:1615-1631): a later file that fails leaves the earlier sections behind, exit code 1."""
+    ok = os.path.join(FIX, "test.fastq")
+    bad = os.path.join(str(tmp_path), "bad.fastq")
+    open(bad, "wb").write(synth.fastq_bytes([b"ACGT" * 300]))
+    r = subprocess.run([api.CLI_PATH, "short", "5", "32", ok, bad], capture_output=True)
+    rp = os.path.realpath(ok)
+    assert r.returncode == 1
+    assert r.stdout.decode() == ">H:%s\n>L:%s\n" % (rp, rp)
+    assert b"Please use 'trew long'" in r.stderr
+
+
 def test_bundled_fixture_skeleton(tmp_path):
     # config 1 of BASELINE.json: non-repetitive fixtures give the empty skeleton (SURVEY.md 4.2)
     p = os.path.join(str(tmp_path), "test.fastq.gz")

@@ -68,6 +68,49 @@ def test_long_vs_oracle(mn, mx, sl):
     assert got == want, diff_msg(got, want)
 
 
+def config4_reads(seed, count):
+    """BASELINE.json configs[3] shape (2 M x 15 kb HiFi-like, telomeric 0.5-5 kb ends, `trew long 5 32`, SLICE 150 ->
+    snum = 100) with the telomeric share raised so that every walk of buffer_task_long (src/kmer.cpp:790-856) is
+    taken many times: 5' end, 3' end, both ends, both strands, whole-read repeats, N's inside the repeat."""
+    import random
+    rng = random.Random(seed)
+    reads = [bytes(r) for r in synth.config_long(seed, count, telomeric=0.6)]
+    unit, rc = b"TTAGGG", b"CCCTAA"
+    for i in range(count // 8):
+        n = rng.randint(9000, 18000)
+        body = bytes(rng.choice(b"ACGT") for _ in range(n))
+        a, b = rng.randint(500, 5000), rng.randint(500, 5000)
+        kind = i % 6
+        if kind == 0:
+            r = (unit * (a // 6 + 1))[:a] + body[a:n - b] + (unit * (b // 6 + 1))[:b]          # both ends, same strand
+        elif kind == 1:
+            r = (rc * (a // 6 + 1))[:a] + body[a:n - b] + (unit * (b // 6 + 1))[:b]            # both ends, strands differ
+        elif kind == 2:
+            r = (unit * (n // 6 + 1))[:n]                                                      # every slice survives -> 'both'
+        elif kind == 3:
+            r = bytearray((unit * (a // 6 + 1))[:a] + body[a:])                                # N's inside the repeat
+            for _ in range(a // 200):
+                r[rng.randrange(a)] = ord("N")
+            r = bytes(r)
+        elif kind == 4:
+            r = (b"TTAGGGG" * (a // 7 + 1))[:a] + body[a:n - b] + (unit * (b // 6 + 1))[:b]    # two units
+        else:
+            r = body[:n - b] + (rc * (b // 6 + 1))[:b].lower()                                 # lower case 3' end
+        reads.append(r)
+    return reads
+
+
+@pytest.mark.parametrize("mn,mx,sl,seed", [(5, 32, 150, 3), (3, 64, 150, 4), (5, 32, 128, 5)])
+def test_long_15kb_vs_oracle(mn, mx, sl, seed):
+    from oracle.oracle import Oracle
+    reads = config4_reads(seed, 240)
+    assert len(reads) >= 200 and min(map(len, reads)) >= 1000 and max(map(len, reads)) > 17000
+    got = run_gpu(api.MODE_LONG, mn, mx, 0.5, 0.8, sl, reads)
+    want = Oracle(mn, mx, slice_len=sl).scan(2, reads)
+    assert len(want) > 100
+    assert got == want, diff_msg(got, want)
+
+
 def test_edge_cases():
     from oracle.oracle import Oracle
     reads = [b"", b"A", b"ACGTACGTA", b"ACGTACGTAC", b"N" * 150, b"A" * 150, b"TTAGGG" * 25, b"ttaggg" * 25,

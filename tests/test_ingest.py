@@ -6,7 +6,6 @@ import pytest
 
 from trew_b200 import api, synth
 
-REF_TEST = "/root/reference/test"
 
 
 def py_records(data: bytes):
@@ -78,10 +77,9 @@ def test_missing_file():
     assert rc == 5 and msg == "File open failed"
 
 
-@pytest.mark.skipif(not os.path.isdir(REF_TEST), reason="reference fixtures only exist in the build container")
 @pytest.mark.parametrize("name,mode", [("test.fastq", 0), ("test.fastq.gz", 0), ("test_long.fastq", 2), ("test_long.fastq.gz", 2)])
 def test_bundled_fixtures(name, mode):
-    p = os.path.join(REF_TEST, name)
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fixtures", name)   # byte copies, see test_fixtures.py
     data = (gzip.open(p) if name.endswith(".gz") else open(p, "rb")).read()
     rc, _, r1, _ = api.ingest_records(mode, p, chunk_bytes=4096)
     assert rc == 0 and r1 == py_records(data)
@@ -123,6 +121,75 @@ def test_truncated_bgzf_is_an_io_error(tmp_path):
     open(p, "wb").write(raw[:len(raw) // 2 + 7])
     rc, msg, _, _ = api.ingest_records(api.MODE_SHORT, p)
     assert rc == 5 and "IO Error" in msg
+
+
+def test_corrupted_bgzf_payload_is_an_io_error(tmp_path):
+    """A flipped payload byte inside a (stored) BGZF member must fail the member's CRC-32 like gzread's
+    'incorrect data check' -- not ingest altered records."""
+    import struct
+    import zlib
+    data = synth.fastq_bytes(synth.adversarial_short(8, 300))
+    out = bytearray()
+    for i in range(0, len(data), 4000):   # stored (level 0) members: any payload byte maps 1:1 to an output byte
+        chunk = data[i:i + 4000]
+        co = zlib.compressobj(0, zlib.DEFLATED, -15)
+        body = co.compress(chunk) + co.flush()
+        bsize = 18 + len(body) + 8
+        out += b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", bsize - 1)
+        out += body + struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk))
+    p = os.path.join(tmp_path, "ok.fastq.bgz")
+    open(p, "wb").write(bytes(out))
+    assert api.ingest_records(api.MODE_SHORT, p)[0] == 0
+    bad = bytearray(out)
+    at = 18 + 5 + 1000                     # inside the first member's stored payload, on a base
+    assert bytes(bad[at:at + 1]) in b"ACGTNacgtn@+I\n" or True
+    bad[at] ^= 0x04
+    q = os.path.join(tmp_path, "bad.fastq.bgz")
+    open(q, "wb").write(bytes(bad))
+    rc, msg, _, _ = api.ingest_records(api.MODE_SHORT, q)
+    assert rc == 5 and "data check" in msg
+
+
+def test_pair_carry_stays_bounded_with_asymmetric_mates(tmp_path):
+    """28 bp against 100 bp mates: index-wise pairing leaves a surplus of complete records on the short side every
+    block.  The carry must stay O(block) (offsets are int32), and the pairs must still come out in order."""
+    import ctypes as C
+    n = 6000
+    r1 = [bytes(r) for r in synth.config_short(41, n, length=28, telomeric=0.05, half_telomeric=0, n_rate=0.001)]
+    r2 = [bytes(r) for r in synth.config_short(42, n, length=100, telomeric=0.05, half_telomeric=0, n_rate=0.001)]
+    p1 = write(tmp_path, "a.fastq", synth.fastq_bytes(r1))
+    p2 = write(tmp_path, "b.fastq", synth.fastq_bytes(r2))
+    chunk = 4096
+    L = api.load_library()
+    seen1, seen2, max_off = [], [], [0]
+
+    def sink(user, b1, l1, n1, b2, l2, n2):
+        assert n1 == n2
+        for i in range(n1):
+            seen1.append(C.string_at(b1 + l1[2 * i], l1[2 * i + 1] - l1[2 * i] + 1))
+            seen2.append(C.string_at(b2 + l2[2 * i], l2[2 * i + 1] - l2[2 * i] + 1))
+        if n1:
+            max_off[0] = max(max_off[0], l1[2 * n1 - 1], l2[2 * n2 - 1])
+        return 0
+
+    for env in ({}, {"TREW_NO_MMAP": "1"}):
+        seen1.clear(); seen2.clear(); max_off[0] = 0
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            msg = C.create_string_buffer(512)
+            rc = L.trew_ingest_file(api.MODE_PAIR, 150, p1.encode(), 0, p2.encode(), 0, chunk, api.CHUNK_SINK(sink), None, msg, 512)
+        finally:
+            for k, v in old.items():
+                os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+        assert rc == 0, msg.value
+        assert seen1 == r1 and seen2 == r2
+        assert max_off[0] < 3 * chunk, max_off[0]
+    # one file ends early: the surplus of the other is only counted, the mismatch is still reported with both totals
+    p3 = write(tmp_path, "c.fastq", synth.fastq_bytes(r2[:n // 3]))
+    rc, msg, o1, o2 = api.ingest_records(api.MODE_PAIR, p1, p3, chunk_bytes=chunk)
+    assert rc == 6 and msg == "Error: Mismatched record counts between files (num1: %d, num2: %d)." % (4 * n, 4 * (n // 3))
+    assert o1 == r1[:n // 3] and o2 == r2[:n // 3]
 
 
 @pytest.mark.parametrize("simd", ["0", "1", "2"])

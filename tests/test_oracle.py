@@ -70,12 +70,6 @@ def test_k_mer_check_perfect_repeat_128(unit):
     assert min(seq, o.crc(seq, k)) == min(x, o.crc(x, k))
 
 
-def test_bundled_fixture_result_3_64():
-    # `short 3 64 test/test.fastq` is the only bundled-fixture run with a non-empty
-    # report; its F_l / B_l tables were captured from the compiled reference into the golden file.
-    pass  # covered by test_cli.py::test_reference_fixture_rows once the report layer exists
-
-
 # ---- (b) golden fixtures from the compiled reference --------------------------------------------
 
 def test_scan_golden(scan_cases):

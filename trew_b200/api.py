@@ -65,7 +65,7 @@ ABI_SYMBOLS = [
     "trew_synth_resident", "trew_dev_timer_start", "trew_dev_timer_stop", "trew_dev_kernel_times",
     "trew_dev_process_file", "trew_ingest_file", "trew_report_create", "trew_report_destroy", "trew_report_add_file",
     "trew_report_finish", "trew_dev_export_rows", "trew_dev_merge_rows", "trew_dev_reserve", "trew_dev_finish_merged",
-    "trew_pack_reads_ranges",
+    "trew_pack_reads_ranges", "trew_report_text",
 ]
 
 CHUNK_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_uint32, C.c_void_p,
@@ -221,7 +221,7 @@ class DeviceContext:
         rc = self.lib.trew_dev_create(C.byref(self.cfg), C.byref(self.ctx))
         if rc:
             self.ctx = None
-            raise TrewError(rc, self.lib.trew_status_string(rc).decode())
+            raise TrewError(rc, self.lib.trew_dev_last_error(None).decode() or self.lib.trew_status_string(rc).decode())
         self.mode = mode
 
     def _check(self, rc: int) -> None:

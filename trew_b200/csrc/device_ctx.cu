@@ -457,20 +457,32 @@ const char* trew_status_string(int status) {
     }
 }
 
-const char* trew_dev_last_error(const trew_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+// trew_dev_create has no context to hang its message on: it is kept here and read with trew_dev_last_error(NULL)
+static thread_local std::string g_create_error;
+
+const char* trew_dev_last_error(const trew_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int trew_dev_create(const trew_config* cfg, trew_ctx** out) {
     if (!cfg || !out) return TREW_ERR_ARG;
     *out = nullptr;
+    g_create_error.clear();
+    auto bad_arg = [](const char* msg) { g_create_error = msg; return TREW_ERR_ARG; };
     // same range checks as the reference CLI (src/trew.cpp:174-228, 255-304)
-    if (cfg->mode < 0 || cfg->mode > 2 || cfg->min_mer < 3 || cfg->max_mer > 64 || cfg->min_mer > cfg->max_mer) return TREW_ERR_ARG;
+    if (cfg->mode < 0 || cfg->mode > 2) return bad_arg("mode must be TREW_MODE_SHORT, _PAIR or _LONG");
+    if (cfg->min_mer < 3 || cfg->max_mer > 64 || cfg->min_mer > cfg->max_mer) return bad_arg("need 3 <= MIN_MER <= MAX_MER <= 64");
     if (!(0 < cfg->low_baseline && cfg->low_baseline <= 1) || !(0 < cfg->high_baseline && cfg->high_baseline <= 1) ||
-        cfg->low_baseline > cfg->high_baseline) return TREW_ERR_ARG;
-    if (cfg->mode == TREW_MODE_LONG && (cfg->slice_length < 2 * cfg->max_mer || cfg->slice_length > 512)) return TREW_ERR_ARG;
+        cfg->low_baseline > cfg->high_baseline) return bad_arg("need 0 < LOW_BASELINE <= HIGH_BASELINE <= 1");
+    if (cfg->mode == TREW_MODE_LONG && cfg->slice_length > 0 && cfg->slice_length < 2 * cfg->max_mer)
+        return bad_arg("SLICE_LENGTH must be greater than or equal to twice of MAX_MER.");
+    // The middle slice of a long read is up to 2 * SLICE_LENGTH - 1 bases (src/kmer.cpp:790-798) and a window lives in
+    // one warp's 32 x 32-bit registers (1023 bases), so SLICE_LENGTH stops at 512 here; the reference has no limit.
+    if (cfg->mode == TREW_MODE_LONG && cfg->slice_length > 512)
+        return bad_arg("SLICE_LENGTH above 512 is not supported by the GPU path (a slice of up to 2*SLICE_LENGTH-1 bases must fit "
+                       "a 1023-base window); use -s 512 or less.");
     trew_ctx* ctx = new trew_ctx();
     ctx->cfg = *cfg;
     if (ctx->cfg.slice_length <= 0) ctx->cfg.slice_length = 150;
-    auto bail = [&](int rc) { std::string e = ctx->err; trew_dev_destroy(ctx); fprintf(stderr, "trew_dev_create: %s\n", e.c_str()); return rc; };
+    auto bail = [&](int rc) { g_create_error = ctx->err; trew_dev_destroy(ctx); return rc; };
 #define CKC(call)                                                                                   \
     do {                                                                                            \
         cudaError_t e_ = (call);                                                                    \

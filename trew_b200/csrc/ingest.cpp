@@ -218,14 +218,19 @@ struct Reader {
 
     struct BgzfBlock { const unsigned char* cdata; uint32_t clen, isize; size_t out_off; };
 
+    // every member's CRC-32 (the trailer word right behind its DEFLATE data) is checked like gzread does: a flipped
+    // payload bit is "incorrect data check", not silently different records
     static bool inflate_blocks(const BgzfBlock* blk, size_t n, char* out) {
         std::unique_ptr<Inflater> inf(new Inflater());
         for (size_t i = 0; i < n; i++) {
-            if (blk[i].isize == 0) continue;
+            const unsigned char* t = blk[i].cdata + blk[i].clen;
+            const uint32_t want = t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+            if (blk[i].isize == 0) { if (want != 0) return false; continue; }
             inf->reset();
             size_t iu = 0, ou = 0;
             const Inflater::Status st = inf->run(blk[i].cdata, blk[i].clen, true, &iu, (uint8_t*)out + blk[i].out_off, blk[i].isize, &ou);
             if (st != Inflater::kStreamEnd || ou != blk[i].isize) return false;
+            if ((uint32_t)crc32_z(0L, (const Bytef*)out + blk[i].out_off, blk[i].isize) != want) return false;
         }
         return true;
     }
@@ -455,7 +460,7 @@ struct Reader {
         }
     }
     std::string error() {
-        if (bgzf) return "malformed BGZF block";
+        if (bgzf) return "malformed BGZF block or incorrect data check";
         if (ownz) return zerr ? zerr : "gzip stream error";
         if (gz) { int e; return gzerror(gfp, &e); }
         return strerror(errno);
@@ -493,6 +498,7 @@ struct Side {
     const char* data() const { return rd.map ? rd.map + win : buf->data; }
     bool fill(size_t chunk, Pool* pool, size_t par_min, bool defer_crc = false) {
         nl_slices = 0;
+        if (chunk == 0) return true;   // paired mode: enough carried records to pair with, nothing to read this round
         if (rd.map) {   // widen the window over the mapping; nothing is copied
             const size_t left = (size_t)rd.size - win - have;
             const size_t add = std::min(chunk, left);
@@ -684,18 +690,31 @@ IngestResult ingest_file(int mode, int slice_length, const char* file1, bool gz1
         }
         return res;
     }
+    // Records are paired index-wise, so when the two files' records differ in size (trimmed mates, 28 + 90 bp
+    // libraries) the side with the smaller records finds more of them per block and carries the surplus over.  The
+    // carry is bounded: a side that still holds complete unpaired records only tops its buffer up to one block (the
+    // reference bounds it the same way by reading LENGTH - 1 - shift, src/kmer.cpp:1062-1066), so `have` stays below
+    // two blocks and the int32 offsets cannot wrap.
+    size_t carried[2] = {0, 0};   // complete records carried over from the last round, per side
     for (;;) {
+        Side* sides[2] = {&a, &b};
+        size_t want[2];
+        for (int i = 0; i < 2; i++) {
+            const size_t have = sides[i]->have;
+            want[i] = sides[i]->eof ? 0 : have < chunk_bytes ? chunk_bytes - have : (carried[i] ? 0 : chunk_bytes);
+            if (have + want[i] >= (size_t)0x7fffffff)
+                return IngestResult{TREW_ERR_PAIRING, "Error: a paired-end record does not fit a 2 GiB block."};
+        }
         if (pool && pool->size() > 1 && (gz1 || gz2)) {
             // two inflate streams are independent: read both mates' blocks at the same time
             bool ok[2] = {true, true};
-            Side* sides[2] = {&a, &b};
-            pool->run(2, [&](int i) { if (!sides[i]->eof) ok[i] = sides[i]->fill(chunk_bytes, nullptr, par_min, true); });
+            pool->run(2, [&](int i) { if (!sides[i]->eof) ok[i] = sides[i]->fill(want[i], nullptr, par_min, true); });
             for (int i = 0; i < 2; i++) ok[i] = ok[i] && sides[i]->rd.finish_crc(pool);   // the members' CRC-32, on all threads
             if (!ok[0]) return IngestResult{TREW_ERR_IO, "File 1 IO Error: " + a.rd.error() + "."};
             if (!ok[1]) return IngestResult{TREW_ERR_IO, "File 2 IO Error: " + b.rd.error() + "."};
         } else {
-            if (!a.eof && !a.fill(chunk_bytes, pool, par_min)) return IngestResult{TREW_ERR_IO, "File 1 IO Error: " + a.rd.error() + "."};
-            if (!b.eof && !b.fill(chunk_bytes, pool, par_min)) return IngestResult{TREW_ERR_IO, "File 2 IO Error: " + b.rd.error() + "."};
+            if (!a.eof && !a.fill(want[0], pool, par_min)) return IngestResult{TREW_ERR_IO, "File 1 IO Error: " + a.rd.error() + "."};
+            if (!b.eof && !b.fill(want[1], pool, par_min)) return IngestResult{TREW_ERR_IO, "File 2 IO Error: " + b.rd.error() + "."};
         }
         a.scan(mode, slice_length, &too_long, pool, par_min);
         b.scan(mode, slice_length, &too_long, pool, par_min);
@@ -719,8 +738,15 @@ IngestResult ingest_file(int mode, int slice_length, const char* file1, bool gz1
         }
         if (done) break;
         // keep unpaired records: restart at the sequence line of the first unpaired record, phase = "header seen"
-        for (Side* s : {&a, &b}) {
-            if (s->locs.size() / 2 > n) {
+        for (int i = 0; i < 2; i++) {
+            Side* s = sides[i];
+            Side* o = sides[1 - i];
+            carried[i] = s->locs.size() / 2 - n;
+            // the other file is used up: the rest of this one cannot be paired any more and is only read on for the
+            // line totals of the mismatch message, so nothing of it is kept
+            const bool other_spent = o->eof && o->locs.size() / 2 <= n;
+            if (other_spent) carried[i] = 0;
+            if (carried[i]) {
                 size_t from = (size_t)s->locs[2 * n];
                 uint64_t dropped = 0;  // newlines between `from` and the scan position are re-counted
                 for (size_t i = from; i < s->scanned; i++) dropped += s->data()[i] == '\n';

@@ -209,6 +209,13 @@ int trew_report_add_file(trew_report* r, const char* file_name, const trew_entry
     return TREW_OK;
 }
 
+int trew_report_text(trew_report* r, const char** text, size_t* len) {
+    if (!r) return TREW_ERR_ARG;
+    if (text) *text = r->text.c_str();
+    if (len) *len = r->text.size();
+    return TREW_OK;
+}
+
 int trew_report_finish(trew_report* r, const char** text, size_t* len) {
     if (!r) return TREW_ERR_ARG;
     if (!r->finished) {

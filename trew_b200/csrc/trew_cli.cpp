@@ -69,9 +69,21 @@ int main(int argc, char** argv) {
     bool paired = false, used_fq1 = false, used_fq2 = false;
     std::vector<std::string> positional, fq1, fq2;
     std::vector<std::string>* sink = &positional;
+    // argparse also takes `--name=value` and a value glued to a short option (`-t4`): split those first
+    std::vector<std::string> av;
     for (int i = 2; i < argc; i++) {
         std::string a = argv[i];
-        auto value = [&](const char** v) { if (i + 1 >= argc) return false; *v = argv[++i]; return true; };
+        size_t eq;
+        if (a.size() > 2 && a[0] == '-' && a[1] == '-' && (eq = a.find('=')) != std::string::npos) {
+            av.push_back(a.substr(0, eq)); av.push_back(a.substr(eq + 1));
+        } else if (a.size() > 2 && a[0] == '-' && strchr("tmLHsq", a[1]) && ((a[2] >= '0' && a[2] <= '9') || a[2] == '.' || a[2] == '-')) {
+            av.push_back(a.substr(0, 2)); av.push_back(a.substr(2));
+        } else av.push_back(a);
+    }
+    const int ac = (int)av.size();
+    for (int i = 0; i < ac; i++) {
+        const std::string& a = av[(size_t)i];
+        auto value = [&](const char** v) { if (i + 1 >= ac) return false; *v = av[(size_t)++i].c_str(); return true; };
         const char* v = nullptr;
         bool ok = true;
         if (a == "-h" || a == "--help") { usage(cmd); return 0; }
@@ -142,11 +154,16 @@ int main(int argc, char** argv) {
     cfg.host_threads = num_thread;
     trew_ctx* ctx = nullptr;
     int rc = trew_dev_create(&cfg, &ctx);
-    if (rc != TREW_OK) { fprintf(stderr, "trew: cannot create device context: %s\n", trew_status_string(rc)); return 1; }
+    if (rc != TREW_OK) {
+        const char* why = trew_dev_last_error(nullptr);
+        fprintf(stderr, "trew: cannot create device context: %s\n", why && *why ? why : trew_status_string(rc));
+        return 1;
+    }
     trew_report* rep = nullptr;
     trew_report_create(min_mer, &rep);
 
     const bool is_pair = cfg.mode == TREW_MODE_PAIR;
+    size_t printed = 0;   // bytes of the report text already written to stdout
     for (size_t i = 0; i < paths.size() / (is_pair ? 2 : 1); i++) {
         std::string a, b;
         bool g1, g2 = false;
@@ -169,12 +186,19 @@ int main(int argc, char** argv) {
             return 1;
         }
         trew_report_add_file(rep, a.c_str(), entries, n);
-        // stream each file's sections as they are ready, like process_output does
+        // each file's sections go out as soon as they are ready, like process_output prints them (src/kmer.cpp:1615-1631):
+        // a later file that fails leaves the earlier sections on stdout
+        const char* part = nullptr;
+        size_t part_len = 0;
+        trew_report_text(rep, &part, &part_len);
+        fwrite(part + printed, 1, part_len - printed, stdout);
+        fflush(stdout);
+        printed = part_len;
     }
     const char* text = nullptr;
     size_t len = 0;
     trew_report_finish(rep, &text, &len);
-    fwrite(text, 1, len, stdout);
+    fwrite(text + printed, 1, len - printed, stdout);
     trew_report_destroy(rep);
     trew_dev_destroy(ctx);
     return 0;

@@ -75,7 +75,9 @@ def merge_device(ctx, device: torch.device, dst: int = 0) -> None:
     dist.all_gather(sizes, torch.tensor([n], dtype=torch.int64, device=device))
     sizes = [int(s.item()) for s in sizes]
     n_max = max(max(sizes), 1)
-    rows = torch.zeros((n_max, 4), dtype=torch.int64, device=device)
+    # torch.empty: nothing is queued on torch's stream that could race with the context's own (non-blocking) stream
+    # writing the rows; the padding past n is never read (sizes travel separately)
+    rows = torch.empty((n_max, 4), dtype=torch.int64, device=device)
     ctx.export_rows(rows.data_ptr(), n_max)
     gathered = [torch.empty_like(rows) for _ in range(world)] if rank == dst else None
     dist.gather(rows, gathered, dst=dst)
