@@ -101,6 +101,16 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": power[-1] if power else None}
 
 
+def load_issue_profile():
+    """Per-kernel pipe utilisation from the committed ncu run (profiles/issue_profile.json, written by
+    tools/ncu_summary.py from an `ncu --set full` capture of tools/profile_scan.py): the evidence for `limiter`."""
+    p = os.path.join(ROOT, "profiles", "issue_profile.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
 def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -292,10 +302,18 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         launches_per_scan = len(handles)
-        screen_avg_ms = screen_ms / max(1, n_scans)
         reads_per_launch = args.reads / len(handles)
-        achieved = BYTES_PER_READ * reads_per_launch / (screen_avg_ms * 1e-3) / 1e9 if screen_avg_ms > 0 else 0.0
         scan_ms = screen_ms + decide_ms + exact_ms
+        per_kernel = {}
+        for kname, kms in (("trew_screen_kernel", screen_ms), ("trew_filter_kernel", decide_ms), ("trew_exact_kernel", exact_ms)):
+            avg = kms / max(1, n_scans)
+            per_kernel[kname] = {"launch_ms": avg, "share_of_scan": kms / scan_ms if scan_ms > 0 else 0.0,
+                                 "gbs_alone": BYTES_PER_READ * reads_per_launch / (avg * 1e-3) / 1e9 if avg > 0 else 0.0}
+        dominant = max(per_kernel, key=lambda k: per_kernel[k]["launch_ms"])
+        # the three kernels of a batch are one pipeline over the same packed reads: the bytes a batch streams, over the
+        # time all three take for it
+        scan_avg_ms = scan_ms / max(1, n_scans)
+        achieved = BYTES_PER_READ * reads_per_launch / (scan_avg_ms * 1e-3) / 1e9 if scan_avg_ms > 0 else 0.0
         line = {
             "metric": METRIC, "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -309,14 +327,15 @@ def run_ours(args):
             "kernel_share": {"screen_ms_per_step": screen_ms / args.steps, "decide_ms_per_step": decide_ms / args.steps,
                              "exact_ms_per_step": exact_ms / args.steps,
                              "survivor_fraction": st.survivors / max(1, st.units)},
-            "roofline": {"bound": "hbm", "kernel": "trew_screen_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "limiter": "instruction issue (XU pipe: POPC), not HBM -- see `issue` and DESIGN.md section 4",
+                         "kernel": dominant, "scope": "screen + decide + exact kernel of one batch (one pipeline over the same packed reads)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_read": BYTES_PER_READ,
                          "algorithmic_bytes_per_launch": BYTES_PER_READ * reads_per_launch,
-                         "launch_ms": screen_avg_ms,
-                         "all_scan_kernels_frac": (BYTES_PER_READ * args.reads * args.steps / (scan_ms * 1e-3) / 1e9 / peak) if scan_ms > 0 else 0.0,
-                         "note": "the screen kernel streams every packed read once; it is bound by the XU pipe (POPC), "
-                                 "not by HBM: see DESIGN.md section 4"},
+                         "launch_ms": scan_avg_ms,
+                         "per_kernel": per_kernel,
+                         "issue": load_issue_profile()},
             "e2e": {"value": e2e_value, "unit": "Gbases/s", "h2d_bytes_per_step": int((st2.h2d_bytes - st1.h2d_bytes) / e2e_steps),
                     "d2h_bytes_per_step": int((st2.d2h_bytes - st1.d2h_bytes) / e2e_steps),
                     "reads_per_step": int(e2e_reads), "steps": e2e_steps,
@@ -332,12 +351,64 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             line["e2e_file"] = file_e2e(ctx, api, synth, rank)
             line["cpu_baseline"] = cpu_baseline()
+        if world == 1 and not args.no_shapes:
+            line["configs"] = other_shapes(api, local_rank, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)))
     for h, _ in handles:
         ctx.free_resident(h)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
     return line if rank == 0 else None
+
+
+def other_shapes(api, device_index, steps, warmup):
+    """The other BASELINE.json shapes (configs[2..4]) on the same GPU in the same run: one device-generated resident
+    batch each, reset -> scan -> table export per step, CUDA events on the scan stream.  Correctness of these shapes
+    is the parity tests' business (tests/test_gpu_parity.py checks the same generator against the oracle)."""
+    shapes = [
+        ("paired_2x150", "synthetic paired-end: 8 M x 2 x 150 bp per batch, both mates of ~1% of the fragments telomeric, "
+                         "--paired_end, MIN_MER=5 MAX_MER=32",
+         dict(mode=api.MODE_PAIR, mn=5, mx=32, reads=16_000_000, read_len=150, flavor=1, **SYNTH)),
+        ("long_15kb", "synthetic long-read: 200 k x 15 kb per batch, 2% with a telomeric 0.5-5 kb end, 0.1% error, "
+                      "trew long 5 32 (SLICE 150)",
+         dict(mode=api.MODE_LONG, mn=5, mx=32, reads=200_000, read_len=15000, flavor=2, tel_ppm=20000, half_ppm=0,
+              n_ppm=100, sub_ppm=1000)),
+        ("sweep_3_64", "full period sweep: 8 M x 150 bp per batch as configs[1], MIN_MER=3 MAX_MER=64 (128-bit units)",
+         dict(mode=api.MODE_SHORT, mn=3, mx=64, reads=8_000_000, read_len=150, flavor=0, **SYNTH)),
+    ]
+    out = {}
+    for name, desc, kw in shapes:
+        ctx = api.DeviceContext(kw["mode"], kw["mn"], kw["mx"], device=device_index)
+        try:
+            h = ctx.synth_resident(11, kw["reads"], kw["read_len"], tel_ppm=kw["tel_ppm"], half_ppm=kw["half_ppm"],
+                                   n_ppm=kw["n_ppm"], sub_ppm=kw["sub_ppm"], flavor=kw["flavor"])
+
+            def one():
+                ctx.reset()
+                ctx.scan_resident(h)
+                return ctx.finish_view()
+
+            for _ in range(max(1, warmup)):
+                rows = one()
+            ctx.kernel_times()
+            ctx.timer_start()
+            for _ in range(steps):
+                rows = one()
+            ms = ctx.timer_stop()
+            s_ms, d_ms, e_ms, n = ctx.kernel_times()
+            st = ctx.stats()
+            bases = kw["reads"] * kw["read_len"]
+            bytes_per_batch = 4 * kw["reads"] + 3 * bases / 8.0
+            scan_ms = (s_ms + d_ms + e_ms) / max(1, n)
+            out[name] = {"workload": desc, "value": bases * steps / (ms * 1e-3) / 1e9, "unit": "Gbases/s", "ms_per_step": ms / steps,
+                         "kernel_share": {"screen_ms": s_ms / max(1, n), "decide_ms": d_ms / max(1, n), "exact_ms": e_ms / max(1, n),
+                                          "survivor_fraction": st.survivors / max(1, st.units)},
+                         "scan_gbs": bytes_per_batch / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0,
+                         "table_rows": int(rows.shape[0])}
+            ctx.free_resident(h)
+        finally:
+            ctx.close()
+    return out
 
 
 def file_e2e(ctx, api, synth, rank):
@@ -404,6 +475,7 @@ def main():
     ap.add_argument("--reads", type=int, default=200_000_000, help="reads per GPU held resident (configs[1]: 200 M)")
     ap.add_argument("--e2e-reads", type=int, default=8_000_000, help="reads per end-to-end step (host buffers)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-shapes", action="store_true", help="skip the paired / long / 3-64 shapes (configs[2..4])")
     args = ap.parse_args()
     # stdout carries exactly one JSON line (rank 0): native libraries that print there (NCCL's version banner)
     # are diverted to stderr for the duration of the run

@@ -153,6 +153,12 @@ int trew_dev_last_resident_ms(trew_ctx* ctx, float* ms);
 int trew_synth_resident(trew_ctx* ctx, uint64_t seed, uint32_t n_reads, uint32_t read_len, uint32_t tel_ppm,
                         uint32_t half_ppm, uint32_t n_ppm, uint32_t sub_ppm, trew_resident** out);
 
+/* The same generator for the other BASELINE.json shapes: flavor 0 = single reads (as above); 1 = pairs (reads 2u and
+ * 2u+1 are the two ends of one fragment: both telomeric or neither, mate 2 on the opposite strand; configs[2]);
+ * 2 = long reads whose first or last 500-5000 bases are telomeric (tel_ppm of the reads; configs[3]). */
+int trew_synth_resident_ex(trew_ctx* ctx, uint64_t seed, uint32_t n_reads, uint32_t read_len, uint32_t tel_ppm,
+                           uint32_t half_ppm, uint32_t n_ppm, uint32_t sub_ppm, uint32_t flavor, trew_resident** out);
+
 /* CUDA-event stopwatch on the context's scan stream (for device-resident scans). */
 int trew_dev_timer_start(trew_ctx* ctx);
 int trew_dev_timer_stop(trew_ctx* ctx, float* ms); /* waits for the stream */

@@ -197,6 +197,34 @@ def test_device_generator_matches_numpy_mirror():
     assert len(got) > 50
 
 
+def test_device_generator_pair_and_long_flavors():
+    """bench.py's `configs` lines time device-generated pairs (flavor 1) and long reads with telomeric ends (flavor 2);
+    the numpy mirror reproduces them, so the oracle checks those very reads too."""
+    from oracle.oracle import Oracle
+    kw = dict(tel_ppm=40000, half_ppm=20000, n_ppm=1000, sub_ppm=10000)
+    n = 12_000
+    with api.DeviceContext(api.MODE_PAIR, 5, 32) as ctx:
+        h = ctx.synth_resident(6, n, 150, flavor=1, **kw)
+        ctx.scan_resident(h)
+        got = ctx.finish()
+        ctx.free_resident(h)
+    mat = synth.device_mirror(6, n, 150, flavor=1, **kw)
+    want = Oracle(5, 32).scan(1, [bytes(r) for r in mat[0::2]], [bytes(r) for r in mat[1::2]])
+    assert got == want, diff_msg(got, want)
+    assert sum(1 for (tb, _, _) in got if tb >= 4) > 10     # fragments telomeric at both ends reach the 'both' tables
+    n = 300
+    kw["tel_ppm"] = 400000
+    with api.DeviceContext(api.MODE_LONG, 5, 32) as ctx:
+        h = ctx.synth_resident(7, n, 15000, flavor=2, **kw)
+        ctx.scan_resident(h)
+        got = ctx.finish()
+        ctx.free_resident(h)
+    mat = synth.device_mirror(7, n, 15000, flavor=2, **kw)
+    want = Oracle(5, 32).scan(2, [bytes(r) for r in mat])
+    assert got == want, diff_msg(got, want)
+    assert len(got) > 50
+
+
 def test_device_row_merge():
     """The multi-GPU merge path on one GPU: two contexts scan disjoint shards, the second one's table is exported as
     device rows and added to the first (trew_dev_export_rows / trew_dev_merge_rows); the result equals one context

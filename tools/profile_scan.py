@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Small driver for ncu: one device-resident batch of the configs[1] shape, scanned a few times.
 
-    python tools/profile_scan.py [reads] [scans] [min_mer] [max_mer] [tel_ppm] [half_ppm] [n_ppm] [mode 0 short / 1 pair / 2 long] [read_len]
+    python tools/profile_scan.py [reads] [scans] [min_mer] [max_mer] [tel_ppm] [half_ppm] [n_ppm] [mode 0 short / 1 pair / 2 long] [read_len] [flavor]
 """
 import os
 import sys
@@ -19,8 +19,9 @@ half = int(sys.argv[6]) if len(sys.argv) > 6 else 2000
 nppm = int(sys.argv[7]) if len(sys.argv) > 7 else 1000
 mode = int(sys.argv[8]) if len(sys.argv) > 8 else api.MODE_SHORT
 read_len = int(sys.argv[9]) if len(sys.argv) > 9 else 150
+flavor = int(sys.argv[10]) if len(sys.argv) > 10 else 0
 with api.DeviceContext(mode, mn, mx) as ctx:
-    h = ctx.synth_resident(1, reads, read_len, tel_ppm=tel, half_ppm=half, n_ppm=nppm, sub_ppm=10000)
+    h = ctx.synth_resident(1, reads, read_len, tel_ppm=tel, half_ppm=half, n_ppm=nppm, sub_ppm=1000 if flavor == 2 else 10000, flavor=flavor)
     for _ in range(scans):
         ctx.scan_resident(h)
     ctx.sync()

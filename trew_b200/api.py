@@ -65,7 +65,7 @@ ABI_SYMBOLS = [
     "trew_synth_resident", "trew_dev_timer_start", "trew_dev_timer_stop", "trew_dev_kernel_times",
     "trew_dev_process_file", "trew_ingest_file", "trew_report_create", "trew_report_destroy", "trew_report_add_file",
     "trew_report_finish", "trew_dev_export_rows", "trew_dev_merge_rows", "trew_dev_reserve", "trew_dev_finish_merged",
-    "trew_pack_reads_ranges", "trew_report_text",
+    "trew_pack_reads_ranges", "trew_report_text", "trew_synth_resident_ex",
 ]
 
 CHUNK_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_uint32, C.c_void_p,
@@ -114,6 +114,8 @@ def load_library() -> C.CDLL:
     L.trew_dev_process_file.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
     L.trew_synth_resident.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                       C.c_uint32, C.POINTER(C.c_void_p)]
+    L.trew_synth_resident_ex.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                         C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
     L.trew_dev_timer_start.argtypes = [C.c_void_p]
     L.trew_dev_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.trew_dev_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -286,10 +288,11 @@ class DeviceContext:
         self.lib.trew_dev_free_resident(self.ctx, handle)
 
     def synth_resident(self, seed: int, n_reads: int, read_len: int = 150, tel_ppm: int = 10000, half_ppm: int = 2000,
-                       n_ppm: int = 1000, sub_ppm: int = 10000):
+                       n_ppm: int = 1000, sub_ppm: int = 10000, flavor: int = 0):
+        """flavor 0 single reads, 1 pairs (mates of one fragment), 2 long reads with telomeric ends."""
         h = C.c_void_p()
-        self._check(self.lib.trew_synth_resident(self.ctx, seed, n_reads, read_len, tel_ppm, half_ppm, n_ppm, sub_ppm,
-                                                 C.byref(h)))
+        self._check(self.lib.trew_synth_resident_ex(self.ctx, seed, n_reads, read_len, tel_ppm, half_ppm, n_ppm, sub_ppm,
+                                                    flavor, C.byref(h)))
         return h
 
     def timer_start(self) -> None:

@@ -91,6 +91,7 @@ struct trew_ctx {
     std::vector<RangeInfo> ranges_tmp;
     unsigned int keys_seen = 0;                  // distinct keys reported by the batches retired so far (lags the device)
     bool sparse_val = true;                      // TREW_DENSE_VAL=1: always copy the validity plane
+    unsigned int exact_flags = 0;                // TREW_EXACT_FLAGS: switches parts of the exact kernel off (A/B measurements)
     std::vector<InvList> inv_tmp;                // per packing range: records of its blocks with invalid bases
     IngestScratch ingest;   // file block buffers, kept across files
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
@@ -164,6 +165,7 @@ int launch_scan(trew_ctx* ctx, const DevBatch& b, uint32_t n_units, uint32_t max
     a.slice_scratch = *d_scratch; a.slice_scratch_stride = stride; a.run_cap = run_cap_for(ctx->cfg, max_read_len);
     a.total_survivors = ctx->d_total_surv;
     a.packed_probes = n_units < (1u << 28) ? 1 : 0;
+    a.exp_flags = ctx->exact_flags;
     launch_exact(ctx->dcfg, b, a, ctx->plan, st);
     if (ev) CK(cudaEventRecord(ev[3], st));
     CK(cudaGetLastError());
@@ -505,6 +507,7 @@ int trew_dev_create(const trew_config* cfg, trew_ctx** out) {
         if ((v = env_int("TREW_GRID_EXACT", 0)) > 0) ctx->plan.exact_blocks = std::min(ctx->plan.exact_blocks, ctx->sm_count * v);
         ctx->resident_streams = env_int("TREW_RESIDENT_STREAMS", 1) >= 2 ? 2 : 1;
         ctx->sparse_val = env_int("TREW_DENSE_VAL", 0) == 0;
+        ctx->exact_flags = (unsigned int)env_int("TREW_EXACT_FLAGS", 0);
     }
     int lg = cfg->table_log2_slots > 0 ? cfg->table_log2_slots : 22;
     if (lg < 10 || lg > 28) { fail(ctx, TREW_ERR_ARG, "table_log2_slots out of range"); return bail(TREW_ERR_ARG); }
@@ -999,7 +1002,12 @@ int trew_dev_kernel_times(trew_ctx* ctx, double* screen_ms, double* decide_ms, d
 
 int trew_synth_resident(trew_ctx* ctx, uint64_t seed, uint32_t n_reads, uint32_t read_len, uint32_t tel_ppm,
                         uint32_t half_ppm, uint32_t n_ppm, uint32_t sub_ppm, trew_resident** out) {
-    if (!ctx || !out || read_len == 0 || (uint64_t)n_reads * read_len >= 0xfffff000ULL) return TREW_ERR_ARG;
+    return trew_synth_resident_ex(ctx, seed, n_reads, read_len, tel_ppm, half_ppm, n_ppm, sub_ppm, 0, out);
+}
+
+int trew_synth_resident_ex(trew_ctx* ctx, uint64_t seed, uint32_t n_reads, uint32_t read_len, uint32_t tel_ppm,
+                           uint32_t half_ppm, uint32_t n_ppm, uint32_t sub_ppm, uint32_t flavor, trew_resident** out) {
+    if (!ctx || !out || read_len == 0 || flavor > 2 || (uint64_t)n_reads * read_len >= 0xfffff000ULL) return TREW_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
     auto thr = [](uint32_t ppm) { return (unsigned int)(((unsigned long long)ppm << 32) / 1000000ULL); };
     uint64_t bases = (uint64_t)n_reads * read_len;
@@ -1008,7 +1016,7 @@ int trew_synth_resident(trew_ctx* ctx, uint64_t seed, uint32_t n_reads, uint32_t
     CK(cudaMalloc(&r->d_buf, bytes));
     BatchView v;
     batch_layout(r->d_buf, n_reads, bases, &v);
-    launch_synth(seed, n_reads, read_len, thr(tel_ppm), thr(half_ppm), thr(n_ppm), thr(sub_ppm), v.bit_off, v.hi, v.lo, v.val,
+    launch_synth(seed, n_reads, read_len, thr(tel_ppm), thr(half_ppm), thr(n_ppm), thr(sub_ppm), flavor, v.bit_off, v.hi, v.lo, v.val,
                  v.plane_words, ctx->main_stream);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->main_stream));

@@ -113,7 +113,7 @@ __host__ __device__ inline u32 synth_hash(u64 seed, u64 a, u64 b) {
     return (u32)(x >> 32);
 }
 
-__global__ void synth_kernel(u64 seed, u32 n_reads, u32 L, u32 tel_thr, u32 half_thr, u32 n_thr, u32 sub_thr,
+__global__ void synth_kernel(u64 seed, u32 n_reads, u32 L, u32 tel_thr, u32 half_thr, u32 n_thr, u32 sub_thr, u32 flavor,
                              u32* __restrict__ bit_off, u32* __restrict__ hi, u32* __restrict__ lo, u32* __restrict__ val,
                              size_t plane_words) {
     const u64 total = (u64)n_reads * L;
@@ -128,15 +128,21 @@ __global__ void synth_kernel(u64 seed, u32 n_reads, u32 L, u32 tel_thr, u32 half
             u64 pos = (u64)w * 32 + b;
             if (pos >= total) break;
             u64 r = pos / L; u32 j = (u32)(pos % L);
-            u32 kind = synth_hash(seed, r, 0xffffffffULL);
-            u32 aux = synth_hash(seed, r, 0xfffffffeULL);
+            const u64 frag = flavor == 1 ? r >> 1 : r;   // pairs: both mates share the fragment's draw
+            u32 kind = synth_hash(seed, frag, 0xffffffffULL);
+            u32 aux = synth_hash(seed, frag, 0xfffffffeULL);
             u32 code = synth_hash(seed, r, j) & 3u;
             bool tel = kind < tel_thr;
             bool halfk = !tel && kind < tel_thr + half_thr;
             if (halfk) tel = ((aux >> 8) & 1u) ? (j < L / 2) : (j >= L / 2);
+            if (flavor == 2 && tel) {   // long reads: telomeric for the first or the last 500..5000 bases only
+                u32 tl = 500u + synth_hash(seed, frag, 0xfffffffdULL) % 4501u;
+                if (tl > L) tl = L;
+                tel = ((aux >> 9) & 1u) ? (j < tl) : (j >= L - tl);
+            }
             if (tel) {
                 u32 phase = aux % 6u;
-                bool rc = (aux >> 4) & 1u;
+                bool rc = (((aux >> 4) & 1u) ^ (flavor == 1 ? (u32)(r & 1u) : 0u)) != 0u;
                 u32 idx = (j + phase) % 6u;
                 u32 c = rc ? unit_r[idx] : unit_f[idx];
                 u32 sh = synth_hash(seed ^ 0x5555555555555555ULL, r, j);
@@ -150,9 +156,9 @@ __global__ void synth_kernel(u64 seed, u32 n_reads, u32 L, u32 tel_thr, u32 half
 }
 
 void launch_synth(unsigned long long seed, unsigned int n_reads, unsigned int read_len, unsigned int tel_thr,
-                  unsigned int half_thr, unsigned int n_thr, unsigned int sub_thr, unsigned int* bit_off, unsigned int* hi,
-                  unsigned int* lo, unsigned int* val, size_t plane_words, cudaStream_t stream) {
-    synth_kernel<<<1184, 256, 0, stream>>>(seed, n_reads, read_len, tel_thr, half_thr, n_thr, sub_thr, bit_off, hi, lo, val,
+                  unsigned int half_thr, unsigned int n_thr, unsigned int sub_thr, unsigned int flavor, unsigned int* bit_off,
+                  unsigned int* hi, unsigned int* lo, unsigned int* val, size_t plane_words, cudaStream_t stream) {
+    synth_kernel<<<1184, 256, 0, stream>>>(seed, n_reads, read_len, tel_thr, half_thr, n_thr, sub_thr, flavor, bit_off, hi, lo, val,
                                             plane_words);
 }
 
@@ -737,7 +743,7 @@ __host__ __device__ inline size_t exact_warp_bytes(int cap) {
 size_t exact_smem_bytes(int run_cap, bool) { return exact_warp_bytes(run_cap) * kExactWarps; }
 
 struct WS {  // this warp's region
-    u32 off; int cap; int hs; u32 lane;
+    u32 off; int cap; int hs; u32 lane; u32 flags;
     __device__ __forceinline__ u32* hdr() const { return (u32*)(g_smem + off); }
     __device__ __forceinline__ u32* H() const { return (u32*)(g_smem + off + 64); }
     __device__ __forceinline__ u32* L() const { return H() + kPlaneWords; }
@@ -819,9 +825,45 @@ __device__ __forceinline__ void crc_pair(u64& lo, u64& hi, int k) {
 
 __device__ __forceinline__ bool homo_pair(u64 lo, u64 hi, int k) {  // get_repeat_check: <= 1 distinct base
     if (k <= 1) return true;
+    if (k <= 32) return ((lo ^ (lo >> 2)) & ((1ULL << (2 * (k - 1))) - 1ULL)) == 0;
     u128 w = ((u128)hi << 64) | lo;
     u128 m = (((u128)1 << (2 * (k - 1))) - 1);
     return ((w ^ (w >> 2)) & m) == 0;
+}
+
+// ---- warp-cooperative minimal rotation: every lane passes the same k-mer, lane l tries rotation l (and l + 32 when
+// k > 32), and the minimum is found with two (four) 32-bit warp reductions.  Worth it when a window has few runs and k
+// is large: the serial loop of canon64 is k - 1 dependent steps on one lane while 31 lanes idle.
+__device__ __forceinline__ u64 canon64_coop(u64 w, int k, u32 lane) {
+    const u64 mask = k >= 32 ? ~0ULL : ((1ULL << (2 * k)) - 1ULL);
+    const int r = 2 * (int)lane;
+    u64 rot = ~0ULL;
+    if ((int)lane < k) rot = lane == 0 ? w : (((w >> r) | (w << (2 * k - r))) & mask);
+    const u32 mh = __reduce_min_sync(0xffffffffu, (u32)(rot >> 32));
+    const u32 ml = __reduce_min_sync(0xffffffffu, (u32)(rot >> 32) == mh ? (u32)rot : 0xffffffffu);
+    return ((u64)mh << 32) | ml;
+}
+
+__device__ __forceinline__ u128 canon128_coop(u128 w, int k, u32 lane) {
+    const u128 mask = k >= 64 ? ~(u128)0 : ((((u128)1) << (2 * k)) - 1);
+    u128 best = ~(u128)0;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const int l = (int)lane + 32 * half;
+        if (l < k) {
+            const u128 rot = l == 0 ? w : (((w >> (2 * l)) | (w << (2 * (k - l)))) & mask);
+            best = rot < best ? rot : best;
+        }
+    }
+    u32 part[4] = {(u32)(best >> 96), (u32)(best >> 64), (u32)(best >> 32), (u32)best};
+    u32 m[4];
+    bool tied = true;   // this lane still equals the minimum on all higher words
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        m[j] = __reduce_min_sync(0xffffffffu, tied ? part[j] : 0xffffffffu);
+        tied = tied && part[j] == m[j];
+    }
+    return ((u128)m[0] << 96) | ((u128)m[1] << 64) | ((u128)m[2] << 32) | (u128)m[3];
 }
 
 __device__ __forceinline__ bool less_pair(u64 alo, u64 ahi, u64 blo, u64 bhi) {
@@ -949,6 +991,47 @@ __device__ __forceinline__ int bound_k(WS ws, int k, u32 wv, int T) {
     return max(max(c00, c01), max(c10, c11));
 }
 
+// Second upper bound on the largest class count, for periods with at most 32 valid windows (what an N leaves of a
+// window at large k): rotation keeps the multiset of bases, so windows of one class have the same (#C|A, #G|A, #A)
+// composition.  One window per lane, equal compositions counted with MATCH.  Exact compositions reject nearly every
+// such period of a non-repeat read, where the parity signature (8 buckets for a dozen windows) cannot.
+// Uses run_start as scratch (emit_classes does not read it).
+__device__ __noinline__ int comp_bound(WS ws, int k, u32 wv, int T) {
+    const u32 lane = ws.lane;
+    const u32 cnt = (u32)__popc(wv);
+    u32 inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, inc, d);
+        if ((int)lane >= d) inc += t;
+    }
+    unsigned short* pos = ws.run_start();
+    {
+        u32 rb = inc - cnt, x = wv;
+        while (x) {
+            int bit = __ffs(x) - 1;
+            x &= x - 1;
+            pos[rb++] = (unsigned short)(32 * lane + bit);
+        }
+    }
+    __syncwarp();
+    const bool act = (int)lane < T;
+    u32 key = 0;
+    if (act) {
+        const u32 *H = ws.H(), *L = ws.L();
+        const int p = pos[lane], w0 = p >> 5, o = p & 31;
+        const u32 m0 = low_mask(min(k, 32)), m1 = k <= 32 ? 0u : low_mask(k - 32);
+        const u32 h0 = __funnelshift_r(H[w0], H[w0 + 1], o) & m0, h1 = __funnelshift_r(H[w0 + 1], H[w0 + 2], o) & m1;
+        const u32 l0 = __funnelshift_r(L[w0], L[w0 + 1], o) & m0, l1 = __funnelshift_r(L[w0 + 1], L[w0 + 2], o) & m1;
+        key = (u32)(__popc(h0) + __popc(h1)) | ((u32)(__popc(l0) + __popc(l1)) << 8) | ((u32)(__popc(h0 & l0) + __popc(h1 & l1)) << 16);
+    }
+    const u32 actm = __ballot_sync(0xffffffffu, act);
+    const u32 same = __match_any_sync(0xffffffffu, key) & actm;
+    const u32 best = __reduce_max_sync(0xffffffffu, act ? (u32)__popc(same) : 0u);
+    __syncwarp();
+    return (int)best;
+}
+
 // Exact class statistics of the loaded window for one period (the inner loops of k_mer_check,
 // src/kmer.cpp:2183-2216, without the early break): T valid windows, M largest class, S the class that
 // first reaches M (stored in the header).  Leaves the run list in shared memory (run_lo/hi canonical class
@@ -993,6 +1076,62 @@ __device__ __noinline__ u32 eval_k(WS ws, int len, int k, u32 wv) {
         }
         if (lane == 0) run_cw[R] = (unsigned short)T;
     }
+    const u64* rev2 = ws.rev2();
+    const bool wide = k > 32;
+    if (R <= 32 && !(ws.flags & 1u)) {
+        // Few runs (every repeat read: a perfect repeat is one run, each substitution adds at most two): one run per
+        // lane, classes grouped in registers with MATCH instead of the shared-memory hash table.
+        __syncwarp();
+        const bool act = (int)lane < R;
+        u64 lo = ~0ULL, hi = ~0ULL;
+        u32 c0 = 0, c1 = 0;
+        if (act) { kmer_at(rev2, len, run_start[lane], k, lo, hi); c0 = run_cw[lane]; c1 = run_cw[lane + 1]; }
+        // minimal rotation: k - 1 dependent steps on the run's own lane, or one warp-wide step per run
+        const int serial_cost = (k - 1) * (k <= 16 ? 3 : (wide ? 14 : 6));
+        const int coop_cost = R * (wide ? 48 : 16);
+        if (coop_cost < serial_cost) {
+            for (int r = 0; r < R; r++) {
+                const u64 wl = __shfl_sync(0xffffffffu, lo, r);
+                if (!wide) {
+                    const u64 c = canon64_coop(wl, k, lane);
+                    if ((int)lane == r) lo = c;
+                } else {
+                    const u64 wh = __shfl_sync(0xffffffffu, hi, r);
+                    const u128 c = canon128_coop(((u128)wh << 64) | wl, k, lane);
+                    if ((int)lane == r) { lo = (u64)c; hi = (u64)(c >> 64); }
+                }
+            }
+        } else if (act) {
+            canon_pair(lo, hi, k);
+        }
+        const u32 actm = __ballot_sync(0xffffffffu, act);
+        u32 grp = __match_any_sync(0xffffffffu, lo);
+        if (wide) grp &= __match_any_sync(0xffffffffu, hi);
+        grp &= actm;
+        u32 score = 0, total = 0;
+        bool leader = false;
+        if (act) {
+            // the class's window total and the ordinal of its last window, over the lanes holding its runs
+            total = __reduce_add_sync(grp, c1 - c0);
+            const u32 last = __reduce_max_sync(grp, c1 - 1u);
+            leader = (u32)(__ffs(grp) - 1) == lane;
+            // K_MER_DATA_MAX_SEQ: the class whose running count first reaches the final maximum
+            // (strict '<' at src/kmer.cpp:2202) = max total, ties broken by the EARLIEST last window
+            if (leader) score = (total << 10) | (1023u - last);
+            run_lo[lane] = lo; if (wide) run_hi[lane] = hi;
+            run_total[lane] = (unsigned short)(leader ? total : 0u);
+        }
+        const u32 wbest = __reduce_max_sync(0xffffffffu, score);
+        const u32 who = __ballot_sync(0xffffffffu, leader && score == wbest);
+        const int bq = __ffs(who) - 1;
+        const u64 s_lo = __shfl_sync(0xffffffffu, lo, bq), s_hi = wide ? __shfl_sync(0xffffffffu, hi, bq) : 0ULL;
+        const bool homo = homo_pair(s_lo, s_hi, k);
+        if (lane == 0) {
+            hd[HD_S] = (u32)s_lo; hd[HD_S + 1] = (u32)(s_lo >> 32); hd[HD_S + 2] = (u32)s_hi; hd[HD_S + 3] = (u32)(s_hi >> 32);
+        }
+        __syncwarp();
+        return (u32)T | ((wbest >> 10) << 10) | ((u32)R << 20) | (homo ? 1u << 30 : 0u);
+    }
     // hash table sized to the run count (power of two >= 1.5 R, so hsz > R; at most hs >= 1.25 cap)
     int hsz = 32;
     while (hsz < R + (R >> 1) && hsz < ws.hs) hsz <<= 1;
@@ -1002,8 +1141,6 @@ __device__ __noinline__ u32 eval_k(WS ws, int len, int k, u32 wv) {
         if (i < R) { grp_tot[i] = 0u; grp_last[i] = 0u; }
     }
     __syncwarp();
-    const u64* rev2 = ws.rev2();
-    const bool wide = k > 32;
     // one canonicalisation per run
     for (int q = lane; q < R; q += 32) {
         u64 lo, hi;
@@ -1122,6 +1259,16 @@ __device__ __noinline__ ScanRes scan_stats(WS ws, DevBatch b, u32 pos, int len, 
         double dU = (double)Uk, dT = (double)Tk;
         bool candL = !blkL && dU >= needL * dT * slack, candH = !blkH && dU >= needH * dT * slack;
         if (!candL && !candH) return false;
+#ifndef TREW_NO_COMP_BOUND
+        if (Tk <= 32 && !(ws.flags & 2u)) {   // few windows: the exact-composition bound is cheap and far tighter than the parity signature
+            const int Mc = comp_bound(ws, kk, wv, Tk);
+            if (Mc < Uk) {
+                dU = (double)Mc;
+                candL = !blkL && dU >= needL * dT * slack; candH = !blkH && dU >= needH * dT * slack;
+                if (!candL && !candH) return false;
+            }
+        }
+#endif
         u32 ev = eval_k(ws, len, kk, wv);
         if (lane == 0) { hd[HD_EV_POS] = pos; hd[HD_EV_LEN] = (u32)len; hd[HD_EV_K] = (u32)kk; hd[HD_EV_PACK] = ev; }
         __syncwarp();
@@ -1435,7 +1582,7 @@ __global__ void __launch_bounds__(kExactWarps * 32, TREW_EXACT_BPS) trew_exact_k
     const u32 lane = lane_id();
     WS ws;
     ws.cap = a.run_cap; ws.hs = exact_hash_slots(a.run_cap);
-    ws.off = (u32)((size_t)wid * exact_warp_bytes(a.run_cap)); ws.lane = lane;
+    ws.off = (u32)((size_t)wid * exact_warp_bytes(a.run_cap)); ws.lane = lane; ws.flags = a.exp_flags;
     TableRef tr{cfg.slots, cfg.slot_mask, cfg.error_flag};
     if (lane < 16) ws.hdr()[lane] = lane == HD_CUR_LEN || lane == HD_EV_LEN || lane == HD_EV_K ? 0xffffffffu : 0u;
     __syncwarp();

@@ -57,6 +57,7 @@ struct ExactArgs {
     int run_cap;                     // run-list capacity per warp (>= longest window + 1)
     unsigned long long* total_survivors;  // running total over all launches (statistics)
     int packed_probes;               // survivor entries carry the undecided-probe mask in bits 28..31
+    unsigned int exp_flags;          // experiments (TREW_EXACT_FLAGS): 1 = no register path for few runs, 2 = no composition bound
 };
 
 // grid sizes (total blocks) of the three scan kernels; all three are grid-stride / work-counter kernels
@@ -85,8 +86,10 @@ cudaError_t combine_sorted_rows(const trew_entry* d_sorted, unsigned int n, trew
 void launch_clear_invalid(unsigned int* val, const unsigned int* rec, unsigned int n, cudaStream_t stream);
 void launch_merge_entries(const DevCfg& cfg, const trew_entry* entries, unsigned int n, cudaStream_t stream);
 
+// flavor 0: single reads (configs[1]); 1: pairs -- reads 2u, 2u+1 are the two ends of one fragment, both telomeric or
+// neither, mate 2 on the opposite strand (configs[2]); 2: long reads whose first or last 0.5-5 kb are telomeric (configs[3])
 void launch_synth(unsigned long long seed, unsigned int n_reads, unsigned int read_len, unsigned int tel_thr,
-                  unsigned int half_thr, unsigned int n_thr, unsigned int sub_thr, unsigned int* bit_off, unsigned int* hi,
-                  unsigned int* lo, unsigned int* val, size_t plane_words, cudaStream_t stream);
+                  unsigned int half_thr, unsigned int n_thr, unsigned int sub_thr, unsigned int flavor, unsigned int* bit_off,
+                  unsigned int* hi, unsigned int* lo, unsigned int* val, size_t plane_words, cudaStream_t stream);
 
 }  // namespace trew

@@ -308,22 +308,32 @@ def _synth_hash(seed: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
 
 
 def device_mirror(seed: int, n_reads: int, read_len: int = 150, tel_ppm: int = 10000, half_ppm: int = 2000,
-                  n_ppm: int = 1000, sub_ppm: int = 10000) -> np.ndarray:
-    """The exact reads trew_synth_resident() generates on the GPU, as an n_reads x read_len ASCII matrix."""
+                  n_ppm: int = 1000, sub_ppm: int = 10000, flavor: int = 0) -> np.ndarray:
+    """The exact reads trew_synth_resident(_ex)() generates on the GPU, as an n_reads x read_len ASCII matrix
+    (flavor 1: rows 2u, 2u+1 are the mates of pair u; flavor 2: long reads with telomeric ends)."""
     thr = lambda ppm: np.uint64((ppm << 32) // 1000000)
     L = read_len
     r = np.repeat(np.arange(n_reads, dtype=np.uint64), L).reshape(n_reads, L)
     j = np.tile(np.arange(L, dtype=np.uint64), n_reads).reshape(n_reads, L)
-    kind = _synth_hash(seed, r[:, :1], np.full((n_reads, 1), 0xffffffff, dtype=np.uint64)).astype(np.uint64)
-    aux = _synth_hash(seed, r[:, :1], np.full((n_reads, 1), 0xfffffffe, dtype=np.uint64))
+    frag = (r[:, :1] >> np.uint64(1)) if flavor == 1 else r[:, :1]
+    kind = _synth_hash(seed, frag, np.full((n_reads, 1), 0xffffffff, dtype=np.uint64)).astype(np.uint64)
+    aux = _synth_hash(seed, frag, np.full((n_reads, 1), 0xfffffffe, dtype=np.uint64))
     code = _synth_hash(seed, r, j) & np.uint32(3)
     tel = np.broadcast_to(kind < thr(tel_ppm), (n_reads, L)).copy()
     halfk = (~(kind < thr(tel_ppm))) & (kind < thr(tel_ppm) + thr(half_ppm))
     left = ((aux >> np.uint32(8)) & np.uint32(1)) == 1
     in_half = np.where(left, j < np.uint64(L // 2), j >= np.uint64(L // 2))
     tel = np.where(halfk, in_half, tel)
+    if flavor == 2:
+        tl = np.minimum(np.uint64(500) + (_synth_hash(seed, frag, np.full((n_reads, 1), 0xfffffffd, dtype=np.uint64)) % np.uint32(4501)).astype(np.uint64),
+                        np.uint64(L))
+        front = ((aux >> np.uint32(9)) & np.uint32(1)) == 1
+        ends = np.where(front, j < tl, j >= np.uint64(L) - tl)
+        tel = np.where(tel, ends, tel)
     phase = (aux % np.uint32(6)).astype(np.uint64)
     rc = ((aux >> np.uint32(4)) & np.uint32(1)) == 1
+    if flavor == 1:
+        rc = rc ^ ((r[:, :1] & np.uint64(1)) == 1)
     idx = ((j + phase) % np.uint64(6)).astype(np.int64)
     unit_f = np.array([0, 0, 3, 1, 1, 1], dtype=np.uint32)
     unit_r = np.array([2, 2, 2, 0, 3, 3], dtype=np.uint32)
