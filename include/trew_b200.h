@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TREW_ABI_VERSION 1
+#define TREW_ABI_VERSION 2
 
 /* status codes (the reference prints a message and exit(1)s instead; src/kmer.cpp:85-86, 1007-1008) */
 #define TREW_OK 0
@@ -107,6 +107,8 @@ typedef struct trew_stats {
     uint64_t h2d_bytes;
     uint64_t d2h_bytes;
     double device_ms;      /* CUDA-event time of all scan kernels so far                          */
+    uint64_t host_pack_bytes; /* ASCII bases the host packer turned into planes (streaming path)   */
+    double host_pack_ms;   /* wall time the submitting thread spent in the packer (all pool threads busy) */
 } trew_stats;
 
 typedef struct trew_ctx trew_ctx;
@@ -202,6 +204,32 @@ int trew_dev_reserve(trew_ctx* ctx, uint64_t expected_new_keys);
  * src/kmer.cpp:89). */
 int trew_dev_reset(trew_ctx* ctx);
 int trew_dev_get_stats(trew_ctx* ctx, trew_stats* out);
+
+/* ---- several GPUs in one process: the consumer fan-out of process_kmer* (src/kmer.cpp:1271-1325) --------------------
+ *
+ * The reference starts NUM_THREAD consumers on one queue and sums their maps at the end (src/kmer.cpp:1486-1515).  A
+ * trew_multi is the same thing with GPUs as the consumers: one trew_ctx per device, one host packing pool shared by all
+ * of them, chunks dealt round-robin (the two mates of a pair always travel together, reads are independent --
+ * src/kmer.cpp:111, 322, 785), and at end of file the devices' compacted tables are copied to the first device over
+ * NVLink (cudaMemcpyPeerAsync) and united there exactly (sort by key, integer sums) before one D2H copy.
+ * devices == NULL or n_devices == 0: every visible device (a device listed k times gets k contexts).  cfg->device is ignored; cfg->host_threads sizes the shared
+ * pool (0 = all cores).  All calls on one group must come from one thread at a time. */
+typedef struct trew_multi trew_multi;
+int trew_multi_create(const trew_config* cfg, const int32_t* devices, int32_t n_devices, trew_multi** out);
+void trew_multi_destroy(trew_multi* m);
+int trew_multi_device_count(const trew_multi* m);
+const char* trew_multi_last_error(const trew_multi* m);
+int trew_multi_submit_chunk(trew_multi* m, const char* buffer1, const int32_t* locs1, uint32_t n1, const char* buffer2,
+                            const int32_t* locs2, uint32_t n2);
+int trew_multi_process_file(trew_multi* m, const char* file1, int is_gz1, const char* file2, int is_gz2);
+int trew_multi_reset(trew_multi* m);
+/* Drain every device, merge, return the six maps sorted by (table, k, seq) like trew_dev_finish (the array belongs to
+ * the group and is valid until the next call that touches the tables). */
+int trew_multi_finish(trew_multi* m, const trew_entry** entries, uint64_t* n_entries);
+/* Sums over the group's contexts (device_ms: the largest). */
+int trew_multi_get_stats(trew_multi* m, trew_stats* out);
+/* The context of the i-th device of the group (e.g. for device-resident batches); owned by the group. */
+trew_ctx* trew_multi_ctx(trew_multi* m, int32_t i);
 
 /* ---- host packer: ASCII -> planar 2-bit (codes[], src/kmer.cpp:14-31) ---------------------------- */
 

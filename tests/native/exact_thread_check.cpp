@@ -1,0 +1,73 @@
+// Host build of the thread-per-read exact routing (trew_b200/csrc/exact_thread.cuh is plain scalar code): packs reads
+// with the same planar layout as the device batches and runs route_short_thread on each, so tests/test_exact_thread.py
+// can diff the result against the CPU oracle without a GPU.  Test infrastructure.
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <tuple>
+#include <vector>
+
+#include "../../trew_b200/csrc/exact_thread.cuh"
+
+using namespace trew::et;
+
+namespace {
+int code_of(unsigned char ch) {   // codes[], src/kmer.cpp:14-31: T=0 G=1 C=2 A=3, anything else invalid
+    switch (ch) {
+        case 'T': case 't': return 0;
+        case 'G': case 'g': return 1;
+        case 'C': case 'c': return 2;
+        case 'A': case 'a': return 3;
+        default: return -1;
+    }
+}
+struct Collect {
+    std::map<std::tuple<int, int, uint64_t>, uint64_t>* m;
+    void operator()(int table, int k, uint64_t key, uint64_t count) { (*m)[std::make_tuple(table, k, key)] += count; }
+};
+}  // namespace
+
+extern "C" {
+
+// thr_low / thr_high: 1025 entries each (min M with (double)M / T >= baseline), built by the caller with IEEE doubles.
+// Returns the number of table entries written (up to cap), or -1 when cap is too small; *n_bailed = reads outside the
+// thread path's limits (the device hands those to the warp kernel).
+long etc_scan_reads(const char* buf, const int32_t* locs, int n_reads, int min_mer, int max_mer, const unsigned short* thr_low,
+                    const unsigned short* thr_high, int32_t* out_table, int32_t* out_k, uint64_t* out_key, uint64_t* out_count, long cap,
+                    long* n_bailed, int32_t* bailed_index) {
+    std::map<std::tuple<int, int, uint64_t>, uint64_t> tables;
+    Collect emit{&tables};
+    long bailed = 0;
+    for (int r = 0; r < n_reads; r++) {
+        const int st = locs[2 * r], nd = locs[2 * r + 1];
+        const int n = nd >= st ? nd - st + 1 : 0;
+        u32 work[kWorkWords];
+        memset(work, 0xA5, sizeof(work));   // the workspace is not cleared between reads on the device either
+        Mem m{work, 1};
+        bool ok = true;
+        if (n <= kMaxRead) {
+            for (int j = 0; j < kReadWords + 2; j++) { m[W_RH + j] = 0; m[W_RL + j] = 0; m[W_RV + j] = 0; }
+            for (int i = 0; i < n; i++) {
+                const int c = code_of((unsigned char)buf[st + i]);
+                if (c >= 0) {
+                    m[W_RV + (i >> 5)] |= 1u << (i & 31); m[W_RH + (i >> 5)] |= (u32)(c >> 1) << (i & 31);
+                    m[W_RL + (i >> 5)] |= (u32)(c & 1) << (i & 31);
+                }
+            }
+            ok = route_short_thread(m, n, 3u, min_mer, max_mer, thr_low, thr_high, emit);
+        } else {
+            ok = n < 2 * min_mer;
+        }
+        if (!ok) { if (bailed_index) bailed_index[bailed] = r; bailed++; }
+    }
+    if (n_bailed) *n_bailed = bailed;
+    if ((long)tables.size() > cap) return -1;
+    long i = 0;
+    for (auto& kv : tables) {
+        out_table[i] = std::get<0>(kv.first); out_k[i] = std::get<1>(kv.first); out_key[i] = std::get<2>(kv.first); out_count[i] = kv.second;
+        i++;
+    }
+    return i;
+}
+
+}  // extern "C"

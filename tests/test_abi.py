@@ -24,7 +24,7 @@ def test_library_exports_every_symbol():
     lib = ctypes.CDLL(api.LIB_PATH)
     for name in declared_symbols():
         assert hasattr(lib, name), name
-    assert lib.trew_abi_version() == 1
+    assert lib.trew_abi_version() == 2
 
 
 def test_status_strings():

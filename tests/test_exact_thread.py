@@ -1,0 +1,86 @@
+"""The thread-per-read exact routing (trew_b200/csrc/exact_thread.cuh) is plain scalar code that also compiles for the
+host: tests/native/exact_thread_check.cpp packs reads into the device's planar layout and runs the very functions the
+CUDA kernel runs.  Here its tables are diffed against the CPU oracle -- bit-exact, no GPU needed.  Reads outside the
+path's limits (length, class-list capacity) must be reported as bailed and contribute nothing."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle
+from trew_b200 import api, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def etc(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("etc") / "libetc.so")
+    src = os.path.join(ROOT, "tests", "native", "exact_thread_check.cpp")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so, src])
+    lib = C.CDLL(so)
+    lib.etc_scan_reads.restype = C.c_long
+    lib.etc_scan_reads.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_long, C.POINTER(C.c_long), C.c_void_p]
+    return lib
+
+
+def thr_table(B):
+    """min M with (double)M / (double)T >= B, the reference's own IEEE division (src/kmer.cpp:2223-2224)."""
+    t = np.full(1025, 0xFFFF, dtype=np.uint16)
+    for T in range(1, 1025):
+        M = np.arange(0, T + 1, dtype=np.float64)
+        ok = M / np.float64(T) >= np.float64(B)
+        t[T] = int(np.argmax(ok))
+    return t
+
+
+def run(lib, reads, mn, mx, low=0.5, high=0.8):
+    buf, locs = api.make_chunk(reads)
+    locs = np.ascontiguousarray(locs, dtype=np.int32)
+    tl, th = thr_table(low), thr_table(high)
+    cap = 1 << 20
+    ot, ok = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    okey, oc = np.zeros(cap, np.uint64), np.zeros(cap, np.uint64)
+    nb = C.c_long(0)
+    bi = np.zeros(max(1, len(reads)), np.int32)
+    n = lib.etc_scan_reads(buf.tobytes(), locs.ctypes.data, len(reads), mn, mx, tl.ctypes.data, th.ctypes.data, ot.ctypes.data,
+                           ok.ctypes.data, okey.ctypes.data, oc.ctypes.data, cap, C.byref(nb), bi.ctypes.data)
+    assert n >= 0
+    tables = {(int(ot[i]), int(ok[i]), int(okey[i])): int(oc[i]) for i in range(n)}
+    return tables, [int(x) for x in bi[:nb.value]]
+
+
+@pytest.mark.parametrize("mn,mx,low,high,lengths", [(5, 32, 0.5, 0.8, [150, 150, 151, 128, 160, 149]),
+                                                    (5, 25, 0.5, 0.8, [100, 101, 125, 150]),
+                                                    (3, 20, 0.5, 0.8, [80, 99, 150]),
+                                                    (7, 20, 0.35, 0.6, [150, 97]),
+                                                    (5, 32, 0.9, 1.0, [150, 131]),
+                                                    (4, 31, 0.5, 0.5, [124, 150])])
+def test_thread_path_equals_oracle(etc, mn, mx, low, high, lengths):
+    reads = synth.adversarial_short(900 + mn * 31 + mx, 2500, max_unit=mx, lengths=lengths)
+    got, bailed = run(etc, reads, mn, mx, low, high)
+    keep = [r for i, r in enumerate(reads) if i not in set(bailed)]
+    want = Oracle(mn, mx, low, high).scan(0, keep)
+    assert got == want, (len(got), len(want), sorted(set(got.items()) ^ set(want.items()))[:6])
+    assert len(got) > 100
+    assert bailed == [i for i, r in enumerate(reads) if len(r) >= 2 * mn and (len(r) > 160 or len(r) < 4 * mx)]   # only the length limits
+
+
+def test_thread_path_on_the_bench_distribution(etc):
+    mat = synth.config_short(77, 30000, telomeric=0.05, half_telomeric=0.02, n_rate=0.003)
+    reads = [bytes(r) for r in mat]
+    got, bailed = run(etc, reads, 5, 32)
+    keep = [r for i, r in enumerate(reads) if i not in set(bailed)]
+    assert got == Oracle(5, 32).scan(0, keep)
+    assert bailed == []
+
+
+def test_thread_path_limits(etc):
+    # shorter than 4 * MAX_MER (the large-k whole-read scan would run), longer than 160 bases: bail
+    reads = [b"TTAGGG" * 20, b"TTAGGG" * 30, b"ACGT" * 2, b"TTAGGG" * 25]
+    got, bailed = run(etc, reads, 5, 32)
+    assert bailed == [0, 1]
+    assert got == Oracle(5, 32).scan(0, reads[2:]) and len(got) > 0

@@ -22,6 +22,10 @@ read_len = int(sys.argv[9]) if len(sys.argv) > 9 else 150
 flavor = int(sys.argv[10]) if len(sys.argv) > 10 else 0
 with api.DeviceContext(mode, mn, mx) as ctx:
     h = ctx.synth_resident(1, reads, read_len, tel_ppm=tel, half_ppm=half, n_ppm=nppm, sub_ppm=1000 if flavor == 2 else 10000, flavor=flavor)
+    for _ in range(2):          # warm-up: first launches load the kernels (lazy module loading costs milliseconds)
+        ctx.scan_resident(h)
+    ctx.sync()
+    ctx.kernel_times()
     for _ in range(scans):
         ctx.scan_resident(h)
     ctx.sync()

@@ -53,7 +53,7 @@ class Entry(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("reads", C.c_uint64), ("bases", C.c_uint64), ("units", C.c_uint64), ("survivors", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("device_ms", C.c_double)]
+                ("device_ms", C.c_double), ("host_pack_bytes", C.c_uint64), ("host_pack_ms", C.c_double)]
 
 
 # every symbol include/trew_b200.h declares (tests/test_abi.py checks the library exports all of them)
@@ -65,7 +65,9 @@ ABI_SYMBOLS = [
     "trew_synth_resident", "trew_dev_timer_start", "trew_dev_timer_stop", "trew_dev_kernel_times",
     "trew_dev_process_file", "trew_ingest_file", "trew_report_create", "trew_report_destroy", "trew_report_add_file",
     "trew_report_finish", "trew_dev_export_rows", "trew_dev_merge_rows", "trew_dev_reserve", "trew_dev_finish_merged",
-    "trew_pack_reads_ranges", "trew_report_text", "trew_synth_resident_ex",
+    "trew_pack_reads_ranges", "trew_report_text", "trew_synth_resident_ex", "trew_multi_create", "trew_multi_destroy",
+    "trew_multi_device_count", "trew_multi_last_error", "trew_multi_submit_chunk", "trew_multi_process_file",
+    "trew_multi_reset", "trew_multi_finish", "trew_multi_get_stats", "trew_multi_ctx",
 ]
 
 CHUNK_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_uint32, C.c_void_p,
@@ -116,6 +118,19 @@ def load_library() -> C.CDLL:
                                       C.c_uint32, C.POINTER(C.c_void_p)]
     L.trew_synth_resident_ex.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                          C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
+    L.trew_multi_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]
+    L.trew_multi_destroy.argtypes = [C.c_void_p]
+    L.trew_multi_destroy.restype = None
+    L.trew_multi_device_count.argtypes = [C.c_void_p]
+    L.trew_multi_last_error.argtypes = [C.c_void_p]
+    L.trew_multi_last_error.restype = C.c_char_p
+    L.trew_multi_submit_chunk.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
+    L.trew_multi_process_file.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    L.trew_multi_reset.argtypes = [C.c_void_p]
+    L.trew_multi_finish.argtypes = [C.c_void_p, C.POINTER(C.POINTER(Entry)), C.POINTER(C.c_uint64)]
+    L.trew_multi_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    L.trew_multi_ctx.argtypes = [C.c_void_p, C.c_int32]
+    L.trew_multi_ctx.restype = C.c_void_p
     L.trew_dev_timer_start.argtypes = [C.c_void_p]
     L.trew_dev_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.trew_dev_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -390,6 +405,100 @@ class DeviceContext:
     def stats(self) -> Stats:
         s = Stats()
         self._check(self.lib.trew_dev_get_stats(self.ctx, C.byref(s)))
+        return s
+
+
+class MultiContext:
+    """Several GPUs in one process (trew_multi): one context per device, one shared host packing pool, chunks dealt
+    round-robin, exact merge on the first device at finish -- the consumer fan-out of process_kmer*
+    (src/kmer.cpp:1271-1325, 1486-1515)."""
+
+    ENTRY_DTYPE = DeviceContext.ENTRY_DTYPE
+
+    def __init__(self, mode: int = MODE_SHORT, min_mer: int = 5, max_mer: int = 32, low: float = 0.5, high: float = 0.8,
+                 slice_length: int = 150, devices: Optional[Sequence[int]] = None, table_log2_slots: int = 0,
+                 n_staging: int = 0, host_threads: int = 0, staging_bytes: int = 0):
+        self.lib = load_library()
+        self.cfg = Config(mode, min_mer, max_mer, slice_length, low, high, 0, table_log2_slots, n_staging, host_threads,
+                          staging_bytes)
+        self.h = C.c_void_p()
+        devs = list(devices) if devices else []
+        arr = (C.c_int32 * max(1, len(devs)))(*devs)
+        rc = self.lib.trew_multi_create(C.byref(self.cfg), arr if devs else None, len(devs), C.byref(self.h))
+        if rc:
+            self.h = None
+            raise TrewError(rc, self.lib.trew_multi_last_error(None).decode() or self.lib.trew_status_string(rc).decode())
+        self.mode = mode
+
+    def _check(self, rc: int) -> None:
+        if rc:
+            raise TrewError(rc, self.lib.trew_multi_last_error(self.h).decode() or self.lib.trew_status_string(rc).decode())
+
+    @property
+    def device_count(self) -> int:
+        return self.lib.trew_multi_device_count(self.h)
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.lib.trew_multi_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def submit_chunk(self, buf1, locs1, buf2=None, locs2=None) -> None:
+        locs1 = np.ascontiguousarray(locs1, dtype=np.int32).reshape(-1, 2)
+        if buf2 is not None:
+            locs2 = np.ascontiguousarray(locs2, dtype=np.int32).reshape(-1, 2)
+            self._check(self.lib.trew_multi_submit_chunk(self.h, buf1.ctypes.data, locs1.ctypes.data, locs1.shape[0],
+                                                         buf2.ctypes.data, locs2.ctypes.data, locs2.shape[0]))
+        else:
+            self._check(self.lib.trew_multi_submit_chunk(self.h, buf1.ctypes.data, locs1.ctypes.data, locs1.shape[0], None, None, 0))
+
+    def submit_reads(self, reads1, reads2=None, chunk_reads: int = 0) -> None:
+        """chunk_reads > 0 cuts the reads into chunks of that many (each chunk goes to the next device)."""
+        step = chunk_reads if chunk_reads > 0 else max(1, len(reads1))
+        for i in range(0, len(reads1), step):
+            b1, l1 = make_chunk(reads1[i:i + step])
+            if reads2 is not None:
+                b2, l2 = make_chunk(reads2[i:i + step])
+                self.submit_chunk(b1, l1, b2, l2)
+            else:
+                self.submit_chunk(b1, l1)
+
+    def process_file(self, file1: str, file2: Optional[str] = None) -> None:
+        gz = lambda p: int(p.endswith(".gz") or p.endswith(".bgz"))
+        self._check(self.lib.trew_multi_process_file(self.h, file1.encode(), gz(file1), file2.encode() if file2 else None,
+                                                     gz(file2) if file2 else 0))
+
+    def reset(self) -> None:
+        self._check(self.lib.trew_multi_reset(self.h))
+
+    def finish_view(self) -> np.ndarray:
+        p = C.POINTER(Entry)()
+        n = C.c_uint64()
+        self._check(self.lib.trew_multi_finish(self.h, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, dtype=self.ENTRY_DTYPE)
+        buf = (C.c_char * (n.value * 32)).from_address(C.addressof(p.contents))
+        return np.frombuffer(buf, dtype=self.ENTRY_DTYPE, count=n.value)
+
+    def finish(self) -> Tables:
+        v = self.finish_view()
+        return {(int(r["table"]), int(r["k"]), (int(r["seq_hi"]) << 64) | int(r["seq_lo"])): int(r["count"]) for r in v}
+
+    def stats(self) -> Stats:
+        s = Stats()
+        self._check(self.lib.trew_multi_get_stats(self.h, C.byref(s)))
         return s
 
 

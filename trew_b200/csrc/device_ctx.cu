@@ -87,6 +87,7 @@ struct trew_ctx {
     bool export_valid = false;   // d_entries reflects the current table (no scan / merge / reset since the last export)
     trew_stats stats{};
     Pool* pool = nullptr;
+    bool own_pool = true;                        // false: the pool belongs to a trew_multi group
     std::string err;
     std::vector<RangeInfo> ranges_tmp;
     unsigned int keys_seen = 0;                  // distinct keys reported by the batches retired so far (lags the device)
@@ -132,7 +133,7 @@ int run_cap_for(const trew_config& cfg, uint32_t max_read_len) {
     uint32_t w = max_read_len;
     if (cfg.mode == TREW_MODE_LONG) w = std::min<uint32_t>(max_read_len, 2u * (uint32_t)cfg.slice_length);
     w = std::min<uint32_t>(w, (uint32_t)kMaxWindow);
-    return (int)((w + 2 + 7) & ~7u);
+    return (int)std::max<uint32_t>((w + 2 + 7) & ~7u, 32u);   // >= 32: eval_k's serial path keeps 96 words in htab + grp_*
 }
 
 size_t scratch_need(const trew_ctx* ctx, uint32_t max_read_len, unsigned int* stride) {
@@ -141,6 +142,13 @@ size_t scratch_need(const trew_ctx* ctx, uint32_t max_read_len, unsigned int* st
     st = (st + 15u) & ~15u;
     *stride = st;
     return (size_t)st * (size_t)exact_warps_total(ctx->sm_count);
+}
+
+constexpr int kScanCounters = 8;
+
+static int env_blocks_thread() {   // TREW_GRID_THREAD: thread-kernel blocks per SM (experiments)
+    static const int v = [] { const char* e = getenv("TREW_GRID_THREAD"); int x = e && *e ? atoi(e) : 4; return x > 0 ? x : 4; }();
+    return v;
 }
 
 // d_survivors holds 2 * n_units entries: survivors in the first half, the screen kernel's deferred list in the second
@@ -155,10 +163,12 @@ int launch_scan(trew_ctx* ctx, const DevBatch& b, uint32_t n_units, uint32_t max
         *scratch_bytes = need;
     }
     ctx->export_valid = false;
-    CK(cudaMemsetAsync(d_counters, 0, 4 * sizeof(unsigned int), st));
+    // d_counters: [0] survivors (list A) [1] work counter [2] deferred [3] thread-kernel bails [4] survivors, list B [5] work counter
+    CK(cudaMemsetAsync(d_counters, 0, kScanCounters * sizeof(unsigned int), st));
     if (ev) CK(cudaEventRecord(ev[0], st));
+    const bool thread_path = thread_path_applies(ctx->dcfg, max_read_len) && !(ctx->exact_flags & 4u) && n_units < (1u << 28);
     launch_filter(ctx->dcfg, b, n_units, max_read_len, d_survivors + n_units, d_counters + 2, d_survivors, d_counters, ctx->plan, st,
-                  ev ? ev[1] : nullptr);
+                  ev ? ev[1] : nullptr, thread_path ? d_survivors + n_units - 1 : nullptr, thread_path ? d_counters + 4 : nullptr);
     if (ev) CK(cudaEventRecord(ev[2], st));
     ExactArgs a{};
     a.survivors = d_survivors; a.n_survivors = d_counters; a.work_counter = d_counters + 1;
@@ -166,6 +176,19 @@ int launch_scan(trew_ctx* ctx, const DevBatch& b, uint32_t n_units, uint32_t max
     a.total_survivors = ctx->d_total_surv;
     a.packed_probes = n_units < (1u << 28) ? 1 : 0;
     a.exp_flags = ctx->exact_flags;
+    if (thread_path) {
+        // list A: thread per survivor; what it cannot take after all (its length limits) lands in the dead deferred list
+        unsigned int* hard = d_survivors + n_units;
+        launch_exact_thread(ctx->dcfg, b, d_survivors, d_counters, a.packed_probes, hard, d_counters + 3, ctx->d_total_surv,
+                            ctx->sm_count * env_blocks_thread(), ctx->exact_flags, st);
+        // list B (downwards from the top of the survivor array): warp per survivor
+        ExactArgs ab = a;
+        ab.survivors = d_survivors + n_units - 1; ab.reverse = 1; ab.n_survivors = d_counters + 4;
+        launch_exact(ctx->dcfg, b, ab, ctx->plan, st);
+        // ... and the thread kernel's leftovers (normally none)
+        a.survivors = hard; a.n_survivors = d_counters + 3; a.work_counter = d_counters + 5; a.total_survivors = nullptr;
+        ctx->stats.kernel_launches += 2;
+    }
     launch_exact(ctx->dcfg, b, a, ctx->plan, st);
     if (ev) CK(cudaEventRecord(ev[3], st));
     CK(cudaGetLastError());
@@ -241,7 +264,7 @@ int submit_ranges(trew_ctx* ctx, const ChunkView& cv, const RangeInfo* rg, int n
     if (rc) return rc;
     const double t1 = trace ? now() : 0;
     if ((rc = maybe_grow_table(ctx)) != TREW_OK) return rc;
-    const double t2 = trace ? now() : 0;
+    const double t2 = now();
     BatchView v;
     batch_layout(s.h_buf, n, total_bases, &v);
     std::vector<uint64_t> bit0((size_t)n_ranges);
@@ -275,7 +298,8 @@ int submit_ranges(trew_ctx* ctx, const ChunkView& cv, const RangeInfo* rg, int n
         if (n_inv > s.inv_cap) { sparse = false; pack(false); }
     }
 
-    const double t3 = trace ? now() : 0;
+    const double t3 = now();
+    ctx->stats.host_pack_bytes += total_bases; ctx->stats.host_pack_ms += t3 - t2;
     CK(cudaEventRecord(s.ev_start, s.stream));
     const size_t head_bytes = (size_t)((char*)v.val - (char*)s.h_buf);
     unsigned int* d_val = (unsigned int*)((char*)s.d_buf + head_bytes);
@@ -461,6 +485,12 @@ const char* trew_status_string(int status) {
 
 // trew_dev_create has no context to hang its message on: it is kept here and read with trew_dev_last_error(NULL)
 static thread_local std::string g_create_error;
+// set by trew_multi_create around its trew_dev_create calls: the group's contexts share one packing pool
+static thread_local Pool* g_shared_pool = nullptr;
+
+static int default_host_threads(int asked) {
+    return asked > 0 ? asked : (int)std::min(64u, std::max(1u, std::thread::hardware_concurrency()));
+}
 
 const char* trew_dev_last_error(const trew_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
@@ -521,12 +551,15 @@ int trew_dev_create(const trew_config* cfg, trew_ctx** out) {
     CKC(cudaMemset(ctx->d_total_surv, 0, sizeof(unsigned long long)));
     std::vector<unsigned short> thr;
     build_thr(cfg->low_baseline, thr);
-    CKC(cudaMalloc((void**)&ctx->d_thr, thr.size() * sizeof(unsigned short)));
+    std::vector<unsigned short> thr_hi;
+    build_thr(cfg->high_baseline, thr_hi);
+    CKC(cudaMalloc((void**)&ctx->d_thr, 2 * thr.size() * sizeof(unsigned short)));
     CKC(cudaMemcpy(ctx->d_thr, thr.data(), thr.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    CKC(cudaMemcpy(ctx->d_thr + thr.size(), thr_hi.data(), thr_hi.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
     ctx->dcfg.mode = cfg->mode; ctx->dcfg.min_mer = cfg->min_mer; ctx->dcfg.max_mer = cfg->max_mer;
     ctx->dcfg.slice_len = ctx->cfg.slice_length; ctx->dcfg.low = cfg->low_baseline; ctx->dcfg.high = cfg->high_baseline;
     ctx->dcfg.slots = d_slots; ctx->dcfg.slot_mask = (unsigned int)(ctx->n_slots - 1);
-    ctx->dcfg.error_flag = ctx->d_error; ctx->dcfg.thr_low = ctx->d_thr;
+    ctx->dcfg.error_flag = ctx->d_error; ctx->dcfg.thr_low = ctx->d_thr; ctx->dcfg.thr_high = ctx->d_thr + kThrTableSize;
     CKC(prepare_exact(kMaxWindow + 9));
     CKC(cudaStreamCreateWithFlags(&ctx->main_stream, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
@@ -548,14 +581,14 @@ int trew_dev_create(const trew_config* cfg, trew_ctx** out) {
         *s.h_keys = 0;
         s.survivors_cap = ctx->staging_bytes / 8;  // >= reads of >= 11 bases; submit_split enforces it
         CKC(cudaMalloc((void**)&s.d_survivors, 2 * s.survivors_cap * sizeof(unsigned int)));
-        CKC(cudaMalloc((void**)&s.d_counters, 4 * sizeof(unsigned int)));
+        CKC(cudaMalloc((void**)&s.d_counters, kScanCounters * sizeof(unsigned int)));
         CKC(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         CKC(cudaEventCreate(&s.ev_start));
         CKC(cudaEventCreate(&s.ev_done));
     }
     CKC(cudaMalloc((void**)&ctx->d_n, sizeof(unsigned int)));
-    int nt = cfg->host_threads > 0 ? cfg->host_threads : (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
-    ctx->pool = new Pool(nt);
+    if (g_shared_pool) { ctx->pool = g_shared_pool; ctx->own_pool = false; }
+    else ctx->pool = new Pool(default_host_threads(cfg->host_threads));
 #undef CKC
     *out = ctx;
     return TREW_OK;
@@ -595,7 +628,7 @@ void trew_dev_destroy(trew_ctx* ctx) {
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
-    delete ctx->pool;
+    if (ctx->own_pool) delete ctx->pool;
     delete ctx;
 }
 
@@ -684,7 +717,7 @@ int trew_dev_upload(trew_ctx* ctx, const trew_batch* batch, trew_resident** out)
     r->batch.lo = r->batch.hi + v.plane_words; r->batch.val = r->batch.lo + v.plane_words;
     r->n_reads = n; r->n_units = ctx->cfg.mode == TREW_MODE_PAIR ? n / 2 : n; r->max_read_len = batch->max_read_len; r->bases = bases;
     CK(cudaMalloc((void**)&r->d_survivors, 2 * (size_t)std::max<uint32_t>(r->n_units, 1) * sizeof(unsigned int)));
-    CK(cudaMalloc((void**)&r->d_counters, 4 * sizeof(unsigned int)));
+    CK(cudaMalloc((void**)&r->d_counters, kScanCounters * sizeof(unsigned int)));
     *out = r;
     return TREW_OK;
 }
@@ -1024,7 +1057,7 @@ int trew_synth_resident_ex(trew_ctx* ctx, uint64_t seed, uint32_t n_reads, uint3
     r->n_reads = n_reads; r->n_units = ctx->cfg.mode == TREW_MODE_PAIR ? n_reads / 2 : n_reads;
     r->max_read_len = read_len; r->bases = bases;
     CK(cudaMalloc((void**)&r->d_survivors, 2 * (size_t)std::max<uint32_t>(r->n_units, 1) * sizeof(unsigned int)));
-    CK(cudaMalloc((void**)&r->d_counters, 4 * sizeof(unsigned int)));
+    CK(cudaMalloc((void**)&r->d_counters, kScanCounters * sizeof(unsigned int)));
     *out = r;
     return TREW_OK;
 }
@@ -1042,6 +1075,171 @@ int trew_dev_process_file(trew_ctx* ctx, const char* file1, int is_gz1, const ch
                                  ctx->pool, &ctx->ingest);
     if (r.status != TREW_OK && r.status != TREW_ERR_CUDA && !r.message.empty()) ctx->err = r.message;
     return r.status;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// several GPUs in one process (see include/trew_b200.h, "several GPUs in one process")
+// ------------------------------------------------------------------------------------------------
+
+struct trew_multi {
+    std::vector<trew_ctx*> ctx;
+    Pool* pool = nullptr;
+    size_t next = 0;                  // device the next chunk goes to
+    std::string err;
+    // per peer device: its rows as copied to the first device (device-0 memory)
+    std::vector<trew_entry*> d_peer; std::vector<size_t> d_peer_cap;
+};
+
+namespace {
+int mfail(trew_multi* m, int status, const std::string& msg) { if (m) m->err = msg; return status; }
+}  // namespace
+
+extern "C" {
+
+int trew_multi_create(const trew_config* cfg, const int32_t* devices, int32_t n_devices, trew_multi** out) {
+    if (!cfg || !out || n_devices < 0 || (n_devices > 0 && !devices)) return TREW_ERR_ARG;
+    *out = nullptr;
+    std::vector<int32_t> dev;
+    if (n_devices == 0) {
+        int nd = 0;
+        if (cudaGetDeviceCount(&nd) != cudaSuccess || nd <= 0) { g_create_error = "no CUDA device"; return TREW_ERR_CUDA; }
+        for (int i = 0; i < nd; i++) dev.push_back(i);
+    } else {
+        dev.assign(devices, devices + n_devices);   // a device listed k times gets k contexts (used by the tests)
+    }
+    trew_multi* m = new trew_multi();
+    m->pool = new Pool(default_host_threads(cfg->host_threads));
+    g_shared_pool = m->pool;
+    int rc = TREW_OK;
+    for (int32_t d : dev) {
+        trew_config c = *cfg;
+        c.device = d;
+        trew_ctx* x = nullptr;
+        rc = trew_dev_create(&c, &x);
+        if (rc != TREW_OK) break;
+        m->ctx.push_back(x);
+    }
+    g_shared_pool = nullptr;
+    if (rc != TREW_OK) { trew_multi_destroy(m); return rc; }   // g_create_error holds the message
+    // rows travel to the first device at end of file: direct NVLink copies where the devices are peers (the copy also
+    // works without, staged through the host)
+    for (size_t i = 1; i < m->ctx.size(); i++) {
+        int can = 0;
+        if (dev[i] != dev[0] && cudaDeviceCanAccessPeer(&can, dev[0], dev[i]) == cudaSuccess && can) {
+            cudaSetDevice(dev[0]);
+            cudaError_t e = cudaDeviceEnablePeerAccess(dev[i], 0);
+            if (e != cudaSuccess) cudaGetLastError();   // already enabled is fine
+        }
+    }
+    m->d_peer.assign(m->ctx.size(), nullptr);
+    m->d_peer_cap.assign(m->ctx.size(), 0);
+    *out = m;
+    return TREW_OK;
+}
+
+void trew_multi_destroy(trew_multi* m) {
+    if (!m) return;
+    if (!m->ctx.empty()) {
+        cudaSetDevice(m->ctx[0]->cfg.device);
+        for (trew_entry* p : m->d_peer) if (p) cudaFree(p);
+    }
+    for (trew_ctx* x : m->ctx) trew_dev_destroy(x);
+    delete m->pool;
+    delete m;
+}
+
+int trew_multi_device_count(const trew_multi* m) { return m ? (int)m->ctx.size() : 0; }
+
+const char* trew_multi_last_error(const trew_multi* m) { return m ? m->err.c_str() : g_create_error.c_str(); }
+
+trew_ctx* trew_multi_ctx(trew_multi* m, int32_t i) { return m && i >= 0 && (size_t)i < m->ctx.size() ? m->ctx[(size_t)i] : nullptr; }
+
+int trew_multi_submit_chunk(trew_multi* m, const char* buffer1, const int32_t* locs1, uint32_t n1, const char* buffer2,
+                            const int32_t* locs2, uint32_t n2) {
+    if (!m) return TREW_ERR_ARG;
+    trew_ctx* x = m->ctx[m->next];
+    m->next = (m->next + 1) % m->ctx.size();
+    int rc = trew_dev_submit_chunk(x, buffer1, locs1, n1, buffer2, locs2, n2);
+    if (rc != TREW_OK) return mfail(m, rc, x->err);
+    return TREW_OK;
+}
+
+int trew_multi_process_file(trew_multi* m, const char* file1, int is_gz1, const char* file2, int is_gz2) {
+    if (!m || !file1) return TREW_ERR_ARG;
+    trew_ctx* x0 = m->ctx[0];
+    if ((x0->cfg.mode == TREW_MODE_PAIR) != (file2 != nullptr)) return mfail(m, TREW_ERR_ARG, "second file only in pair mode");
+    // one reader, N consumers: every block of the file goes to the next device
+    IngestResult r = ingest_file(x0->cfg.mode, x0->cfg.slice_length, file1, is_gz1 != 0, file2, is_gz2 != 0, 0,
+                                 [&](const char* b1, const std::vector<int32_t>& l1, const char* b2, const std::vector<int32_t>& l2) {
+                                     return trew_multi_submit_chunk(m, b1, l1.data(), (uint32_t)(l1.size() / 2), b2, b2 ? l2.data() : nullptr,
+                                                                    b2 ? (uint32_t)(l2.size() / 2) : 0u);
+                                 },
+                                 m->pool, &x0->ingest);
+    if (r.status != TREW_OK && !r.message.empty()) m->err = r.message;
+    return r.status;
+}
+
+int trew_multi_reset(trew_multi* m) {
+    if (!m) return TREW_ERR_ARG;
+    for (trew_ctx* x : m->ctx) { int rc = trew_dev_reset(x); if (rc != TREW_OK) return mfail(m, rc, x->err); }
+    m->next = 0;
+    return TREW_OK;
+}
+
+int trew_multi_finish(trew_multi* m, const trew_entry** entries, uint64_t* n_entries) {
+    if (!m) return TREW_ERR_ARG;
+    trew_ctx* x0 = m->ctx[0];
+    const size_t nd = m->ctx.size();
+    if (nd == 1) {
+        int rc = trew_dev_finish(x0, entries, n_entries);
+        return rc == TREW_OK ? rc : mfail(m, rc, x0->err);
+    }
+    // every peer compacts its table on its own device (they do so concurrently: the kernels are queued on all devices
+    // before the first wait) ...
+    std::vector<const trew_entry*> d_src(nd, nullptr);
+    std::vector<uint64_t> n_rows(nd, 0);
+    for (size_t i = 1; i < nd; i++) {
+        int rc = export_entries(m->ctx[i], false, &d_src[i], &n_rows[i]);
+        if (rc != TREW_OK) return mfail(m, rc, m->ctx[i]->err);
+    }
+    // ... and its rows are copied to the first device over NVLink
+    trew_ctx* ctx = x0;   // for CK
+    CK(cudaSetDevice(x0->cfg.device));
+    std::vector<const trew_entry*> lists;
+    std::vector<uint64_t> sizes;
+    for (size_t i = 1; i < nd; i++) {
+        if (n_rows[i] == 0) continue;
+        if (n_rows[i] > m->d_peer_cap[i]) {
+            if (m->d_peer[i]) CK(cudaFree(m->d_peer[i]));
+            m->d_peer[i] = nullptr;
+            m->d_peer_cap[i] = (size_t)n_rows[i] + n_rows[i] / 4 + 1024;
+            CK(cudaMalloc((void**)&m->d_peer[i], m->d_peer_cap[i] * sizeof(trew_entry)));
+        }
+        CK(cudaMemcpyPeerAsync(m->d_peer[i], x0->cfg.device, d_src[i], m->ctx[i]->cfg.device, n_rows[i] * sizeof(trew_entry), x0->main_stream));
+        lists.push_back(m->d_peer[i]);
+        sizes.push_back(n_rows[i]);
+    }
+    int rc = trew_dev_finish_merged(x0, lists.data(), sizes.data(), (uint32_t)lists.size(), entries, n_entries);
+    return rc == TREW_OK ? rc : mfail(m, rc, x0->err);
+}
+
+int trew_multi_get_stats(trew_multi* m, trew_stats* out) {
+    if (!m || !out) return TREW_ERR_ARG;
+    trew_stats t;
+    memset(&t, 0, sizeof(t));
+    for (trew_ctx* x : m->ctx) {
+        trew_stats s;
+        int rc = trew_dev_get_stats(x, &s);
+        if (rc != TREW_OK) return mfail(m, rc, x->err);
+        t.reads += s.reads; t.bases += s.bases; t.units += s.units; t.survivors += s.survivors;
+        t.kernel_launches += s.kernel_launches; t.h2d_bytes += s.h2d_bytes; t.d2h_bytes += s.d2h_bytes;
+        t.host_pack_bytes += s.host_pack_bytes; t.host_pack_ms += s.host_pack_ms;
+        t.device_ms = std::max(t.device_ms, s.device_ms);
+    }
+    *out = t;
+    return TREW_OK;
 }
 
 }  // extern "C"

@@ -1,0 +1,358 @@
+// Thread-per-read exact routing for short single-end reads: the whole of buffer_task (src/kmer.cpp:80-266) with
+// k_mer_check (src/kmer.cpp:2144-2344) and k_mer_target (src/kmer.cpp:1894-2017) as plain scalar code.
+//
+// Why it exists: the warp-per-survivor kernel (scan_kernels.cu, trew_exact_kernel) spends its time on latency -- one
+// survivor per warp, most instructions warp-uniform, stack traffic around its calls, an instruction footprint that
+// does not fit the instruction cache.  Here every THREAD owns a survivor, so an SM works on several hundred survivors
+// at once instead of 32 and the per-survivor instruction stream is issued for 32 survivors at a time.
+//
+// Layout: a thread's working set (the read's bit-planes, the window being scanned, prefix planes, masks, the first
+// classes of an evaluation) lives in a per-thread slice of SHARED memory, word i of thread t at base[i * stride + t]:
+// consecutive threads hit consecutive banks, array indices may be run-time values (register arrays would need
+// compile-time indices, i.e. fully unrolled code -- tried: 256 KB of SASS and spilled planes), and the functions below
+// stay small, out-of-line and loop-based, which keeps the instruction footprint at a few KB.
+//
+// The code is scalar (no warp intrinsics), so it also compiles for the host: tests/native/exact_thread_check.cpp runs
+// this very file against the oracle without a GPU (stride 1, base = a plain array).
+//
+// Limits (anything else is handed to the warp kernel through the `false` return, before anything was emitted):
+// 4 * MAX_MER <= read length <= 160 (so the large-k whole-read scan of src/kmer.cpp:165-171 never runs) and
+// MAX_MER <= 32 (64-bit units).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ET_HD __host__ __device__ __forceinline__
+#define ET_FN __host__ __device__ __noinline__
+#else
+#define ET_HD inline
+#define ET_FN inline
+#endif
+
+namespace trew {
+namespace et {
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+constexpr int kReadWords = 5;      // read planes: up to 160 bases
+constexpr int kMaxRead = 32 * kReadWords;
+constexpr int kClsCap = 6;         // distinct rotation classes of an evaluated (window, period) kept in the workspace ...
+constexpr int kClsSpill = kMaxRead - kClsCap;   // ... the rest (noisy windows, rare) in thread-local memory
+
+// workspace words of one thread
+enum {
+    W_RH = 0, W_RL = W_RH + kReadWords + 2, W_RV = W_RL + kReadWords + 2,     // the read's planes (+ zero words behind)
+    W_H = W_RV + kReadWords + 2, W_L = W_H + kReadWords + 2, W_V = W_L + kReadWords + 2,   // the current window
+    W_PH = W_V + kReadWords + 2, W_PL = W_PH + kReadWords + 2,               // its exclusive prefix-XOR planes
+    W_WV = W_PL + kReadWords + 2, W_LINK = W_WV + kReadWords, W_RS = W_LINK + kReadWords,   // valid windows, links, run starts
+    W_CKEY = W_RS + kReadWords,                                              // class keys: lo, hi words alternating
+    W_CTOT = W_CKEY + 2 * kClsCap, W_CLAST = W_CTOT + kClsCap,
+    kWorkWords = W_CLAST + kClsCap
+};
+
+struct Mem {
+    u32* base; int stride;
+    ET_HD u32& operator[](int i) const { return base[i * stride]; }
+};
+
+ET_HD int popc(u32 x) {
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+ET_HD int ffs1(u32 x) {   // index of the lowest set bit, x != 0
+#if defined(__CUDA_ARCH__)
+    return __ffs(x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+ET_HD u32 fshr(u32 lo, u32 hi, int sh) {   // low word of (hi:lo) >> (sh & 31)
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    sh &= 31;
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+ET_HD u32 brev32(u32 x) {
+#if defined(__CUDA_ARCH__)
+    return __brev(x);
+#else
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0f0f0f0fu) | ((x & 0x0f0f0f0fu) << 4);
+    x = ((x >> 8) & 0x00ff00ffu) | ((x & 0x00ff00ffu) << 8);
+    return (x >> 16) | (x << 16);
+#endif
+}
+ET_HD u32 lowmask(int bits) { return bits >= 32 ? 0xffffffffu : (bits <= 0 ? 0u : ((1u << bits) - 1u)); }
+ET_HD u32 pxor32(u32 x) { x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16; return x; }
+ET_HD u64 spread(u32 x) {   // bit m -> bit 2m
+    u64 v = x;
+    v = (v | (v << 16)) & 0x0000FFFF0000FFFFULL;
+    v = (v | (v << 8)) & 0x00FF00FF00FF00FFULL;
+    v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0FULL;
+    v = (v | (v << 2)) & 0x3333333333333333ULL;
+    v = (v | (v << 1)) & 0x5555555555555555ULL;
+    return v;
+}
+
+// minimal rotation of a k-mer, k <= 32 (get_rot_seq, src/kmer.cpp:1815-1823)
+ET_FN u64 canon(u64 w, int k) {
+    const int sh = 2 * (k - 1);
+    if (k <= 16) {
+        u32 b = (u32)w, c = (u32)w;
+        for (int r = 1; r < k; r++) { c = ((c & 3u) << sh) | (c >> 2); b = c < b ? c : b; }
+        return b;
+    }
+    u64 best = w, cur = w;
+    for (int r = 1; r < k; r++) { cur = ((cur & 3ULL) << sh) | (cur >> 2); best = cur < best ? cur : best; }
+    return best;
+}
+// canonical rotation of the reverse complement (rot_reverse_complement, src/kmer.cpp:72-74)
+ET_HD u64 crc(u64 w, int k) {
+    const u32 lo = brev32((u32)w), hi = brev32((u32)(w >> 32));
+    u64 x = ((u64)lo << 32) | hi;                                                 // all 64 bits reversed
+    x = ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);   // 2-bit symbols reversed
+    return canon(~x >> (64 - 2 * k), k);
+}
+ET_HD bool homo(u64 w, int k) {   // get_repeat_check: at most one distinct base
+    return k <= 1 || ((w ^ (w >> 2)) & ((1ULL << (2 * (k - 1))) - 1ULL)) == 0;
+}
+
+// bases [off, off + len) of the read (W_RH / W_RL / W_RV) become the current window (W_H / W_L / W_V)
+ET_FN void set_window(Mem m, int off, int len) {
+    const int nw = (len + 31) >> 5, jo = off >> 5, sh = off & 31;
+    for (int j = 0; j < kReadWords + 2; j++) {
+        u32 h = 0, l = 0, v = 0;
+        if (j < nw) {
+            const u32 msk = lowmask(len - 32 * j);
+            h = fshr(m[W_RH + jo + j], m[W_RH + jo + j + 1], sh) & msk;
+            l = fshr(m[W_RL + jo + j], m[W_RL + jo + j + 1], sh) & msk;
+            v = fshr(m[W_RV + jo + j], m[W_RV + jo + j + 1], sh) & msk;
+        }
+        m[W_H + j] = h; m[W_L + j] = l; m[W_V + j] = v;
+    }
+}
+
+// the spill part of a class list (classes beyond the first kClsCap of an evaluation)
+struct ClsSpill {
+    u64 key[kClsSpill];
+    unsigned short tot[kClsSpill], last[kClsSpill];
+};
+
+ET_HD u64 cls_key(Mem m, int q) { return (u64)m[W_CKEY + 2 * q] | ((u64)m[W_CKEY + 2 * q + 1] << 32); }
+
+// Match-bit runs of the current window for one period (Lemma L1: windows i and i+1 are in the same rotation class iff
+// both are valid and base[i] == base[i+k], so classes are unions of maximal runs).  W_WV = valid k-windows (input);
+// fills W_LINK and W_RS (run starts) and returns the number of runs.
+ET_FN int prepare_runs(Mem m, int nw, int k) {
+    for (int j = 0; j < nw; j++) {
+        // plane >> k for k <= 32
+        const u32 hs = k < 32 ? fshr(m[W_H + j], m[W_H + j + 1], k) : m[W_H + j + 1];
+        const u32 ls = k < 32 ? fshr(m[W_L + j], m[W_L + j + 1], k) : m[W_L + j + 1];
+        const u32 eq = ~((hs ^ m[W_H + j]) | (ls ^ m[W_L + j]));
+        const u32 wvj = m[W_WV + j];
+        const u32 nxt = (wvj >> 1) | (j + 1 < nw ? m[W_WV + j + 1] << 31 : 0u);
+        m[W_LINK + j] = eq & wvj & nxt;
+    }
+    int runs = 0;
+    for (int j = 0; j < nw; j++) {
+        const u32 rs = m[W_WV + j] & ~((m[W_LINK + j] << 1) | (j ? m[W_LINK + j - 1] >> 31 : 0u));
+        m[W_RS + j] = rs;
+        runs += popc(rs);
+    }
+    return runs;
+}
+
+// Class statistics from the runs: the inner loops of k_mer_check (src/kmer.cpp:2183-2216), one minimal rotation per
+// run.  Returns the number of classes: the first kClsCap in the workspace, the others in `x`.
+// approx: classes by base composition (#C|A, #G|A, #A of the run's first window) instead of by minimal rotation.
+// Rotation keeps the composition, so these classes are unions of the true ones and their largest total bounds the true
+// largest class from above -- at a fraction of the cost (no k-step rotation loop); used to turn away noisy windows.
+ET_FN int classify_runs(Mem m, int nw, int k, ClsSpill& x, bool approx) {
+    int n = 0, ord = 0;
+    const u32 km = lowmask(k);
+    for (int j = 0; j < nw; j++) {
+        const u32 wvj = m[W_WV + j];
+        u32 rr = m[W_RS + j];
+        while (rr) {
+            const int b = ffs1(rr);
+            rr &= rr - 1;
+            const u32 c0 = (u32)(ord + popc(wvj & ((1u << b) - 1u)));
+            // the run ends at the first window without a link to its successor (the last valid window has none)
+            int jj = j;
+            u32 z = ~m[W_LINK + j] & (0xffffffffu << b);
+            while (!z) { jj++; z = ~m[W_LINK + jj]; }
+            const u32 cnt = (u32)(32 * (jj - j) + ffs1(z) - b + 1);
+            // the run's first k-mer, first base most significant (the reference's shift-in order, src/kmer.cpp:2186-2189)
+            const u32 hk = fshr(m[W_H + j], m[W_H + j + 1], b) & km, lk = fshr(m[W_L + j], m[W_L + j + 1], b) & km;
+            u64 key;
+            if (approx) key = (u64)((u32)popc(hk) | ((u32)popc(lk) << 8) | ((u32)popc(hk & lk) << 16));
+            else key = canon((spread(brev32(hk) >> (32 - k)) << 1) | spread(brev32(lk) >> (32 - k)), k);
+            const u32 last = c0 + cnt - 1u;
+            int q = 0;
+            const int nq = n < kClsCap ? n : kClsCap;
+            while (q < nq && cls_key(m, q) != key) q++;
+            if (q < nq) {
+                m[W_CTOT + q] += cnt; m[W_CLAST + q] = last;
+            } else if (n < kClsCap) {
+                m[W_CKEY + 2 * n] = (u32)key; m[W_CKEY + 2 * n + 1] = (u32)(key >> 32); m[W_CTOT + n] = cnt; m[W_CLAST + n] = last;
+                n++;
+            } else {
+                int s = 0;
+                while (s < n - kClsCap && x.key[s] != key) s++;
+                if (s < n - kClsCap) { x.tot[s] = (unsigned short)(x.tot[s] + cnt); x.last[s] = (unsigned short)last; }
+                else { x.key[s] = key; x.tot[s] = (unsigned short)cnt; x.last[s] = (unsigned short)last; n++; }
+            }
+        }
+        ord += popc(wvj);
+    }
+    return n;
+}
+
+// M and K_MER_DATA_MAX_SEQ of the last evaluation: the class whose running count first reaches the final maximum (strict
+// '<' at src/kmer.cpp:2202) = largest total, ties broken by the EARLIEST last window
+ET_FN int cls_max(Mem m, int n, const ClsSpill& x, u64& S) {
+    u32 best = 0;
+    S = 0;
+    for (int q = 0; q < n && q < kClsCap; q++) {
+        const u32 score = (m[W_CTOT + q] << 10) | (1023u - m[W_CLAST + q]);
+        if (score > best) { best = score; S = cls_key(m, q); }
+    }
+    for (int q = 0; q < n - kClsCap; q++) {
+        const u32 score = ((u32)x.tot[q] << 10) | (1023u - x.last[q]);
+        if (score > best) { best = score; S = x.key[q]; }
+    }
+    return (int)(best >> 10);
+}
+
+// max(baseline, last accepted frequency) without floating point: see scan_kernels.cu, "No floating point on the device"
+ET_HD bool need_pass(const unsigned short* thr, u32 need, int M, int T) {
+    const u32 mm = need & 0xffffu, t = need >> 16;
+    return M >= (int)thr[T] && (t == 0u || (u32)M * t >= mm * (u32)T);
+}
+
+ET_HD void shrink_valid(Mem m, int nw) {   // valid k-windows -> valid (k+1)-windows
+    for (int j = 0; j < nw; j++) m[W_WV + j] &= (m[W_WV + j] >> 1) | (j + 1 < nw ? m[W_WV + j + 1] << 31 : 0u);
+}
+
+// k_mer_check without emission (src/kmer.cpp:2144-2258) on the current window: returns target_k_high | target_k_low << 8
+ET_FN u32 scan_window(Mem m, int len, int kmin, int kmax, const unsigned short* thr_low, const unsigned short* thr_high, ClsSpill& x) {
+    if (kmax > len) kmax = len;
+    if (kmax < kmin) return 0u;
+    const int nw = (len + 31) >> 5;
+    // exclusive prefix-XOR planes: entry i = parity of the hi (lo) bits of bases [0, i)
+    {
+        u32 ch = 0, cl = 0, tph = 0, tpl = 0;
+        for (int j = 0; j <= nw; j++) {
+            const u32 ih = pxor32(m[W_H + j]) ^ ch, il = pxor32(m[W_L + j]) ^ cl;
+            m[W_PH + j] = (ih << 1) | tph; m[W_PL + j] = (il << 1) | tpl;
+            tph = ih >> 31; tpl = il >> 31;
+            ch = 0u - tph; cl = 0u - tpl;
+        }
+        m[W_PH + nw + 1] = 0u; m[W_PL + nw + 1] = 0u;
+    }
+    for (int j = 0; j < nw; j++) m[W_WV + j] = m[W_V + j];
+    for (int t = 1; t < kmin; t++) shrink_valid(m, nw);
+    u64 blockedL = 0, blockedH = 0;   // periods with an accepted divisor (src/kmer.cpp:2225-2230); k <= 32 here
+    u32 needL = 0, needH = 0;         // last accepted ratio, m | t << 16
+    u32 res = 0;
+    for (int k = kmin; k <= kmax; k++, shrink_valid(m, nw)) {
+        const bool blkL = (blockedL >> k) & 1ULL, blkH = (blockedH >> k) & 1ULL;
+        // upper bound on the largest class: largest bucket of the (hi parity, lo parity) signature (Lemma L2)
+        int T = 0, cH = 0, cL = 0, c11 = 0;
+        for (int j = 0; j < nw; j++) {
+            const u32 wvj = m[W_WV + j];
+            const u32 dh = ((k < 32 ? fshr(m[W_PH + j], m[W_PH + j + 1], k) : m[W_PH + j + 1]) ^ m[W_PH + j]) & wvj;
+            const u32 dl = ((k < 32 ? fshr(m[W_PL + j], m[W_PL + j + 1], k) : m[W_PL + j + 1]) ^ m[W_PL + j]) & wvj;
+            T += popc(wvj); cH += popc(dh); cL += popc(dl); c11 += popc(dh & dl);
+        }
+        if (T == 0) break;   // the valid-window mask only shrinks with k
+        if (blkL && blkH) continue;
+        const int c10 = cH - c11, c01 = cL - c11, c00 = T - cH - cL + c11;
+        int U = c00 > c01 ? c00 : c01;
+        U = U > c10 ? U : c10;
+        U = U > c11 ? U : c11;
+        if (!((!blkL && need_pass(thr_low, needL, U, T)) || (!blkH && need_pass(thr_high, needH, U, T)))) continue;
+        u64 S;
+        if (prepare_runs(m, nw, k) > 3) {   // several runs: first the cheap bound from the runs' base compositions
+            const int Mu = cls_max(m, classify_runs(m, nw, k, x, true), x, S);
+            if (!((!blkL && need_pass(thr_low, needL, Mu, T)) || (!blkH && need_pass(thr_high, needH, Mu, T)))) continue;
+        }
+        const int n = classify_runs(m, nw, k, x, false);
+        const int M = cls_max(m, n, x, S);
+        if (homo(S, k)) continue;
+        const bool accL = !blkL && need_pass(thr_low, needL, M, T), accH = !blkH && need_pass(thr_high, needH, M, T);
+        if (accL || accH) {
+            u64 mm = 0;
+            for (int j = k; j < 64; j += k) mm |= 1ULL << j;
+            const u32 need = (u32)M | ((u32)T << 16);
+            if (accL) { res = (res & 0xffu) | ((u32)k << 8); needL = need; blockedL |= mm; }
+            if (accH) { res = (res & 0xff00u) | (u32)k; needH = need; blockedH |= mm; }
+        }
+    }
+    return res;
+}
+
+enum { T_F = 0, T_B = 2, T_O = 4 };
+
+// buffer_task for one read (src/kmer.cpp:111-171).  The read's planes are in W_RH / W_RL / W_RV (zero beyond base n).
+// pm: probes (bit 0 left half, bit 1 right half) the filter kernels could not rule out; the scan of any other window
+// finds nothing.  emit(table, k, key, count) receives the emissions.  Returns false when the read is outside this
+// path's limits: then nothing was emitted and the warp kernel has to take it.
+template <class Emit>
+ET_HD bool route_short_thread(Mem m, int n, u32 pm, int min_mer, int max_mer, const unsigned short* thr_low,
+                              const unsigned short* thr_high, Emit& emit) {
+    if (n < 2 * min_mer) return true;                                   // src/kmer.cpp:113
+    if (max_mer > 32 || n > kMaxRead || 4 * max_mer > n) return false;   // outside the limits (n >= 4 * MIN follows)
+    const int kmax = n / 4 < max_mer ? n / 4 : max_mer;
+    const int llen = n / 2, rlen = (n + 1) / 2, roff = n - rlen;
+    ClsSpill x;
+    u32 L = 0, R = 0;   // target_k_high | target_k_low << 8 of the two halves
+    if (pm & 1u) { set_window(m, 0, llen); L = scan_window(m, llen, min_mer, kmax, thr_low, thr_high, x); }
+    if (pm & 2u) { set_window(m, roff, rlen); R = scan_window(m, rlen, min_mer, kmax, thr_low, thr_high, x); }   // "always evaluated"
+    if ((L | R) == 0u) return true;
+    // right-half emissions survive only for classes where the left half found nothing (src/kmer.cpp:123-159)
+    int cur_win = -1, cur_k = 0, ncls = 0, T = 0;   // the evaluation in the workspace
+    for (int c = 0; c < 2; c++) {
+        const int Lc = (int)((L >> (8 * c)) & 0xffu), Rc = (int)((R >> (8 * c)) & 0xffu);
+        int win, k, table;
+        if (Lc > 0 && Lc == Rc) { win = 2; k = Lc; table = T_O + c; }          // k_mer_target on the whole read -> both
+        else if (Lc > 0) { win = 0; k = Lc; table = T_F + c; }
+        else if (Rc > 0) { win = 1; k = Rc; table = T_B + c; }
+        else continue;
+        if (win != cur_win || k != cur_k) {   // the two selections usually ask for the same evaluation
+            const int off = win == 1 ? roff : 0, len = win == 2 ? n : (win == 0 ? llen : rlen), nw = (len + 31) >> 5;
+            set_window(m, off, len);
+            for (int j = 0; j < nw; j++) m[W_WV + j] = m[W_V + j];
+            for (int t = 1; t < k; t++) shrink_valid(m, nw);
+            T = 0;
+            for (int j = 0; j < nw; j++) T += popc(m[W_WV + j]);
+            ncls = 0;
+            if (T) { prepare_runs(m, nw, k); ncls = classify_runs(m, nw, k, x, false); }
+            cur_win = win; cur_k = k;
+        }
+        if (T == 0) continue;
+        const bool target = win == 2;
+        if (target) {   // k_mer_target (src/kmer.cpp:1894-2017): largest class no homopolymer and at the baseline, classes RC-folded
+            u64 S;
+            const int M = cls_max(m, ncls, x, S);
+            if (homo(S, k) || M < (int)(c == 0 ? thr_high : thr_low)[T]) continue;
+        }
+        for (int q = 0; q < ncls; q++) {
+            u64 key = q < kClsCap ? cls_key(m, q) : x.key[q - kClsCap];
+            const u64 cnt = q < kClsCap ? (u64)m[W_CTOT + q] : (u64)x.tot[q - kClsCap];
+            if (target) { const u64 t = crc(key, k); key = t < key ? t : key; }
+            emit(table, k, key, cnt);
+        }
+    }
+    return true;
+}
+
+}  // namespace et
+}  // namespace trew

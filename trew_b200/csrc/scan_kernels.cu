@@ -15,6 +15,7 @@
 //       of the hi-bit count, lo-bit count (and, second level, A count) of the window, computed for all
 //       window positions at once from prefix-XOR bit-planes: sig_k = (P >> k) ^ P.
 #include "scan_kernels.cuh"
+#include "exact_thread.cuh"
 
 #include <cstdio>
 
@@ -74,21 +75,29 @@ __device__ __noinline__ void table_add_impl(Slot* slots, u32 slot_mask, u32* err
             }
             continue;
         }
-        st = atomicCAS(&s->state, 0u, 1u);
-        if (st == 0u) {
-            s->seq_lo = lo; s->seq_hi = hi; s->meta = meta;
-            __threadfence();
-            atomicExch(&s->state, 2u);
-            atomicAdd(&s->count, cnt);
-            atomicAdd(error_flag + 1, 1u);  // distinct keys so far: the host grows the table before it fills up
-            return;
-        }
-        while (st == 1u) st = *(volatile u32*)&s->state;
-        __threadfence();
-        if (__ldcg(&s->meta) == meta && __ldcg(&s->seq_lo) == lo && __ldcg(&s->seq_hi) == hi) {
-            atomicAdd(&s->count, cnt);
-            return;
-        }
+        // The slot is empty or being written.  Lanes of ONE warp may be here with the same key (the thread-per-survivor
+        // kernel: 32 reads of the same repeat), so nobody spins on the writer: every round all of them try the CAS, the
+        // winner publishes inside the same round, and the others meet a ready slot in the next one.  (A plain spin on
+        // `state == 1` leaves it to the scheduler when the winner's branch runs -- measured: tens of ms.)
+        int outcome = 0;   // 0 look again, 1 added, 2 the slot holds another key
+        do {
+            st = atomicCAS(&s->state, 0u, 1u);
+            if (st == 0u) {
+                s->seq_lo = lo; s->seq_hi = hi; s->meta = meta;
+                __threadfence();
+                atomicExch(&s->state, 2u);
+                atomicAdd(&s->count, cnt);
+                atomicAdd(error_flag + 1, 1u);  // distinct keys so far: the host grows the table before it fills up
+                outcome = 1;
+            } else if (st == 2u) {
+                __threadfence();
+                if (__ldcg(&s->meta) == meta && __ldcg(&s->seq_lo) == lo && __ldcg(&s->seq_hi) == hi) {
+                    atomicAdd(&s->count, cnt);
+                    outcome = 1;
+                } else outcome = 2;
+            }
+        } while (outcome == 0);
+        if (outcome == 1) return;
     }
     atomicExch(error_flag, 3u);  // TREW_ERR_TABLE_FULL
 }
@@ -414,6 +423,7 @@ constexpr int kScreenUnroll = TREW_SCREEN_UNROLL;
 constexpr int kFastMaxWl = 95;
 constexpr int kFastTabSize = kFastMaxWl + 2;
 constexpr int kProbeShift = 28;  // deferred-list entry: unit index | probe mask << 28
+constexpr int kThreadMinWindows = 36;   // decide kernel: survivors whose first passing period has fewer valid windows go to the warp kernel
 
 // per-T entry: x = packed base word, y / z = masks of the window positions in words 0 / 1
 __device__ __forceinline__ uint4 fast_entry(int T, int need) {
@@ -555,6 +565,17 @@ __device__ __forceinline__ void list_append(bool flag, u32 value, u32* __restric
     }
 }
 
+// the same, for a list that grows downwards from *top
+__device__ __forceinline__ void list_append_rev(bool flag, u32 value, u32* __restrict__ top, u32* __restrict__ count) {
+    u32 m = __ballot_sync(0xffffffffu, flag);
+    if (m) {
+        u32 base = 0;
+        if (lane_id() == 0) base = atomicAdd(count, (u32)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (flag) *(top - (base + __popc(m & ((1u << lane_id()) - 1u)))) = value;
+    }
+}
+
 #ifndef TREW_SCREEN_BPS
 #define TREW_SCREEN_BPS 8
 #endif
@@ -591,7 +612,7 @@ __device__ __forceinline__ int max4(int a, int b, int c, int d) { return max(max
 
 template <int S>
 __device__ __forceinline__ bool decide_span(const u32 (&ph)[5], const u32 (&pl)[5], const u32 (&pa)[5], u32 (&wv)[3], int ka, int kb,
-                                            const unsigned short* __restrict__ thr, bool& done) {
+                                            const unsigned short* __restrict__ thr, bool& done, int& t_hit) {
     for (int k = ka; k <= kb; k++) {
         const int T01 = __popc(wv[0]) + __popc(wv[1]), E = __popc(wv[2]), T = T01 + E;
         if (T == 0) { done = true; return false; }  // the valid-window mask only shrinks with k
@@ -611,7 +632,7 @@ __device__ __forceinline__ bool decide_span(const u32 (&ph)[5], const u32 (&pl)[
                 int n01 = __popc(b0 & ~a0 & x0) + __popc(b1 & ~a1 & x1) + __popc(b2 & ~a2 & x2);
                 int n00 = __popc(wv[0] & ~a0 & ~b0 & x0) + __popc(wv[1] & ~a1 & ~b1 & x1) + __popc(wv[2] & ~a2 & ~b2 & x2);
                 int U2 = max(max4(n11, c11 - n11, n10, c10 - n10), max4(n01, c01 - n01, n00, c00 - n00));
-                if (U2 >= need) return true;
+                if (U2 >= need) { t_hit = T; return true; }
             }
         }
         u32 t0 = __funnelshift_r(wv[0], wv[1], 1), t1 = __funnelshift_r(wv[1], wv[2], 1), t2 = wv[2] >> 1;
@@ -620,7 +641,9 @@ __device__ __forceinline__ bool decide_span(const u32 (&ph)[5], const u32 (&pl)[
     return false;
 }
 
-__device__ __noinline__ bool decide_short(const DevBatch& b, u32 pos, int wl, int k0, int k1, const unsigned short* __restrict__ thr) {
+// t_hit: the number of valid windows at the first period that passes (tells a repeat -- most of the window -- from a
+// window an N left a dozen k-windows of)
+__device__ __noinline__ bool decide_short(const DevBatch& b, u32 pos, int wl, int k0, int k1, const unsigned short* __restrict__ thr, int& t_hit) {
     u32 wv[3], ph[5], pl[5], pa[5];
     load_bits<3>(b.val, pos, wv); mask_bits<3>(wv, wl);
     {
@@ -637,18 +660,19 @@ __device__ __noinline__ bool decide_short(const DevBatch& b, u32 pos, int wl, in
     sliding_and<3>(wv, k0);
     bool done = false;
     if (k0 < 32) {
-        if (decide_span<0>(ph, pl, pa, wv, k0, min(k1, 31), thr, done)) return true;
+        if (decide_span<0>(ph, pl, pa, wv, k0, min(k1, 31), thr, done, t_hit)) return true;
         if (done) return false;
         k0 = 32;
     }
-    return k1 >= 32 && decide_span<1>(ph, pl, pa, wv, k0, k1, thr, done);
+    return k1 >= 32 && decide_span<1>(ph, pl, pa, wv, k0, k1, thr, done, t_hit);
 }
 
 // ---- decide kernel: exact 4-bucket bound + A-parity second level for every (probe, k) of the deferred units ----
 template <int MAXNW>
 __global__ void __launch_bounds__(256) trew_filter_kernel(DevCfg cfg, DevBatch b, const u32* __restrict__ units,
                                                           const u32* __restrict__ n_units_ptr, u32 n_units_all,
-                                                          u32* __restrict__ survivors, u32* __restrict__ n_survivors) {
+                                                          u32* __restrict__ survivors, u32* __restrict__ n_survivors,
+                                                          u32* __restrict__ surv_b_top, u32* __restrict__ n_surv_b) {
     __shared__ unsigned short thr[kThrTableSize];
     for (int i = threadIdx.x; i < kThrTableSize; i += blockDim.x) thr[i] = cfg.thr_low[i];
     __syncthreads();
@@ -659,6 +683,7 @@ __global__ void __launch_bounds__(256) trew_filter_kernel(DevCfg cfg, DevBatch b
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
         bool maybe = false;
         u32 u = 0, live = 0;
+        int t_hit = 1 << 20;
         if (i < n_units) {
             u32 pm = 0xfu;
             u = i;
@@ -668,18 +693,36 @@ __global__ void __launch_bounds__(256) trew_filter_kernel(DevCfg cfg, DevBatch b
             live = pm & ((1u << np) - 1u);   // probes that may still find a target period
             for (int j = 0; j < np && !maybe; j++) {
                 if (((pm >> j) & 1u) && p[j].k1 >= p[j].k0)
-                    maybe = probe_is_fast(p[j]) ? decide_short(b, p[j].pos, p[j].wl, p[j].k0, p[j].k1, thr) : probe_dispatch<MAXNW>(b, p[j], thr);
+                    maybe = probe_is_fast(p[j]) ? decide_short(b, p[j].pos, p[j].wl, p[j].k0, p[j].k1, thr, t_hit) : probe_dispatch<MAXNW>(b, p[j], thr);
                 if (!maybe) live &= ~(1u << j);
             }
         }
         // the exact kernel skips the scan of a window no probe vouches for (its result is "no target period")
-        list_append(maybe, pack_probes ? u | (live << kProbeShift) : u, survivors, n_survivors);
+        const u32 entry = pack_probes ? u | (live << kProbeShift) : u;
+        if (surv_b_top == nullptr) {
+            list_append(maybe, entry, survivors, n_survivors);
+        } else {
+            // Two lists for the two exact kernels (short single-end mode).  Up from the bottom of the survivor array: reads
+            // the thread-per-survivor kernel takes -- at most 160 bases, and the period that made them survivors still
+            // has most of its windows (a repeat).  Down from the top: the others, above all reads an N made survivors of
+            // (a period the N leaves a dozen windows of passes the bound easily; turning those away means comparing
+            // many one-window runs -- long, lane-divergent loops in the thread kernel, a few warp-wide instructions in the
+            // warp kernel's comp_bound).  Both kernels are exact for every read; the split only places the work.
+            bool to_b = false;
+            if (maybe) {
+                const int len = (int)(__ldg(b.bit_off + u + 1) - __ldg(b.bit_off + u));
+                to_b = len > et::kMaxRead || t_hit < kThreadMinWindows;
+            }
+            list_append(maybe && !to_b, entry, survivors, n_survivors);
+            list_append_rev(maybe && to_b, entry, surv_b_top, n_surv_b);
+        }
     }
 }
 
 void launch_filter(const DevCfg& cfg, const DevBatch& b, unsigned int n_units, unsigned int max_read_len,
                    unsigned int* deferred, unsigned int* n_deferred, unsigned int* survivors, unsigned int* n_survivors,
-                   const LaunchPlan& plan, cudaStream_t stream, cudaEvent_t after_screen) {
+                   const LaunchPlan& plan, cudaStream_t stream, cudaEvent_t after_screen, unsigned int* surv_b_top,
+                   unsigned int* n_surv_b) {
     if (n_units == 0) return;
     // longest probe window: a half read, a whole read (n < 4*MAX) or a slice (long mode)
     unsigned int longest;
@@ -698,9 +741,9 @@ void launch_filter(const DevCfg& cfg, const DevBatch& b, unsigned int n_units, u
     const unsigned int* list = screen ? deferred : nullptr;
     int blocks = plan.decide_blocks;
     if ((unsigned)blocks > need) blocks = (int)need;
-    if (longest + 1 <= 96) trew_filter_kernel<3><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors);
-    else if (longest + 1 <= 160) trew_filter_kernel<5><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors);
-    else trew_filter_kernel<8><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors);
+    if (longest + 1 <= 96) trew_filter_kernel<3><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors, surv_b_top, n_surv_b);
+    else if (longest + 1 <= 160) trew_filter_kernel<5><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors, surv_b_top, n_surv_b);
+    else trew_filter_kernel<8><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors, surv_b_top, n_surv_b);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -724,8 +767,14 @@ constexpr int kPlaneWords = 36;  // 32 window words + zero padding for shifted r
 #endif
 constexpr int kExactWarps = TREW_EXACT_WARPS;
 constexpr u32 kEmptySlot = 0xffffffffu;
+constexpr int kSerialMaxRuns = 12;   // eval_k: windows with at most this many match-bit runs take the collective-free path
 
-enum { HD_CUR_POS = 0, HD_CUR_LEN, HD_ALLVALID, HD_EV_POS, HD_EV_LEN, HD_EV_K, HD_EV_PACK, HD_S = 8 /* 4 words: s_lo, s_hi */ };
+// header words.  12..27: the state of one scan_stats() call -- warp-uniform, so it lives here once instead of in
+// every lane's registers (which the calls into eval_k would spill to local memory)
+enum { HD_CUR_POS = 0, HD_CUR_LEN, HD_ALLVALID, HD_EV_POS, HD_EV_LEN, HD_EV_K, HD_EV_PACK, HD_S = 8 /* 4 words: s_lo, s_hi */,
+       HD_BLK_L = 12 /* 2 words */, HD_BLK_H = 14 /* 2 words */, HD_NEED_L = 16, HD_NEED_H = 17, HD_BLK64 = 18, HD_RES = 19,
+       HD_SH = 20 /* 4 words */, HD_SL = 24 /* 4 words */ };
+constexpr int kHeaderBytes = 128;
 
 __host__ __device__ inline int exact_hash_slots(int cap) {
     int hs = 64;
@@ -734,7 +783,7 @@ __host__ __device__ inline int exact_hash_slots(int cap) {
 }
 
 __host__ __device__ inline size_t exact_warp_bytes(int cap) {
-    size_t b = 64 + 5 * kPlaneWords * sizeof(u32) + kPlaneWords * sizeof(u64);
+    size_t b = kHeaderBytes + 5 * kPlaneWords * sizeof(u32) + kPlaneWords * sizeof(u64);
     b += (size_t)2 * cap * sizeof(u64) + (size_t)exact_hash_slots(cap) * sizeof(u32) + (size_t)2 * cap * sizeof(u32);
     b += (size_t)(3 * cap + 4) * sizeof(unsigned short);
     return (b + 15) & ~(size_t)15;
@@ -745,7 +794,7 @@ size_t exact_smem_bytes(int run_cap, bool) { return exact_warp_bytes(run_cap) * 
 struct WS {  // this warp's region
     u32 off; int cap; int hs; u32 lane; u32 flags;
     __device__ __forceinline__ u32* hdr() const { return (u32*)(g_smem + off); }
-    __device__ __forceinline__ u32* H() const { return (u32*)(g_smem + off + 64); }
+    __device__ __forceinline__ u32* H() const { return (u32*)(g_smem + off + kHeaderBytes); }
     __device__ __forceinline__ u32* L() const { return H() + kPlaneWords; }
     __device__ __forceinline__ u32* V() const { return H() + 2 * kPlaneWords; }
     __device__ __forceinline__ u32* PH() const { return H() + 3 * kPlaneWords; }
@@ -829,41 +878,6 @@ __device__ __forceinline__ bool homo_pair(u64 lo, u64 hi, int k) {  // get_repea
     u128 w = ((u128)hi << 64) | lo;
     u128 m = (((u128)1 << (2 * (k - 1))) - 1);
     return ((w ^ (w >> 2)) & m) == 0;
-}
-
-// ---- warp-cooperative minimal rotation: every lane passes the same k-mer, lane l tries rotation l (and l + 32 when
-// k > 32), and the minimum is found with two (four) 32-bit warp reductions.  Worth it when a window has few runs and k
-// is large: the serial loop of canon64 is k - 1 dependent steps on one lane while 31 lanes idle.
-__device__ __forceinline__ u64 canon64_coop(u64 w, int k, u32 lane) {
-    const u64 mask = k >= 32 ? ~0ULL : ((1ULL << (2 * k)) - 1ULL);
-    const int r = 2 * (int)lane;
-    u64 rot = ~0ULL;
-    if ((int)lane < k) rot = lane == 0 ? w : (((w >> r) | (w << (2 * k - r))) & mask);
-    const u32 mh = __reduce_min_sync(0xffffffffu, (u32)(rot >> 32));
-    const u32 ml = __reduce_min_sync(0xffffffffu, (u32)(rot >> 32) == mh ? (u32)rot : 0xffffffffu);
-    return ((u64)mh << 32) | ml;
-}
-
-__device__ __forceinline__ u128 canon128_coop(u128 w, int k, u32 lane) {
-    const u128 mask = k >= 64 ? ~(u128)0 : ((((u128)1) << (2 * k)) - 1);
-    u128 best = ~(u128)0;
-#pragma unroll
-    for (int half = 0; half < 2; half++) {
-        const int l = (int)lane + 32 * half;
-        if (l < k) {
-            const u128 rot = l == 0 ? w : (((w >> (2 * l)) | (w << (2 * (k - l)))) & mask);
-            best = rot < best ? rot : best;
-        }
-    }
-    u32 part[4] = {(u32)(best >> 96), (u32)(best >> 64), (u32)(best >> 32), (u32)best};
-    u32 m[4];
-    bool tied = true;   // this lane still equals the minimum on all higher words
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        m[j] = __reduce_min_sync(0xffffffffu, tied ? part[j] : 0xffffffffu);
-        tied = tied && part[j] == m[j];
-    }
-    return ((u128)m[0] << 96) | ((u128)m[1] << 64) | ((u128)m[2] << 32) | (u128)m[3];
 }
 
 __device__ __forceinline__ bool less_pair(u64 alo, u64 ahi, u64 blo, u64 bhi) {
@@ -1039,8 +1053,6 @@ __device__ __noinline__ int comp_bound(WS ws, int k, u32 wv, int T) {
 __device__ __noinline__ u32 eval_k(WS ws, int len, int k, u32 wv) {
     const u32 lane = ws.lane;
     u32* hd = ws.hdr();
-    int T = (int)__reduce_add_sync(0xffffffffu, (u32)__popc(wv));
-    if (T == 0) return 0u;
     const u32 *H = ws.H(), *L = ws.L();
     // link bits: windows i and i+1 are both valid and base[i] == base[i+k]   (Lemma L1)
     int s = k >> 5, r = k & 31;
@@ -1051,8 +1063,68 @@ __device__ __noinline__ u32 eval_k(WS ws, int len, int k, u32 wv) {
     u32 link = eq & wv & ((wv >> 1) | (nb << 31));
     u32 link_prev = __shfl_up_sync(0xffffffffu, link, 1);
     u32 rs = wv & ~((link << 1) | (lane ? link_prev >> 31 : 0u));  // run starts
-    // exclusive scans over lanes of (valid windows, run starts), packed 16:16
     u32 pk = (u32)__popc(wv) | ((u32)__popc(rs) << 16);
+    const u32 tot_pk = __reduce_add_sync(0xffffffffu, pk);
+    const int T = (int)(tot_pk & 0xffffu), R = (int)(tot_pk >> 16);
+    if (T == 0) return 0u;
+    unsigned short *run_start = ws.run_start(), *run_cw = ws.run_cw(), *run_total = ws.run_total();
+    u64 *run_lo = ws.run_lo(), *run_hi = ws.run_hi();
+    u32 *htab = ws.htab(), *grp_tot = ws.grp_tot(), *grp_last = ws.grp_last();
+    const u64* rev2 = ws.rev2();
+    const bool wide = k > 32;
+    if (!wide && R <= kSerialMaxRuns && !(ws.flags & 1u)) {
+        // Few runs (every repeat read: a perfect repeat is one run, each substitution adds at most two).  The warp
+        // collectives of the general path below (prefix scans, shared-memory atomics, reductions) cost more latency
+        // than the work they spread, so here every lane walks the runs redundantly in plain ALU / shared-memory
+        // instructions: the three mask words per lane go to shared memory once, then run by run -- end of the run,
+        // minimal rotation of its first k-mer, linear search in the class list.  Classes land in run_lo / run_total
+        // (entries 0 .. classes-1), which is what emit_classes() reads.
+        u32* scr = htab;                       // [wv | link | run starts], 32 words each (htab + grp_tot + grp_last: >= 96 words)
+        scr[lane] = wv; scr[32 + lane] = link; scr[64 + lane] = rs;
+        __syncwarp();
+        unsigned short* cls_last = run_cw;     // ordinal of the class's last window
+        int ncls = 0, ord = 0;
+        const int nw = (len + 31) >> 5;
+        for (int j = 0; j < nw; j++) {
+            const u32 wvj = scr[j];
+            u32 rr = scr[64 + j];
+            while (rr) {
+                const int b = __ffs(rr) - 1;
+                rr &= rr - 1;
+                const int c0 = ord + __popc(wvj & ((1u << b) - 1u));
+                // the run ends at the first window without a link to its successor
+                int jj = j;
+                u32 x = ~scr[32 + j] & (0xffffffffu << b);
+                while (!x) { jj++; x = ~scr[32 + jj]; }     // lanes past the window hold wv = 0, hence link = 0: terminates
+                const int cnt = 32 * (jj - j) + (__ffs(x) - 1) - b + 1;
+                u64 lo, hi;
+                kmer_at(rev2, len, 32 * j + b, k, lo, hi);
+                lo = canon64(lo, k);
+                int q = 0;
+                while (q < ncls && run_lo[q] != lo) q++;
+                u32 tot = (u32)cnt;
+                if (q == ncls) { ncls++; run_lo[q] = lo; }
+                else tot += run_total[q];
+                run_total[q] = (unsigned short)tot;
+                cls_last[q] = (unsigned short)(c0 + cnt - 1);
+            }
+            ord += __popc(wvj);
+        }
+        // K_MER_DATA_MAX_SEQ: the class whose running count first reaches the final maximum
+        // (strict '<' at src/kmer.cpp:2202) = max total, ties broken by the EARLIEST last window
+        u32 best = 0; int bq = 0;
+        for (int q = 0; q < ncls; q++) {
+            const u32 score = ((u32)run_total[q] << 10) | (1023u - cls_last[q]);
+            if (score > best) { best = score; bq = q; }
+        }
+        const u64 s_lo = run_lo[bq];
+        const bool homo = homo_pair(s_lo, 0ULL, k);
+        __syncwarp();
+        if (lane == 0) { hd[HD_S] = (u32)s_lo; hd[HD_S + 1] = (u32)(s_lo >> 32); hd[HD_S + 2] = 0u; hd[HD_S + 3] = 0u; }
+        __syncwarp();
+        return (u32)T | ((best >> 10) << 10) | ((u32)ncls << 20) | (homo ? 1u << 30 : 0u);
+    }
+    // exclusive scans over lanes of (valid windows, run starts), packed 16:16
     u32 inc = pk;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -1060,10 +1132,6 @@ __device__ __noinline__ u32 eval_k(WS ws, int len, int k, u32 wv) {
         if ((int)lane >= d) inc += t;
     }
     u32 exc = inc - pk;
-    const int R = (int)(__shfl_sync(0xffffffffu, inc, 31) >> 16);
-    unsigned short *run_start = ws.run_start(), *run_cw = ws.run_cw(), *run_total = ws.run_total();
-    u64 *run_lo = ws.run_lo(), *run_hi = ws.run_hi();
-    u32 *htab = ws.htab(), *grp_tot = ws.grp_tot(), *grp_last = ws.grp_last();
     {
         u32 cwb = exc & 0xffffu, rb = exc >> 16;
         u32 x = rs;
@@ -1075,62 +1143,6 @@ __device__ __noinline__ u32 eval_k(WS ws, int len, int k, u32 wv) {
             rb++;
         }
         if (lane == 0) run_cw[R] = (unsigned short)T;
-    }
-    const u64* rev2 = ws.rev2();
-    const bool wide = k > 32;
-    if (R <= 32 && !(ws.flags & 1u)) {
-        // Few runs (every repeat read: a perfect repeat is one run, each substitution adds at most two): one run per
-        // lane, classes grouped in registers with MATCH instead of the shared-memory hash table.
-        __syncwarp();
-        const bool act = (int)lane < R;
-        u64 lo = ~0ULL, hi = ~0ULL;
-        u32 c0 = 0, c1 = 0;
-        if (act) { kmer_at(rev2, len, run_start[lane], k, lo, hi); c0 = run_cw[lane]; c1 = run_cw[lane + 1]; }
-        // minimal rotation: k - 1 dependent steps on the run's own lane, or one warp-wide step per run
-        const int serial_cost = (k - 1) * (k <= 16 ? 3 : (wide ? 14 : 6));
-        const int coop_cost = R * (wide ? 48 : 16);
-        if (coop_cost < serial_cost) {
-            for (int r = 0; r < R; r++) {
-                const u64 wl = __shfl_sync(0xffffffffu, lo, r);
-                if (!wide) {
-                    const u64 c = canon64_coop(wl, k, lane);
-                    if ((int)lane == r) lo = c;
-                } else {
-                    const u64 wh = __shfl_sync(0xffffffffu, hi, r);
-                    const u128 c = canon128_coop(((u128)wh << 64) | wl, k, lane);
-                    if ((int)lane == r) { lo = (u64)c; hi = (u64)(c >> 64); }
-                }
-            }
-        } else if (act) {
-            canon_pair(lo, hi, k);
-        }
-        const u32 actm = __ballot_sync(0xffffffffu, act);
-        u32 grp = __match_any_sync(0xffffffffu, lo);
-        if (wide) grp &= __match_any_sync(0xffffffffu, hi);
-        grp &= actm;
-        u32 score = 0, total = 0;
-        bool leader = false;
-        if (act) {
-            // the class's window total and the ordinal of its last window, over the lanes holding its runs
-            total = __reduce_add_sync(grp, c1 - c0);
-            const u32 last = __reduce_max_sync(grp, c1 - 1u);
-            leader = (u32)(__ffs(grp) - 1) == lane;
-            // K_MER_DATA_MAX_SEQ: the class whose running count first reaches the final maximum
-            // (strict '<' at src/kmer.cpp:2202) = max total, ties broken by the EARLIEST last window
-            if (leader) score = (total << 10) | (1023u - last);
-            run_lo[lane] = lo; if (wide) run_hi[lane] = hi;
-            run_total[lane] = (unsigned short)(leader ? total : 0u);
-        }
-        const u32 wbest = __reduce_max_sync(0xffffffffu, score);
-        const u32 who = __ballot_sync(0xffffffffu, leader && score == wbest);
-        const int bq = __ffs(who) - 1;
-        const u64 s_lo = __shfl_sync(0xffffffffu, lo, bq), s_hi = wide ? __shfl_sync(0xffffffffu, hi, bq) : 0ULL;
-        const bool homo = homo_pair(s_lo, s_hi, k);
-        if (lane == 0) {
-            hd[HD_S] = (u32)s_lo; hd[HD_S + 1] = (u32)(s_lo >> 32); hd[HD_S + 2] = (u32)s_hi; hd[HD_S + 3] = (u32)(s_hi >> 32);
-        }
-        __syncwarp();
-        return (u32)T | ((wbest >> 10) << 10) | ((u32)R << 20) | (homo ? 1u << 30 : 0u);
     }
     // hash table sized to the run count (power of two >= 1.5 R, so hsz > R; at most hs >= 1.25 cap)
     int hsz = 32;
@@ -1233,59 +1245,81 @@ __constant__ MultTab c_mult = make_mult_tab();
 // the K_MER_DATA_MAX_SEQ of each.  Periods that cannot be accepted by either selection (divisor rule,
 // or the signature bound below the running threshold) are skipped without an exact count.
 //
-// Pre-test soundness: the reference accepts k iff fl(M/T) >= need.  fl(M/T) >= need implies
-// M >= need*T*(1 - 2^-53), and U >= M, so "U >= need*T*(1 - 1e-12)" (evaluated in double, relative error
-// ~2^-52) never rejects a period the reference would accept.  The exact test after eval_k uses the same
-// IEEE division as the reference.
-__device__ __noinline__ ScanRes scan_stats(WS ws, DevBatch b, u32 pos, int len, int kmin, int kmax, double low, double high) {
-    ScanRes res;
-    res.th = res.tl = 0; res.sh_lo = res.sh_hi = res.sl_lo = res.sl_hi = 0;
-    if (kmax < kmin) return res;
+// No floating point on the device: the reference accepts k iff fl(M/T) >= max(B, f_prev) in doubles
+// (src/kmer.cpp:2223-2224, 2243-2244).  "fl(M/T) >= B" is "M >= thr_B[T]", thr_B built on the host with the same IEEE
+// division (device_ctx.cu:build_thr); "fl(M/T) >= fl(M'/T')" between two ratios with denominators <= 1023 is
+// "M * T' >= M' * T" exactly (distinct such ratios differ by > 1e-6, far more than an ulp, and rounding is monotone).
+// The pre-test replaces M by its upper bound U in the same two comparisons, so it never rejects a period the
+// reference would accept.
+// max(baseline, last accepted frequency) of one selection: need = m | t << 16 of the last accepted ratio (0: none yet)
+__device__ __forceinline__ bool need_pass(const unsigned short* thr, u32 need, int M, int T) {
+    const u32 m = need & 0xffffu, t = need >> 16;
+    return M >= (int)__ldg(thr + T) && (t == 0u || (u32)M * t >= m * (u32)T);
+}
+
+__device__ __forceinline__ bool blocked_k(const u32* hd, int which /* HD_BLK_L or HD_BLK_H */, int k) {
+    if (k >= 64) return (hd[HD_BLK64] >> (which == HD_BLK_H ? 1 : 0)) & 1u;
+    return (hd[which + (k >> 5)] >> (k & 31)) & 1u;
+}
+
+// one exact evaluation + the two acceptance tests of src/kmer.cpp:2221-2258 for period kk; the selection state is in the
+// header.  Returns true when the period was accepted (the thresholds / divisor masks changed).
+__device__ __noinline__ bool try_k(WS ws, const unsigned short* thr_low, u32 pos, int len, int kk, int Uk, int Tk, u32 wv) {
+    u32* hd = ws.hdr();
+    const unsigned short* thr_high = thr_low + kThrTableSize;
+    const bool blkL = blocked_k(hd, HD_BLK_L, kk), blkH = blocked_k(hd, HD_BLK_H, kk);
+    if (blkL && blkH) return false;
+    const u32 needL = hd[HD_NEED_L], needH = hd[HD_NEED_H];
+    bool candL = !blkL && need_pass(thr_low, needL, Uk, Tk), candH = !blkH && need_pass(thr_high, needH, Uk, Tk);
+    if (!candL && !candH) return false;
+#ifndef TREW_NO_COMP_BOUND
+    if (Tk <= 32 && !(ws.flags & 2u)) {   // few windows: the exact-composition bound is cheap and far tighter than the parity signature
+        const int Mc = comp_bound(ws, kk, wv, Tk);
+        if (Mc < Uk) {
+            candL = !blkL && need_pass(thr_low, needL, Mc, Tk); candH = !blkH && need_pass(thr_high, needH, Mc, Tk);
+            if (!candL && !candH) return false;
+        }
+    }
+#endif
+    const u32 ev = eval_k(ws, len, kk, wv);
+    if (ws.lane == 0) { hd[HD_EV_POS] = pos; hd[HD_EV_LEN] = (u32)len; hd[HD_EV_K] = (u32)kk; hd[HD_EV_PACK] = ev; }
+    __syncwarp();
+    if (pk_homo(ev) || pk_T(ev) == 0) return false;
+    const int M = pk_M(ev), T = pk_T(ev);
+    const bool accL = !blkL && need_pass(thr_low, needL, M, T), accH = !blkH && need_pass(thr_high, needH, M, T);
+    if (!(accL || accH)) return false;
+    if (ws.lane == 0) {
+        const u64 mm = c_mult.m[kk];   // multiples of kk below 64
+        const u32 m64 = (64 % kk) == 0 ? 1u : 0u;
+        const u32 need = (u32)M | ((u32)T << 16);
+        u32 res = hd[HD_RES];
+        if (accL) {
+            hd[HD_NEED_L] = need; hd[HD_BLK_L] |= (u32)mm; hd[HD_BLK_L + 1] |= (u32)(mm >> 32); hd[HD_BLK64] |= m64;
+            res = (res & 0xffu) | ((u32)kk << 8);
+            hd[HD_SL] = hd[HD_S]; hd[HD_SL + 1] = hd[HD_S + 1]; hd[HD_SL + 2] = hd[HD_S + 2]; hd[HD_SL + 3] = hd[HD_S + 3];
+        }
+        if (accH) {
+            hd[HD_NEED_H] = need; hd[HD_BLK_H] |= (u32)mm; hd[HD_BLK_H + 1] |= (u32)(mm >> 32); hd[HD_BLK64] |= m64 << 1;
+            res = (res & 0xff00u) | (u32)kk;
+            hd[HD_SH] = hd[HD_S]; hd[HD_SH + 1] = hd[HD_S + 1]; hd[HD_SH + 2] = hd[HD_S + 2]; hd[HD_SH + 3] = hd[HD_S + 3];
+        }
+        hd[HD_RES] = res;
+    }
+    __syncwarp();
+    return true;
+}
+
+// k_mer_check without emission for window [pos, pos + len), periods kmin..kmax: returns target_k_high | target_k_low << 8;
+// the K_MER_DATA_MAX_SEQ of the two are left in the header (HD_SH, HD_SL).
+__device__ __noinline__ u32 scan_core(WS ws, DevBatch b, u32 pos, int len, int kmin, int kmax, const unsigned short* thr_low) {
+    if (kmax < kmin) return 0u;
     load_window(ws, b.hi, b.lo, b.val, pos, len);
-    u64 blockedL = 0, blockedH = 0;   // periods with an accepted divisor (k % tk == 0, src/kmer.cpp:2225-2230)
-    bool blk64L = false, blk64H = false;
-    double needL = low, needH = high; // max(baseline, last accepted frequency)
-    const double slack = 1.0 - 1e-12;
     const u32 lane = ws.lane;
     u32* hd = ws.hdr();
+    if (lane >= HD_BLK_L && lane <= HD_SL + 3) hd[lane] = 0u;   // fresh selection state
+    __syncwarp();
     const bool all_valid = hd[HD_ALLVALID] != 0;
-
-    // one exact evaluation + the two acceptance tests of src/kmer.cpp:2221-2258
-    // returns true when a period was accepted (the thresholds / divisor masks changed)
-    auto try_k = [&](int kk, int Uk, int Tk, u32 wv) -> bool {
-        bool blkL = kk < 64 ? ((blockedL >> kk) & 1ULL) != 0 : blk64L;
-        bool blkH = kk < 64 ? ((blockedH >> kk) & 1ULL) != 0 : blk64H;
-        if (blkL && blkH) return false;
-        double dU = (double)Uk, dT = (double)Tk;
-        bool candL = !blkL && dU >= needL * dT * slack, candH = !blkH && dU >= needH * dT * slack;
-        if (!candL && !candH) return false;
-#ifndef TREW_NO_COMP_BOUND
-        if (Tk <= 32 && !(ws.flags & 2u)) {   // few windows: the exact-composition bound is cheap and far tighter than the parity signature
-            const int Mc = comp_bound(ws, kk, wv, Tk);
-            if (Mc < Uk) {
-                dU = (double)Mc;
-                candL = !blkL && dU >= needL * dT * slack; candH = !blkH && dU >= needH * dT * slack;
-                if (!candL && !candH) return false;
-            }
-        }
-#endif
-        u32 ev = eval_k(ws, len, kk, wv);
-        if (lane == 0) { hd[HD_EV_POS] = pos; hd[HD_EV_LEN] = (u32)len; hd[HD_EV_K] = (u32)kk; hd[HD_EV_PACK] = ev; }
-        __syncwarp();
-        if (pk_homo(ev) || pk_T(ev) == 0) return false;
-        double f = (double)pk_M(ev) / (double)pk_T(ev);
-        bool accL = !blkL && f >= needL, accH = !blkH && f >= needH;
-        if (accL || accH) {
-            u64 mm = c_mult.m[kk];
-            bool m64 = (64 % kk) == 0;
-            u64 slo, shi;
-            eval_S(ws, slo, shi);
-            if (accL) { res.tl = kk; needL = f; blockedL |= mm; blk64L |= m64; res.sl_lo = slo; res.sl_hi = shi; }
-            if (accH) { res.th = kk; needH = f; blockedH |= mm; blk64H |= m64; res.sh_lo = slo; res.sh_hi = shi; }
-            return true;
-        }
-        return false;
-    };
+    const unsigned short* thr_high = thr_low + kThrTableSize;
 
     if (len <= 127 || all_valid) {
         // Every lane bounds its own period (lane <-> k); the qualifying periods are then visited in ascending order.
@@ -1322,7 +1356,7 @@ __device__ __noinline__ ScanRes scan_stats(WS ws, DevBatch b, u32 pos, int len, 
                 int c10 = cH - c11, c01 = cL - c11, c00 = T - cH - cL + c11;
                 U = max(max(c00, c01), max(c10, c11));
             }
-            bool cand = T > 0 && (double)U >= low * (double)T * slack;
+            bool cand = T > 0 && U >= (int)__ldg(thr_low + T);
             u32 cm = __ballot_sync(0xffffffffu, cand);
             while (cm) {
                 int bit = __ffs(cm) - 1;
@@ -1337,17 +1371,18 @@ __device__ __noinline__ ScanRes scan_stats(WS ws, DevBatch b, u32 pos, int len, 
                     u32 a2 = __shfl_sync(0xffffffffu, wvv[2], bit), a3 = __shfl_sync(0xffffffffu, wvv[3], bit);
                     wv = lane == 0 ? a0 : lane == 1 ? a1 : lane == 2 ? a2 : lane == 3 ? a3 : 0u;
                 }
-                if (try_k(kb + bit, Uk, Tk, wv) && cm) {
+                if (try_k(ws, thr_low, pos, len, kb + bit, Uk, Tk, wv) && cm) {
                     // an acceptance raised the thresholds / blocked multiples: drop the remaining periods of
                     // this block that can no longer be accepted by either selection (lane <-> period again)
-                    bool bl = k < 64 ? ((blockedL >> k) & 1ULL) != 0 : blk64L, bh = k < 64 ? ((blockedH >> k) & 1ULL) != 0 : blk64H;
-                    double dU = (double)U, dT = (double)T;
-                    bool still = (!bl && dU >= needL * dT * slack) || (!bh && dU >= needH * dT * slack);
+                    bool still = false;
+                    if (T > 0 && k <= 64)
+                        still = (!blocked_k(hd, HD_BLK_L, k) && need_pass(thr_low, hd[HD_NEED_L], U, T)) ||
+                                (!blocked_k(hd, HD_BLK_H, k) && need_pass(thr_high, hd[HD_NEED_H], U, T));
                     cm &= __ballot_sync(0xffffffffu, still);
                 }
             }
         }
-        return res;
+        return hd[HD_RES];
     }
 
     // long windows with invalid bases: walk the periods in order, keeping the window-valid mask incrementally
@@ -1356,8 +1391,21 @@ __device__ __noinline__ ScanRes scan_stats(WS ws, DevBatch b, u32 pos, int len, 
         int T = (int)__reduce_add_sync(0xffffffffu, (u32)__popc(wv));
         if (T == 0) break;
         int U = bound_k(ws, k, wv, T);
-        try_k(k, U, T, wv);
+        try_k(ws, thr_low, pos, len, k, U, T, wv);
     }
+    return hd[HD_RES];
+}
+
+// the result of scan_core with the two K_MER_DATA_MAX_SEQ read back from the header (callers that do not look at them --
+// short and long routing -- never load them)
+__device__ __forceinline__ ScanRes scan_stats(WS ws, const DevBatch& b, u32 pos, int len, int kmin, int kmax, const unsigned short* thr_low,
+                                              const unsigned short*) {
+    const u32 r = scan_core(ws, b, pos, len, kmin, kmax, thr_low);
+    const u32* hd = ws.hdr();
+    ScanRes res;
+    res.th = (int)(r & 0xffu); res.tl = (int)(r >> 8);
+    res.sh_lo = (u64)hd[HD_SH] | ((u64)hd[HD_SH + 1] << 32); res.sh_hi = (u64)hd[HD_SH + 2] | ((u64)hd[HD_SH + 3] << 32);
+    res.sl_lo = (u64)hd[HD_SL] | ((u64)hd[HD_SL + 1] << 32); res.sl_hi = (u64)hd[HD_SL + 2] | ((u64)hd[HD_SL + 3] << 32);
     return res;
 }
 
@@ -1380,9 +1428,9 @@ __device__ void emit_window(TableRef tr, WS ws, const DevBatch& b, u32 pos, int 
 }
 
 // k_mer_target / k_mer_target_128 (src/kmer.cpp:1894-2142)
-__device__ void target_window(TableRef tr, WS ws, const DevBatch& b, u32 pos, int len, int k, double B, int table) {
+__device__ void target_window(TableRef tr, WS ws, const DevBatch& b, u32 pos, int len, int k, const unsigned short* thr, int table) {
     u32 ev = eval_cached(ws, b, pos, len, k);
-    if (pk_T(ev) > 0 && !pk_homo(ev) && (double)pk_M(ev) / (double)pk_T(ev) >= B) emit_classes(tr, ws, k, pk_runs(ev), table, true);
+    if (pk_T(ev) > 0 && !pk_homo(ev) && pk_M(ev) >= (int)__ldg(thr + pk_T(ev))) emit_classes(tr, ws, k, pk_runs(ev), table, true);
 }
 
 // ---- routing -----------------------------------------------------------------------------------
@@ -1401,21 +1449,21 @@ __device__ void route_short(const DevCfg& cfg, TableRef tr, WS ws, const DevBatc
         int kmax = min(n / 4, MAXM);
         u32 lpos = b0, rpos = b0 + (u32)(n - (n + 1) / 2);
         int llen = n / 2, rlen = (n + 1) / 2;
-        if (pm & 1u) { ScanRes l = scan_stats(ws, b, lpos, llen, MINM, kmax, cfg.low, cfg.high); L[0] = l.th; L[1] = l.tl; }
-        if (pm & 2u) { ScanRes r = scan_stats(ws, b, rpos, rlen, MINM, kmax, cfg.low, cfg.high); R[0] = r.th; R[1] = r.tl; }  // "always evaluated"
+        if (pm & 1u) { ScanRes l = scan_stats(ws, b, lpos, llen, MINM, kmax, cfg.thr_low, cfg.thr_high); L[0] = l.th; L[1] = l.tl; }
+        if (pm & 2u) { ScanRes r = scan_stats(ws, b, rpos, rlen, MINM, kmax, cfg.thr_low, cfg.thr_high); R[0] = r.th; R[1] = r.tl; }  // "always evaluated"
         pm >>= 2;
         // right-half emissions survive only for classes where the left half found nothing
         // (nullptr maps at src/kmer.cpp:125, result.backward at :158)
 #pragma unroll
         for (int c = 0; c < 2; c++) {
-            if (L[c] > 0 && L[c] == R[c]) target_window(tr, ws, b, b0, n, L[c], c == 0 ? cfg.high : cfg.low, T_O + c);
+            if (L[c] > 0 && L[c] == R[c]) target_window(tr, ws, b, b0, n, L[c], c == 0 ? cfg.thr_high : cfg.thr_low, T_O + c);
             else if (L[c] > 0) emit_window(tr, ws, b, lpos, llen, L[c], T_F + c, false);
             else if (R[c] > 0) emit_window(tr, ws, b, rpos, rlen, R[c], T_B + c, false);
         }
     }
     bool hc[2] = {L[0] == 0 && R[0] == 0, L[1] == 0 && R[1] == 0};
     if (4 * MAXM > n && (hc[0] || hc[1]) && (pm & 1u)) {
-        ScanRes s = scan_stats(ws, b, b0, n, max(n / 4 + 1, MINM), min(n / 2, MAXM), cfg.low, cfg.high);
+        ScanRes s = scan_stats(ws, b, b0, n, max(n / 4 + 1, MINM), min(n / 2, MAXM), cfg.thr_low, cfg.thr_high);
         if (hc[0] && s.th) emit_window(tr, ws, b, b0, n, s.th, T_O + 0, false);  // un-folded into 'both'
         if (hc[1] && s.tl) emit_window(tr, ws, b, b0, n, s.tl, T_O + 1, false);
     }
@@ -1440,7 +1488,7 @@ __device__ void route_pair(const DevCfg& cfg, TableRef tr, WS ws, const DevBatch
         int si[2] = {1, 1}; bool ended[2] = {false, false};
         u64 ks_lo[2] = {0, 0}, ks_hi[2] = {0, 0};
         for (int ti = 1; ti <= 4 && !(ended[0] && ended[1]); ti++) {
-            if (!have[ti]) { sr[ti] = scan_stats(ws, b, spos[ti], slen[ti], MINM, kmax, cfg.low, cfg.high); have[ti] = true; }
+            if (!have[ti]) { sr[ti] = scan_stats(ws, b, spos[ti], slen[ti], MINM, kmax, cfg.thr_low, cfg.thr_high); have[ti] = true; }
             int k[2] = {sr[ti].th, sr[ti].tl};
             u64 slo[2] = {sr[ti].sh_lo, sr[ti].sl_lo}, shi[2] = {sr[ti].sh_hi, sr[ti].sl_hi};
 #pragma unroll
@@ -1469,7 +1517,7 @@ __device__ void route_pair(const DevCfg& cfg, TableRef tr, WS ws, const DevBatch
         if (si[0] <= 4 || si[1] <= 4) {
             int sj[2] = {4, 4}; km[0] = km[1] = 0; ended[0] = ended[1] = false;
             for (int tj = 4; tj >= 1 && !(ended[0] && ended[1]); tj--) {
-                if (!have[tj]) { sr[tj] = scan_stats(ws, b, spos[tj], slen[tj], MINM, kmax, cfg.low, cfg.high); have[tj] = true; }
+                if (!have[tj]) { sr[tj] = scan_stats(ws, b, spos[tj], slen[tj], MINM, kmax, cfg.thr_low, cfg.thr_high); have[tj] = true; }
                 int k[2] = {sr[tj].th, sr[tj].tl};
                 u64 slo[2] = {sr[tj].sh_lo, sr[tj].sl_lo}, shi[2] = {sr[tj].sh_hi, sr[tj].sl_hi};
 #pragma unroll
@@ -1500,8 +1548,8 @@ __device__ void route_pair(const DevCfg& cfg, TableRef tr, WS ws, const DevBatch
     if (4 * MAXM > n && (lef[0] == 0 || lef[1] == 0 || km[0] == 0 || km[1] == 0)) {
         int lo = max(n / 4 + 1, MINM), hi = min(n / 2, MAXM);
         ScanRes l, r; l.th = l.tl = r.th = r.tl = 0; l.sh_lo = l.sh_hi = l.sl_lo = l.sl_hi = 0; r = l;
-        if (lef[0] == 0 || lef[1] == 0) l = scan_stats(ws, b, a0, n1, lo, hi, cfg.low, cfg.high);
-        if (km[0] == 0 || km[1] == 0) r = scan_stats(ws, b, a1, n2, lo, hi, cfg.low, cfg.high);
+        if (lef[0] == 0 || lef[1] == 0) l = scan_stats(ws, b, a0, n1, lo, hi, cfg.thr_low, cfg.thr_high);
+        if (km[0] == 0 || km[1] == 0) r = scan_stats(ws, b, a1, n2, lo, hi, cfg.thr_low, cfg.thr_high);
         int ltk[2] = {l.th, l.tl}, rtk[2] = {r.th, r.tl};
         u64 llo[2] = {l.sh_lo, l.sl_lo}, lhi[2] = {l.sh_hi, l.sl_hi}, rlo[2] = {r.sh_lo, r.sl_lo}, rhi[2] = {r.sh_hi, r.sl_hi};
 #pragma unroll
@@ -1536,7 +1584,7 @@ __device__ void route_long(const DevCfg& cfg, TableRef tr, WS ws, const DevBatch
     int si[2] = {1, 1}, km[2] = {0, 0}; bool ended[2] = {false, false};
     int nf = 0;
     for (int ti = 1; ti <= snum && !(ended[0] && ended[1]); ti++) {
-        ScanRes sr = scan_stats(ws, b, b0 + s_start(ti), s_len(ti), MINM, MAXM, cfg.low, cfg.high);
+        ScanRes sr = scan_stats(ws, b, b0 + s_start(ti), s_len(ti), MINM, MAXM, cfg.thr_low, cfg.thr_high);
         if (ws.lane == 0) { scratch[2 * (ti - 1)] = (unsigned char)sr.th; scratch[2 * (ti - 1) + 1] = (unsigned char)sr.tl; }
         int k[2] = {sr.th, sr.tl};
 #pragma unroll
@@ -1564,7 +1612,7 @@ __device__ void route_long(const DevCfg& cfg, TableRef tr, WS ws, const DevBatch
     if (si[0] <= snum || si[1] <= snum) {
         int sj[2] = {snum, snum}; km[0] = km[1] = 0; ended[0] = ended[1] = false;
         for (int tj = snum; tj >= 1 && !(ended[0] && ended[1]); tj--) {
-            ScanRes sr = scan_stats(ws, b, b0 + s_start(tj), s_len(tj), MINM, MAXM, cfg.low, cfg.high);
+            ScanRes sr = scan_stats(ws, b, b0 + s_start(tj), s_len(tj), MINM, MAXM, cfg.thr_low, cfg.thr_high);
             int k[2] = {sr.th, sr.tl};
 #pragma unroll
             for (int c = 0; c < 2; c++) {
@@ -1576,6 +1624,123 @@ __device__ void route_long(const DevCfg& cfg, TableRef tr, WS ws, const DevBatch
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// thread-per-survivor exact kernel (short single-end reads within the limits of exact_thread.cuh)
+// ------------------------------------------------------------------------------------------------
+//
+// One THREAD per survivor: the read's planes in registers, buffer_task as scalar code (exact_thread.cuh, also built
+// for the host and diffed against the oracle in tests/test_exact_thread.py).  A survivor outside the limits of that
+// path is appended to `hard`; the warp-per-survivor kernel below then takes exactly those.
+
+// Emissions are staged in a per-block shared-memory count table and flushed to the global table once, when the block
+// is done: nearly every emission of a batch hits the same handful of keys (TTAGGG and its one-error variants), and
+// global atomics to one address retire one at a time in L2 (measured: 2 M all-telomeric survivors cost the same
+// 4.7 ms whatever the kernel in front of the atomics does).  Staged, a block adds to shared memory -- 148 SMs in
+// parallel -- and sends one global add per distinct key.  A key that finds no free slot within a few probes goes
+// straight to the global table (noisy batches: many distinct keys of count 1).
+constexpr int kStageSlots = 512;            // per block; 16 bytes each
+constexpr int kStageProbes = 6;
+constexpr u32 kStageLock = 0xffffffffu;     // s_meta: 0 empty, kStageLock being written, else (meta | 1 << 31) ready
+
+struct StageEmit {
+    u32* s_meta; u32* s_cnt; u64* s_key;    // shared
+    Slot* slots; u32 mask; u32* err;        // global table
+    __device__ __forceinline__ void operator()(int table, int k, u64 key, u64 count) const {
+        const u32 meta = ((u32)table << 8) | (u32)k, tag = meta | 0x80000000u;
+        u32 i = (u32)(mix64(key ^ ((u64)meta << 53)) >> 40) & (kStageSlots - 1);
+        bool done = false;
+        for (int p = 0; p < kStageProbes && !done; p++, i = (i + 1) & (kStageSlots - 1)) {
+            int outcome = 0;   // 0 look again (a neighbour is publishing this slot), 1 added, 2 another key lives here
+            do {               // same protocol as table_add_impl: no lane waits inside a divergent branch
+                const u32 st = atomicCAS(&s_meta[i], 0u, kStageLock);
+                if (st == 0u) {
+                    s_key[i] = key;
+                    __threadfence_block();
+                    atomicExch(&s_meta[i], tag);
+                    atomicAdd(&s_cnt[i], (u32)count);
+                    outcome = 1;
+                } else if (st != kStageLock) {
+                    __threadfence_block();
+                    if (st == tag && *(volatile u64*)&s_key[i] == key) { atomicAdd(&s_cnt[i], (u32)count); outcome = 1; }
+                    else outcome = 2;
+                }
+            } while (outcome == 0);
+            done = outcome == 1;
+        }
+        if (!done) table_add_impl(slots, mask, err, meta, key, 0ULL, count);
+    }
+};
+
+#ifndef TREW_THREAD_BLOCK
+#define TREW_THREAD_BLOCK 128
+#endif
+constexpr size_t kThreadKernelSmem = (size_t)et::kWorkWords * TREW_THREAD_BLOCK * sizeof(u32) + (size_t)kStageSlots * 16;
+
+__global__ void __launch_bounds__(TREW_THREAD_BLOCK) trew_exact_thread_kernel(DevCfg cfg, DevBatch b, const u32* __restrict__ survivors,
+                                                                              const u32* __restrict__ n_survivors, int packed_probes,
+                                                                              u32* __restrict__ hard, u32* __restrict__ n_hard,
+                                                                              unsigned long long* total_survivors, u32 exp_flags) {
+    // word i of thread t's workspace at work[i * blockDim + t]: no bank conflicts
+    u32* work = reinterpret_cast<u32*>(g_smem);
+    u64* s_key = reinterpret_cast<u64*>(work + et::kWorkWords * TREW_THREAD_BLOCK);
+    u32* s_meta = reinterpret_cast<u32*>(s_key + kStageSlots);
+    u32* s_cnt = s_meta + kStageSlots;
+    for (int i = threadIdx.x; i < kStageSlots; i += blockDim.x) { s_meta[i] = 0u; s_cnt[i] = 0u; }
+    __syncthreads();
+    const et::Mem m{work + threadIdx.x, TREW_THREAD_BLOCK};
+    const u32 n = *n_survivors;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && total_survivors) atomicAdd(total_survivors, (unsigned long long)n);
+    StageEmit emit{s_meta, s_cnt, s_key, cfg.slots, cfg.slot_mask, cfg.error_flag};
+    const u32 stride = gridDim.x * blockDim.x;
+    const u32 n_round = (n + 31u) & ~31u;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        bool bail = false;
+        u32 entry = 0;
+        if (i < n) {
+            entry = survivors[i];
+            u32 u = entry, pm = 3u;
+            if (packed_probes) { pm = entry >> kProbeShift; u &= (1u << kProbeShift) - 1u; }
+            const u32 b0 = __ldg(b.bit_off + u);
+            const int len = (int)(__ldg(b.bit_off + u + 1) - b0);
+            if (len > et::kMaxRead) {
+                bail = true;
+            } else {
+                const u32 w0 = b0 >> 5, sh = b0 & 31u;
+                u32 invalid = 0;
+                for (int j = 0; j < et::kReadWords + 2; j++) {
+                    const u32 msk = low_mask(min(32, max(0, len - 32 * j)));
+                    const u32 v = __funnelshift_r(__ldg(b.val + w0 + j), __ldg(b.val + w0 + j + 1), sh) & msk;
+                    m[et::W_RH + j] = __funnelshift_r(__ldg(b.hi + w0 + j), __ldg(b.hi + w0 + j + 1), sh) & msk;
+                    m[et::W_RL + j] = __funnelshift_r(__ldg(b.lo + w0 + j), __ldg(b.lo + w0 + j + 1), sh) & msk;
+                    m[et::W_RV + j] = v;
+                    invalid |= v ^ msk;
+                }
+                (void)invalid; (void)exp_flags;
+                bail = !et::route_short_thread(m, len, pm & 3u, cfg.min_mer, cfg.max_mer, cfg.thr_low, cfg.thr_high, emit);
+            }
+        }
+        list_append(bail, entry, hard, n_hard);
+    }
+    // flush the staged counts
+    __syncthreads();
+    for (int i = threadIdx.x; i < kStageSlots; i += blockDim.x) {
+        const u32 st = s_meta[i], c = s_cnt[i];
+        if (st != 0u && st != kStageLock && c != 0u) table_add_impl(cfg.slots, cfg.slot_mask, cfg.error_flag, st & 0x7fffffffu, s_key[i], 0ULL, (u64)c);
+    }
+}
+
+// true when the thread kernel can take (most of) a batch: short single-end mode, 64-bit units
+bool thread_path_applies(const DevCfg& cfg, unsigned int max_read_len) {
+    return cfg.mode == 0 && cfg.max_mer <= 32 && max_read_len >= 4u * (unsigned)cfg.max_mer;
+}
+
+void launch_exact_thread(const DevCfg& cfg, const DevBatch& b, const unsigned int* survivors, const unsigned int* n_survivors,
+                         int packed_probes, unsigned int* hard, unsigned int* n_hard, unsigned long long* total_survivors, int blocks,
+                         unsigned int exp_flags, cudaStream_t stream) {
+    trew_exact_thread_kernel<<<blocks, TREW_THREAD_BLOCK, kThreadKernelSmem, stream>>>(cfg, b, survivors, n_survivors, packed_probes, hard,
+                                                                                       n_hard, total_survivors, exp_flags);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kExactWarps * 32, TREW_EXACT_BPS) trew_exact_kernel(DevCfg cfg, DevBatch b, ExactArgs a) {
     const int wid = threadIdx.x >> 5;
@@ -1584,7 +1749,7 @@ __global__ void __launch_bounds__(kExactWarps * 32, TREW_EXACT_BPS) trew_exact_k
     ws.cap = a.run_cap; ws.hs = exact_hash_slots(a.run_cap);
     ws.off = (u32)((size_t)wid * exact_warp_bytes(a.run_cap)); ws.lane = lane; ws.flags = a.exp_flags;
     TableRef tr{cfg.slots, cfg.slot_mask, cfg.error_flag};
-    if (lane < 16) ws.hdr()[lane] = lane == HD_CUR_LEN || lane == HD_EV_LEN || lane == HD_EV_K ? 0xffffffffu : 0u;
+    ws.hdr()[lane] = lane == HD_CUR_LEN || lane == HD_EV_LEN || lane == HD_EV_K ? 0xffffffffu : 0u;
     __syncwarp();
     const u32 n = *a.n_survivors;
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.total_survivors) atomicAdd(a.total_survivors, (u64)n);
@@ -1594,7 +1759,7 @@ __global__ void __launch_bounds__(kExactWarps * 32, TREW_EXACT_BPS) trew_exact_k
         if (lane == 0) idx = atomicAdd(a.work_counter, 1u);
         idx = __shfl_sync(0xffffffffu, idx, 0);
         if (idx >= n) break;
-        u32 u = a.survivors[idx], pm = 0xfu;
+        u32 u = a.reverse ? *(a.survivors - idx) : a.survivors[idx], pm = 0xfu;
         if (a.packed_probes) { pm = u >> kProbeShift; u &= (1u << kProbeShift) - 1u; }
         if constexpr (MODE == 0) route_short(cfg, tr, ws, b, u, pm);
         else if constexpr (MODE == 1) route_pair(cfg, tr, ws, b, u);
@@ -1610,6 +1775,7 @@ cudaError_t prepare_exact(int run_cap_max) {
     cudaError_t e = cudaFuncSetAttribute(trew_exact_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(trew_exact_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(trew_exact_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(trew_exact_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kThreadKernelSmem);
     return e;
 }
 

@@ -3,6 +3,8 @@
 // Two kernels implement the reference's per-read scan-and-count (buffer_task*, src/kmer.cpp:80-985,
 // with k_mer_check/k_mer_target, src/kmer.cpp:1894-2547):
 //
+//   (short single-end mode adds trew_exact_thread_kernel, one THREAD per survivor, in front of the warp kernel: see
+//   exact_thread.cuh; the decide kernel then writes two survivor lists, one per exact kernel)
 //   trew_filter_kernel  one THREAD per read/pair.  Bit-parallel, sound rejection test: for every probe
 //                       window the routing would scan first and every period k, an upper bound U_k on
 //                       the largest rotation-class count M_k is compared with the smallest count that
@@ -38,6 +40,7 @@ struct DevCfg {
     unsigned int slot_mask;
     unsigned int* error_flag;        // [0] set to TREW_ERR_TABLE_FULL on overflow, [1] number of distinct keys inserted
     const unsigned short* thr_low;   // kThrTableSize entries: min M with (double)M/(double)T >= low; 0xFFFF for T = 0
+    const unsigned short* thr_high;  // the same for the high baseline
 };
 
 struct DevBatch {
@@ -57,7 +60,9 @@ struct ExactArgs {
     int run_cap;                     // run-list capacity per warp (>= longest window + 1)
     unsigned long long* total_survivors;  // running total over all launches (statistics)
     int packed_probes;               // survivor entries carry the undecided-probe mask in bits 28..31
-    unsigned int exp_flags;          // experiments (TREW_EXACT_FLAGS): 1 = no register path for few runs, 2 = no composition bound
+    int reverse;                     // the list grows downwards: entry idx is survivors[-idx]
+    unsigned int exp_flags;          // experiments (TREW_EXACT_FLAGS): 1 = no serial path for few runs, 2 = no composition bound,
+                                     // 4 = no thread-per-survivor kernel, 8 = reads with invalid bases stay in the thread kernel
 };
 
 // grid sizes (total blocks) of the three scan kernels; all three are grid-stride / work-counter kernels
@@ -68,11 +73,18 @@ LaunchPlan default_launch_plan(int sm_count);
 // deferred / n_deferred: scratch list of n_units entries + its counter (zeroed) for the screen kernel
 void launch_filter(const DevCfg& cfg, const DevBatch& b, unsigned int n_units, unsigned int max_read_len,
                    unsigned int* deferred, unsigned int* n_deferred, unsigned int* survivors, unsigned int* n_survivors,
-                   const LaunchPlan& plan, cudaStream_t stream, cudaEvent_t after_screen = nullptr);
+                   const LaunchPlan& plan, cudaStream_t stream, cudaEvent_t after_screen = nullptr,
+                   unsigned int* surv_b_top = nullptr, unsigned int* n_surv_b = nullptr);
 size_t exact_smem_bytes(int run_cap, bool wide);
 cudaError_t prepare_exact(int run_cap_max);
 void launch_exact(const DevCfg& cfg, const DevBatch& b, const ExactArgs& a, const LaunchPlan& plan, cudaStream_t stream);
 int exact_warps_total(int sm_count);
+// thread-per-survivor exact kernel (exact_thread.cuh): takes the survivors of a short-mode batch, appends the ones
+// outside its limits to `hard` (counter n_hard, zeroed) for launch_exact
+bool thread_path_applies(const DevCfg& cfg, unsigned int max_read_len);
+void launch_exact_thread(const DevCfg& cfg, const DevBatch& b, const unsigned int* survivors, const unsigned int* n_survivors,
+                         int packed_probes, unsigned int* hard, unsigned int* n_hard, unsigned long long* total_survivors, int blocks,
+                         unsigned int exp_flags, cudaStream_t stream);
 // table_kernels.cu
 void launch_compact(const Slot* slots, unsigned int n_slots, trew_entry* out, unsigned int* d_n, cudaStream_t stream, unsigned int cap);
 // sort by (table, k, seq): sorted rows into d_out (d_entries untouched); wide = some key uses seq_hi (MAX_MER > 32);

@@ -1,7 +1,7 @@
 // `trew` command line: same subcommands, positionals, option names, defaults, validation messages and
 // exit codes as the reference's main (src/trew.cpp:22-477), driving the B200 scan through the C ABI.
-// -t / -m / -q are accepted and validated for compatibility but do not steer the GPU path
-// (threads -> host packing threads; the rotation table and the chunk queue do not exist here).
+// -t / -m / -q are accepted and validated for compatibility but do not steer the GPU path (the consumers are GPUs,
+// the host side always uses every core; the rotation table and the chunk queue do not exist here).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -150,12 +150,29 @@ int main(int argc, char** argv) {
     cfg.mode = is_short ? (paired ? TREW_MODE_PAIR : TREW_MODE_SHORT) : TREW_MODE_LONG;
     cfg.min_mer = min_mer; cfg.max_mer = max_mer; cfg.slice_length = slice_length;
     cfg.low_baseline = low; cfg.high_baseline = high;
-    cfg.device = getenv("TREW_DEVICE") ? atoi(getenv("TREW_DEVICE")) : 0;
-    cfg.host_threads = num_thread;
-    trew_ctx* ctx = nullptr;
-    int rc = trew_dev_create(&cfg, &ctx);
+    // -t sized the reference's consumer pool; the consumers are GPUs here, and the host side (FASTQ index, packer,
+    // BGZF inflate) always uses every core: a reference command line with the default -t 2 must not throttle it.
+    cfg.host_threads = 0;
+    // Which GPUs: TREW_DEVICES = "all", a count, or a comma list of ordinals; TREW_DEVICE = one ordinal.  By default
+    // every visible GPU takes part once the input is large enough to feed more than one (512 MiB), else device 0.
+    std::vector<int32_t> devices;
+    {
+        const char* list = getenv("TREW_DEVICES");
+        const char* one = getenv("TREW_DEVICE");
+        uintmax_t input_bytes = 0;
+        for (auto& p : paths) { std::error_code ec; uintmax_t sz = std::filesystem::file_size(p, ec); if (!ec) input_bytes += sz; }
+        if (list && *list && strcmp(list, "all") != 0) {
+            if (strchr(list, ',')) { for (const char* q = list; q && *q; q = strchr(q, ',') ? strchr(q, ',') + 1 : nullptr) devices.push_back(atoi(q)); }
+            else { int n = atoi(list); for (int i = 0; i < n; i++) devices.push_back(i); }
+        } else if (!(list && *list)) {
+            if (one && *one) devices.push_back(atoi(one));
+            else if (input_bytes < ((uintmax_t)512 << 20)) devices.push_back(0);
+        }   // empty list = all visible devices
+    }
+    trew_multi* ctx = nullptr;
+    int rc = trew_multi_create(&cfg, devices.empty() ? nullptr : devices.data(), (int32_t)devices.size(), &ctx);
     if (rc != TREW_OK) {
-        const char* why = trew_dev_last_error(nullptr);
+        const char* why = trew_multi_last_error(nullptr);
         fprintf(stderr, "trew: cannot create device context: %s\n", why && *why ? why : trew_status_string(rc));
         return 1;
     }
@@ -174,15 +191,15 @@ int main(int argc, char** argv) {
             a = std::filesystem::canonical(paths[i]).string();
             g1 = has_gz_ext(paths[i]);
         }
-        trew_dev_reset(ctx);
-        rc = trew_dev_process_file(ctx, a.c_str(), g1, is_pair ? b.c_str() : nullptr, g2);
+        trew_multi_reset(ctx);
+        rc = trew_multi_process_file(ctx, a.c_str(), g1, is_pair ? b.c_str() : nullptr, g2);
         const trew_entry* entries = nullptr;
         uint64_t n = 0;
-        if (rc == TREW_OK) rc = trew_dev_finish(ctx, &entries, &n);
+        if (rc == TREW_OK) rc = trew_multi_finish(ctx, &entries, &n);
         if (rc != TREW_OK) {
-            fprintf(stderr, "%s\n", trew_dev_last_error(ctx));  // the reference prints and exit(EXIT_FAILURE)s
+            fprintf(stderr, "%s\n", trew_multi_last_error(ctx));  // the reference prints and exit(EXIT_FAILURE)s
             trew_report_destroy(rep);
-            trew_dev_destroy(ctx);
+            trew_multi_destroy(ctx);
             return 1;
         }
         trew_report_add_file(rep, a.c_str(), entries, n);
@@ -200,6 +217,6 @@ int main(int argc, char** argv) {
     trew_report_finish(rep, &text, &len);
     fwrite(text + printed, 1, len - printed, stdout);
     trew_report_destroy(rep);
-    trew_dev_destroy(ctx);
+    trew_multi_destroy(ctx);
     return 0;
 }
