@@ -231,7 +231,7 @@ ET_FN int cls_max(Mem m, int n, const ClsSpill& x, u64& S) {
     return (int)(best >> 10);
 }
 
-// max(baseline, last accepted frequency) without floating point: see scan_kernels.cu, "No floating point on the device"
+// max(baseline, last accepted frequency) without floating point: see scan_kernels.cu, need_pass
 ET_HD bool need_pass(const unsigned short* thr, u32 need, int M, int T) {
     const u32 mm = need & 0xffffu, t = need >> 16;
     return M >= (int)thr[T] && (t == 0u || (u32)M * t >= mm * (u32)T);

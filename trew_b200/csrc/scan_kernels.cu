@@ -1072,7 +1072,7 @@ __device__ __noinline__ u32 eval_k(WS ws, int len, int k, u32 wv) {
     u32 *htab = ws.htab(), *grp_tot = ws.grp_tot(), *grp_last = ws.grp_last();
     const u64* rev2 = ws.rev2();
     const bool wide = k > 32;
-    if (!wide && R <= kSerialMaxRuns && !(ws.flags & 1u)) {
+    if (!wide && R <= kSerialMaxRuns && (ws.flags & 1u)) {   // off by default: measured slower than the general path below
         // Few runs (every repeat read: a perfect repeat is one run, each substitution adds at most two).  The warp
         // collectives of the general path below (prefix scans, shared-memory atomics, reductions) cost more latency
         // than the work they spread, so here every lane walks the runs redundantly in plain ALU / shared-memory
@@ -1245,16 +1245,27 @@ __constant__ MultTab c_mult = make_mult_tab();
 // the K_MER_DATA_MAX_SEQ of each.  Periods that cannot be accepted by either selection (divisor rule,
 // or the signature bound below the running threshold) are skipped without an exact count.
 //
-// No floating point on the device: the reference accepts k iff fl(M/T) >= max(B, f_prev) in doubles
+// The reference accepts k iff fl(M/T) >= max(B, f_prev) in doubles
 // (src/kmer.cpp:2223-2224, 2243-2244).  "fl(M/T) >= B" is "M >= thr_B[T]", thr_B built on the host with the same IEEE
 // division (device_ctx.cu:build_thr); "fl(M/T) >= fl(M'/T')" between two ratios with denominators <= 1023 is
 // "M * T' >= M' * T" exactly (distinct such ratios differ by > 1e-6, far more than an ulp, and rounding is monotone).
 // The pre-test replaces M by its upper bound U in the same two comparisons, so it never rejects a period the
 // reference would accept.
 // max(baseline, last accepted frequency) of one selection: need = m | t << 16 of the last accepted ratio (0: none yet)
-__device__ __forceinline__ bool need_pass(const unsigned short* thr, u32 need, int M, int T) {
+__device__ __forceinline__ int thr_at(const WS& ws, const unsigned short* thr_low, bool high, int T) {
+    return (int)__ldg(thr_low + (high ? kThrTableSize : 0) + T);
+}
+// the exact acceptance test (a table read: only behind an exact evaluation, a few times per survivor)
+__device__ __forceinline__ bool need_pass(const WS& ws, const unsigned short* thr_low, bool high, u32 need, int M, int T) {
     const u32 m = need & 0xffffu, t = need >> 16;
-    return M >= (int)__ldg(thr + T) && (t == 0u || (u32)M * t >= m * (u32)T);
+    return M >= thr_at(ws, thr_low, high, T) && (t == 0u || (u32)M * t >= m * (u32)T);
+}
+// the pre-test on an upper bound U of M, without a memory access (it runs for every lane and period): the baseline half
+// in doubles with a slack -- fl(M/T) >= B implies M >= B*T*(1 - 2^-53) and U >= M, so "U >= B*T*(1 - 1e-12)" never
+// rejects a period the reference accepts -- the ratio half exactly
+__device__ __forceinline__ bool need_pre(double B, u32 need, int U, int T) {
+    const u32 m = need & 0xffffu, t = need >> 16;
+    return (double)U >= B * (double)T * (1.0 - 1e-12) && (t == 0u || (u32)U * t >= m * (u32)T);
 }
 
 __device__ __forceinline__ bool blocked_k(const u32* hd, int which /* HD_BLK_L or HD_BLK_H */, int k) {
@@ -1264,19 +1275,18 @@ __device__ __forceinline__ bool blocked_k(const u32* hd, int which /* HD_BLK_L o
 
 // one exact evaluation + the two acceptance tests of src/kmer.cpp:2221-2258 for period kk; the selection state is in the
 // header.  Returns true when the period was accepted (the thresholds / divisor masks changed).
-__device__ __noinline__ bool try_k(WS ws, const unsigned short* thr_low, u32 pos, int len, int kk, int Uk, int Tk, u32 wv) {
+__device__ __forceinline__ bool try_k(WS ws, const unsigned short* thr_low, double low, double high, u32 pos, int len, int kk, int Uk, int Tk, u32 wv) {
     u32* hd = ws.hdr();
-    const unsigned short* thr_high = thr_low + kThrTableSize;
     const bool blkL = blocked_k(hd, HD_BLK_L, kk), blkH = blocked_k(hd, HD_BLK_H, kk);
     if (blkL && blkH) return false;
     const u32 needL = hd[HD_NEED_L], needH = hd[HD_NEED_H];
-    bool candL = !blkL && need_pass(thr_low, needL, Uk, Tk), candH = !blkH && need_pass(thr_high, needH, Uk, Tk);
+    bool candL = !blkL && need_pre(low, needL, Uk, Tk), candH = !blkH && need_pre(high, needH, Uk, Tk);
     if (!candL && !candH) return false;
 #ifndef TREW_NO_COMP_BOUND
     if (Tk <= 32 && !(ws.flags & 2u)) {   // few windows: the exact-composition bound is cheap and far tighter than the parity signature
         const int Mc = comp_bound(ws, kk, wv, Tk);
         if (Mc < Uk) {
-            candL = !blkL && need_pass(thr_low, needL, Mc, Tk); candH = !blkH && need_pass(thr_high, needH, Mc, Tk);
+            candL = !blkL && need_pre(low, needL, Mc, Tk); candH = !blkH && need_pre(high, needH, Mc, Tk);
             if (!candL && !candH) return false;
         }
     }
@@ -1286,7 +1296,7 @@ __device__ __noinline__ bool try_k(WS ws, const unsigned short* thr_low, u32 pos
     __syncwarp();
     if (pk_homo(ev) || pk_T(ev) == 0) return false;
     const int M = pk_M(ev), T = pk_T(ev);
-    const bool accL = !blkL && need_pass(thr_low, needL, M, T), accH = !blkH && need_pass(thr_high, needH, M, T);
+    const bool accL = !blkL && need_pass(ws, thr_low, false, needL, M, T), accH = !blkH && need_pass(ws, thr_low, true, needH, M, T);
     if (!(accL || accH)) return false;
     if (ws.lane == 0) {
         const u64 mm = c_mult.m[kk];   // multiples of kk below 64
@@ -1311,7 +1321,8 @@ __device__ __noinline__ bool try_k(WS ws, const unsigned short* thr_low, u32 pos
 
 // k_mer_check without emission for window [pos, pos + len), periods kmin..kmax: returns target_k_high | target_k_low << 8;
 // the K_MER_DATA_MAX_SEQ of the two are left in the header (HD_SH, HD_SL).
-__device__ __noinline__ u32 scan_core(WS ws, DevBatch b, u32 pos, int len, int kmin, int kmax, const unsigned short* thr_low) {
+__device__ __noinline__ u32 scan_core(WS ws, DevBatch b, u32 pos, int len, int kmin, int kmax, const unsigned short* thr_low, double low,
+                                      double high) {
     if (kmax < kmin) return 0u;
     load_window(ws, b.hi, b.lo, b.val, pos, len);
     const u32 lane = ws.lane;
@@ -1319,7 +1330,6 @@ __device__ __noinline__ u32 scan_core(WS ws, DevBatch b, u32 pos, int len, int k
     if (lane >= HD_BLK_L && lane <= HD_SL + 3) hd[lane] = 0u;   // fresh selection state
     __syncwarp();
     const bool all_valid = hd[HD_ALLVALID] != 0;
-    const unsigned short* thr_high = thr_low + kThrTableSize;
 
     if (len <= 127 || all_valid) {
         // Every lane bounds its own period (lane <-> k); the qualifying periods are then visited in ascending order.
@@ -1356,7 +1366,7 @@ __device__ __noinline__ u32 scan_core(WS ws, DevBatch b, u32 pos, int len, int k
                 int c10 = cH - c11, c01 = cL - c11, c00 = T - cH - cL + c11;
                 U = max(max(c00, c01), max(c10, c11));
             }
-            bool cand = T > 0 && U >= (int)__ldg(thr_low + T);
+            bool cand = T > 0 && need_pre(low, 0u, U, T);
             u32 cm = __ballot_sync(0xffffffffu, cand);
             while (cm) {
                 int bit = __ffs(cm) - 1;
@@ -1371,13 +1381,13 @@ __device__ __noinline__ u32 scan_core(WS ws, DevBatch b, u32 pos, int len, int k
                     u32 a2 = __shfl_sync(0xffffffffu, wvv[2], bit), a3 = __shfl_sync(0xffffffffu, wvv[3], bit);
                     wv = lane == 0 ? a0 : lane == 1 ? a1 : lane == 2 ? a2 : lane == 3 ? a3 : 0u;
                 }
-                if (try_k(ws, thr_low, pos, len, kb + bit, Uk, Tk, wv) && cm) {
+                if (try_k(ws, thr_low, low, high, pos, len, kb + bit, Uk, Tk, wv) && cm) {
                     // an acceptance raised the thresholds / blocked multiples: drop the remaining periods of
                     // this block that can no longer be accepted by either selection (lane <-> period again)
                     bool still = false;
                     if (T > 0 && k <= 64)
-                        still = (!blocked_k(hd, HD_BLK_L, k) && need_pass(thr_low, hd[HD_NEED_L], U, T)) ||
-                                (!blocked_k(hd, HD_BLK_H, k) && need_pass(thr_high, hd[HD_NEED_H], U, T));
+                        still = (!blocked_k(hd, HD_BLK_L, k) && need_pre(low, hd[HD_NEED_L], U, T)) ||
+                                (!blocked_k(hd, HD_BLK_H, k) && need_pre(high, hd[HD_NEED_H], U, T));
                     cm &= __ballot_sync(0xffffffffu, still);
                 }
             }
@@ -1391,16 +1401,15 @@ __device__ __noinline__ u32 scan_core(WS ws, DevBatch b, u32 pos, int len, int k
         int T = (int)__reduce_add_sync(0xffffffffu, (u32)__popc(wv));
         if (T == 0) break;
         int U = bound_k(ws, k, wv, T);
-        try_k(ws, thr_low, pos, len, k, U, T, wv);
+        try_k(ws, thr_low, low, high, pos, len, k, U, T, wv);
     }
     return hd[HD_RES];
 }
 
 // the result of scan_core with the two K_MER_DATA_MAX_SEQ read back from the header (callers that do not look at them --
 // short and long routing -- never load them)
-__device__ __forceinline__ ScanRes scan_stats(WS ws, const DevBatch& b, u32 pos, int len, int kmin, int kmax, const unsigned short* thr_low,
-                                              const unsigned short*) {
-    const u32 r = scan_core(ws, b, pos, len, kmin, kmax, thr_low);
+__device__ __forceinline__ ScanRes scan_stats(WS ws, const DevBatch& b, u32 pos, int len, int kmin, int kmax, const DevCfg& cfg) {
+    const u32 r = scan_core(ws, b, pos, len, kmin, kmax, cfg.thr_low, cfg.low, cfg.high);
     const u32* hd = ws.hdr();
     ScanRes res;
     res.th = (int)(r & 0xffu); res.tl = (int)(r >> 8);
@@ -1428,9 +1437,9 @@ __device__ void emit_window(TableRef tr, WS ws, const DevBatch& b, u32 pos, int 
 }
 
 // k_mer_target / k_mer_target_128 (src/kmer.cpp:1894-2142)
-__device__ void target_window(TableRef tr, WS ws, const DevBatch& b, u32 pos, int len, int k, const unsigned short* thr, int table) {
+__device__ void target_window(TableRef tr, WS ws, const DevBatch& b, u32 pos, int len, int k, const unsigned short* thr_low, bool high, int table) {
     u32 ev = eval_cached(ws, b, pos, len, k);
-    if (pk_T(ev) > 0 && !pk_homo(ev) && pk_M(ev) >= (int)__ldg(thr + pk_T(ev))) emit_classes(tr, ws, k, pk_runs(ev), table, true);
+    if (pk_T(ev) > 0 && !pk_homo(ev) && pk_M(ev) >= thr_at(ws, thr_low, high, pk_T(ev))) emit_classes(tr, ws, k, pk_runs(ev), table, true);
 }
 
 // ---- routing -----------------------------------------------------------------------------------
@@ -1449,21 +1458,21 @@ __device__ void route_short(const DevCfg& cfg, TableRef tr, WS ws, const DevBatc
         int kmax = min(n / 4, MAXM);
         u32 lpos = b0, rpos = b0 + (u32)(n - (n + 1) / 2);
         int llen = n / 2, rlen = (n + 1) / 2;
-        if (pm & 1u) { ScanRes l = scan_stats(ws, b, lpos, llen, MINM, kmax, cfg.thr_low, cfg.thr_high); L[0] = l.th; L[1] = l.tl; }
-        if (pm & 2u) { ScanRes r = scan_stats(ws, b, rpos, rlen, MINM, kmax, cfg.thr_low, cfg.thr_high); R[0] = r.th; R[1] = r.tl; }  // "always evaluated"
+        if (pm & 1u) { ScanRes l = scan_stats(ws, b, lpos, llen, MINM, kmax, cfg); L[0] = l.th; L[1] = l.tl; }
+        if (pm & 2u) { ScanRes r = scan_stats(ws, b, rpos, rlen, MINM, kmax, cfg); R[0] = r.th; R[1] = r.tl; }  // "always evaluated"
         pm >>= 2;
         // right-half emissions survive only for classes where the left half found nothing
         // (nullptr maps at src/kmer.cpp:125, result.backward at :158)
 #pragma unroll
         for (int c = 0; c < 2; c++) {
-            if (L[c] > 0 && L[c] == R[c]) target_window(tr, ws, b, b0, n, L[c], c == 0 ? cfg.thr_high : cfg.thr_low, T_O + c);
+            if (L[c] > 0 && L[c] == R[c]) target_window(tr, ws, b, b0, n, L[c], cfg.thr_low, c == 0, T_O + c);
             else if (L[c] > 0) emit_window(tr, ws, b, lpos, llen, L[c], T_F + c, false);
             else if (R[c] > 0) emit_window(tr, ws, b, rpos, rlen, R[c], T_B + c, false);
         }
     }
     bool hc[2] = {L[0] == 0 && R[0] == 0, L[1] == 0 && R[1] == 0};
     if (4 * MAXM > n && (hc[0] || hc[1]) && (pm & 1u)) {
-        ScanRes s = scan_stats(ws, b, b0, n, max(n / 4 + 1, MINM), min(n / 2, MAXM), cfg.thr_low, cfg.thr_high);
+        ScanRes s = scan_stats(ws, b, b0, n, max(n / 4 + 1, MINM), min(n / 2, MAXM), cfg);
         if (hc[0] && s.th) emit_window(tr, ws, b, b0, n, s.th, T_O + 0, false);  // un-folded into 'both'
         if (hc[1] && s.tl) emit_window(tr, ws, b, b0, n, s.tl, T_O + 1, false);
     }
@@ -1488,7 +1497,7 @@ __device__ void route_pair(const DevCfg& cfg, TableRef tr, WS ws, const DevBatch
         int si[2] = {1, 1}; bool ended[2] = {false, false};
         u64 ks_lo[2] = {0, 0}, ks_hi[2] = {0, 0};
         for (int ti = 1; ti <= 4 && !(ended[0] && ended[1]); ti++) {
-            if (!have[ti]) { sr[ti] = scan_stats(ws, b, spos[ti], slen[ti], MINM, kmax, cfg.thr_low, cfg.thr_high); have[ti] = true; }
+            if (!have[ti]) { sr[ti] = scan_stats(ws, b, spos[ti], slen[ti], MINM, kmax, cfg); have[ti] = true; }
             int k[2] = {sr[ti].th, sr[ti].tl};
             u64 slo[2] = {sr[ti].sh_lo, sr[ti].sl_lo}, shi[2] = {sr[ti].sh_hi, sr[ti].sl_hi};
 #pragma unroll
@@ -1517,7 +1526,7 @@ __device__ void route_pair(const DevCfg& cfg, TableRef tr, WS ws, const DevBatch
         if (si[0] <= 4 || si[1] <= 4) {
             int sj[2] = {4, 4}; km[0] = km[1] = 0; ended[0] = ended[1] = false;
             for (int tj = 4; tj >= 1 && !(ended[0] && ended[1]); tj--) {
-                if (!have[tj]) { sr[tj] = scan_stats(ws, b, spos[tj], slen[tj], MINM, kmax, cfg.thr_low, cfg.thr_high); have[tj] = true; }
+                if (!have[tj]) { sr[tj] = scan_stats(ws, b, spos[tj], slen[tj], MINM, kmax, cfg); have[tj] = true; }
                 int k[2] = {sr[tj].th, sr[tj].tl};
                 u64 slo[2] = {sr[tj].sh_lo, sr[tj].sl_lo}, shi[2] = {sr[tj].sh_hi, sr[tj].sl_hi};
 #pragma unroll
@@ -1548,8 +1557,8 @@ __device__ void route_pair(const DevCfg& cfg, TableRef tr, WS ws, const DevBatch
     if (4 * MAXM > n && (lef[0] == 0 || lef[1] == 0 || km[0] == 0 || km[1] == 0)) {
         int lo = max(n / 4 + 1, MINM), hi = min(n / 2, MAXM);
         ScanRes l, r; l.th = l.tl = r.th = r.tl = 0; l.sh_lo = l.sh_hi = l.sl_lo = l.sl_hi = 0; r = l;
-        if (lef[0] == 0 || lef[1] == 0) l = scan_stats(ws, b, a0, n1, lo, hi, cfg.thr_low, cfg.thr_high);
-        if (km[0] == 0 || km[1] == 0) r = scan_stats(ws, b, a1, n2, lo, hi, cfg.thr_low, cfg.thr_high);
+        if (lef[0] == 0 || lef[1] == 0) l = scan_stats(ws, b, a0, n1, lo, hi, cfg);
+        if (km[0] == 0 || km[1] == 0) r = scan_stats(ws, b, a1, n2, lo, hi, cfg);
         int ltk[2] = {l.th, l.tl}, rtk[2] = {r.th, r.tl};
         u64 llo[2] = {l.sh_lo, l.sl_lo}, lhi[2] = {l.sh_hi, l.sl_hi}, rlo[2] = {r.sh_lo, r.sl_lo}, rhi[2] = {r.sh_hi, r.sl_hi};
 #pragma unroll
@@ -1584,7 +1593,7 @@ __device__ void route_long(const DevCfg& cfg, TableRef tr, WS ws, const DevBatch
     int si[2] = {1, 1}, km[2] = {0, 0}; bool ended[2] = {false, false};
     int nf = 0;
     for (int ti = 1; ti <= snum && !(ended[0] && ended[1]); ti++) {
-        ScanRes sr = scan_stats(ws, b, b0 + s_start(ti), s_len(ti), MINM, MAXM, cfg.thr_low, cfg.thr_high);
+        ScanRes sr = scan_stats(ws, b, b0 + s_start(ti), s_len(ti), MINM, MAXM, cfg);
         if (ws.lane == 0) { scratch[2 * (ti - 1)] = (unsigned char)sr.th; scratch[2 * (ti - 1) + 1] = (unsigned char)sr.tl; }
         int k[2] = {sr.th, sr.tl};
 #pragma unroll
@@ -1612,7 +1621,7 @@ __device__ void route_long(const DevCfg& cfg, TableRef tr, WS ws, const DevBatch
     if (si[0] <= snum || si[1] <= snum) {
         int sj[2] = {snum, snum}; km[0] = km[1] = 0; ended[0] = ended[1] = false;
         for (int tj = snum; tj >= 1 && !(ended[0] && ended[1]); tj--) {
-            ScanRes sr = scan_stats(ws, b, b0 + s_start(tj), s_len(tj), MINM, MAXM, cfg.thr_low, cfg.thr_high);
+            ScanRes sr = scan_stats(ws, b, b0 + s_start(tj), s_len(tj), MINM, MAXM, cfg);
             int k[2] = {sr.th, sr.tl};
 #pragma unroll
             for (int c = 0; c < 2; c++) {

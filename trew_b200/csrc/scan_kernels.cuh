@@ -61,7 +61,7 @@ struct ExactArgs {
     unsigned long long* total_survivors;  // running total over all launches (statistics)
     int packed_probes;               // survivor entries carry the undecided-probe mask in bits 28..31
     int reverse;                     // the list grows downwards: entry idx is survivors[-idx]
-    unsigned int exp_flags;          // experiments (TREW_EXACT_FLAGS): 1 = no serial path for few runs, 2 = no composition bound,
+    unsigned int exp_flags;          // experiments (TREW_EXACT_FLAGS): 1 = serial path for few runs in eval_k, 2 = no composition bound,
                                      // 4 = no thread-per-survivor kernel, 8 = reads with invalid bases stay in the thread kernel
 };
 
