@@ -258,6 +258,11 @@ def run_ours(args):
         i += 1
     total_reads = reads_rank * world
 
+    # a step ends with the tables of the "file" on the host: the rows that can reach the report of a one-file run (groups
+    # with a class total >= 10, trew_dev_set_report_filter) -- what `trew short 5 32 FILE` copies; the same step with every
+    # row (the six raw maps) is timed beside it as full_tables_ms_per_step
+    ctx.set_report_filter(0 if args.full_tables else 10)
+
     def step():
         ctx.reset()
         for h, _ in handles:
@@ -291,6 +296,17 @@ def run_ours(args):
     screen_ms, decide_ms, exact_ms, n_scans = ctx.kernel_times()
     st = ctx.stats()
     launches = st.kernel_launches - launches0
+    # the same step returning every row of the six maps
+    ctx.set_report_filter(0)
+    step()
+    barrier()
+    ctx.timer_start()
+    for _ in range(3):
+        full_rows = step()
+    full_ms = max_over_ranks(ctx.timer_stop()) / 3
+    barrier()
+    ctx.kernel_times()
+    full_table_rows = int(full_rows.shape[0]) if rank == 0 else 0
     value = total_reads * READ_LEN * args.steps / (ms * 1e-3) / 1e9
     survivor_fraction = st.survivors / max(1, st.units)
 
@@ -363,11 +379,12 @@ def run_ours(args):
             "dtype": "u64", "data": "synthetic",
             "config": {"workload": workload_name(total_reads, world, strong), "min_mer": 5, "max_mer": 32, "low": 0.5, "high": 0.8,
                        "reads_per_gpu": reads_rank, "batches_per_gpu_per_step": launches_per_scan, "reads_per_batch": BATCH_READS,
+                       "tables": "every row of the six maps" if args.full_tables else "rows of groups with a class total >= 10 (what a one-file report can show)",
                        "l2": "inputs (%.1f GB packed per GPU and pass) exceed L2; no flush" % (BYTES_PER_READ * reads_rank / 1e9),
                        "parallelism": "reads sharded over %d GPU(s), one exact NCCL table merge per step" % world},
             "wall_ms_per_step": wall_ms / args.steps,
             "gpu_launches": int(launches),
-            "table_rows": table_rows,
+            "table_rows": table_rows, "full_table_rows": full_table_rows, "full_tables_ms_per_step": full_ms,
             "kernel_share": {"screen_ms_per_step": screen_ms / args.steps, "decide_ms_per_step": decide_ms / args.steps,
                              "exact_ms_per_step": exact_ms / args.steps, "survivor_fraction": survivor_fraction,
                              "rest_ms_per_step": ms / args.steps - scan_ms / args.steps,
@@ -527,6 +544,7 @@ def main():
                     help="strong (default): the 200 M reads are sharded over the GPUs; weak: every GPU holds --reads reads")
     ap.add_argument("--e2e-reads", type=int, default=8_000_000, help="reads per GPU and end-to-end step (host buffers)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-tables", action="store_true", help="time the steps with every table row copied to the host (no report filter)")
     ap.add_argument("--no-shapes", action="store_true", help="skip the paired / long / 3-64 shapes (configs[2..4])")
     args = ap.parse_args()
     # stdout carries exactly one JSON line (rank 0): native libraries that print there (NCCL's version banner)

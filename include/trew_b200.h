@@ -196,6 +196,15 @@ int trew_dev_merge_rows(trew_ctx* ctx, const trew_entry* d_rows, uint64_t n_rows
  * table is left as it is. */
 int trew_dev_finish_merged(trew_ctx* ctx, const trew_entry* const* d_lists, const uint64_t* n_rows, uint32_t n_lists,
                            const trew_entry** entries, uint64_t* n_entries);
+/* Report filter.  With min_total > 0, trew_dev_finish / trew_dev_finish_merged copy to the host only the rows that can
+ * reach the report of a ONE-FILE run: a row's group is (k, min(seq, canonical rotation of its reverse complement)) --
+ * every forward / backward / both count of one report entry comes from one group (src/kmer.cpp:1518-1549) -- and the
+ * group is kept when its high-class or its low-class total reaches min_total.  With min_total = 10 (ABS_MIN_PRINT_COUNT,
+ * the print and scoring threshold, src/kmer.cpp:1615-1620, 2693-2761) trew_report_add_file + trew_report_finish print
+ * exactly what they print from the full tables, while the one- and two-window repeats that N-bearing reads leave behind
+ * (most rows of a large file, exactly as in the reference) stay on the device.  Runs over several files must keep 0:
+ * entries below the threshold still add up across files (src/trew.cpp:454-467).  0 (default) = no filter. */
+int trew_dev_set_report_filter(trew_ctx* ctx, uint32_t min_total);
 /* Make room for about expected_new_keys more distinct keys (grows and re-hashes the table when it would pass a
  * quarter full).  Call before merging other ranks' rows. */
 int trew_dev_reserve(trew_ctx* ctx, uint64_t expected_new_keys);
@@ -226,6 +235,8 @@ int trew_multi_reset(trew_multi* m);
 /* Drain every device, merge, return the six maps sorted by (table, k, seq) like trew_dev_finish (the array belongs to
  * the group and is valid until the next call that touches the tables). */
 int trew_multi_finish(trew_multi* m, const trew_entry** entries, uint64_t* n_entries);
+/* trew_dev_set_report_filter for the group's merged result. */
+int trew_multi_set_report_filter(trew_multi* m, uint32_t min_total);
 /* Sums over the group's contexts (device_ms: the largest). */
 int trew_multi_get_stats(trew_multi* m, trew_stats* out);
 /* The context of the i-th device of the group (e.g. for device-resident batches); owned by the group. */

@@ -324,3 +324,58 @@ def test_sparse_and_dense_validity_paths(monkeypatch):
     assert dense == want, diff_msg(dense, want)
     assert b_sparse < b_dense                                        # the records are smaller than the plane they replace
     assert b_over <= b_dense and b_over > 0.9 * b_dense              # the fallback copied (nearly) everything densely
+
+
+def test_report_filter_keeps_exactly_what_a_report_can_show():
+    """trew_dev_set_report_filter(10): the rows that stay on the device belong to groups (k, RC-folded key) whose high
+    and low totals are both below the print / scoring threshold, so the report text of a one-file run is identical --
+    and the rows that do come back are exactly the groups that reach the threshold, with unchanged counts."""
+    from oracle.oracle import Oracle
+    reads = synth.adversarial_short(61, 3000) + [bytes(r) for r in synth.config_short(62, 60000, telomeric=0.02, half_telomeric=0.01,
+                                                                                        n_rate=0.004)]
+    o = Oracle(5, 32)
+
+    def groups(tables):
+        tot = {}
+        for (tb, k, seq), c in tables.items():
+            key = (k, min(seq, o.crc(seq, k)))
+            t = tot.setdefault(key, [0, 0])
+            t[tb & 1] += c
+        return tot
+
+    with api.DeviceContext(api.MODE_SHORT, 5, 32) as ctx:
+        ctx.submit_reads(reads)
+        full = ctx.finish()
+        ctx.set_report_filter(10)
+        kept = ctx.finish()
+        ctx.set_report_filter(0)
+        assert ctx.finish() == full
+    tot = groups(full)
+    want = {key: c for key, c in full.items() if max(tot[(key[1], min(key[2], o.crc(key[2], key[1])))]) >= 10}
+    assert kept == want
+    assert 0 < len(kept) < len(full) / 2          # most rows are below the threshold
+    texts = []
+    for tables in (full, kept):
+        rep = api.Report(5)
+        rep.add_file("F", tables)
+        texts.append(rep.finish())
+    assert texts[0] == texts[1] and texts[0].count("\n") > 8
+
+
+def test_report_filter_through_the_merge_and_the_cli(tmp_path):
+    import os
+    import subprocess
+    reads = [bytes(r) for r in synth.config_short(63, 40000, telomeric=0.02, half_telomeric=0.01, n_rate=0.004)]
+    with api.DeviceContext(api.MODE_SHORT, 5, 32) as ctx:
+        ctx.submit_reads(reads)
+        ctx.set_report_filter(10)
+        want = ctx.finish()
+    with api.MultiContext(api.MODE_SHORT, 5, 32, devices=[0, 0, 0]) as m:
+        m.set_report_filter(10)
+        m.submit_reads(reads, chunk_reads=7000)
+        assert m.finish() == want
+    p = os.path.join(str(tmp_path), "a.fastq")
+    open(p, "wb").write(synth.fastq_bytes(reads))
+    a = subprocess.run([api.CLI_PATH, "short", "5", "32", p], capture_output=True, check=True).stdout
+    b = subprocess.run([api.CLI_PATH, "short", "5", "32", p], capture_output=True, check=True, env=dict(os.environ, TREW_FULL_TABLES="1")).stdout
+    assert a == b and a.count(b"\n") > 6

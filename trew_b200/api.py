@@ -67,7 +67,8 @@ ABI_SYMBOLS = [
     "trew_report_finish", "trew_dev_export_rows", "trew_dev_merge_rows", "trew_dev_reserve", "trew_dev_finish_merged",
     "trew_pack_reads_ranges", "trew_report_text", "trew_synth_resident_ex", "trew_multi_create", "trew_multi_destroy",
     "trew_multi_device_count", "trew_multi_last_error", "trew_multi_submit_chunk", "trew_multi_process_file",
-    "trew_multi_reset", "trew_multi_finish", "trew_multi_get_stats", "trew_multi_ctx",
+    "trew_multi_reset", "trew_multi_finish", "trew_multi_get_stats", "trew_multi_ctx", "trew_dev_set_report_filter",
+    "trew_multi_set_report_filter",
 ]
 
 CHUNK_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_uint32, C.c_void_p,
@@ -131,6 +132,8 @@ def load_library() -> C.CDLL:
     L.trew_multi_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     L.trew_multi_ctx.argtypes = [C.c_void_p, C.c_int32]
     L.trew_multi_ctx.restype = C.c_void_p
+    L.trew_dev_set_report_filter.argtypes = [C.c_void_p, C.c_uint32]
+    L.trew_multi_set_report_filter.argtypes = [C.c_void_p, C.c_uint32]
     L.trew_dev_timer_start.argtypes = [C.c_void_p]
     L.trew_dev_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.trew_dev_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -395,6 +398,10 @@ class DeviceContext:
         buf = (C.c_char * (n.value * 32)).from_address(C.addressof(p.contents))
         return np.frombuffer(buf, dtype=self.ENTRY_DTYPE, count=n.value)
 
+    def set_report_filter(self, min_total: int) -> None:
+        """finish*() then return only the rows a one-file report can show (groups with a class total >= min_total)."""
+        self._check(self.lib.trew_dev_set_report_filter(self.ctx, min_total))
+
     def reserve(self, expected_new_keys: int) -> None:
         """Grow the count table so that about this many more distinct keys fit at a load factor <= 1/4."""
         self._check(self.lib.trew_dev_reserve(self.ctx, expected_new_keys))
@@ -479,6 +486,9 @@ class MultiContext:
         gz = lambda p: int(p.endswith(".gz") or p.endswith(".bgz"))
         self._check(self.lib.trew_multi_process_file(self.h, file1.encode(), gz(file1), file2.encode() if file2 else None,
                                                      gz(file2) if file2 else 0))
+
+    def set_report_filter(self, min_total: int) -> None:
+        self._check(self.lib.trew_multi_set_report_filter(self.h, min_total))
 
     def reset(self) -> None:
         self._check(self.lib.trew_multi_reset(self.h))

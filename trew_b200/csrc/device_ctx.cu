@@ -99,6 +99,8 @@ struct trew_ctx {
     double screen_ms = 0, decide_ms = 0, exact_ms = 0; uint64_t n_prof_scans = 0;
     std::vector<trew_resident*> pending_prof;
     void* h_export = nullptr; size_t h_export_bytes = 0;
+    unsigned int report_min = 0;                                 // > 0: finish copies only the rows a one-file report can show
+    trew_entry* d_filtered = nullptr; size_t d_filtered_cap = 0;
 };
 
 namespace {
@@ -618,6 +620,7 @@ void trew_dev_destroy(trew_ctx* ctx) {
     if (ctx->d_entries) cudaFree(ctx->d_entries);
     if (ctx->d_sorted) cudaFree(ctx->d_sorted);
     if (ctx->d_concat) cudaFree(ctx->d_concat);
+    if (ctx->d_filtered) cudaFree(ctx->d_filtered);
     if (ctx->d_sort_tmp) cudaFree(ctx->d_sort_tmp);
     if (ctx->d_n) cudaFree(ctx->d_n);
     if (ctx->h_export) cudaFreeHost(ctx->h_export);
@@ -829,6 +832,91 @@ int export_entries(trew_ctx* ctx, bool need_sorted, const trew_entry** out, uint
 
 int export_sorted(trew_ctx* ctx, uint64_t* n_out) { return export_entries(ctx, false, nullptr, n_out); }
 
+// n rows in device memory -> the pinned host array handed to the caller
+int rows_to_host(trew_ctx* ctx, const trew_entry* d_rows, uint64_t n, const trew_entry** entries, uint64_t* n_entries) {
+    // one D2H of the rows into a pinned array (grown on demand) that is handed to the caller as is
+    size_t need_host = (size_t)n * sizeof(trew_entry) + 64;
+    if (need_host > ctx->h_export_bytes) {
+        if (ctx->h_export) CK(cudaFreeHost(ctx->h_export));
+        ctx->h_export = nullptr;
+        size_t cap = std::max(need_host * 2, (size_t)1 << 20);
+        CK(cudaHostAlloc(&ctx->h_export, cap, cudaHostAllocDefault));
+        ctx->h_export_bytes = cap;
+    }
+    if (n) {
+        CK(cudaMemcpyAsync(ctx->h_export, d_rows, n * sizeof(trew_entry), cudaMemcpyDeviceToHost, ctx->main_stream));
+        CK(cudaStreamSynchronize(ctx->main_stream));
+    }
+    ctx->stats.d2h_bytes += n * sizeof(trew_entry) + 4;
+    if (entries) *entries = (const trew_entry*)ctx->h_export;
+    if (n_entries) *n_entries = n;
+    return TREW_OK;
+}
+
+// Unsorted rows in device memory (with repeated keys when they come from several tables: combine) -> [report filter] ->
+// sort by (table, k, seq) -> [sum equal keys] -> host.  The filter runs first: it needs neither order nor unique keys
+// (group totals add up either way), and what it keeps is a few thousand rows where the tables of a large file hold
+// hundreds of thousands.
+int finish_rows(trew_ctx* ctx, const trew_entry* d_in, uint64_t n_in, bool combine, const trew_entry** entries, uint64_t* n_entries) {
+    auto ensure = [&](trew_entry** buf, size_t* cap, size_t want) -> int {
+        if (want <= *cap) return TREW_OK;
+        if (*buf) CK(cudaFree(*buf));
+        *buf = nullptr;
+        *cap = std::max<size_t>(want + want / 4 + 1024, (size_t)1 << 20);
+        CK(cudaMalloc((void**)buf, *cap * sizeof(trew_entry)));
+        return TREW_OK;
+    };
+    auto ensure_tmp = [&](size_t need) -> int {
+        if (need <= ctx->sort_tmp_bytes) return TREW_OK;
+        CK(cudaStreamSynchronize(ctx->main_stream));
+        if (ctx->d_sort_tmp) CK(cudaFree(ctx->d_sort_tmp));
+        ctx->d_sort_tmp = nullptr;
+        ctx->sort_tmp_bytes = need + need / 4;
+        CK(cudaMalloc(&ctx->d_sort_tmp, ctx->sort_tmp_bytes));
+        return TREW_OK;
+    };
+    int rc;
+    if ((rc = ensure(&ctx->d_sorted, &ctx->d_sorted_cap, (size_t)n_in)) != TREW_OK) return rc;
+    if ((rc = ensure(&ctx->d_filtered, &ctx->d_filtered_cap, (size_t)n_in)) != TREW_OK) return rc;
+    ctx->sorted_valid = false;   // d_sorted is reused below
+    const bool wide = ctx->cfg.max_mer > 32;
+    const trew_entry* src = d_in;
+    unsigned int n = (unsigned int)n_in;
+    if (ctx->report_min > 0 && n > 0) {
+        size_t need = 0;
+        CK(filter_report_rows(src, n, ctx->report_min, ctx->d_filtered, ctx->d_n, nullptr, &need, ctx->main_stream));
+        if ((rc = ensure_tmp(need)) != TREW_OK) return rc;
+        size_t bytes = ctx->sort_tmp_bytes;
+        CK(filter_report_rows(src, n, ctx->report_min, ctx->d_filtered, ctx->d_n, ctx->d_sort_tmp, &bytes, ctx->main_stream));
+        CK(cudaMemcpyAsync(&n, ctx->d_n, sizeof(n), cudaMemcpyDeviceToHost, ctx->main_stream));
+        CK(cudaStreamSynchronize(ctx->main_stream));
+        ctx->stats.kernel_launches += 5;
+        src = ctx->d_filtered;
+    }
+    if (n == 1) CK(cudaMemcpyAsync(ctx->d_sorted, src, sizeof(trew_entry), cudaMemcpyDeviceToDevice, ctx->main_stream));
+    if (n > 1) {
+        size_t need = 0;
+        CK(sort_entries_radix(src, ctx->d_sorted, n, wide, nullptr, &need, ctx->main_stream));
+        if ((rc = ensure_tmp(need)) != TREW_OK) return rc;
+        size_t bytes = ctx->sort_tmp_bytes;
+        CK(sort_entries_radix(src, ctx->d_sorted, n, wide, ctx->d_sort_tmp, &bytes, ctx->main_stream));
+        ctx->stats.kernel_launches += wide ? 11 : 8;
+    }
+    const trew_entry* rows = ctx->d_sorted;
+    if (combine && n > 0) {   // the sort's input is no longer needed: d_filtered takes the combined rows
+        size_t need = 0;
+        CK(combine_sorted_rows(ctx->d_sorted, n, ctx->d_filtered, ctx->d_n, nullptr, &need, ctx->main_stream));
+        if ((rc = ensure_tmp(need)) != TREW_OK) return rc;
+        size_t bytes = ctx->sort_tmp_bytes;
+        CK(combine_sorted_rows(ctx->d_sorted, n, ctx->d_filtered, ctx->d_n, ctx->d_sort_tmp, &bytes, ctx->main_stream));
+        CK(cudaMemcpyAsync(&n, ctx->d_n, sizeof(n), cudaMemcpyDeviceToHost, ctx->main_stream));
+        CK(cudaStreamSynchronize(ctx->main_stream));
+        ctx->stats.kernel_launches += 3;
+        rows = ctx->d_filtered;
+    }
+    return rows_to_host(ctx, rows, n, entries, n_entries);
+}
+
 }  // namespace
 
 extern "C" {
@@ -842,25 +930,14 @@ int trew_dev_finish(trew_ctx* ctx, const trew_entry** entries, uint64_t* n_entri
     if (!ctx) return TREW_ERR_ARG;
     uint64_t n = 0;
     const trew_entry* d_rows = nullptr;
+    if (ctx->report_min > 0) {   // filter first, then sort the few rows that are left
+        int rc = export_entries(ctx, false, &d_rows, &n);
+        if (rc) return rc;
+        return finish_rows(ctx, d_rows, n, false, entries, n_entries);
+    }
     int rc = export_entries(ctx, true, &d_rows, &n);
     if (rc) return rc;
-    // one D2H of the sorted entries into a pinned array (grown on demand) that is handed to the caller as is
-    size_t need = (size_t)n * sizeof(trew_entry) + 64;
-    if (need > ctx->h_export_bytes) {
-        if (ctx->h_export) CK(cudaFreeHost(ctx->h_export));
-        ctx->h_export = nullptr;
-        size_t cap = std::max(need * 2, (size_t)1 << 20);
-        CK(cudaHostAlloc(&ctx->h_export, cap, cudaHostAllocDefault));
-        ctx->h_export_bytes = cap;
-    }
-    if (n) {
-        CK(cudaMemcpyAsync(ctx->h_export, d_rows, n * sizeof(trew_entry), cudaMemcpyDeviceToHost, ctx->main_stream));
-        CK(cudaStreamSynchronize(ctx->main_stream));
-    }
-    ctx->stats.d2h_bytes += n * sizeof(trew_entry) + 4;
-    if (entries) *entries = (const trew_entry*)ctx->h_export;
-    if (n_entries) *n_entries = n;
-    return TREW_OK;
+    return rows_to_host(ctx, d_rows, n, entries, n_entries);
 }
 
 int trew_dev_finish_merged(trew_ctx* ctx, const trew_entry* const* d_lists, const uint64_t* n_rows, uint32_t n_lists,
@@ -883,8 +960,6 @@ int trew_dev_finish_merged(trew_ctx* ctx, const trew_entry* const* d_lists, cons
         return TREW_OK;
     };
     if ((rc = ensure(&ctx->d_concat, &ctx->d_concat_cap)) != TREW_OK) return rc;
-    if ((rc = ensure(&ctx->d_sorted, &ctx->d_sorted_cap)) != TREW_OK) return rc;
-    ctx->sorted_valid = false;   // d_sorted is reused below
     uint64_t at = 0;
     if (n0) CK(cudaMemcpyAsync(ctx->d_concat, d_own, n0 * sizeof(trew_entry), cudaMemcpyDeviceToDevice, ctx->main_stream));
     at += n0;
@@ -892,44 +967,7 @@ int trew_dev_finish_merged(trew_ctx* ctx, const trew_entry* const* d_lists, cons
         if (n_rows[i]) CK(cudaMemcpyAsync(ctx->d_concat + at, d_lists[i], n_rows[i] * sizeof(trew_entry), cudaMemcpyDeviceToDevice, ctx->main_stream));
         at += n_rows[i];
     }
-    const unsigned int n = (unsigned int)total;
-    unsigned int n_out = 0;
-    if (n) {
-        const bool wide = ctx->cfg.max_mer > 32;
-        size_t need_sort = 0, need_comb = 0;
-        CK(sort_entries_radix(ctx->d_concat, ctx->d_sorted, n, wide, nullptr, &need_sort, ctx->main_stream));
-        CK(combine_sorted_rows(ctx->d_sorted, n, ctx->d_concat, ctx->d_n, nullptr, &need_comb, ctx->main_stream));
-        const size_t need = std::max(need_sort, need_comb);
-        if (need > ctx->sort_tmp_bytes) {
-            if (ctx->d_sort_tmp) CK(cudaFree(ctx->d_sort_tmp));
-            ctx->d_sort_tmp = nullptr;
-            ctx->sort_tmp_bytes = need + need / 4;
-            CK(cudaMalloc(&ctx->d_sort_tmp, ctx->sort_tmp_bytes));
-        }
-        size_t bytes = ctx->sort_tmp_bytes;
-        CK(sort_entries_radix(ctx->d_concat, ctx->d_sorted, n, wide, ctx->d_sort_tmp, &bytes, ctx->main_stream));
-        bytes = ctx->sort_tmp_bytes;
-        CK(combine_sorted_rows(ctx->d_sorted, n, ctx->d_concat, ctx->d_n, ctx->d_sort_tmp, &bytes, ctx->main_stream));
-        CK(cudaMemcpyAsync(&n_out, ctx->d_n, sizeof(n_out), cudaMemcpyDeviceToHost, ctx->main_stream));
-        CK(cudaStreamSynchronize(ctx->main_stream));
-        ctx->stats.kernel_launches += (wide ? 11 : 8) + 3;
-    }
-    size_t need_host = (size_t)n_out * sizeof(trew_entry) + 64;
-    if (need_host > ctx->h_export_bytes) {
-        if (ctx->h_export) CK(cudaFreeHost(ctx->h_export));
-        ctx->h_export = nullptr;
-        size_t cap = std::max(need_host * 2, (size_t)1 << 20);
-        CK(cudaHostAlloc(&ctx->h_export, cap, cudaHostAllocDefault));
-        ctx->h_export_bytes = cap;
-    }
-    if (n_out) {
-        CK(cudaMemcpyAsync(ctx->h_export, ctx->d_concat, (size_t)n_out * sizeof(trew_entry), cudaMemcpyDeviceToHost, ctx->main_stream));
-        CK(cudaStreamSynchronize(ctx->main_stream));
-    }
-    ctx->stats.d2h_bytes += (uint64_t)n_out * sizeof(trew_entry) + 4;
-    if (entries) *entries = (const trew_entry*)ctx->h_export;
-    if (n_entries) *n_entries = n_out;
-    return TREW_OK;
+    return finish_rows(ctx, ctx->d_concat, total, true, entries, n_entries);
 }
 
 int trew_dev_export_rows(trew_ctx* ctx, trew_entry* d_rows, uint64_t capacity_rows, uint64_t* n_rows) {
@@ -955,6 +993,12 @@ int trew_dev_merge_rows(trew_ctx* ctx, const trew_entry* d_rows, uint64_t n_rows
     launch_merge_entries(ctx->dcfg, d_rows, (unsigned int)n_rows, ctx->main_stream);   // asynchronous: the next sync / export
     CK(cudaGetLastError());                                                             // waits and checks the error flag
     ctx->stats.kernel_launches += n_rows ? 1 : 0;
+    return TREW_OK;
+}
+
+int trew_dev_set_report_filter(trew_ctx* ctx, uint32_t min_total) {
+    if (!ctx) return TREW_ERR_ARG;
+    ctx->report_min = min_total;
     return TREW_OK;
 }
 
@@ -1223,6 +1267,11 @@ int trew_multi_finish(trew_multi* m, const trew_entry** entries, uint64_t* n_ent
     }
     int rc = trew_dev_finish_merged(x0, lists.data(), sizes.data(), (uint32_t)lists.size(), entries, n_entries);
     return rc == TREW_OK ? rc : mfail(m, rc, x0->err);
+}
+
+int trew_multi_set_report_filter(trew_multi* m, uint32_t min_total) {
+    if (!m) return TREW_ERR_ARG;
+    return trew_dev_set_report_filter(m->ctx[0], min_total);   // the first device copies the merged rows to the host
 }
 
 int trew_multi_get_stats(trew_multi* m, trew_stats* out) {

@@ -94,6 +94,10 @@ cudaError_t sort_entries_radix(const trew_entry* d_entries, trew_entry* d_out, u
 // sorted rows with repeated keys -> one row per key, counts summed (the union of several tables' rows)
 cudaError_t combine_sorted_rows(const trew_entry* d_sorted, unsigned int n, trew_entry* d_out, unsigned int* d_n_out, void* d_temp,
                                 size_t* temp_bytes, cudaStream_t stream);
+// the rows of groups (k, folded key) whose high- or low-class total reaches min_total (what the report of a one-file run
+// can show), order kept; d_temp == nullptr queries *temp_bytes
+cudaError_t filter_report_rows(const trew_entry* d_rows, unsigned int n, unsigned int min_total, trew_entry* d_out, unsigned int* d_n_out,
+                               void* d_temp, size_t* temp_bytes, cudaStream_t stream);
 // validity plane from n 12-byte records (u32 block position, u64 mask of invalid bases): clears those bits of val
 void launch_clear_invalid(unsigned int* val, const unsigned int* rec, unsigned int n, cudaStream_t stream);
 void launch_merge_entries(const DevCfg& cfg, const trew_entry* entries, unsigned int n, cudaStream_t stream);

@@ -170,4 +170,105 @@ cudaError_t combine_sorted_rows(const trew_entry* d_sorted, unsigned int n, trew
     return cudaGetLastError();
 }
 
+// ---- report filter: only the rows that can reach the report of a one-file run ------------------------------------------
+//
+// process_output prints an entry when forward + backward + both >= 10 (ABS_MIN_PRINT_COUNT, src/kmer.cpp:1615-1620) and
+// final_process_output scores entries with a sum >= 10, then looks the scored keys up in BOTH classes
+// (src/kmer.cpp:2604-2650, 2693-2761).  Every count of such an entry comes from rows whose key folds to the entry's
+// (k, min(seq, crc(seq))) -- forward / backward / both rows of either strand (src/kmer.cpp:1518-1549).  So a row
+// matters iff its GROUP (k, folded key), classes high and low taken together, has a per-class total >= min_total in at
+// least one class.  Groups are accumulated under a 64-bit fingerprint of (k, folded key): two groups that collide are
+// merged, which can only keep more rows (the host recomputes everything exactly from the rows it gets).
+// Most rows of a large file are one- and two-window repeats an N made (exactly as in the reference); none of them
+// prints, and without the filter they are most of the device-to-host copy.
+
+typedef unsigned __int128 u128;
+
+__device__ __forceinline__ u128 filt_canon(u128 w, int k) {
+    u128 best = w, cur = w;
+    const int sh = 2 * (k - 1);
+    for (int r = 1; r < k; r++) { cur = ((cur & 3) << sh) | (cur >> 2); best = cur < best ? cur : best; }
+    return best;
+}
+__device__ __forceinline__ u128 filt_fold(u128 w, int k) {   // min(w, canonical rotation of the reverse complement)
+    u128 r = 0, x = w;
+    for (int i = 0; i < k; i++) { r = (r << 2) | (3 - (x & 3)); x >>= 2; }
+    const u128 t = filt_canon(r, k);
+    // rows of the forward / backward tables hold canonical rotations; 'both' rows from the large-k path may not, and fold
+    // with their own canonical rotation's group
+    const u128 c = filt_canon(w, k);
+    return t < c ? t : c;
+}
+__device__ __forceinline__ u64 filt_tag(const trew_entry& e) {
+    const u128 f = filt_fold(((u128)e.seq_hi << 64) | e.seq_lo, e.k);
+    u64 x = (u64)f ^ ((u64)(f >> 64) * 0x9e3779b97f4a7c15ULL) ^ ((u64)e.k << 56);
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x | 1ULL;   // 0 = empty slot
+}
+
+struct FiltGroup { u64 tag; u32 tot[2]; };
+
+__global__ void filter_accumulate_kernel(const trew_entry* __restrict__ e, u32 n, FiltGroup* __restrict__ g, u32 gmask, u32 cap_add,
+                                         u64* __restrict__ tags) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u64 tag = filt_tag(e[i]);
+        tags[i] = tag;
+        const u32 add = (u32)(e[i].count < (u64)cap_add ? e[i].count : (u64)cap_add);   // saturating: only ">= min_total" matters
+        u32 s = (u32)(tag >> 20) & gmask;
+        for (;;) {
+            const u64 old = atomicCAS((unsigned long long*)&g[s].tag, 0ULL, (unsigned long long)tag);
+            if (old == 0ULL || old == tag) { atomicAdd(&g[s].tot[e[i].table & 1], add); break; }
+            s = (s + 1) & gmask;
+        }
+    }
+}
+
+__global__ void filter_flags_kernel(const trew_entry* __restrict__ e, u32 n, const FiltGroup* __restrict__ g, u32 gmask, u32 min_total,
+                                    const u64* __restrict__ tags, u32* __restrict__ flags) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u64 tag = tags[i];
+        u32 s = (u32)(tag >> 20) & gmask;
+        while (g[s].tag != tag) s = (s + 1) & gmask;
+        flags[i] = (g[s].tot[0] >= min_total || g[s].tot[1] >= min_total) ? 1u : 0u;
+    }
+}
+
+__global__ void filter_scatter_kernel(const trew_entry* __restrict__ e, u32 n, const u32* __restrict__ flags, const u32* __restrict__ pos,
+                                      trew_entry* __restrict__ out, u32* __restrict__ n_out) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (flags[i]) out[pos[i]] = e[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_out = n ? pos[n - 1] + flags[n - 1] : 0u;
+}
+
+// d_rows (n rows, any order) -> d_out: the rows of groups with a per-class total >= min_total, order kept.
+// d_temp == nullptr queries *temp_bytes.
+cudaError_t filter_report_rows(const trew_entry* d_rows, unsigned int n, unsigned int min_total, trew_entry* d_out, unsigned int* d_n_out,
+                               void* d_temp, size_t* temp_bytes, cudaStream_t stream) {
+    size_t scan_bytes = 0;
+    cudaError_t err = cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (u32*)nullptr, (u32*)nullptr, (int)n, stream);
+    if (err != cudaSuccess) return err;
+    size_t gslots = 1024;
+    while (gslots < (size_t)n * 2) gslots <<= 1;
+    const size_t need = align256(gslots * sizeof(FiltGroup)) + align256((size_t)n * 8) + 2 * align256((size_t)n * 4) + align256(scan_bytes);
+    if (!d_temp) { *temp_bytes = need; return cudaSuccess; }
+    if (*temp_bytes < need) return cudaErrorInvalidValue;
+    char* p = (char*)d_temp;
+    FiltGroup* g = (FiltGroup*)p; p += align256(gslots * sizeof(FiltGroup));
+    u64* tags = (u64*)p; p += align256((size_t)n * 8);
+    u32* flags = (u32*)p; p += align256((size_t)n * 4);
+    u32* pos = (u32*)p; p += align256((size_t)n * 4);
+    const int blocks = (int)std::min<unsigned int>((n + 255) / 256, 4736u);
+    err = cudaMemsetAsync(g, 0, gslots * sizeof(FiltGroup), stream);
+    if (err != cudaSuccess) return err;
+    if (n) {
+        filter_accumulate_kernel<<<blocks, 256, 0, stream>>>(d_rows, n, g, (u32)(gslots - 1), min_total, tags);
+        filter_flags_kernel<<<blocks, 256, 0, stream>>>(d_rows, n, g, (u32)(gslots - 1), min_total, tags, flags);
+    }
+    size_t sb = align256(scan_bytes);
+    err = cub::DeviceScan::ExclusiveSum(p, sb, flags, pos, (int)n, stream);
+    if (err != cudaSuccess) return err;
+    filter_scatter_kernel<<<n ? blocks : 1, 256, 0, stream>>>(d_rows, n, flags, pos, d_out, d_n_out);
+    return cudaGetLastError();
+}
+
 }  // namespace trew

@@ -176,6 +176,9 @@ int main(int argc, char** argv) {
         fprintf(stderr, "trew: cannot create device context: %s\n", why && *why ? why : trew_status_string(rc));
         return 1;
     }
+    // One input (file or pair): only rows that can reach the report leave the device (see trew_dev_set_report_filter);
+    // with several inputs every entry is needed, small counts add up across files (src/trew.cpp:454-467).
+    if (paths.size() == (cfg.mode == TREW_MODE_PAIR ? 2u : 1u) && !getenv("TREW_FULL_TABLES")) trew_multi_set_report_filter(ctx, 10);
     trew_report* rep = nullptr;
     trew_report_create(min_mer, &rep);
 
