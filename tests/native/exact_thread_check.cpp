@@ -70,4 +70,47 @@ long etc_scan_reads(const char* buf, const int32_t* locs, int n_reads, int min_m
     return i;
 }
 
+namespace {
+struct StringLoad {
+    Mem m; const char* s[2]; int n[2];
+    void operator()(int mate) const {
+        for (int j = 0; j < kReadWords + 2; j++) { m[W_RH + j] = 0; m[W_RL + j] = 0; m[W_RV + j] = 0; }
+        for (int i = 0; i < n[mate]; i++) {
+            const int c = code_of((unsigned char)s[mate][i]);
+            if (c >= 0) {
+                m[W_RV + (i >> 5)] |= 1u << (i & 31); m[W_RH + (i >> 5)] |= (u32)(c >> 1) << (i & 31);
+                m[W_RL + (i >> 5)] |= (u32)(c & 1) << (i & 31);
+            }
+        }
+    }
+};
+}  // namespace
+
+// the same for pairs (buffer_task_pair): mate i of pair r is locs{1,2}[2r .. 2r+1] in buf{1,2}
+long etc_scan_pairs(const char* buf1, const int32_t* locs1, const char* buf2, const int32_t* locs2, int n_pairs, int min_mer, int max_mer,
+                    const unsigned short* thr_low, const unsigned short* thr_high, int32_t* out_table, int32_t* out_k, uint64_t* out_key,
+                    uint64_t* out_count, long cap, long* n_bailed, int32_t* bailed_index) {
+    std::map<std::tuple<int, int, uint64_t>, uint64_t> tables;
+    Collect emit{&tables};
+    long bailed = 0;
+    for (int r = 0; r < n_pairs; r++) {
+        const int n1 = locs1[2 * r + 1] >= locs1[2 * r] ? locs1[2 * r + 1] - locs1[2 * r] + 1 : 0;
+        const int n2 = locs2[2 * r + 1] >= locs2[2 * r] ? locs2[2 * r + 1] - locs2[2 * r] + 1 : 0;
+        u32 work[kWorkWords];
+        memset(work, 0xA5, sizeof(work));
+        Mem m{work, 1};
+        StringLoad load{m, {buf1 + locs1[2 * r], buf2 + locs2[2 * r]}, {n1 <= kMaxRead ? n1 : 0, n2 <= kMaxRead ? n2 : 0}};
+        const bool ok = route_pair_thread(m, n1, n2, min_mer, max_mer, thr_low, thr_high, load, emit);
+        if (!ok) { if (bailed_index) bailed_index[bailed] = r; bailed++; }
+    }
+    if (n_bailed) *n_bailed = bailed;
+    if ((long)tables.size() > cap) return -1;
+    long i = 0;
+    for (auto& kv : tables) {
+        out_table[i] = std::get<0>(kv.first); out_k[i] = std::get<1>(kv.first); out_key[i] = std::get<2>(kv.first); out_count[i] = kv.second;
+        i++;
+    }
+    return i;
+}
+
 }  // extern "C"

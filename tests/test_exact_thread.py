@@ -24,6 +24,9 @@ def etc(tmp_path_factory):
     lib.etc_scan_reads.restype = C.c_long
     lib.etc_scan_reads.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_long, C.POINTER(C.c_long), C.c_void_p]
+    lib.etc_scan_pairs.restype = C.c_long
+    lib.etc_scan_pairs.argtypes = [C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.POINTER(C.c_long), C.c_void_p]
     return lib
 
 
@@ -84,3 +87,36 @@ def test_thread_path_limits(etc):
     got, bailed = run(etc, reads, 5, 32)
     assert bailed == [0, 1]
     assert got == Oracle(5, 32).scan(0, reads[2:]) and len(got) > 0
+
+
+def run_pairs(lib, r1, r2, mn, mx, low=0.5, high=0.8):
+    b1, l1 = api.make_chunk(r1)
+    b2, l2 = api.make_chunk(r2)
+    l1 = np.ascontiguousarray(l1, dtype=np.int32)
+    l2 = np.ascontiguousarray(l2, dtype=np.int32)
+    tl, th = thr_table(low), thr_table(high)
+    cap = 1 << 20
+    ot, ok = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    okey, oc = np.zeros(cap, np.uint64), np.zeros(cap, np.uint64)
+    nb = C.c_long(0)
+    bi = np.zeros(max(1, len(r1)), np.int32)
+    n = lib.etc_scan_pairs(b1.tobytes(), l1.ctypes.data, b2.tobytes(), l2.ctypes.data, len(r1), mn, mx, tl.ctypes.data, th.ctypes.data,
+                           ot.ctypes.data, ok.ctypes.data, okey.ctypes.data, oc.ctypes.data, cap, C.byref(nb), bi.ctypes.data)
+    assert n >= 0
+    return {(int(ot[i]), int(ok[i]), int(okey[i])): int(oc[i]) for i in range(n)}, [int(x) for x in bi[:nb.value]]
+
+
+@pytest.mark.parametrize("mn,mx,rl,trunc", [(5, 32, 150, 0.0), (5, 32, 150, 0.15), (5, 25, 120, 0.1), (3, 20, 100, 0.2), (7, 30, 160, 0.05)])
+def test_thread_pair_path_equals_oracle(etc, mn, mx, rl, trunc):
+    r1, r2 = synth.adversarial_pairs(400 + mx + rl, 1500, read_len=rl, max_unit=mx, truncate_mate2=trunc)
+    got, bailed = run_pairs(etc, r1, r2, mn, mx)
+    skip = set(bailed)
+    k1 = [r for i, r in enumerate(r1) if i not in skip]
+    k2 = [r for i, r in enumerate(r2) if i not in skip]
+    want = Oracle(mn, mx).scan(1, k1, k2)
+    assert got == want, (len(got), len(want), sorted(set(got.items()) ^ set(want.items()))[:6])
+    assert len(got) > 100
+    # only the limits bail: a mate longer than 160 bases, or the shorter mate below 4 * MAX_MER (and at least 2 * MIN_MER)
+    expect = [i for i, (a, b) in enumerate(zip(r1, r2))
+              if min(len(a), len(b)) >= 2 * mn and (max(len(a), len(b)) > 160 or min(len(a), len(b)) < 4 * mx)]
+    assert bailed == expect

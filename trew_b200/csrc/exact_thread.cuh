@@ -174,13 +174,15 @@ ET_FN int prepare_runs(Mem m, int nw, int k) {
 // approx: classes by base composition (#C|A, #G|A, #A of the run's first window) instead of by minimal rotation.
 // Rotation keeps the composition, so these classes are unions of the true ones and their largest total bounds the true
 // largest class from above -- at a fraction of the cost (no k-step rotation loop); used to turn away noisy windows.
-ET_FN int classify_runs(Mem m, int nw, int k, ClsSpill& x, bool approx) {
-    int n = 0, ord = 0;
+ET_FN int classify_runs(Mem m, int runs, int k, ClsSpill& x, bool approx) {
+    int n = 0, ord = 0, j = 0;
     const u32 km = lowmask(k);
-    for (int j = 0; j < nw; j++) {
-        const u32 wvj = m[W_WV + j];
-        u32 rr = m[W_RS + j];
-        while (rr) {
+    u32 wvj = m[W_WV], rr = m[W_RS];
+    // one loop over the runs, not one per plane word: the lanes of a warp then meet in the body for their r-th run
+    // wherever it lies (a per-word loop serialises lanes whose runs start in different words)
+    for (int r = 0; r < runs; r++) {
+        while (!rr) { ord += popc(wvj); j++; rr = m[W_RS + j]; wvj = m[W_WV + j]; }
+        {
             const int b = ffs1(rr);
             rr &= rr - 1;
             const u32 c0 = (u32)(ord + popc(wvj & ((1u << b) - 1u)));
@@ -210,7 +212,6 @@ ET_FN int classify_runs(Mem m, int nw, int k, ClsSpill& x, bool approx) {
                 else { x.key[s] = key; x.tot[s] = (unsigned short)cnt; x.last[s] = (unsigned short)last; n++; }
             }
         }
-        ord += popc(wvj);
     }
     return n;
 }
@@ -241,8 +242,11 @@ ET_HD void shrink_valid(Mem m, int nw) {   // valid k-windows -> valid (k+1)-win
     for (int j = 0; j < nw; j++) m[W_WV + j] &= (m[W_WV + j] >> 1) | (j + 1 < nw ? m[W_WV + j + 1] << 31 : 0u);
 }
 
-// k_mer_check without emission (src/kmer.cpp:2144-2258) on the current window: returns target_k_high | target_k_low << 8
-ET_FN u32 scan_window(Mem m, int len, int kmin, int kmax, const unsigned short* thr_low, const unsigned short* thr_high, ClsSpill& x) {
+// k_mer_check without emission (src/kmer.cpp:2144-2258) on the current window: returns target_k_high | target_k_low << 8;
+// S_h / S_l: the K_MER_DATA_MAX_SEQ of the two (the paired routing compares them between segments)
+ET_FN u32 scan_window(Mem m, int len, int kmin, int kmax, const unsigned short* thr_low, const unsigned short* thr_high, ClsSpill& x,
+                      u64& S_h, u64& S_l) {
+    S_h = S_l = 0;
     if (kmax > len) kmax = len;
     if (kmax < kmin) return 0u;
     const int nw = (len + 31) >> 5;
@@ -280,11 +284,12 @@ ET_FN u32 scan_window(Mem m, int len, int kmin, int kmax, const unsigned short* 
         U = U > c11 ? U : c11;
         if (!((!blkL && need_pass(thr_low, needL, U, T)) || (!blkH && need_pass(thr_high, needH, U, T)))) continue;
         u64 S;
-        if (prepare_runs(m, nw, k) > 3) {   // several runs: first the cheap bound from the runs' base compositions
-            const int Mu = cls_max(m, classify_runs(m, nw, k, x, true), x, S);
+        const int runs = prepare_runs(m, nw, k);
+        if (runs > 3) {   // several runs: first the cheap bound from the runs' base compositions
+            const int Mu = cls_max(m, classify_runs(m, runs, k, x, true), x, S);
             if (!((!blkL && need_pass(thr_low, needL, Mu, T)) || (!blkH && need_pass(thr_high, needH, Mu, T)))) continue;
         }
-        const int n = classify_runs(m, nw, k, x, false);
+        const int n = classify_runs(m, runs, k, x, false);
         const int M = cls_max(m, n, x, S);
         if (homo(S, k)) continue;
         const bool accL = !blkL && need_pass(thr_low, needL, M, T), accH = !blkH && need_pass(thr_high, needH, M, T);
@@ -292,8 +297,8 @@ ET_FN u32 scan_window(Mem m, int len, int kmin, int kmax, const unsigned short* 
             u64 mm = 0;
             for (int j = k; j < 64; j += k) mm |= 1ULL << j;
             const u32 need = (u32)M | ((u32)T << 16);
-            if (accL) { res = (res & 0xffu) | ((u32)k << 8); needL = need; blockedL |= mm; }
-            if (accH) { res = (res & 0xff00u) | (u32)k; needH = need; blockedH |= mm; }
+            if (accL) { res = (res & 0xffu) | ((u32)k << 8); needL = need; blockedL |= mm; S_l = S; }
+            if (accH) { res = (res & 0xff00u) | (u32)k; needH = need; blockedH |= mm; S_h = S; }
         }
     }
     return res;
@@ -314,8 +319,9 @@ ET_HD bool route_short_thread(Mem m, int n, u32 pm, int min_mer, int max_mer, co
     const int llen = n / 2, rlen = (n + 1) / 2, roff = n - rlen;
     ClsSpill x;
     u32 L = 0, R = 0;   // target_k_high | target_k_low << 8 of the two halves
-    if (pm & 1u) { set_window(m, 0, llen); L = scan_window(m, llen, min_mer, kmax, thr_low, thr_high, x); }
-    if (pm & 2u) { set_window(m, roff, rlen); R = scan_window(m, rlen, min_mer, kmax, thr_low, thr_high, x); }   // "always evaluated"
+    u64 sh, sl;
+    if (pm & 1u) { set_window(m, 0, llen); L = scan_window(m, llen, min_mer, kmax, thr_low, thr_high, x, sh, sl); }
+    if (pm & 2u) { set_window(m, roff, rlen); R = scan_window(m, rlen, min_mer, kmax, thr_low, thr_high, x, sh, sl); }   // "always evaluated"
     if ((L | R) == 0u) return true;
     // right-half emissions survive only for classes where the left half found nothing (src/kmer.cpp:123-159)
     int cur_win = -1, cur_k = 0, ncls = 0, T = 0;   // the evaluation in the workspace
@@ -334,7 +340,7 @@ ET_HD bool route_short_thread(Mem m, int n, u32 pm, int min_mer, int max_mer, co
             T = 0;
             for (int j = 0; j < nw; j++) T += popc(m[W_WV + j]);
             ncls = 0;
-            if (T) { prepare_runs(m, nw, k); ncls = classify_runs(m, nw, k, x, false); }
+            if (T) ncls = classify_runs(m, prepare_runs(m, nw, k), k, x, false);
             cur_win = win; cur_k = k;
         }
         if (T == 0) continue;
@@ -349,6 +355,113 @@ ET_HD bool route_short_thread(Mem m, int n, u32 pm, int min_mer, int max_mer, co
             const u64 cnt = q < kClsCap ? (u64)m[W_CTOT + q] : (u64)x.tot[q - kClsCap];
             if (target) { const u64 t = crc(key, k); key = t < key ? t : key; }
             emit(table, k, key, cnt);
+        }
+    }
+    return true;
+}
+
+// every class of (current window, k) into `table`, RC-folded on request: the emission half of k_mer_check
+// (src/kmer.cpp:2264-2328)
+template <class Emit>
+ET_HD void emit_window_classes(Mem m, int len, int k, int table, bool folded, ClsSpill& x, Emit& emit) {
+    const int nw = (len + 31) >> 5;
+    for (int j = 0; j < nw; j++) m[W_WV + j] = m[W_V + j];
+    for (int t = 1; t < k; t++) shrink_valid(m, nw);
+    int T = 0;
+    for (int j = 0; j < nw; j++) T += popc(m[W_WV + j]);
+    if (T == 0) return;
+    const int ncls = classify_runs(m, prepare_runs(m, nw, k), k, x, false);
+    for (int q = 0; q < ncls; q++) {
+        u64 key = q < kClsCap ? cls_key(m, q) : x.key[q - kClsCap];
+        const u64 cnt = q < kClsCap ? (u64)m[W_CTOT + q] : (u64)x.tot[q - kClsCap];
+        if (folded) { const u64 t = crc(key, k); key = t < key ? t : key; }
+        emit(table, k, key, cnt);
+    }
+}
+
+// buffer_task_pair for one pair (src/kmer.cpp:268-745; the 128-bit path's semantics where the two differ, like the warp
+// kernel's route_pair, which this mirrors statement by statement).  load(mate) brings that mate's planes into W_RH /
+// W_RL / W_RV.  Limits: both mates <= 160 bases, MAX_MER <= 32, min(n1, n2) >= 4 * MAX_MER (so the large-k block of
+// src/kmer.cpp:467-505 never runs); false = outside them, nothing emitted.
+template <class Load, class Emit>
+ET_HD bool route_pair_thread(Mem m, int n1, int n2, int min_mer, int max_mer, const unsigned short* thr_low,
+                             const unsigned short* thr_high, Load& load, Emit& emit) {
+    const int n = n1 < n2 ? n1 : n2;
+    if (n < 2 * min_mer) return true;
+    if (max_mer > 32 || n1 > kMaxRead || n2 > kMaxRead || 4 * max_mer > n) return false;
+    const int kmax = n / 4 < max_mer ? n / 4 : max_mer;
+    // segments in fragment order: R1 left, R1 right, R2 right, R2 left (src/kmer.cpp:338-340)
+    const int soff[5] = {0, 0, n1 - (n1 + 1) / 2, n2 - (n2 + 1) / 2, 0};
+    const int slen[5] = {0, n1 / 2, (n1 + 1) / 2, (n2 + 1) / 2, n2 / 2};
+    ClsSpill x;
+    u32 res[5] = {0, 0, 0, 0, 0};
+    u64 S[5][2];
+    bool have[5] = {false, false, false, false, false};
+    int cur_mate = -1;
+    auto window = [&](int t) {
+        const int mate = t <= 2 ? 0 : 1;
+        if (cur_mate != mate) { load(mate); cur_mate = mate; }
+        set_window(m, soff[t], slen[t]);
+    };
+    auto scan = [&](int t) {
+        if (have[t]) return;
+        window(t);
+        res[t] = scan_window(m, slen[t], min_mer, kmax, thr_low, thr_high, x, S[t][0], S[t][1]);
+        have[t] = true;
+    };
+    // pending emissions per class: segment + temp map id (0 = left, 1 = right)
+    int pseg[2][8], ptmp[2][8], np[2] = {0, 0};
+    int si[2] = {1, 1}, km[2] = {0, 0};
+    bool ended[2] = {false, false};
+    u64 ks[2] = {0, 0};
+    for (int ti = 1; ti <= 4 && !(ended[0] && ended[1]); ti++) {   // forward walk
+        scan(ti);
+        for (int c = 0; c < 2; c++) {
+            const int k = (int)((res[ti] >> (8 * c)) & 0xffu);
+            if (!ended[c] && k) { pseg[c][np[c]] = ti; ptmp[c][np[c]] = ti <= 2 ? 0 : 1; np[c]++; }   // emission before the test
+            bool ok = !ended[c] && k > 0;
+            if (ok && ti != 1) {
+                const u64 ds = ti > 2 ? crc(S[ti][c], k) : S[ti][c];   // get_dir_seq, src/kmer.cpp:307-313
+                ok = km[c] == k && ks[c] == ds;
+            }
+            if (ok) { si[c]++; km[c] = k; if (ti == 1) ks[c] = S[ti][c]; }
+            else ended[c] = true;
+        }
+    }
+    for (int c = 0; c < 2; c++) {
+        if (si[c] == 5) {   // every segment agreed: everything into 'both', RC-folded (src/kmer.cpp:378-399)
+            for (int e = 0; e < np[c]; e++) {
+                const int sg = pseg[c][e];
+                window(sg);
+                emit_window_classes(m, slen[sg], (int)((res[sg] >> (8 * c)) & 0xffu), T_O + c, true, x, emit);
+            }
+        }
+    }
+    if (si[0] <= 4 || si[1] <= 4) {   // backward walk (src/kmer.cpp:401-436), temps swapped
+        int sj[2] = {4, 4};
+        km[0] = km[1] = 0; ended[0] = ended[1] = false;
+        for (int tj = 4; tj >= 1 && !(ended[0] && ended[1]); tj--) {
+            scan(tj);
+            for (int c = 0; c < 2; c++) {
+                const int k = (int)((res[tj] >> (8 * c)) & 0xffu);
+                if (!ended[c] && k) { pseg[c][np[c]] = tj; ptmp[c][np[c]] = tj <= 2 ? 1 : 0; np[c]++; }
+                bool ok = sj[c] >= si[c] && !ended[c] && k > 0;
+                if (ok && tj != 4) {
+                    const u64 ds = tj <= 2 ? crc(S[tj][c], k) : S[tj][c];
+                    ok = km[c] == k && ks[c] == ds;
+                }
+                if (ok) { sj[c]--; km[c] = k; if (tj == 4) ks[c] = S[tj][c]; }
+                else ended[c] = true;
+            }
+        }
+    }
+    for (int c = 0; c < 2; c++) {
+        if (si[c] <= 4) {   // forward += left temp, backward += right temp (src/kmer.cpp:438-455)
+            for (int e = 0; e < np[c]; e++) {
+                const int sg = pseg[c][e];
+                window(sg);
+                emit_window_classes(m, slen[sg], (int)((res[sg] >> (8 * c)) & 0xffu), (ptmp[c][e] == 0 ? T_F : T_B) + c, false, x, emit);
+            }
         }
     }
     return true;

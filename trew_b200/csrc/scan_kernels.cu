@@ -710,7 +710,13 @@ __global__ void __launch_bounds__(256) trew_filter_kernel(DevCfg cfg, DevBatch b
             // warp kernel's comp_bound).  Both kernels are exact for every read; the split only places the work.
             bool to_b = false;
             if (maybe) {
-                const int len = (int)(__ldg(b.bit_off + u + 1) - __ldg(b.bit_off + u));
+                int len;
+                if (cfg.mode == 1) {
+                    const u32 a0 = __ldg(b.bit_off + 2 * u), a1 = __ldg(b.bit_off + 2 * u + 1), a2 = __ldg(b.bit_off + 2 * u + 2);
+                    len = (int)max(a1 - a0, a2 - a1);
+                } else {
+                    len = (int)(__ldg(b.bit_off + u + 1) - __ldg(b.bit_off + u));
+                }
                 to_b = len > et::kMaxRead || t_hit < kThreadMinWindows;
             }
             list_append(maybe && !to_b, entry, survivors, n_survivors);
@@ -1685,7 +1691,23 @@ struct StageEmit {
 #endif
 constexpr size_t kThreadKernelSmem = (size_t)et::kWorkWords * TREW_THREAD_BLOCK * sizeof(u32) + (size_t)kStageSlots * 16;
 
-__global__ void __launch_bounds__(TREW_THREAD_BLOCK) trew_exact_thread_kernel(DevCfg cfg, DevBatch b, const u32* __restrict__ survivors,
+// brings one read's planes (bit offset b0, len bases) into the thread's workspace
+struct PlaneLoad {
+    et::Mem m; const u32 *hi, *lo, *val; u32 b0[2]; int len[2];
+    __device__ __forceinline__ void operator()(int mate) const {
+        const u32 w0 = b0[mate] >> 5, sh = b0[mate] & 31u;
+        const int n = len[mate];
+        for (int j = 0; j < et::kReadWords + 2; j++) {
+            const u32 msk = low_mask(min(32, max(0, n - 32 * j)));
+            m[et::W_RH + j] = __funnelshift_r(__ldg(hi + w0 + j), __ldg(hi + w0 + j + 1), sh) & msk;
+            m[et::W_RL + j] = __funnelshift_r(__ldg(lo + w0 + j), __ldg(lo + w0 + j + 1), sh) & msk;
+            m[et::W_RV + j] = __funnelshift_r(__ldg(val + w0 + j), __ldg(val + w0 + j + 1), sh) & msk;
+        }
+    }
+};
+
+template <int MODE>   // 0 short single-end, 1 paired
+__global__ void __launch_bounds__(TREW_THREAD_BLOCK, 4) trew_exact_thread_kernel(DevCfg cfg, DevBatch b, const u32* __restrict__ survivors,
                                                                               const u32* __restrict__ n_survivors, int packed_probes,
                                                                               u32* __restrict__ hard, u32* __restrict__ n_hard,
                                                                               unsigned long long* total_survivors, u32 exp_flags) {
@@ -1709,23 +1731,22 @@ __global__ void __launch_bounds__(TREW_THREAD_BLOCK) trew_exact_thread_kernel(De
             entry = survivors[i];
             u32 u = entry, pm = 3u;
             if (packed_probes) { pm = entry >> kProbeShift; u &= (1u << kProbeShift) - 1u; }
-            const u32 b0 = __ldg(b.bit_off + u);
-            const int len = (int)(__ldg(b.bit_off + u + 1) - b0);
-            if (len > et::kMaxRead) {
-                bail = true;
-            } else {
-                const u32 w0 = b0 >> 5, sh = b0 & 31u;
-                u32 invalid = 0;
-                for (int j = 0; j < et::kReadWords + 2; j++) {
-                    const u32 msk = low_mask(min(32, max(0, len - 32 * j)));
-                    const u32 v = __funnelshift_r(__ldg(b.val + w0 + j), __ldg(b.val + w0 + j + 1), sh) & msk;
-                    m[et::W_RH + j] = __funnelshift_r(__ldg(b.hi + w0 + j), __ldg(b.hi + w0 + j + 1), sh) & msk;
-                    m[et::W_RL + j] = __funnelshift_r(__ldg(b.lo + w0 + j), __ldg(b.lo + w0 + j + 1), sh) & msk;
-                    m[et::W_RV + j] = v;
-                    invalid |= v ^ msk;
+            (void)exp_flags;
+            if (MODE == 0) {
+                const u32 b0 = __ldg(b.bit_off + u);
+                const int len = (int)(__ldg(b.bit_off + u + 1) - b0);
+                if (len > et::kMaxRead) {
+                    bail = true;
+                } else {
+                    PlaneLoad load{m, b.hi, b.lo, b.val, {b0, 0u}, {len, 0}};
+                    load(0);
+                    bail = !et::route_short_thread(m, len, pm & 3u, cfg.min_mer, cfg.max_mer, cfg.thr_low, cfg.thr_high, emit);
                 }
-                (void)invalid; (void)exp_flags;
-                bail = !et::route_short_thread(m, len, pm & 3u, cfg.min_mer, cfg.max_mer, cfg.thr_low, cfg.thr_high, emit);
+            } else {
+                const u32 a0 = __ldg(b.bit_off + 2 * u), a1 = __ldg(b.bit_off + 2 * u + 1), a2 = __ldg(b.bit_off + 2 * u + 2);
+                const int n1 = (int)(a1 - a0), n2 = (int)(a2 - a1);
+                PlaneLoad load{m, b.hi, b.lo, b.val, {a0, a1}, {n1, n2}};
+                bail = !et::route_pair_thread(m, n1, n2, cfg.min_mer, cfg.max_mer, cfg.thr_low, cfg.thr_high, load, emit);
             }
         }
         list_append(bail, entry, hard, n_hard);
@@ -1738,16 +1759,20 @@ __global__ void __launch_bounds__(TREW_THREAD_BLOCK) trew_exact_thread_kernel(De
     }
 }
 
-// true when the thread kernel can take (most of) a batch: short single-end mode, 64-bit units
+// true when the thread kernel can take (most of) a batch: short single-end or paired mode, 64-bit units
 bool thread_path_applies(const DevCfg& cfg, unsigned int max_read_len) {
-    return cfg.mode == 0 && cfg.max_mer <= 32 && max_read_len >= 4u * (unsigned)cfg.max_mer;
+    return (cfg.mode == 0 || cfg.mode == 1) && cfg.max_mer <= 32 && max_read_len >= 4u * (unsigned)cfg.max_mer;
 }
 
 void launch_exact_thread(const DevCfg& cfg, const DevBatch& b, const unsigned int* survivors, const unsigned int* n_survivors,
                          int packed_probes, unsigned int* hard, unsigned int* n_hard, unsigned long long* total_survivors, int blocks,
                          unsigned int exp_flags, cudaStream_t stream) {
-    trew_exact_thread_kernel<<<blocks, TREW_THREAD_BLOCK, kThreadKernelSmem, stream>>>(cfg, b, survivors, n_survivors, packed_probes, hard,
-                                                                                       n_hard, total_survivors, exp_flags);
+    if (cfg.mode == 0)
+        trew_exact_thread_kernel<0><<<blocks, TREW_THREAD_BLOCK, kThreadKernelSmem, stream>>>(cfg, b, survivors, n_survivors, packed_probes,
+                                                                                              hard, n_hard, total_survivors, exp_flags);
+    else
+        trew_exact_thread_kernel<1><<<blocks, TREW_THREAD_BLOCK, kThreadKernelSmem, stream>>>(cfg, b, survivors, n_survivors, packed_probes,
+                                                                                              hard, n_hard, total_survivors, exp_flags);
 }
 
 template <int MODE>
@@ -1784,7 +1809,8 @@ cudaError_t prepare_exact(int run_cap_max) {
     cudaError_t e = cudaFuncSetAttribute(trew_exact_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(trew_exact_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(trew_exact_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(trew_exact_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kThreadKernelSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(trew_exact_thread_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kThreadKernelSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(trew_exact_thread_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kThreadKernelSmem);
     return e;
 }
 
