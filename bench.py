@@ -412,8 +412,29 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline()
         if world == 1 and not args.no_shapes:
             line["configs"] = other_shapes(api, local_rank, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)))
+    # weak scaling beside it (N > 1): every GPU holds the full 200 M reads
+    if world > 1 and strong and not args.no_weak:
+        reads_left = args.reads - reads_rank
+        while reads_left > 0:
+            n = min(BATCH_READS, reads_left)
+            handles.append((ctx.synth_resident(1 + 1000 * rank + i, n, READ_LEN, **SYNTH), n))
+            reads_left -= n
+            i += 1
+        ctx.set_report_filter(0 if args.full_tables else 10)
+        step()
+        barrier()
+        ctx.timer_start()
+        for _ in range(3):
+            step()
+        weak_ms = max_over_ranks(ctx.timer_stop()) / 3
+        barrier()
+        if rank == 0:
+            line["weak_scaling"] = {"value": world * args.reads * READ_LEN / (weak_ms * 1e-3) / 1e9, "unit": "Gbases/s",
+                                    "ms_per_step": weak_ms, "reads_per_gpu": args.reads,
+                                    "note": "the same step with 200 M reads on EVERY GPU (round 1's definition)"}
     for h, _ in handles:
         ctx.free_resident(h)
+    merge.forget(ctx)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -545,6 +566,7 @@ def main():
     ap.add_argument("--e2e-reads", type=int, default=8_000_000, help="reads per GPU and end-to-end step (host buffers)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--full-tables", action="store_true", help="time the steps with every table row copied to the host (no report filter)")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling figure beside the strong one")
     ap.add_argument("--no-shapes", action="store_true", help="skip the paired / long / 3-64 shapes (configs[2..4])")
     args = ap.parse_args()
     # stdout carries exactly one JSON line (rank 0): native libraries that print there (NCCL's version banner)

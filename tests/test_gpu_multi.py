@@ -90,3 +90,18 @@ def test_multi_process_file_and_cli(tmp_path):
         env = dict(os.environ, TREW_DEVICES=spec)
         outs.append(subprocess.run([api.CLI_PATH, "short", "5", "32", plain, gz], capture_output=True, check=True, env=env).stdout)
     assert outs[0] == outs[1] == outs[2] and outs[0].count(b"\n") > 6
+
+
+def test_nccl_merge_across_ranks():
+    """One process per GPU: merge.finish_merged over NCCL gives rank 0 the tables of one context scanning everything
+    (tools/merge_check.py under torchrun; needs at least two GPUs, so the single-GPU box skips it)."""
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 4)),
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "merge_check.py")],
+                       capture_output=True, timeout=600)
+    assert r.returncode == 0 and b"merge_check ok" in r.stdout, r.stderr.decode()[-2000:]
