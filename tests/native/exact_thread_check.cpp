@@ -54,7 +54,7 @@ long etc_scan_reads(const char* buf, const int32_t* locs, int n_reads, int min_m
                     m[W_RL + (i >> 5)] |= (u32)(c & 1) << (i & 31);
                 }
             }
-            ok = route_short_thread(m, n, 3u, min_mer, max_mer, thr_low, thr_high, emit);
+            ok = route_short_thread(m, n, 7u, min_mer, max_mer, thr_low, thr_high, emit);
         } else {
             ok = n < 2 * min_mer;
         }

@@ -69,7 +69,7 @@ def test_thread_path_equals_oracle(etc, mn, mx, low, high, lengths):
     want = Oracle(mn, mx, low, high).scan(0, keep)
     assert got == want, (len(got), len(want), sorted(set(got.items()) ^ set(want.items()))[:6])
     assert len(got) > 100
-    assert bailed == [i for i, r in enumerate(reads) if len(r) >= 2 * mn and (len(r) > 160 or len(r) < 4 * mx)]   # only the length limits
+    assert bailed == [i for i, r in enumerate(reads) if len(r) > 160]   # only the length limit
 
 
 def test_thread_path_on_the_bench_distribution(etc):
@@ -81,12 +81,24 @@ def test_thread_path_on_the_bench_distribution(etc):
     assert bailed == []
 
 
-def test_thread_path_limits(etc):
-    # shorter than 4 * MAX_MER (the large-k whole-read scan would run), longer than 160 bases: bail
-    reads = [b"TTAGGG" * 20, b"TTAGGG" * 30, b"ACGT" * 2, b"TTAGGG" * 25]
+def test_thread_path_limits_and_short_reads(etc):
+    # longer than 160 bases: bail; shorter than 4 * MAX_MER: the whole-read scan for the large periods runs here too
+    reads = [b"TTAGGG" * 20, b"TTAGGG" * 30, b"ACGT" * 2, b"TTAGGG" * 25, (b"TTAGGGATCGATCGGCTAGCTAGGACT" * 5)[:100], b"ACGTTGCA" * 2,
+             b"TTAGGG" * 3, (b"GATTACAGATTACCGATTAC" * 4)[:70]]
     got, bailed = run(etc, reads, 5, 32)
-    assert bailed == [0, 1]
-    assert got == Oracle(5, 32).scan(0, reads[2:]) and len(got) > 0
+    assert bailed == [1]
+    assert got == Oracle(5, 32).scan(0, [r for i, r in enumerate(reads) if i != 1]) and len(got) > 3
+
+
+@pytest.mark.parametrize("mn,mx,lengths", [(5, 32, [100, 100, 75, 50, 36, 20, 12, 9]), (3, 30, [60, 90, 119, 121, 11, 6]), (7, 24, [95, 97, 40, 28, 27])])
+def test_thread_path_short_reads_equal_oracle(etc, mn, mx, lengths):
+    """Reads below 4 * MAX_MER: the large-k whole-read scan (src/kmer.cpp:165-171) and every guard (n < 2 MIN, n < 4 MIN)."""
+    reads = synth.adversarial_short(700 + mn + mx, 3000, max_unit=mx, lengths=lengths)
+    got, bailed = run(etc, reads, mn, mx)
+    assert bailed == []
+    want = Oracle(mn, mx).scan(0, reads)
+    assert got == want, (len(got), len(want), sorted(set(got.items()) ^ set(want.items()))[:6])
+    assert len(got) > 100
 
 
 def run_pairs(lib, r1, r2, mn, mx, low=0.5, high=0.8):

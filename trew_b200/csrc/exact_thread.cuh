@@ -16,8 +16,7 @@
 // this very file against the oracle without a GPU (stride 1, base = a plain array).
 //
 // Limits (anything else is handed to the warp kernel through the `false` return, before anything was emitted):
-// 4 * MAX_MER <= read length <= 160 (so the large-k whole-read scan of src/kmer.cpp:165-171 never runs) and
-// MAX_MER <= 32 (64-bit units).
+// reads of at most 160 bases and MAX_MER <= 32 (64-bit units); pairs additionally min(n1, n2) >= 4 * MAX_MER.
 #pragma once
 #include <stdint.h>
 
@@ -306,22 +305,42 @@ ET_FN u32 scan_window(Mem m, int len, int kmin, int kmax, const unsigned short* 
 
 enum { T_F = 0, T_B = 2, T_O = 4 };
 
+template <class Emit>
+ET_HD void emit_window_classes(Mem m, int len, int k, int table, bool folded, ClsSpill& x, Emit& emit);
+
 // buffer_task for one read (src/kmer.cpp:111-171).  The read's planes are in W_RH / W_RL / W_RV (zero beyond base n).
-// pm: probes (bit 0 left half, bit 1 right half) the filter kernels could not rule out; the scan of any other window
-// finds nothing.  emit(table, k, key, count) receives the emissions.  Returns false when the read is outside this
+// pm: probes (unit_probes order: left half, right half, whole read -- or the whole read alone when n < 4 * MIN_MER)
+// the filter kernels could not rule out; the scan of any other window finds nothing.  emit(table, k, key, count) receives the emissions.  Returns false when the read is outside this
 // path's limits: then nothing was emitted and the warp kernel has to take it.
 template <class Emit>
 ET_HD bool route_short_thread(Mem m, int n, u32 pm, int min_mer, int max_mer, const unsigned short* thr_low,
                               const unsigned short* thr_high, Emit& emit) {
     if (n < 2 * min_mer) return true;                                   // src/kmer.cpp:113
-    if (max_mer > 32 || n > kMaxRead || 4 * max_mer > n) return false;   // outside the limits (n >= 4 * MIN follows)
+    if (max_mer > 32 || n > kMaxRead) return false;                      // outside the limits
     const int kmax = n / 4 < max_mer ? n / 4 : max_mer;
     const int llen = n / 2, rlen = (n + 1) / 2, roff = n - rlen;
     ClsSpill x;
     u32 L = 0, R = 0;   // target_k_high | target_k_low << 8 of the two halves
     u64 sh, sl;
-    if (pm & 1u) { set_window(m, 0, llen); L = scan_window(m, llen, min_mer, kmax, thr_low, thr_high, x, sh, sl); }
-    if (pm & 2u) { set_window(m, roff, rlen); R = scan_window(m, rlen, min_mer, kmax, thr_low, thr_high, x, sh, sl); }   // "always evaluated"
+    const bool halves = n >= 4 * min_mer;
+    if (halves && (pm & 1u)) { set_window(m, 0, llen); L = scan_window(m, llen, min_mer, kmax, thr_low, thr_high, x, sh, sl); }
+    if (halves && (pm & 2u)) { set_window(m, roff, rlen); R = scan_window(m, rlen, min_mer, kmax, thr_low, thr_high, x, sh, sl); }   // "always evaluated"
+    if (4 * max_mer > n) {
+        // short reads: periods above n / 4 are looked for in the whole read, for the selections that found nothing in
+        // either half; their classes go into 'both' UN-folded (src/kmer.cpp:165-171).  The probe of this scan is bit 2
+        // when the halves were probed (bits 0, 1), bit 0 when the read is too short for halves.
+        const bool hc0 = ((L | R) & 0xffu) == 0u, hc1 = ((L | R) >> 8) == 0u;
+        const u32 wbit = halves ? 4u : 1u;
+        if ((hc0 || hc1) && (pm & wbit)) {
+            const int lo = n / 4 + 1 > min_mer ? n / 4 + 1 : min_mer, hi = n / 2 < max_mer ? n / 2 : max_mer;
+            set_window(m, 0, n);
+            const u32 W = scan_window(m, n, lo, hi, thr_low, thr_high, x, sh, sl);
+            for (int c = 0; c < 2; c++) {
+                const int k = (int)((W >> (8 * c)) & 0xffu);
+                if ((c == 0 ? hc0 : hc1) && k) { set_window(m, 0, n); emit_window_classes(m, n, k, T_O + c, false, x, emit); }
+            }
+        }
+    }
     if ((L | R) == 0u) return true;
     // right-half emissions survive only for classes where the left half found nothing (src/kmer.cpp:123-159)
     int cur_win = -1, cur_k = 0, ncls = 0, T = 0;   // the evaluation in the workspace

@@ -1740,7 +1740,7 @@ __global__ void __launch_bounds__(TREW_THREAD_BLOCK, 4) trew_exact_thread_kernel
                 } else {
                     PlaneLoad load{m, b.hi, b.lo, b.val, {b0, 0u}, {len, 0}};
                     load(0);
-                    bail = !et::route_short_thread(m, len, pm & 3u, cfg.min_mer, cfg.max_mer, cfg.thr_low, cfg.thr_high, emit);
+                    bail = !et::route_short_thread(m, len, pm & 7u, cfg.min_mer, cfg.max_mer, cfg.thr_low, cfg.thr_high, emit);
                 }
             } else {
                 const u32 a0 = __ldg(b.bit_off + 2 * u), a1 = __ldg(b.bit_off + 2 * u + 1), a2 = __ldg(b.bit_off + 2 * u + 2);
@@ -1761,7 +1761,9 @@ __global__ void __launch_bounds__(TREW_THREAD_BLOCK, 4) trew_exact_thread_kernel
 
 // true when the thread kernel can take (most of) a batch: short single-end or paired mode, 64-bit units
 bool thread_path_applies(const DevCfg& cfg, unsigned int max_read_len) {
-    return (cfg.mode == 0 || cfg.mode == 1) && cfg.max_mer <= 32 && max_read_len >= 4u * (unsigned)cfg.max_mer;
+    if (cfg.max_mer > 32) return false;
+    if (cfg.mode == 0) return true;
+    return cfg.mode == 1 && max_read_len >= 4u * (unsigned)cfg.max_mer;   // pairs below 4 * MAX_MER all take the large-k block
 }
 
 void launch_exact_thread(const DevCfg& cfg, const DevBatch& b, const unsigned int* survivors, const unsigned int* n_survivors,
