@@ -113,4 +113,59 @@ long etc_scan_pairs(const char* buf1, const int32_t* locs1, const char* buf2, co
     return i;
 }
 
+namespace {
+struct OffsetLoad {   // bases [off, off + len) of one read
+    Mem m; const char* s;
+    void operator()(int off, int len) const {
+        for (int j = 0; j < kReadWords + 2; j++) { m[W_RH + j] = 0; m[W_RL + j] = 0; m[W_RV + j] = 0; }
+        for (int i = 0; i < len; i++) {
+            const int c = code_of((unsigned char)s[off + i]);
+            if (c >= 0) {
+                m[W_RV + (i >> 5)] |= 1u << (i & 31); m[W_RH + (i >> 5)] |= (u32)(c >> 1) << (i & 31);
+                m[W_RL + (i >> 5)] |= (u32)(c & 1) << (i & 31);
+            }
+        }
+    }
+};
+}  // namespace
+
+// long reads (buffer_task_long) through the three steps of the thread path, run one after the other per read
+long etc_scan_long(const char* buf, const int32_t* locs, int n_reads, int min_mer, int max_mer, int slice_len, const unsigned short* thr_low,
+                   const unsigned short* thr_high, int32_t* out_table, int32_t* out_k, uint64_t* out_key, uint64_t* out_count, long cap,
+                   long* n_bailed, int32_t* bailed_index) {
+    std::map<std::tuple<int, int, uint64_t>, uint64_t> tables;
+    Collect emit{&tables};
+    long bailed = 0;
+    for (int r = 0; r < n_reads; r++) {
+        const int st = locs[2 * r], n = locs[2 * r + 1] >= st ? locs[2 * r + 1] - st + 1 : 0;
+        if (n < slice_len) continue;   // the reader drops these (src/kmer.cpp:1184)
+        u32 work[kWorkWords];
+        memset(work, 0xA5, sizeof(work));
+        Mem m{work, 1};
+        OffsetLoad load{m, buf + st};
+        ClsSpill x;
+        bool ok = max_mer <= 32 && slice_len <= kMaxRead;
+        if (ok) {
+            LongGeom g(n, slice_len);
+            std::vector<u32> stats((size_t)g.snum + 1, 0u);
+            for (int t = 1; t <= g.snum; t++)
+                if (g.len(t) <= kMaxRead) stats[(size_t)t] = long_slice_stats(m, g, t, min_mer, max_mer, thr_low, thr_high, load, x);
+            std::vector<LongTask> tasks;
+            auto stat = [&](int t) { return stats[(size_t)t]; };
+            auto task = [&](const LongTask& tk) { tasks.push_back(tk); };
+            ok = long_walk(g, stat, task);
+            if (ok) for (const LongTask& tk : tasks) long_emit(m, g, tk, load, x, emit);
+        }
+        if (!ok) { if (bailed_index) bailed_index[bailed] = r; bailed++; }
+    }
+    if (n_bailed) *n_bailed = bailed;
+    if ((long)tables.size() > cap) return -1;
+    long i = 0;
+    for (auto& kv : tables) {
+        out_table[i] = std::get<0>(kv.first); out_k[i] = std::get<1>(kv.first); out_key[i] = std::get<2>(kv.first); out_count[i] = kv.second;
+        i++;
+    }
+    return i;
+}
+
 }  // extern "C"

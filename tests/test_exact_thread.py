@@ -24,6 +24,9 @@ def etc(tmp_path_factory):
     lib.etc_scan_reads.restype = C.c_long
     lib.etc_scan_reads.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_long, C.POINTER(C.c_long), C.c_void_p]
+    lib.etc_scan_long.restype = C.c_long
+    lib.etc_scan_long.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.POINTER(C.c_long), C.c_void_p]
     lib.etc_scan_pairs.restype = C.c_long
     lib.etc_scan_pairs.argtypes = [C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.POINTER(C.c_long), C.c_void_p]
@@ -132,3 +135,31 @@ def test_thread_pair_path_equals_oracle(etc, mn, mx, rl, trunc):
     expect = [i for i, (a, b) in enumerate(zip(r1, r2))
               if min(len(a), len(b)) >= 2 * mn and (max(len(a), len(b)) > 160 or min(len(a), len(b)) < 4 * mx)]
     assert bailed == expect
+
+
+def run_long(lib, reads, mn, mx, sl, low=0.5, high=0.8):
+    buf, locs = api.make_chunk(reads)
+    locs = np.ascontiguousarray(locs, dtype=np.int32)
+    tl, th = thr_table(low), thr_table(high)
+    cap = 1 << 20
+    ot, ok = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    okey, oc = np.zeros(cap, np.uint64), np.zeros(cap, np.uint64)
+    nb = C.c_long(0)
+    bi = np.zeros(max(1, len(reads)), np.int32)
+    n = lib.etc_scan_long(buf.tobytes(), locs.ctypes.data, len(reads), mn, mx, sl, tl.ctypes.data, th.ctypes.data, ot.ctypes.data,
+                          ok.ctypes.data, okey.ctypes.data, oc.ctypes.data, cap, C.byref(nb), bi.ctypes.data)
+    assert n >= 0
+    return {(int(ot[i]), int(ok[i]), int(okey[i])): int(oc[i]) for i in range(n)}, [int(x) for x in bi[:nb.value]]
+
+
+@pytest.mark.parametrize("mn,mx,sl,seed", [(5, 32, 150, 3), (5, 32, 128, 5), (5, 20, 64, 6), (7, 30, 160, 7)])
+def test_thread_long_path_equals_oracle(etc, mn, mx, sl, seed):
+    """The three-step long-read path (all slice statistics, the walks over them, the emissions) against the oracle on
+    adversarial long reads and on config-4 shaped reads; reads whose walk reaches the (longer) middle slice bail out."""
+    from test_gpu_parity import config4_reads
+    reads = [r for r in synth.adversarial_long(500 + sl, 150, min_len=sl, max_len=4000, max_unit=mx)] + config4_reads(seed, 64)
+    got, bailed = run_long(etc, reads, mn, mx, sl)
+    keep = [r for i, r in enumerate(reads) if i not in set(bailed)]
+    want = Oracle(mn, mx, slice_len=sl).scan(2, keep)
+    assert got == want, (len(got), len(want), sorted(set(got.items()) ^ set(want.items()))[:6])
+    assert len(got) > 100 and len(bailed) < len(reads) / 2

@@ -379,3 +379,14 @@ def test_report_filter_through_the_merge_and_the_cli(tmp_path):
     a = subprocess.run([api.CLI_PATH, "short", "5", "32", p], capture_output=True, check=True).stdout
     b = subprocess.run([api.CLI_PATH, "short", "5", "32", p], capture_output=True, check=True, env=dict(os.environ, TREW_FULL_TABLES="1")).stdout
     assert a == b and a.count(b"\n") > 6
+
+
+def test_long_thread_path_when_switched_on(monkeypatch):
+    """The three-kernel long-read path (statistics of every slice, the walks, the emissions; exact_thread.cuh) is off by
+    default -- measured slower than the warp kernel's serial walk -- but stays exact: TREW_EXACT_FLAGS=16 runs it."""
+    from oracle.oracle import Oracle
+    monkeypatch.setenv("TREW_EXACT_FLAGS", "16")
+    reads = config4_reads(9, 160) + synth.adversarial_long(310, 120, min_len=150, max_len=4000, max_unit=32)
+    got = run_gpu(api.MODE_LONG, 5, 32, 0.5, 0.8, 150, reads)
+    want = Oracle(5, 32, slice_len=150).scan(2, reads)
+    assert got == want, diff_msg(got, want)

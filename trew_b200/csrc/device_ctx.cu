@@ -138,12 +138,28 @@ int run_cap_for(const trew_config& cfg, uint32_t max_read_len) {
     return (int)std::max<uint32_t>((w + 2 + 7) & ~7u, 32u);   // >= 32: eval_k's serial path keeps 96 words in htab + grp_*
 }
 
-size_t scratch_need(const trew_ctx* ctx, uint32_t max_read_len, unsigned int* stride) {
+constexpr unsigned int kLongThreadCap = 32768;   // survivors per batch the long-read thread path takes (the rest: warp kernel)
+
+// warp kernel: per-warp (th, tl) per slice; long-read thread path (behind it, at *long_off): statistics + emissions per
+// (survivor, slice)
+size_t scratch_need(const trew_ctx* ctx, uint32_t max_read_len, uint32_t n_units, unsigned int* stride, size_t* long_off,
+                    unsigned int* s_cap, unsigned int* max_slices) {
     unsigned int st = 16;
     if (ctx->cfg.mode == TREW_MODE_LONG) st = 2u * (max_read_len / (uint32_t)ctx->cfg.slice_length + 2u);
     st = (st + 15u) & ~15u;
     *stride = st;
-    return (size_t)st * (size_t)exact_warps_total(ctx->sm_count);
+    size_t bytes = ((size_t)st * (size_t)exact_warps_total(ctx->sm_count) + 255) & ~(size_t)255;
+    *long_off = bytes;
+    *s_cap = 0; *max_slices = 0;
+    // off unless TREW_EXACT_FLAGS has bit 16: measured slower than the warp kernel's serial walk on configs[3] (2.0 against
+    // 1.03 ms per 200 k x 15 kb batch; 6.3 against 3.7 ms with 10 % telomeric reads) -- scanning every slice of a survivor
+    // is 5x the slices the walks look at when the repeat sits at one end
+    if (long_thread_path_applies(ctx->dcfg) && (ctx->exact_flags & 16u)) {
+        *s_cap = std::min<unsigned int>(std::max<unsigned int>(n_units, 1u), kLongThreadCap);
+        *max_slices = max_read_len / (uint32_t)ctx->cfg.slice_length + 1u;
+        bytes += long_thread_scratch_bytes(*s_cap, *max_slices);
+    }
+    return bytes;
 }
 
 constexpr int kScanCounters = 8;
@@ -157,8 +173,9 @@ static int env_blocks_thread() {   // TREW_GRID_THREAD: thread-kernel blocks per
 int launch_scan(trew_ctx* ctx, const DevBatch& b, uint32_t n_units, uint32_t max_read_len, unsigned int* d_survivors,
                 unsigned int* d_counters, unsigned char** d_scratch, size_t* scratch_bytes, cudaStream_t st,
                 cudaEvent_t* ev = nullptr) {
-    unsigned int stride;
-    size_t need = scratch_need(ctx, max_read_len, &stride);
+    unsigned int stride, s_cap, max_slices;
+    size_t long_off;
+    size_t need = scratch_need(ctx, max_read_len, n_units, &stride, &long_off, &s_cap, &max_slices);
     if (need > *scratch_bytes) {
         if (*d_scratch) { CK(cudaStreamSynchronize(st)); CK(cudaFree(*d_scratch)); *d_scratch = nullptr; }
         CK(cudaMalloc((void**)d_scratch, need));
@@ -190,6 +207,14 @@ int launch_scan(trew_ctx* ctx, const DevBatch& b, uint32_t n_units, uint32_t max
         // ... and the thread kernel's leftovers (normally none)
         a.survivors = hard; a.n_survivors = d_counters + 3; a.work_counter = d_counters + 5; a.total_survivors = nullptr;
         ctx->stats.kernel_launches += 2;
+    } else if (s_cap > 0 && n_units < (1u << 28)) {
+        // long reads: statistics of every slice of a survivor, the walks over them, the emissions (three kernels); reads
+        // whose walk reaches the long middle slice -- or beyond the scratch's capacity -- go to the warp kernel
+        unsigned int* hard = d_survivors + n_units;
+        launch_long_thread(ctx->dcfg, b, d_survivors, d_counters, a.packed_probes, s_cap, max_slices, *d_scratch + long_off, hard,
+                           d_counters + 3, ctx->d_total_surv, ctx->sm_count, st);
+        a.survivors = hard; a.n_survivors = d_counters + 3; a.total_survivors = nullptr;
+        ctx->stats.kernel_launches += 3;
     }
     launch_exact(ctx->dcfg, b, a, ctx->plan, st);
     if (ev) CK(cudaEventRecord(ev[3], st));

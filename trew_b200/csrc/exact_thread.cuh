@@ -486,5 +486,101 @@ ET_HD bool route_pair_thread(Mem m, int n1, int n2, int min_mer, int max_mer, co
     return true;
 }
 
+// ---- long reads (buffer_task_long, src/kmer.cpp:747-985) in three data-parallel steps ---------------------------------
+//
+// The reference walks a read's slices inwards from both ends and stops a walk at the first slice that breaks it, so a
+// telomere-rich read is a long serial chain (one warp, up to ~100 slice scans, in the warp kernel).  The statistics of a
+// slice do not depend on the walk, only which of them are LOOKED at does.  So for a surviving read:
+//   1. long_slice_stats   target_k_high / target_k_low of EVERY slice but the middle one (threads: one per slice);
+//   2. long_walk          the two walks over those numbers (cheap, one thread per read) -> a list of emissions;
+//   3. long_emit          one emission = the classes of one (slice, k) into one table (threads: one per emission).
+// The middle slice carries the read's remainder and can be up to 2 * SLICE_LENGTH - 1 bases: a walk that reaches it makes
+// the read a case for the warp kernel (long_walk returns false before anything is emitted), as does SLICE_LENGTH > 160.
+
+struct LongGeom {   // src/kmer.cpp:790-798
+    int n, SL, snum, mid, bonus;
+    ET_HD LongGeom(int n_, int SL_) : n(n_), SL(SL_), snum(n_ / SL_), mid((n_ / SL_ + 1) / 2), bonus(n_ % SL_) {}
+    ET_HD int start(int t) const { return (t - 1) * SL + (t > mid ? bonus : 0); }   // slices are 1-based
+    ET_HD int len(int t) const { return SL + (t == mid ? bonus : 0); }
+};
+
+// step 1 for one slice: load(off, len) brings bases [off, off + len) of the read into W_RH / W_RL / W_RV
+template <class Load>
+ET_HD u32 long_slice_stats(Mem m, const LongGeom& g, int t, int min_mer, int max_mer, const unsigned short* thr_low,
+                           const unsigned short* thr_high, Load& load, ClsSpill& x) {
+    const int len = g.len(t);
+    load(g.start(t), len);
+    set_window(m, 0, len);
+    u64 sh, sl;
+    return scan_window(m, len, min_mer, max_mer, thr_low, thr_high, x, sh, sl);
+}
+
+// one emission of a long read: slice t, period k, destination table, RC-folded or not
+struct LongTask { unsigned short slice; unsigned char k, table_folded; };   // table | folded << 3
+
+// step 2.  stat(t) = target_k_high | target_k_low << 8 of slice t (never asked for the middle slice: the walk bails out
+// first when the slice is longer than the thread path takes); task(LongTask) receives the emissions in the reference's
+// order.  Returns false when the read has to go to the warp kernel; then no task was produced.
+// The walks are run twice: first only to see whether the middle slice is needed, then to produce the tasks.
+template <class Stat, class Task>
+ET_HD bool long_walk(const LongGeom& g, Stat& stat, Task& task) {
+    const int snum = g.snum;
+    const bool mid_ok = g.len(g.mid) <= kMaxRead;
+    for (int pass = mid_ok ? 1 : 0; pass < 2; pass++) {
+        int si[2] = {1, 1}, km[2] = {0, 0};
+        bool ended[2] = {false, false};
+        int nf = 0;
+        for (int ti = 1; ti <= snum && !(ended[0] && ended[1]); ti++) {   // forward walk
+            if (pass == 0 && ti == g.mid) return false;
+            const u32 r = stat(ti);
+            for (int c = 0; c < 2; c++) {
+                const int k = (int)((r >> (8 * c)) & 0xffu);
+                if (!ended[c] && k > 0 && (ti == 1 || km[c] == k)) { si[c]++; km[c] = k; }
+                else ended[c] = true;
+            }
+            nf = ti;
+        }
+        if (pass == 1) {
+            // replay: emit into 'both' (folded) when every slice survived, else into 'forward' (src/kmer.cpp:819-830, 858-867)
+            bool en[2] = {false, false};
+            int kk[2] = {0, 0};
+            const bool full[2] = {si[0] == snum + 1, si[1] == snum + 1};
+            for (int ti = 1; ti <= nf; ti++) {
+                const u32 r = stat(ti);
+                for (int c = 0; c < 2; c++) {
+                    const int k = (int)((r >> (8 * c)) & 0xffu);
+                    if (!en[c] && k) task(LongTask{(unsigned short)ti, (unsigned char)k, (unsigned char)(((full[c] ? T_O : T_F) + c) | (full[c] ? 8 : 0))});
+                    if (!en[c] && k > 0 && (ti == 1 || kk[c] == k)) kk[c] = k;
+                    else en[c] = true;
+                }
+            }
+        }
+        if (si[0] <= snum || si[1] <= snum) {   // backward walk: straight into 'backward' (src/kmer.cpp:836-856)
+            int sj[2] = {snum, snum};
+            km[0] = km[1] = 0; ended[0] = ended[1] = false;
+            for (int tj = snum; tj >= 1 && !(ended[0] && ended[1]); tj--) {
+                if (pass == 0 && tj == g.mid) return false;
+                const u32 r = stat(tj);
+                for (int c = 0; c < 2; c++) {
+                    const int k = (int)((r >> (8 * c)) & 0xffu);
+                    if (pass == 1 && !ended[c] && k) task(LongTask{(unsigned short)tj, (unsigned char)k, (unsigned char)(T_B + c)});
+                    if (sj[c] >= si[c] && !ended[c] && k > 0 && (tj == snum || km[c] == k)) { sj[c]--; km[c] = k; }
+                    else ended[c] = true;
+                }
+            }
+        }
+    }
+    return true;
+}
+
+// step 3 for one emission
+template <class Load, class Emit>
+ET_HD void long_emit(Mem m, const LongGeom& g, const LongTask& tk, Load& load, ClsSpill& x, Emit& emit) {
+    const int len = g.len(tk.slice);
+    load(g.start(tk.slice), len);
+    set_window(m, 0, len);
+    emit_window_classes(m, len, tk.k, tk.table_folded & 7, (tk.table_folded & 8) != 0, x, emit);
+}
+
 }  // namespace et
 }  // namespace trew

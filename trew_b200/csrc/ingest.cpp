@@ -664,9 +664,12 @@ IngestResult ingest_file(int mode, int slice_length, const char* file1, bool gz1
     const bool pair = mode == TREW_MODE_PAIR;
     if (pair && !b.rd.open(file2, gz2)) return IngestResult{TREW_ERR_IO, "File open failed"};
     if (auto_chunk) {
-        // inflated blocks stay small enough that the index and the packer find most of them still in the last-level
-        // cache (measured: BGZF at 128 MiB blocks is 20 % slower than at 32 MiB); mapped plain files want few hand-offs
-        chunk_bytes = (a.rd.gz || (pair && b.rd.gz)) ? ((size_t)32 << 20) : ((size_t)256 << 20);
+        // blocks small enough that the packer finds part of what the index just read in the last-level cache, large enough
+        // that the fork-join hand-offs do not show
+        // measured on the 16-core GPU hosts (4 M x 150 bp): plain 22.8 Gbases/s at 64 MiB against 20.4 at 256 MiB and
+        // 18.0 at 32 MiB; BGZF 5.5 at 64 MiB against 5.0-5.3 at 32 and 256 MiB
+        chunk_bytes = (size_t)64 << 20;
+        if (const char* e = getenv("TREW_CHUNK_MB")) { long v = atol(e); if (v > 0 && v <= 1024) chunk_bytes = (size_t)v << 20; }   // experiments
     }
     bool too_long = false;
     const bool trace = getenv("TREW_INGEST_TRACE") != nullptr;

@@ -1759,6 +1759,156 @@ __global__ void __launch_bounds__(TREW_THREAD_BLOCK, 4) trew_exact_thread_kernel
     }
 }
 
+// ---- long reads: the three steps of exact_thread.cuh (long_slice_stats / long_walk / long_emit) as kernels -------------
+//
+// Survivor idx (at most s_cap of them; the rest goes to the warp kernel) owns row idx of two arrays of max_slices + 1
+// entries: stats (u16: target_k_high | target_k_low << 8 per slice) and emis (u32 per slice: one byte per emission --
+// forward walk high / low: k | 0x80 when it goes to 'both' folded; backward walk high / low: k).
+
+struct SliceLoad {   // bases [off, off + len) of one read into the thread's workspace
+    et::Mem m; const u32 *hi, *lo, *val; u32 b0;
+    __device__ __forceinline__ void operator()(int off, int len) const {
+        const u32 pos = b0 + (u32)off, w0 = pos >> 5, sh = pos & 31u;
+        for (int j = 0; j < et::kReadWords + 2; j++) {
+            const u32 msk = low_mask(min(32, max(0, len - 32 * j)));
+            m[et::W_RH + j] = __funnelshift_r(__ldg(hi + w0 + j), __ldg(hi + w0 + j + 1), sh) & msk;
+            m[et::W_RL + j] = __funnelshift_r(__ldg(lo + w0 + j), __ldg(lo + w0 + j + 1), sh) & msk;
+            m[et::W_RV + j] = __funnelshift_r(__ldg(val + w0 + j), __ldg(val + w0 + j + 1), sh) & msk;
+        }
+    }
+};
+
+struct LongArgs {
+    const u32* survivors; const u32* n_survivors; int packed_probes;
+    u32 s_cap, max_slices;
+    unsigned short* stats; u32* emis;
+    u32* hard; u32* n_hard;
+    unsigned long long* total_survivors;
+};
+
+// step 1: warp per survivor, lane per slice
+__global__ void __launch_bounds__(TREW_THREAD_BLOCK, 4) trew_long_stats_kernel(DevCfg cfg, DevBatch b, LongArgs a) {
+    u32* work = reinterpret_cast<u32*>(g_smem);
+    const et::Mem m{work + threadIdx.x, TREW_THREAD_BLOCK};
+    const u32 n = min(*a.n_survivors, a.s_cap);
+    const u32 warps = gridDim.x * (blockDim.x >> 5), lane = lane_id();
+    et::ClsSpill x;
+    for (u32 idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); idx < n; idx += warps) {
+        u32 u = a.survivors[idx];
+        if (a.packed_probes) u &= (1u << kProbeShift) - 1u;
+        const u32 b0 = __ldg(b.bit_off + u);
+        const int len = (int)(__ldg(b.bit_off + u + 1) - b0);
+        if (len < cfg.slice_len) continue;
+        const et::LongGeom g(len, cfg.slice_len);
+        SliceLoad load{m, b.hi, b.lo, b.val, b0};
+        unsigned short* row = a.stats + (size_t)idx * (a.max_slices + 1);
+        for (int t = 1 + (int)lane; t <= g.snum; t += 32) {
+            u32 r = 0;
+            if (g.len(t) <= et::kMaxRead) r = et::long_slice_stats(m, g, t, cfg.min_mer, cfg.max_mer, cfg.thr_low, cfg.thr_high, load, x);
+            row[t] = (unsigned short)r;
+        }
+    }
+}
+
+// step 2: thread per survivor
+__global__ void __launch_bounds__(256) trew_long_walk_kernel(DevCfg cfg, DevBatch b, LongArgs a) {
+    const u32 n_all = *a.n_survivors;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.total_survivors) atomicAdd(a.total_survivors, (unsigned long long)n_all);
+    const u32 stride = gridDim.x * blockDim.x, n_round = (n_all + 31u) & ~31u;
+    for (u32 idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_round; idx += stride) {
+        bool bail = false;
+        u32 entry = 0;
+        if (idx < n_all) {
+            entry = a.survivors[idx];
+            u32 u = entry;
+            if (a.packed_probes) u &= (1u << kProbeShift) - 1u;
+            const int len = (int)(__ldg(b.bit_off + u + 1) - __ldg(b.bit_off + u));
+            if (idx >= a.s_cap) bail = len >= cfg.slice_len;
+            else if (len >= cfg.slice_len) {
+                const et::LongGeom g(len, cfg.slice_len);
+                const unsigned short* row = a.stats + (size_t)idx * (a.max_slices + 1);
+                u32* em = a.emis + (size_t)idx * (a.max_slices + 1);
+                for (int t = 1; t <= g.snum; t++) em[t] = 0u;
+                auto stat = [&](int t) { return (u32)row[t]; };
+                auto task = [&](const et::LongTask& tk) {
+                    const int tb = tk.table_folded & 7, c = tb & 1;
+                    const bool backward = (tb & 6) == et::T_B;
+                    const u32 byte = (u32)tk.k | ((tk.table_folded & 8) ? 0x80u : 0u);
+                    em[tk.slice] |= byte << (8 * ((backward ? 2 : 0) + c));
+                };
+                bail = !et::long_walk(g, stat, task);
+                if (bail) for (int t = 1; t <= g.snum; t++) em[t] = 0u;
+            }
+        }
+        list_append(bail, entry, a.hard, a.n_hard);
+    }
+}
+
+// step 3: warp per survivor, lane per slice with emissions
+__global__ void __launch_bounds__(TREW_THREAD_BLOCK, 4) trew_long_emit_kernel(DevCfg cfg, DevBatch b, LongArgs a) {
+    u32* work = reinterpret_cast<u32*>(g_smem);
+    u64* s_key = reinterpret_cast<u64*>(work + et::kWorkWords * TREW_THREAD_BLOCK);
+    u32* s_meta = reinterpret_cast<u32*>(s_key + kStageSlots);
+    u32* s_cnt = s_meta + kStageSlots;
+    for (int i = threadIdx.x; i < kStageSlots; i += blockDim.x) { s_meta[i] = 0u; s_cnt[i] = 0u; }
+    __syncthreads();
+    const et::Mem m{work + threadIdx.x, TREW_THREAD_BLOCK};
+    StageEmit emit{s_meta, s_cnt, s_key, cfg.slots, cfg.slot_mask, cfg.error_flag};
+    const u32 n = min(*a.n_survivors, a.s_cap);
+    const u32 warps = gridDim.x * (blockDim.x >> 5), lane = lane_id();
+    et::ClsSpill x;
+    for (u32 idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); idx < n; idx += warps) {
+        u32 u = a.survivors[idx];
+        if (a.packed_probes) u &= (1u << kProbeShift) - 1u;
+        const u32 b0 = __ldg(b.bit_off + u);
+        const int len = (int)(__ldg(b.bit_off + u + 1) - b0);
+        if (len < cfg.slice_len) continue;
+        const et::LongGeom g(len, cfg.slice_len);
+        SliceLoad load{m, b.hi, b.lo, b.val, b0};
+        const u32* em = a.emis + (size_t)idx * (a.max_slices + 1);
+        for (int t = 1 + (int)lane; t <= g.snum; t += 32) {
+            const u32 e = em[t];
+            if (e == 0u) continue;
+            for (int f = 0; f < 4; f++) {   // forward high, forward low, backward high, backward low
+                const u32 byte = (e >> (8 * f)) & 0xffu;
+                if (byte == 0u) continue;
+                const int c = f & 1;
+                const bool folded = (byte & 0x80u) != 0u;
+                const int table = (f >= 2 ? et::T_B : (folded ? et::T_O : et::T_F)) + c;
+                et::LongTask tk{(unsigned short)t, (unsigned char)(byte & 0x7fu), (unsigned char)(table | (folded ? 8 : 0))};
+                et::long_emit(m, g, tk, load, x, emit);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kStageSlots; i += blockDim.x) {
+        const u32 st = s_meta[i], c = s_cnt[i];
+        if (st != 0u && st != kStageLock && c != 0u) table_add_impl(cfg.slots, cfg.slot_mask, cfg.error_flag, st & 0x7fffffffu, s_key[i], 0ULL, (u64)c);
+    }
+}
+
+bool long_thread_path_applies(const DevCfg& cfg) { return cfg.mode == 2 && cfg.max_mer <= 32 && cfg.slice_len <= et::kMaxRead; }
+
+size_t long_thread_scratch_bytes(unsigned int s_cap, unsigned int max_slices) {
+    return (size_t)s_cap * (max_slices + 1) * (sizeof(unsigned short) + sizeof(u32)) + 64;
+}
+
+// survivors (list, counter) -> statistics, walks, emissions; reads the path cannot take are appended to hard / n_hard
+void launch_long_thread(const DevCfg& cfg, const DevBatch& b, const unsigned int* survivors, const unsigned int* n_survivors,
+                        int packed_probes, unsigned int s_cap, unsigned int max_slices, unsigned char* scratch, unsigned int* hard,
+                        unsigned int* n_hard, unsigned long long* total_survivors, int sm_count, cudaStream_t stream) {
+    LongArgs a{};
+    a.survivors = survivors; a.n_survivors = n_survivors; a.packed_probes = packed_probes;
+    a.s_cap = s_cap; a.max_slices = max_slices;
+    a.emis = reinterpret_cast<u32*>(scratch);
+    a.stats = reinterpret_cast<unsigned short*>(scratch + (size_t)s_cap * (max_slices + 1) * sizeof(u32));
+    a.hard = hard; a.n_hard = n_hard; a.total_survivors = total_survivors;
+    const size_t smem_stats = (size_t)et::kWorkWords * TREW_THREAD_BLOCK * sizeof(u32);
+    trew_long_stats_kernel<<<sm_count * 4, TREW_THREAD_BLOCK, smem_stats, stream>>>(cfg, b, a);
+    trew_long_walk_kernel<<<sm_count * 2, 256, 0, stream>>>(cfg, b, a);
+    trew_long_emit_kernel<<<sm_count * 4, TREW_THREAD_BLOCK, kThreadKernelSmem, stream>>>(cfg, b, a);
+}
+
 // true when the thread kernel can take (most of) a batch: short single-end or paired mode, 64-bit units
 bool thread_path_applies(const DevCfg& cfg, unsigned int max_read_len) {
     if (cfg.max_mer > 32) return false;
@@ -1813,6 +1963,8 @@ cudaError_t prepare_exact(int run_cap_max) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(trew_exact_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(trew_exact_thread_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kThreadKernelSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(trew_exact_thread_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kThreadKernelSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(trew_long_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kThreadKernelSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(trew_long_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kThreadKernelSmem);
     return e;
 }
 

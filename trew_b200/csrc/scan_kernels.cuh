@@ -62,7 +62,7 @@ struct ExactArgs {
     int packed_probes;               // survivor entries carry the undecided-probe mask in bits 28..31
     int reverse;                     // the list grows downwards: entry idx is survivors[-idx]
     unsigned int exp_flags;          // experiments (TREW_EXACT_FLAGS): 1 = serial path for few runs in eval_k, 2 = no composition bound,
-                                     // 4 = no thread-per-survivor kernel, 8 = reads with invalid bases stay in the thread kernel
+                                     // 4 = no thread-per-survivor kernel, 16 = long reads through the three-step thread path
 };
 
 // grid sizes (total blocks) of the three scan kernels; all three are grid-stride / work-counter kernels
@@ -79,6 +79,13 @@ size_t exact_smem_bytes(int run_cap, bool wide);
 cudaError_t prepare_exact(int run_cap_max);
 void launch_exact(const DevCfg& cfg, const DevBatch& b, const ExactArgs& a, const LaunchPlan& plan, cudaStream_t stream);
 int exact_warps_total(int sm_count);
+// long reads through the thread path (exact_thread.cuh: statistics of every slice, the walks, the emissions -- three
+// kernels); scratch: long_thread_scratch_bytes(s_cap, max_slices); what it cannot take lands in hard / n_hard
+bool long_thread_path_applies(const DevCfg& cfg);
+size_t long_thread_scratch_bytes(unsigned int s_cap, unsigned int max_slices);
+void launch_long_thread(const DevCfg& cfg, const DevBatch& b, const unsigned int* survivors, const unsigned int* n_survivors,
+                        int packed_probes, unsigned int s_cap, unsigned int max_slices, unsigned char* scratch, unsigned int* hard,
+                        unsigned int* n_hard, unsigned long long* total_survivors, int sm_count, cudaStream_t stream);
 // thread-per-survivor exact kernel (exact_thread.cuh): takes the survivors of a short-mode batch, appends the ones
 // outside its limits to `hard` (counter n_hard, zeroed) for launch_exact
 bool thread_path_applies(const DevCfg& cfg, unsigned int max_read_len);
