@@ -38,6 +38,7 @@ constexpr int kReadWords = 5;      // read planes: up to 160 bases
 constexpr int kMaxRead = 32 * kReadWords;
 constexpr int kClsCap = 6;         // distinct rotation classes of an evaluated (window, period) kept in the workspace ...
 constexpr int kClsSpill = kMaxRead - kClsCap;   // ... the rest (noisy windows, rare) in thread-local memory
+constexpr int kApproxMaxWindows = 48;           // scan_window: composition pre-pass only for periods with at most this many windows
 
 // workspace words of one thread
 enum {
@@ -284,7 +285,10 @@ ET_FN u32 scan_window(Mem m, int len, int kmin, int kmax, const unsigned short* 
         if (!((!blkL && need_pass(thr_low, needL, U, T)) || (!blkH && need_pass(thr_high, needH, U, T)))) continue;
         u64 S;
         const int runs = prepare_runs(m, nw, k);
-        if (runs > 3) {   // several runs: first the cheap bound from the runs' base compositions
+        // several runs over few windows (what an N leaves of a window): first the cheap bound from the runs' base
+        // compositions.  With many windows it is not worth its price: TTAGGG at k = 5 has ~35 runs per half, half of them in
+        // one class AND one composition, so the bound never rejects there (measured: 5 % of the kernel).
+        if (runs > 3 && T <= kApproxMaxWindows) {
             const int Mu = cls_max(m, classify_runs(m, runs, k, x, true), x, S);
             if (!((!blkL && need_pass(thr_low, needL, Mu, T)) || (!blkH && need_pass(thr_high, needH, Mu, T)))) continue;
         }
