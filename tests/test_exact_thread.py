@@ -163,3 +163,18 @@ def test_thread_long_path_equals_oracle(etc, mn, mx, sl, seed):
     want = Oracle(mn, mx, slice_len=sl).scan(2, keep)
     assert got == want, (len(got), len(want), sorted(set(got.items()) ^ set(want.items()))[:6])
     assert len(got) > 100 and len(bailed) < len(reads) / 2
+
+
+def test_thread_path_under_sanitizers(tmp_path):
+    """compute-sanitizer is closed on the GPU pool; the thread kernels' code is plain scalar C++, so it is run here
+    under AddressSanitizer + UndefinedBehaviorSanitizer instead (workspace indices, shift counts, class-list spill)."""
+    import sys
+    so = os.path.join(str(tmp_path), "libetc_asan.so")
+    src = os.path.join(ROOT, "tests", "native", "exact_thread_check.cpp")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-fsanitize=address,undefined",
+                           "-fno-sanitize-recover=undefined", "-Wno-unknown-pragmas", "-o", so, src])
+    asan = subprocess.check_output(["g++", "-print-file-name=libasan.so"]).decode().strip()
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "native", "exact_thread_sanitize.py"), so], env=env,
+                       capture_output=True, timeout=900)
+    assert r.returncode == 0 and b"sanitizer run clean" in r.stdout, (r.stdout[-500:], r.stderr[-3000:])
