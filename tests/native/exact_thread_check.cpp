@@ -21,27 +21,35 @@ int code_of(unsigned char ch) {   // codes[], src/kmer.cpp:14-31: T=0 G=1 C=2 A=
         default: return -1;
     }
 }
+typedef std::map<std::tuple<int, int, uint64_t, uint64_t>, uint64_t> Tables;   // (table, k, key hi, key lo) -> count
 struct Collect {
-    std::map<std::tuple<int, int, uint64_t>, uint64_t>* m;
-    void operator()(int table, int k, uint64_t key, uint64_t count) { (*m)[std::make_tuple(table, k, key)] += count; }
+    Tables* m;
+    void operator()(int table, int k, u64 key, uint64_t count) { (*m)[std::make_tuple(table, k, (uint64_t)0, key)] += count; }
+    void operator()(int table, int k, u128 key, uint64_t count) {
+        (*m)[std::make_tuple(table, k, (uint64_t)(key >> 64), (uint64_t)key)] += count;
+    }
 };
-}  // namespace
+long write_out(const Tables& tables, int32_t* out_table, int32_t* out_k, uint64_t* out_key, uint64_t* out_key_hi, uint64_t* out_count, long cap) {
+    if ((long)tables.size() > cap) return -1;
+    long i = 0;
+    for (auto& kv : tables) {
+        out_table[i] = std::get<0>(kv.first); out_k[i] = std::get<1>(kv.first); out_key[i] = std::get<3>(kv.first);
+        if (out_key_hi) out_key_hi[i] = std::get<2>(kv.first);
+        out_count[i] = kv.second;
+        i++;
+    }
+    return i;
+}
 
-extern "C" {
-
-// thr_low / thr_high: 1025 entries each (min M with (double)M / T >= baseline), built by the caller with IEEE doubles.
-// Returns the number of table entries written (up to cap), or -1 when cap is too small; *n_bailed = reads outside the
-// thread path's limits (the device hands those to the warp kernel).
-long etc_scan_reads(const char* buf, const int32_t* locs, int n_reads, int min_mer, int max_mer, const unsigned short* thr_low,
-                    const unsigned short* thr_high, int32_t* out_table, int32_t* out_k, uint64_t* out_key, uint64_t* out_count, long cap,
-                    long* n_bailed, int32_t* bailed_index) {
-    std::map<std::tuple<int, int, uint64_t>, uint64_t> tables;
+template <class K>
+long scan_reads(const char* buf, const int32_t* locs, int n_reads, int min_mer, int max_mer, const unsigned short* thr_low,
+                const unsigned short* thr_high, Tables& tables, int32_t* bailed_index) {
     Collect emit{&tables};
     long bailed = 0;
     for (int r = 0; r < n_reads; r++) {
         const int st = locs[2 * r], nd = locs[2 * r + 1];
         const int n = nd >= st ? nd - st + 1 : 0;
-        u32 work[kWorkWords];
+        u32 work[Lay<K>::WORDS];
         memset(work, 0xA5, sizeof(work));   // the workspace is not cleared between reads on the device either
         Mem m{work, 1};
         bool ok = true;
@@ -54,21 +62,15 @@ long etc_scan_reads(const char* buf, const int32_t* locs, int n_reads, int min_m
                     m[W_RL + (i >> 5)] |= (u32)(c & 1) << (i & 31);
                 }
             }
-            ok = route_short_thread(m, n, 7u, min_mer, max_mer, thr_low, thr_high, emit);
+            ok = route_short_thread<K>(m, n, 7u, min_mer, max_mer, thr_low, thr_high, emit);
         } else {
             ok = n < 2 * min_mer;
         }
         if (!ok) { if (bailed_index) bailed_index[bailed] = r; bailed++; }
     }
-    if (n_bailed) *n_bailed = bailed;
-    if ((long)tables.size() > cap) return -1;
-    long i = 0;
-    for (auto& kv : tables) {
-        out_table[i] = std::get<0>(kv.first); out_k[i] = std::get<1>(kv.first); out_key[i] = std::get<2>(kv.first); out_count[i] = kv.second;
-        i++;
-    }
-    return i;
+    return bailed;
 }
+}  // namespace
 
 namespace {
 struct StringLoad {
@@ -86,32 +88,25 @@ struct StringLoad {
 };
 }  // namespace
 
-// the same for pairs (buffer_task_pair): mate i of pair r is locs{1,2}[2r .. 2r+1] in buf{1,2}
-long etc_scan_pairs(const char* buf1, const int32_t* locs1, const char* buf2, const int32_t* locs2, int n_pairs, int min_mer, int max_mer,
-                    const unsigned short* thr_low, const unsigned short* thr_high, int32_t* out_table, int32_t* out_k, uint64_t* out_key,
-                    uint64_t* out_count, long cap, long* n_bailed, int32_t* bailed_index) {
-    std::map<std::tuple<int, int, uint64_t>, uint64_t> tables;
+namespace {
+template <class K>
+long scan_pairs(const char* buf1, const int32_t* locs1, const char* buf2, const int32_t* locs2, int n_pairs, int min_mer, int max_mer,
+                const unsigned short* thr_low, const unsigned short* thr_high, Tables& tables, int32_t* bailed_index) {
     Collect emit{&tables};
     long bailed = 0;
     for (int r = 0; r < n_pairs; r++) {
         const int n1 = locs1[2 * r + 1] >= locs1[2 * r] ? locs1[2 * r + 1] - locs1[2 * r] + 1 : 0;
         const int n2 = locs2[2 * r + 1] >= locs2[2 * r] ? locs2[2 * r + 1] - locs2[2 * r] + 1 : 0;
-        u32 work[kWorkWords];
+        u32 work[Lay<K>::WORDS];
         memset(work, 0xA5, sizeof(work));
         Mem m{work, 1};
         StringLoad load{m, {buf1 + locs1[2 * r], buf2 + locs2[2 * r]}, {n1 <= kMaxRead ? n1 : 0, n2 <= kMaxRead ? n2 : 0}};
-        const bool ok = route_pair_thread(m, n1, n2, min_mer, max_mer, thr_low, thr_high, load, emit);
+        const bool ok = route_pair_thread<K>(m, n1, n2, min_mer, max_mer, thr_low, thr_high, load, emit);
         if (!ok) { if (bailed_index) bailed_index[bailed] = r; bailed++; }
     }
-    if (n_bailed) *n_bailed = bailed;
-    if ((long)tables.size() > cap) return -1;
-    long i = 0;
-    for (auto& kv : tables) {
-        out_table[i] = std::get<0>(kv.first); out_k[i] = std::get<1>(kv.first); out_key[i] = std::get<2>(kv.first); out_count[i] = kv.second;
-        i++;
-    }
-    return i;
+    return bailed;
 }
+}  // namespace
 
 namespace {
 struct OffsetLoad {   // bases [off, off + len) of one read
@@ -129,11 +124,52 @@ struct OffsetLoad {   // bases [off, off + len) of one read
 };
 }  // namespace
 
+extern "C" {
+
+// thr_low / thr_high: 1025 entries each (min M with (double)M / T >= baseline), built by the caller with IEEE doubles.
+// Returns the number of table entries written (up to cap), or -1 when cap is too small; *n_bailed = reads outside the
+// thread path's limits (the device hands those to the warp kernel).
+long etc_scan_reads(const char* buf, const int32_t* locs, int n_reads, int min_mer, int max_mer, const unsigned short* thr_low,
+                    const unsigned short* thr_high, int32_t* out_table, int32_t* out_k, uint64_t* out_key, uint64_t* out_count, long cap,
+                    long* n_bailed, int32_t* bailed_index) {
+    Tables tables;
+    const long bailed = scan_reads<u64>(buf, locs, n_reads, min_mer, max_mer, thr_low, thr_high, tables, bailed_index);
+    if (n_bailed) *n_bailed = bailed;
+    return write_out(tables, out_table, out_k, out_key, nullptr, out_count, cap);
+}
+// the 128-bit instantiation (MAX_MER <= 64); out_key_hi receives bits 64..127 of the keys
+long etc_scan_reads_wide(const char* buf, const int32_t* locs, int n_reads, int min_mer, int max_mer, const unsigned short* thr_low,
+                         const unsigned short* thr_high, int32_t* out_table, int32_t* out_k, uint64_t* out_key, uint64_t* out_key_hi,
+                         uint64_t* out_count, long cap, long* n_bailed, int32_t* bailed_index) {
+    Tables tables;
+    const long bailed = scan_reads<u128>(buf, locs, n_reads, min_mer, max_mer, thr_low, thr_high, tables, bailed_index);
+    if (n_bailed) *n_bailed = bailed;
+    return write_out(tables, out_table, out_k, out_key, out_key_hi, out_count, cap);
+}
+
+// the same for pairs (buffer_task_pair): mate i of pair r is locs{1,2}[2r .. 2r+1] in buf{1,2}
+long etc_scan_pairs(const char* buf1, const int32_t* locs1, const char* buf2, const int32_t* locs2, int n_pairs, int min_mer, int max_mer,
+                    const unsigned short* thr_low, const unsigned short* thr_high, int32_t* out_table, int32_t* out_k, uint64_t* out_key,
+                    uint64_t* out_count, long cap, long* n_bailed, int32_t* bailed_index) {
+    Tables tables;
+    const long bailed = scan_pairs<u64>(buf1, locs1, buf2, locs2, n_pairs, min_mer, max_mer, thr_low, thr_high, tables, bailed_index);
+    if (n_bailed) *n_bailed = bailed;
+    return write_out(tables, out_table, out_k, out_key, nullptr, out_count, cap);
+}
+long etc_scan_pairs_wide(const char* buf1, const int32_t* locs1, const char* buf2, const int32_t* locs2, int n_pairs, int min_mer, int max_mer,
+                         const unsigned short* thr_low, const unsigned short* thr_high, int32_t* out_table, int32_t* out_k, uint64_t* out_key,
+                         uint64_t* out_key_hi, uint64_t* out_count, long cap, long* n_bailed, int32_t* bailed_index) {
+    Tables tables;
+    const long bailed = scan_pairs<u128>(buf1, locs1, buf2, locs2, n_pairs, min_mer, max_mer, thr_low, thr_high, tables, bailed_index);
+    if (n_bailed) *n_bailed = bailed;
+    return write_out(tables, out_table, out_k, out_key, out_key_hi, out_count, cap);
+}
+
 // long reads (buffer_task_long) through the three steps of the thread path, run one after the other per read
 long etc_scan_long(const char* buf, const int32_t* locs, int n_reads, int min_mer, int max_mer, int slice_len, const unsigned short* thr_low,
                    const unsigned short* thr_high, int32_t* out_table, int32_t* out_k, uint64_t* out_key, uint64_t* out_count, long cap,
                    long* n_bailed, int32_t* bailed_index) {
-    std::map<std::tuple<int, int, uint64_t>, uint64_t> tables;
+    Tables tables;
     Collect emit{&tables};
     long bailed = 0;
     for (int r = 0; r < n_reads; r++) {
@@ -143,7 +179,7 @@ long etc_scan_long(const char* buf, const int32_t* locs, int n_reads, int min_me
         memset(work, 0xA5, sizeof(work));
         Mem m{work, 1};
         OffsetLoad load{m, buf + st};
-        ClsSpill x;
+        ClsSpill<u64> x;
         bool ok = max_mer <= 32 && slice_len <= kMaxRead;
         if (ok) {
             LongGeom g(n, slice_len);
@@ -159,13 +195,7 @@ long etc_scan_long(const char* buf, const int32_t* locs, int n_reads, int min_me
         if (!ok) { if (bailed_index) bailed_index[bailed] = r; bailed++; }
     }
     if (n_bailed) *n_bailed = bailed;
-    if ((long)tables.size() > cap) return -1;
-    long i = 0;
-    for (auto& kv : tables) {
-        out_table[i] = std::get<0>(kv.first); out_k[i] = std::get<1>(kv.first); out_key[i] = std::get<2>(kv.first); out_count[i] = kv.second;
-        i++;
-    }
-    return i;
+    return write_out(tables, out_table, out_k, out_key, nullptr, out_count, cap);
 }
 
 }  // extern "C"

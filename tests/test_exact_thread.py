@@ -30,6 +30,12 @@ def etc(tmp_path_factory):
     lib.etc_scan_pairs.restype = C.c_long
     lib.etc_scan_pairs.argtypes = [C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.POINTER(C.c_long), C.c_void_p]
+    lib.etc_scan_reads_wide.restype = C.c_long
+    lib.etc_scan_reads_wide.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.POINTER(C.c_long), C.c_void_p]
+    lib.etc_scan_pairs_wide.restype = C.c_long
+    lib.etc_scan_pairs_wide.argtypes = [C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.POINTER(C.c_long), C.c_void_p]
     return lib
 
 
@@ -43,7 +49,8 @@ def thr_table(B):
     return t
 
 
-def run(lib, reads, mn, mx, low=0.5, high=0.8):
+def run(lib, reads, mn, mx, low=0.5, high=0.8, wide=False):
+    """wide: the 128-bit-key instantiation (MAX_MER <= 64); keys come back as hi << 64 | lo like the oracle's."""
     buf, locs = api.make_chunk(reads)
     locs = np.ascontiguousarray(locs, dtype=np.int32)
     tl, th = thr_table(low), thr_table(high)
@@ -52,10 +59,15 @@ def run(lib, reads, mn, mx, low=0.5, high=0.8):
     okey, oc = np.zeros(cap, np.uint64), np.zeros(cap, np.uint64)
     nb = C.c_long(0)
     bi = np.zeros(max(1, len(reads)), np.int32)
-    n = lib.etc_scan_reads(buf.tobytes(), locs.ctypes.data, len(reads), mn, mx, tl.ctypes.data, th.ctypes.data, ot.ctypes.data,
-                           ok.ctypes.data, okey.ctypes.data, oc.ctypes.data, cap, C.byref(nb), bi.ctypes.data)
+    ohi = np.zeros(cap if wide else 1, np.uint64)
+    if wide:
+        n = lib.etc_scan_reads_wide(buf.tobytes(), locs.ctypes.data, len(reads), mn, mx, tl.ctypes.data, th.ctypes.data, ot.ctypes.data,
+                                    ok.ctypes.data, okey.ctypes.data, ohi.ctypes.data, oc.ctypes.data, cap, C.byref(nb), bi.ctypes.data)
+    else:
+        n = lib.etc_scan_reads(buf.tobytes(), locs.ctypes.data, len(reads), mn, mx, tl.ctypes.data, th.ctypes.data, ot.ctypes.data,
+                               ok.ctypes.data, okey.ctypes.data, oc.ctypes.data, cap, C.byref(nb), bi.ctypes.data)
     assert n >= 0
-    tables = {(int(ot[i]), int(ok[i]), int(okey[i])): int(oc[i]) for i in range(n)}
+    tables = {(int(ot[i]), int(ok[i]), int(okey[i]) | ((int(ohi[i]) << 64) if wide else 0)): int(oc[i]) for i in range(n)}
     return tables, [int(x) for x in bi[:nb.value]]
 
 
@@ -73,6 +85,23 @@ def test_thread_path_equals_oracle(etc, mn, mx, low, high, lengths):
     assert got == want, (len(got), len(want), sorted(set(got.items()) ^ set(want.items()))[:6])
     assert len(got) > 100
     assert bailed == [i for i, r in enumerate(reads) if len(r) > 160]   # only the length limit
+
+
+@pytest.mark.parametrize("mn,mx,lengths", [(3, 64, [150, 150, 151, 160, 131]), (5, 40, [150, 100, 128]), (12, 64, [160, 150, 90]),
+                                           (5, 33, [150, 140]), (5, 32, [150, 99])])
+def test_wide_thread_path_equals_oracle(etc, mn, mx, lengths):
+    """Units above 32 bases (128-bit keys, the reference's k_mer_check_128 path, src/kmer.cpp:2264-2328) -- and the
+    same instantiation on a configuration the 64-bit one handles too."""
+    reads = synth.adversarial_short(1300 + mn * 67 + mx, 2500, max_unit=mx, lengths=lengths)
+    got, bailed = run(etc, reads, mn, mx, wide=True)
+    assert bailed == []
+    want = Oracle(mn, mx).scan(0, reads)
+    assert got == want, (len(got), len(want), sorted(set(got.items()) ^ set(want.items()))[:6])
+    assert len(got) > 100
+    if mx > 32:
+        assert any(k > 32 for (_, k, _) in got)
+        narrow, nb = run(etc, reads, mn, mx)          # the 64-bit instantiation refuses MAX_MER > 32
+        assert narrow == {} and len(nb) == len([r for r in reads if len(r) >= 2 * mn])
 
 
 def test_thread_path_on_the_bench_distribution(etc):
@@ -104,7 +133,7 @@ def test_thread_path_short_reads_equal_oracle(etc, mn, mx, lengths):
     assert len(got) > 100
 
 
-def run_pairs(lib, r1, r2, mn, mx, low=0.5, high=0.8):
+def run_pairs(lib, r1, r2, mn, mx, low=0.5, high=0.8, wide=False):
     b1, l1 = api.make_chunk(r1)
     b2, l2 = api.make_chunk(r2)
     l1 = np.ascontiguousarray(l1, dtype=np.int32)
@@ -115,10 +144,17 @@ def run_pairs(lib, r1, r2, mn, mx, low=0.5, high=0.8):
     okey, oc = np.zeros(cap, np.uint64), np.zeros(cap, np.uint64)
     nb = C.c_long(0)
     bi = np.zeros(max(1, len(r1)), np.int32)
-    n = lib.etc_scan_pairs(b1.tobytes(), l1.ctypes.data, b2.tobytes(), l2.ctypes.data, len(r1), mn, mx, tl.ctypes.data, th.ctypes.data,
-                           ot.ctypes.data, ok.ctypes.data, okey.ctypes.data, oc.ctypes.data, cap, C.byref(nb), bi.ctypes.data)
+    ohi = np.zeros(cap if wide else 1, np.uint64)
+    if wide:
+        n = lib.etc_scan_pairs_wide(b1.tobytes(), l1.ctypes.data, b2.tobytes(), l2.ctypes.data, len(r1), mn, mx, tl.ctypes.data,
+                                    th.ctypes.data, ot.ctypes.data, ok.ctypes.data, okey.ctypes.data, ohi.ctypes.data, oc.ctypes.data, cap,
+                                    C.byref(nb), bi.ctypes.data)
+    else:
+        n = lib.etc_scan_pairs(b1.tobytes(), l1.ctypes.data, b2.tobytes(), l2.ctypes.data, len(r1), mn, mx, tl.ctypes.data, th.ctypes.data,
+                               ot.ctypes.data, ok.ctypes.data, okey.ctypes.data, oc.ctypes.data, cap, C.byref(nb), bi.ctypes.data)
     assert n >= 0
-    return {(int(ot[i]), int(ok[i]), int(okey[i])): int(oc[i]) for i in range(n)}, [int(x) for x in bi[:nb.value]]
+    return ({(int(ot[i]), int(ok[i]), int(okey[i]) | ((int(ohi[i]) << 64) if wide else 0)): int(oc[i]) for i in range(n)},
+            [int(x) for x in bi[:nb.value]])
 
 
 @pytest.mark.parametrize("mn,mx,rl,trunc", [(5, 32, 150, 0.0), (5, 32, 150, 0.15), (5, 25, 120, 0.1), (3, 20, 100, 0.2), (7, 30, 160, 0.05)])
@@ -132,6 +168,19 @@ def test_thread_pair_path_equals_oracle(etc, mn, mx, rl, trunc):
     assert got == want, (len(got), len(want), sorted(set(got.items()) ^ set(want.items()))[:6])
     assert len(got) > 100
     # only the limits bail: a mate longer than 160 bases, or the shorter mate below 4 * MAX_MER (and at least 2 * MIN_MER)
+    expect = [i for i, (a, b) in enumerate(zip(r1, r2))
+              if min(len(a), len(b)) >= 2 * mn and (max(len(a), len(b)) > 160 or min(len(a), len(b)) < 4 * mx)]
+    assert bailed == expect
+
+
+@pytest.mark.parametrize("mn,mx,rl,trunc", [(5, 40, 160, 0.0), (3, 36, 150, 0.1), (5, 32, 150, 0.1)])
+def test_wide_thread_pair_path_equals_oracle(etc, mn, mx, rl, trunc):
+    r1, r2 = synth.adversarial_pairs(900 + mx + rl, 1500, read_len=rl, max_unit=mx, truncate_mate2=trunc)
+    got, bailed = run_pairs(etc, r1, r2, mn, mx, wide=True)
+    skip = set(bailed)
+    want = Oracle(mn, mx).scan(1, [r for i, r in enumerate(r1) if i not in skip], [r for i, r in enumerate(r2) if i not in skip])
+    assert got == want, (len(got), len(want), sorted(set(got.items()) ^ set(want.items()))[:6])
+    assert len(got) > 100
     expect = [i for i, (a, b) in enumerate(zip(r1, r2))
               if min(len(a), len(b)) >= 2 * mn and (max(len(a), len(b)) > 160 or min(len(a), len(b)) < 4 * mx)]
     assert bailed == expect

@@ -49,7 +49,7 @@ def test_short_vs_oracle(mn, mx, low, high):
     assert got == want, diff_msg(got, want)
 
 
-@pytest.mark.parametrize("mn,mx,rl,trunc", [(5, 32, 150, 0.0), (5, 40, 100, 0.15), (3, 64, 120, 0.1), (5, 32, 100, 0.2)])
+@pytest.mark.parametrize("mn,mx,rl,trunc", [(5, 32, 150, 0.0), (5, 40, 100, 0.15), (3, 64, 120, 0.1), (5, 32, 100, 0.2), (5, 40, 160, 0.05), (3, 36, 150, 0.1)])
 def test_pair_vs_oracle(mn, mx, rl, trunc):
     # the oracle follows the cleared-temp-map (128-bit path) semantics, like the CUDA path
     from oracle.oracle import Oracle

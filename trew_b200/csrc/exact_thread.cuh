@@ -33,6 +33,7 @@ namespace et {
 
 typedef uint32_t u32;
 typedef uint64_t u64;
+typedef unsigned __int128 u128;   // repeat units above 32 bases (MAX_MER <= 64): the reference's uint128_t path
 
 constexpr int kReadWords = 5;      // read planes: up to 160 bases
 constexpr int kMaxRead = 32 * kReadWords;
@@ -40,16 +41,20 @@ constexpr int kClsCap = 6;         // distinct rotation classes of an evaluated 
 constexpr int kClsSpill = kMaxRead - kClsCap;   // ... the rest (noisy windows, rare) in thread-local memory
 constexpr int kApproxMaxWindows = 48;           // scan_window: composition pre-pass only for periods with at most this many windows
 
-// workspace words of one thread
+// workspace words of one thread (the class keys at the end take 2 words each for 64-bit units, 4 for 128-bit ones: Lay<K>)
 enum {
     W_RH = 0, W_RL = W_RH + kReadWords + 2, W_RV = W_RL + kReadWords + 2,     // the read's planes (+ zero words behind)
     W_H = W_RV + kReadWords + 2, W_L = W_H + kReadWords + 2, W_V = W_L + kReadWords + 2,   // the current window
     W_PH = W_V + kReadWords + 2, W_PL = W_PH + kReadWords + 2,               // its exclusive prefix-XOR planes
     W_WV = W_PL + kReadWords + 2, W_LINK = W_WV + kReadWords, W_RS = W_LINK + kReadWords,   // valid windows, links, run starts
-    W_CKEY = W_RS + kReadWords,                                              // class keys: lo, hi words alternating
-    W_CTOT = W_CKEY + 2 * kClsCap, W_CLAST = W_CTOT + kClsCap,
-    kWorkWords = W_CLAST + kClsCap
+    W_CKEY = W_RS + kReadWords                                               // class keys, least significant word first
 };
+template <class K>
+struct Lay {
+    static constexpr int KW = (int)(sizeof(K) / 4);
+    static constexpr int CTOT = W_CKEY + KW * kClsCap, CLAST = CTOT + kClsCap, WORDS = CLAST + kClsCap;
+};
+constexpr int kWorkWords = Lay<u64>::WORDS;
 
 struct Mem {
     u32* base; int stride;
@@ -101,8 +106,8 @@ ET_HD u64 spread(u32 x) {   // bit m -> bit 2m
     return v;
 }
 
-// minimal rotation of a k-mer, k <= 32 (get_rot_seq, src/kmer.cpp:1815-1823)
-ET_FN u64 canon(u64 w, int k) {
+// minimal rotation of a k-mer (get_rot_seq / get_rot_seq_128, src/kmer.cpp:1815-1833)
+ET_FN u64 canon64(u64 w, int k) {
     const int sh = 2 * (k - 1);
     if (k <= 16) {
         u32 b = (u32)w, c = (u32)w;
@@ -113,15 +118,32 @@ ET_FN u64 canon(u64 w, int k) {
     for (int r = 1; r < k; r++) { cur = ((cur & 3ULL) << sh) | (cur >> 2); best = cur < best ? cur : best; }
     return best;
 }
+ET_FN u128 canon128(u128 w, int k) {
+    const int sh = 2 * (k - 1);
+    u128 best = w, cur = w;
+    for (int r = 1; r < k; r++) { cur = ((cur & 3) << sh) | (cur >> 2); best = cur < best ? cur : best; }
+    return best;
+}
+ET_HD u64 canon(u64 w, int k) { return canon64(w, k); }
+ET_HD u128 canon(u128 w, int k) { return k <= 32 ? (u128)canon64((u64)w, k) : canon128(w, k); }
 // canonical rotation of the reverse complement (rot_reverse_complement, src/kmer.cpp:72-74)
 ET_HD u64 crc(u64 w, int k) {
     const u32 lo = brev32((u32)w), hi = brev32((u32)(w >> 32));
     u64 x = ((u64)lo << 32) | hi;                                                 // all 64 bits reversed
     x = ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);   // 2-bit symbols reversed
-    return canon(~x >> (64 - 2 * k), k);
+    return canon64(~x >> (64 - 2 * k), k);
+}
+ET_HD u128 crc(u128 w, int k) {
+    if (k <= 32) return (u128)crc((u64)w, k);
+    u128 r = 0;
+    for (int i = 0; i < k; i++) { r = (r << 2) | (3 - (w & 3)); w >>= 2; }
+    return canon128(r, k);
 }
 ET_HD bool homo(u64 w, int k) {   // get_repeat_check: at most one distinct base
     return k <= 1 || ((w ^ (w >> 2)) & ((1ULL << (2 * (k - 1))) - 1ULL)) == 0;
+}
+ET_HD bool homo(u128 w, int k) {
+    return k <= 1 || ((w ^ (w >> 2)) & ((((u128)1) << (2 * (k - 1))) - 1)) == 0;
 }
 
 // bases [off, off + len) of the read (W_RH / W_RL / W_RV) become the current window (W_H / W_L / W_V)
@@ -140,21 +162,57 @@ ET_FN void set_window(Mem m, int off, int len) {
 }
 
 // the spill part of a class list (classes beyond the first kClsCap of an evaluation)
+template <class K>
 struct ClsSpill {
-    u64 key[kClsSpill];
+    K key[kClsSpill];
     unsigned short tot[kClsSpill], last[kClsSpill];
 };
 
-ET_HD u64 cls_key(Mem m, int q) { return (u64)m[W_CKEY + 2 * q] | ((u64)m[W_CKEY + 2 * q + 1] << 32); }
+template <class K>
+ET_HD K cls_key(Mem m, int q) {
+    K v = 0;
+    for (int i = Lay<K>::KW - 1; i >= 0; i--) v = (v << 16 << 16) | (K)m[W_CKEY + Lay<K>::KW * q + i];
+    return v;
+}
+template <class K>
+ET_HD void cls_put(Mem m, int q, K key) {
+    for (int i = 0; i < Lay<K>::KW; i++) { m[W_CKEY + Lay<K>::KW * q + i] = (u32)key; key = key >> 16 >> 16; }
+}
+
+// word j of (plane >> k), 0 < k <= 64; the planes have two zero words behind the window
+ET_HD u32 shr_plane(Mem m, int base, int j, int k) {
+    if (k < 32) return fshr(m[base + j], m[base + j + 1], k);
+    if (k == 32) return m[base + j + 1];
+    if (k < 64) return fshr(m[base + j + 1], m[base + j + 2], k - 32);
+    return m[base + j + 2];
+}
+
+// the k-mer starting at bit b of word j of the current window, first base most significant (the reference's shift-in
+// order, src/kmer.cpp:2186-2189); hk / lk receive its hi and lo plane bits (for the composition key)
+ET_HD u64 raw_kmer(Mem m, int j, int b, int k, u64& hk, u64& lk, u64) {
+    const u32 km = lowmask(k);
+    const u32 h = fshr(m[W_H + j], m[W_H + j + 1], b) & km, l = fshr(m[W_L + j], m[W_L + j + 1], b) & km;
+    hk = h; lk = l;
+    return (spread(brev32(h) >> (32 - k)) << 1) | spread(brev32(l) >> (32 - k));
+}
+ET_HD u128 raw_kmer(Mem m, int j, int b, int k, u64& hk, u64& lk, u128) {
+    if (k <= 32) return (u128)raw_kmer(m, j, b, k, hk, lk, (u64)0);
+    const u64 km = k >= 64 ? ~0ULL : ((1ULL << k) - 1ULL);
+    hk = ((u64)fshr(m[W_H + j], m[W_H + j + 1], b) | ((u64)fshr(m[W_H + j + 1], m[W_H + j + 2], b) << 32)) & km;
+    lk = ((u64)fshr(m[W_L + j], m[W_L + j + 1], b) | ((u64)fshr(m[W_L + j + 1], m[W_L + j + 2], b) << 32)) & km;
+    // reverse the k bits of each plane, then interleave: bit (k - 1 - i) of hr / lr is base i
+    const u64 hr = (((u64)brev32((u32)hk) << 32) | brev32((u32)(hk >> 32))) >> (64 - k);
+    const u64 lr = (((u64)brev32((u32)lk) << 32) | brev32((u32)(lk >> 32))) >> (64 - k);
+    const u64 lo = (spread((u32)hr) << 1) | spread((u32)lr), hi = (spread((u32)(hr >> 32)) << 1) | spread((u32)(lr >> 32));
+    return ((u128)hi << 64) | lo;
+}
 
 // Match-bit runs of the current window for one period (Lemma L1: windows i and i+1 are in the same rotation class iff
 // both are valid and base[i] == base[i+k], so classes are unions of maximal runs).  W_WV = valid k-windows (input);
 // fills W_LINK and W_RS (run starts) and returns the number of runs.
 ET_FN int prepare_runs(Mem m, int nw, int k) {
     for (int j = 0; j < nw; j++) {
-        // plane >> k for k <= 32
-        const u32 hs = k < 32 ? fshr(m[W_H + j], m[W_H + j + 1], k) : m[W_H + j + 1];
-        const u32 ls = k < 32 ? fshr(m[W_L + j], m[W_L + j + 1], k) : m[W_L + j + 1];
+        const u32 hs = shr_plane(m, W_H, j, k), ls = shr_plane(m, W_L, j, k);
         const u32 eq = ~((hs ^ m[W_H + j]) | (ls ^ m[W_L + j]));
         const u32 wvj = m[W_WV + j];
         const u32 nxt = (wvj >> 1) | (j + 1 < nw ? m[W_WV + j + 1] << 31 : 0u);
@@ -174,9 +232,9 @@ ET_FN int prepare_runs(Mem m, int nw, int k) {
 // approx: classes by base composition (#C|A, #G|A, #A of the run's first window) instead of by minimal rotation.
 // Rotation keeps the composition, so these classes are unions of the true ones and their largest total bounds the true
 // largest class from above -- at a fraction of the cost (no k-step rotation loop); used to turn away noisy windows.
-ET_FN int classify_runs(Mem m, int runs, int k, ClsSpill& x, bool approx) {
+template <class K>
+ET_FN int classify_runs(Mem m, int runs, int k, ClsSpill<K>& x, bool approx) {
     int n = 0, ord = 0, j = 0;
-    const u32 km = lowmask(k);
     u32 wvj = m[W_WV], rr = m[W_RS];
     // one loop over the runs, not one per plane word: the lanes of a warp then meet in the body for their r-th run
     // wherever it lies (a per-word loop serialises lanes whose runs start in different words)
@@ -191,19 +249,19 @@ ET_FN int classify_runs(Mem m, int runs, int k, ClsSpill& x, bool approx) {
             u32 z = ~m[W_LINK + j] & (0xffffffffu << b);
             while (!z) { jj++; z = ~m[W_LINK + jj]; }
             const u32 cnt = (u32)(32 * (jj - j) + ffs1(z) - b + 1);
-            // the run's first k-mer, first base most significant (the reference's shift-in order, src/kmer.cpp:2186-2189)
-            const u32 hk = fshr(m[W_H + j], m[W_H + j + 1], b) & km, lk = fshr(m[W_L + j], m[W_L + j + 1], b) & km;
-            u64 key;
-            if (approx) key = (u64)((u32)popc(hk) | ((u32)popc(lk) << 8) | ((u32)popc(hk & lk) << 16));
-            else key = canon((spread(brev32(hk) >> (32 - k)) << 1) | spread(brev32(lk) >> (32 - k)), k);
+            u64 hk, lk;
+            K key = raw_kmer(m, j, b, k, hk, lk, (K)0);
+            if (approx) key = (K)((u32)(popc((u32)hk) + popc((u32)(hk >> 32))) | ((u32)(popc((u32)lk) + popc((u32)(lk >> 32))) << 8) |
+                                  ((u32)(popc((u32)(hk & lk)) + popc((u32)((hk & lk) >> 32))) << 16));
+            else key = canon(key, k);
             const u32 last = c0 + cnt - 1u;
             int q = 0;
             const int nq = n < kClsCap ? n : kClsCap;
-            while (q < nq && cls_key(m, q) != key) q++;
+            while (q < nq && cls_key<K>(m, q) != key) q++;
             if (q < nq) {
-                m[W_CTOT + q] += cnt; m[W_CLAST + q] = last;
+                m[Lay<K>::CTOT + q] += cnt; m[Lay<K>::CLAST + q] = last;
             } else if (n < kClsCap) {
-                m[W_CKEY + 2 * n] = (u32)key; m[W_CKEY + 2 * n + 1] = (u32)(key >> 32); m[W_CTOT + n] = cnt; m[W_CLAST + n] = last;
+                cls_put<K>(m, n, key); m[Lay<K>::CTOT + n] = cnt; m[Lay<K>::CLAST + n] = last;
                 n++;
             } else {
                 int s = 0;
@@ -218,12 +276,13 @@ ET_FN int classify_runs(Mem m, int runs, int k, ClsSpill& x, bool approx) {
 
 // M and K_MER_DATA_MAX_SEQ of the last evaluation: the class whose running count first reaches the final maximum (strict
 // '<' at src/kmer.cpp:2202) = largest total, ties broken by the EARLIEST last window
-ET_FN int cls_max(Mem m, int n, const ClsSpill& x, u64& S) {
+template <class K>
+ET_FN int cls_max(Mem m, int n, const ClsSpill<K>& x, K& S) {
     u32 best = 0;
     S = 0;
     for (int q = 0; q < n && q < kClsCap; q++) {
-        const u32 score = (m[W_CTOT + q] << 10) | (1023u - m[W_CLAST + q]);
-        if (score > best) { best = score; S = cls_key(m, q); }
+        const u32 score = (m[Lay<K>::CTOT + q] << 10) | (1023u - m[Lay<K>::CLAST + q]);
+        if (score > best) { best = score; S = cls_key<K>(m, q); }
     }
     for (int q = 0; q < n - kClsCap; q++) {
         const u32 score = ((u32)x.tot[q] << 10) | (1023u - x.last[q]);
@@ -244,8 +303,9 @@ ET_HD void shrink_valid(Mem m, int nw) {   // valid k-windows -> valid (k+1)-win
 
 // k_mer_check without emission (src/kmer.cpp:2144-2258) on the current window: returns target_k_high | target_k_low << 8;
 // S_h / S_l: the K_MER_DATA_MAX_SEQ of the two (the paired routing compares them between segments)
-ET_FN u32 scan_window(Mem m, int len, int kmin, int kmax, const unsigned short* thr_low, const unsigned short* thr_high, ClsSpill& x,
-                      u64& S_h, u64& S_l) {
+template <class K>
+ET_FN u32 scan_window(Mem m, int len, int kmin, int kmax, const unsigned short* thr_low, const unsigned short* thr_high, ClsSpill<K>& x,
+                      K& S_h, K& S_l) {
     S_h = S_l = 0;
     if (kmax > len) kmax = len;
     if (kmax < kmin) return 0u;
@@ -263,17 +323,17 @@ ET_FN u32 scan_window(Mem m, int len, int kmin, int kmax, const unsigned short* 
     }
     for (int j = 0; j < nw; j++) m[W_WV + j] = m[W_V + j];
     for (int t = 1; t < kmin; t++) shrink_valid(m, nw);
-    u64 blockedL = 0, blockedH = 0;   // periods with an accepted divisor (src/kmer.cpp:2225-2230); k <= 32 here
+    K blockedL = 0, blockedH = 0;     // periods with an accepted divisor (src/kmer.cpp:2225-2230); bit k, k <= kmax
     u32 needL = 0, needH = 0;         // last accepted ratio, m | t << 16
     u32 res = 0;
     for (int k = kmin; k <= kmax; k++, shrink_valid(m, nw)) {
-        const bool blkL = (blockedL >> k) & 1ULL, blkH = (blockedH >> k) & 1ULL;
+        const bool blkL = (bool)((blockedL >> k) & 1), blkH = (bool)((blockedH >> k) & 1);
         // upper bound on the largest class: largest bucket of the (hi parity, lo parity) signature (Lemma L2)
         int T = 0, cH = 0, cL = 0, c11 = 0;
         for (int j = 0; j < nw; j++) {
             const u32 wvj = m[W_WV + j];
-            const u32 dh = ((k < 32 ? fshr(m[W_PH + j], m[W_PH + j + 1], k) : m[W_PH + j + 1]) ^ m[W_PH + j]) & wvj;
-            const u32 dl = ((k < 32 ? fshr(m[W_PL + j], m[W_PL + j + 1], k) : m[W_PL + j + 1]) ^ m[W_PL + j]) & wvj;
+            const u32 dh = (shr_plane(m, W_PH, j, k) ^ m[W_PH + j]) & wvj;
+            const u32 dl = (shr_plane(m, W_PL, j, k) ^ m[W_PL + j]) & wvj;
             T += popc(wvj); cH += popc(dh); cL += popc(dl); c11 += popc(dh & dl);
         }
         if (T == 0) break;   // the valid-window mask only shrinks with k
@@ -283,7 +343,7 @@ ET_FN u32 scan_window(Mem m, int len, int kmin, int kmax, const unsigned short* 
         U = U > c10 ? U : c10;
         U = U > c11 ? U : c11;
         if (!((!blkL && need_pass(thr_low, needL, U, T)) || (!blkH && need_pass(thr_high, needH, U, T)))) continue;
-        u64 S;
+        K S;
         const int runs = prepare_runs(m, nw, k);
         // several runs over few windows (what an N leaves of a window): first the cheap bound from the runs' base
         // compositions.  With many windows it is not worth its price: TTAGGG at k = 5 has ~35 runs per half, half of them in
@@ -297,8 +357,8 @@ ET_FN u32 scan_window(Mem m, int len, int kmin, int kmax, const unsigned short* 
         if (homo(S, k)) continue;
         const bool accL = !blkL && need_pass(thr_low, needL, M, T), accH = !blkH && need_pass(thr_high, needH, M, T);
         if (accL || accH) {
-            u64 mm = 0;
-            for (int j = k; j < 64; j += k) mm |= 1ULL << j;
+            K mm = 0;
+            for (int j = k; j <= kmax; j += k) mm |= ((K)1) << j;
             const u32 need = (u32)M | ((u32)T << 16);
             if (accL) { res = (res & 0xffu) | ((u32)k << 8); needL = need; blockedL |= mm; S_l = S; }
             if (accH) { res = (res & 0xff00u) | (u32)k; needH = need; blockedH |= mm; S_h = S; }
@@ -309,23 +369,23 @@ ET_FN u32 scan_window(Mem m, int len, int kmin, int kmax, const unsigned short* 
 
 enum { T_F = 0, T_B = 2, T_O = 4 };
 
-template <class Emit>
-ET_HD void emit_window_classes(Mem m, int len, int k, int table, bool folded, ClsSpill& x, Emit& emit);
+template <class K, class Emit>
+ET_HD void emit_window_classes(Mem m, int len, int k, int table, bool folded, ClsSpill<K>& x, Emit& emit);
 
 // buffer_task for one read (src/kmer.cpp:111-171).  The read's planes are in W_RH / W_RL / W_RV (zero beyond base n).
 // pm: probes (unit_probes order: left half, right half, whole read -- or the whole read alone when n < 4 * MIN_MER)
 // the filter kernels could not rule out; the scan of any other window finds nothing.  emit(table, k, key, count) receives the emissions.  Returns false when the read is outside this
 // path's limits: then nothing was emitted and the warp kernel has to take it.
-template <class Emit>
+template <class K, class Emit>
 ET_HD bool route_short_thread(Mem m, int n, u32 pm, int min_mer, int max_mer, const unsigned short* thr_low,
                               const unsigned short* thr_high, Emit& emit) {
     if (n < 2 * min_mer) return true;                                   // src/kmer.cpp:113
-    if (max_mer > 32 || n > kMaxRead) return false;                      // outside the limits
+    if (max_mer > (int)(4 * sizeof(K)) || n > kMaxRead) return false;    // outside the limits (K = u64: 32, u128: 64)
     const int kmax = n / 4 < max_mer ? n / 4 : max_mer;
     const int llen = n / 2, rlen = (n + 1) / 2, roff = n - rlen;
-    ClsSpill x;
+    ClsSpill<K> x;
     u32 L = 0, R = 0;   // target_k_high | target_k_low << 8 of the two halves
-    u64 sh, sl;
+    K sh, sl;
     const bool halves = n >= 4 * min_mer;
     if (halves && (pm & 1u)) { set_window(m, 0, llen); L = scan_window(m, llen, min_mer, kmax, thr_low, thr_high, x, sh, sl); }
     if (halves && (pm & 2u)) { set_window(m, roff, rlen); R = scan_window(m, rlen, min_mer, kmax, thr_low, thr_high, x, sh, sl); }   // "always evaluated"
@@ -369,14 +429,14 @@ ET_HD bool route_short_thread(Mem m, int n, u32 pm, int min_mer, int max_mer, co
         if (T == 0) continue;
         const bool target = win == 2;
         if (target) {   // k_mer_target (src/kmer.cpp:1894-2017): largest class no homopolymer and at the baseline, classes RC-folded
-            u64 S;
+            K S;
             const int M = cls_max(m, ncls, x, S);
             if (homo(S, k) || M < (int)(c == 0 ? thr_high : thr_low)[T]) continue;
         }
         for (int q = 0; q < ncls; q++) {
-            u64 key = q < kClsCap ? cls_key(m, q) : x.key[q - kClsCap];
-            const u64 cnt = q < kClsCap ? (u64)m[W_CTOT + q] : (u64)x.tot[q - kClsCap];
-            if (target) { const u64 t = crc(key, k); key = t < key ? t : key; }
+            K key = q < kClsCap ? cls_key<K>(m, q) : x.key[q - kClsCap];
+            const u64 cnt = q < kClsCap ? (u64)m[Lay<K>::CTOT + q] : (u64)x.tot[q - kClsCap];
+            if (target) { const K t = crc(key, k); key = t < key ? t : key; }
             emit(table, k, key, cnt);
         }
     }
@@ -385,8 +445,8 @@ ET_HD bool route_short_thread(Mem m, int n, u32 pm, int min_mer, int max_mer, co
 
 // every class of (current window, k) into `table`, RC-folded on request: the emission half of k_mer_check
 // (src/kmer.cpp:2264-2328)
-template <class Emit>
-ET_HD void emit_window_classes(Mem m, int len, int k, int table, bool folded, ClsSpill& x, Emit& emit) {
+template <class K, class Emit>
+ET_HD void emit_window_classes(Mem m, int len, int k, int table, bool folded, ClsSpill<K>& x, Emit& emit) {
     const int nw = (len + 31) >> 5;
     for (int j = 0; j < nw; j++) m[W_WV + j] = m[W_V + j];
     for (int t = 1; t < k; t++) shrink_valid(m, nw);
@@ -395,9 +455,9 @@ ET_HD void emit_window_classes(Mem m, int len, int k, int table, bool folded, Cl
     if (T == 0) return;
     const int ncls = classify_runs(m, prepare_runs(m, nw, k), k, x, false);
     for (int q = 0; q < ncls; q++) {
-        u64 key = q < kClsCap ? cls_key(m, q) : x.key[q - kClsCap];
-        const u64 cnt = q < kClsCap ? (u64)m[W_CTOT + q] : (u64)x.tot[q - kClsCap];
-        if (folded) { const u64 t = crc(key, k); key = t < key ? t : key; }
+        K key = q < kClsCap ? cls_key<K>(m, q) : x.key[q - kClsCap];
+        const u64 cnt = q < kClsCap ? (u64)m[Lay<K>::CTOT + q] : (u64)x.tot[q - kClsCap];
+        if (folded) { const K t = crc(key, k); key = t < key ? t : key; }
         emit(table, k, key, cnt);
     }
 }
@@ -406,19 +466,19 @@ ET_HD void emit_window_classes(Mem m, int len, int k, int table, bool folded, Cl
 // kernel's route_pair, which this mirrors statement by statement).  load(mate) brings that mate's planes into W_RH /
 // W_RL / W_RV.  Limits: both mates <= 160 bases, MAX_MER <= 32, min(n1, n2) >= 4 * MAX_MER (so the large-k block of
 // src/kmer.cpp:467-505 never runs); false = outside them, nothing emitted.
-template <class Load, class Emit>
+template <class K, class Load, class Emit>
 ET_HD bool route_pair_thread(Mem m, int n1, int n2, int min_mer, int max_mer, const unsigned short* thr_low,
                              const unsigned short* thr_high, Load& load, Emit& emit) {
     const int n = n1 < n2 ? n1 : n2;
     if (n < 2 * min_mer) return true;
-    if (max_mer > 32 || n1 > kMaxRead || n2 > kMaxRead || 4 * max_mer > n) return false;
+    if (max_mer > (int)(4 * sizeof(K)) || n1 > kMaxRead || n2 > kMaxRead || 4 * max_mer > n) return false;
     const int kmax = n / 4 < max_mer ? n / 4 : max_mer;
     // segments in fragment order: R1 left, R1 right, R2 right, R2 left (src/kmer.cpp:338-340)
     const int soff[5] = {0, 0, n1 - (n1 + 1) / 2, n2 - (n2 + 1) / 2, 0};
     const int slen[5] = {0, n1 / 2, (n1 + 1) / 2, (n2 + 1) / 2, n2 / 2};
-    ClsSpill x;
+    ClsSpill<K> x;
     u32 res[5] = {0, 0, 0, 0, 0};
-    u64 S[5][2];
+    K S[5][2];
     bool have[5] = {false, false, false, false, false};
     int cur_mate = -1;
     auto window = [&](int t) {
@@ -436,7 +496,7 @@ ET_HD bool route_pair_thread(Mem m, int n1, int n2, int min_mer, int max_mer, co
     int pseg[2][8], ptmp[2][8], np[2] = {0, 0};
     int si[2] = {1, 1}, km[2] = {0, 0};
     bool ended[2] = {false, false};
-    u64 ks[2] = {0, 0};
+    K ks[2] = {0, 0};
     for (int ti = 1; ti <= 4 && !(ended[0] && ended[1]); ti++) {   // forward walk
         scan(ti);
         for (int c = 0; c < 2; c++) {
@@ -444,7 +504,7 @@ ET_HD bool route_pair_thread(Mem m, int n1, int n2, int min_mer, int max_mer, co
             if (!ended[c] && k) { pseg[c][np[c]] = ti; ptmp[c][np[c]] = ti <= 2 ? 0 : 1; np[c]++; }   // emission before the test
             bool ok = !ended[c] && k > 0;
             if (ok && ti != 1) {
-                const u64 ds = ti > 2 ? crc(S[ti][c], k) : S[ti][c];   // get_dir_seq, src/kmer.cpp:307-313
+                const K ds = ti > 2 ? crc(S[ti][c], k) : S[ti][c];   // get_dir_seq, src/kmer.cpp:307-313
                 ok = km[c] == k && ks[c] == ds;
             }
             if (ok) { si[c]++; km[c] = k; if (ti == 1) ks[c] = S[ti][c]; }
@@ -470,7 +530,7 @@ ET_HD bool route_pair_thread(Mem m, int n1, int n2, int min_mer, int max_mer, co
                 if (!ended[c] && k) { pseg[c][np[c]] = tj; ptmp[c][np[c]] = tj <= 2 ? 1 : 0; np[c]++; }
                 bool ok = sj[c] >= si[c] && !ended[c] && k > 0;
                 if (ok && tj != 4) {
-                    const u64 ds = tj <= 2 ? crc(S[tj][c], k) : S[tj][c];
+                    const K ds = tj <= 2 ? crc(S[tj][c], k) : S[tj][c];
                     ok = km[c] == k && ks[c] == ds;
                 }
                 if (ok) { sj[c]--; km[c] = k; if (tj == 4) ks[c] = S[tj][c]; }
@@ -511,7 +571,7 @@ struct LongGeom {   // src/kmer.cpp:790-798
 // step 1 for one slice: load(off, len) brings bases [off, off + len) of the read into W_RH / W_RL / W_RV
 template <class Load>
 ET_HD u32 long_slice_stats(Mem m, const LongGeom& g, int t, int min_mer, int max_mer, const unsigned short* thr_low,
-                           const unsigned short* thr_high, Load& load, ClsSpill& x) {
+                           const unsigned short* thr_high, Load& load, ClsSpill<u64>& x) {
     const int len = g.len(t);
     load(g.start(t), len);
     set_window(m, 0, len);
@@ -579,7 +639,7 @@ ET_HD bool long_walk(const LongGeom& g, Stat& stat, Task& task) {
 
 // step 3 for one emission
 template <class Load, class Emit>
-ET_HD void long_emit(Mem m, const LongGeom& g, const LongTask& tk, Load& load, ClsSpill& x, Emit& emit) {
+ET_HD void long_emit(Mem m, const LongGeom& g, const LongTask& tk, Load& load, ClsSpill<u64>& x, Emit& emit) {
     const int len = g.len(tk.slice);
     load(g.start(tk.slice), len);
     set_window(m, 0, len);

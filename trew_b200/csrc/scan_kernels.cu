@@ -1660,7 +1660,15 @@ constexpr u32 kStageLock = 0xffffffffu;     // s_meta: 0 empty, kStageLock being
 struct StageEmit {
     u32* s_meta; u32* s_cnt; u64* s_key;    // shared
     Slot* slots; u32 mask; u32* err;        // global table
-    __device__ __forceinline__ void operator()(int table, int k, u64 key, u64 count) const {
+    // 128-bit keys (units above 32 bases): staged when they fit 64 bits (the period is part of the tag), else -- a unit of 33+
+    // bases whose first bases are not all T, rarely the same one twice in a block -- straight to the global table
+    __device__ __forceinline__ void operator()(int table, int k, et::u128 key, u64 count) const {
+        const u64 hi = (u64)(key >> 64);
+        if (hi) table_add_impl(slots, mask, err, ((u32)table << 8) | (u32)k, (u64)key, hi, count);
+        else (*this)(table, k, (et::u64)key, count);
+    }
+    __device__ __forceinline__ void operator()(int table, int k, et::u64 key_, u64 count) const {
+        const u64 key = (u64)key_;
         const u32 meta = ((u32)table << 8) | (u32)k, tag = meta | 0x80000000u;
         u32 i = (u32)(mix64(key ^ ((u64)meta << 53)) >> 40) & (kStageSlots - 1);
         bool done = false;
@@ -1689,7 +1697,9 @@ struct StageEmit {
 #ifndef TREW_THREAD_BLOCK
 #define TREW_THREAD_BLOCK 128
 #endif
-constexpr size_t kThreadKernelSmem = (size_t)et::kWorkWords * TREW_THREAD_BLOCK * sizeof(u32) + (size_t)kStageSlots * 16;
+template <class K>
+constexpr size_t thread_kernel_smem() { return (size_t)et::Lay<K>::WORDS * TREW_THREAD_BLOCK * sizeof(u32) + (size_t)kStageSlots * 16; }
+constexpr size_t kThreadKernelSmem = thread_kernel_smem<et::u64>();   // 4 blocks per SM; the 128-bit instantiation: 3
 
 // brings one read's planes (bit offset b0, len bases) into the thread's workspace
 struct PlaneLoad {
@@ -1706,14 +1716,14 @@ struct PlaneLoad {
     }
 };
 
-template <int MODE>   // 0 short single-end, 1 paired
+template <int MODE, class K>   // MODE 0 short single-end, 1 paired; K: u64 (MAX_MER <= 32) or u128 (<= 64)
 __global__ void __launch_bounds__(TREW_THREAD_BLOCK, 4) trew_exact_thread_kernel(DevCfg cfg, DevBatch b, const u32* __restrict__ survivors,
                                                                               const u32* __restrict__ n_survivors, int packed_probes,
                                                                               u32* __restrict__ hard, u32* __restrict__ n_hard,
                                                                               unsigned long long* total_survivors, u32 exp_flags) {
     // word i of thread t's workspace at work[i * blockDim + t]: no bank conflicts
     u32* work = reinterpret_cast<u32*>(g_smem);
-    u64* s_key = reinterpret_cast<u64*>(work + et::kWorkWords * TREW_THREAD_BLOCK);
+    u64* s_key = reinterpret_cast<u64*>(work + et::Lay<K>::WORDS * TREW_THREAD_BLOCK);
     u32* s_meta = reinterpret_cast<u32*>(s_key + kStageSlots);
     u32* s_cnt = s_meta + kStageSlots;
     for (int i = threadIdx.x; i < kStageSlots; i += blockDim.x) { s_meta[i] = 0u; s_cnt[i] = 0u; }
@@ -1740,13 +1750,13 @@ __global__ void __launch_bounds__(TREW_THREAD_BLOCK, 4) trew_exact_thread_kernel
                 } else {
                     PlaneLoad load{m, b.hi, b.lo, b.val, {b0, 0u}, {len, 0}};
                     load(0);
-                    bail = !et::route_short_thread(m, len, pm & 7u, cfg.min_mer, cfg.max_mer, cfg.thr_low, cfg.thr_high, emit);
+                    bail = !et::route_short_thread<K>(m, len, pm & 7u, cfg.min_mer, cfg.max_mer, cfg.thr_low, cfg.thr_high, emit);
                 }
             } else {
                 const u32 a0 = __ldg(b.bit_off + 2 * u), a1 = __ldg(b.bit_off + 2 * u + 1), a2 = __ldg(b.bit_off + 2 * u + 2);
                 const int n1 = (int)(a1 - a0), n2 = (int)(a2 - a1);
                 PlaneLoad load{m, b.hi, b.lo, b.val, {a0, a1}, {n1, n2}};
-                bail = !et::route_pair_thread(m, n1, n2, cfg.min_mer, cfg.max_mer, cfg.thr_low, cfg.thr_high, load, emit);
+                bail = !et::route_pair_thread<K>(m, n1, n2, cfg.min_mer, cfg.max_mer, cfg.thr_low, cfg.thr_high, load, emit);
             }
         }
         list_append(bail, entry, hard, n_hard);
@@ -1792,7 +1802,7 @@ __global__ void __launch_bounds__(TREW_THREAD_BLOCK, 4) trew_long_stats_kernel(D
     const et::Mem m{work + threadIdx.x, TREW_THREAD_BLOCK};
     const u32 n = min(*a.n_survivors, a.s_cap);
     const u32 warps = gridDim.x * (blockDim.x >> 5), lane = lane_id();
-    et::ClsSpill x;
+    et::ClsSpill<et::u64> x;
     for (u32 idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); idx < n; idx += warps) {
         u32 u = a.survivors[idx];
         if (a.packed_probes) u &= (1u << kProbeShift) - 1u;
@@ -1856,7 +1866,7 @@ __global__ void __launch_bounds__(TREW_THREAD_BLOCK, 4) trew_long_emit_kernel(De
     StageEmit emit{s_meta, s_cnt, s_key, cfg.slots, cfg.slot_mask, cfg.error_flag};
     const u32 n = min(*a.n_survivors, a.s_cap);
     const u32 warps = gridDim.x * (blockDim.x >> 5), lane = lane_id();
-    et::ClsSpill x;
+    et::ClsSpill<et::u64> x;
     for (u32 idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); idx < n; idx += warps) {
         u32 u = a.survivors[idx];
         if (a.packed_probes) u &= (1u << kProbeShift) - 1u;
@@ -1911,7 +1921,7 @@ void launch_long_thread(const DevCfg& cfg, const DevBatch& b, const unsigned int
 
 // true when the thread kernel can take (most of) a batch: short single-end or paired mode, 64-bit units
 bool thread_path_applies(const DevCfg& cfg, unsigned int max_read_len) {
-    if (cfg.max_mer > 32) return false;
+    if (cfg.max_mer > 64) return false;
     if (cfg.mode == 0) return true;
     return cfg.mode == 1 && max_read_len >= 4u * (unsigned)cfg.max_mer;   // pairs below 4 * MAX_MER all take the large-k block
 }
@@ -1919,12 +1929,13 @@ bool thread_path_applies(const DevCfg& cfg, unsigned int max_read_len) {
 void launch_exact_thread(const DevCfg& cfg, const DevBatch& b, const unsigned int* survivors, const unsigned int* n_survivors,
                          int packed_probes, unsigned int* hard, unsigned int* n_hard, unsigned long long* total_survivors, int blocks,
                          unsigned int exp_flags, cudaStream_t stream) {
-    if (cfg.mode == 0)
-        trew_exact_thread_kernel<0><<<blocks, TREW_THREAD_BLOCK, kThreadKernelSmem, stream>>>(cfg, b, survivors, n_survivors, packed_probes,
-                                                                                              hard, n_hard, total_survivors, exp_flags);
-    else
-        trew_exact_thread_kernel<1><<<blocks, TREW_THREAD_BLOCK, kThreadKernelSmem, stream>>>(cfg, b, survivors, n_survivors, packed_probes,
-                                                                                              hard, n_hard, total_survivors, exp_flags);
+    const bool wide = cfg.max_mer > 32;
+#define TREW_LAUNCH_THREAD(MODE, K)                                                                                               \
+    trew_exact_thread_kernel<MODE, K><<<blocks, TREW_THREAD_BLOCK, thread_kernel_smem<K>(), stream>>>(                            \
+        cfg, b, survivors, n_survivors, packed_probes, hard, n_hard, total_survivors, exp_flags)
+    if (cfg.mode == 0) { if (wide) TREW_LAUNCH_THREAD(0, et::u128); else TREW_LAUNCH_THREAD(0, et::u64); }
+    else               { if (wide) TREW_LAUNCH_THREAD(1, et::u128); else TREW_LAUNCH_THREAD(1, et::u64); }
+#undef TREW_LAUNCH_THREAD
 }
 
 template <int MODE>
@@ -1961,8 +1972,10 @@ cudaError_t prepare_exact(int run_cap_max) {
     cudaError_t e = cudaFuncSetAttribute(trew_exact_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(trew_exact_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(trew_exact_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(trew_exact_thread_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kThreadKernelSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(trew_exact_thread_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kThreadKernelSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(trew_exact_thread_kernel<0, et::u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thread_kernel_smem<et::u64>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(trew_exact_thread_kernel<1, et::u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thread_kernel_smem<et::u64>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(trew_exact_thread_kernel<0, et::u128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thread_kernel_smem<et::u128>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(trew_exact_thread_kernel<1, et::u128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thread_kernel_smem<et::u128>());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(trew_long_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kThreadKernelSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(trew_long_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kThreadKernelSmem);
     return e;
