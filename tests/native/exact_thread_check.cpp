@@ -22,6 +22,21 @@ int code_of(unsigned char ch) {   // codes[], src/kmer.cpp:14-31: T=0 G=1 C=2 A=
     }
 }
 typedef std::map<std::tuple<int, int, uint64_t, uint64_t>, uint64_t> Tables;   // (table, k, key hi, key lo) -> count
+// bases [off, off + len) of mate `mate` become the current window (what the device's PlaneLoad does from the packed batch)
+struct StringLoad {
+    Mem m; const char* s[2];
+    void operator()(int mate, int off, int len) const {
+        for (int j = 0; j < kReadWords + 2; j++) { m[W_H + j] = 0; m[W_L + j] = 0; }
+        for (int j = 0; j < kReadWords; j++) m[W_V + j] = 0;
+        for (int i = 0; i < len; i++) {
+            const int c = code_of((unsigned char)s[mate][off + i]);
+            if (c >= 0) {
+                m[W_V + (i >> 5)] |= 1u << (i & 31); m[W_H + (i >> 5)] |= (u32)(c >> 1) << (i & 31);
+                m[W_L + (i >> 5)] |= (u32)(c & 1) << (i & 31);
+            }
+        }
+    }
+};
 struct Collect {
     Tables* m;
     void operator()(int table, int k, u64 key, uint64_t count) { (*m)[std::make_tuple(table, k, (uint64_t)0, key)] += count; }
@@ -54,15 +69,8 @@ long scan_reads(const char* buf, const int32_t* locs, int n_reads, int min_mer, 
         Mem m{work, 1};
         bool ok = true;
         if (n <= kMaxRead) {
-            for (int j = 0; j < kReadWords + 2; j++) { m[W_RH + j] = 0; m[W_RL + j] = 0; m[W_RV + j] = 0; }
-            for (int i = 0; i < n; i++) {
-                const int c = code_of((unsigned char)buf[st + i]);
-                if (c >= 0) {
-                    m[W_RV + (i >> 5)] |= 1u << (i & 31); m[W_RH + (i >> 5)] |= (u32)(c >> 1) << (i & 31);
-                    m[W_RL + (i >> 5)] |= (u32)(c & 1) << (i & 31);
-                }
-            }
-            ok = route_short_thread<K>(m, n, 7u, min_mer, max_mer, thr_low, thr_high, emit);
+            StringLoad load{m, {buf + st, nullptr}};
+            ok = route_short_thread<K>(m, n, 7u, min_mer, max_mer, thr_low, thr_high, load, emit);
         } else {
             ok = n < 2 * min_mer;
         }
@@ -72,21 +80,6 @@ long scan_reads(const char* buf, const int32_t* locs, int n_reads, int min_mer, 
 }
 }  // namespace
 
-namespace {
-struct StringLoad {
-    Mem m; const char* s[2]; int n[2];
-    void operator()(int mate) const {
-        for (int j = 0; j < kReadWords + 2; j++) { m[W_RH + j] = 0; m[W_RL + j] = 0; m[W_RV + j] = 0; }
-        for (int i = 0; i < n[mate]; i++) {
-            const int c = code_of((unsigned char)s[mate][i]);
-            if (c >= 0) {
-                m[W_RV + (i >> 5)] |= 1u << (i & 31); m[W_RH + (i >> 5)] |= (u32)(c >> 1) << (i & 31);
-                m[W_RL + (i >> 5)] |= (u32)(c & 1) << (i & 31);
-            }
-        }
-    }
-};
-}  // namespace
 
 namespace {
 template <class K>
@@ -100,7 +93,7 @@ long scan_pairs(const char* buf1, const int32_t* locs1, const char* buf2, const 
         u32 work[Lay<K>::WORDS];
         memset(work, 0xA5, sizeof(work));
         Mem m{work, 1};
-        StringLoad load{m, {buf1 + locs1[2 * r], buf2 + locs2[2 * r]}, {n1 <= kMaxRead ? n1 : 0, n2 <= kMaxRead ? n2 : 0}};
+        StringLoad load{m, {buf1 + locs1[2 * r], buf2 + locs2[2 * r]}};
         const bool ok = route_pair_thread<K>(m, n1, n2, min_mer, max_mer, thr_low, thr_high, load, emit);
         if (!ok) { if (bailed_index) bailed_index[bailed] = r; bailed++; }
     }
@@ -108,21 +101,6 @@ long scan_pairs(const char* buf1, const int32_t* locs1, const char* buf2, const 
 }
 }  // namespace
 
-namespace {
-struct OffsetLoad {   // bases [off, off + len) of one read
-    Mem m; const char* s;
-    void operator()(int off, int len) const {
-        for (int j = 0; j < kReadWords + 2; j++) { m[W_RH + j] = 0; m[W_RL + j] = 0; m[W_RV + j] = 0; }
-        for (int i = 0; i < len; i++) {
-            const int c = code_of((unsigned char)s[off + i]);
-            if (c >= 0) {
-                m[W_RV + (i >> 5)] |= 1u << (i & 31); m[W_RH + (i >> 5)] |= (u32)(c >> 1) << (i & 31);
-                m[W_RL + (i >> 5)] |= (u32)(c & 1) << (i & 31);
-            }
-        }
-    }
-};
-}  // namespace
 
 extern "C" {
 
@@ -175,10 +153,10 @@ long etc_scan_long(const char* buf, const int32_t* locs, int n_reads, int min_me
     for (int r = 0; r < n_reads; r++) {
         const int st = locs[2 * r], n = locs[2 * r + 1] >= st ? locs[2 * r + 1] - st + 1 : 0;
         if (n < slice_len) continue;   // the reader drops these (src/kmer.cpp:1184)
-        u32 work[kWorkWords];
+        u32 work[Lay<u64>::WORDS];
         memset(work, 0xA5, sizeof(work));
         Mem m{work, 1};
-        OffsetLoad load{m, buf + st};
+        StringLoad load{m, {buf + st, nullptr}};
         ClsSpill<u64> x;
         bool ok = max_mer <= 32 && slice_len <= kMaxRead;
         if (ok) {

@@ -165,7 +165,7 @@ size_t scratch_need(const trew_ctx* ctx, uint32_t max_read_len, uint32_t n_units
 constexpr int kScanCounters = 8;
 
 static int env_blocks_thread() {   // TREW_GRID_THREAD: thread-kernel blocks per SM (experiments)
-    static const int v = [] { const char* e = getenv("TREW_GRID_THREAD"); int x = e && *e ? atoi(e) : 4; return x > 0 ? x : 4; }();
+    static const int v = [] { const char* e = getenv("TREW_GRID_THREAD"); int x = e && *e ? atoi(e) : 0; return x > 0 ? x : 0; }();
     return v;
 }
 
@@ -182,7 +182,7 @@ int launch_scan(trew_ctx* ctx, const DevBatch& b, uint32_t n_units, uint32_t max
         *scratch_bytes = need;
     }
     ctx->export_valid = false;
-    // d_counters: [0] survivors (list A) [1] work counter [2] deferred [3] thread-kernel bails [4] survivors, list B [5] work counter
+    // d_counters: [0] survivors (list A) [1] work counter [2] deferred [3] thread-kernel bails [4] survivors, list B [5] work counter [6] work counter of the thread kernel
     CK(cudaMemsetAsync(d_counters, 0, kScanCounters * sizeof(unsigned int), st));
     if (ev) CK(cudaEventRecord(ev[0], st));
     const bool thread_path = thread_path_applies(ctx->dcfg, max_read_len) && !(ctx->exact_flags & 4u) && n_units < (1u << 28);
@@ -199,7 +199,7 @@ int launch_scan(trew_ctx* ctx, const DevBatch& b, uint32_t n_units, uint32_t max
         // list A: thread per survivor; what it cannot take after all (its length limits) lands in the dead deferred list
         unsigned int* hard = d_survivors + n_units;
         launch_exact_thread(ctx->dcfg, b, d_survivors, d_counters, a.packed_probes, hard, d_counters + 3, ctx->d_total_surv,
-                            ctx->sm_count * env_blocks_thread(), ctx->exact_flags, st);
+                            ctx->sm_count, env_blocks_thread(), d_counters + 6, st);
         // list B (downwards from the top of the survivor array): warp per survivor
         ExactArgs ab = a;
         ab.survivors = d_survivors + n_units - 1; ab.reverse = 1; ab.n_survivors = d_counters + 4;

@@ -41,18 +41,18 @@ constexpr int kClsCap = 6;         // distinct rotation classes of an evaluated 
 constexpr int kClsSpill = kMaxRead - kClsCap;   // ... the rest (noisy windows, rare) in thread-local memory
 constexpr int kApproxMaxWindows = 48;           // scan_window: composition pre-pass only for periods with at most this many windows
 
-// workspace words of one thread (the class keys at the end take 2 words each for 64-bit units, 4 for 128-bit ones: Lay<K>)
+// workspace words of one thread.  The read itself stays in global memory: a window is brought in by the caller's
+// load(mate, off, len), which fills W_H / W_L (kReadWords + 2 words each, zero beyond the window) and W_V (kReadWords).
 enum {
-    W_RH = 0, W_RL = W_RH + kReadWords + 2, W_RV = W_RL + kReadWords + 2,     // the read's planes (+ zero words behind)
-    W_H = W_RV + kReadWords + 2, W_L = W_H + kReadWords + 2, W_V = W_L + kReadWords + 2,   // the current window
-    W_PH = W_V + kReadWords + 2, W_PL = W_PH + kReadWords + 2,               // its exclusive prefix-XOR planes
-    W_WV = W_PL + kReadWords + 2, W_LINK = W_WV + kReadWords, W_RS = W_LINK + kReadWords,   // valid windows, links, run starts
-    W_CKEY = W_RS + kReadWords                                               // class keys, least significant word first
+    W_H = 0, W_L = W_H + kReadWords + 2, W_V = W_L + kReadWords + 2,          // the current window: hi / lo / valid planes
+    W_PH = W_V + kReadWords, W_PL = W_PH + kReadWords + 2,                   // its exclusive prefix-XOR planes
+    W_WV = W_PL + kReadWords + 2, W_LINK = W_WV + kReadWords,                // valid k-windows, links between neighbours
+    W_CKEY = W_LINK + kReadWords                                             // class keys, least significant word first
 };
 template <class K>
-struct Lay {
+struct Lay {   // ... then per class: the key (2 or 4 words) and total << 16 | last window
     static constexpr int KW = (int)(sizeof(K) / 4);
-    static constexpr int CTOT = W_CKEY + KW * kClsCap, CLAST = CTOT + kClsCap, WORDS = CLAST + kClsCap;
+    static constexpr int CT = W_CKEY + KW * kClsCap, WORDS = CT + kClsCap;
 };
 constexpr int kWorkWords = Lay<u64>::WORDS;
 
@@ -146,21 +146,6 @@ ET_HD bool homo(u128 w, int k) {
     return k <= 1 || ((w ^ (w >> 2)) & ((((u128)1) << (2 * (k - 1))) - 1)) == 0;
 }
 
-// bases [off, off + len) of the read (W_RH / W_RL / W_RV) become the current window (W_H / W_L / W_V)
-ET_FN void set_window(Mem m, int off, int len) {
-    const int nw = (len + 31) >> 5, jo = off >> 5, sh = off & 31;
-    for (int j = 0; j < kReadWords + 2; j++) {
-        u32 h = 0, l = 0, v = 0;
-        if (j < nw) {
-            const u32 msk = lowmask(len - 32 * j);
-            h = fshr(m[W_RH + jo + j], m[W_RH + jo + j + 1], sh) & msk;
-            l = fshr(m[W_RL + jo + j], m[W_RL + jo + j + 1], sh) & msk;
-            v = fshr(m[W_RV + jo + j], m[W_RV + jo + j + 1], sh) & msk;
-        }
-        m[W_H + j] = h; m[W_L + j] = l; m[W_V + j] = v;
-    }
-}
-
 // the spill part of a class list (classes beyond the first kClsCap of an evaluation)
 template <class K>
 struct ClsSpill {
@@ -209,7 +194,10 @@ ET_HD u128 raw_kmer(Mem m, int j, int b, int k, u64& hk, u64& lk, u128) {
 
 // Match-bit runs of the current window for one period (Lemma L1: windows i and i+1 are in the same rotation class iff
 // both are valid and base[i] == base[i+k], so classes are unions of maximal runs).  W_WV = valid k-windows (input);
-// fills W_LINK and W_RS (run starts) and returns the number of runs.
+// fills W_LINK and returns the number of runs.
+ET_HD u32 run_starts(Mem m, int j) {   // valid windows of word j without a link from their predecessor
+    return m[W_WV + j] & ~((m[W_LINK + j] << 1) | (j ? m[W_LINK + j - 1] >> 31 : 0u));
+}
 ET_FN int prepare_runs(Mem m, int nw, int k) {
     for (int j = 0; j < nw; j++) {
         const u32 hs = shr_plane(m, W_H, j, k), ls = shr_plane(m, W_L, j, k);
@@ -219,11 +207,7 @@ ET_FN int prepare_runs(Mem m, int nw, int k) {
         m[W_LINK + j] = eq & wvj & nxt;
     }
     int runs = 0;
-    for (int j = 0; j < nw; j++) {
-        const u32 rs = m[W_WV + j] & ~((m[W_LINK + j] << 1) | (j ? m[W_LINK + j - 1] >> 31 : 0u));
-        m[W_RS + j] = rs;
-        runs += popc(rs);
-    }
+    for (int j = 0; j < nw; j++) runs += popc(run_starts(m, j));
     return runs;
 }
 
@@ -232,14 +216,18 @@ ET_FN int prepare_runs(Mem m, int nw, int k) {
 // approx: classes by base composition (#C|A, #G|A, #A of the run's first window) instead of by minimal rotation.
 // Rotation keeps the composition, so these classes are unions of the true ones and their largest total bounds the true
 // largest class from above -- at a fraction of the cost (no k-step rotation loop); used to turn away noisy windows.
+// T, need_min: the windows of the evaluation and the smallest largest-class total anybody is interested in; the pass
+// stops (returns -1) as soon as the largest class so far plus every window not yet seen cannot reach it -- a noisy window
+// (one run per k-window, ever more classes to search) is turned away about half way through.  need_min = 0: full statistics.
 template <class K>
-ET_FN int classify_runs(Mem m, int runs, int k, ClsSpill<K>& x, bool approx) {
-    int n = 0, ord = 0, j = 0;
-    u32 wvj = m[W_WV], rr = m[W_RS];
+ET_FN int classify_runs(Mem m, int runs, int k, ClsSpill<K>& x, bool approx, int T = 0, int need_min = 0) {
+    int n = 0, ord = 0, j = 0, best = 0;
+    const int slack = T - need_min;   // windows seen outside the largest class may not exceed this
+    u32 wvj = m[W_WV], rr = run_starts(m, 0);
     // one loop over the runs, not one per plane word: the lanes of a warp then meet in the body for their r-th run
     // wherever it lies (a per-word loop serialises lanes whose runs start in different words)
     for (int r = 0; r < runs; r++) {
-        while (!rr) { ord += popc(wvj); j++; rr = m[W_RS + j]; wvj = m[W_WV + j]; }
+        while (!rr) { ord += popc(wvj); j++; rr = run_starts(m, j); wvj = m[W_WV + j]; }
         {
             const int b = ffs1(rr);
             rr &= rr - 1;
@@ -258,16 +246,24 @@ ET_FN int classify_runs(Mem m, int runs, int k, ClsSpill<K>& x, bool approx) {
             int q = 0;
             const int nq = n < kClsCap ? n : kClsCap;
             while (q < nq && cls_key<K>(m, q) != key) q++;
+            u32 tot = cnt;
             if (q < nq) {
-                m[Lay<K>::CTOT + q] += cnt; m[Lay<K>::CLAST + q] = last;
+                const u32 ct = (m[Lay<K>::CT + q] & 0xffff0000u) + (cnt << 16);
+                m[Lay<K>::CT + q] = ct | last;
+                tot = ct >> 16;
             } else if (n < kClsCap) {
-                cls_put<K>(m, n, key); m[Lay<K>::CTOT + n] = cnt; m[Lay<K>::CLAST + n] = last;
+                cls_put<K>(m, n, key); m[Lay<K>::CT + n] = (cnt << 16) | last;
                 n++;
             } else {
                 int s = 0;
                 while (s < n - kClsCap && x.key[s] != key) s++;
-                if (s < n - kClsCap) { x.tot[s] = (unsigned short)(x.tot[s] + cnt); x.last[s] = (unsigned short)last; }
+                if (s < n - kClsCap) { tot = x.tot[s] + cnt; x.tot[s] = (unsigned short)tot; x.last[s] = (unsigned short)last; }
                 else { x.key[s] = key; x.tot[s] = (unsigned short)cnt; x.last[s] = (unsigned short)last; n++; }
+            }
+            if (need_min > 0) {
+                // seen = last + 1 windows so far, `best` of them in the largest class: best + (T - seen) >= need_min must stay possible
+                best = (int)tot > best ? (int)tot : best;
+                if ((int)last + 1 - best > slack) return -1;
             }
         }
     }
@@ -281,7 +277,8 @@ ET_FN int cls_max(Mem m, int n, const ClsSpill<K>& x, K& S) {
     u32 best = 0;
     S = 0;
     for (int q = 0; q < n && q < kClsCap; q++) {
-        const u32 score = (m[Lay<K>::CTOT + q] << 10) | (1023u - m[Lay<K>::CLAST + q]);
+        const u32 ct = m[Lay<K>::CT + q];
+        const u32 score = ((ct >> 16) << 10) | (1023u - (ct & 0xffffu));
         if (score > best) { best = score; S = cls_key<K>(m, q); }
     }
     for (int q = 0; q < n - kClsCap; q++) {
@@ -295,6 +292,13 @@ ET_FN int cls_max(Mem m, int n, const ClsSpill<K>& x, K& S) {
 ET_HD bool need_pass(const unsigned short* thr, u32 need, int M, int T) {
     const u32 mm = need & 0xffffu, t = need >> 16;
     return M >= (int)thr[T] && (t == 0u || (u32)M * t >= mm * (u32)T);
+}
+
+// the smallest M need_pass lets through (M only grows the left sides)
+ET_HD int min_accept(const unsigned short* thr, u32 need, int T) {
+    const u32 mm = need & 0xffffu, t = need >> 16;
+    const int a = (int)thr[T], b = t ? (int)((mm * (u32)T + t - 1u) / t) : 0;
+    return a > b ? a : b;
 }
 
 ET_HD void shrink_valid(Mem m, int nw) {   // valid k-windows -> valid (k+1)-windows
@@ -345,14 +349,20 @@ ET_FN u32 scan_window(Mem m, int len, int kmin, int kmax, const unsigned short* 
         if (!((!blkL && need_pass(thr_low, needL, U, T)) || (!blkH && need_pass(thr_high, needH, U, T)))) continue;
         K S;
         const int runs = prepare_runs(m, nw, k);
+        int need_min = 1 << 20;
+        if (!blkL) need_min = min_accept(thr_low, needL, T);
+        if (!blkH) { const int a = min_accept(thr_high, needH, T); need_min = a < need_min ? a : need_min; }
         // several runs over few windows (what an N leaves of a window): first the cheap bound from the runs' base
         // compositions.  With many windows it is not worth its price: TTAGGG at k = 5 has ~35 runs per half, half of them in
         // one class AND one composition, so the bound never rejects there (measured: 5 % of the kernel).
         if (runs > 3 && T <= kApproxMaxWindows) {
-            const int Mu = cls_max(m, classify_runs(m, runs, k, x, true), x, S);
+            const int na = classify_runs(m, runs, k, x, true, T, need_min);
+            if (na < 0) continue;
+            const int Mu = cls_max(m, na, x, S);
             if (!((!blkL && need_pass(thr_low, needL, Mu, T)) || (!blkH && need_pass(thr_high, needH, Mu, T)))) continue;
         }
-        const int n = classify_runs(m, runs, k, x, false);
+        const int n = classify_runs(m, runs, k, x, false, T, need_min);
+        if (n < 0) continue;
         const int M = cls_max(m, n, x, S);
         if (homo(S, k)) continue;
         const bool accL = !blkL && need_pass(thr_low, needL, M, T), accH = !blkH && need_pass(thr_high, needH, M, T);
@@ -372,13 +382,13 @@ enum { T_F = 0, T_B = 2, T_O = 4 };
 template <class K, class Emit>
 ET_HD void emit_window_classes(Mem m, int len, int k, int table, bool folded, ClsSpill<K>& x, Emit& emit);
 
-// buffer_task for one read (src/kmer.cpp:111-171).  The read's planes are in W_RH / W_RL / W_RV (zero beyond base n).
+// buffer_task for one read (src/kmer.cpp:111-171).  load(0, off, len) brings bases [off, off + len) of the read in.
 // pm: probes (unit_probes order: left half, right half, whole read -- or the whole read alone when n < 4 * MIN_MER)
 // the filter kernels could not rule out; the scan of any other window finds nothing.  emit(table, k, key, count) receives the emissions.  Returns false when the read is outside this
 // path's limits: then nothing was emitted and the warp kernel has to take it.
-template <class K, class Emit>
+template <class K, class Load, class Emit>
 ET_HD bool route_short_thread(Mem m, int n, u32 pm, int min_mer, int max_mer, const unsigned short* thr_low,
-                              const unsigned short* thr_high, Emit& emit) {
+                              const unsigned short* thr_high, Load& load, Emit& emit) {
     if (n < 2 * min_mer) return true;                                   // src/kmer.cpp:113
     if (max_mer > (int)(4 * sizeof(K)) || n > kMaxRead) return false;    // outside the limits (K = u64: 32, u128: 64)
     const int kmax = n / 4 < max_mer ? n / 4 : max_mer;
@@ -387,8 +397,8 @@ ET_HD bool route_short_thread(Mem m, int n, u32 pm, int min_mer, int max_mer, co
     u32 L = 0, R = 0;   // target_k_high | target_k_low << 8 of the two halves
     K sh, sl;
     const bool halves = n >= 4 * min_mer;
-    if (halves && (pm & 1u)) { set_window(m, 0, llen); L = scan_window(m, llen, min_mer, kmax, thr_low, thr_high, x, sh, sl); }
-    if (halves && (pm & 2u)) { set_window(m, roff, rlen); R = scan_window(m, rlen, min_mer, kmax, thr_low, thr_high, x, sh, sl); }   // "always evaluated"
+    if (halves && (pm & 1u)) { load(0, 0, llen); L = scan_window(m, llen, min_mer, kmax, thr_low, thr_high, x, sh, sl); }
+    if (halves && (pm & 2u)) { load(0, roff, rlen); R = scan_window(m, rlen, min_mer, kmax, thr_low, thr_high, x, sh, sl); }   // "always evaluated"
     if (4 * max_mer > n) {
         // short reads: periods above n / 4 are looked for in the whole read, for the selections that found nothing in
         // either half; their classes go into 'both' UN-folded (src/kmer.cpp:165-171).  The probe of this scan is bit 2
@@ -397,11 +407,11 @@ ET_HD bool route_short_thread(Mem m, int n, u32 pm, int min_mer, int max_mer, co
         const u32 wbit = halves ? 4u : 1u;
         if ((hc0 || hc1) && (pm & wbit)) {
             const int lo = n / 4 + 1 > min_mer ? n / 4 + 1 : min_mer, hi = n / 2 < max_mer ? n / 2 : max_mer;
-            set_window(m, 0, n);
+            load(0, 0, n);
             const u32 W = scan_window(m, n, lo, hi, thr_low, thr_high, x, sh, sl);
             for (int c = 0; c < 2; c++) {
                 const int k = (int)((W >> (8 * c)) & 0xffu);
-                if ((c == 0 ? hc0 : hc1) && k) { set_window(m, 0, n); emit_window_classes(m, n, k, T_O + c, false, x, emit); }
+                if ((c == 0 ? hc0 : hc1) && k) emit_window_classes(m, n, k, T_O + c, false, x, emit);
             }
         }
     }
@@ -417,7 +427,7 @@ ET_HD bool route_short_thread(Mem m, int n, u32 pm, int min_mer, int max_mer, co
         else continue;
         if (win != cur_win || k != cur_k) {   // the two selections usually ask for the same evaluation
             const int off = win == 1 ? roff : 0, len = win == 2 ? n : (win == 0 ? llen : rlen), nw = (len + 31) >> 5;
-            set_window(m, off, len);
+            load(0, off, len);
             for (int j = 0; j < nw; j++) m[W_WV + j] = m[W_V + j];
             for (int t = 1; t < k; t++) shrink_valid(m, nw);
             T = 0;
@@ -435,7 +445,7 @@ ET_HD bool route_short_thread(Mem m, int n, u32 pm, int min_mer, int max_mer, co
         }
         for (int q = 0; q < ncls; q++) {
             K key = q < kClsCap ? cls_key<K>(m, q) : x.key[q - kClsCap];
-            const u64 cnt = q < kClsCap ? (u64)m[Lay<K>::CTOT + q] : (u64)x.tot[q - kClsCap];
+            const u64 cnt = q < kClsCap ? (u64)(m[Lay<K>::CT + q] >> 16) : (u64)x.tot[q - kClsCap];
             if (target) { const K t = crc(key, k); key = t < key ? t : key; }
             emit(table, k, key, cnt);
         }
@@ -456,15 +466,15 @@ ET_HD void emit_window_classes(Mem m, int len, int k, int table, bool folded, Cl
     const int ncls = classify_runs(m, prepare_runs(m, nw, k), k, x, false);
     for (int q = 0; q < ncls; q++) {
         K key = q < kClsCap ? cls_key<K>(m, q) : x.key[q - kClsCap];
-        const u64 cnt = q < kClsCap ? (u64)m[Lay<K>::CTOT + q] : (u64)x.tot[q - kClsCap];
+        const u64 cnt = q < kClsCap ? (u64)(m[Lay<K>::CT + q] >> 16) : (u64)x.tot[q - kClsCap];
         if (folded) { const K t = crc(key, k); key = t < key ? t : key; }
         emit(table, k, key, cnt);
     }
 }
 
 // buffer_task_pair for one pair (src/kmer.cpp:268-745; the 128-bit path's semantics where the two differ, like the warp
-// kernel's route_pair, which this mirrors statement by statement).  load(mate) brings that mate's planes into W_RH /
-// W_RL / W_RV.  Limits: both mates <= 160 bases, MAX_MER <= 32, min(n1, n2) >= 4 * MAX_MER (so the large-k block of
+// kernel's route_pair, which this mirrors statement by statement).  load(mate, off, len) brings bases [off, off + len) of
+// that mate in.  Limits: both mates <= 160 bases, MAX_MER <= 32, min(n1, n2) >= 4 * MAX_MER (so the large-k block of
 // src/kmer.cpp:467-505 never runs); false = outside them, nothing emitted.
 template <class K, class Load, class Emit>
 ET_HD bool route_pair_thread(Mem m, int n1, int n2, int min_mer, int max_mer, const unsigned short* thr_low,
@@ -480,12 +490,7 @@ ET_HD bool route_pair_thread(Mem m, int n1, int n2, int min_mer, int max_mer, co
     u32 res[5] = {0, 0, 0, 0, 0};
     K S[5][2];
     bool have[5] = {false, false, false, false, false};
-    int cur_mate = -1;
-    auto window = [&](int t) {
-        const int mate = t <= 2 ? 0 : 1;
-        if (cur_mate != mate) { load(mate); cur_mate = mate; }
-        set_window(m, soff[t], slen[t]);
-    };
+    auto window = [&](int t) { load(t <= 2 ? 0 : 1, soff[t], slen[t]); };
     auto scan = [&](int t) {
         if (have[t]) return;
         window(t);
@@ -568,13 +573,12 @@ struct LongGeom {   // src/kmer.cpp:790-798
     ET_HD int len(int t) const { return SL + (t == mid ? bonus : 0); }
 };
 
-// step 1 for one slice: load(off, len) brings bases [off, off + len) of the read into W_RH / W_RL / W_RV
+// step 1 for one slice: load(0, off, len) brings bases [off, off + len) of the read in
 template <class Load>
 ET_HD u32 long_slice_stats(Mem m, const LongGeom& g, int t, int min_mer, int max_mer, const unsigned short* thr_low,
                            const unsigned short* thr_high, Load& load, ClsSpill<u64>& x) {
     const int len = g.len(t);
-    load(g.start(t), len);
-    set_window(m, 0, len);
+    load(0, g.start(t), len);
     u64 sh, sl;
     return scan_window(m, len, min_mer, max_mer, thr_low, thr_high, x, sh, sl);
 }
@@ -641,8 +645,7 @@ ET_HD bool long_walk(const LongGeom& g, Stat& stat, Task& task) {
 template <class Load, class Emit>
 ET_HD void long_emit(Mem m, const LongGeom& g, const LongTask& tk, Load& load, ClsSpill<u64>& x, Emit& emit) {
     const int len = g.len(tk.slice);
-    load(g.start(tk.slice), len);
-    set_window(m, 0, len);
+    load(0, g.start(tk.slice), len);
     emit_window_classes(m, len, tk.k, tk.table_folded & 7, (tk.table_folded & 8) != 0, x, emit);
 }
 

@@ -1653,7 +1653,7 @@ __device__ void route_long(const DevCfg& cfg, TableRef tr, WS ws, const DevBatch
 // 4.7 ms whatever the kernel in front of the atomics does).  Staged, a block adds to shared memory -- 148 SMs in
 // parallel -- and sends one global add per distinct key.  A key that finds no free slot within a few probes goes
 // straight to the global table (noisy batches: many distinct keys of count 1).
-constexpr int kStageSlots = 512;            // per block; 16 bytes each
+constexpr int kStageSlots = 256;            // per block; 16 bytes each
 constexpr int kStageProbes = 6;
 constexpr u32 kStageLock = 0xffffffffu;     // s_meta: 0 empty, kStageLock being written, else (meta | 1 << 31) ready
 
@@ -1699,28 +1699,35 @@ struct StageEmit {
 #endif
 template <class K>
 constexpr size_t thread_kernel_smem() { return (size_t)et::Lay<K>::WORDS * TREW_THREAD_BLOCK * sizeof(u32) + (size_t)kStageSlots * 16; }
-constexpr size_t kThreadKernelSmem = thread_kernel_smem<et::u64>();   // 4 blocks per SM; the 128-bit instantiation: 3
+constexpr size_t kThreadKernelSmem = thread_kernel_smem<et::u64>();
+// blocks per SM the kernels are built for: shared memory allows 6 (64-bit units: 61 words per thread + the staging table =
+// 35 KB) or 5 (128-bit units), the registers of the paired routing one less
+template <int MODE, class K>
+constexpr int thread_kernel_bps() { return (sizeof(K) == 8 ? 6 : 5) - (MODE == 1 ? 1 : 0); }
 
-// brings one read's planes (bit offset b0, len bases) into the thread's workspace
+// brings bases [off, off + len) of a read (mate 0 / 1 of a pair) into the thread's workspace as the current window
 struct PlaneLoad {
-    et::Mem m; const u32 *hi, *lo, *val; u32 b0[2]; int len[2];
-    __device__ __forceinline__ void operator()(int mate) const {
-        const u32 w0 = b0[mate] >> 5, sh = b0[mate] & 31u;
-        const int n = len[mate];
+    et::Mem m; const u32 *hi, *lo, *val; u32 b0[2];
+    __device__ __forceinline__ void operator()(int mate, int off, int len) const {
+        const u32 pos = b0[mate] + (u32)off, w0 = pos >> 5, sh = pos & 31u;
         for (int j = 0; j < et::kReadWords + 2; j++) {
-            const u32 msk = low_mask(min(32, max(0, n - 32 * j)));
-            m[et::W_RH + j] = __funnelshift_r(__ldg(hi + w0 + j), __ldg(hi + w0 + j + 1), sh) & msk;
-            m[et::W_RL + j] = __funnelshift_r(__ldg(lo + w0 + j), __ldg(lo + w0 + j + 1), sh) & msk;
-            m[et::W_RV + j] = __funnelshift_r(__ldg(val + w0 + j), __ldg(val + w0 + j + 1), sh) & msk;
+            const u32 msk = low_mask(min(32, max(0, len - 32 * j)));
+            u32 h = 0u, l = 0u;
+            if (msk) {
+                h = __funnelshift_r(__ldg(hi + w0 + j), __ldg(hi + w0 + j + 1), sh) & msk;
+                l = __funnelshift_r(__ldg(lo + w0 + j), __ldg(lo + w0 + j + 1), sh) & msk;
+            }
+            m[et::W_H + j] = h; m[et::W_L + j] = l;
+            if (j < et::kReadWords) m[et::W_V + j] = msk ? __funnelshift_r(__ldg(val + w0 + j), __ldg(val + w0 + j + 1), sh) & msk : 0u;
         }
     }
 };
 
 template <int MODE, class K>   // MODE 0 short single-end, 1 paired; K: u64 (MAX_MER <= 32) or u128 (<= 64)
-__global__ void __launch_bounds__(TREW_THREAD_BLOCK, 4) trew_exact_thread_kernel(DevCfg cfg, DevBatch b, const u32* __restrict__ survivors,
+__global__ void __launch_bounds__(TREW_THREAD_BLOCK, (thread_kernel_bps<MODE, K>())) trew_exact_thread_kernel(DevCfg cfg, DevBatch b, const u32* __restrict__ survivors,
                                                                               const u32* __restrict__ n_survivors, int packed_probes,
                                                                               u32* __restrict__ hard, u32* __restrict__ n_hard,
-                                                                              unsigned long long* total_survivors, u32 exp_flags) {
+                                                                              unsigned long long* total_survivors, u32* work_counter) {
     // word i of thread t's workspace at work[i * blockDim + t]: no bank conflicts
     u32* work = reinterpret_cast<u32*>(g_smem);
     u64* s_key = reinterpret_cast<u64*>(work + et::Lay<K>::WORDS * TREW_THREAD_BLOCK);
@@ -1732,30 +1739,34 @@ __global__ void __launch_bounds__(TREW_THREAD_BLOCK, 4) trew_exact_thread_kernel
     const u32 n = *n_survivors;
     if (blockIdx.x == 0 && threadIdx.x == 0 && total_survivors) atomicAdd(total_survivors, (unsigned long long)n);
     StageEmit emit{s_meta, s_cnt, s_key, cfg.slots, cfg.slot_mask, cfg.error_flag};
-    const u32 stride = gridDim.x * blockDim.x;
-    const u32 n_round = (n + 31u) & ~31u;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    // a warp takes 32 survivors at a time from a shared counter: the cost of a survivor varies by an order of magnitude
+    // (a clean repeat against a noisy window), and with one or two rounds per warp a fixed assignment leaves most warps
+    // waiting at the final barrier for the unlucky ones
+    for (;;) {
+        u32 base = 0;
+        if (lane_id() == 0) base = atomicAdd(work_counter, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const u32 i = base + lane_id();
         bool bail = false;
         u32 entry = 0;
         if (i < n) {
             entry = survivors[i];
             u32 u = entry, pm = 3u;
             if (packed_probes) { pm = entry >> kProbeShift; u &= (1u << kProbeShift) - 1u; }
-            (void)exp_flags;
             if (MODE == 0) {
                 const u32 b0 = __ldg(b.bit_off + u);
                 const int len = (int)(__ldg(b.bit_off + u + 1) - b0);
                 if (len > et::kMaxRead) {
                     bail = true;
                 } else {
-                    PlaneLoad load{m, b.hi, b.lo, b.val, {b0, 0u}, {len, 0}};
-                    load(0);
-                    bail = !et::route_short_thread<K>(m, len, pm & 7u, cfg.min_mer, cfg.max_mer, cfg.thr_low, cfg.thr_high, emit);
+                    PlaneLoad load{m, b.hi, b.lo, b.val, {b0, 0u}};
+                    bail = !et::route_short_thread<K>(m, len, pm & 7u, cfg.min_mer, cfg.max_mer, cfg.thr_low, cfg.thr_high, load, emit);
                 }
             } else {
                 const u32 a0 = __ldg(b.bit_off + 2 * u), a1 = __ldg(b.bit_off + 2 * u + 1), a2 = __ldg(b.bit_off + 2 * u + 2);
                 const int n1 = (int)(a1 - a0), n2 = (int)(a2 - a1);
-                PlaneLoad load{m, b.hi, b.lo, b.val, {a0, a1}, {n1, n2}};
+                PlaneLoad load{m, b.hi, b.lo, b.val, {a0, a1}};
                 bail = !et::route_pair_thread<K>(m, n1, n2, cfg.min_mer, cfg.max_mer, cfg.thr_low, cfg.thr_high, load, emit);
             }
         }
@@ -1774,19 +1785,6 @@ __global__ void __launch_bounds__(TREW_THREAD_BLOCK, 4) trew_exact_thread_kernel
 // Survivor idx (at most s_cap of them; the rest goes to the warp kernel) owns row idx of two arrays of max_slices + 1
 // entries: stats (u16: target_k_high | target_k_low << 8 per slice) and emis (u32 per slice: one byte per emission --
 // forward walk high / low: k | 0x80 when it goes to 'both' folded; backward walk high / low: k).
-
-struct SliceLoad {   // bases [off, off + len) of one read into the thread's workspace
-    et::Mem m; const u32 *hi, *lo, *val; u32 b0;
-    __device__ __forceinline__ void operator()(int off, int len) const {
-        const u32 pos = b0 + (u32)off, w0 = pos >> 5, sh = pos & 31u;
-        for (int j = 0; j < et::kReadWords + 2; j++) {
-            const u32 msk = low_mask(min(32, max(0, len - 32 * j)));
-            m[et::W_RH + j] = __funnelshift_r(__ldg(hi + w0 + j), __ldg(hi + w0 + j + 1), sh) & msk;
-            m[et::W_RL + j] = __funnelshift_r(__ldg(lo + w0 + j), __ldg(lo + w0 + j + 1), sh) & msk;
-            m[et::W_RV + j] = __funnelshift_r(__ldg(val + w0 + j), __ldg(val + w0 + j + 1), sh) & msk;
-        }
-    }
-};
 
 struct LongArgs {
     const u32* survivors; const u32* n_survivors; int packed_probes;
@@ -1810,7 +1808,7 @@ __global__ void __launch_bounds__(TREW_THREAD_BLOCK, 4) trew_long_stats_kernel(D
         const int len = (int)(__ldg(b.bit_off + u + 1) - b0);
         if (len < cfg.slice_len) continue;
         const et::LongGeom g(len, cfg.slice_len);
-        SliceLoad load{m, b.hi, b.lo, b.val, b0};
+        PlaneLoad load{m, b.hi, b.lo, b.val, {b0, 0u}};
         unsigned short* row = a.stats + (size_t)idx * (a.max_slices + 1);
         for (int t = 1 + (int)lane; t <= g.snum; t += 32) {
             u32 r = 0;
@@ -1857,7 +1855,7 @@ __global__ void __launch_bounds__(256) trew_long_walk_kernel(DevCfg cfg, DevBatc
 // step 3: warp per survivor, lane per slice with emissions
 __global__ void __launch_bounds__(TREW_THREAD_BLOCK, 4) trew_long_emit_kernel(DevCfg cfg, DevBatch b, LongArgs a) {
     u32* work = reinterpret_cast<u32*>(g_smem);
-    u64* s_key = reinterpret_cast<u64*>(work + et::kWorkWords * TREW_THREAD_BLOCK);
+    u64* s_key = reinterpret_cast<u64*>(work + et::Lay<et::u64>::WORDS * TREW_THREAD_BLOCK);
     u32* s_meta = reinterpret_cast<u32*>(s_key + kStageSlots);
     u32* s_cnt = s_meta + kStageSlots;
     for (int i = threadIdx.x; i < kStageSlots; i += blockDim.x) { s_meta[i] = 0u; s_cnt[i] = 0u; }
@@ -1874,7 +1872,7 @@ __global__ void __launch_bounds__(TREW_THREAD_BLOCK, 4) trew_long_emit_kernel(De
         const int len = (int)(__ldg(b.bit_off + u + 1) - b0);
         if (len < cfg.slice_len) continue;
         const et::LongGeom g(len, cfg.slice_len);
-        SliceLoad load{m, b.hi, b.lo, b.val, b0};
+        PlaneLoad load{m, b.hi, b.lo, b.val, {b0, 0u}};
         const u32* em = a.emis + (size_t)idx * (a.max_slices + 1);
         for (int t = 1 + (int)lane; t <= g.snum; t += 32) {
             const u32 e = em[t];
@@ -1913,7 +1911,7 @@ void launch_long_thread(const DevCfg& cfg, const DevBatch& b, const unsigned int
     a.emis = reinterpret_cast<u32*>(scratch);
     a.stats = reinterpret_cast<unsigned short*>(scratch + (size_t)s_cap * (max_slices + 1) * sizeof(u32));
     a.hard = hard; a.n_hard = n_hard; a.total_survivors = total_survivors;
-    const size_t smem_stats = (size_t)et::kWorkWords * TREW_THREAD_BLOCK * sizeof(u32);
+    const size_t smem_stats = (size_t)et::Lay<et::u64>::WORDS * TREW_THREAD_BLOCK * sizeof(u32);
     trew_long_stats_kernel<<<sm_count * 4, TREW_THREAD_BLOCK, smem_stats, stream>>>(cfg, b, a);
     trew_long_walk_kernel<<<sm_count * 2, 256, 0, stream>>>(cfg, b, a);
     trew_long_emit_kernel<<<sm_count * 4, TREW_THREAD_BLOCK, kThreadKernelSmem, stream>>>(cfg, b, a);
@@ -1927,12 +1925,14 @@ bool thread_path_applies(const DevCfg& cfg, unsigned int max_read_len) {
 }
 
 void launch_exact_thread(const DevCfg& cfg, const DevBatch& b, const unsigned int* survivors, const unsigned int* n_survivors,
-                         int packed_probes, unsigned int* hard, unsigned int* n_hard, unsigned long long* total_survivors, int blocks,
-                         unsigned int exp_flags, cudaStream_t stream) {
+                         int packed_probes, unsigned int* hard, unsigned int* n_hard, unsigned long long* total_survivors, int sm_count,
+                         int blocks_per_sm, unsigned int* work_counter, cudaStream_t stream) {
     const bool wide = cfg.max_mer > 32;
+    // blocks_per_sm 0: as many as the kernel was built to have resident (one wave)
 #define TREW_LAUNCH_THREAD(MODE, K)                                                                                               \
-    trew_exact_thread_kernel<MODE, K><<<blocks, TREW_THREAD_BLOCK, thread_kernel_smem<K>(), stream>>>(                            \
-        cfg, b, survivors, n_survivors, packed_probes, hard, n_hard, total_survivors, exp_flags)
+    trew_exact_thread_kernel<MODE, K><<<sm_count * (blocks_per_sm > 0 ? blocks_per_sm : thread_kernel_bps<MODE, K>()),            \
+                                        TREW_THREAD_BLOCK, thread_kernel_smem<K>(), stream>>>(                                    \
+        cfg, b, survivors, n_survivors, packed_probes, hard, n_hard, total_survivors, work_counter)
     if (cfg.mode == 0) { if (wide) TREW_LAUNCH_THREAD(0, et::u128); else TREW_LAUNCH_THREAD(0, et::u64); }
     else               { if (wide) TREW_LAUNCH_THREAD(1, et::u128); else TREW_LAUNCH_THREAD(1, et::u64); }
 #undef TREW_LAUNCH_THREAD

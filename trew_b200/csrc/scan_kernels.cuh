@@ -90,8 +90,8 @@ void launch_long_thread(const DevCfg& cfg, const DevBatch& b, const unsigned int
 // outside its limits to `hard` (counter n_hard, zeroed) for launch_exact
 bool thread_path_applies(const DevCfg& cfg, unsigned int max_read_len);
 void launch_exact_thread(const DevCfg& cfg, const DevBatch& b, const unsigned int* survivors, const unsigned int* n_survivors,
-                         int packed_probes, unsigned int* hard, unsigned int* n_hard, unsigned long long* total_survivors, int blocks,
-                         unsigned int exp_flags, cudaStream_t stream);
+                         int packed_probes, unsigned int* hard, unsigned int* n_hard, unsigned long long* total_survivors, int sm_count,
+                         int blocks_per_sm, unsigned int* work_counter, cudaStream_t stream);
 // table_kernels.cu
 void launch_compact(const Slot* slots, unsigned int n_slots, trew_entry* out, unsigned int* d_n, cudaStream_t stream, unsigned int cap);
 // sort by (table, k, seq): sorted rows into d_out (d_entries untouched); wide = some key uses seq_hi (MAX_MER > 32);
