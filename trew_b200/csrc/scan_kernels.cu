@@ -672,7 +672,7 @@ template <int MAXNW>
 __global__ void __launch_bounds__(256) trew_filter_kernel(DevCfg cfg, DevBatch b, const u32* __restrict__ units,
                                                           const u32* __restrict__ n_units_ptr, u32 n_units_all,
                                                           u32* __restrict__ survivors, u32* __restrict__ n_survivors,
-                                                          u32* __restrict__ surv_b_top, u32* __restrict__ n_surv_b) {
+                                                          u32* __restrict__ surv_b_top, u32* __restrict__ n_surv_b, int thread_min_windows) {
     __shared__ unsigned short thr[kThrTableSize];
     for (int i = threadIdx.x; i < kThrTableSize; i += blockDim.x) thr[i] = cfg.thr_low[i];
     __syncthreads();
@@ -717,7 +717,7 @@ __global__ void __launch_bounds__(256) trew_filter_kernel(DevCfg cfg, DevBatch b
                 } else {
                     len = (int)(__ldg(b.bit_off + u + 1) - __ldg(b.bit_off + u));
                 }
-                to_b = len > et::kMaxRead || t_hit < kThreadMinWindows;
+                to_b = len > et::kMaxRead || t_hit < thread_min_windows;
             }
             list_append(maybe && !to_b, entry, survivors, n_survivors);
             list_append_rev(maybe && to_b, entry, surv_b_top, n_surv_b);
@@ -744,12 +744,13 @@ void launch_filter(const DevCfg& cfg, const DevBatch& b, unsigned int n_units, u
         else trew_screen_kernel<true><<<blocks, 256, 0, stream>>>(cfg, b, n_units, deferred, n_deferred);
     }
     if (after_screen) cudaEventRecord(after_screen, stream);
+    static const int tmw = [] { const char* e = getenv("TREW_THREAD_MIN_WINDOWS"); return e && *e ? atoi(e) : kThreadMinWindows; }();   // experiments
     const unsigned int* list = screen ? deferred : nullptr;
     int blocks = plan.decide_blocks;
     if ((unsigned)blocks > need) blocks = (int)need;
-    if (longest + 1 <= 96) trew_filter_kernel<3><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors, surv_b_top, n_surv_b);
-    else if (longest + 1 <= 160) trew_filter_kernel<5><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors, surv_b_top, n_surv_b);
-    else trew_filter_kernel<8><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors, surv_b_top, n_surv_b);
+    if (longest + 1 <= 96) trew_filter_kernel<3><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors, surv_b_top, n_surv_b, tmw);
+    else if (longest + 1 <= 160) trew_filter_kernel<5><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors, surv_b_top, n_surv_b, tmw);
+    else trew_filter_kernel<8><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors, surv_b_top, n_surv_b, tmw);
 }
 
 // ------------------------------------------------------------------------------------------------
