@@ -423,6 +423,7 @@ constexpr int kScreenUnroll = TREW_SCREEN_UNROLL;
 constexpr int kFastMaxWl = 95;
 constexpr int kFastTabSize = kFastMaxWl + 2;
 constexpr int kProbeShift = 28;  // deferred-list entry: unit index | probe mask << 28
+constexpr int kMod4BelowWindows = 48;    // decide kernel: the third (mod-4) level is asked for periods with fewer valid windows than this (measured: 24 / 36 / 48 / always -> 2.07 / 2.05 / 2.03 / 2.14 ms decide + exact per 25 M reads, none: 2.18)
 constexpr int kThreadMinWindows = 36;   // decide kernel: survivors whose first passing period has fewer valid windows go to the warp kernel
 
 // per-T entry: x = packed base word, y / z = masks of the window positions in words 0 / 1
@@ -610,9 +611,94 @@ __global__ void __launch_bounds__(256, LONG ? 4 : TREW_SCREEN_BPS) trew_screen_k
 // 3-word bound, then the #A-parity second level.  Same decisions as probe_filter<3>, fewer instructions.
 __device__ __forceinline__ int max4(int a, int b, int c, int d) { return max(max(a, b), max(c, d)); }
 
+// Third level of the decide test: the counts of hi bits, lo bits and A's of a k-window MOD 4 are rotation invariants too
+// (the first two levels use them mod 2), so a class lies inside one of 64 buckets.  The second bits of the three counts
+// come from second-order prefix planes -- P1 = exclusive prefix XOR of (x & P0), the carries of a running 2-bit count;
+// bit 1 of a window's count is P1[i + k] ^ P1[i] ^ (~P0[i + k] & P0[i]) (the borrow of the low bits).  What an N leaves
+// of a window -- a dozen k-windows, half of which fall into one of 8 buckets by chance at some period -- stops here
+// instead of becoming a survivor.  Reached by a few percent of the decided probes, so it is a function of its own: nothing
+// of it lives in the registers of the loop over the periods; the probe's first call builds the six prefix planes from the
+// batch and parks them in shared memory (cache: word i of the thread at cache[i * 256]), later calls reload them.
+// pass8: the buckets of the second level that hold `need` windows (bit = hi | lo << 1 | A << 2 parity differences).
+// true = some bucket of the 64 may still hold `need` of the valid windows wv (the k-windows of this period).
+__device__ __forceinline__ u32 shr3(const u32 (&p)[3], int j, int k) {   // word j of (p >> k), k < 64, zero beyond word 2
+    const int s = k >> 5;
+    const u32 lo = j + s < 3 ? (s ? (j == 0 ? p[1] : p[2]) : p[j]) : 0u;
+    const u32 hi = j + s + 1 < 3 ? (s ? p[2] : (j == 0 ? p[1] : p[2])) : 0u;
+    return __funnelshift_r(lo, hi, k);
+}
+constexpr int kDecideThreads = 256;
+__device__ __noinline__ bool mod4_level(const DevBatch& b, u32 pos, int wl, int k, int need, u32 pass8, u32 wv0, u32 wv1, u32 wv2, u32* cache,
+                                        bool& cached) {
+    const u32 wv[3] = {wv0, wv1, wv2};
+    u32 p0[3][3], p1[3][3];   // planes: hi, lo, A
+    if (!cached) {
+        u32 x[3][3];
+        load_bits<3>(b.hi, pos, x[0]); mask_bits<3>(x[0], wl);
+        load_bits<3>(b.lo, pos, x[1]); mask_bits<3>(x[1], wl);
+#pragma unroll
+        for (int j = 0; j < 3; j++) x[2][j] = x[0][j] & x[1][j];
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
+            prefix_xor_excl<3>(x[p], p0[p]);
+            u32 c[3];
+#pragma unroll
+            for (int j = 0; j < 3; j++) c[j] = x[p][j] & p0[p][j];
+            prefix_xor_excl<3>(c, p1[p]);
+#pragma unroll
+            for (int j = 0; j < 3; j++) { cache[(6 * p + j) * kDecideThreads] = p0[p][j]; cache[(6 * p + 3 + j) * kDecideThreads] = p1[p][j]; }
+        }
+        cached = true;
+    } else {
+#pragma unroll
+        for (int p = 0; p < 3; p++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) { p0[p][j] = cache[(6 * p + j) * kDecideThreads]; p1[p][j] = cache[(6 * p + 3 + j) * kDecideThreads]; }
+    }
+    u32 d0[3][3], d1[3][3];   // first and second bit of the three counts of the window starting at each position
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const u32 q0 = shr3(p0[p], j, k);
+            d0[p][j] = q0 ^ p0[p][j];
+            d1[p][j] = shr3(p1[p], j, k) ^ p1[p][j] ^ (~q0 & p0[p][j]);
+        }
+    }
+#pragma unroll 1
+    for (int c2 = 0; c2 < 8; c2++) {   // buckets of the second level
+        if (!((pass8 >> c2) & 1u)) continue;
+        u32 mw[3];
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            mw[j] = wv[j] & (d0[0][j] ^ ((c2 & 1) ? 0u : ~0u)) & (d0[1][j] ^ ((c2 & 2) ? 0u : ~0u)) & (d0[2][j] ^ ((c2 & 4) ? 0u : ~0u));
+            cnt += __popc(mw[j]);
+        }
+        if (cnt < need) continue;
+        // split by the three second bits in turn, following the larger side; a smaller side that could still reach `need`
+        // too (a tie at exactly half) is not followed but counted as "may"
+        bool may = true;
+#pragma unroll
+        for (int p = 0; p < 3 && may; p++) {
+            const int one = __popc(mw[0] & d1[p][0]) + __popc(mw[1] & d1[p][1]) + __popc(mw[2] & d1[p][2]);
+            const int zero = cnt - one;
+            if (min(one, zero) >= need) return true;
+            const u32 flip = one >= zero ? 0u : ~0u;
+#pragma unroll
+            for (int j = 0; j < 3; j++) mw[j] &= d1[p][j] ^ flip;
+            cnt = max(one, zero);
+            may = cnt >= need;
+        }
+        if (may) return true;
+    }
+    return false;
+}
+
 template <int S>
 __device__ __forceinline__ bool decide_span(const u32 (&ph)[5], const u32 (&pl)[5], const u32 (&pa)[5], u32 (&wv)[3], int ka, int kb,
-                                            const unsigned short* __restrict__ thr, bool& done, int& t_hit) {
+                                            const unsigned short* __restrict__ thr, bool& done, int& t_hit, const DevBatch& bt, u32 pos, int wl,
+                                            u32* cache, bool& cached, int m4_below) {
     for (int k = ka; k <= kb; k++) {
         const int T01 = __popc(wv[0]) + __popc(wv[1]), E = __popc(wv[2]), T = T01 + E;
         if (T == 0) { done = true; return false; }  // the valid-window mask only shrinks with k
@@ -632,7 +718,13 @@ __device__ __forceinline__ bool decide_span(const u32 (&ph)[5], const u32 (&pl)[
                 int n01 = __popc(b0 & ~a0 & x0) + __popc(b1 & ~a1 & x1) + __popc(b2 & ~a2 & x2);
                 int n00 = __popc(wv[0] & ~a0 & ~b0 & x0) + __popc(wv[1] & ~a1 & ~b1 & x1) + __popc(wv[2] & ~a2 & ~b2 & x2);
                 int U2 = max(max4(n11, c11 - n11, n10, c10 - n10), max4(n01, c01 - n01, n00, c00 - n00));
-                if (U2 >= need) { t_hit = T; return true; }
+                if (U2 >= need) {
+                    const u32 pass8 = (u32)(c00 - n00 >= need) | (u32)(c10 - n10 >= need) << 1 | (u32)(c01 - n01 >= need) << 2 |
+                                      (u32)(c11 - n11 >= need) << 3 | (u32)(n00 >= need) << 4 | (u32)(n10 >= need) << 5 |
+                                      (u32)(n01 >= need) << 6 | (u32)(n11 >= need) << 7;
+                    // with most of the window's k-windows still valid this is nearly always a repeat: no need to ask
+                    if (T >= m4_below || mod4_level(bt, pos, wl, k, need, pass8, wv[0], wv[1], wv[2], cache, cached)) { t_hit = T; return true; }
+                }
             }
         }
         u32 t0 = __funnelshift_r(wv[0], wv[1], 1), t1 = __funnelshift_r(wv[1], wv[2], 1), t2 = wv[2] >> 1;
@@ -643,7 +735,9 @@ __device__ __forceinline__ bool decide_span(const u32 (&ph)[5], const u32 (&pl)[
 
 // t_hit: the number of valid windows at the first period that passes (tells a repeat -- most of the window -- from a
 // window an N left a dozen k-windows of)
-__device__ __noinline__ bool decide_short(const DevBatch& b, u32 pos, int wl, int k0, int k1, const unsigned short* __restrict__ thr, int& t_hit) {
+__device__ __noinline__ bool decide_short(const DevBatch& b, u32 pos, int wl, int k0, int k1, const unsigned short* __restrict__ thr, int& t_hit,
+                                          u32* cache, int m4_below) {
+    bool cached = false;
     u32 wv[3], ph[5], pl[5], pa[5];
     load_bits<3>(b.val, pos, wv); mask_bits<3>(wv, wl);
     {
@@ -660,20 +754,21 @@ __device__ __noinline__ bool decide_short(const DevBatch& b, u32 pos, int wl, in
     sliding_and<3>(wv, k0);
     bool done = false;
     if (k0 < 32) {
-        if (decide_span<0>(ph, pl, pa, wv, k0, min(k1, 31), thr, done, t_hit)) return true;
+        if (decide_span<0>(ph, pl, pa, wv, k0, min(k1, 31), thr, done, t_hit, b, pos, wl, cache, cached, m4_below)) return true;
         if (done) return false;
         k0 = 32;
     }
-    return k1 >= 32 && decide_span<1>(ph, pl, pa, wv, k0, k1, thr, done, t_hit);
+    return k1 >= 32 && decide_span<1>(ph, pl, pa, wv, k0, k1, thr, done, t_hit, b, pos, wl, cache, cached, m4_below);
 }
 
 // ---- decide kernel: exact 4-bucket bound + A-parity second level for every (probe, k) of the deferred units ----
 template <int MAXNW>
-__global__ void __launch_bounds__(256) trew_filter_kernel(DevCfg cfg, DevBatch b, const u32* __restrict__ units,
+__global__ void __launch_bounds__(kDecideThreads, (MAXNW <= 5 ? 4 : 2)) trew_filter_kernel(DevCfg cfg, DevBatch b, const u32* __restrict__ units,
                                                           const u32* __restrict__ n_units_ptr, u32 n_units_all,
                                                           u32* __restrict__ survivors, u32* __restrict__ n_survivors,
-                                                          u32* __restrict__ surv_b_top, u32* __restrict__ n_surv_b, int thread_min_windows) {
+                                                          u32* __restrict__ surv_b_top, u32* __restrict__ n_surv_b, int thread_min_windows, int third_level) {   // third_level: asked for periods with fewer valid windows than this
     __shared__ unsigned short thr[kThrTableSize];
+    __shared__ u32 s_m4[18 * kDecideThreads];   // mod4_level: the probe's prefix planes, per thread
     for (int i = threadIdx.x; i < kThrTableSize; i += blockDim.x) thr[i] = cfg.thr_low[i];
     __syncthreads();
     const u32 n_units = units ? *n_units_ptr : n_units_all;   // no list: every unit of the batch
@@ -693,7 +788,7 @@ __global__ void __launch_bounds__(256) trew_filter_kernel(DevCfg cfg, DevBatch b
             live = pm & ((1u << np) - 1u);   // probes that may still find a target period
             for (int j = 0; j < np && !maybe; j++) {
                 if (((pm >> j) & 1u) && p[j].k1 >= p[j].k0)
-                    maybe = probe_is_fast(p[j]) ? decide_short(b, p[j].pos, p[j].wl, p[j].k0, p[j].k1, thr, t_hit) : probe_dispatch<MAXNW>(b, p[j], thr);
+                    maybe = probe_is_fast(p[j]) ? decide_short(b, p[j].pos, p[j].wl, p[j].k0, p[j].k1, thr, t_hit, s_m4 + threadIdx.x, third_level) : probe_dispatch<MAXNW>(b, p[j], thr);
                 if (!maybe) live &= ~(1u << j);
             }
         }
@@ -745,12 +840,13 @@ void launch_filter(const DevCfg& cfg, const DevBatch& b, unsigned int n_units, u
     }
     if (after_screen) cudaEventRecord(after_screen, stream);
     static const int tmw = [] { const char* e = getenv("TREW_THREAD_MIN_WINDOWS"); return e && *e ? atoi(e) : kThreadMinWindows; }();   // experiments
+    static const int m4_on = [] { const char* e = getenv("TREW_MOD4_BELOW"); return e && *e ? atoi(e) : kMod4BelowWindows; }();   // experiments (0: no third level)
     const unsigned int* list = screen ? deferred : nullptr;
     int blocks = plan.decide_blocks;
     if ((unsigned)blocks > need) blocks = (int)need;
-    if (longest + 1 <= 96) trew_filter_kernel<3><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors, surv_b_top, n_surv_b, tmw);
-    else if (longest + 1 <= 160) trew_filter_kernel<5><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors, surv_b_top, n_surv_b, tmw);
-    else trew_filter_kernel<8><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors, surv_b_top, n_surv_b, tmw);
+    if (longest + 1 <= 96) trew_filter_kernel<3><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors, surv_b_top, n_surv_b, tmw, m4_on);
+    else if (longest + 1 <= 160) trew_filter_kernel<5><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors, surv_b_top, n_surv_b, tmw, m4_on);
+    else trew_filter_kernel<8><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors, surv_b_top, n_surv_b, tmw, m4_on);
 }
 
 // ------------------------------------------------------------------------------------------------
