@@ -404,7 +404,8 @@ def run_ours(args):
         traffic = os.path.join(ROOT, "profiles", "screen_traffic.json")
         if os.path.exists(traffic):
             try:
-                line["roofline"]["traffic"] = json.load(open(traffic)).get("dram_bytes_per_launch")
+                t = json.load(open(traffic))   # measured per launch of t["reads_per_launch"] reads; scaled to this run's launches
+                line["roofline"]["traffic"] = t["dram_bytes_per_launch"] * reads_per_launch / t["reads_per_launch"]
             except Exception:
                 pass
         line.update(extra)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Run under torchrun with one rank per GPU: every rank scans its share of a read set, merge.finish_merged unites the
 tables over NCCL, and rank 0 checks the result against one context scanning everything (with and without the report
-filter, and with a capacity too small for the rows, which forces the regrow path).  Used by tests/test_gpu_multi.py on
+filter, with a capacity too small for the rows, which forces the regrow path, and with a stale row estimate).  Used by tests/test_gpu_multi.py on
 boxes with at least two GPUs.
 
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/merge_check.py
@@ -31,12 +31,16 @@ def main():
     mine = reads[rank::world]
     with api.DeviceContext(api.MODE_SHORT, 5, 32, device=local) as ctx:
         ctx.submit_reads(mine)
-        for filt in (0, 10, 0):
+        for step, filt in enumerate((0, 10, 0, 10)):
             ctx.set_report_filter(filt)
-            if filt == 10:
-                merge._exchange[id(ctx)] = (16, torch.empty((17, 4), dtype=torch.int64, device=device),
-                                            torch.empty((world * 17, 4), dtype=torch.int64, device=device))   # too small: regrow
+            if step == 1:
+                merge._exchange[id(ctx)] = [16, torch.empty((17, 4), dtype=torch.int64, device=device),
+                                            torch.empty((world * 17, 4), dtype=torch.int64, device=device), 16]   # too small: regrow
+            if step == 3:
+                merge._exchange[id(ctx)][3] = 8   # fewer rows announced last time than there are now: whole buffer, no regrow
             got = merge.finish_merged(ctx, device)
+            if step == 3:
+                assert merge._exchange[id(ctx)][3] < merge._exchange[id(ctx)][0]   # back to the trimmed exchange
             if rank == 0:
                 with api.DeviceContext(api.MODE_SHORT, 5, 32, device=local) as one:
                     one.submit_reads(reads)

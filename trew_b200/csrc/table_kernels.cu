@@ -13,30 +13,41 @@ namespace trew {
 typedef unsigned int u32;
 typedef unsigned long long u64;
 
-// slot -> entry; unused slots are skipped, the survivors are appended in arbitrary order
+// slot -> entry; unused slots are skipped, the survivors are appended in arbitrary order.  A warp looks at 128 slots per
+// round -- four independent 16-byte loads of the halves that hold count / meta / state per lane, so that the (mostly empty)
+// table streams at memory speed instead of one dependent 32-byte load per ballot -- and fetches the key halves of used
+// slots only.
 __global__ void compact_kernel(const Slot* __restrict__ slots, u32 n_slots, trew_entry* __restrict__ out, u32* __restrict__ d_n, u32 cap) {
     const u32 lane = threadIdx.x & 31;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += gridDim.x * blockDim.x) {
-        Slot s = slots[i];
-        bool used = s.state == 2u && s.count != 0;
-        u32 m = __ballot_sync(0xffffffffu, used);
-        if (m) {
-            u32 base = 0;
-            if (lane == (u32)(__ffs(m) - 1)) base = atomicAdd(d_n, (u32)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-            u32 o = base + __popc(m & ((1u << lane) - 1u));
-            if (used && o < cap) {  // past the end of the array: count only, the host grows it and runs again
-                trew_entry e;
-                e.seq_lo = s.seq_lo; e.seq_hi = s.seq_hi; e.count = s.count;
-                e.table = (int)(s.meta >> 8); e.k = (int)(s.meta & 0xffu);
-                out[o] = e;
+    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (u32 i0 = warp * 128u; i0 < n_slots; i0 += n_warps * 128u) {   // n_slots is a multiple of 128
+        uint4 h[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) h[r] = __ldg(reinterpret_cast<const uint4*>(slots + i0 + 32u * r + lane) + 1);   // count lo, count hi, meta, state
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const bool used = h[r].w == 2u && (h[r].x | h[r].y) != 0u;
+            const u32 m = __ballot_sync(0xffffffffu, used);
+            if (m) {
+                u32 base = 0;
+                if (lane == (u32)(__ffs(m) - 1)) base = atomicAdd(d_n, (u32)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                const u32 o = base + __popc(m & ((1u << lane) - 1u));
+                if (used && o < cap) {  // past the end of the array: count only, the host grows it and runs again
+                    const uint4 key = __ldg(reinterpret_cast<const uint4*>(slots + i0 + 32u * r + lane));
+                    trew_entry e;
+                    e.seq_lo = (u64)key.x | ((u64)key.y << 32); e.seq_hi = (u64)key.z | ((u64)key.w << 32);
+                    e.count = (u64)h[r].x | ((u64)h[r].y << 32);
+                    e.table = (int)(h[r].z >> 8); e.k = (int)(h[r].z & 0xffu);
+                    out[o] = e;
+                }
             }
         }
     }
 }
 
 void launch_compact(const Slot* slots, unsigned int n_slots, trew_entry* out, unsigned int* d_n, cudaStream_t stream, unsigned int cap) {
-    // n_slots is a power of two >= 1024, so every warp iterates the same number of times
+    // n_slots is a power of two >= 1024
     compact_kernel<<<592, 256, 0, stream>>>(slots, n_slots, out, d_n, cap);
 }
 

@@ -90,16 +90,22 @@ def merge_device(ctx, device: torch.device, dst: int = 0) -> None:
         ctx.sync()   # the gathered buffers must outlive the merge kernels
 
 
-_exchange = {}   # id(ctx) -> (capacity in rows, row buffer with a header row, gathered buffer)
+_exchange = {}   # id(ctx) -> [capacity in rows, row buffer with a header row, gathered buffer, rows to send next time]
+
+
+def _round_rows(n: int) -> int:
+    return (n + n // 8 + 1023) // 1024 * 1024
 
 
 def finish_merged(ctx, device: torch.device, dst: int = 0):
     """End-of-file merge without touching the count tables: every rank copies its compacted rows into a fixed-capacity
     device buffer whose first row carries the row count, ONE NCCL all-gather moves the buffers, and `dst` forms the union
     on the device (concatenate, [report filter], radix sort, sum equal keys: trew_dev_finish_merged) and copies it to the
-    host.  All ranks see all headers, so a rank whose rows did not fit (negative header) makes every rank double the
-    capacity and repeat -- no extra collective in the steady state.  Returns the merged entries (structured numpy view,
-    sorted by (table, k, seq)) on `dst`, None elsewhere."""
+    host.  Only the first `send` rows of the buffers travel: the largest count any rank announced last time plus an
+    eighth (the same number on every rank, since all ranks see all headers), so a file's exchange moves little more than
+    its rows.  A rank whose rows do not fit (negative header) makes every rank send the whole buffer -- doubled first if
+    that is too small as well -- and repeat: no extra collective in the steady state.  Returns the merged entries
+    (structured numpy view, sorted by (table, k, seq)) on `dst`, None elsewhere."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return ctx.finish_view()
     world, rank = dist.get_world_size(), dist.get_rank()
@@ -107,34 +113,38 @@ def finish_merged(ctx, device: torch.device, dst: int = 0):
     while True:
         st = _exchange.get(id(ctx))
         if st is None:
-            # first use: learn the sizes once (the only step with a second collective)
             all_n = torch.zeros(world, dtype=torch.int64, device=device)
             dist.all_gather_into_tensor(all_n, torch.tensor([n], dtype=torch.int64, device=device))
             cap = 1024
             while cap < 2 * max(all_n.tolist()) + 1024:
                 cap *= 2
-            st = (cap, torch.empty((cap + 1, 4), dtype=torch.int64, device=device),
-                  torch.empty((world * (cap + 1), 4), dtype=torch.int64, device=device))
+            st = [cap, torch.empty((cap + 1, 4), dtype=torch.int64, device=device),
+                  torch.empty((world * (cap + 1), 4), dtype=torch.int64, device=device), min(cap, _round_rows(max(all_n.tolist())))]
             _exchange[id(ctx)] = st
-        cap, rows, gathered = st
-        if n <= cap:
+        cap, rows, gathered, send = st
+        if n <= send:
             ctx.export_rows(rows[1:].data_ptr(), cap)
             rows[0, 0] = n
         else:
             rows[0, 0] = -n
-        dist.all_gather_into_tensor(gathered, rows)
-        heads = gathered.view(world, cap + 1, 4)[:, 0, 0].tolist()     # one small D2H; also orders the gather before the union
+        got = gathered[: world * (send + 1)]
+        dist.all_gather_into_tensor(got, rows[: send + 1])
+        heads = got.view(world, send + 1, 4)[:, 0, 0].tolist()     # one small D2H; also orders the gather before the union
         if min(heads) >= 0:
+            st[3] = min(cap, _round_rows(max(heads)))
             break
         need = max(-h for h in heads if h < 0)
+        if need <= cap:
+            st[3] = cap
+            continue
         while cap < 2 * need + 1024:
             cap *= 2
-        _exchange[id(ctx)] = (cap, torch.empty((cap + 1, 4), dtype=torch.int64, device=device),
-                              torch.empty((world * (cap + 1), 4), dtype=torch.int64, device=device))
+        _exchange[id(ctx)] = [cap, torch.empty((cap + 1, 4), dtype=torch.int64, device=device),
+                              torch.empty((world * (cap + 1), 4), dtype=torch.int64, device=device), cap]
     if rank != dst:
         return None
-    base = gathered.data_ptr()
-    stride = (cap + 1) * 32
+    base = got.data_ptr()
+    stride = (send + 1) * 32
     return ctx.finish_merged_view([(base + r * stride + 32, heads[r]) for r in range(world) if r != dst])
 
 
