@@ -559,8 +559,8 @@ int trew_dev_create(const trew_config* cfg, trew_ctx** out) {
         // tuning knobs (experiments): blocks per SM of each scan kernel, and 2 streams for resident scans
         auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e && *e ? atoi(e) : dflt; };
         int v;
-        if ((v = env_int("TREW_GRID_SCREEN", 0)) > 0) ctx->plan.screen_blocks = std::min(ctx->plan.screen_blocks, ctx->sm_count * v);
-        if ((v = env_int("TREW_GRID_DECIDE", 0)) > 0) ctx->plan.decide_blocks = std::min(ctx->plan.decide_blocks, ctx->sm_count * v);
+        if ((v = env_int("TREW_GRID_SCREEN", 0)) > 0) ctx->plan.screen_blocks = ctx->sm_count * v;
+        if ((v = env_int("TREW_GRID_DECIDE", 0)) > 0) ctx->plan.decide_blocks = ctx->sm_count * v;
         if ((v = env_int("TREW_GRID_EXACT", 0)) > 0) ctx->plan.exact_blocks = std::min(ctx->plan.exact_blocks, ctx->sm_count * v);
         ctx->resident_streams = env_int("TREW_RESIDENT_STREAMS", 1) >= 2 ? 2 : 1;
         ctx->sparse_val = env_int("TREW_DENSE_VAL", 0) == 0;
