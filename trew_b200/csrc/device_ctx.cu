@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -513,7 +514,6 @@ const char* trew_status_string(int status) {
 // trew_dev_create has no context to hang its message on: it is kept here and read with trew_dev_last_error(NULL)
 static thread_local std::string g_create_error;
 // set by trew_multi_create around its trew_dev_create calls: the group's contexts share one packing pool
-static thread_local Pool* g_shared_pool = nullptr;
 
 static int default_host_threads(int asked) {
     return asked > 0 ? asked : (int)std::min(64u, std::max(1u, std::thread::hardware_concurrency()));
@@ -521,11 +521,13 @@ static int default_host_threads(int asked) {
 
 const char* trew_dev_last_error(const trew_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
-int trew_dev_create(const trew_config* cfg, trew_ctx** out) {
+// err: the message of a failed creation (trew_dev_create keeps it for trew_dev_last_error(NULL); trew_multi_create runs
+// one of these per device on threads of its own)
+static int create_ctx(const trew_config* cfg, trew_ctx** out, std::string& g_create_error, Pool* shared_pool) {
     if (!cfg || !out) return TREW_ERR_ARG;
     *out = nullptr;
     g_create_error.clear();
-    auto bad_arg = [](const char* msg) { g_create_error = msg; return TREW_ERR_ARG; };
+    auto bad_arg = [&](const char* msg) { g_create_error = msg; return TREW_ERR_ARG; };
     // same range checks as the reference CLI (src/trew.cpp:174-228, 255-304)
     if (cfg->mode < 0 || cfg->mode > 2) return bad_arg("mode must be TREW_MODE_SHORT, _PAIR or _LONG");
     if (cfg->min_mer < 3 || cfg->max_mer > 64 || cfg->min_mer > cfg->max_mer) return bad_arg("need 3 <= MIN_MER <= MAX_MER <= 64");
@@ -547,8 +549,19 @@ int trew_dev_create(const trew_config* cfg, trew_ctx** out) {
         cudaError_t e_ = (call);                                                                    \
         if (e_ != cudaSuccess) { fail(ctx, TREW_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); return bail(TREW_ERR_CUDA); } \
     } while (0)
+    // TREW_CLI_TIMING=1: where the start-up time goes (stderr)
+    const bool timing = getenv("TREW_CLI_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_prev = now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const double t = now();
+        fprintf(stderr, "[trew] create, device %d: %s %.1f ms\n", cfg->device, what, t - t_prev);
+        t_prev = t;
+    };
     int ndev = 0;
     CKC(cudaGetDeviceCount(&ndev));
+    lap("driver init");
     if (cfg->device < 0 || cfg->device >= ndev) { fail(ctx, TREW_ERR_CUDA, "no CUDA device %d (found %d)", cfg->device, ndev); return bail(TREW_ERR_CUDA); }
     CKC(cudaSetDevice(cfg->device));
     cudaDeviceProp prop;
@@ -572,6 +585,7 @@ int trew_dev_create(const trew_config* cfg, trew_ctx** out) {
     Slot* d_slots = nullptr;
     CKC(cudaMalloc((void**)&d_slots, ctx->n_slots * sizeof(Slot)));
     CKC(cudaMemset(d_slots, 0, ctx->n_slots * sizeof(Slot)));
+    lap("primary context + count table");
     CKC(cudaMalloc((void**)&ctx->d_error, 2 * sizeof(unsigned int)));
     CKC(cudaMemset(ctx->d_error, 0, 2 * sizeof(unsigned int)));
     CKC(cudaMalloc((void**)&ctx->d_total_surv, sizeof(unsigned long long)));
@@ -588,6 +602,7 @@ int trew_dev_create(const trew_config* cfg, trew_ctx** out) {
     ctx->dcfg.slots = d_slots; ctx->dcfg.slot_mask = (unsigned int)(ctx->n_slots - 1);
     ctx->dcfg.error_flag = ctx->d_error; ctx->dcfg.thr_low = ctx->d_thr; ctx->dcfg.thr_high = ctx->d_thr + kThrTableSize;
     CKC(prepare_exact(kMaxWindow + 9));
+    lap("kernel attributes (module load)");
     CKC(cudaStreamCreateWithFlags(&ctx->main_stream, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
     CKC(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
@@ -614,12 +629,15 @@ int trew_dev_create(const trew_config* cfg, trew_ctx** out) {
         CKC(cudaEventCreate(&s.ev_done));
     }
     CKC(cudaMalloc((void**)&ctx->d_n, sizeof(unsigned int)));
-    if (g_shared_pool) { ctx->pool = g_shared_pool; ctx->own_pool = false; }
+    lap("staging ring (pinned + device buffers)");
+    if (shared_pool) { ctx->pool = shared_pool; ctx->own_pool = false; }
     else ctx->pool = new Pool(default_host_threads(cfg->host_threads));
 #undef CKC
     *out = ctx;
     return TREW_OK;
 }
+
+int trew_dev_create(const trew_config* cfg, trew_ctx** out) { return create_ctx(cfg, out, g_create_error, nullptr); }
 
 void trew_dev_destroy(trew_ctx* ctx) {
     if (!ctx) return;
@@ -1180,17 +1198,26 @@ int trew_multi_create(const trew_config* cfg, const int32_t* devices, int32_t n_
     }
     trew_multi* m = new trew_multi();
     m->pool = new Pool(default_host_threads(cfg->host_threads));
-    g_shared_pool = m->pool;
+    // one thread per device: a primary context takes ~0.5 s to come up, and the devices do not wait for each other
     int rc = TREW_OK;
-    for (int32_t d : dev) {
-        trew_config c = *cfg;
-        c.device = d;
-        trew_ctx* x = nullptr;
-        rc = trew_dev_create(&c, &x);
-        if (rc != TREW_OK) break;
-        m->ctx.push_back(x);
+    {
+        std::vector<trew_ctx*> made(dev.size(), nullptr);
+        std::vector<int> rcs(dev.size(), TREW_OK);
+        std::vector<std::string> errs(dev.size());
+        std::vector<std::thread> th;
+        auto make = [&](size_t i) {
+            trew_config c = *cfg;
+            c.device = dev[i];
+            rcs[i] = create_ctx(&c, &made[i], errs[i], m->pool);
+        };
+        for (size_t i = 1; i < dev.size(); i++) th.emplace_back(make, i);
+        make(0);
+        for (auto& t : th) t.join();
+        for (size_t i = 0; i < dev.size(); i++) {
+            if (rcs[i] != TREW_OK && rc == TREW_OK) { rc = rcs[i]; g_create_error = errs[i]; }
+            if (made[i]) m->ctx.push_back(made[i]);
+        }
     }
-    g_shared_pool = nullptr;
     if (rc != TREW_OK) { trew_multi_destroy(m); return rc; }   // g_create_error holds the message
     // rows travel to the first device at end of file: direct NVLink copies where the devices are peers (the copy also
     // works without, staged through the host)

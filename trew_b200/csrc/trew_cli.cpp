@@ -2,6 +2,8 @@
 // exit codes as the reference's main (src/trew.cpp:22-477), driving the B200 scan through the C ABI.
 // -t / -m / -q are accepted and validated for compatibility but do not steer the GPU path (the consumers are GPUs,
 // the host side always uses every core; the rotation table and the chunk queue do not exist here).
+#include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -169,6 +171,21 @@ int main(int argc, char** argv) {
             else if (input_bytes < ((uintmax_t)512 << 20)) devices.push_back(0);
         }   // empty list = all visible devices
     }
+    // Only the chosen devices are made visible to the CUDA runtime (unless the caller set CUDA_VISIBLE_DEVICES already):
+    // initialising the driver takes time per visible GPU, and a small input that runs on one GPU of an eight-GPU box
+    // should not pay for the other seven.
+    if (!devices.empty() && !getenv("CUDA_VISIBLE_DEVICES")) {
+        std::vector<int32_t> uniq;
+        for (int32_t d : devices) if (std::find(uniq.begin(), uniq.end(), d) == uniq.end()) uniq.push_back(d);
+        std::string vis;
+        for (size_t i = 0; i < uniq.size(); i++) vis += (i ? "," : "") + std::to_string(uniq[i]);
+        setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
+        for (int32_t& d : devices) d = (int32_t)(std::find(uniq.begin(), uniq.end(), d) - uniq.begin());
+    }
+    // TREW_CLI_TIMING=1: wall-clock of the phases on stderr
+    const bool timing = getenv("TREW_CLI_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = now();
     trew_multi* ctx = nullptr;
     int rc = trew_multi_create(&cfg, devices.empty() ? nullptr : devices.data(), (int32_t)devices.size(), &ctx);
     if (rc != TREW_OK) {
@@ -179,6 +196,7 @@ int main(int argc, char** argv) {
     // One input (file or pair): only rows that can reach the report leave the device (see trew_dev_set_report_filter);
     // with several inputs every entry is needed, small counts add up across files (src/trew.cpp:454-467).
     if (paths.size() == (cfg.mode == TREW_MODE_PAIR ? 2u : 1u) && !getenv("TREW_FULL_TABLES")) trew_multi_set_report_filter(ctx, 10);
+    if (timing) fprintf(stderr, "[trew] contexts on %d device(s): %.1f ms\n", trew_multi_device_count(ctx), now() - t_start);
     trew_report* rep = nullptr;
     trew_report_create(min_mer, &rep);
 
@@ -194,11 +212,14 @@ int main(int argc, char** argv) {
             a = std::filesystem::canonical(paths[i]).string();
             g1 = has_gz_ext(paths[i]);
         }
+        const double t_file = now();
         trew_multi_reset(ctx);
         rc = trew_multi_process_file(ctx, a.c_str(), g1, is_pair ? b.c_str() : nullptr, g2);
         const trew_entry* entries = nullptr;
         uint64_t n = 0;
+        const double t_scanned = now();
         if (rc == TREW_OK) rc = trew_multi_finish(ctx, &entries, &n);
+        if (timing) fprintf(stderr, "[trew] %s: read + scan %.1f ms, tables %.1f ms\n", a.c_str(), t_scanned - t_file, now() - t_scanned);
         if (rc != TREW_OK) {
             fprintf(stderr, "%s\n", trew_multi_last_error(ctx));  // the reference prints and exit(EXIT_FAILURE)s
             trew_report_destroy(rep);
@@ -220,6 +241,8 @@ int main(int argc, char** argv) {
     trew_report_finish(rep, &text, &len);
     fwrite(text + printed, 1, len - printed, stdout);
     trew_report_destroy(rep);
+    const double t_done = now();
     trew_multi_destroy(ctx);
+    if (timing) fprintf(stderr, "[trew] report %.1f ms after the last file, teardown %.1f ms, total %.1f ms\n", t_done - t_start, now() - t_done, now() - t_start);
     return 0;
 }
