@@ -397,8 +397,15 @@ ET_HD bool route_short_thread(Mem m, int n, u32 pm, int min_mer, int max_mer, co
     u32 L = 0, R = 0;   // target_k_high | target_k_low << 8 of the two halves
     K sh, sl;
     const bool halves = n >= 4 * min_mer;
-    if (halves && (pm & 1u)) { load(0, 0, llen); L = scan_window(m, llen, min_mer, kmax, thr_low, thr_high, x, sh, sl); }
-    if (halves && (pm & 2u)) { load(0, roff, rlen); R = scan_window(m, rlen, min_mer, kmax, thr_low, thr_high, x, sh, sl); }   // "always evaluated"
+    // both halves are "always evaluated"; every lane starts with ITS first vouched-for half (half-repeats and chance
+    // survivors have one), so the lanes of a warp scan together instead of taking turns by half
+    for (u32 todo = halves ? pm & 3u : 0u; todo != 0u; todo &= todo - 1u) {
+        const bool right = (todo & 1u) == 0u;
+        const int len = right ? rlen : llen;
+        load(0, right ? roff : 0, len);
+        const u32 r = scan_window(m, len, min_mer, kmax, thr_low, thr_high, x, sh, sl);
+        if (right) R = r; else L = r;
+    }
     if (4 * max_mer > n) {
         // short reads: periods above n / 4 are looked for in the whole read, for the selections that found nothing in
         // either half; their classes go into 'both' UN-folded (src/kmer.cpp:165-171).  The probe of this scan is bit 2

@@ -786,8 +786,13 @@ __global__ void __launch_bounds__(kDecideThreads, (MAXNW <= 5 ? 4 : 2)) trew_fil
             Probe p[4];
             int np = unit_probes(cfg, b, u, p);
             live = pm & ((1u << np) - 1u);   // probes that may still find a target period
-            for (int j = 0; j < np && !maybe; j++) {
-                if (((pm >> j) & 1u) && p[j].k1 >= p[j].k0)
+            // every lane goes to ITS next flagged probe (most units have one: the half an N fell into), not all lanes to
+            // probe 0, then 1, ...: in index order the lanes of a warp took turns
+            u32 todo = live;
+            while (todo != 0u && !maybe) {
+                const int j = __ffs(todo) - 1;
+                todo &= todo - 1u;
+                if (p[j].k1 >= p[j].k0)
                     maybe = probe_is_fast(p[j]) ? decide_short(b, p[j].pos, p[j].wl, p[j].k0, p[j].k1, thr, t_hit, s_m4 + threadIdx.x, third_level) : probe_dispatch<MAXNW>(b, p[j], thr);
                 if (!maybe) live &= ~(1u << j);
             }
