@@ -183,12 +183,13 @@ int launch_scan(trew_ctx* ctx, const DevBatch& b, uint32_t n_units, uint32_t max
         *scratch_bytes = need;
     }
     ctx->export_valid = false;
-    // d_counters: [0] survivors (list A) [1] work counter [2] deferred [3] thread-kernel bails [4] survivors, list B [5] work counter [6] work counter of the thread kernel
+    // d_counters: [0] survivors (list A) [1] work counter [2] deferred [3] thread-kernel bails [4] survivors, list B [5] work counter [6] work counter of the thread kernel [7] work counter of the decide kernel
     CK(cudaMemsetAsync(d_counters, 0, kScanCounters * sizeof(unsigned int), st));
     if (ev) CK(cudaEventRecord(ev[0], st));
     const bool thread_path = thread_path_applies(ctx->dcfg, max_read_len) && !(ctx->exact_flags & 4u) && n_units < (1u << 28);
     launch_filter(ctx->dcfg, b, n_units, max_read_len, d_survivors + n_units, d_counters + 2, d_survivors, d_counters, ctx->plan, st,
-                  ev ? ev[1] : nullptr, thread_path ? d_survivors + n_units - 1 : nullptr, thread_path ? d_counters + 4 : nullptr);
+                  ev ? ev[1] : nullptr, thread_path ? d_survivors + n_units - 1 : nullptr, thread_path ? d_counters + 4 : nullptr,
+                  d_counters + 7);
     if (ev) CK(cudaEventRecord(ev[2], st));
     ExactArgs a{};
     a.survivors = d_survivors; a.n_survivors = d_counters; a.work_counter = d_counters + 1;

@@ -766,50 +766,65 @@ template <int MAXNW>
 __global__ void __launch_bounds__(kDecideThreads, (MAXNW <= 5 ? 4 : 2)) trew_filter_kernel(DevCfg cfg, DevBatch b, const u32* __restrict__ units,
                                                           const u32* __restrict__ n_units_ptr, u32 n_units_all,
                                                           u32* __restrict__ survivors, u32* __restrict__ n_survivors,
-                                                          u32* __restrict__ surv_b_top, u32* __restrict__ n_surv_b, int thread_min_windows, int third_level) {   // third_level: asked for periods with fewer valid windows than this
+                                                          u32* __restrict__ surv_b_top, u32* __restrict__ n_surv_b, int thread_min_windows, int third_level,   // third_level: asked for periods with fewer valid windows than this
+                                                          u32* __restrict__ work_counter) {
     __shared__ unsigned short thr[kThrTableSize];
     __shared__ u32 s_m4[18 * kDecideThreads];   // mod4_level: the probe's prefix planes, per thread
     for (int i = threadIdx.x; i < kThrTableSize; i += blockDim.x) thr[i] = cfg.thr_low[i];
     __syncthreads();
     const u32 n_units = units ? *n_units_ptr : n_units_all;   // no list: every unit of the batch
     const bool pack_probes = n_units_all < (1u << kProbeShift);
-    u32 stride = gridDim.x * blockDim.x;
-    u32 n_round = (n_units + 31u) & ~31u;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        bool maybe = false;
-        u32 u = 0, live = 0;
-        int t_hit = 1 << 20;
-        if (i < n_units) {
-            u32 pm = 0xfu;
-            u = i;
-            if (units) { u32 e = units[i]; u = e & ((1u << kProbeShift) - 1u); pm = e >> kProbeShift; }
-            Probe p[4];
-            int np = unit_probes(cfg, b, u, p);
-            live = pm & ((1u << np) - 1u);   // probes that may still find a target period
-            // every lane goes to ITS next flagged probe (most units have one: the half an N fell into), not all lanes to
-            // probe 0, then 1, ...: in index order the lanes of a warp took turns
-            u32 todo = live;
-            while (todo != 0u && !maybe) {
-                const int j = __ffs(todo) - 1;
-                todo &= todo - 1u;
-                if (p[j].k1 >= p[j].k0)
-                    maybe = probe_is_fast(p[j]) ? decide_short(b, p[j].pos, p[j].wl, p[j].k0, p[j].k1, thr, t_hit, s_m4 + threadIdx.x, third_level) : probe_dispatch<MAXNW>(b, p[j], thr);
-                if (!maybe) live &= ~(1u << j);
+    // Lane-level work queue.  A probe is ~2 400 instructions; most units have one flagged probe (the half an N fell into),
+    // some two or three, repeats leave their first after two periods.  With a unit per lane and round the few lanes with a
+    // second probe cost the warp a whole pass (ncu: 18 of 32 lanes in the period loop).  Instead every round each lane
+    // decides ONE probe; a lane whose unit is done hands it in and takes the next unit from the shared counter, so the
+    // warp keeps 32 probes in flight until the list is empty.
+    const u32 lane = lane_id();
+    bool have = false, maybe = false, exhausted = false;
+    u32 u = 0, live = 0, todo = 0;
+    int t_hit = 1 << 20;
+    Probe p[4];
+    for (;;) {
+        const u32 idle = __ballot_sync(0xffffffffu, !have);
+        if (idle != 0u && !exhausted) {
+            u32 base = 0;
+            if (lane == 0) base = atomicAdd(work_counter, (u32)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            exhausted = base + (u32)__popc(idle) >= n_units;
+            const u32 i = base + (u32)__popc(idle & ((1u << lane) - 1u));
+            if (!have && i < n_units) {
+                u32 pm = 0xfu;
+                u = i;
+                if (units) { const u32 e = units[i]; u = e & ((1u << kProbeShift) - 1u); pm = e >> kProbeShift; }
+                const int np = unit_probes(cfg, b, u, p);
+                live = todo = pm & ((1u << np) - 1u);   // live: probes that may still find a target period
+                maybe = false; t_hit = 1 << 20; have = true;
             }
         }
+        if (__ballot_sync(0xffffffffu, have) == 0u) break;
+        if (have && todo != 0u) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            if (p[j].k1 >= p[j].k0)
+                maybe = probe_is_fast(p[j]) ? decide_short(b, p[j].pos, p[j].wl, p[j].k0, p[j].k1, thr, t_hit, s_m4 + threadIdx.x, third_level)
+                                            : probe_dispatch<MAXNW>(b, p[j], thr);
+            if (!maybe) live &= ~(1u << j);
+        }
+        const bool fin = have && (todo == 0u || maybe);
+        const bool keep = fin && maybe;
         // the exact kernel skips the scan of a window no probe vouches for (its result is "no target period")
         const u32 entry = pack_probes ? u | (live << kProbeShift) : u;
         if (surv_b_top == nullptr) {
-            list_append(maybe, entry, survivors, n_survivors);
+            list_append(keep, entry, survivors, n_survivors);
         } else {
-            // Two lists for the two exact kernels (short single-end mode).  Up from the bottom of the survivor array: reads
+            // Two lists for the two exact kernels (short and paired mode).  Up from the bottom of the survivor array: reads
             // the thread-per-survivor kernel takes -- at most 160 bases, and the period that made them survivors still
             // has most of its windows (a repeat).  Down from the top: the others, above all reads an N made survivors of
             // (a period the N leaves a dozen windows of passes the bound easily; turning those away means comparing
             // many one-window runs -- long, lane-divergent loops in the thread kernel, a few warp-wide instructions in the
             // warp kernel's comp_bound).  Both kernels are exact for every read; the split only places the work.
             bool to_b = false;
-            if (maybe) {
+            if (keep) {
                 int len;
                 if (cfg.mode == 1) {
                     const u32 a0 = __ldg(b.bit_off + 2 * u), a1 = __ldg(b.bit_off + 2 * u + 1), a2 = __ldg(b.bit_off + 2 * u + 2);
@@ -819,16 +834,17 @@ __global__ void __launch_bounds__(kDecideThreads, (MAXNW <= 5 ? 4 : 2)) trew_fil
                 }
                 to_b = len > et::kMaxRead || t_hit < thread_min_windows;
             }
-            list_append(maybe && !to_b, entry, survivors, n_survivors);
-            list_append_rev(maybe && to_b, entry, surv_b_top, n_surv_b);
+            list_append(keep && !to_b, entry, survivors, n_survivors);
+            list_append_rev(keep && to_b, entry, surv_b_top, n_surv_b);
         }
+        if (fin) have = false;
     }
 }
 
 void launch_filter(const DevCfg& cfg, const DevBatch& b, unsigned int n_units, unsigned int max_read_len,
                    unsigned int* deferred, unsigned int* n_deferred, unsigned int* survivors, unsigned int* n_survivors,
                    const LaunchPlan& plan, cudaStream_t stream, cudaEvent_t after_screen, unsigned int* surv_b_top,
-                   unsigned int* n_surv_b) {
+                   unsigned int* n_surv_b, unsigned int* work_counter) {
     if (n_units == 0) return;
     // longest probe window: a half read, a whole read (n < 4*MAX) or a slice (long mode)
     unsigned int longest;
@@ -849,9 +865,9 @@ void launch_filter(const DevCfg& cfg, const DevBatch& b, unsigned int n_units, u
     const unsigned int* list = screen ? deferred : nullptr;
     int blocks = plan.decide_blocks;
     if ((unsigned)blocks > need) blocks = (int)need;
-    if (longest + 1 <= 96) trew_filter_kernel<3><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors, surv_b_top, n_surv_b, tmw, m4_on);
-    else if (longest + 1 <= 160) trew_filter_kernel<5><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors, surv_b_top, n_surv_b, tmw, m4_on);
-    else trew_filter_kernel<8><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors, surv_b_top, n_surv_b, tmw, m4_on);
+    if (longest + 1 <= 96) trew_filter_kernel<3><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors, surv_b_top, n_surv_b, tmw, m4_on, work_counter);
+    else if (longest + 1 <= 160) trew_filter_kernel<5><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors, surv_b_top, n_surv_b, tmw, m4_on, work_counter);
+    else trew_filter_kernel<8><<<blocks, 256, 0, stream>>>(cfg, b, list, n_deferred, n_units, survivors, n_survivors, surv_b_top, n_surv_b, tmw, m4_on, work_counter);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2083,11 +2099,11 @@ cudaError_t prepare_exact(int run_cap_max) {
     return e;
 }
 
-// screen / decide: many more blocks than are resident (8 / 4 per SM).  Their threads all do the same amount of work, but
-// the warps of an SM drift apart, and in a single wave a third of the warp slots stood empty on average (ncu: 42 of 64
-// warps active) while the last warps finished; with 16 / 8 waves the block scheduler refills the slots.  Measured on
-// 25 M reads: screen 2.24 -> 2.05 ms (8 -> 128 blocks per SM; 64: 2.06, 256: 2.05), decide 0.95 -> 0.92 (8 -> 32; 128: 0.94).
-LaunchPlan default_launch_plan(int sm_count) { return LaunchPlan{sm_count * 128, sm_count * 32, sm_count * kExactBlocksPerSM}; }
+// screen: many more blocks than are resident (8 per SM).  Its threads all do the same amount of work, but the warps of an
+// SM drift apart, and in a single wave a third of the warp slots stood empty on average (ncu: 42 of 64 warps active)
+// while the last warps finished; with 16 waves the block scheduler refills the slots.  Measured on 25 M reads: 2.24 ->
+// 2.05 ms (8 -> 128 blocks per SM; 64: 2.06, 256: 2.05).  decide: resident blocks that share a work counter.
+LaunchPlan default_launch_plan(int sm_count) { return LaunchPlan{sm_count * 128, sm_count * 4, sm_count * kExactBlocksPerSM}; }
 
 void launch_exact(const DevCfg& cfg, const DevBatch& b, const ExactArgs& a, const LaunchPlan& plan, cudaStream_t stream) {
     size_t smem = exact_smem_bytes(a.run_cap, true);

@@ -73,8 +73,8 @@ LaunchPlan default_launch_plan(int sm_count);
 // deferred / n_deferred: scratch list of n_units entries + its counter (zeroed) for the screen kernel
 void launch_filter(const DevCfg& cfg, const DevBatch& b, unsigned int n_units, unsigned int max_read_len,
                    unsigned int* deferred, unsigned int* n_deferred, unsigned int* survivors, unsigned int* n_survivors,
-                   const LaunchPlan& plan, cudaStream_t stream, cudaEvent_t after_screen = nullptr,
-                   unsigned int* surv_b_top = nullptr, unsigned int* n_surv_b = nullptr);
+                   const LaunchPlan& plan, cudaStream_t stream, cudaEvent_t after_screen,
+                   unsigned int* surv_b_top, unsigned int* n_surv_b, unsigned int* work_counter);
 size_t exact_smem_bytes(int run_cap, bool wide);
 cudaError_t prepare_exact(int run_cap_max);
 void launch_exact(const DevCfg& cfg, const DevBatch& b, const ExactArgs& a, const LaunchPlan& plan, cudaStream_t stream);
