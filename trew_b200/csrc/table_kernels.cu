@@ -24,24 +24,29 @@ __global__ void compact_kernel(const Slot* __restrict__ slots, u32 n_slots, trew
         uint4 h[4];
 #pragma unroll
         for (int r = 0; r < 4; r++) h[r] = __ldg(reinterpret_cast<const uint4*>(slots + i0 + 32u * r + lane) + 1);   // count lo, count hi, meta, state
+        u32 m[4], total = 0;
 #pragma unroll
         for (int r = 0; r < 4; r++) {
-            const bool used = h[r].w == 2u && (h[r].x | h[r].y) != 0u;
-            const u32 m = __ballot_sync(0xffffffffu, used);
-            if (m) {
-                u32 base = 0;
-                if (lane == (u32)(__ffs(m) - 1)) base = atomicAdd(d_n, (u32)__popc(m));
-                base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-                const u32 o = base + __popc(m & ((1u << lane) - 1u));
-                if (used && o < cap) {  // past the end of the array: count only, the host grows it and runs again
-                    const uint4 key = __ldg(reinterpret_cast<const uint4*>(slots + i0 + 32u * r + lane));
-                    trew_entry e;
-                    e.seq_lo = (u64)key.x | ((u64)key.y << 32); e.seq_hi = (u64)key.z | ((u64)key.w << 32);
-                    e.count = (u64)h[r].x | ((u64)h[r].y << 32);
-                    e.table = (int)(h[r].z >> 8); e.k = (int)(h[r].z & 0xffu);
-                    out[o] = e;
-                }
+            m[r] = __ballot_sync(0xffffffffu, h[r].w == 2u && (h[r].x | h[r].y) != 0u);
+            total += (u32)__popc(m[r]);
+        }
+        if (total == 0u) continue;
+        // one atomic per 128 slots: every add goes to the same address, and same-address atomics retire one at a time
+        u32 base = 0;
+        if (lane == 0) base = atomicAdd(d_n, total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const u32 o = base + __popc(m[r] & ((1u << lane) - 1u));
+            if (((m[r] >> lane) & 1u) && o < cap) {  // past the end of the array: count only, the host grows it and runs again
+                const uint4 key = __ldg(reinterpret_cast<const uint4*>(slots + i0 + 32u * r + lane));
+                trew_entry e;
+                e.seq_lo = (u64)key.x | ((u64)key.y << 32); e.seq_hi = (u64)key.z | ((u64)key.w << 32);
+                e.count = (u64)h[r].x | ((u64)h[r].y << 32);
+                e.table = (int)(h[r].z >> 8); e.k = (int)(h[r].z & 0xffu);
+                out[o] = e;
             }
+            base += (u32)__popc(m[r]);
         }
     }
 }
