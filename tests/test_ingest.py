@@ -312,3 +312,66 @@ def test_gzip_own_reader_equals_zlib_reader(tmp_path):
         outs.append(out.stdout.split())
     assert outs[0] == outs[1]
     assert outs[0][1:] == ["0", "1500", "1500"]
+
+
+# ---- parallel gzip (pinflate.cpp): the same stream layer, every member's DEFLATE stream decoded by all threads ----------
+
+@pytest.fixture
+def parallel_gz(monkeypatch):
+    """Force the parallel path on small files: no size threshold, segments of a few KiB of compressed input."""
+    def on(segment):
+        monkeypatch.setenv("TREW_PGZ_MIN_BYTES", "0")
+        monkeypatch.setenv("TREW_PGZ_SEGMENT", str(segment))
+    return on
+
+
+@pytest.mark.parametrize("segment", [4096, 40000, 1 << 20])
+@pytest.mark.parametrize("chunk", [1000, 70000, 0])
+def test_parallel_gzip_members_headers_and_garbage(tmp_path, parallel_gz, segment, chunk):
+    parallel_gz(segment)
+    reads = synth.adversarial_short(31, 2500) + [bytes(r) for r in synth.config_short(32, 12000, telomeric=0.02, n_rate=0.002)]
+    data = synth.fastq_bytes(reads)
+    cut = [0, 1, 777, len(data) // 3, len(data) // 3 + 1, len(data) // 2, len(data)]
+    opts = [dict(), dict(extra=True), dict(name=b"a.fastq"), dict(comment=b"hello", hcrc=True), dict(level=0),
+            dict(extra=True, name=b"n", comment=b"c", hcrc=True, level=9)]
+    blob = b"".join(_gz_member(data[a:b], **o) for a, b, o in zip(cut, cut[1:], opts))
+    blob += _gz_member(b"") + b"\0\0\0 trailing bytes that are not a gzip member"
+    p = write(tmp_path, "m.fastq.gz", blob)
+    rc, msg, r1, _ = api.ingest_records(api.MODE_SHORT, p, chunk_bytes=chunk)
+    assert rc == 0, msg
+    assert r1 == reads
+
+
+@pytest.mark.parametrize("level", [1, 6, 9])
+def test_parallel_gzip_levels_and_pairs(tmp_path, parallel_gz, level):
+    parallel_gz(50000)   # a few DEFLATE blocks per segment: chains of several segments
+    a = [bytes(r) for r in synth.config_short(33, 16000, telomeric=0.01, n_rate=0.001)]
+    b = synth.adversarial_short(34, 16000)
+    p1, p2 = os.path.join(tmp_path, "a.fastq.gz"), os.path.join(tmp_path, "b.fastq.gz")
+    for p, r in ((p1, a), (p2, b)):
+        with gzip.open(p, "wb", compresslevel=level) as f:
+            f.write(synth.fastq_bytes(r))
+    rc, msg, r1, _ = api.ingest_records(api.MODE_SHORT, p1, chunk_bytes=50000)
+    assert rc == 0 and r1 == a, msg
+    rc, msg, r1, r2 = api.ingest_records(api.MODE_PAIR, p1, p2, chunk_bytes=40000)
+    assert rc == 0 and r1 == a and r2 == b, msg
+
+
+def test_parallel_gzip_errors(tmp_path, parallel_gz):
+    import struct
+    parallel_gz(30000)
+    reads = synth.adversarial_short(35, 12000)
+    good = _gz_member(synth.fastq_bytes(reads))
+    cases = {
+        "truncated body": good[:len(good) // 2],
+        "truncated trailer": good[:-3],
+        "bad crc": good[:-8] + struct.pack("<I", 12345) + good[-4:],
+        "bad isize": good[:-4] + struct.pack("<I", 7),
+        "corrupt body": good[:4000] + bytes([good[4000] ^ 0xFF, good[4001] ^ 0x55]) + good[4002:],
+        "reserved header flag": good[:3] + b"\x80" + good[4:],
+    }
+    for name, blob in cases.items():
+        p = write(tmp_path, "bad.fastq.gz", blob)
+        rc, msg, r1, _ = api.ingest_records(api.MODE_SHORT, p)
+        assert rc != 0, name
+        assert "File-IO Error" in msg, (name, msg)

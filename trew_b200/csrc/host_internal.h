@@ -189,6 +189,54 @@ private:
     uint8_t hist_[kWindow];
 };
 
+// pinflate.cpp: one DEFLATE stream held in memory, decoded by all threads of a pool (speculative block starts, 16-bit
+// symbols for what a segment copies from before its start; see the file's header)
+struct RawBytes {   // growing byte array that is never zero-filled
+    uint8_t* d = nullptr; size_t n = 0, cap = 0;
+    RawBytes() {}
+    RawBytes(const RawBytes&) = delete;
+    RawBytes& operator=(const RawBytes&) = delete;
+    ~RawBytes() { free(d); }
+    bool reserve(size_t want) {
+        if (want <= cap) return true;
+        size_t c = cap ? cap : ((size_t)1 << 20);
+        while (c < want) c += c / 2;
+        uint8_t* p = (uint8_t*)realloc(d, c);
+        if (!p) return false;
+        d = p; cap = c;
+        return true;
+    }
+};
+
+class ParallelInflate {
+public:
+    ParallelInflate();
+    ~ParallelInflate();
+    // the stream starts at byte first_byte of in[0, n) (right behind a gzip header); no history
+    void start(const uint8_t* in, size_t n, size_t first_byte);
+    // Decodes the next part (about pool->size() segments of compressed input) and appends its bytes to `out`.
+    // *member_end: the final block ended, *next_byte = offset of the byte behind the stream.  false: bad data, *err says what.
+    bool next(Pool* pool, RawBytes& out, bool* member_end, size_t* next_byte, const char** err);
+    // the same in two steps, for callers that place the bytes themselves: decode() keeps the part as symbols and says
+    // how many bytes it is, emit() writes bytes [off, off + len) of it to dst (any ranges, any order, until the next decode())
+    bool decode(Pool* pool, size_t* total, bool* member_end, size_t* next_byte, const char** err);
+    void emit(Pool* pool, uint8_t* dst, size_t off, size_t len);
+    size_t segment_bytes() const { return seg_bytes_; }
+    // how the work went (tests, traces): calls of next(), segments with a block start found, segments on the chains
+    uint64_t stat_calls = 0, stat_found = 0, stat_chained = 0;
+
+private:
+    struct Segment;
+    std::vector<Segment*> seg_;        // kept between calls: their symbol arrays are large
+    std::vector<int> chain_;           // the segments of the last decode() that follow each other
+    std::vector<std::vector<uint8_t>> wins_;   // ... and the window before each of them
+    const uint8_t* in_ = nullptr;
+    size_t n_ = 0;
+    uint64_t pos_ = 0;                 // next bit of the stream
+    std::vector<uint8_t> window_;      // the last <= 32 KiB produced
+    size_t seg_bytes_;
+};
+
 // ingest.cpp: FASTQ / FASTQ.gz record reader with the reference's record semantics
 struct IngestResult { int status; std::string message; };
 typedef std::function<int(const char* buf1, const std::vector<int32_t>& locs1, const char* buf2,

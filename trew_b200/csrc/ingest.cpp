@@ -159,6 +159,13 @@ struct Reader {
     struct CrcPiece { const char* p; size_t len; bool member_end; uint32_t want; };
     std::vector<CrcPiece> crc_todo;
     uint32_t z_crc = 0;
+    // With a pool of at least four threads the members' DEFLATE streams are decoded by all of them (pinflate.cpp:
+    // speculative block starts in the mapped compressed file); same stream semantics and checks as read_gz.
+    bool pgz = false, pgz_tried = false;
+    ParallelInflate pz;
+    size_t pz_pos = 0;            // next member header
+    bool pz_in_member = false, pz_trailer_due = false, pz_done = false;
+    size_t pz_total = 0, pz_emitted = 0, pz_next_byte = 0;   // the part decode() holds, what was handed out of it, the byte behind the stream
 
     static bool bgzf_header(const unsigned char* p, size_t avail, uint32_t* bsize, uint32_t* hdr_len) {
         if (avail < 18 || p[0] != 31 || p[1] != 139 || p[2] != 8 || !(p[3] & 4)) return false;
@@ -385,6 +392,62 @@ struct Reader {
         return (long)done;
     }
 
+    void try_parallel_gz(Pool* pool) {
+        if (!pool) return;   // (asked again when a pool comes along)
+        pgz_tried = true;
+        size_t min_bytes = (size_t)1 << 20;
+        if (const char* e = getenv("TREW_PGZ_MIN_BYTES")) min_bytes = (size_t)std::max(0L, atol(e));
+        if (!pool || pool->size() < 4 || size < (int64_t)min_bytes || offset != 0 || z_have != 0 || getenv("TREW_NO_PARALLEL_GZ")) return;
+        void* m = mmap(nullptr, (size_t)size, PROT_READ, MAP_SHARED, fd, 0);
+        if (m == MAP_FAILED) return;
+        cmap = (const unsigned char*)m;
+        pgz = true;
+    }
+
+    static uint32_t le32(const unsigned char* p) { return p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+    long read_pgz(char* buf, size_t n, Pool* pool) {
+        size_t done = 0;
+        while (done < n) {
+            if (pz_emitted < pz_total) {   // straight into the caller's block; what does not fit waits in the decoder as symbols
+                const size_t m = std::min(n - done, pz_total - pz_emitted);
+                pz.emit(pool, (uint8_t*)buf + done, pz_emitted, m);
+                crc_todo.push_back(CrcPiece{buf + done, m, false, 0});
+                pz_emitted += m; done += m; z_len += m;
+                continue;
+            }
+            if (pz_trailer_due) {   // CRC-32 and ISIZE, little endian
+                if (pz_next_byte + 8 > (size_t)size) { zerr = "unexpected end of file"; return -1; }
+                if (le32(cmap + pz_next_byte + 4) != (uint32_t)z_len) { zerr = "incorrect length check"; return -1; }
+                crc_todo.push_back(CrcPiece{buf + done, 0, true, le32(cmap + pz_next_byte)});
+                pz_pos = pz_next_byte + 8;
+                pz_in_member = false; pz_trailer_due = false;
+                continue;
+            }
+            if (pz_done) break;
+            if (!pz_in_member) {
+                const unsigned char* p = cmap + pz_pos;
+                const size_t avail = (size_t)size - pz_pos;
+                if (avail < 2 || p[0] != 31 || p[1] != 139) {
+                    // end of file, or bytes that are not another member: ignored once a member was read (as gzread does)
+                    if (avail == 0 || z_any_member) { pz_done = true; break; }
+                    zerr = "not in gzip format"; return -1;
+                }
+                const long hl = gz_header_len(p, avail);
+                if (hl < 0) { zerr = "unknown compression method or header flags"; return -1; }
+                if (hl == 0) { zerr = "unexpected end of file"; return -1; }
+                pz.start(cmap, (size_t)size, pz_pos + (size_t)hl);
+                pz_in_member = true; z_any_member = true; z_len = 0;
+            }
+            const char* e = nullptr;
+            bool mend = false;
+            size_t nb = 0, total = 0;
+            if (!pz.decode(pool, &total, &mend, &nb, &e)) { zerr = e ? e : "invalid compressed data"; return -1; }
+            pz_total = total; pz_emitted = 0; pz_trailer_due = mend; pz_next_byte = nb;
+        }
+        return (long)done;
+    }
+
     // CRC-32 of what read_gz handed out since the last call (parallel slices combined with crc32_combine)
     bool finish_crc(Pool* pool) {
         bool ok = true;
@@ -423,6 +486,8 @@ struct Reader {
     long read(char* buf, size_t n, Pool* pool, size_t par_min, const Hook* hook = nullptr, int* hook_slices = nullptr) {
         if (hook_slices) *hook_slices = 0;
         if (bgzf) return read_bgzf(buf, std::min<size_t>(n, (size_t)1 << 30), pool);
+        if (ownz && !pgz_tried) try_parallel_gz(pool);
+        if (pgz) return read_pgz(buf, std::min<size_t>(n, (size_t)1 << 30), pool);
         if (ownz) return read_gz(buf, std::min<size_t>(n, (size_t)1 << 30));
         if (gz) {
             int r = gzread(gfp, buf, (unsigned)std::min<size_t>(n, 1u << 30));
@@ -708,8 +773,11 @@ IngestResult ingest_file(int mode, int slice_length, const char* file1, bool gz1
             if (have + want[i] >= (size_t)0x7fffffff)
                 return IngestResult{TREW_ERR_PAIRING, "Error: a paired-end record does not fit a 2 GiB block."};
         }
-        if (pool && pool->size() > 1 && (gz1 || gz2)) {
-            // two inflate streams are independent: read both mates' blocks at the same time
+        for (int i = 0; i < 2; i++) if (sides[i]->rd.ownz && !sides[i]->rd.pgz_tried) sides[i]->rd.try_parallel_gz(pool);
+        const bool one_stream_per_thread = (gz1 && !a.rd.pgz && !a.rd.bgzf) || (gz2 && !b.rd.pgz && !b.rd.bgzf);
+        if (pool && pool->size() > 1 && (gz1 || gz2) && one_stream_per_thread) {
+            // two inflate streams are independent: read both mates' blocks at the same time (streams that all threads
+            // decode together -- parallel gzip, BGZF -- take the other branch, one file after the other)
             bool ok[2] = {true, true};
             pool->run(2, [&](int i) { if (!sides[i]->eof) ok[i] = sides[i]->fill(want[i], nullptr, par_min, true); });
             for (int i = 0; i < 2; i++) ok[i] = ok[i] && sides[i]->rd.finish_crc(pool);   // the members' CRC-32, on all threads
