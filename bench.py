@@ -529,8 +529,9 @@ def file_e2e(multi, api, synth, n_gpus):
             cli_s = time.perf_counter() - t0
             out[name] = {"value": n * READ_LEN / best / 1e9, "unit": "Gbases/s", "reads": n, "file_bytes": os.path.getsize(path),
                          "trew_cli": {"wall_s": cli_s, "value": n * READ_LEN / cli_s / 1e9, "unit": "Gbases/s"}}
-        out["note"] = ("one file: plain gzip is bound by single-stream inflate as in the reference (the library's own DEFLATE decoder, "
-                       "about 2x zlib); BGZF (bgzip) members are inflated in parallel; plain FASTQ by the newline index and the packer, both working "
+        out["note"] = ("one file: a plain gzip member is ONE DEFLATE stream (the reference reads it through one gzread); here all host threads "
+                       "decode it together (speculative block starts, pinflate.cpp; this file is gzip -1, the worst case: more symbols per byte; "
+                       "TREW_NO_PARALLEL_GZ=1 gives the one-core figure); BGZF (bgzip) members are inflated in parallel; plain FASTQ is bound by the newline index and the packer, both working "
                        "on the mapped file.  trew_cli = the `trew short 5 32 FILE` binary as a subprocess, wall clock: CUDA context creation "
                        "and pinned-buffer allocation (a fixed ~0.5-1 s per GPU) dominate at this file size")
     finally:
