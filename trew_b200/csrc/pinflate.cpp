@@ -33,6 +33,7 @@ namespace {
 constexpr size_t kWin = 32768;
 constexpr uint16_t kMark = 0x8000u;
 constexpr size_t kLitCap32 = 4096, kDistCap32 = 1024;
+constexpr size_t kMaxSegmentSymbols = (size_t)32 << 20;   // a segment that has produced this much stops at its next block boundary
 
 inline uint64_t load_le64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v; }
 
@@ -307,7 +308,8 @@ bool block_starts_at(const uint8_t* in, size_t n, uint64_t pos, Tables& t) {
 struct ParallelInflate::Segment {
     uint64_t start = 0, end = 0;     // bit positions
     bool found = false;              // a block start was found (segment 0: given)
-    int stop = 0;                    // 1 landed on a later segment's start / the end of the span, 2 the final block ended, 0 error
+    int stop = 0;                    // 1 landed on a later segment's start / the end of the span, 2 the final block ended,
+                                     // 3 stopped early at a block boundary (output bound), 0 error
     bool eof = false;                // ... because the input ended
     Sym out;
     size_t out_off = 0;              // where its bytes go
@@ -374,6 +376,9 @@ bool ParallelInflate::decode(Pool* pool, size_t* total_out, bool* member_end, si
         for (bool first = true;; first = false) {
             if (!first) {
                 if (br.pos >= span_end || std::binary_search(starts.begin(), starts.end(), br.pos)) { s.stop = 1; break; }
+                // very compressible data (runs of one base, of N): the round ends here and the next one goes on from this
+                // boundary, so that the symbols of a round stay bounded (16 segments x 64 MB) whatever the ratio
+                if (s.out.n > kMaxSegmentSymbols) { s.stop = 3; break; }
             }
             bool fin; int type; uint32_t sl = 0;
             if (!read_block_header(br, false, &fin, &type, &sl, *t)) break;
@@ -425,7 +430,7 @@ bool ParallelInflate::decode(Pool* pool, size_t* total_out, bool* member_end, si
             }
             w.swap(nw);
             if (s.stop == 2) { *member_end = true; break; }
-            if (s.end >= span_end) break;
+            if (s.end >= span_end || s.stop == 3) break;
             int nxt = -1;
             for (int j = cur + 1; j < P; j++) if (seg[(size_t)j].found && seg[(size_t)j].start == s.end) { nxt = j; break; }
             if (nxt < 0) { *err = "invalid compressed data"; return false; }   // cannot happen: it stopped there because of j
