@@ -449,28 +449,33 @@ bool ParallelInflate::decode(Pool* pool, size_t* total_out, bool* member_end, si
     return true;
 }
 
-// bytes [off, off + len) of what the last decode() produced: symbols -> bytes, the chain's links in parallel
+// bytes [off, off + len) of what the last decode() produced: symbols -> bytes.  The range is cut into equal parts, one per
+// thread, whatever links of the chain they fall into (a caller's block often ends in the middle of a round: by link, the
+// few links of such a tail would be all the parallelism).
 void ParallelInflate::emit(Pool* pool, uint8_t* dst, size_t off, size_t len) {
-    auto translate = [&](int c) {
-        const Segment& s = *seg_[(size_t)chain_[(size_t)c]];
-        const size_t a = std::max(off, s.out_off), b = std::min(off + len, s.out_off + s.out.n);
-        if (a >= b) return;
-        const std::vector<uint8_t>& win = wins_[(size_t)c];
-        const uint8_t* wend = win.data() + win.size();
-        uint8_t* o = dst + (a - off);
-        const uint16_t* d = s.out.d + (a - s.out_off);
-        const size_t n = b - a;
-        size_t k = 0;
-        for (; k + 32 <= n; k += 32) {   // blocks without marks (nearly all) are narrowed without a branch per symbol
-            uint16_t any = 0;
-            for (int q = 0; q < 32; q++) any |= d[k + q];
-            if (any < kMark) { for (int q = 0; q < 32; q++) o[k + q] = (uint8_t)d[k + q]; }
-            else for (int q = 0; q < 32; q++) { const uint16_t v = d[k + q]; o[k + q] = v < kMark ? (uint8_t)v : *(wend - (kWin - (size_t)(v & 0x7FFFu))); }
+    auto narrow = [&](size_t lo, size_t hi) {   // bytes [lo, hi) of the round
+        for (size_t c = 0; c < chain_.size() && lo < hi; c++) {
+            const Segment& s = *seg_[(size_t)chain_[c]];
+            const size_t a = std::max(lo, s.out_off), b = std::min(hi, s.out_off + s.out.n);
+            if (a >= b) continue;
+            const std::vector<uint8_t>& win = wins_[c];
+            const uint8_t* wend = win.data() + win.size();
+            uint8_t* o = dst + (a - off);
+            const uint16_t* d = s.out.d + (a - s.out_off);
+            const size_t n = b - a;
+            size_t k = 0;
+            for (; k + 32 <= n; k += 32) {   // blocks without marks (nearly all) are narrowed without a branch per symbol
+                uint16_t any = 0;
+                for (int q = 0; q < 32; q++) any |= d[k + q];
+                if (any < kMark) { for (int q = 0; q < 32; q++) o[k + q] = (uint8_t)d[k + q]; }
+                else for (int q = 0; q < 32; q++) { const uint16_t v = d[k + q]; o[k + q] = v < kMark ? (uint8_t)v : *(wend - (kWin - (size_t)(v & 0x7FFFu))); }
+            }
+            for (; k < n; k++) { const uint16_t v = d[k]; o[k] = v < kMark ? (uint8_t)v : *(wend - (kWin - (size_t)(v & 0x7FFFu))); }
         }
-        for (; k < n; k++) { const uint16_t v = d[k]; o[k] = v < kMark ? (uint8_t)v : *(wend - (kWin - (size_t)(v & 0x7FFFu))); }
     };
-    if (pool && chain_.size() > 1) pool->run((int)chain_.size(), translate);
-    else for (size_t c = 0; c < chain_.size(); c++) translate((int)c);
+    const int P = pool && len >= ((size_t)1 << 20) ? pool->size() : 1;
+    if (P > 1) pool->run(P, [&](int i) { narrow(off + len * (size_t)i / (size_t)P, off + len * (size_t)(i + 1) / (size_t)P); });
+    else narrow(off, off + len);
 }
 
 }  // namespace trew
