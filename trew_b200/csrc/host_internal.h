@@ -229,7 +229,7 @@ private:
     struct Segment;
     std::vector<Segment*> seg_;        // kept between calls: their symbol arrays are large
     std::vector<int> chain_;           // the segments of the last decode() that follow each other
-    std::vector<std::vector<uint8_t>> wins_;   // ... and the window before each of them
+    std::vector<std::vector<uint8_t>> wins_;   // ... and each one's symbol -> byte table (built from the window before it)
     const uint8_t* in_ = nullptr;
     size_t n_ = 0;
     uint64_t pos_ = 0;                 // next bit of the stream
