@@ -286,6 +286,22 @@ int huffman_block(Bits& br, const Tables& t, Sym* out, size_t limit) {
     return rc;
 }
 
+// Cheap necessary conditions for "a non-final dynamic block starts at bit pos", straight from the bits: BFINAL = 0,
+// BTYPE = 10, HLIT <= 29, HDIST <= 29 and a code-length code that is a complete prefix code (Kraft sum exactly 1 over
+// the HCLEN + 4 three-bit lengths).  One position in a few hundred passes; only those are parsed for real.
+inline bool maybe_block_start(const uint8_t* in, size_t n, uint64_t pos) {
+    if ((pos >> 3) + 24 > n) return true;   // near the end of the input: let the checked parser decide
+    const uint64_t w = load_le64(in + (pos >> 3)) >> (pos & 7);
+    if ((w & 7u) != 4u) return false;
+    if (((w >> 3) & 31u) > 29u || ((w >> 8) & 31u) > 29u) return false;
+    const int hclen = (int)((w >> 13) & 15u) + 4;
+    const uint64_t p2 = pos + 17;
+    uint64_t v = load_le64(in + (p2 >> 3)) >> (p2 & 7);   // 57 bits = 19 fields
+    int kraft = 0;
+    for (int i = 0; i < hclen; i++) { const unsigned l = (unsigned)(v & 7u); v >>= 3; kraft += l ? 128 >> l : 0; }
+    return kraft == 128;
+}
+
 // Does a non-final dynamic block start at bit `pos`?  It must parse strictly, decode to its end, and be followed by
 // another valid block header.
 bool block_starts_at(const uint8_t* in, size_t n, uint64_t pos, Tables& t) {
@@ -357,7 +373,7 @@ bool ParallelInflate::decode(Pool* pool, size_t* total_out, bool* member_end, si
         const uint64_t a = (pos_ & ~(uint64_t)7) + (uint64_t)i * seg_bytes_ * 8, b = std::min(span_end, a + (uint64_t)seg_bytes_ * 8);
         Tables* t = new Tables();
         for (uint64_t p = a; p < b; p++) {
-            if (block_starts_at(in_, n_, p, *t)) { seg[(size_t)i].start = p; seg[(size_t)i].found = true; break; }
+            if (maybe_block_start(in_, n_, p) && block_starts_at(in_, n_, p, *t)) { seg[(size_t)i].start = p; seg[(size_t)i].found = true; break; }
         }
         delete t;
     };
