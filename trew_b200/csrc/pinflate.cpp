@@ -333,9 +333,10 @@ struct ParallelInflate::Segment {
 
 ParallelInflate::ParallelInflate() {
     // 512 KiB of compressed input per segment: the symbols of one round (16 segments x ~2 M symbols x 2 bytes) stay in the
-    // last-level cache between decode() and emit(), and the search for a block start (~1.6 ms whatever the segment) is
-    // a third of a segment's time.  Measured on the 16-core hosts, 2 M reads, gzip -6 / -1: 256 KiB 1.73 / 1.21 Gbases/s,
-    // 512 KiB 2.24 / 1.28, 1 MiB 1.86 / 1.16, 2 MiB 1.61 / 1.04 (one stream through the sequential decoder: 0.70 / 0.58)
+    // last-level cache between decode() and emit(), and the search for a block start is a small part of a segment's time.
+    // Measured on the 16-core hosts, 2 M reads, gzip -6 / -1 (before the table translation and the search prefilter):
+    // 256 KiB 1.73 / 1.21 Gbases/s, 512 KiB 2.24 / 1.28, 1 MiB 1.86 / 1.16, 2 MiB 1.61 / 1.04; now 2.92 / 2.31 at 512 KiB
+    // (one stream through the sequential decoder: 0.70 / 0.58)
     seg_bytes_ = (size_t)512 << 10;
     if (const char* e = getenv("TREW_PGZ_SEGMENT")) { const long v = atol(e); if (v >= 1024) seg_bytes_ = (size_t)v; }
 }
