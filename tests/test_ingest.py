@@ -357,9 +357,10 @@ def test_parallel_gzip_levels_and_pairs(tmp_path, parallel_gz, level):
     assert rc == 0 and r1 == a and r2 == b, msg
 
 
-def test_parallel_gzip_errors(tmp_path, parallel_gz):
+@pytest.mark.parametrize("segment", [30000, 4096])   # 4096: no block start inside a segment, the member ends on the sequential decoder
+def test_parallel_gzip_errors(tmp_path, parallel_gz, segment):
     import struct
-    parallel_gz(30000)
+    parallel_gz(segment)
     reads = synth.adversarial_short(35, 12000)
     good = _gz_member(synth.fastq_bytes(reads))
     cases = {

@@ -169,6 +169,9 @@ public:
     Status run(const uint8_t* in, size_t in_len, bool in_final, size_t* in_used, uint8_t* out, size_t out_cap, size_t* out_used);
     // after kStreamEnd: the whole bytes that were pulled into the bit buffer but belong to whatever follows the stream
     size_t leftover(uint8_t out[8]);
+    // continue a stream somebody else decoded so far: the next block header starts `bit` bits (0..7) into *first_byte, the
+    // last hist_len (<= 32768) bytes produced were hist.  The caller feeds run() with the input behind first_byte.
+    void resume(uint8_t first_byte, unsigned bit, const uint8_t* hist, size_t hist_len);
 
 private:
     enum State { kHeader, kStored, kHuffman, kDone };
@@ -222,6 +225,11 @@ public:
     bool decode(Pool* pool, size_t* total, bool* member_end, size_t* next_byte, const char** err);
     void emit(Pool* pool, uint8_t* dst, size_t off, size_t len);
     size_t segment_bytes() const { return seg_bytes_; }
+    // where the stream stands after the last decode(): next bit, and the last <= 32 KiB produced (to hand the rest of the
+    // stream to the sequential decoder)
+    uint64_t position() const { return pos_; }
+    const std::vector<uint8_t>& window() const { return window_; }
+    size_t last_chain() const { return chain_.size(); }
     // how the work went (tests, traces): calls of next(), segments with a block start found, segments on the chains
     uint64_t stat_calls = 0, stat_found = 0, stat_chained = 0;
 

@@ -56,6 +56,15 @@ void Inflater::reset() {
     bitbuf_ = 0; bitcnt_ = 0; state_ = kHeader; final_ = false; stored_left_ = 0; hist_len_ = 0;
 }
 
+void Inflater::resume(uint8_t first_byte, unsigned bit, const uint8_t* hist, size_t hist_len) {
+    reset();
+    bitbuf_ = (uint64_t)first_byte >> bit;
+    bitcnt_ = 8 - (int)bit;
+    if (hist_len > kWindow) { hist += hist_len - kWindow; hist_len = kWindow; }
+    if (hist_len) memcpy(hist_, hist, hist_len);
+    hist_len_ = hist_len;
+}
+
 size_t Inflater::leftover(uint8_t out[8]) {
     size_t n = 0;
     while (bitcnt_ >= 8) { out[n++] = (uint8_t)bitbuf_; bitbuf_ >>= 8; bitcnt_ -= 8; }

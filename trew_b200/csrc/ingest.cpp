@@ -166,6 +166,11 @@ struct Reader {
     size_t pz_pos = 0;            // next member header
     bool pz_in_member = false, pz_trailer_due = false, pz_done = false;
     size_t pz_total = 0, pz_emitted = 0, pz_next_byte = 0;   // the part decode() holds, what was handed out of it, the byte behind the stream
+    // A stream whose blocks are not found (stored / fixed blocks only, blocks larger than a segment) leaves one thread
+    // decoding 16-bit symbols: slower than the byte decoder.  Two such rounds in a row hand the rest of the member to it.
+    int pz_poor_rounds = 0;
+    bool pz_seq = false;          // the rest of this member goes through `inf`
+    size_t pz_seq_pos = 0;        // its next input byte
 
     static bool bgzf_header(const unsigned char* p, size_t avail, uint32_t* bsize, uint32_t* hdr_len) {
         if (avail < 18 || p[0] != 31 || p[1] != 139 || p[2] != 8 || !(p[3] & 4)) return false;
@@ -409,6 +414,14 @@ struct Reader {
     long read_pgz(char* buf, size_t n, Pool* pool) {
         size_t done = 0;
         while (done < n) {
+            if (pending_pos < pending.size()) {   // bytes the sequential decoder produced aside (below) go out first
+                const size_t m = std::min(n - done, pending.size() - pending_pos);
+                memcpy(buf + done, pending.data() + pending_pos, m);
+                crc_todo.push_back(CrcPiece{buf + done, m, false, 0});
+                pending_pos += m; done += m;
+                if (pending_pos == pending.size()) { pending.clear(); pending_pos = 0; }
+                continue;
+            }
             if (pz_emitted < pz_total) {   // straight into the caller's block; what does not fit waits in the decoder as symbols
                 const size_t m = std::min(n - done, pz_total - pz_emitted);
                 pz.emit(pool, (uint8_t*)buf + done, pz_emitted, m);
@@ -425,6 +438,34 @@ struct Reader {
                 continue;
             }
             if (pz_done) break;
+            if (pz_seq) {
+                size_t iu = 0, ou = 0;
+                Inflater::Status st;
+                if (n - done < 1024) {
+                    // too little room left for the decoder to be sure of progress (a match is up to 258 bytes): decode aside
+                    pending.resize((size_t)64 << 10); pending_pos = 0;
+                    st = inf->run(cmap + pz_seq_pos, (size_t)size - pz_seq_pos, true, &iu, (uint8_t*)pending.data(), pending.size(), &ou);
+                    pending.resize(ou);
+                } else {
+                    st = inf->run(cmap + pz_seq_pos, (size_t)size - pz_seq_pos, true, &iu, (uint8_t*)buf + done, n - done, &ou);
+                    if (ou) crc_todo.push_back(CrcPiece{buf + done, ou, false, 0});
+                    done += ou;
+                }
+                pz_seq_pos += iu;
+                z_len += ou;
+                if (st == Inflater::kError || st == Inflater::kNeedInput) {
+                    zerr = pz_seq_pos >= (size_t)size ? "unexpected end of file" : "invalid compressed data";
+                    return -1;
+                }
+                if (st == Inflater::kStreamEnd) {
+                    uint8_t back[8];
+                    pz_next_byte = pz_seq_pos - inf->leftover(back);
+                    pz_trailer_due = true; pz_seq = false;
+                    continue;
+                }
+                if (pending.empty()) break;   // kOutputFull: the caller's block is as full as it gets
+                continue;
+            }
             if (!pz_in_member) {
                 const unsigned char* p = cmap + pz_pos;
                 const size_t avail = (size_t)size - pz_pos;
@@ -437,13 +478,24 @@ struct Reader {
                 if (hl < 0) { zerr = "unknown compression method or header flags"; return -1; }
                 if (hl == 0) { zerr = "unexpected end of file"; return -1; }
                 pz.start(cmap, (size_t)size, pz_pos + (size_t)hl);
-                pz_in_member = true; z_any_member = true; z_len = 0;
+                pz_in_member = true; z_any_member = true; z_len = 0; pz_poor_rounds = 0;
             }
             const char* e = nullptr;
             bool mend = false;
             size_t nb = 0, total = 0;
             if (!pz.decode(pool, &total, &mend, &nb, &e)) { zerr = e ? e : "invalid compressed data"; return -1; }
             pz_total = total; pz_emitted = 0; pz_trailer_due = mend; pz_next_byte = nb;
+            if (!mend && pool && (pz.last_chain() == 1 || pz.last_chain() * 8 <= (size_t)pool->size())) {
+                if (++pz_poor_rounds >= 2) {
+                    const uint64_t bit = pz.position();
+                    if ((bit >> 3) >= (uint64_t)size) { zerr = "unexpected end of file"; return -1; }
+                    const std::vector<uint8_t>& w = pz.window();
+                    if (!inf) inf.reset(new Inflater());
+                    inf->resume(cmap[bit >> 3], (unsigned)(bit & 7), w.data(), w.size());
+                    pz_seq = true; pz_seq_pos = (size_t)(bit >> 3) + 1;
+                    if (getenv("TREW_PGZ_TRACE")) fprintf(stderr, "[pgz] block starts are not found: the rest of the member goes to the sequential decoder (byte %zu)\n", pz_seq_pos);
+                }
+            } else pz_poor_rounds = 0;
         }
         return (long)done;
     }
