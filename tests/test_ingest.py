@@ -376,3 +376,18 @@ def test_parallel_gzip_errors(tmp_path, parallel_gz, segment):
         rc, msg, r1, _ = api.ingest_records(api.MODE_SHORT, p)
         assert rc != 0, name
         assert "File-IO Error" in msg, (name, msg)
+
+
+@pytest.mark.parametrize("chunk", [5000, 0])
+def test_parallel_gzip_many_small_members(tmp_path, parallel_gz, chunk):
+    """A file of many small members (a member is less than a segment): after two of them the members are decoded
+    sequentially from their start, and a large member later brings the parallel decoder back -- same records throughout."""
+    parallel_gz(40000)
+    reads = synth.adversarial_short(41, 1500) + [bytes(r) for r in synth.config_short(42, 14000, telomeric=0.02, n_rate=0.002)]
+    data = synth.fastq_bytes(reads)
+    cuts = list(range(0, 60000, 3000)) + [60000, len(data) - 9000, len(data) - 6000, len(data) - 3000, len(data)]   # 20 small, one large, 3 small
+    blob = b"".join(_gz_member(data[a:b]) for a, b in zip(cuts, cuts[1:]))
+    p = write(tmp_path, "many.fastq.gz", blob)
+    rc, msg, r1, _ = api.ingest_records(api.MODE_SHORT, p, chunk_bytes=chunk)
+    assert rc == 0, msg
+    assert r1 == reads

@@ -171,6 +171,12 @@ struct Reader {
     int pz_poor_rounds = 0;
     bool pz_seq = false;          // the rest of this member goes through `inf`
     size_t pz_seq_pos = 0;        // its next input byte
+    // Files made of many small members (a member smaller than a segment is one round for one thread, and the others search
+    // in vain): after two such members in a row the members are decoded sequentially from their start, until one turns out
+    // to be large again.
+    int pz_small_members = 0;
+    bool pz_members_seq = false;
+    size_t pz_member_start = 0;
 
     static bool bgzf_header(const unsigned char* p, size_t avail, uint32_t* bsize, uint32_t* hdr_len) {
         if (avail < 18 || p[0] != 31 || p[1] != 139 || p[2] != 8 || !(p[3] & 4)) return false;
@@ -433,6 +439,12 @@ struct Reader {
                 if (pz_next_byte + 8 > (size_t)size) { zerr = "unexpected end of file"; return -1; }
                 if (le32(cmap + pz_next_byte + 4) != (uint32_t)z_len) { zerr = "incorrect length check"; return -1; }
                 crc_todo.push_back(CrcPiece{buf + done, 0, true, le32(cmap + pz_next_byte)});
+                {
+                    const size_t member_bytes = pz_next_byte - pz_member_start, seg = pz.segment_bytes();
+                    if (member_bytes < seg) pz_small_members++; else pz_small_members = 0;
+                    if (pz_small_members >= 2) pz_members_seq = true;
+                    else if (member_bytes >= 16 * seg) pz_members_seq = false;
+                }
                 pz_pos = pz_next_byte + 8;
                 pz_in_member = false; pz_trailer_due = false;
                 continue;
@@ -477,8 +489,15 @@ struct Reader {
                 const long hl = gz_header_len(p, avail);
                 if (hl < 0) { zerr = "unknown compression method or header flags"; return -1; }
                 if (hl == 0) { zerr = "unexpected end of file"; return -1; }
-                pz.start(cmap, (size_t)size, pz_pos + (size_t)hl);
+                pz_member_start = pz_pos;
                 pz_in_member = true; z_any_member = true; z_len = 0; pz_poor_rounds = 0;
+                if (pz_members_seq) {
+                    if (!inf) inf.reset(new Inflater());
+                    inf->reset();
+                    pz_seq = true; pz_seq_pos = pz_pos + (size_t)hl;
+                    continue;
+                }
+                pz.start(cmap, (size_t)size, pz_pos + (size_t)hl);
             }
             const char* e = nullptr;
             bool mend = false;
