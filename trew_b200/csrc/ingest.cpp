@@ -504,7 +504,7 @@ struct Reader {
             size_t nb = 0, total = 0;
             if (!pz.decode(pool, &total, &mend, &nb, &e)) { zerr = e ? e : "invalid compressed data"; return -1; }
             pz_total = total; pz_emitted = 0; pz_trailer_due = mend; pz_next_byte = nb;
-            if (!mend && pool && (pz.last_chain() == 1 || pz.last_chain() * 8 <= (size_t)pool->size())) {
+            if (!mend && (!pool || pz.last_chain() == 1 || pz.last_chain() * 8 <= (size_t)pool->size())) {
                 if (++pz_poor_rounds >= 2) {
                     const uint64_t bit = pz.position();
                     if ((bit >> 3) >= (uint64_t)size) { zerr = "unexpected end of file"; return -1; }
